@@ -1,0 +1,112 @@
+"""Config plumbing for the path: attribute dicts compatible with the reference's EasyDict usage
+(``cfg.KEY``, ``cfg.get('KEY', default)``), a loader for the reference's yaml files
+(pcdet/config.py:51-85, incl. ``_BASE_CONFIG_``) and built-in copies of the hyper-parameters
+of the named configs (tools/cfgs/*/gd_mae*.yaml) for runs without the reference checkout."""
+import copy
+import os
+
+import numpy as np
+
+
+class AttrDict(dict):
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+    def __deepcopy__(self, memo):
+        return AttrDict({k: copy.deepcopy(v, memo) for k, v in self.items()})
+
+
+def to_attr(d):
+    if isinstance(d, dict):
+        return AttrDict({k: to_attr(v) for k, v in d.items()})
+    if isinstance(d, list):
+        return [to_attr(v) for v in d]
+    return d
+
+
+def cfg_from_yaml_file(path, root=None):
+    """pcdet/config.py:71-85 (merge ``_BASE_CONFIG_`` recursively, relative to ``root`` = tools/)."""
+    import yaml
+    root = root or os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(path))))
+
+    def merge(new, cfg):
+        if "_BASE_CONFIG_" in new:
+            with open(os.path.join(root, new["_BASE_CONFIG_"])) as f:
+                cfg.update(to_attr(yaml.safe_load(f)))
+        for k, v in new.items():
+            if isinstance(v, dict):
+                cfg.setdefault(k, AttrDict())
+                merge(v, cfg[k])
+            else:
+                cfg[k] = to_attr(v)
+        return cfg
+
+    with open(path) as f:
+        return merge(yaml.safe_load(f), AttrDict())
+
+
+def _drop_info():
+    lv = {"0": {"max_tokens": 16, "drop_range": [0, 16]}, "1": {"max_tokens": 32, "drop_range": [16, 32]},
+          "2": {"max_tokens": 64, "drop_range": [32, 100000]}}
+    return {"train": copy.deepcopy(lv), "test": copy.deepcopy(lv)}
+
+
+def _sst_block(name, d, dff, stride):
+    return {"NAME": name,
+            "PREPROCESS": {"WINDOW_SHAPE": [8, 8, 1], "DROP_INFO": _drop_info(), "SHUFFLE_VOXELS": False,
+                           "POS_TEMPERATURE": 1000, "NORMALIZE_POS": False},
+            "ENCODER": {"NUM_BLOCKS": 2, "STRIDE": stride, "D_MODEL": d, "NHEAD": 8, "DIM_FEEDFORWARD": dff, "DROPOUT": 0.0,
+                        "ACTIVATION": "gelu", "LAYER_CFG": {"cosine": True, "tau_min": 0.01}}}
+
+
+def builtin_cfg(name="waymo_ssl"):
+    """Model + data hyper-parameters of the named configs, restated (not copied) from
+    tools/cfgs/waymo_models/gd_mae_ssl.yaml, tools/cfgs/once_models/gd_mae_ssl.yaml and
+    tools/cfgs/kitti_models/gd_mae.yaml. ``tiny`` is a 40x48-pillar grid for tests."""
+    data = {"waymo_ssl": ([-74.88, -74.88, -2.0, 74.88, 74.88, 4.0], [0.32, 0.32, 6.0], 5),
+            "once_ssl": ([-74.88, -74.88, -5.0, 74.88, 74.88, 3.0], [0.32, 0.32, 8.0], 4),
+            "kitti": ([0.0, -39.68, -3.0, 69.12, 39.68, 1.0], [0.32, 0.32, 4.0], 4),
+            "tiny": ([-6.4, -7.68, -2.0, 6.4, 7.68, 4.0], [0.32, 0.32, 6.0], 5)}[name]
+    pc_range = np.array(data[0], dtype=np.float32)
+    voxel = data[1]
+    grid = np.round((pc_range[3:6] - pc_range[0:3]) / np.array(voxel)).astype(np.int64)
+    model = {"NAME": "GDMAE",
+             "VFE": {"NAME": "DynVFE", "TYPE": "mean", "WITH_DISTANCE": False, "USE_ABSLOTE_XYZ": True,
+                     "USE_CLUSTER_XYZ": True, "MLPS": [[64, 128]]},
+             "BACKBONE_3D": {"NAME": "SPTBackboneMAE",
+                             "SST_BLOCK_LIST": [_sst_block("sst_block_x1", 128, 256, 1), _sst_block("sst_block_x2", 256, 512, 2),
+                                                _sst_block("sst_block_x4", 256, 512, 2)],
+                             "MASK_CONFIG": {"RATIO": 0.85, "NUM_PRD_POINTS": 16, "NUM_GT_POINTS": 64},
+                             "FEATURES_SOURCE": ["x_conv1", "x_conv2", "x_conv3"],
+                             "FUSE_LAYER": {"x_conv1": {"UPSAMPLE_STRIDE": 1, "NUM_FILTER": 128, "NUM_UPSAMPLE_FILTER": 128},
+                                            "x_conv2": {"UPSAMPLE_STRIDE": 2, "NUM_FILTER": 256, "NUM_UPSAMPLE_FILTER": 128},
+                                            "x_conv3": {"UPSAMPLE_STRIDE": 4, "NUM_FILTER": 256, "NUM_UPSAMPLE_FILTER": 128}}}}
+    optim = {"BATCH_SIZE_PER_GPU": 8, "NUM_EPOCHS": 30, "OPTIMIZER": "adam_onecycle", "LR": 0.003, "WEIGHT_DECAY": 0.01,
+             "MOMENTUM": 0.9, "MOMS": [0.95, 0.85], "PCT_START": 0.4, "DIV_FACTOR": 10, "GRAD_NORM_CLIP": 10}
+    return to_attr({"MODEL": model, "OPTIMIZATION": optim, "POINT_CLOUD_RANGE": pc_range, "VOXEL_SIZE": voxel,
+                    "GRID_SIZE": grid, "NUM_POINT_FEATURES": data[2]})
+
+
+class SyntheticDataset:
+    """The attributes Detector3DTemplate.build_networks reads from the dataset object
+    (detector3d_template.py:45-58, dataset.py:27-41)."""
+
+    def __init__(self, cfg, class_names=('Vehicle', 'Pedestrian', 'Cyclist')):
+        self.class_names = list(class_names)
+        self.point_feature_encoder = AttrDict(num_point_features=int(cfg.NUM_POINT_FEATURES))
+        self.grid_size = np.asarray(cfg.GRID_SIZE)
+        self.point_cloud_range = np.asarray(cfg.POINT_CLOUD_RANGE, dtype=np.float32)
+        self.voxel_size = list(cfg.VOXEL_SIZE)
+
+
+def build_mae_model(cfg):
+    """GDMAE built the way tools/train.py does (build_network(model_cfg, num_class, dataset))."""
+    from .pcdet.models import build_network
+    ds = SyntheticDataset(cfg)
+    return build_network(cfg.MODEL, len(ds.class_names), ds)

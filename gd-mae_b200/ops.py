@@ -1,0 +1,405 @@
+"""Python-side operators over the C ABI (include/gdmae_b200.h): thin launch wrappers and the
+``torch.autograd.Function``s that wire the hand-written forward/backward kernels into autograd.
+
+Nothing here computes on the CPU and nothing falls back to PyTorch ops for the kernels' work.
+"""
+import ctypes
+
+import torch
+
+from . import _lib as L
+
+I32, I64, F32 = torch.int32, torch.int64, torch.float32
+
+
+def _dev(t):
+    if not t.is_cuda:
+        raise L.GdmaeError("gd-mae_b200 operators need CUDA tensors (no CPU path exists)")
+    return t.device
+
+
+# ----------------------------------------------------------------------------- a1/a2 voxelisation
+class PillarSet:
+    """Result of dynamic voxelisation (all device tensors, exact sizes)."""
+    __slots__ = ("points", "point_coords", "inverse", "voxel_coords", "cell2pillar", "seg_offsets", "seg_points",
+                 "batch_offsets", "batch_offsets_dev", "n_points", "n_pillars", "grid", "batch_size")
+
+
+def dynamic_voxelize(points, pc_range, voxel_size, grid_xyz, batch_size):
+    """common_utils.get_in_range_mask + unique(dim=0) of DynVFE.forward (dyn_vfe.py:60-68).
+    ONE host sync (reads the 4+B+1 int32 counts) to size the outputs exactly."""
+    dev = _dev(points)
+    points = points.contiguous().float()
+    n_in, n_cols = points.shape
+    X, Y, Z = [int(g) for g in grid_xyz]
+    n_cells = batch_size * X * Y * Z
+    cap_m = max(min(n_in, n_cells), 1)
+    out_points = torch.empty((max(n_in, 1), n_cols), dtype=F32, device=dev)
+    out_coords = torch.empty((max(n_in, 1), 4), dtype=I64, device=dev)
+    out_inverse = torch.empty((max(n_in, 1),), dtype=I64, device=dev)
+    out_vcoords = torch.empty((cap_m, 4), dtype=I64, device=dev)
+    cell2pillar = torch.empty((n_cells,), dtype=I32, device=dev)
+    seg_off = torch.empty((cap_m + 1,), dtype=I32, device=dev)
+    seg_pts = torch.empty((max(n_in, 1),), dtype=I32, device=dev)
+    counts = torch.empty((4 + batch_size + 1,), dtype=I32, device=dev)
+    lib = L.lib()
+    nbytes = lib.gdmae_dynvox_workspace_bytes(L.i64(n_in), L.i64(n_cells))
+    ws = L.workspace(nbytes, dev)
+    L.check(lib.gdmae_dynvox(L.P(points), L.i64(n_in), n_cols, L.farr(pc_range), L.farr(voxel_size), L.iarr([X, Y, Z]),
+                             batch_size, L.P(out_points), L.P(out_coords), L.P(out_inverse), L.P(out_vcoords),
+                             L.P(cell2pillar), L.P(seg_off), L.P(seg_pts), L.P(counts), L.P(ws),
+                             ctypes.c_size_t(ws.numel()), L.stream()), "gdmae_dynvox")
+    host = counts.cpu().tolist()  # the single sync of DynVFE.forward
+    if host[2] != 0:
+        raise L.GdmaeError("dynamic_voxelize: a point carries a frame index outside [0, batch_size)")
+    ps = PillarSet()
+    ps.n_points, ps.n_pillars = host[0], host[1]
+    ps.batch_offsets = host[4:4 + batch_size + 1]
+    ps.batch_offsets_dev = counts[4:4 + batch_size + 1]
+    ps.points = out_points[:ps.n_points]
+    ps.point_coords = out_coords[:ps.n_points]
+    ps.inverse = out_inverse[:ps.n_points]
+    ps.voxel_coords = out_vcoords[:ps.n_pillars]
+    ps.cell2pillar = cell2pillar
+    ps.seg_offsets = seg_off[:ps.n_pillars + 1]
+    ps.seg_points = seg_pts[:ps.n_points]
+    ps.grid, ps.batch_size = (X, Y, Z), batch_size
+    return ps
+
+
+def segment_mean(src, col0, C, seg_offsets, seg_points, M):
+    """torch_scatter.scatter(src[:, col0:col0+C], inverse, reduce='mean') (dyn_vfe.py:81)."""
+    out = torch.empty((M, C), dtype=F32, device=_dev(src))
+    L.check(L.lib().gdmae_segment_mean(L.P(src), src.shape[1], col0, C, L.P(seg_offsets), L.P(seg_points), L.i64(M),
+                                       L.P(out), L.stream()), "gdmae_segment_mean")
+    return out
+
+
+def vfe_point_features(ps, mean, pc_range, voxel_size):
+    """dyn_vfe.py:86-105."""
+    n_cols = ps.points.shape[1]
+    out = torch.empty((ps.n_points, n_cols - 1 + 6), dtype=F32, device=ps.points.device)
+    L.check(L.lib().gdmae_vfe_point_features(L.P(ps.points), L.P(ps.point_coords), L.P(ps.inverse), L.P(mean),
+                                             mean.shape[1], L.i64(ps.n_points), n_cols, L.farr(pc_range),
+                                             L.farr(voxel_size), L.P(out), L.stream()), "gdmae_vfe_point_features")
+    return out
+
+
+class SegmentMax(torch.autograd.Function):
+    """torch_scatter.scatter_max(x, inverse, dim=0)[0] over the pillar CSR (dyn_vfe.py:109-111)."""
+
+    @staticmethod
+    def forward(ctx, x, seg_offsets, seg_points, M):
+        x = x.contiguous()
+        out = torch.empty((M, x.shape[1]), dtype=F32, device=_dev(x))
+        arg = torch.empty((M, x.shape[1]), dtype=I32, device=x.device)
+        L.check(L.lib().gdmae_segment_max_fwd(L.P(x), x.shape[1], L.P(seg_offsets), L.P(seg_points), L.i64(M), L.P(out),
+                                              L.P(arg), L.stream()), "gdmae_segment_max_fwd")
+        ctx.save_for_backward(arg, seg_offsets, seg_points)
+        ctx.shape = x.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        arg, seg_offsets, seg_points = ctx.saved_tensors
+        dout = dout.contiguous()
+        dx = torch.empty(ctx.shape, dtype=F32, device=dout.device)
+        L.check(L.lib().gdmae_segment_max_bwd(L.P(dout), L.P(arg), ctx.shape[1], L.P(seg_offsets), L.P(seg_points),
+                                              L.i64(arg.shape[0]), L.P(dx), L.stream()), "gdmae_segment_max_bwd")
+        return dx, None, None, None
+
+
+# ----------------------------------------------------------------------------- a7 mask
+def random_mask(noise, batch_offsets_dev, batch_size, mask_ratio):
+    """common_utils.random_masking per frame (common_utils.py:49-63). 0 = visible, 1 = masked."""
+    dev = _dev(noise)
+    M = noise.shape[0]
+    out = torch.empty((M,), dtype=F32, device=dev)
+    lib = L.lib()
+    ws = L.workspace(lib.gdmae_random_mask_workspace_bytes(L.i64(M)), dev)
+    L.check(lib.gdmae_random_mask(L.P(noise.contiguous().float()), L.i64(M), L.P(batch_offsets_dev), batch_size,
+                                  ctypes.c_double(1 - mask_ratio), L.P(out), L.P(ws), ctypes.c_size_t(ws.numel()),
+                                  L.stream()), "gdmae_random_mask")
+    return out
+
+
+# ----------------------------------------------------------------------------- sst_ops
+def ingroup_inds(group_inds, out_inds=None):
+    dev = _dev(group_inds)
+    N = group_inds.shape[0]
+    if out_inds is None:
+        out_inds = torch.empty((N,), dtype=I64, device=dev)
+    lib = L.lib()
+    ws = L.workspace(lib.gdmae_ingroup_inds_workspace_bytes(L.i64(N)), dev)
+    L.check(lib.gdmae_ingroup_inds(L.P(group_inds), L.i64(N), L.P(out_inds), L.P(ws), ctypes.c_size_t(ws.numel()),
+                                   L.stream()), "gdmae_ingroup_inds")
+    return out_inds
+
+
+def group_inner_inds(inverse_inds, M, K, out=None):
+    dev = _dev(inverse_inds)
+    if out is None:
+        out = torch.empty((M, K), dtype=I64, device=dev)
+    lib = L.lib()
+    Np = inverse_inds.shape[0]
+    ws = L.workspace(lib.gdmae_group_inner_inds_workspace_bytes(L.i64(Np), L.i64(M)), dev)
+    L.check(lib.gdmae_group_inner_inds(L.P(inverse_inds), L.i64(Np), L.i64(M), K, L.P(out), L.P(ws),
+                                       ctypes.c_size_t(ws.numel()), L.stream()), "gdmae_group_inner_inds")
+    return out
+
+
+def group_inner_inds_csr(seg_offsets, seg_points, M, K):
+    out = torch.empty((M, K), dtype=I64, device=_dev(seg_offsets))
+    L.check(L.lib().gdmae_group_inner_inds_csr(L.P(seg_offsets), L.P(seg_points), L.i64(M), K, L.P(out), L.stream()),
+            "gdmae_group_inner_inds_csr")
+    return out
+
+
+# ----------------------------------------------------------------------------- sparse structure
+def visible_sites(voxel_coords, mask, n_visible, B, Y, X):
+    """-> vis_idx (N1) int32 pillar rows, indices (N1,3) int32, rank_grid (B*Y*X) int32, count (1) int32 (device)."""
+    dev = _dev(voxel_coords)
+    M = voxel_coords.shape[0]
+    vis_idx = torch.empty((max(n_visible, 1),), dtype=I32, device=dev)
+    indices = torch.empty((max(n_visible, 1), 3), dtype=I32, device=dev)
+    grid = torch.empty((B * Y * X,), dtype=I32, device=dev)
+    count = torch.empty((1,), dtype=I32, device=dev)
+    lib = L.lib()
+    ws = L.workspace(lib.gdmae_visible_sites_workspace_bytes(L.i64(M)), dev)
+    L.check(lib.gdmae_visible_sites(L.P(voxel_coords), L.P(mask), L.i64(M), B, Y, X, L.P(vis_idx), L.P(indices), L.P(grid),
+                                    L.P(count), L.P(ws), ctypes.c_size_t(ws.numel()), L.stream()), "gdmae_visible_sites")
+    return vis_idx[:n_visible], indices[:n_visible], grid, count
+
+
+def build_rank_grid(indices, B, H, W):
+    grid = torch.empty((B * H * W,), dtype=I32, device=_dev(indices))
+    L.check(L.lib().gdmae_build_rank_grid(L.P(indices), L.i64(indices.shape[0]), B, H, W, L.P(grid), L.stream()),
+            "gdmae_build_rank_grid")
+    return grid
+
+
+def down_sites(in_indices, n_in_rows, B, H, W):
+    """SparseConv2d(3, s2, p1) output sites.  ``in_indices`` may be a capacity buffer: rows whose frame
+    index is -1 are skipped, and the returned capacity buffer is pre-filled with -1 for the same reason
+    (lets two pyramid levels be planned before the single host sync that reads their counts).
+    -> (indices (cap,3), rank_grid, count (1) device, Ho, Wo)."""
+    dev = _dev(in_indices)
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    cap = max(min(4 * n_in_rows, B * Ho * Wo), 1)
+    out_idx = torch.full((cap, 3), -1, dtype=I32, device=dev)
+    grid = torch.empty((B * Ho * Wo,), dtype=I32, device=dev)
+    count = torch.empty((1,), dtype=I32, device=dev)
+    lib = L.lib()
+    ws = L.workspace(lib.gdmae_down_sites_workspace_bytes(L.i64(B * Ho * Wo)), dev)
+    L.check(lib.gdmae_down_sites(L.P(in_indices), L.i64(n_in_rows), B, H, W, L.P(out_idx), L.P(grid), L.P(count), L.P(ws),
+                                 ctypes.c_size_t(ws.numel()), L.stream()), "gdmae_down_sites")
+    return out_idx, grid, count, Ho, Wo
+
+
+def subm_neighbor_map(indices, rank_grid, B, H, W):
+    N = indices.shape[0]
+    nbr = torch.empty((N, 9), dtype=I32, device=_dev(indices))
+    L.check(L.lib().gdmae_subm_neighbor_map(L.P(indices), L.i64(N), L.P(rank_grid), B, H, W, L.P(nbr), L.stream()),
+            "gdmae_subm_neighbor_map")
+    return nbr
+
+
+def down_neighbor_maps(in_indices, in_grid, H, W, out_indices, out_grid):
+    dev = _dev(in_indices)
+    N, No = in_indices.shape[0], out_indices.shape[0]
+    down = torch.empty((No, 9), dtype=I32, device=dev)
+    up = torch.empty((N, 9), dtype=I32, device=dev)
+    L.check(L.lib().gdmae_down_neighbor_maps(L.P(in_indices), L.i64(N), L.P(in_grid), H, W, L.P(out_indices), L.i64(No),
+                                             L.P(out_grid), L.P(down), L.P(up), L.stream()), "gdmae_down_neighbor_maps")
+    return down, up
+
+
+class WindowTable:
+    """Window bookkeeping of one shift (replaces batch_win_inds / coors_in_win / drop levels /
+    flat2win_inds / key masks / pos dict of SSTInputLayer.forward, spt_backbone.py:106-135)."""
+    __slots__ = ("win_of_token", "pos_of_token", "inner", "level", "win_mask", "win_off", "win_tok", "lvl_rank",
+                 "lvl_counts", "n_windows", "nWx", "nWy", "N")
+
+
+def window_table(indices, B, H, W, shifted):
+    dev = _dev(indices)
+    N = indices.shape[0]
+    nWx, nWy = (W + 7) // 8 + 1, (H + 7) // 8 + 1
+    nW = B * nWx * nWy
+    t = WindowTable()
+    t.N, t.n_windows, t.nWx, t.nWy = N, nW, nWx, nWy
+    t.win_of_token = torch.empty((max(N, 1),), dtype=I32, device=dev)[:N]
+    t.pos_of_token = torch.empty((max(N, 1),), dtype=torch.uint8, device=dev)[:N]
+    t.inner = torch.empty((max(N, 1),), dtype=I32, device=dev)[:N]
+    t.level = torch.empty((max(N, 1),), dtype=I32, device=dev)[:N]
+    t.win_mask = torch.empty((nW,), dtype=I64, device=dev)
+    t.win_off = torch.empty((nW + 1,), dtype=I32, device=dev)
+    t.win_tok = torch.empty((max(N, 1),), dtype=I32, device=dev)[:N]
+    t.lvl_rank = torch.empty((nW,), dtype=I32, device=dev)
+    t.lvl_counts = torch.empty((3,), dtype=I32, device=dev)
+    lib = L.lib()
+    ws = L.workspace(lib.gdmae_window_table_workspace_bytes(L.i64(nW)), dev)
+    L.check(lib.gdmae_window_table(L.P(indices), L.i64(N), B, H, W, int(bool(shifted)), L.P(t.win_of_token),
+                                   L.P(t.pos_of_token), L.P(t.inner), L.P(t.level), L.P(t.win_mask), L.P(t.win_off),
+                                   L.P(t.win_tok), L.P(t.lvl_rank), L.P(t.lvl_counts), L.P(ws), ctypes.c_size_t(ws.numel()),
+                                   L.stream()), "gdmae_window_table")
+    return t
+
+
+# ----------------------------------------------------------------------------- sparse conv gather
+class GatherRows(torch.autograd.Function):
+    """col (N, 9*C) for a sparse 3x3 conv; backward is the transposed gather (no atomics)."""
+
+    @staticmethod
+    def forward(ctx, x, fwd_map, bwd_map, mirror):
+        x = x.contiguous()
+        N, K = fwd_map.shape
+        C = x.shape[1]
+        col = torch.empty((N, K * C), dtype=F32, device=_dev(x))
+        L.check(L.lib().gdmae_gather_rows(L.P(x), L.P(fwd_map), L.i64(N), K, C, L.P(col), L.stream()), "gdmae_gather_rows")
+        ctx.save_for_backward(bwd_map)
+        ctx.mirror, ctx.n_src, ctx.C, ctx.K = mirror, x.shape[0], C, K
+        return col
+
+    @staticmethod
+    def backward(ctx, dcol):
+        (bwd_map,) = ctx.saved_tensors
+        dcol = dcol.contiguous()
+        dx = torch.empty((ctx.n_src, ctx.C), dtype=F32, device=dcol.device)
+        L.check(L.lib().gdmae_gather_rows_transposed(L.P(dcol), L.P(bwd_map), L.i64(ctx.n_src), ctx.K, ctx.C,
+                                                     int(ctx.mirror), L.P(dx), L.stream()), "gdmae_gather_rows_transposed")
+        return dx, None, None, None
+
+
+# ----------------------------------------------------------------------------- SRA attention core
+class SraAttention(torch.autograd.Function):
+    """Cosine window attention on flat tokens (cosine_msa.py:114-176 + sst_basic_block.py:22-54)."""
+
+    @staticmethod
+    def forward(ctx, qkv, lut, tau, table, tau_min, nhead):
+        qkv, lut = qkv.contiguous(), lut.contiguous()
+        N, d3 = qkv.shape
+        d = d3 // 3
+        out = torch.empty((N, d), dtype=F32, device=_dev(qkv))
+        lse = torch.empty((N, nhead), dtype=F32, device=qkv.device)
+        tau_c = tau.detach().reshape(-1).contiguous()
+        L.check(L.lib().gdmae_sra_attention_fwd(L.P(qkv), L.P(lut), L.P(table.win_tok), L.P(table.win_of_token),
+                                                L.P(table.pos_of_token), L.P(table.win_off), L.i64(N), d, nhead,
+                                                L.P(tau_c), L.f32(tau_min), L.P(out), L.P(lse), L.stream()),
+                "gdmae_sra_attention_fwd")
+        ctx.save_for_backward(qkv, lut, tau_c, out, lse)
+        ctx.table, ctx.tau_min, ctx.nhead, ctx.tau_shape = table, tau_min, nhead, tau.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, lut, tau_c, out, lse = ctx.saved_tensors
+        t = ctx.table
+        N, d3 = qkv.shape
+        d = d3 // 3
+        dout = dout.contiguous()
+        dqkv = torch.empty_like(qkv)
+        dtau_sum = torch.zeros((1,), dtype=torch.float64, device=qkv.device)
+        work = torch.empty((N, ctx.nhead), dtype=F32, device=qkv.device)
+        L.check(L.lib().gdmae_sra_attention_bwd(L.P(qkv), L.P(lut), L.P(t.win_tok), L.P(t.win_of_token), L.P(t.pos_of_token),
+                                                L.P(t.win_off), L.i64(N), d, ctx.nhead, L.P(tau_c), L.f32(ctx.tau_min),
+                                                L.P(out), L.P(lse), L.P(dout), L.P(dqkv), L.P(dtau_sum), L.P(work),
+                                                L.stream()), "gdmae_sra_attention_bwd")
+        # the LUT rows receive the q/k gradients of the tokens sitting on that in-window cell
+        dlut = torch.zeros_like(lut)
+        dlut.index_add_(0, t.pos_of_token.long(), dqkv[:, :2 * d])
+        tau_eff = torch.clamp(tau_c, min=ctx.tau_min)
+        dtau = torch.where(tau_c >= ctx.tau_min, -(dtau_sum.float() / tau_eff), torch.zeros_like(tau_c))
+        return dqkv, dlut, dtau.reshape(ctx.tau_shape), None, None, None
+
+
+# ----------------------------------------------------------------------------- decoder
+class DenseFill(torch.autograd.Function):
+    """(B, Y, X, 3*Cs) NHWC map: scale-s rows at covered cells, bg_s elsewhere (see sparse_feat.cu)."""
+
+    @staticmethod
+    def forward(ctx, r0, r1, r2, bg0, bg1, bg2, grids, indices, strides, B, Y, X):
+        rows = [r.contiguous() for r in (r0, r1, r2)]
+        bgs = [b.contiguous() for b in (bg0, bg1, bg2)]
+        Cs = bgs[0].shape[0]
+        out = torch.empty((B, Y, X, 3 * Cs), dtype=F32, device=_dev(rows[0]))
+        L.check(L.lib().gdmae_dense_fill(L.parr(rows), L.parr(bgs), L.parr(grids), L.iarr(strides), B, Y, X, Cs, L.P(out),
+                                         L.stream()), "gdmae_dense_fill")
+        ctx.grids, ctx.indices, ctx.strides, ctx.dims = grids, indices, strides, (B, Y, X, Cs)
+        ctx.row_shapes = [r.shape for r in rows]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, Y, X, Cs = ctx.dims
+        dout = dout.contiguous()
+        drows = [torch.empty(s, dtype=F32, device=dout.device) for s in ctx.row_shapes]
+        dbg = torch.empty((3 * Cs,), dtype=F32, device=dout.device)
+        n_sites = (ctypes.c_int64 * 3)(*[int(i.shape[0]) for i in ctx.indices])
+        L.check(L.lib().gdmae_dense_fill_bwd(L.P(dout), L.parr(ctx.grids), L.parr(ctx.indices), n_sites, L.iarr(ctx.strides),
+                                             B, Y, X, Cs, L.parr(drows), L.P(dbg), L.stream()), "gdmae_dense_fill_bwd")
+        return (drows[0], drows[1], drows[2], dbg[:Cs], dbg[Cs:2 * Cs], dbg[2 * Cs:], None, None, None, None, None, None)
+
+
+class GatherNHWC(torch.autograd.Function):
+    """spatial_features.permute(0,2,3,1)[b, y, x] at all pillars (spt_backbone_mae.py:141-143)."""
+
+    @staticmethod
+    def forward(ctx, src_nhwc, voxel_coords):
+        src_nhwc = src_nhwc.contiguous()
+        B, Y, X, C = src_nhwc.shape
+        M = voxel_coords.shape[0]
+        out = torch.empty((M, C), dtype=F32, device=_dev(src_nhwc))
+        L.check(L.lib().gdmae_gather_nhwc(L.P(src_nhwc), L.P(voxel_coords), L.i64(M), Y, X, C, L.P(out), L.stream()),
+                "gdmae_gather_nhwc")
+        ctx.save_for_backward(voxel_coords)
+        ctx.shape = (B, Y, X, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (voxel_coords,) = ctx.saved_tensors
+        B, Y, X, C = ctx.shape
+        dsrc = torch.zeros(ctx.shape, dtype=F32, device=dout.device)
+        L.check(L.lib().gdmae_scatter_nhwc(L.P(dout.contiguous()), L.P(voxel_coords), L.i64(voxel_coords.shape[0]), Y, X, C,
+                                           L.P(dsrc), L.stream()), "gdmae_scatter_nhwc")
+        return dsrc, None
+
+
+# ----------------------------------------------------------------------------- chamfer head
+def group_points_centered(ps, pc_range, voxel_size, K):
+    """gt_points - voxel_centers of target_assigner (spt_backbone_mae.py:67-72), (M, K, 3)."""
+    out = torch.empty((ps.n_pillars, K, 3), dtype=F32, device=ps.points.device)
+    L.check(L.lib().gdmae_group_points_centered(L.P(ps.points), ps.points.shape[1], L.P(ps.seg_offsets), L.P(ps.seg_points),
+                                                L.P(ps.voxel_coords), L.farr(pc_range[:3]), L.farr(voxel_size), L.i64(ps.n_pillars),
+                                                K, L.P(out), L.stream()), "gdmae_group_points_centered")
+    return out
+
+
+class ChamferLoss(torch.autograd.Function):
+    """pytorch3d.loss.chamfer_distance(pred, gt, weights=w)[0] with its defaults."""
+
+    @staticmethod
+    def forward(ctx, pred, gt, weights):
+        pred, gt, weights = pred.contiguous(), gt.contiguous(), weights.contiguous()
+        N, P1, _ = pred.shape
+        per_item = torch.empty((N,), dtype=F32, device=_dev(pred))
+        dpred = torch.empty_like(pred)
+        L.check(L.lib().gdmae_chamfer_fwd(L.P(pred), L.P(gt), L.P(weights), L.i64(N), P1, gt.shape[1], L.P(per_item), L.P(dpred),
+                                          L.stream()), "gdmae_chamfer_fwd")
+        wsum = weights.sum()
+        ctx.save_for_backward(dpred, wsum)
+        # weights.sum() == 0 -> 0 (pytorch3d returns zeros in that case); per_item is all zero then
+        return per_item.sum() / torch.clamp(wsum, min=1e-30)
+
+    @staticmethod
+    def backward(ctx, g):
+        dpred, wsum = ctx.saved_tensors
+        return dpred * (g / torch.clamp(wsum, min=1e-30)), None, None
+
+
+def chamfer_distance(x, y, weights=None):
+    """Drop-in for pytorch3d.loss.chamfer_distance on the path's call shape: returns (loss, None)."""
+    if weights is None:
+        weights = torch.ones((x.shape[0],), dtype=F32, device=x.device)
+    return ChamferLoss.apply(x, y, weights), None

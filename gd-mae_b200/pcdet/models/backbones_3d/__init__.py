@@ -1,0 +1,4 @@
+"""NAME registry as in pcdet/models/backbones_3d/__init__.py:8-16 (hot-path entries only)."""
+from .spt_backbone_mae import SPTBackboneMAE
+
+__all__ = {'SPTBackboneMAE': SPTBackboneMAE}

@@ -1,0 +1,59 @@
+"""Mirror of pcdet/models/backbones_3d/vfe/dyn_vfe.py:10-124 (DynVFE) over the B200 kernels.
+
+Same constructor signature, parameter names (``dvfe_mlps.0.{0,1,3,4}``) and batch_dict keys.
+Supported configuration = the one every GD-MAE config uses: TYPE mean, WITH_DISTANCE False,
+USE_ABSLOTE_XYZ / USE_CLUSTER_XYZ True, one MLP group, no aggregation MLP."""
+from functools import partial
+
+import torch.nn as nn
+
+from ..... import ops as _ops
+from ...model_utils.network_utils import make_fc_layers
+
+
+class VFETemplate(nn.Module):
+    def __init__(self, model_cfg, **kwargs):
+        super().__init__()
+        self.model_cfg = model_cfg
+
+    def get_output_feature_dim(self):
+        raise NotImplementedError
+
+
+class DynVFE(VFETemplate):
+    def __init__(self, model_cfg, num_point_features, voxel_size, point_cloud_range, grid_size, **kwargs):
+        super().__init__(model_cfg=model_cfg)
+        self.sample_type = model_cfg.get('TYPE', 'mean')
+        mlps = model_cfg.get('MLPS', None)
+        if (self.sample_type != 'mean' or mlps is None or len(mlps) != 1 or model_cfg.get('AGGREGATION_MLPS', None)
+                or model_cfg.WITH_DISTANCE or not model_cfg.USE_ABSLOTE_XYZ or not model_cfg.USE_CLUSTER_XYZ):
+            raise NotImplementedError("gd-mae_b200 DynVFE implements the GD-MAE configuration (TYPE mean, one MLP group, "
+                                      "absolute + cluster xyz, no distance)")
+        input_channels = num_point_features + 6
+        norm_fn = partial(nn.BatchNorm1d, eps=1e-3, momentum=0.01)
+        self.dvfe_mlps = nn.ModuleList([make_fc_layers(mlps[0], input_channels, norm_fn=norm_fn)])
+        self.num_point_features = mlps[0][-1]
+        self.voxel_size = [float(v) for v in voxel_size]
+        self.point_cloud_range = [float(v) for v in point_cloud_range]
+        self.grid_size = [int(g) for g in grid_size]
+
+    def get_output_feature_dim(self):
+        return self.num_point_features
+
+    def forward(self, batch_dict, **kwargs):
+        points = batch_dict['points']
+        ps = _ops.dynamic_voxelize(points, self.point_cloud_range, self.voxel_size, self.grid_size, batch_dict['batch_size'])
+        n_feat = points.shape[1] - 1
+        mean = _ops.segment_mean(ps.points, 1, n_feat, ps.seg_offsets, ps.seg_points, ps.n_pillars)
+        x = _ops.vfe_point_features(ps, mean, self.point_cloud_range, self.voxel_size)
+        x = self.dvfe_mlps[0](x)  # Linear -> BN1d(train: batch statistics) -> ReLU, twice (cuBLAS / ATen)
+        x = _ops.SegmentMax.apply(x, ps.seg_offsets, ps.seg_points, ps.n_pillars)
+
+        batch_dict['points'] = ps.points
+        batch_dict['point_coords'] = ps.point_coords
+        batch_dict['point_inverse_indices'] = ps.inverse
+        batch_dict['voxel_coords'] = ps.voxel_coords
+        batch_dict['pillar_features'] = x
+        batch_dict['voxel_features'] = x
+        batch_dict['pillar_set'] = ps  # extra key: CSR / batch offsets reused by SPTBackboneMAE
+        return batch_dict

@@ -1,0 +1,8 @@
+"""NAME registry as in pcdet/models/detectors/__init__.py:10-29 (hot-path entries only)."""
+from .gd_mae import GDMAE, Detector3DTemplate
+
+__all__ = {'Detector3DTemplate': Detector3DTemplate, 'GDMAE': GDMAE}
+
+
+def build_detector(model_cfg, num_class, dataset, logger=None):
+    return __all__[model_cfg.NAME](model_cfg=model_cfg, num_class=num_class, dataset=dataset, logger=logger)

@@ -1,0 +1,83 @@
+"""Mirror of pcdet/models/detectors/gd_mae.py:4-37 (GDMAE) and of the part of
+Detector3DTemplate that the MAE path needs (pcdet/models/detectors/detector3d_template.py:15-100):
+the ``global_step`` buffer, NAME-keyed construction of ``vfe`` and ``backbone_3d`` and the
+``forward(batch_dict) -> (ret_dict, tb_dict, disp_dict)`` training contract of
+model_func (pcdet/models/__init__.py:29-39)."""
+import torch
+import torch.nn as nn
+
+from ..backbones_3d import vfe as _vfe_registry
+from .. import backbones_3d as _backbone_registry
+
+
+class Detector3DTemplate(nn.Module):
+    def __init__(self, model_cfg, num_class, dataset, logger=None):
+        super().__init__()
+        self.model_cfg, self.num_class, self.dataset, self.logger = model_cfg, num_class, dataset, logger
+        self.class_names = getattr(dataset, 'class_names', None)
+        self.register_buffer('global_step', torch.LongTensor(1).zero_())
+        self.module_topology = ['vfe', 'backbone_3d']
+
+    @property
+    def mode(self):
+        return 'TRAIN' if self.training else 'TEST'
+
+    def update_global_step(self):
+        self.global_step += 1
+
+    def build_networks(self):
+        info = {'module_list': [],
+                'num_rawpoint_features': self.dataset.point_feature_encoder.num_point_features,
+                'num_point_features': self.dataset.point_feature_encoder.num_point_features,
+                'grid_size': self.dataset.grid_size, 'point_cloud_range': self.dataset.point_cloud_range,
+                'voxel_size': self.dataset.voxel_size}
+        for name in self.module_topology:
+            module, info = getattr(self, 'build_%s' % name)(model_info_dict=info)
+            self.add_module(name, module)
+        return info['module_list']
+
+    def build_vfe(self, model_info_dict):
+        if self.model_cfg.get('VFE', None) is None:
+            return None, model_info_dict
+        m = _vfe_registry.__all__[self.model_cfg.VFE.NAME](
+            model_cfg=self.model_cfg.VFE, num_point_features=model_info_dict['num_rawpoint_features'],
+            point_cloud_range=model_info_dict['point_cloud_range'], voxel_size=model_info_dict['voxel_size'],
+            grid_size=model_info_dict['grid_size'])
+        model_info_dict['num_point_features'] = m.get_output_feature_dim()
+        model_info_dict['module_list'].append(m)
+        return m, model_info_dict
+
+    def build_backbone_3d(self, model_info_dict):
+        if self.model_cfg.get('BACKBONE_3D', None) is None:
+            return None, model_info_dict
+        m = _backbone_registry.__all__[self.model_cfg.BACKBONE_3D.NAME](
+            model_cfg=self.model_cfg.BACKBONE_3D, input_channels=model_info_dict['num_point_features'],
+            grid_size=model_info_dict['grid_size'], voxel_size=model_info_dict['voxel_size'],
+            point_cloud_range=model_info_dict['point_cloud_range'])
+        model_info_dict['module_list'].append(m)
+        model_info_dict['num_point_features'] = m.num_point_features
+        return m, model_info_dict
+
+
+class GDMAE(Detector3DTemplate):
+    def __init__(self, model_cfg, num_class, dataset, logger=None):
+        super().__init__(model_cfg=model_cfg, num_class=num_class, dataset=dataset, logger=logger)
+        self.module_list = self.build_networks()
+
+    def forward(self, batch_dict):
+        for cur_module in self.module_list:
+            batch_dict = cur_module(batch_dict)
+        if self.training:
+            loss, tb_dict, disp_dict = self.get_training_loss()
+            return {'loss': loss}, tb_dict, disp_dict
+        return self.post_processing(batch_dict)
+
+    def post_processing(self, batch_dict):
+        return {}, {}
+
+    def get_training_loss(self, sync_for_logging=False):
+        """gd_mae.py:27-37.  The reference puts ``loss_rpn.item()`` (a host sync) into tb_dict every
+        step; here the tensor itself is stored unless ``sync_for_logging`` is set."""
+        loss_rpn, tb_dict = self.backbone_3d.get_loss()
+        tb_dict = {'loss_rpn': loss_rpn.item() if sync_for_logging else loss_rpn.detach(), **tb_dict}
+        return loss_rpn, tb_dict, {}

@@ -1,0 +1,180 @@
+/* gdmae_b200 - C ABI of the B200 (sm_100a) kernels behind GD-MAE's MAE pre-train hot path.
+ *
+ * Plain pointers and sizes only: no torch / ATen types.  Every pointer named below is a DEVICE
+ * pointer unless marked "host".  Every function takes the cudaStream_t to launch on as `stream`
+ * (void*), allocates nothing, never synchronises and returns 0 on success or a negative code
+ * (GDMAE_ERR_*); gdmae_last_error() gives the message.  Scratch memory comes from the caller:
+ * query gdmae_<op>_workspace_bytes(), pass `workspace` / `ws_bytes`.
+ *
+ * Each entry cites the reference interface it replaces (file:line relative to the reference
+ * checkout, Nightmare-n/GD-MAE @ abd05ce).  INTEGRATION.md shows the reference-side bindings.
+ */
+#ifndef GDMAE_B200_H
+#define GDMAE_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GDMAE_OK 0
+#define GDMAE_ERR_ARG (-1)
+#define GDMAE_ERR_WORKSPACE (-2)
+#define GDMAE_ERR_CUDA (-3)
+
+const char* gdmae_last_error(void);
+int gdmae_version(void);
+int gdmae_check_device(void); /* 0 iff the current device is sm_100 class; there is no fallback path */
+
+/* ---- a1/a2 dynamic voxelisation --------------------------------------------------------------
+ * replaces common_utils.get_in_range_mask (pcdet/utils/common_utils.py:66-76) and the boolean
+ * compaction + coords.unique(dim=0, return_inverse=True) of DynVFE.forward
+ * (pcdet/models/backbones_3d/vfe/dyn_vfe.py:60-68).
+ * points (n_in, n_cols) fp32 rows [frame, x, y, z, feat...]; pc_range[6], voxel[3], grid_xyz[3]: host.
+ * Outputs (capacities): out_points (n_in, n_cols) kept points in input order; out_point_coords
+ * (n_in, 4) int64 [b,z,y,x]; out_inverse (n_in) int64; out_voxel_coords (min(n_in, n_cells), 4)
+ * int64, lexicographically sorted unique rows; out_cell2pillar (n_cells) int32, -1 = empty;
+ * out_seg_offsets (cap_m + 1) / out_seg_points (n_in): CSR of the kept-point rows of each pillar,
+ * ascending point index inside a pillar; out_counts int32[4 + batch_size + 1]:
+ * [0] = kept points, [1] = pillars M, [2] = error flags (1: frame index out of range),
+ * [4 + b] = first pillar of frame b, [4 + batch_size] = M.   n_cells = B*Z*Y*X. */
+size_t gdmae_dynvox_workspace_bytes(int64_t n_in, int64_t n_cells);
+int gdmae_dynvox(const float* points, int64_t n_in, int n_cols, const float* pc_range, const float* voxel,
+                 const int* grid_xyz, int batch_size, float* out_points, int64_t* out_point_coords,
+                 int64_t* out_inverse, int64_t* out_voxel_coords, int32_t* out_cell2pillar,
+                 int32_t* out_seg_offsets, int32_t* out_seg_points, int32_t* out_counts, void* workspace,
+                 size_t ws_bytes, void* stream);
+
+/* ---- a3 pillar mean --------------------------------------------------------------------------
+ * replaces torch_scatter.scatter(points[:, 1:], inverse, dim=0, reduce='mean') (dyn_vfe.py:81).
+ * src rows have src_stride floats; columns [col0, col0+C) are averaged. out (M, C). */
+int gdmae_segment_mean(const float* src, int src_stride, int col0, int C, const int32_t* seg_offsets,
+                       const int32_t* seg_points, int64_t M, float* out, void* stream);
+
+/* ---- a4 point feature build ------------------------------------------------------------------
+ * replaces dyn_vfe.py:86-105: out (Np, n_feat+6) = [xyz - pillar centre, points[:,1:], xyz - mean_xyz]. */
+int gdmae_vfe_point_features(const float* points, const int64_t* point_coords, const int64_t* inverse,
+                             const float* mean, int mean_stride, int64_t Np, int n_cols, const float* pc_range,
+                             const float* voxel, float* out, void* stream);
+
+/* ---- a6 pillar max ---------------------------------------------------------------------------
+ * replaces torch_scatter.scatter_max(x, inverse, dim=0) (dyn_vfe.py:109-111) and its backward.
+ * src (Np, C), out (M, C), out_argmax (M, C) int32 point row (may be NULL in fwd). C % 4 == 0. */
+int gdmae_segment_max_fwd(const float* src, int C, const int32_t* seg_offsets, const int32_t* seg_points, int64_t M,
+                          float* out, int32_t* out_argmax, void* stream);
+int gdmae_segment_max_bwd(const float* dout, const int32_t* argmax, int C, const int32_t* seg_offsets,
+                          const int32_t* seg_points, int64_t M, float* dsrc, void* stream);
+
+/* ---- a7 MAE random mask ----------------------------------------------------------------------
+ * replaces common_utils.random_masking per frame (pcdet/utils/common_utils.py:49-63,
+ * spt_backbone_mae.py:96-100). noise (M) uniform [0,1); batch_offsets (B+1) int32 (= counts + 4);
+ * keep_ratio = 1 - mask_ratio as a double. out_mask (M) float: 0 visible, 1 masked. */
+size_t gdmae_random_mask_workspace_bytes(int64_t M);
+int gdmae_random_mask(const float* noise, int64_t M, const int32_t* batch_offsets, int batch_size,
+                      double keep_ratio, float* out_mask, void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- a11 / a24 sst_ops -----------------------------------------------------------------------
+ * gdmae_ingroup_inds replaces sst_ops_cuda.ingroup_inds_wrapper (pcdet/ops/sst_ops/src/sst_ops.cpp:21-33,
+ * sst_ops_gpu.cu:14-20); gdmae_group_inner_inds replaces sst_ops_cuda.group_inner_inds_wrapper
+ * (sst_ops.cpp:35-48, sst_ops_gpu.cu:22-39). Deterministic: order inside a group = ascending index.
+ * The _csr variant reuses the pillar CSR of gdmae_dynvox. */
+size_t gdmae_ingroup_inds_workspace_bytes(int64_t N);
+int gdmae_ingroup_inds(const int64_t* group_inds, int64_t N, int64_t* out_inds, void* workspace, size_t ws_bytes,
+                       void* stream);
+size_t gdmae_group_inner_inds_workspace_bytes(int64_t Np, int64_t M);
+int gdmae_group_inner_inds(const int64_t* inverse_inds, int64_t Np, int64_t M, int K, int64_t* out_group_inds,
+                           void* workspace, size_t ws_bytes, void* stream);
+int gdmae_group_inner_inds_csr(const int32_t* seg_offsets, const int32_t* seg_points, int64_t M, int K,
+                               int64_t* out_group_inds, void* stream);
+
+/* ---- a8/a9/a21 sparse tensor structure -------------------------------------------------------
+ * replaces the SparseConvTensor built from the visible pillars (spt_backbone_mae.py:102-107) and the
+ * indice-pair generation of spconv's SparseConv2d(3, stride 2, pad 1) / SubMConv2d(3)
+ * (pcdet/utils/spconv_utils.py:37-56; spconv 2.x is not vendored in the reference).
+ * indices are (N,3) int32 [b,y,x], lexicographic; rank grids are (B*H*W) int32, -1 = empty. */
+size_t gdmae_visible_sites_workspace_bytes(int64_t M);
+int gdmae_visible_sites(const int64_t* voxel_coords, const float* mask, int64_t M, int B, int Y, int X,
+                        int32_t* out_vis_idx, int32_t* out_indices, int32_t* out_rank_grid, int32_t* out_count,
+                        void* workspace, size_t ws_bytes, void* stream);
+int gdmae_build_rank_grid(const int32_t* indices, int64_t N, int B, int H, int W, int32_t* out_rank_grid, void* stream);
+/* in_indices rows with b < 0 are skipped (capacity buffers pre-filled with -1) */
+size_t gdmae_down_sites_workspace_bytes(int64_t n_out_cells);
+int gdmae_down_sites(const int32_t* in_indices, int64_t N, int B, int H, int W, int32_t* out_indices,
+                     int32_t* out_rank_grid, int32_t* out_count, void* workspace, size_t ws_bytes, void* stream);
+int gdmae_subm_neighbor_map(const int32_t* indices, int64_t N, const int32_t* rank_grid, int B, int H, int W,
+                            int32_t* out_nbr, void* stream);
+int gdmae_down_neighbor_maps(const int32_t* in_indices, int64_t N, const int32_t* in_rank_grid, int H, int W,
+                             const int32_t* out_indices, int64_t No, const int32_t* out_rank_grid,
+                             int32_t* out_nbr_down, int32_t* out_nbr_up, void* stream);
+/* out (N, K*C) = rows of src (.., C) gathered through map (N, K); 0 where map < 0 */
+int gdmae_gather_rows(const float* src, const int32_t* map, int64_t N, int K, int C, float* out, void* stream);
+/* dsrc (N, C) = sum_k dcol[tmap[i, mirror ? K-1-k : k], k*C:(k+1)*C] */
+int gdmae_gather_rows_transposed(const float* dcol, const int32_t* tmap, int64_t N, int K, int C, int mirror,
+                                 float* dsrc, void* stream);
+
+/* ---- a10-a16 window tables -------------------------------------------------------------------
+ * replaces sst_utils.get_window_coors (pcdet/models/model_utils/sst_utils.py:6-47),
+ * get_inner_win_inds + drop_single_shift (pcdet/models/backbones_3d/spt_backbone.py:32-51),
+ * make_continuous_inds / get_flat2win_inds (sst_utils.py:50-96) and the key-padding mask
+ * (spt_backbone.py:184-194) for 8x8x1 windows. nW = B*(ceil(W/8)+1)*(ceil(H/8)+1); the
+ * reference's batch_win_inds == 2 * win_of_token. */
+size_t gdmae_window_table_workspace_bytes(int64_t n_windows);
+int gdmae_window_table(const int32_t* indices, int64_t N, int B, int H, int W, int shifted, int32_t* win_of_token,
+                       uint8_t* pos_of_token, int32_t* inner, int32_t* level, uint64_t* win_mask, int32_t* win_off,
+                       int32_t* win_tok, int32_t* lvl_rank, int32_t* lvl_counts, void* workspace, size_t ws_bytes,
+                       void* stream);
+
+/* ---- a16-a18 SRA attention core --------------------------------------------------------------
+ * replaces flat2window/window2flat (sst_utils.py:107-181), the per-level loop of
+ * WindowAttention.forward (pcdet/models/model_utils/sst_basic_block.py:22-54) and
+ * _scaled_cosine_attention (pcdet/models/model_utils/cosine_msa.py:114-176) incl. the -inf key mask.
+ * qkv (N, 3d) = [x Wq^T | x Wk^T | x Wv^T + bv]; lut (64, 2d) = pos_table [Wq;Wk]^T + [bq;bk];
+ * out (N, d) pre out-proj; lse (N, 8).  nhead == 8, d in {128, 256}. */
+int gdmae_sra_attention_fwd(const float* qkv, const float* lut, const int32_t* win_tok, const int32_t* win_of_token,
+                            const uint8_t* pos_of_token, const int32_t* win_off, int64_t N, int d, int nhead,
+                            const float* tau, float tau_min, float* out, float* lse, void* stream);
+int gdmae_sra_attention_bwd(const float* qkv, const float* lut, const int32_t* win_tok, const int32_t* win_of_token,
+                            const uint8_t* pos_of_token, const int32_t* win_off, int64_t N, int d, int nhead,
+                            const float* tau, float tau_min, const float* out, const float* lse, const float* dout,
+                            float* dqkv, double* dtau_sum, float* work_D, void* stream);
+
+/* ---- a22/a23 decoder dense fill and pillar gather --------------------------------------------
+ * replaces SparseConvTensor.dense() + ConvTranspose2d(k=s) + BatchNorm2d + ReLU + torch.cat
+ * (spt_backbone_mae.py:125-132) once the per-site GEMM/BN is done on the sparse rows, and the
+ * gather at all pillars (spt_backbone_mae.py:141-143).  rows/bg/rank_grids/indices/drows are HOST
+ * arrays of 3 device pointers; out (B, Y, X, 3*Cs) NHWC. */
+int gdmae_dense_fill(const float* const* rows, const float* const* bg, const int32_t* const* rank_grids,
+                     const int* strides, int B, int Y, int X, int Cs, float* out, void* stream);
+int gdmae_dense_fill_bwd(const float* dout, const int32_t* const* rank_grids, const int32_t* const* indices,
+                         const int64_t* n_sites, const int* strides, int B, int Y, int X, int Cs,
+                         float* const* drows, float* dbg, void* stream);
+int gdmae_gather_nhwc(const float* src, const int64_t* voxel_coords, int64_t M, int Y, int X, int C, float* out,
+                      void* stream);
+int gdmae_scatter_nhwc(const float* dout, const int64_t* voxel_coords, int64_t M, int Y, int X, int C, float* dsrc,
+                       void* stream);
+
+/* ---- a24-a26 chamfer head --------------------------------------------------------------------
+ * gdmae_group_points_centered replaces sst_ops_utils.group_inner_inds + points[group_inds]
+ * (pcdet/ops/sst_ops/sst_ops_utils.py:15-27) fused with get_voxel_centers
+ * (pcdet/utils/common_utils.py:130-145) and the subtraction at spt_backbone_mae.py:67-72.
+ * gdmae_chamfer_fwd replaces pytorch3d.loss.chamfer_distance(pred, gt, weights=mask)
+ * (spt_backbone_mae.py:88): per_item (N) and dpred (N, P1, 3); loss = sum(per_item)/sum(w). */
+int gdmae_group_points_centered(const float* points, int n_cols, const int32_t* seg_offsets, const int32_t* seg_points,
+                                const int64_t* voxel_coords, const float* pc_range, const float* voxel, int64_t M, int K,
+                                float* out_gt, void* stream);
+int gdmae_chamfer_fwd(const float* pred, const float* gt, const float* weights, int64_t N, int P1, int P2,
+                      float* per_item, float* dpred, void* stream);
+
+/* ---- optimizer ---------------------------------------------------------------------------------
+ * replaces clip_grad_norm_ (tools/train_utils/train_utils.py:52) and OptimWrapper.step + Adam
+ * (tools/train_utils/optimization/fastai_optim.py:135-152) on one flat fp32 bucket. */
+int gdmae_grad_sumsq(const float* grads, int64_t n, double* out, void* stream);
+int gdmae_adam_onecycle_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n_opt,
+                             const double* sumsq, float clip, float decay, float mom, float beta2, float eps,
+                             float step_size, float bc2_sqrt, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
