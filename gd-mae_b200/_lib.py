@@ -41,6 +41,8 @@ def lib():
             fn = getattr(L, name)
             if name.endswith("_workspace_bytes"):
                 fn.restype = ctypes.c_size_t
+            elif name == "gdmae_launch_count":
+                fn.restype = ctypes.c_int64
             elif name != "gdmae_last_error":
                 fn.restype = ctypes.c_int
         _lib = L
@@ -82,6 +84,30 @@ def iarr(vals):
 
 def parr(tensors):
     return (ctypes.c_void_p * len(tensors))(*[0 if t is None else t.data_ptr() for t in tensors])
+
+
+# optional per-kernel timing (bench.py): name -> list of (start_event, end_event, algorithmic_bytes)
+KERNEL_TIMERS = None
+
+
+class timed:
+    """with timed("sra_fwd", nbytes): <C-ABI call>  - CUDA events on the launching stream."""
+
+    def __init__(self, name, nbytes):
+        self.name, self.nbytes = name, nbytes
+
+    def __enter__(self):
+        if KERNEL_TIMERS is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if KERNEL_TIMERS is not None:
+            self.e1.record()
+            KERNEL_TIMERS.setdefault(self.name, []).append((self.e0, self.e1, self.nbytes))
+        return False
 
 
 _workspaces = {}

@@ -9,6 +9,11 @@ extern "C" void gdmae_set_error(const char* msg) {
   g_err[sizeof(g_err) - 1] = 0;
 }
 extern "C" const char* gdmae_last_error(void) { return g_err; }
+
+static unsigned long long g_launches = 0;
+extern "C" void gdmae_count_launch(void) { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+// number of hand-written kernels launched by this process so far (CUB primitives not counted)
+extern "C" int64_t gdmae_launch_count(void) { return (int64_t)__atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 extern "C" int gdmae_version(void) { return 100; }
 
 // 0 when a device of compute capability 10.x is current, negative otherwise (the library carries

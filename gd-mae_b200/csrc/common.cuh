@@ -32,7 +32,13 @@ extern "C" void gdmae_set_error(const char* msg);
     }                                                                                           \
   } while (0)
 
-#define GDMAE_LAUNCH_CHECK() GDMAE_CHECK_CUDA(cudaGetLastError())
+extern "C" void gdmae_count_launch(void);
+// every hand-written kernel launch is followed by this macro: it also feeds gdmae_launch_count()
+#define GDMAE_LAUNCH_CHECK()                 \
+  do {                                       \
+    gdmae_count_launch();                    \
+    GDMAE_CHECK_CUDA(cudaGetLastError());    \
+  } while (0)
 
 static inline int gdmae_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline size_t gdmae_align(size_t x) { return (x + 255) & ~(size_t)255; }

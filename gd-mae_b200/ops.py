@@ -6,8 +6,13 @@ Nothing here computes on the CPU and nothing falls back to PyTorch ops for the k
 import ctypes
 
 import torch
+from torch.amp import custom_bwd, custom_fwd
 
 from . import _lib as L
+
+# the kernels compute in fp32: under torch.autocast (bf16 GEMM/conv mode) inputs are cast back up
+_fwd = custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+_bwd = custom_bwd(device_type="cuda")
 
 I32, I64, F32 = torch.int32, torch.int64, torch.float32
 
@@ -89,17 +94,21 @@ class SegmentMax(torch.autograd.Function):
     """torch_scatter.scatter_max(x, inverse, dim=0)[0] over the pillar CSR (dyn_vfe.py:109-111)."""
 
     @staticmethod
+    @_fwd
     def forward(ctx, x, seg_offsets, seg_points, M):
         x = x.contiguous()
         out = torch.empty((M, x.shape[1]), dtype=F32, device=_dev(x))
         arg = torch.empty((M, x.shape[1]), dtype=I32, device=x.device)
-        L.check(L.lib().gdmae_segment_max_fwd(L.P(x), x.shape[1], L.P(seg_offsets), L.P(seg_points), L.i64(M), L.P(out),
-                                              L.P(arg), L.stream()), "gdmae_segment_max_fwd")
+        # algorithmic bytes (SURVEY.md 8d, op boundary a6): Np*C*4 + Np*4 + M*C*4
+        with L.timed("segment_max_fwd", x.shape[0] * x.shape[1] * 4 + x.shape[0] * 4 + M * x.shape[1] * 4):
+            L.check(L.lib().gdmae_segment_max_fwd(L.P(x), x.shape[1], L.P(seg_offsets), L.P(seg_points), L.i64(M), L.P(out),
+                                                  L.P(arg), L.stream()), "gdmae_segment_max_fwd")
         ctx.save_for_backward(arg, seg_offsets, seg_points)
         ctx.shape = x.shape
         return out
 
     @staticmethod
+    @_bwd
     def backward(ctx, dout):
         arg, seg_offsets, seg_points = ctx.saved_tensors
         dout = dout.contiguous()
@@ -251,6 +260,7 @@ class GatherRows(torch.autograd.Function):
     """col (N, 9*C) for a sparse 3x3 conv; backward is the transposed gather (no atomics)."""
 
     @staticmethod
+    @_fwd
     def forward(ctx, x, fwd_map, bwd_map, mirror):
         x = x.contiguous()
         N, K = fwd_map.shape
@@ -262,6 +272,7 @@ class GatherRows(torch.autograd.Function):
         return col
 
     @staticmethod
+    @_bwd
     def backward(ctx, dcol):
         (bwd_map,) = ctx.saved_tensors
         dcol = dcol.contiguous()
@@ -276,6 +287,7 @@ class SraAttention(torch.autograd.Function):
     """Cosine window attention on flat tokens (cosine_msa.py:114-176 + sst_basic_block.py:22-54)."""
 
     @staticmethod
+    @_fwd
     def forward(ctx, qkv, lut, tau, table, tau_min, nhead):
         qkv, lut = qkv.contiguous(), lut.contiguous()
         N, d3 = qkv.shape
@@ -283,15 +295,18 @@ class SraAttention(torch.autograd.Function):
         out = torch.empty((N, d), dtype=F32, device=_dev(qkv))
         lse = torch.empty((N, nhead), dtype=F32, device=qkv.device)
         tau_c = tau.detach().reshape(-1).contiguous()
-        L.check(L.lib().gdmae_sra_attention_fwd(L.P(qkv), L.P(lut), L.P(table.win_tok), L.P(table.win_of_token),
-                                                L.P(table.pos_of_token), L.P(table.win_off), L.i64(N), d, nhead,
-                                                L.P(tau_c), L.f32(tau_min), L.P(out), L.P(lse), L.stream()),
-                "gdmae_sra_attention_fwd")
+        # algorithmic bytes (SURVEY.md 8d, a18 minus projections): N*d*(3*s_in + s_out) + N*8
+        with L.timed(f"sra_fwd_d{d}", N * d * 16 + N * 8):
+            L.check(L.lib().gdmae_sra_attention_fwd(L.P(qkv), L.P(lut), L.P(table.win_tok), L.P(table.win_of_token),
+                                                    L.P(table.pos_of_token), L.P(table.win_off), L.i64(N), d, nhead,
+                                                    L.P(tau_c), L.f32(tau_min), L.P(out), L.P(lse), L.stream()),
+                    "gdmae_sra_attention_fwd")
         ctx.save_for_backward(qkv, lut, tau_c, out, lse)
         ctx.table, ctx.tau_min, ctx.nhead, ctx.tau_shape = table, tau_min, nhead, tau.shape
         return out
 
     @staticmethod
+    @_bwd
     def backward(ctx, dout):
         qkv, lut, tau_c, out, lse = ctx.saved_tensors
         t = ctx.table
@@ -301,10 +316,12 @@ class SraAttention(torch.autograd.Function):
         dqkv = torch.empty_like(qkv)
         dtau_sum = torch.zeros((1,), dtype=torch.float64, device=qkv.device)
         work = torch.empty((N, ctx.nhead), dtype=F32, device=qkv.device)
-        L.check(L.lib().gdmae_sra_attention_bwd(L.P(qkv), L.P(lut), L.P(t.win_tok), L.P(t.win_of_token), L.P(t.pos_of_token),
-                                                L.P(t.win_off), L.i64(N), d, ctx.nhead, L.P(tau_c), L.f32(ctx.tau_min),
-                                                L.P(out), L.P(lse), L.P(dout), L.P(dqkv), L.P(dtau_sum), L.P(work),
-                                                L.stream()), "gdmae_sra_attention_bwd")
+        # bwd algorithmic bytes: qkv + o + dO in, dqkv out
+        with L.timed(f"sra_bwd_d{d}", N * d * 4 * (3 + 1 + 1 + 3) + N * 8):
+            L.check(L.lib().gdmae_sra_attention_bwd(L.P(qkv), L.P(lut), L.P(t.win_tok), L.P(t.win_of_token), L.P(t.pos_of_token),
+                                                    L.P(t.win_off), L.i64(N), d, ctx.nhead, L.P(tau_c), L.f32(ctx.tau_min),
+                                                    L.P(out), L.P(lse), L.P(dout), L.P(dqkv), L.P(dtau_sum), L.P(work),
+                                                    L.stream()), "gdmae_sra_attention_bwd")
         # the LUT rows receive the q/k gradients of the tokens sitting on that in-window cell
         dlut = torch.zeros_like(lut)
         dlut.index_add_(0, t.pos_of_token.long(), dqkv[:, :2 * d])
@@ -318,6 +335,7 @@ class DenseFill(torch.autograd.Function):
     """(B, Y, X, 3*Cs) NHWC map: scale-s rows at covered cells, bg_s elsewhere (see sparse_feat.cu)."""
 
     @staticmethod
+    @_fwd
     def forward(ctx, r0, r1, r2, bg0, bg1, bg2, grids, indices, strides, B, Y, X):
         rows = [r.contiguous() for r in (r0, r1, r2)]
         bgs = [b.contiguous() for b in (bg0, bg1, bg2)]
@@ -330,6 +348,7 @@ class DenseFill(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_bwd
     def backward(ctx, dout):
         B, Y, X, Cs = ctx.dims
         dout = dout.contiguous()
@@ -345,6 +364,7 @@ class GatherNHWC(torch.autograd.Function):
     """spatial_features.permute(0,2,3,1)[b, y, x] at all pillars (spt_backbone_mae.py:141-143)."""
 
     @staticmethod
+    @_fwd
     def forward(ctx, src_nhwc, voxel_coords):
         src_nhwc = src_nhwc.contiguous()
         B, Y, X, C = src_nhwc.shape
@@ -357,6 +377,7 @@ class GatherNHWC(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_bwd
     def backward(ctx, dout):
         (voxel_coords,) = ctx.saved_tensors
         B, Y, X, C = ctx.shape
@@ -380,6 +401,7 @@ class ChamferLoss(torch.autograd.Function):
     """pytorch3d.loss.chamfer_distance(pred, gt, weights=w)[0] with its defaults."""
 
     @staticmethod
+    @_fwd
     def forward(ctx, pred, gt, weights):
         pred, gt, weights = pred.contiguous(), gt.contiguous(), weights.contiguous()
         N, P1, _ = pred.shape
@@ -393,6 +415,7 @@ class ChamferLoss(torch.autograd.Function):
         return per_item.sum() / torch.clamp(wsum, min=1e-30)
 
     @staticmethod
+    @_bwd
     def backward(ctx, g):
         dpred, wsum = ctx.saved_tensors
         return dpred * (g / torch.clamp(wsum, min=1e-30)), None, None

@@ -5,6 +5,7 @@ Supported configuration = the one every GD-MAE config uses: TYPE mean, WITH_DIST
 USE_ABSLOTE_XYZ / USE_CLUSTER_XYZ True, one MLP group, no aggregation MLP."""
 from functools import partial
 
+import torch
 import torch.nn as nn
 
 from ..... import ops as _ops
@@ -46,7 +47,8 @@ class DynVFE(VFETemplate):
         n_feat = points.shape[1] - 1
         mean = _ops.segment_mean(ps.points, 1, n_feat, ps.seg_offsets, ps.seg_points, ps.n_pillars)
         x = _ops.vfe_point_features(ps, mean, self.point_cloud_range, self.voxel_size)
-        x = self.dvfe_mlps[0](x)  # Linear -> BN1d(train: batch statistics) -> ReLU, twice (cuBLAS / ATen)
+        with torch.autocast("cuda", enabled=False):  # absolute coordinates (|x| up to 75 m) stay fp32
+            x = self.dvfe_mlps[0](x)  # Linear -> BN1d(train: batch statistics) -> ReLU, twice (cuBLAS / ATen)
         x = _ops.SegmentMax.apply(x, ps.seg_offsets, ps.seg_points, ps.n_pillars)
 
         batch_dict['points'] = ps.points

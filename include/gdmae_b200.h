@@ -25,6 +25,7 @@ extern "C" {
 
 const char* gdmae_last_error(void);
 int gdmae_version(void);
+int64_t gdmae_launch_count(void); /* hand-written kernels launched so far by this process */
 int gdmae_check_device(void); /* 0 iff the current device is sm_100 class; there is no fallback path */
 
 /* ---- a1/a2 dynamic voxelisation --------------------------------------------------------------

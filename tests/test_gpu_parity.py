@@ -310,6 +310,7 @@ def test_mask_from_noise_inside_model_and_trainer_steps(G):
     assert optimised_parameter_names(model) == {k for k in P if O.in_optimizer(k)}
     trainer = MAETrainer(model, cfg.OPTIMIZATION, total_steps=20)
     opt = O.AdamOneCycle(P, ocfg, 20)
+    P0 = {k: v.clone() for k, v in P.items()}
     r = np.random.RandomState(0)
     for it in range(3):
         n = 1800
@@ -321,11 +322,36 @@ def test_mask_from_noise_inside_model_and_trainer_steps(G):
         lc = trainer.step(dict(points=pts.cuda(), batch_size=2, voxel_mae_noise=noise.cuda()))
         assert abs(float(lc) - lo) / lo < 2e-3, (it, float(lc), lo)
     sd = model.state_dict()
-    worst = max(rel(sd[k], P[k]) for k in P)
-    assert worst < 5e-3, worst
-    for k in P:  # never-updated attention in-proj / tau (optimizer quirk)
+    # Adam's first steps move every element by ~lr * sign(g): elements whose gradient is at noise
+    # level may flip, so compare the update as a whole (relative L2 over all optimised parameters) ...
+    num = sum(float(((sd[k].cpu().double() - P[k].double()) ** 2).sum()) for k in P)
+    den = sum(float(((P[k].double() - P0[k].double()) ** 2).sum()) for k in P)
+    assert (num / den) ** 0.5 < 5e-2, (num / den) ** 0.5
+    for k in P:  # ... and the never-updated attention in-proj / tau exactly (optimizer quirk)
         if not O.in_optimizer(k):
-            assert rel(sd[k], P[k]) == 0.0
+            assert torch.equal(sd[k].cpu(), P0[k]), k
+
+
+def test_fused_adam_onecycle_kernel_matches_oracle(G):
+    """The clip + decoupled-wd + Adam kernel in isolation: identical synthetic gradients on both sides."""
+    from gd_mae_b200.trainer import MAETrainer
+    model, cfg, ocfg, P, Bf = build(G, "tiny", 0.85, 6)
+    trainer = MAETrainer(model, cfg.OPTIMIZATION, total_steps=50)
+    opt = O.AdamOneCycle(P, ocfg, 50)
+    params = dict(model.named_parameters())
+    g = torch.Generator().manual_seed(0)
+    for it in range(4):
+        scale = [3.0, 0.01, 1.0, 30.0][it]  # exercises both sides of the clip threshold
+        Gd = {k: torch.randn(v.shape, generator=g) * scale * 1e-3 for k, v in P.items()}
+        for k in P:
+            params[k].grad.copy_(Gd[k].cuda())
+        norm_o, lr_o, mom_o = opt.step(P, Gd, it)
+        lr_c, mom_c = trainer.optimizer_step()
+        assert (lr_c, mom_c) == (lr_o, mom_o)
+        assert abs(float(trainer.sumsq.sqrt()) - norm_o) / norm_o < 1e-5
+    sd = model.state_dict()
+    for k in P:
+        assert rel(sd[k], P[k]) < 2e-5, k
 
 
 # ------------------------------------------------------------------------------ full-size properties (Waymo shape)
