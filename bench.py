@@ -175,11 +175,14 @@ def main():
     tf32 = args.dtype != "fp32"
     torch.backends.cudnn.allow_tf32 = tf32
     torch.backends.cuda.matmul.allow_tf32 = tf32
-    autocast = torch.autocast("cuda", dtype=torch.bfloat16, enabled=args.dtype == "bf16")
+    import contextlib
+    autocast = contextlib.nullcontext()  # no autocast: encoder GEMMs run TF32, the decoder map/conv are emitted in bf16
 
     torch.manual_seed(666 + rank)
     cfg = config.builtin_cfg("waymo_ssl")
     model = config.build_mae_model(cfg).to(dev)
+    if args.dtype == "bf16":
+        model.backbone_3d.decoder_dtype = torch.bfloat16
     if world > 1:  # identical initial weights on every rank (DDP broadcasts rank 0's, train.py:146)
         for t in list(model.parameters()) + list(model.buffers()):
             dist.broadcast(t.data, 0)

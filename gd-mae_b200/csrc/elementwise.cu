@@ -1,0 +1,282 @@
+// Fused row-wise kernels of the SRA encoder layer: residual + LayerNorm (fwd/bwd), bias + exact
+// GELU (fwd/bwd) and column sums (bias gradients).  All HBM-bound, 128-bit accesses, one warp per
+// token row, parameter gradients reduced deterministically in two stages (per-CTA partials, then a
+// fixed-order final sum) instead of float atomics.
+//
+// Replaces (reference file:line, relative to /root/reference):
+//   src = norm1(src + src2); src = norm2(src + src2)        pcdet/models/model_utils/sst_basic_block.py:79-83
+//   activation(linear1(src)) with activation = F.gelu (erf)   pcdet/models/model_utils/sst_basic_block.py:81,117-125
+#include "common.cuh"
+
+#define EW_PART_BLOCKS (GDMAE_NUM_SMS * 2)
+
+// ------------------------------------------------------------------ y = LayerNorm(x + res)
+// VEC = d / 128 float4 per lane (d = 128 -> 1, d = 256 -> 2)
+template <int VEC>
+__global__ void __launch_bounds__(256) add_ln_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ res,
+                                                         const float4* __restrict__ gamma, const float4* __restrict__ beta,
+                                                         long long N, float eps, float4* __restrict__ y,
+                                                         float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  constexpr int D = VEC * 128;
+  int lane = threadIdx.x & 31;
+  long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  float4 g[VEC], b[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) { g[v] = __ldg(gamma + v * 32 + lane); b[v] = __ldg(beta + v * 32 + lane); }
+  for (long long row = warp; row < N; row += nwarps) {
+    float4 z[VEC];
+    float s = 0.f;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      float4 a = __ldg(x + row * (D / 4) + v * 32 + lane);
+      float4 r = __ldg(res + row * (D / 4) + v * 32 + lane);
+      z[v] = make_float4(a.x + r.x, a.y + r.y, a.z + r.z, a.w + r.w);
+      s += z[v].x + z[v].y + z[v].z + z[v].w;
+    }
+    float mean = warp_sum(s) * (1.f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      float dx = z[v].x - mean, dy = z[v].y - mean, dz = z[v].z - mean, dw = z[v].w - mean;
+      q += dx * dx + dy * dy + dz * dz + dw * dw;
+    }
+    float rstd = rsqrtf(warp_sum(q) * (1.f / D) + eps);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      float4 o;
+      o.x = (z[v].x - mean) * rstd * g[v].x + b[v].x;
+      o.y = (z[v].y - mean) * rstd * g[v].y + b[v].y;
+      o.z = (z[v].z - mean) * rstd * g[v].z + b[v].z;
+      o.w = (z[v].w - mean) * rstd * g[v].w + b[v].w;
+      y[row * (D / 4) + v * 32 + lane] = o;
+    }
+    if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+  }
+}
+
+// dz = rstd * (dy*gamma - mean(dy*gamma) - xhat * mean(dy*gamma*xhat));  partial dgamma/dbeta per CTA
+template <int VEC>
+__global__ void __launch_bounds__(256) add_ln_bwd_kernel(const float4* __restrict__ x, const float4* __restrict__ res,
+                                                         const float4* __restrict__ gamma, const float* __restrict__ mean_in,
+                                                         const float* __restrict__ rstd_in, const float4* __restrict__ dy,
+                                                         long long N, float4* __restrict__ dz, float* __restrict__ partial) {
+  constexpr int D = VEC * 128;
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  float4 g[VEC], dg[VEC], db[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    g[v] = __ldg(gamma + v * 32 + lane);
+    dg[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    db[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (long long row = warp; row < N; row += nwarps) {
+    float mean = mean_in[row], rstd = rstd_in[row];
+    float4 xh[VEC], dxh[VEC];
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      float4 a = __ldg(x + row * (D / 4) + v * 32 + lane);
+      float4 r = __ldg(res + row * (D / 4) + v * 32 + lane);
+      float4 d = __ldg(dy + row * (D / 4) + v * 32 + lane);
+      xh[v] = make_float4((a.x + r.x - mean) * rstd, (a.y + r.y - mean) * rstd, (a.z + r.z - mean) * rstd, (a.w + r.w - mean) * rstd);
+      dxh[v] = make_float4(d.x * g[v].x, d.y * g[v].y, d.z * g[v].z, d.w * g[v].w);
+      c1 += dxh[v].x + dxh[v].y + dxh[v].z + dxh[v].w;
+      c2 += dxh[v].x * xh[v].x + dxh[v].y * xh[v].y + dxh[v].z * xh[v].z + dxh[v].w * xh[v].w;
+      dg[v].x += d.x * xh[v].x; dg[v].y += d.y * xh[v].y; dg[v].z += d.z * xh[v].z; dg[v].w += d.w * xh[v].w;
+      db[v].x += d.x; db[v].y += d.y; db[v].z += d.z; db[v].w += d.w;
+    }
+    c1 = warp_sum(c1) * (1.f / D);
+    c2 = warp_sum(c2) * (1.f / D);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      float4 o;
+      o.x = rstd * (dxh[v].x - c1 - xh[v].x * c2);
+      o.y = rstd * (dxh[v].y - c1 - xh[v].y * c2);
+      o.z = rstd * (dxh[v].z - c1 - xh[v].z * c2);
+      o.w = rstd * (dxh[v].w - c1 - xh[v].w * c2);
+      dz[row * (D / 4) + v * 32 + lane] = o;
+    }
+  }
+  // CTA reduction over its 8 warps (fixed order), then one partial row [dgamma(D) | dbeta(D)] per CTA
+  __shared__ float4 red[8][2 * VEC][32];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) { red[wid][v][lane] = dg[v]; red[wid][VEC + v][lane] = db[v]; }
+  __syncthreads();
+  if (wid == 0) {
+#pragma unroll
+    for (int v = 0; v < 2 * VEC; ++v) {
+      float4 acc = red[0][v][lane];
+      for (int w = 1; w < 8; ++w) {
+        float4 t = red[w][v][lane];
+        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+      }
+      // v < VEC: dgamma columns [128 v + 4 lane ..]; v >= VEC: dbeta
+      int colbase = (v < VEC ? 0 : D) + (v % VEC) * 128 + 4 * lane;
+      *reinterpret_cast<float4*>(partial + (long long)blockIdx.x * 2 * D + colbase) = acc;
+    }
+  }
+}
+
+// out[c] = sum_b partial[b * stride + c]   (fixed order)
+__global__ void partial_reduce_kernel(const float* __restrict__ partial, int nblocks, int stride, int C, float* __restrict__ out,
+                                      int accumulate) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float acc = 0.f;
+  for (int b = 0; b < nblocks; ++b) acc += partial[(long long)b * stride + c];
+  out[c] = accumulate ? out[c] + acc : acc;
+}
+
+extern "C" size_t gdmae_rowwise_workspace_bytes(int max_cols) { return (size_t)EW_PART_BLOCKS * 2 * max_cols * 4 + 256; }
+
+static int ew_grid(long long rows) {
+  long long need = (rows + 7) / 8;
+  return (int)(need < EW_PART_BLOCKS ? (need < 1 ? 1 : need) : EW_PART_BLOCKS);
+}
+
+// y = LayerNorm(x + res) * gamma + beta over rows of d in {128, 256}; mean/rstd (N) saved for backward.
+extern "C" int gdmae_add_layernorm_fwd(const float* x, const float* res, const float* gamma, const float* beta, int64_t N, int d,
+                                       float eps, float* y, float* mean, float* rstd, void* stream_) {
+  GDMAE_CHECK_ARG(N >= 0 && (d == 128 || d == 256));
+  if (N == 0) return GDMAE_OK;
+  cudaStream_t st = (cudaStream_t)stream_;
+  int grid = gdmae_grid(N * 32, 256, 8);
+  if (d == 128) add_ln_fwd_kernel<1><<<grid, 256, 0, st>>>((const float4*)x, (const float4*)res, (const float4*)gamma, (const float4*)beta, N, eps, (float4*)y, mean, rstd);
+  else add_ln_fwd_kernel<2><<<grid, 256, 0, st>>>((const float4*)x, (const float4*)res, (const float4*)gamma, (const float4*)beta, N, eps, (float4*)y, mean, rstd);
+  GDMAE_LAUNCH_CHECK();
+  return GDMAE_OK;
+}
+
+// dz (N,d) = gradient w.r.t. (x + res); dgamma/dbeta (d) written (accumulate=0) or added to (accumulate=1).
+extern "C" int gdmae_add_layernorm_bwd(const float* x, const float* res, const float* gamma, const float* mean, const float* rstd,
+                                       const float* dy, int64_t N, int d, float* dz, float* dgamma, float* dbeta, int accumulate,
+                                       void* workspace, size_t ws_bytes, void* stream_) {
+  GDMAE_CHECK_ARG(N >= 0 && (d == 128 || d == 256));
+  if (ws_bytes < gdmae_rowwise_workspace_bytes(d)) { gdmae_set_error("add_layernorm_bwd: workspace too small"); return GDMAE_ERR_WORKSPACE; }
+  if (N == 0) return GDMAE_OK;
+  cudaStream_t st = (cudaStream_t)stream_;
+  float* partial = (float*)workspace;
+  int grid = ew_grid(N);
+  if (d == 128) add_ln_bwd_kernel<1><<<grid, 256, 0, st>>>((const float4*)x, (const float4*)res, (const float4*)gamma, mean, rstd, (const float4*)dy, N, (float4*)dz, partial);
+  else add_ln_bwd_kernel<2><<<grid, 256, 0, st>>>((const float4*)x, (const float4*)res, (const float4*)gamma, mean, rstd, (const float4*)dy, N, (float4*)dz, partial);
+  GDMAE_LAUNCH_CHECK();
+  // every CTA left one partial row [dgamma(d) | dbeta(d)]
+  partial_reduce_kernel<<<gdmae_div_up(d, 128), 128, 0, st>>>(partial, grid, 2 * d, d, dgamma, accumulate);
+  GDMAE_LAUNCH_CHECK();
+  partial_reduce_kernel<<<gdmae_div_up(d, 128), 128, 0, st>>>(partial + d, grid, 2 * d, d, dbeta, accumulate);
+  GDMAE_LAUNCH_CHECK();
+  return GDMAE_OK;
+}
+
+// ------------------------------------------------------------------ g = gelu_erf(h + b)
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  return 0.5f * (1.f + erff(x * 0.70710678118654752440f)) + x * 0.39894228040143267794f * __expf(-0.5f * x * x);
+}
+
+__global__ void __launch_bounds__(256) bias_gelu_fwd_kernel(const float4* __restrict__ h, const float4* __restrict__ bias,
+                                                            long long n4, int C4, float4* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 a = __ldg(h + i), b = __ldg(bias + (int)(i % C4));
+    out[i] = make_float4(gelu_f(a.x + b.x), gelu_f(a.y + b.y), gelu_f(a.z + b.z), gelu_f(a.w + b.w));
+  }
+}
+
+// dh = dg * gelu'(h + b); partial column sums of dh (bias gradient).  blockDim.x == C/4 * rows_per_block is not
+// required: thread t owns float4 column (t % C4) of rows (t / C4), stepping whole CTAs.
+__global__ void __launch_bounds__(256) bias_gelu_bwd_kernel(const float4* __restrict__ h, const float4* __restrict__ bias,
+                                                            const float4* __restrict__ dg, long long N, int C4,
+                                                            float4* __restrict__ dh, float* __restrict__ partial) {
+  int c = threadIdx.x % C4, rsub = threadIdx.x / C4, rper = blockDim.x / C4;
+  float4 b = __ldg(bias + c);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long row = (long long)blockIdx.x * rper + rsub; row < N; row += (long long)gridDim.x * rper) {
+    float4 a = __ldg(h + row * C4 + c), g = __ldg(dg + row * C4 + c);
+    float4 o = make_float4(g.x * gelu_grad_f(a.x + b.x), g.y * gelu_grad_f(a.y + b.y), g.z * gelu_grad_f(a.z + b.z),
+                           g.w * gelu_grad_f(a.w + b.w));
+    dh[row * C4 + c] = o;
+    acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+  }
+  __shared__ float4 red[256];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (rsub == 0) {
+    for (int j = 1; j < rper; ++j) {
+      float4 t = red[j * C4 + c];
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    *reinterpret_cast<float4*>(partial + (long long)blockIdx.x * 4 * C4 + 4 * c) = acc;
+  }
+}
+
+extern "C" int gdmae_bias_gelu_fwd(const float* h, const float* bias, int64_t N, int C, float* out, void* stream_) {
+  GDMAE_CHECK_ARG(N >= 0 && C > 0 && (C % 4) == 0);
+  if (N == 0) return GDMAE_OK;
+  bias_gelu_fwd_kernel<<<gdmae_grid(N * (C / 4), 256, 8), 256, 0, (cudaStream_t)stream_>>>((const float4*)h, (const float4*)bias,
+                                                                                         N * (C / 4), C / 4, (float4*)out);
+  GDMAE_LAUNCH_CHECK();
+  return GDMAE_OK;
+}
+
+extern "C" int gdmae_bias_gelu_bwd(const float* h, const float* bias, const float* dg, int64_t N, int C, float* dh, float* dbias,
+                                   int accumulate, void* workspace, size_t ws_bytes, void* stream_) {
+  GDMAE_CHECK_ARG(N >= 0 && C > 0 && (C % 4) == 0 && (C / 4) <= 256 && 256 % (C / 4) == 0);
+  if (ws_bytes < gdmae_rowwise_workspace_bytes(C)) { gdmae_set_error("bias_gelu_bwd: workspace too small"); return GDMAE_ERR_WORKSPACE; }
+  if (N == 0) return GDMAE_OK;
+  cudaStream_t st = (cudaStream_t)stream_;
+  int rper = 256 / (C / 4);
+  long long need = (N + rper - 1) / rper;
+  int grid = (int)(need < EW_PART_BLOCKS ? need : EW_PART_BLOCKS);
+  float* partial = (float*)workspace;
+  bias_gelu_bwd_kernel<<<grid, 256, 0, st>>>((const float4*)h, (const float4*)bias, (const float4*)dg, N, C / 4, (float4*)dh, partial);
+  GDMAE_LAUNCH_CHECK();
+  partial_reduce_kernel<<<gdmae_div_up(C, 128), 128, 0, st>>>(partial, grid, C, C, dbias, accumulate);
+  GDMAE_LAUNCH_CHECK();
+  return GDMAE_OK;
+}
+
+// ------------------------------------------------------------------ column sums (bias gradients of the GEMMs)
+__global__ void __launch_bounds__(256) colsum_kernel(const float4* __restrict__ x, long long N, int ld4, int col4, int C4,
+                                                     float* __restrict__ partial) {
+  int c = threadIdx.x % C4, rsub = threadIdx.x / C4, rper = blockDim.x / C4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long row = (long long)blockIdx.x * rper + rsub; row < N; row += (long long)gridDim.x * rper) {
+    float4 a = __ldg(x + row * ld4 + col4 + c);
+    acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+  }
+  __shared__ float4 red[256];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (rsub == 0) {
+    for (int j = 1; j < rper; ++j) {
+      float4 t = red[j * C4 + c];
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    *reinterpret_cast<float4*>(partial + (long long)blockIdx.x * 4 * C4 + 4 * c) = acc;
+  }
+}
+
+// out (C) = (accumulate ? out : 0) + sum over rows of x (N, ld) columns [col0, col0 + C)
+extern "C" int gdmae_colsum(const float* x, int64_t N, int ld, int col0, int C, float* out, int accumulate, void* workspace,
+                            size_t ws_bytes, void* stream_) {
+  GDMAE_CHECK_ARG(N >= 0 && C > 0 && (C % 4) == 0 && (ld % 4) == 0 && (col0 % 4) == 0 && col0 + C <= ld && (C / 4) <= 256);
+  if (ws_bytes < gdmae_rowwise_workspace_bytes(C)) { gdmae_set_error("colsum: workspace too small"); return GDMAE_ERR_WORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (N == 0) {
+    if (!accumulate) GDMAE_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)C * 4, st));
+    return GDMAE_OK;
+  }
+  int C4 = C / 4;
+  int rper = 256 / C4;
+  long long need = (N + rper - 1) / rper;
+  int grid = (int)(need < EW_PART_BLOCKS ? need : EW_PART_BLOCKS);
+  float* partial = (float*)workspace;
+  colsum_kernel<<<grid, C4 * rper, 0, st>>>((const float4*)x, N, ld / 4, col0 / 4, C4, partial);
+  GDMAE_LAUNCH_CHECK();
+  partial_reduce_kernel<<<gdmae_div_up(C, 128), 128, 0, st>>>(partial, grid, C, C, out, accumulate);
+  GDMAE_LAUNCH_CHECK();
+  return GDMAE_OK;
+}

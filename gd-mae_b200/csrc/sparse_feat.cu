@@ -13,6 +13,31 @@
 // per-site GEMMs on the sparse rows plus ONE write-only pass over the dense NHWC map
 // (gdmae_dense_fill); the reference makes ten dense passes for the same tensor.
 #include "common.cuh"
+#include <cuda_bf16.h>
+
+// 4-channel packets in fp32 (16 B) or bf16 (8 B)
+template <typename T> struct Pack4;
+template <> struct Pack4<float> {
+  typedef float4 type;
+  static __device__ __forceinline__ float4 load(const float* p, long long i4) { return __ldg(reinterpret_cast<const float4*>(p) + i4); }
+  static __device__ __forceinline__ void store(float* p, long long i4, float4 v) { reinterpret_cast<float4*>(p)[i4] = v; }
+};
+template <> struct Pack4<__nv_bfloat16> {
+  typedef uint2 type;
+  static __device__ __forceinline__ float4 load(const __nv_bfloat16* p, long long i4) {
+    uint2 u = __ldg(reinterpret_cast<const uint2*>(p) + i4);
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&u.x), b = *reinterpret_cast<__nv_bfloat162*>(&u.y);
+    float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, long long i4, float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<unsigned int*>(&a);
+    u.y = *reinterpret_cast<unsigned int*>(&b);
+    reinterpret_cast<uint2*>(p)[i4] = u;
+  }
+};
 
 // out[n, k*C + c] = src[map[n,k], c] (0 where map < 0).  One thread per float4.
 __global__ void gather_rows_kernel(const float4* __restrict__ src, const int* __restrict__ map, long long N, int K, int C4,
@@ -79,7 +104,8 @@ struct DenseFillArgs {
   int B, Y, X, Cs;
 };
 
-__global__ void dense_fill_kernel(DenseFillArgs a, float4* __restrict__ out) {
+template <typename T>
+__global__ void dense_fill_kernel(DenseFillArgs a, T* __restrict__ out) {
   int C4 = a.Cs >> 2;
   long long total = (long long)a.B * a.Y * a.X * 3 * C4;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
@@ -100,14 +126,15 @@ __global__ void dense_fill_kernel(DenseFillArgs a, float4* __restrict__ out) {
     } else {
       v = __ldg(reinterpret_cast<const float4*>(a.bg[s]) + c);
     }
-    out[t] = v;
+    Pack4<T>::store(out, t, v);
   }
 }
 
 // backward: drows_s[row] = dout[cell, s*Cs : (s+1)*Cs] at covered cells (gather),
 //           dbg_s[c]     = sum over uncovered cells of dout[cell, s*Cs + c].
+template <typename T>
 __global__ void dense_fill_bwd_rows_kernel(DenseFillArgs a, int s, const int* __restrict__ indices, long long Ns,
-                                           const float4* __restrict__ dout, float4* __restrict__ drows) {
+                                           const T* __restrict__ dout, float4* __restrict__ drows) {
   int C4 = a.Cs >> 2;
   int k = a.k[s], kk = k * k;
   long long total = Ns * kk * C4;
@@ -118,7 +145,7 @@ __global__ void dense_fill_bwd_rows_kernel(DenseFillArgs a, int s, const int* __
     int sub = (int)(row % kk);
     int b = indices[3 * n], y = indices[3 * n + 1] * k + sub / k, x = indices[3 * n + 2] * k + sub % k;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (y < a.Y && x < a.X) v = __ldg(dout + ((((long long)b * a.Y + y) * a.X + x) * 3 + s) * C4 + c);
+    if (y < a.Y && x < a.X) v = Pack4<T>::load(dout, ((((long long)b * a.Y + y) * a.X + x) * 3 + s) * C4 + c);
     drows[t] = v;
   }
 }
@@ -126,7 +153,8 @@ __global__ void dense_fill_bwd_rows_kernel(DenseFillArgs a, int s, const int* __
 // column sums of dout over the cells NOT covered at scale s.  grid = (chunks, 3); block 256 =
 // 8 cell-lanes x 32 channel-lanes(float4); per-block partials are combined with float atomics
 // into dbg (3*Cs, caller zeroes) - 3*Cs*gridDim.x adds in total, negligible contention.
-__global__ void __launch_bounds__(256) dense_fill_bwd_bg_kernel(DenseFillArgs a, const float4* __restrict__ dout,
+template <typename T>
+__global__ void __launch_bounds__(256) dense_fill_bwd_bg_kernel(DenseFillArgs a, const T* __restrict__ dout,
                                                                float* __restrict__ dbg) {
   int C4 = a.Cs >> 2;  // == 32 for Cs = 128
   int s = blockIdx.y;
@@ -141,7 +169,7 @@ __global__ void __launch_bounds__(256) dense_fill_bwd_bg_kernel(DenseFillArgs a,
     int gy = y / k, gx = x / k;
     int rank = (gy < a.H[s] && gx < a.W[s]) ? __ldg(a.grid[s] + ((long long)b * a.H[s] + gy) * a.W[s] + gx) : -1;
     if (rank < 0) {
-      float4 v = __ldg(dout + (cell * 3 + s) * C4 + lane);
+      float4 v = Pack4<T>::load(dout, (cell * 3 + s) * C4 + lane);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
   }
@@ -176,20 +204,21 @@ static int fill_args(DenseFillArgs& a, const float* const* rows, const float* co
   return GDMAE_OK;
 }
 
-extern "C" int gdmae_dense_fill(const float* const* rows, const float* const* bg, const int32_t* const* rank_grids,
-                                const int* strides, int B, int Y, int X, int Cs, float* out, void* stream_) {
+template <typename T>
+static int dense_fill_impl(const float* const* rows, const float* const* bg, const int32_t* const* rank_grids, const int* strides,
+                           int B, int Y, int X, int Cs, T* out, void* stream_) {
   DenseFillArgs a;
   int rc = fill_args(a, rows, bg, rank_grids, strides, B, Y, X, Cs);
   if (rc) return rc;
   long long total = (long long)B * Y * X * 3 * (Cs / 4);
-  dense_fill_kernel<<<gdmae_grid(total, 256, 32), 256, 0, (cudaStream_t)stream_>>>(a, (float4*)out);
+  dense_fill_kernel<T><<<gdmae_grid(total, 256, 32), 256, 0, (cudaStream_t)stream_>>>(a, out);
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;
 }
 
-extern "C" int gdmae_dense_fill_bwd(const float* dout, const int32_t* const* rank_grids, const int32_t* const* indices,
-                                    const int64_t* n_sites, const int* strides, int B, int Y, int X, int Cs,
-                                    float* const* drows, float* dbg /* (3*Cs) */, void* stream_) {
+template <typename T>
+static int dense_fill_bwd_impl(const T* dout, const int32_t* const* rank_grids, const int32_t* const* indices, const int64_t* n_sites,
+                               const int* strides, int B, int Y, int X, int Cs, float* const* drows, float* dbg, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   DenseFillArgs a;
   int rc = fill_args(a, nullptr, nullptr, rank_grids, strides, B, Y, X, Cs);
@@ -198,56 +227,76 @@ extern "C" int gdmae_dense_fill_bwd(const float* dout, const int32_t* const* ran
   for (int s = 0; s < 3; ++s) {
     long long total = n_sites[s] * strides[s] * strides[s] * (Cs / 4);
     if (total == 0) continue;
-    dense_fill_bwd_rows_kernel<<<gdmae_grid(total, 256, 32), 256, 0, st>>>(a, s, indices[s], n_sites[s], (const float4*)dout,
-                                                                          (float4*)drows[s]);
+    dense_fill_bwd_rows_kernel<T><<<gdmae_grid(total, 256, 32), 256, 0, st>>>(a, s, indices[s], n_sites[s], dout, (float4*)drows[s]);
     GDMAE_LAUNCH_CHECK();
   }
   dim3 grid(GDMAE_NUM_SMS * 4, 3);
-  dense_fill_bwd_bg_kernel<<<grid, 256, 0, st>>>(a, (const float4*)dout, dbg);
+  dense_fill_bwd_bg_kernel<T><<<grid, 256, 0, st>>>(a, dout, dbg);
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;
 }
 
+// out_dtype / dtype: 0 = fp32, 1 = bf16 (the dense BEV map feeds the cuDNN decoder conv)
+extern "C" int gdmae_dense_fill(const float* const* rows, const float* const* bg, const int32_t* const* rank_grids,
+                                const int* strides, int B, int Y, int X, int Cs, void* out, int out_dtype, void* stream_) {
+  if (out_dtype == 0) return dense_fill_impl<float>(rows, bg, rank_grids, strides, B, Y, X, Cs, (float*)out, stream_);
+  return dense_fill_impl<__nv_bfloat16>(rows, bg, rank_grids, strides, B, Y, X, Cs, (__nv_bfloat16*)out, stream_);
+}
+
+extern "C" int gdmae_dense_fill_bwd(const void* dout, int dtype, const int32_t* const* rank_grids, const int32_t* const* indices,
+                                    const int64_t* n_sites, const int* strides, int B, int Y, int X, int Cs,
+                                    float* const* drows, float* dbg /* (3*Cs) */, void* stream_) {
+  if (dtype == 0) return dense_fill_bwd_impl<float>((const float*)dout, rank_grids, indices, n_sites, strides, B, Y, X, Cs, drows, dbg, stream_);
+  return dense_fill_bwd_impl<__nv_bfloat16>((const __nv_bfloat16*)dout, rank_grids, indices, n_sites, strides, B, Y, X, Cs, drows, dbg, stream_);
+}
+
 // out[m, :] = src[b, y, x, :] for NHWC src (B,Y,X,C) at the M pillar cells (coalesced row gather);
 // coords are the int64 (M,4) [b,z,y,x] voxel coords.  spt_backbone_mae.py:141-143.
-__global__ void gather_nhwc_kernel(const float4* __restrict__ src, const long long* __restrict__ coords, long long M, int Y, int X,
+template <typename T>
+__global__ void gather_nhwc_kernel(const T* __restrict__ src, const long long* __restrict__ coords, long long M, int Y, int X,
                                    int C4, float4* __restrict__ out) {
   long long total = M * C4;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     int c = (int)(t % C4);
     long long m = t / C4;
     long long b = coords[4 * m], y = coords[4 * m + 2], x = coords[4 * m + 3];
-    out[t] = __ldg(src + ((b * Y + y) * X + x) * C4 + c);
+    out[t] = Pack4<T>::load(src, ((b * Y + y) * X + x) * C4 + c);
   }
 }
+template <typename T>
 __global__ void scatter_nhwc_kernel(const float4* __restrict__ dout, const long long* __restrict__ coords, long long M, int Y, int X,
-                                    int C4, float4* __restrict__ dsrc) {
+                                    int C4, T* __restrict__ dsrc) {
   long long total = M * C4;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     int c = (int)(t % C4);
     long long m = t / C4;
     long long b = coords[4 * m], y = coords[4 * m + 2], x = coords[4 * m + 3];
-    dsrc[((b * Y + y) * X + x) * C4 + c] = dout[t];
+    Pack4<T>::store(dsrc, ((b * Y + y) * X + x) * C4 + c, dout[t]);
   }
 }
 
-extern "C" int gdmae_gather_nhwc(const float* src, const int64_t* voxel_coords, int64_t M, int Y, int X, int C, float* out,
+// src (B,Y,X,C) NHWC in fp32 (dtype 0) or bf16 (dtype 1); out (M, C) fp32
+extern "C" int gdmae_gather_nhwc(const void* src, int dtype, const int64_t* voxel_coords, int64_t M, int Y, int X, int C, float* out,
                                  void* stream_) {
   GDMAE_CHECK_ARG(M >= 0 && C > 0 && (C % 4) == 0);
   if (M == 0) return GDMAE_OK;
-  gather_nhwc_kernel<<<gdmae_grid(M * (C / 4), 256, 32), 256, 0, (cudaStream_t)stream_>>>(
-      (const float4*)src, (const long long*)voxel_coords, M, Y, X, C / 4, (float4*)out);
+  int g = gdmae_grid(M * (C / 4), 256, 32);
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (dtype == 0) gather_nhwc_kernel<float><<<g, 256, 0, st>>>((const float*)src, (const long long*)voxel_coords, M, Y, X, C / 4, (float4*)out);
+  else gather_nhwc_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, (const long long*)voxel_coords, M, Y, X, C / 4, (float4*)out);
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;
 }
 
 // dsrc must be zero-filled by the caller (pillar cells are unique, so plain stores suffice).
-extern "C" int gdmae_scatter_nhwc(const float* dout, const int64_t* voxel_coords, int64_t M, int Y, int X, int C, float* dsrc,
-                                  void* stream_) {
+extern "C" int gdmae_scatter_nhwc(const float* dout, const int64_t* voxel_coords, int64_t M, int Y, int X, int C, void* dsrc,
+                                  int dtype, void* stream_) {
   GDMAE_CHECK_ARG(M >= 0 && C > 0 && (C % 4) == 0);
   if (M == 0) return GDMAE_OK;
-  scatter_nhwc_kernel<<<gdmae_grid(M * (C / 4), 256, 32), 256, 0, (cudaStream_t)stream_>>>(
-      (const float4*)dout, (const long long*)voxel_coords, M, Y, X, C / 4, (float4*)dsrc);
+  int g = gdmae_grid(M * (C / 4), 256, 32);
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (dtype == 0) scatter_nhwc_kernel<float><<<g, 256, 0, st>>>((const float4*)dout, (const long long*)voxel_coords, M, Y, X, C / 4, (float*)dsrc);
+  else scatter_nhwc_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const float4*)dout, (const long long*)voxel_coords, M, Y, X, C / 4, (__nv_bfloat16*)dsrc);
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;
 }

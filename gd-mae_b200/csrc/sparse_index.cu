@@ -251,7 +251,8 @@ struct PopCount {
 
 __global__ void win_finish_kernel(const int* __restrict__ win_of, const unsigned char* __restrict__ pos_of, int N,
                                   const unsigned long long* __restrict__ wmask, const int* __restrict__ win_off,
-                                  int* __restrict__ inner, int* __restrict__ level, int* __restrict__ win_tok) {
+                                  int* __restrict__ inner, int* __restrict__ level, int* __restrict__ win_tok,
+                                  int4* __restrict__ row_info) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
     int w = win_of[i];
     unsigned long long m = wmask[w];
@@ -260,7 +261,10 @@ __global__ void win_finish_kernel(const int* __restrict__ win_of, const unsigned
     int n = __popcll(m);
     inner[i] = r;
     level[i] = n < 16 ? 0 : (n < 32 ? 1 : 2);
-    win_tok[win_off[w] + r] = i;
+    int s = win_off[w];
+    win_tok[s + r] = i;
+    // everything the SRA kernels need about CSR row (s + r), one 16-byte load: token, window extent, cell
+    row_info[s + r] = make_int4(i, s, s + n, pos);
   }
 }
 
@@ -292,11 +296,12 @@ extern "C" size_t gdmae_window_table_workspace_bytes(int64_t n_windows) {
 // Outputs: win_of_token (N) dense window id; pos_of_token (N) u8 = yy*8+xx; inner (N) rank in window;
 // level (N) drop level; win_mask (nW) u64; win_off (nW+1) CSR offsets over dense windows;
 // win_tok (N) tokens grouped by window; lvl_rank (nW) rank of the window among the non-empty
-// windows of its level (-1 if empty); lvl_counts (3).
+// windows of its level (-1 if empty); lvl_counts (3); row_info (N,4) int32 per CSR row:
+// [token, first row of its window, one past its last row, in-window cell].
 extern "C" int gdmae_window_table(const int32_t* indices, int64_t N, int B, int H, int W, int shifted,
                                   int32_t* win_of_token, uint8_t* pos_of_token, int32_t* inner, int32_t* level,
                                   uint64_t* win_mask, int32_t* win_off, int32_t* win_tok, int32_t* lvl_rank,
-                                  int32_t* lvl_counts, void* workspace, size_t ws_bytes, void* stream_) {
+                                  int32_t* lvl_counts, int32_t* row_info, void* workspace, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   int nWx = (W + 7) / 8 + 1, nWy = (H + 7) / 8 + 1;
   long long nW = (long long)B * nWx * nWy;
@@ -326,7 +331,8 @@ extern "C" int gdmae_window_table(const int32_t* indices, int64_t N, int B, int 
   win_level_kernel<<<gdmae_grid(nW, 256), 256, 0, stream>>>(wm, lscan, (int)nW, lvl_rank, lvl_counts, win_off, (int)N);
   GDMAE_LAUNCH_CHECK();
   if (N > 0) {
-    win_finish_kernel<<<gdmae_grid(N, 256), 256, 0, stream>>>(win_of_token, pos_of_token, (int)N, wm, win_off, inner, level, win_tok);
+    win_finish_kernel<<<gdmae_grid(N, 256), 256, 0, stream>>>(win_of_token, pos_of_token, (int)N, wm, win_off, inner, level, win_tok,
+                                                              (int4*)row_info);
     GDMAE_LAUNCH_CHECK();
   }
   return GDMAE_OK;

@@ -15,6 +15,7 @@ _fwd = custom_fwd(device_type="cuda", cast_inputs=torch.float32)
 _bwd = custom_bwd(device_type="cuda")
 
 I32, I64, F32 = torch.int32, torch.int64, torch.float32
+_DT = {torch.float32: 0, torch.bfloat16: 1}  # dtype codes of the C ABI
 
 
 def _dev(t):
@@ -227,7 +228,13 @@ class WindowTable:
     """Window bookkeeping of one shift (replaces batch_win_inds / coors_in_win / drop levels /
     flat2win_inds / key masks / pos dict of SSTInputLayer.forward, spt_backbone.py:106-135)."""
     __slots__ = ("win_of_token", "pos_of_token", "inner", "level", "win_mask", "win_off", "win_tok", "lvl_rank",
-                 "lvl_counts", "n_windows", "nWx", "nWy", "N")
+                 "lvl_counts", "row_info", "n_windows", "nWx", "nWy", "N", "_pos_long")
+
+    def pos_long(self):
+        """in-window cell per token as int64 (index for torch gathers), cached"""
+        if getattr(self, "_pos_long", None) is None:
+            self._pos_long = self.pos_of_token.long()
+        return self._pos_long
 
 
 def window_table(indices, B, H, W, shifted):
@@ -246,13 +253,43 @@ def window_table(indices, B, H, W, shifted):
     t.win_tok = torch.empty((max(N, 1),), dtype=I32, device=dev)[:N]
     t.lvl_rank = torch.empty((nW,), dtype=I32, device=dev)
     t.lvl_counts = torch.empty((3,), dtype=I32, device=dev)
+    t.row_info = torch.empty((max(N, 1), 4), dtype=I32, device=dev)[:N]
+    t._pos_long = None
     lib = L.lib()
     ws = L.workspace(lib.gdmae_window_table_workspace_bytes(L.i64(nW)), dev)
     L.check(lib.gdmae_window_table(L.P(indices), L.i64(N), B, H, W, int(bool(shifted)), L.P(t.win_of_token),
                                    L.P(t.pos_of_token), L.P(t.inner), L.P(t.level), L.P(t.win_mask), L.P(t.win_off),
-                                   L.P(t.win_tok), L.P(t.lvl_rank), L.P(t.lvl_counts), L.P(ws), ctypes.c_size_t(ws.numel()),
-                                   L.stream()), "gdmae_window_table")
+                                   L.P(t.win_tok), L.P(t.lvl_rank), L.P(t.lvl_counts), L.P(t.row_info), L.P(ws),
+                                   ctypes.c_size_t(ws.numel()), L.stream()), "gdmae_window_table")
     return t
+
+
+def sra_fwd(qkv, lut, tau, table, tau_min, nhead):
+    """raw launch: -> (out (N,d), lse (N,nhead))"""
+    N, d3 = qkv.shape
+    d = d3 // 3
+    out = torch.empty((N, d), dtype=F32, device=qkv.device)
+    lse = torch.empty((N, nhead), dtype=F32, device=qkv.device)
+    # algorithmic bytes (SURVEY.md 8d, a18 minus projections): N*d*(3*s_in + s_out) + N*8
+    with L.timed(f"sra_fwd_d{d}", N * d * 16 + N * 8):
+        L.check(L.lib().gdmae_sra_attention_fwd(L.P(qkv), L.P(lut), L.P(table.row_info), L.i64(N), d, nhead, L.P(tau),
+                                                L.f32(tau_min), L.P(out), L.P(lse), L.stream()), "gdmae_sra_attention_fwd")
+    return out, lse
+
+
+def sra_bwd(qkv, lut, tau, table, tau_min, nhead, out, lse, dout):
+    """raw launch: -> (dqkv (N,3d), dtau_sum (1) float64 = sum dS*S)"""
+    N, d3 = qkv.shape
+    d = d3 // 3
+    dqkv = torch.empty_like(qkv)
+    dtau_sum = torch.zeros((1,), dtype=torch.float64, device=qkv.device)
+    work = torch.empty((N, nhead), dtype=F32, device=qkv.device)
+    # bwd algorithmic bytes: qkv + o + dO in, dqkv out
+    with L.timed(f"sra_bwd_d{d}", N * d * 4 * (3 + 1 + 1 + 3) + N * 8):
+        L.check(L.lib().gdmae_sra_attention_bwd(L.P(qkv), L.P(lut), L.P(table.row_info), L.i64(N), d, nhead, L.P(tau),
+                                                L.f32(tau_min), L.P(out), L.P(lse), L.P(dout), L.P(dqkv), L.P(dtau_sum), L.P(work),
+                                                L.stream()), "gdmae_sra_attention_bwd")
+    return dqkv, dtau_sum
 
 
 # ----------------------------------------------------------------------------- sparse conv gather
@@ -290,17 +327,9 @@ class SraAttention(torch.autograd.Function):
     @_fwd
     def forward(ctx, qkv, lut, tau, table, tau_min, nhead):
         qkv, lut = qkv.contiguous(), lut.contiguous()
-        N, d3 = qkv.shape
-        d = d3 // 3
-        out = torch.empty((N, d), dtype=F32, device=_dev(qkv))
-        lse = torch.empty((N, nhead), dtype=F32, device=qkv.device)
+        _dev(qkv)
         tau_c = tau.detach().reshape(-1).contiguous()
-        # algorithmic bytes (SURVEY.md 8d, a18 minus projections): N*d*(3*s_in + s_out) + N*8
-        with L.timed(f"sra_fwd_d{d}", N * d * 16 + N * 8):
-            L.check(L.lib().gdmae_sra_attention_fwd(L.P(qkv), L.P(lut), L.P(table.win_tok), L.P(table.win_of_token),
-                                                    L.P(table.pos_of_token), L.P(table.win_off), L.i64(N), d, nhead,
-                                                    L.P(tau_c), L.f32(tau_min), L.P(out), L.P(lse), L.stream()),
-                    "gdmae_sra_attention_fwd")
+        out, lse = sra_fwd(qkv, lut, tau_c, table, tau_min, nhead)
         ctx.save_for_backward(qkv, lut, tau_c, out, lse)
         ctx.table, ctx.tau_min, ctx.nhead, ctx.tau_shape = table, tau_min, nhead, tau.shape
         return out
@@ -310,21 +339,11 @@ class SraAttention(torch.autograd.Function):
     def backward(ctx, dout):
         qkv, lut, tau_c, out, lse = ctx.saved_tensors
         t = ctx.table
-        N, d3 = qkv.shape
-        d = d3 // 3
-        dout = dout.contiguous()
-        dqkv = torch.empty_like(qkv)
-        dtau_sum = torch.zeros((1,), dtype=torch.float64, device=qkv.device)
-        work = torch.empty((N, ctx.nhead), dtype=F32, device=qkv.device)
-        # bwd algorithmic bytes: qkv + o + dO in, dqkv out
-        with L.timed(f"sra_bwd_d{d}", N * d * 4 * (3 + 1 + 1 + 3) + N * 8):
-            L.check(L.lib().gdmae_sra_attention_bwd(L.P(qkv), L.P(lut), L.P(t.win_tok), L.P(t.win_of_token), L.P(t.pos_of_token),
-                                                    L.P(t.win_off), L.i64(N), d, ctx.nhead, L.P(tau_c), L.f32(ctx.tau_min),
-                                                    L.P(out), L.P(lse), L.P(dout), L.P(dqkv), L.P(dtau_sum), L.P(work),
-                                                    L.stream()), "gdmae_sra_attention_bwd")
+        d = qkv.shape[1] // 3
+        dqkv, dtau_sum = sra_bwd(qkv, lut, tau_c, t, ctx.tau_min, ctx.nhead, out, lse, dout.contiguous())
         # the LUT rows receive the q/k gradients of the tokens sitting on that in-window cell
         dlut = torch.zeros_like(lut)
-        dlut.index_add_(0, t.pos_of_token.long(), dqkv[:, :2 * d])
+        dlut.index_add_(0, t.pos_long(), dqkv[:, :2 * d])
         tau_eff = torch.clamp(tau_c, min=ctx.tau_min)
         dtau = torch.where(tau_c >= ctx.tau_min, -(dtau_sum.float() / tau_eff), torch.zeros_like(tau_c))
         return dqkv, dlut, dtau.reshape(ctx.tau_shape), None, None, None
@@ -336,13 +355,14 @@ class DenseFill(torch.autograd.Function):
 
     @staticmethod
     @_fwd
-    def forward(ctx, r0, r1, r2, bg0, bg1, bg2, grids, indices, strides, B, Y, X):
-        rows = [r.contiguous() for r in (r0, r1, r2)]
-        bgs = [b.contiguous() for b in (bg0, bg1, bg2)]
+    def forward(ctx, r0, r1, r2, bg0, bg1, bg2, grids, indices, strides, B, Y, X, out_dtype=torch.float32):
+        rows = [r.contiguous().float() for r in (r0, r1, r2)]
+        bgs = [b.contiguous().float() for b in (bg0, bg1, bg2)]
         Cs = bgs[0].shape[0]
-        out = torch.empty((B, Y, X, 3 * Cs), dtype=F32, device=_dev(rows[0]))
-        L.check(L.lib().gdmae_dense_fill(L.parr(rows), L.parr(bgs), L.parr(grids), L.iarr(strides), B, Y, X, Cs, L.P(out),
-                                         L.stream()), "gdmae_dense_fill")
+        out = torch.empty((B, Y, X, 3 * Cs), dtype=out_dtype, device=_dev(rows[0]))
+        with L.timed("dense_fill", out.numel() * out.element_size()):
+            L.check(L.lib().gdmae_dense_fill(L.parr(rows), L.parr(bgs), L.parr(grids), L.iarr(strides), B, Y, X, Cs, L.P(out),
+                                             _DT[out_dtype], L.stream()), "gdmae_dense_fill")
         ctx.grids, ctx.indices, ctx.strides, ctx.dims = grids, indices, strides, (B, Y, X, Cs)
         ctx.row_shapes = [r.shape for r in rows]
         return out
@@ -355,35 +375,35 @@ class DenseFill(torch.autograd.Function):
         drows = [torch.empty(s, dtype=F32, device=dout.device) for s in ctx.row_shapes]
         dbg = torch.empty((3 * Cs,), dtype=F32, device=dout.device)
         n_sites = (ctypes.c_int64 * 3)(*[int(i.shape[0]) for i in ctx.indices])
-        L.check(L.lib().gdmae_dense_fill_bwd(L.P(dout), L.parr(ctx.grids), L.parr(ctx.indices), n_sites, L.iarr(ctx.strides),
-                                             B, Y, X, Cs, L.parr(drows), L.P(dbg), L.stream()), "gdmae_dense_fill_bwd")
-        return (drows[0], drows[1], drows[2], dbg[:Cs], dbg[Cs:2 * Cs], dbg[2 * Cs:], None, None, None, None, None, None)
+        with L.timed("dense_fill_bwd", dout.numel() * dout.element_size()):
+            L.check(L.lib().gdmae_dense_fill_bwd(L.P(dout), _DT[dout.dtype], L.parr(ctx.grids), L.parr(ctx.indices), n_sites,
+                                                 L.iarr(ctx.strides), B, Y, X, Cs, L.parr(drows), L.P(dbg), L.stream()),
+                    "gdmae_dense_fill_bwd")
+        return (drows[0], drows[1], drows[2], dbg[:Cs], dbg[Cs:2 * Cs], dbg[2 * Cs:], None, None, None, None, None, None, None)
 
 
 class GatherNHWC(torch.autograd.Function):
     """spatial_features.permute(0,2,3,1)[b, y, x] at all pillars (spt_backbone_mae.py:141-143)."""
 
     @staticmethod
-    @_fwd
     def forward(ctx, src_nhwc, voxel_coords):
         src_nhwc = src_nhwc.contiguous()
         B, Y, X, C = src_nhwc.shape
         M = voxel_coords.shape[0]
         out = torch.empty((M, C), dtype=F32, device=_dev(src_nhwc))
-        L.check(L.lib().gdmae_gather_nhwc(L.P(src_nhwc), L.P(voxel_coords), L.i64(M), Y, X, C, L.P(out), L.stream()),
-                "gdmae_gather_nhwc")
+        L.check(L.lib().gdmae_gather_nhwc(L.P(src_nhwc), _DT[src_nhwc.dtype], L.P(voxel_coords), L.i64(M), Y, X, C, L.P(out),
+                                          L.stream()), "gdmae_gather_nhwc")
         ctx.save_for_backward(voxel_coords)
-        ctx.shape = (B, Y, X, C)
+        ctx.shape, ctx.dtype = (B, Y, X, C), src_nhwc.dtype
         return out
 
     @staticmethod
-    @_bwd
     def backward(ctx, dout):
         (voxel_coords,) = ctx.saved_tensors
         B, Y, X, C = ctx.shape
-        dsrc = torch.zeros(ctx.shape, dtype=F32, device=dout.device)
-        L.check(L.lib().gdmae_scatter_nhwc(L.P(dout.contiguous()), L.P(voxel_coords), L.i64(voxel_coords.shape[0]), Y, X, C,
-                                           L.P(dsrc), L.stream()), "gdmae_scatter_nhwc")
+        dsrc = torch.zeros(ctx.shape, dtype=ctx.dtype, device=dout.device)
+        L.check(L.lib().gdmae_scatter_nhwc(L.P(dout.contiguous().float()), L.P(voxel_coords), L.i64(voxel_coords.shape[0]), Y, X, C,
+                                           L.P(dsrc), _DT[ctx.dtype], L.stream()), "gdmae_scatter_nhwc")
         return dsrc, None
 
 

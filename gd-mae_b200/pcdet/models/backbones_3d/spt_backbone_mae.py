@@ -56,6 +56,9 @@ class SPTBackboneMAE(nn.Module):
         self.decoder_pred = nn.Linear(in_channels, self.mask_cfg.NUM_PRD_POINTS * 3, bias=True)
         self.forward_ret_dict = {}
         self.num_point_features = in_channels
+        # dtype of the dense 384-channel BEV map and of the cuDNN decoder conv (fp32 = parity mode,
+        # torch.bfloat16 = the bf16 configuration of BASELINE.json; BN statistics stay fp32 either way)
+        self.decoder_dtype = torch.float32
 
     # ------------------------------------------------------------------ loss (spt_backbone_mae.py:83-89)
     def get_loss(self, tb_dict=None):
@@ -145,9 +148,16 @@ class SPTBackboneMAE(nn.Module):
         srcs = [multi_scale_3d_features[s] for s in self.model_cfg.FEATURES_SOURCE]
         n_cells_total = batch_size * Y * X
         rows, bgs = zip(*[self._deblock_rows(i, sp, n_cells_total) for i, sp in enumerate(srcs)])
+        dt = self.decoder_dtype
         fused = _ops.DenseFill.apply(rows[0], rows[1], rows[2], bgs[0], bgs[1], bgs[2], [sp.rank_grid() for sp in srcs],
-                                     [sp.indices for sp in srcs], self.fuse_strides, batch_size, Y, X)   # (B, Y, X, 384) NHWC
-        spatial_features = self.decoder_conv_out(fused.permute(0, 3, 1, 2))                                  # (B, C, Y, X)
+                                     [sp.indices for sp in srcs], self.fuse_strides, batch_size, Y, X, dt)  # (B,Y,X,384) NHWC
+        conv, bn = self.decoder_conv_out[0], self.decoder_conv_out[1]
+        w = conv.weight if dt == torch.float32 else conv.weight.to(dt)
+        y = F.conv2d(fused.permute(0, 3, 1, 2), w.contiguous(memory_format=torch.channels_last), padding=1)  # cuDNN, NHWC
+        y = F.batch_norm(y, bn.running_mean, bn.running_var, bn.weight, bn.bias, self.training, bn.momentum, bn.eps)
+        if self.training:
+            bn.num_batches_tracked += 1
+        spatial_features = F.relu(y)                                                                         # (B, C, Y, X)
         spatial_features_stride = multi_scale_3d_strides[self.model_cfg.FEATURES_SOURCE[0]] // self.fuse_strides[0]
 
         batch_dict['multi_scale_3d_features'] = multi_scale_3d_features

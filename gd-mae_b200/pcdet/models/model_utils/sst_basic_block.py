@@ -8,6 +8,7 @@ the ops.WindowTable of the shift (replaces flat2win_inds + voxel_drop_level), an
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .... import fused as _fused
 from .cosine_msa import CosineMultiheadAttention
 
 
@@ -37,7 +38,11 @@ class EncoderLayer(nn.Module):
         self.norm2 = nn.LayerNorm(d_model)
         self.activation = _get_activation_fn(activation)
 
+    fused = True  # one autograd node per layer (fused.EncoderLayerFunction); False = op-by-op autograd
+
     def forward(self, src, pos_dict, ind_dict, key_padding_mask_dict=None):
+        if self.fused and self.activation is F.gelu:
+            return _fused.encoder_layer(self, src, pos_dict, ind_dict)
         src2 = self.win_attn(src, pos_dict, ind_dict, key_padding_mask_dict)
         src = self.norm1(src + src2)
         src2 = self.linear2(self.activation(self.linear1(src)))

@@ -123,8 +123,9 @@ int gdmae_gather_rows_transposed(const float* dcol, const int32_t* tmap, int64_t
 size_t gdmae_window_table_workspace_bytes(int64_t n_windows);
 int gdmae_window_table(const int32_t* indices, int64_t N, int B, int H, int W, int shifted, int32_t* win_of_token,
                        uint8_t* pos_of_token, int32_t* inner, int32_t* level, uint64_t* win_mask, int32_t* win_off,
-                       int32_t* win_tok, int32_t* lvl_rank, int32_t* lvl_counts, void* workspace, size_t ws_bytes,
-                       void* stream);
+                       int32_t* win_tok, int32_t* lvl_rank, int32_t* lvl_counts, int32_t* row_info /* (N,4): token,
+                       first row of its window, one past its last row, in-window cell; 16-byte aligned */,
+                       void* workspace, size_t ws_bytes, void* stream);
 
 /* ---- a16-a18 SRA attention core --------------------------------------------------------------
  * replaces flat2window/window2flat (sst_utils.py:107-181), the per-level loop of
@@ -132,13 +133,28 @@ int gdmae_window_table(const int32_t* indices, int64_t N, int B, int H, int W, i
  * _scaled_cosine_attention (pcdet/models/model_utils/cosine_msa.py:114-176) incl. the -inf key mask.
  * qkv (N, 3d) = [x Wq^T | x Wk^T | x Wv^T + bv]; lut (64, 2d) = pos_table [Wq;Wk]^T + [bq;bk];
  * out (N, d) pre out-proj; lse (N, 8).  nhead == 8, d in {128, 256}. */
-int gdmae_sra_attention_fwd(const float* qkv, const float* lut, const int32_t* win_tok, const int32_t* win_of_token,
-                            const uint8_t* pos_of_token, const int32_t* win_off, int64_t N, int d, int nhead,
+int gdmae_sra_attention_fwd(const float* qkv, const float* lut, const int32_t* row_info, int64_t N, int d, int nhead,
                             const float* tau, float tau_min, float* out, float* lse, void* stream);
-int gdmae_sra_attention_bwd(const float* qkv, const float* lut, const int32_t* win_tok, const int32_t* win_of_token,
-                            const uint8_t* pos_of_token, const int32_t* win_off, int64_t N, int d, int nhead,
+int gdmae_sra_attention_bwd(const float* qkv, const float* lut, const int32_t* row_info, int64_t N, int d, int nhead,
                             const float* tau, float tau_min, const float* out, const float* lse, const float* dout,
                             float* dqkv, double* dtau_sum, float* work_D, void* stream);
+
+/* ---- a19 encoder-layer row kernels ------------------------------------------------------------
+ * replace the residual + LayerNorm pairs and the GELU(linear1) of EncoderLayer.forward
+ * (pcdet/models/model_utils/sst_basic_block.py:77-84) and the bias-gradient reductions of its
+ * linears.  d in {128,256}; parameter gradients are written (accumulate=0) or added (accumulate=1).
+ * workspace: gdmae_rowwise_workspace_bytes(max columns). */
+size_t gdmae_rowwise_workspace_bytes(int max_cols);
+int gdmae_add_layernorm_fwd(const float* x, const float* res, const float* gamma, const float* beta, int64_t N, int d,
+                            float eps, float* y, float* mean, float* rstd, void* stream);
+int gdmae_add_layernorm_bwd(const float* x, const float* res, const float* gamma, const float* mean, const float* rstd,
+                            const float* dy, int64_t N, int d, float* dz, float* dgamma, float* dbeta, int accumulate,
+                            void* workspace, size_t ws_bytes, void* stream);
+int gdmae_bias_gelu_fwd(const float* h, const float* bias, int64_t N, int C, float* out, void* stream);
+int gdmae_bias_gelu_bwd(const float* h, const float* bias, const float* dg, int64_t N, int C, float* dh, float* dbias,
+                        int accumulate, void* workspace, size_t ws_bytes, void* stream);
+int gdmae_colsum(const float* x, int64_t N, int ld, int col0, int C, float* out, int accumulate, void* workspace,
+                 size_t ws_bytes, void* stream);
 
 /* ---- a22/a23 decoder dense fill and pillar gather --------------------------------------------
  * replaces SparseConvTensor.dense() + ConvTranspose2d(k=s) + BatchNorm2d + ReLU + torch.cat
@@ -146,14 +162,15 @@ int gdmae_sra_attention_bwd(const float* qkv, const float* lut, const int32_t* w
  * gather at all pillars (spt_backbone_mae.py:141-143).  rows/bg/rank_grids/indices/drows are HOST
  * arrays of 3 device pointers; out (B, Y, X, 3*Cs) NHWC. */
 int gdmae_dense_fill(const float* const* rows, const float* const* bg, const int32_t* const* rank_grids,
-                     const int* strides, int B, int Y, int X, int Cs, float* out, void* stream);
-int gdmae_dense_fill_bwd(const float* dout, const int32_t* const* rank_grids, const int32_t* const* indices,
+                     const int* strides, int B, int Y, int X, int Cs, void* out, int out_dtype /* 0 fp32, 1 bf16 */,
+                     void* stream);
+int gdmae_dense_fill_bwd(const void* dout, int dtype, const int32_t* const* rank_grids, const int32_t* const* indices,
                          const int64_t* n_sites, const int* strides, int B, int Y, int X, int Cs,
                          float* const* drows, float* dbg, void* stream);
-int gdmae_gather_nhwc(const float* src, const int64_t* voxel_coords, int64_t M, int Y, int X, int C, float* out,
+int gdmae_gather_nhwc(const void* src, int dtype, const int64_t* voxel_coords, int64_t M, int Y, int X, int C, float* out,
                       void* stream);
-int gdmae_scatter_nhwc(const float* dout, const int64_t* voxel_coords, int64_t M, int Y, int X, int C, float* dsrc,
-                       void* stream);
+int gdmae_scatter_nhwc(const float* dout, const int64_t* voxel_coords, int64_t M, int Y, int X, int C, void* dsrc,
+                       int dtype, void* stream);
 
 /* ---- a24-a26 chamfer head --------------------------------------------------------------------
  * gdmae_group_points_centered replaces sst_ops_utils.group_inner_inds + points[group_inds]

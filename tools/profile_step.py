@@ -24,7 +24,10 @@ cfg = config.builtin_cfg("waymo_ssl")
 model = config.build_mae_model(cfg).cuda()
 trainer = MAETrainer(model, cfg.OPTIMIZATION, total_steps=100)
 pts = torch.from_numpy(O.synth_batch(list(range(args.batch)), O.make_cfg("waymo_ssl"))).cuda()
-ac = torch.autocast("cuda", dtype=torch.bfloat16, enabled=args.dtype == "bf16")
+import contextlib  # noqa: E402
+ac = contextlib.nullcontext()
+if args.dtype == "bf16":
+    model.backbone_3d.decoder_dtype = torch.bfloat16
 for _ in range(4):
     with ac:
         trainer.step({"points": pts, "batch_size": args.batch})
@@ -36,3 +39,4 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
             trainer.step({"points": pts, "batch_size": args.batch})
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
+print(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=45, max_name_column_width=70))
