@@ -150,6 +150,7 @@ def main():
     ap.add_argument("--impl", default="gdmae_b200")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "tf32", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--matmul", default="high", choices=["high", "medium"], help="torch float32 matmul precision in tf32/bf16 mode")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
@@ -172,17 +173,13 @@ def main():
     _lib.check(_lib.lib().gdmae_check_device(), "gdmae_check_device")
 
     torch.backends.cudnn.benchmark = True
-    tf32 = args.dtype != "fp32"
-    torch.backends.cudnn.allow_tf32 = tf32
-    torch.backends.cuda.matmul.allow_tf32 = tf32
     import contextlib
     autocast = contextlib.nullcontext()  # no autocast: encoder GEMMs run TF32, the decoder map/conv are emitted in bf16
 
     torch.manual_seed(666 + rank)
     cfg = config.builtin_cfg("waymo_ssl")
     model = config.build_mae_model(cfg).to(dev)
-    if args.dtype == "bf16":
-        model.backbone_3d.decoder_dtype = torch.bfloat16
+    config.set_precision(model, args.dtype, args.matmul)
     if world > 1:  # identical initial weights on every rank (DDP broadcasts rank 0's, train.py:146)
         for t in list(model.parameters()) + list(model.buffers()):
             dist.broadcast(t.data, 0)

@@ -123,11 +123,20 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(const float4* __restric
 // out[c] = sum_b partial[b * stride + c]   (fixed order)
 __global__ void partial_reduce_kernel(const float* __restrict__ partial, int nblocks, int stride, int C, float* __restrict__ out,
                                       int accumulate) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  // blockDim = 128 = 32 columns x 4 row groups: coalesced over columns, 4 partial sums per column
+  // combined in a fixed order (deterministic)
+  int cg = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  int c = blockIdx.x * 32 + cg;
   float acc = 0.f;
-  for (int b = 0; b < nblocks; ++b) acc += partial[(long long)b * stride + c];
-  out[c] = accumulate ? out[c] + acc : acc;
+  if (c < C)
+    for (int b = rg; b < nblocks; b += 4) acc += partial[(long long)b * stride + c];
+  __shared__ float red[4][32];
+  red[rg][cg] = acc;
+  __syncthreads();
+  if (rg == 0 && c < C) {
+    float t = (red[0][cg] + red[1][cg]) + (red[2][cg] + red[3][cg]);
+    out[c] = accumulate ? out[c] + t : t;
+  }
 }
 
 extern "C" size_t gdmae_rowwise_workspace_bytes(int max_cols) { return (size_t)EW_PART_BLOCKS * 2 * max_cols * 4 + 256; }
@@ -164,9 +173,9 @@ extern "C" int gdmae_add_layernorm_bwd(const float* x, const float* res, const f
   else add_ln_bwd_kernel<2><<<grid, 256, 0, st>>>((const float4*)x, (const float4*)res, (const float4*)gamma, mean, rstd, (const float4*)dy, N, (float4*)dz, partial);
   GDMAE_LAUNCH_CHECK();
   // every CTA left one partial row [dgamma(d) | dbeta(d)]
-  partial_reduce_kernel<<<gdmae_div_up(d, 128), 128, 0, st>>>(partial, grid, 2 * d, d, dgamma, accumulate);
+  partial_reduce_kernel<<<gdmae_div_up(d, 32), 128, 0, st>>>(partial, grid, 2 * d, d, dgamma, accumulate);
   GDMAE_LAUNCH_CHECK();
-  partial_reduce_kernel<<<gdmae_div_up(d, 128), 128, 0, st>>>(partial + d, grid, 2 * d, d, dbeta, accumulate);
+  partial_reduce_kernel<<<gdmae_div_up(d, 32), 128, 0, st>>>(partial + d, grid, 2 * d, d, dbeta, accumulate);
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;
 }
@@ -233,7 +242,7 @@ extern "C" int gdmae_bias_gelu_bwd(const float* h, const float* bias, const floa
   float* partial = (float*)workspace;
   bias_gelu_bwd_kernel<<<grid, 256, 0, st>>>((const float4*)h, (const float4*)bias, (const float4*)dg, N, C / 4, (float4*)dh, partial);
   GDMAE_LAUNCH_CHECK();
-  partial_reduce_kernel<<<gdmae_div_up(C, 128), 128, 0, st>>>(partial, grid, C, C, dbias, accumulate);
+  partial_reduce_kernel<<<gdmae_div_up(C, 32), 128, 0, st>>>(partial, grid, C, C, dbias, accumulate);
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;
 }
@@ -276,7 +285,7 @@ extern "C" int gdmae_colsum(const float* x, int64_t N, int ld, int col0, int C, 
   float* partial = (float*)workspace;
   colsum_kernel<<<grid, C4 * rper, 0, st>>>((const float4*)x, N, ld / 4, col0 / 4, C4, partial);
   GDMAE_LAUNCH_CHECK();
-  partial_reduce_kernel<<<gdmae_div_up(C, 128), 128, 0, st>>>(partial, grid, C, C, out, accumulate);
+  partial_reduce_kernel<<<gdmae_div_up(C, 32), 128, 0, st>>>(partial, grid, C, C, out, accumulate);
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;
 }

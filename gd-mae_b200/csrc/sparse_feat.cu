@@ -40,22 +40,27 @@ template <> struct Pack4<__nv_bfloat16> {
 };
 
 // out[n, k*C + c] = src[map[n,k], c] (0 where map < 0).  One thread per float4.
+template <typename T>
 __global__ void gather_rows_kernel(const float4* __restrict__ src, const int* __restrict__ map, long long N, int K, int C4,
-                                   float4* __restrict__ out) {
+                                   T* __restrict__ out) {
   long long total = N * K * C4;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     int c = (int)(t % C4);
     long long nk = t / C4;
     int m = __ldg(map + nk);
-    out[t] = m >= 0 ? __ldg(src + (long long)m * C4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    Pack4<T>::store(out, t, m >= 0 ? __ldg(src + (long long)m * C4 + c) : make_float4(0.f, 0.f, 0.f, 0.f));
   }
 }
 
-extern "C" int gdmae_gather_rows(const float* src, const int32_t* map, int64_t N, int K, int C, float* out, void* stream_) {
+// out (N, K*C) in fp32 (out_dtype 0) or bf16 (1): the GEMM operand of the sparse conv
+extern "C" int gdmae_gather_rows(const float* src, const int32_t* map, int64_t N, int K, int C, void* out, int out_dtype,
+                                 void* stream_) {
   GDMAE_CHECK_ARG(N >= 0 && K > 0 && C > 0 && (C % 4) == 0);
   if (N == 0) return GDMAE_OK;
-  gather_rows_kernel<<<gdmae_grid(N * K * (C / 4), 256, 32), 256, 0, (cudaStream_t)stream_>>>(
-      (const float4*)src, map, N, K, C / 4, (float4*)out);
+  int g = gdmae_grid(N * K * (C / 4), 256, 32);
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (out_dtype == 0) gather_rows_kernel<float><<<g, 256, 0, st>>>((const float4*)src, map, N, K, C / 4, (float*)out);
+  else gather_rows_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const float4*)src, map, N, K, C / 4, (__nv_bfloat16*)out);
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;
 }
@@ -63,7 +68,8 @@ extern "C" int gdmae_gather_rows(const float* src, const int32_t* map, int64_t N
 // dsrc[i, c] = sum_k dcol[tmap[i, mirror ? K-1-k : k], k*C + c]   (gather form of the scatter-add:
 // deterministic, no atomics).  For SubM convs tmap is the forward map and mirror = 1
 // (nbr[n,k] = m  <=>  nbr[m,8-k] = n); for strided convs tmap is the "up" map and mirror = 0.
-__global__ void gather_rows_t_kernel(const float4* __restrict__ dcol, const int* __restrict__ tmap, long long N, int K, int C4,
+template <typename T>
+__global__ void gather_rows_t_kernel(const T* __restrict__ dcol, const int* __restrict__ tmap, long long N, int K, int C4,
                                      int mirror, float4* __restrict__ dsrc) {
   long long total = N * C4;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
@@ -73,7 +79,7 @@ __global__ void gather_rows_t_kernel(const float4* __restrict__ dcol, const int*
     for (int k = 0; k < K; ++k) {
       int m = __ldg(tmap + i * K + (mirror ? K - 1 - k : k));
       if (m >= 0) {
-        float4 v = __ldg(dcol + ((long long)m * K + k) * C4 + c);
+        float4 v = Pack4<T>::load(dcol, ((long long)m * K + k) * C4 + c);
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
       }
     }
@@ -81,12 +87,15 @@ __global__ void gather_rows_t_kernel(const float4* __restrict__ dcol, const int*
   }
 }
 
-extern "C" int gdmae_gather_rows_transposed(const float* dcol, const int32_t* tmap, int64_t N, int K, int C, int mirror,
-                                            float* dsrc, void* stream_) {
+// dcol in fp32 (in_dtype 0) or bf16 (1); dsrc fp32
+extern "C" int gdmae_gather_rows_transposed(const void* dcol, int in_dtype, const int32_t* tmap, int64_t N, int K, int C,
+                                            int mirror, float* dsrc, void* stream_) {
   GDMAE_CHECK_ARG(N >= 0 && K > 0 && C > 0 && (C % 4) == 0);
   if (N == 0) return GDMAE_OK;
-  gather_rows_t_kernel<<<gdmae_grid(N * (C / 4), 256, 32), 256, 0, (cudaStream_t)stream_>>>(
-      (const float4*)dcol, tmap, N, K, C / 4, mirror, (float4*)dsrc);
+  int g = gdmae_grid(N * (C / 4), 256, 32);
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (in_dtype == 0) gather_rows_t_kernel<float><<<g, 256, 0, st>>>((const float*)dcol, tmap, N, K, C / 4, mirror, (float4*)dsrc);
+  else gather_rows_t_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)dcol, tmap, N, K, C / 4, mirror, (float4*)dsrc);
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;
 }

@@ -14,25 +14,42 @@
 // rows), softmax is computed online.  HBM traffic = qkv in + o out (+ the L2-resident LUT):
 // N*d*(3+1)*4 + N*8 bytes, the algorithmic minimum of SURVEY.md 8d.
 //
-// Work decomposition (v3): the CSR row order is cut into bins of 32 rows; a CTA owns the windows
-// that START inside its bin (<= 95 rows because a window holds <= 64 tokens) and a 128-channel
-// slice of the embedding (all 8 heads for d=128, 4 of 8 heads for d=256).  Everything a CTA must
-// know about a row (token, window extent, in-window cell) is ONE 16-byte row_info record written
-// by gdmae_window_table, so the bin bounds cost two dependent loads instead of a search.  The
-// "stationary" operands of the bin (k-hat and v for the forward / dq pass, q-hat and dO for the
-// dk,dv pass) are staged ONCE in shared memory with coalesced 128-bit loads (pitch 132 floats so
-// that rows of different windows fall into different banks); every (row, head) pair is then one
-// thread that keeps its own operand in registers and streams its window partners from shared
-// memory - lanes of a warp are consecutive rows, so partners of the same window are a broadcast.
-// No global load sits inside the partner loop.  107 KB of shared memory per CTA -> two CTAs per
-// SM overlap one CTA's staging latency with the other's partner loop.
+// Work decomposition (v4): the CSR row order is cut into bins of SRA_BIN rows; a CTA owns the
+// windows that START inside its bin (<= BIN+63 rows because a window holds <= 64 tokens) and a
+// 128-channel slice of the embedding (all 8 heads for d=128, 4 of 8 heads for d=256).
+// The kernel is organised around its dependent-load chain (r1 ncu: long-scoreboard stalls
+// dominated v3), which is now two round trips deep:
+//   trip 1  one coalesced read of the 16-byte row_info records of rows [bin, bin+BIN+64) - a
+//           superset of the CTA's rows, so the bin bounds need no separate lookup;
+//   trip 2  cp.async (LDGSTS) copies of the raw k / v (or q / dO) rows straight into shared
+//           memory, all in flight at once, while every thread loads its own operand rows
+//           (q, or k and v) into registers;
+//   then    in-place "+LUT, L2-normalise per head" pass over the staged rows, and the partner
+//           loop: each (row, head) pair is one thread that streams its window partners from
+//           shared memory (pitch SLICE+4 floats: rows of different windows hit different banks,
+//           partners of the same window are a broadcast).  No global load inside the loop.
 #include "common.cuh"
 
 #define SRA_EPS 1e-12f
-#define SRA_BIN 32
-#define SRA_ROWS 96           // >= SRA_BIN + 63
-#define SRA_SLICE 128         // channels per CTA
-#define SRA_PITCH 132         // floats per staged row (128 + 4: bank shift of 4 per row)
+// tunables (overridable with -D for tools/bench_sra.py sweeps)
+#ifndef SRA_BIN
+#define SRA_BIN 64            // CSR rows per bin            (r1 sweep, tools/bench_sra.py: 64/64 is the best
+#endif                        //                              of {16,32,64} x {64,128} on all three scales)
+#ifndef SRA_SLICE
+#define SRA_SLICE 64          // channels per CTA
+#endif
+#ifndef SRA_FWD_THREADS
+#define SRA_FWD_THREADS 256
+#endif
+#ifndef SRA_BWD_THREADS
+#define SRA_BWD_THREADS 128
+#endif
+#ifndef SRA_MIN_CTAS
+#define SRA_MIN_CTAS 2
+#endif
+#define SRA_ROWS (SRA_BIN + 64)        // >= SRA_BIN + 63
+#define SRA_C4 (SRA_SLICE / 4)         // float4 per staged row
+#define SRA_PITCH (SRA_SLICE + 4)      // floats per staged row (+4: bank shift of 4 per row)
 #define SRA_SMEM_BYTES (2 * SRA_ROWS * SRA_PITCH * 4 + SRA_ROWS * 16 + 2 * SRA_ROWS * 8 * 4 + 64)
 
 struct SraArgs {
@@ -47,10 +64,9 @@ struct SraArgs {
 struct SraSmem {
   float* a;     // [SRA_ROWS][SRA_PITCH]  k-hat   (fwd, bwd_q)   | q-hat (bwd_kv)
   float* b;     // [SRA_ROWS][SRA_PITCH]  v       (fwd, bwd_q)   | dO    (bwd_kv)
-  int4* info;   // [SRA_ROWS] row_info with the window extent made bin-relative
+  int4* info;   // [SRA_ROWS] raw row_info of rows bin .. bin+SRA_ROWS-1 (absolute row numbers)
   float* lse;   // [SRA_ROWS][8]  (bwd_kv)
   float* D;     // [SRA_ROWS][8]  (bwd_kv)
-  int* hdr;     // [0] row0, [1] R
 };
 
 __device__ __forceinline__ SraSmem sra_carve(unsigned char* base) {
@@ -60,60 +76,70 @@ __device__ __forceinline__ SraSmem sra_carve(unsigned char* base) {
   s.info = (int4*)(s.b + SRA_ROWS * SRA_PITCH);
   s.lse = (float*)(s.info + SRA_ROWS);
   s.D = s.lse + SRA_ROWS * 8;
-  s.hdr = (int*)(s.D + SRA_ROWS * 8);
   return s;
 }
 
-// first window start >= row t (t < N): t itself if row t opens a window, else the end of its window
-__device__ __forceinline__ int sra_first_start(const int4* __restrict__ info, int t, int N) {
-  if (t >= N) return N;
-  int4 r = __ldg(info + t);
-  return r.y == t ? t : r.z;
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
-// Rows of the bin + per-row window extents.  Returns R (0 -> nothing to do).  Ends with __syncthreads.
-__device__ __forceinline__ int sra_bin_setup(const SraArgs& a, const SraSmem& s) {
-  if (threadIdx.x < 2) {
-    int t = (blockIdx.x + threadIdx.x) * SRA_BIN;
-    s.hdr[threadIdx.x] = sra_first_start(a.row_info, t, a.N);
+// Trip 1: records of rows [bin, bin + SRA_ROWS) -> smem; returns the CTA's row range [row0, row0+R)
+// (the windows that start inside the bin).  info is indexed with (absolute row - bin).
+__device__ __forceinline__ void sra_bin_setup(const SraArgs& a, const SraSmem& s, int& row0, int& R) {
+  const int bin = blockIdx.x * SRA_BIN;
+  for (int r = threadIdx.x; r < SRA_ROWS; r += blockDim.x) {
+    int p = bin + r;
+    s.info[r] = p < a.N ? __ldg(a.row_info + p) : make_int4(0, a.N, a.N, 0);
   }
   __syncthreads();
-  int row0 = s.hdr[0], R = s.hdr[1] - row0;
-  for (int r = threadIdx.x; r < R; r += blockDim.x) {
-    int4 v = __ldg(a.row_info + row0 + r);
-    v.y -= row0;
-    v.z -= row0;
-    s.info[r] = v;
+  int4 f = s.info[0];                       // first window start >= bin
+  row0 = (f.y == bin) ? bin : f.z;
+  int p1 = bin + SRA_BIN;                   // first window start >= bin + BIN
+  int row1 = a.N;
+  if (p1 < a.N) {
+    int4 l = s.info[SRA_BIN];
+    row1 = (l.y == p1) ? p1 : l.z;
   }
-  __syncthreads();
-  return R;
+  R = row1 - row0;
 }
 
-// Stage rows [0,R) x 128-channel slice:  dstA = normalise_per_head(srcA[:, colA] + lut[pos, lutcol]) ,
-// dstB = srcB[:, colB].  One float4 per thread per step, a warp covers one row (32 float4 = 128 ch).
+// Trip 2: raw 16-byte pieces of srcA[:, colA] and srcB[:, colB] for rows [row0, row0+R) -> smem (async).
+__device__ __forceinline__ void sra_stage_async(const SraSmem& s, int row0, int R, const float* __restrict__ srcA,
+                                                long long strideA, int colA, const float* __restrict__ srcB, long long strideB,
+                                                int colB) {
+  const int shift = row0 - blockIdx.x * SRA_BIN;
+  for (int idx = threadIdx.x; idx < R * SRA_C4; idx += blockDim.x) {
+    int r = idx / SRA_C4, c4 = idx % SRA_C4;
+    long long tok = s.info[r + shift].x;
+    cp_async16(s.a + r * SRA_PITCH + 4 * c4, srcA + tok * strideA + colA + 4 * c4);
+    cp_async16(s.b + r * SRA_PITCH + 4 * c4, srcB + tok * strideB + colB + 4 * c4);
+  }
+}
+
+// In place: a[r] = normalise_per_head(a[r] + lut[pos(r), lutcol : lutcol + SLICE])
 template <int HD>
-__device__ __forceinline__ void sra_stage(const SraSmem& s, int R, const float* __restrict__ srcA, long long strideA, int colA,
-                                          const float* __restrict__ lut, int lut_stride, int lutcol,
-                                          const float* __restrict__ srcB, long long strideB, int colB) {
+__device__ __forceinline__ void sra_normalise(const SraSmem& s, int row0, int R, const float* __restrict__ lut, int lut_stride,
+                                              int lutcol) {
   constexpr int LPH = HD / 4;  // lanes per head
-  int steps = (R * 32 + blockDim.x - 1) / blockDim.x;
+  const int shift = row0 - blockIdx.x * SRA_BIN;
+  int steps = (R * SRA_C4 + blockDim.x - 1) / blockDim.x;
   for (int it = 0; it < steps; ++it) {
     int idx = it * blockDim.x + threadIdx.x;
-    int r = idx >> 5, c4 = idx & 31;
+    int r = idx / SRA_C4, c4 = idx % SRA_C4;
     bool valid = r < R;
-    int4 inf = s.info[valid ? r : 0];
-    float4 k = __ldg(reinterpret_cast<const float4*>(srcA + (long long)inf.x * strideA + colA) + c4);
-    float4 l = __ldg(reinterpret_cast<const float4*>(lut + inf.w * lut_stride + lutcol) + c4);
-    float4 v = __ldg(reinterpret_cast<const float4*>(srcB + (long long)inf.x * strideB + colB) + c4);
+    int rr = valid ? r : 0;
+    float4 k = *reinterpret_cast<const float4*>(s.a + rr * SRA_PITCH + 4 * c4);
+    float4 l = __ldg(reinterpret_cast<const float4*>(lut + s.info[rr + shift].w * lut_stride + lutcol) + c4);
     k.x += l.x; k.y += l.y; k.z += l.z; k.w += l.w;
     float ss = k.x * k.x + k.y * k.y + k.z * k.z + k.w * k.w;
 #pragma unroll
     for (int o = 1; o < LPH; o <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     float sc = 1.f / fmaxf(sqrtf(ss), SRA_EPS);
-    if (valid) {
-      *reinterpret_cast<float4*>(s.a + r * SRA_PITCH + 4 * c4) = make_float4(k.x * sc, k.y * sc, k.z * sc, k.w * sc);
-      *reinterpret_cast<float4*>(s.b + r * SRA_PITCH + 4 * c4) = v;
-    }
+    if (valid) *reinterpret_cast<float4*>(s.a + r * SRA_PITCH + 4 * c4) = make_float4(k.x * sc, k.y * sc, k.z * sc, k.w * sc);
   }
 }
 
@@ -127,13 +153,12 @@ __device__ __forceinline__ void load_head(const float* __restrict__ p, float* v)
   }
 }
 template <int HD>
-__device__ __forceinline__ void load_head_add(const float* __restrict__ p, const float* __restrict__ q, float* v) {
+__device__ __forceinline__ void add_head(const float* __restrict__ p, float* v) {
   const float4* p4 = reinterpret_cast<const float4*>(p);
-  const float4* q4 = reinterpret_cast<const float4*>(q);
 #pragma unroll
   for (int i = 0; i < HD / 4; ++i) {
-    float4 s = __ldg(p4 + i), t = __ldg(q4 + i);
-    v[4 * i] = s.x + t.x; v[4 * i + 1] = s.y + t.y; v[4 * i + 2] = s.z + t.z; v[4 * i + 3] = s.w + t.w;
+    float4 t = __ldg(p4 + i);
+    v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
   }
 }
 template <int HD>
@@ -172,28 +197,47 @@ __device__ __forceinline__ float dot_reg(const float* a, const float* b) {
 
 // ------------------------------------------------------------------------------ forward
 template <int HD>
-__global__ void __launch_bounds__(256, 2) sra_fwd_kernel(SraArgs a, float* __restrict__ out, float* __restrict__ lse) {
+__global__ void __launch_bounds__(SRA_FWD_THREADS, SRA_MIN_CTAS) sra_fwd_kernel(SraArgs a, float* __restrict__ out,
+                                                                              float* __restrict__ lse) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SraSmem s = sra_carve(smem_raw);
   constexpr int HS = SRA_SLICE / HD;  // heads per slice
   const int d = a.d, col = blockIdx.y * SRA_SLICE;
-  int R = sra_bin_setup(a, s);
+  int row0, R;
+  sra_bin_setup(a, s, row0, R);
   if (R == 0) return;
-  sra_stage<HD>(s, R, a.qkv, 3 * d, d + col, a.lut, 2 * d, d + col, a.qkv, 3 * d, 2 * d + col);
+  const int shift = row0 - blockIdx.x * SRA_BIN;
+  sra_stage_async(s, row0, R, a.qkv, 3 * d, d + col, a.qkv, 3 * d, 2 * d + col);
+  // this thread's first (row, head) pair: q row + LUT row are fetched while the copies fly
+  const int npairs = R * HS;
+  float q[HD];
+  int4 inf = make_int4(0, 0, 0, 0);
+  if ((int)threadIdx.x < npairs) {
+    int r = threadIdx.x % R, h = threadIdx.x / R;
+    inf = s.info[r + shift];
+    load_head<HD>(a.qkv + (long long)inf.x * 3 * d + col + h * HD, q);
+    add_head<HD>(a.lut + inf.w * 2 * d + col + h * HD, q);
+  }
+  const float inv_tau = 1.f / fmaxf(__ldg(a.tau), a.tau_min);
+  cp_async_wait_all();
   __syncthreads();
-  float inv_tau = 1.f / fmaxf(__ldg(a.tau), a.tau_min);
-  for (int p = threadIdx.x; p < R * HS; p += blockDim.x) {
+  sra_normalise<HD>(s, row0, R, a.lut, 2 * d, d + col);
+  __syncthreads();
+  for (int p = threadIdx.x; p < npairs; p += blockDim.x) {
     int r = p % R, h = p / R;
-    int4 inf = s.info[r];
-    float q[HD];
-    load_head_add<HD>(a.qkv + (long long)inf.x * 3 * d + col + h * HD, a.lut + inf.w * 2 * d + col + h * HD, q);
+    if (p != (int)threadIdx.x) {  // later passes: fetch now
+      inf = s.info[r + shift];
+      load_head<HD>(a.qkv + (long long)inf.x * 3 * d + col + h * HD, q);
+      add_head<HD>(a.lut + inf.w * 2 * d + col + h * HD, q);
+    }
     float qs = inv_tau / fmaxf(sqrtf(dot_reg<HD>(q, q)), SRA_EPS);
 #pragma unroll
     for (int i = 0; i < HD; ++i) q[i] *= qs;
     float m = -INFINITY, l = 0.f, o[HD];
 #pragma unroll
     for (int i = 0; i < HD; ++i) o[i] = 0.f;
-    for (int j = inf.y; j < inf.z; ++j) {
+    const int je = inf.z - row0;
+    for (int j = inf.y - row0; j < je; ++j) {
       float sc = dot_smem<HD>(s.a + j * SRA_PITCH + h * HD, q);
       float mn = fmaxf(m, sc);
       float corr = __expf(m - mn);
@@ -215,39 +259,53 @@ __global__ void __launch_bounds__(256, 2) sra_fwd_kernel(SraArgs a, float* __res
 // ------------------------------------------------------------------------------ backward, query side
 // dq_t and D_t = dO_t . O_t ; accumulates sum_ij dS_ij S_ij for the temperature gradient.
 template <int HD>
-__global__ void __launch_bounds__(128, 2) sra_bwd_q_kernel(SraArgs a, const float* __restrict__ out, const float* __restrict__ lse,
-                                                           const float* __restrict__ dout, float* __restrict__ dqkv,
-                                                           float* __restrict__ Dbuf, double* __restrict__ dtau_acc) {
+__global__ void __launch_bounds__(SRA_BWD_THREADS, SRA_MIN_CTAS) sra_bwd_q_kernel(SraArgs a, const float* __restrict__ out,
+                                                                                const float* __restrict__ lse,
+                                                                                const float* __restrict__ dout,
+                                                                                float* __restrict__ dqkv, float* __restrict__ Dbuf,
+                                                                                double* __restrict__ dtau_acc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SraSmem s = sra_carve(smem_raw);
   constexpr int HS = SRA_SLICE / HD;
   const int d = a.d, col = blockIdx.y * SRA_SLICE;
-  int R = sra_bin_setup(a, s);
+  int row0, R;
+  sra_bin_setup(a, s, row0, R);
   if (R == 0) return;
-  sra_stage<HD>(s, R, a.qkv, 3 * d, d + col, a.lut, 2 * d, d + col, a.qkv, 3 * d, 2 * d + col);
-  __syncthreads();
-  float inv_tau = 1.f / fmaxf(__ldg(a.tau), a.tau_min);
-  float tacc = 0.f;
-  for (int p = threadIdx.x; p < R * HS; p += blockDim.x) {
+  const int shift = row0 - blockIdx.x * SRA_BIN;
+  sra_stage_async(s, row0, R, a.qkv, 3 * d, d + col, a.qkv, 3 * d, 2 * d + col);
+  const float inv_tau = 1.f / fmaxf(__ldg(a.tau), a.tau_min);
+  const int npairs = R * HS;
+  float q[HD], dO[HD];
+  float Dt = 0.f, ls = 0.f;
+  int4 inf = make_int4(0, 0, 0, 0);
+  auto fetch = [&](int p) {
     int r = p % R, h = p / R;
-    int4 inf = s.info[r];
-    int hg = blockIdx.y * HS + h;
-    float q[HD], dO[HD], dq[HD];
-    load_head_add<HD>(a.qkv + (long long)inf.x * 3 * d + col + h * HD, a.lut + inf.w * 2 * d + col + h * HD, q);
+    inf = s.info[r + shift];
+    load_head<HD>(a.qkv + (long long)inf.x * 3 * d + col + h * HD, q);
+    add_head<HD>(a.lut + inf.w * 2 * d + col + h * HD, q);
+    load_head<HD>(dout + (long long)inf.x * d + col + h * HD, dO);
+    float o[HD];
+    load_head<HD>(out + (long long)inf.x * d + col + h * HD, o);
+    Dt = dot_reg<HD>(dO, o);
+    ls = lse[(long long)inf.x * 8 + blockIdx.y * HS + h];
+  };
+  if ((int)threadIdx.x < npairs) fetch(threadIdx.x);
+  cp_async_wait_all();
+  __syncthreads();
+  sra_normalise<HD>(s, row0, R, a.lut, 2 * d, d + col);
+  __syncthreads();
+  float tacc = 0.f;
+  for (int p = threadIdx.x; p < npairs; p += blockDim.x) {
+    int h = p / R;
+    if (p != (int)threadIdx.x) fetch(p);
     float iqn = 1.f / fmaxf(sqrtf(dot_reg<HD>(q, q)), SRA_EPS);
 #pragma unroll
     for (int i = 0; i < HD; ++i) q[i] *= iqn;  // q-hat
-    load_head<HD>(dout + (long long)inf.x * d + col + h * HD, dO);
-    float Dt;
-    {
-      float o[HD];
-      load_head<HD>(out + (long long)inf.x * d + col + h * HD, o);
-      Dt = dot_reg<HD>(dO, o);
-    }
-    float ls = lse[(long long)inf.x * 8 + hg];
+    float dq[HD];
 #pragma unroll
     for (int i = 0; i < HD; ++i) dq[i] = 0.f;
-    for (int j = inf.y; j < inf.z; ++j) {
+    const int je = inf.z - row0;
+    for (int j = inf.y - row0; j < je; ++j) {
       const float* kj = s.a + j * SRA_PITCH + h * HD;
       float sc = dot_smem<HD>(kj, q) * inv_tau;
       float dp = dot_smem<HD>(s.b + j * SRA_PITCH + h * HD, dO);
@@ -260,7 +318,7 @@ __global__ void __launch_bounds__(128, 2) sra_bwd_q_kernel(SraArgs a, const floa
 #pragma unroll
     for (int i = 0; i < HD; ++i) dq[i] = (dq[i] - q[i] * proj) * iqn;
     store_head<HD>(dqkv + (long long)inf.x * 3 * d + col + h * HD, dq);
-    Dbuf[(long long)inf.x * 8 + hg] = Dt;
+    Dbuf[(long long)inf.x * 8 + blockIdx.y * HS + h] = Dt;
   }
   tacc = warp_sum(tacc);
   __shared__ float red[8];
@@ -275,34 +333,51 @@ __global__ void __launch_bounds__(128, 2) sra_bwd_q_kernel(SraArgs a, const floa
 
 // ------------------------------------------------------------------------------ backward, key/value side
 template <int HD>
-__global__ void __launch_bounds__(128, 2) sra_bwd_kv_kernel(SraArgs a, const float* __restrict__ lse, const float* __restrict__ dout,
-                                                            const float* __restrict__ Dbuf, float* __restrict__ dqkv) {
+__global__ void __launch_bounds__(SRA_BWD_THREADS, SRA_MIN_CTAS) sra_bwd_kv_kernel(SraArgs a, const float* __restrict__ lse,
+                                                                                 const float* __restrict__ dout,
+                                                                                 const float* __restrict__ Dbuf,
+                                                                                 float* __restrict__ dqkv) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SraSmem s = sra_carve(smem_raw);
   constexpr int HS = SRA_SLICE / HD;
   const int d = a.d, col = blockIdx.y * SRA_SLICE;
-  int R = sra_bin_setup(a, s);
+  int row0, R;
+  sra_bin_setup(a, s, row0, R);
   if (R == 0) return;
-  // stationary operands of this pass: q-hat (normalised, LUT added) and dO
-  sra_stage<HD>(s, R, a.qkv, 3 * d, col, a.lut, 2 * d, col, dout, d, col);
-  for (int i = threadIdx.x; i < R * HS; i += blockDim.x) {
+  const int shift = row0 - blockIdx.x * SRA_BIN;
+  // stationary operands of this pass: q (normalised below) and dO
+  sra_stage_async(s, row0, R, a.qkv, 3 * d, col, dout, d, col);
+  const int npairs = R * HS;
+  for (int i = threadIdx.x; i < npairs; i += blockDim.x) {
     int r = i / HS, h = i % HS;
-    long long g = (long long)s.info[r].x * 8 + blockIdx.y * HS + h;
+    long long g = (long long)s.info[r + shift].x * 8 + blockIdx.y * HS + h;
     s.lse[r * 8 + h] = lse[g];
     s.D[r * 8 + h] = Dbuf[g];
   }
-  __syncthreads();
-  float inv_tau = 1.f / fmaxf(__ldg(a.tau), a.tau_min);
-  for (int p = threadIdx.x; p < R * HS; p += blockDim.x) {
+  const float inv_tau = 1.f / fmaxf(__ldg(a.tau), a.tau_min);
+  float k[HD], v[HD];
+  int4 inf = make_int4(0, 0, 0, 0);
+  auto fetch = [&](int p) {
     int r = p % R, h = p / R;
-    int4 inf = s.info[r];
-    float k[HD], v[HD], dk[HD], dv[HD];
-    load_head_add<HD>(a.qkv + (long long)inf.x * 3 * d + d + col + h * HD, a.lut + inf.w * 2 * d + d + col + h * HD, k);
+    inf = s.info[r + shift];
+    load_head<HD>(a.qkv + (long long)inf.x * 3 * d + d + col + h * HD, k);
+    add_head<HD>(a.lut + inf.w * 2 * d + d + col + h * HD, k);
     load_head<HD>(a.qkv + (long long)inf.x * 3 * d + 2 * d + col + h * HD, v);
+  };
+  if ((int)threadIdx.x < npairs) fetch(threadIdx.x);
+  cp_async_wait_all();
+  __syncthreads();
+  sra_normalise<HD>(s, row0, R, a.lut, 2 * d, col);
+  __syncthreads();
+  for (int p = threadIdx.x; p < npairs; p += blockDim.x) {
+    int h = p / R;
+    if (p != (int)threadIdx.x) fetch(p);
+    float dk[HD], dv[HD];
     float ikn = 1.f / fmaxf(sqrtf(dot_reg<HD>(k, k)), SRA_EPS);
 #pragma unroll
     for (int i = 0; i < HD; ++i) { k[i] *= ikn; dk[i] = 0.f; dv[i] = 0.f; }
-    for (int i = inf.y; i < inf.z; ++i) {
+    const int ie = inf.z - row0;
+    for (int i = inf.y - row0; i < ie; ++i) {
       const float* qi = s.a + i * SRA_PITCH + h * HD;
       const float* doi = s.b + i * SRA_PITCH + h * HD;
       float sc = dot_smem<HD>(qi, k) * inv_tau;
@@ -350,8 +425,8 @@ extern "C" int gdmae_sra_attention_fwd(const float* qkv, const float* lut, const
   cudaStream_t st = (cudaStream_t)stream_;
   dim3 grid(gdmae_div_up(N, SRA_BIN), d / SRA_SLICE);
   if ((rc = sra_smem_attrs())) return rc;
-  if (d == 128) sra_fwd_kernel<16><<<grid, 256, SRA_SMEM_BYTES, st>>>(a, out, lse);
-  else sra_fwd_kernel<32><<<grid, 256, SRA_SMEM_BYTES, st>>>(a, out, lse);
+  if (d == 128) sra_fwd_kernel<16><<<grid, SRA_FWD_THREADS, SRA_SMEM_BYTES, st>>>(a, out, lse);
+  else sra_fwd_kernel<32><<<grid, SRA_FWD_THREADS, SRA_SMEM_BYTES, st>>>(a, out, lse);
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;
 }
@@ -369,13 +444,13 @@ extern "C" int gdmae_sra_attention_bwd(const float* qkv, const float* lut, const
   dim3 grid(gdmae_div_up(N, SRA_BIN), d / SRA_SLICE);
   if ((rc = sra_smem_attrs())) return rc;
   if (d == 128) {
-    sra_bwd_q_kernel<16><<<grid, 128, SRA_SMEM_BYTES, st>>>(a, out, lse, dout, dqkv, work_D, dtau_sum);
+    sra_bwd_q_kernel<16><<<grid, SRA_BWD_THREADS, SRA_SMEM_BYTES, st>>>(a, out, lse, dout, dqkv, work_D, dtau_sum);
     GDMAE_LAUNCH_CHECK();
-    sra_bwd_kv_kernel<16><<<grid, 128, SRA_SMEM_BYTES, st>>>(a, lse, dout, work_D, dqkv);
+    sra_bwd_kv_kernel<16><<<grid, SRA_BWD_THREADS, SRA_SMEM_BYTES, st>>>(a, lse, dout, work_D, dqkv);
   } else {
-    sra_bwd_q_kernel<32><<<grid, 128, SRA_SMEM_BYTES, st>>>(a, out, lse, dout, dqkv, work_D, dtau_sum);
+    sra_bwd_q_kernel<32><<<grid, SRA_BWD_THREADS, SRA_SMEM_BYTES, st>>>(a, out, lse, dout, dqkv, work_D, dtau_sum);
     GDMAE_LAUNCH_CHECK();
-    sra_bwd_kv_kernel<32><<<grid, 128, SRA_SMEM_BYTES, st>>>(a, lse, dout, work_D, dqkv);
+    sra_bwd_kv_kernel<32><<<grid, SRA_BWD_THREADS, SRA_SMEM_BYTES, st>>>(a, lse, dout, work_D, dqkv);
   }
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;

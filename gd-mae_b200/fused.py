@@ -75,6 +75,29 @@ def colsum(x, col0=0, C=None):
 
 sra_fwd, sra_bwd = _ops.sra_fwd, _ops.sra_bwd
 
+# dtype of the cuBLAS GEMM operands of the encoder layers / sparse convs.  torch.float32 = parity
+# (or TF32 when allowed); torch.bfloat16 = bf16 operands, fp32 accumulation and fp32 outputs
+# (config.set_precision('bf16')).  Residual stream, LayerNorm, softmax and gradients stay fp32.
+GEMM_DTYPE = torch.float32
+
+
+def _g(t):
+    """GEMM operand in the configured dtype."""
+    return t if GEMM_DTYPE == torch.float32 else t.to(GEMM_DTYPE)
+
+
+def _mm(a, b):
+    if a.dtype == torch.float32:
+        return torch.mm(a, b)
+    return torch.mm(a, b, out_dtype=torch.float32)
+
+
+def _addmm(c, a, b):
+    """c + a @ b with fp32 output (c fp32: bias row or a full residual matrix)."""
+    if a.dtype == torch.float32:
+        return torch.addmm(c, a, b)
+    return torch.addmm(c, a, b, out_dtype=torch.float32)
+
 
 class EncoderLayerFunction(torch.autograd.Function):
     """x -> LN2( x1 + W2 gelu(W1 x1 + b1) + b2 ),  x1 = LN1( x + Wo SRA(x) + bo )."""
@@ -86,17 +109,21 @@ class EncoderLayerFunction(torch.autograd.Function):
         d = x.shape[1]
         tau_c = tau.reshape(-1).contiguous()
         bias_v = torch.cat([torch.zeros(2 * d, dtype=F32, device=x.device), b_in[2 * d:]])
-        qkv = torch.addmm(bias_v, x, w_in.t())
+        # GEMM operands: fp32 (TF32 when allowed) or bf16 copies with fp32 accumulate/output
+        xg, w_in_g, w_o_g, w1_g, w2_g = _g(x), _g(w_in), _g(w_o), _g(w1), _g(w2)
+        qkv = _addmm(bias_v, xg, w_in_g.t())
         lut = torch.addmm(b_in[:2 * d], pos_table, w_in[:2 * d].t())
         o, lse = sra_fwd(qkv, lut, tau_c, table, tau_min, nhead)
-        a = torch.addmm(b_o, o, w_o.t())
+        og = _g(o)
+        a = _addmm(b_o, og, w_o_g.t())
         x1, mean1, rstd1 = add_layernorm_fwd(x, a, g1, be1)
-        h = torch.mm(x1, w1.t())
-        g = bias_gelu_fwd(h, b1)
-        f = torch.addmm(b2, g, w2.t())
+        x1g = _g(x1)
+        h = _mm(x1g, w1_g.t())
+        g = _g(bias_gelu_fwd(h, b1))
+        f = _addmm(b2, g, w2_g.t())
         x2, mean2, rstd2 = add_layernorm_fwd(x1, f, g2, be2)
-        ctx.save_for_backward(x, pos_table, w_in, b_in, tau_c, w_o, g1, w1, b1, w2, g2, qkv, lut, o, lse, a, x1, mean1, rstd1, h, g,
-                              f, mean2, rstd2)
+        ctx.save_for_backward(x, pos_table, w_in_g, b_in, tau_c, w_o_g, g1, w1_g, b1, w2_g, g2, qkv, lut, o, lse, a, x1, mean1, rstd1,
+                              h, g, f, mean2, rstd2, xg, og, x1g)
         ctx.table, ctx.tau_min, ctx.nhead, ctx.tau_shape = table, tau_min, nhead, tau.shape
         return x2
 
@@ -104,32 +131,34 @@ class EncoderLayerFunction(torch.autograd.Function):
     @_ops._bwd
     def backward(ctx, dx2):
         (x, pos_table, w_in, b_in, tau_c, w_o, g1, w1, b1, w2, g2, qkv, lut, o, lse, a, x1, mean1, rstd1, h, g, f, mean2,
-         rstd2) = ctx.saved_tensors
+         rstd2, xg, og, x1g) = ctx.saved_tensors           # w_*, g, xg, og, x1g are in the GEMM operand dtype
         t = ctx.table
         d = x.shape[1]
         dx2 = dx2.contiguous()
         # ---- LN2 and the feed-forward
         dz2, dg2, dbe2 = add_layernorm_bwd(x1, f, g2, mean2, rstd2, dx2)     # grad wrt f and (residual) x1
         db2 = colsum(dz2)
-        dw2 = torch.mm(dz2.t(), g)
-        dgl = torch.mm(dz2, w2)
+        dz2g = _g(dz2)
+        dw2 = _mm(dz2g.t(), g)
+        dgl = _mm(dz2g, w2)
         dh, db1 = bias_gelu_bwd(h, b1, dgl)
-        dw1 = torch.mm(dh.t(), x1)
-        dx1 = dz2.addmm_(dh, w1)                                             # residual + through linear1 (dz2 no longer needed)
+        dhg = _g(dh)
+        dw1 = _mm(dhg.t(), x1g)
+        dx1 = _addmm(dz2, dhg, w1)                                           # residual + through linear1
         # ---- LN1 and the attention
         dz1, dg1, dbe1 = add_layernorm_bwd(x, a, g1, mean1, rstd1, dx1)      # grad wrt a and (residual) x
         db_o = colsum(dz1)
-        dw_o = torch.mm(dz1.t(), o)
-        do = torch.mm(dz1, w_o)
+        dz1g = _g(dz1)
+        dw_o = _mm(dz1g.t(), og)
+        do = _mm(dz1g, w_o)
         dqkv, dtau_sum = sra_bwd(qkv, lut, tau_c, t, ctx.tau_min, ctx.nhead, o, lse, do)
         # in-projection: q = (x + pos) Wq^T + bq, k likewise, v = x Wv^T + bv
         xpos = pos_table.index_select(0, t.pos_long())
         xpos += x
-        dw_in = torch.empty_like(w_in)
-        torch.mm(dqkv[:, :2 * d].t(), xpos, out=dw_in[:2 * d])
-        torch.mm(dqkv[:, 2 * d:].t(), x, out=dw_in[2 * d:])
+        dqkvg = _g(dqkv)
+        dw_in = torch.cat([_mm(dqkvg[:, :2 * d].t(), _g(xpos)), _mm(dqkvg[:, 2 * d:].t(), xg)])
         db_in = torch.cat([colsum(dqkv, 0, 2 * d), colsum(dqkv, 2 * d, d)])
-        dx = dz1.addmm_(dqkv, w_in)
+        dx = _addmm(dz1, dqkvg, w_in)
         tau_eff = torch.clamp(tau_c, min=ctx.tau_min)
         dtau = torch.where(tau_c >= ctx.tau_min, -(dtau_sum.float() / tau_eff), torch.zeros_like(tau_c)).reshape(ctx.tau_shape)
         return (dx, None, None, None, None, dw_in, db_in, dtau, dw_o, db_o, dg1, dbe1, dw1, db1, dw2, db2, dg2, dbe2)
@@ -142,3 +171,31 @@ def encoder_layer(layer, x, pos_table, table):
                                       at.out_proj.weight, at.out_proj.bias, layer.norm1.weight, layer.norm1.bias,
                                       layer.linear1.weight, layer.linear1.bias, layer.linear2.weight, layer.linear2.bias,
                                       layer.norm2.weight, layer.norm2.bias)
+
+
+class SparseConvFunction(torch.autograd.Function):
+    """3x3 sparse conv as gather -> ONE GEMM (spconv SubMConv2d / SparseConv2d, spconv_utils.py:37-56),
+    manual backward: dW = dy^T col, dcol = dy W, dx = transposed gather (no atomics).  In the bf16
+    configuration the gathered (N, 9*C_in) operand, dy and dcol are bf16 (written directly by the
+    gather kernel / the GEMM), accumulation and outputs are fp32."""
+
+    @staticmethod
+    @_ops._fwd
+    def forward(ctx, x, weight, fwd_map, bwd_map, mirror):
+        x = x.contiguous()
+        w = _g(weight.view(weight.shape[0], -1))            # (C_out, 9*C_in)
+        col = _ops.gather_rows(x, fwd_map, GEMM_DTYPE)
+        y = _mm(col, w.t())
+        ctx.save_for_backward(col, w, bwd_map)
+        ctx.mirror, ctx.n_src, ctx.wshape = mirror, x.shape[0], weight.shape
+        return y
+
+    @staticmethod
+    @_ops._bwd
+    def backward(ctx, dy):
+        col, w, bwd_map = ctx.saved_tensors
+        dyg = _g(dy.contiguous())
+        dw = _mm(dyg.t(), col).view(ctx.wshape)
+        dcol = torch.mm(dyg, w)                              # operand dtype (bf16 in the bf16 configuration)
+        dx = _ops.gather_rows_transposed(dcol, bwd_map, ctx.n_src, ctx.mirror)
+        return dx, dw, None, None, None

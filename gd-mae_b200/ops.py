@@ -264,6 +264,10 @@ def window_table(indices, B, H, W, shifted):
     return t
 
 
+# False: fp32 SIMT kernel (parity configuration).  True: TF32 tensor-core kernel (bf16/tf32 configuration).
+SRA_TENSOR_CORES = False
+
+
 def sra_fwd(qkv, lut, tau, table, tau_min, nhead):
     """raw launch: -> (out (N,d), lse (N,nhead))"""
     N, d3 = qkv.shape
@@ -271,9 +275,10 @@ def sra_fwd(qkv, lut, tau, table, tau_min, nhead):
     out = torch.empty((N, d), dtype=F32, device=qkv.device)
     lse = torch.empty((N, nhead), dtype=F32, device=qkv.device)
     # algorithmic bytes (SURVEY.md 8d, a18 minus projections): N*d*(3*s_in + s_out) + N*8
+    fn = L.lib().gdmae_sra_attention_fwd_tc if SRA_TENSOR_CORES else L.lib().gdmae_sra_attention_fwd
     with L.timed(f"sra_fwd_d{d}", N * d * 16 + N * 8):
-        L.check(L.lib().gdmae_sra_attention_fwd(L.P(qkv), L.P(lut), L.P(table.row_info), L.i64(N), d, nhead, L.P(tau),
-                                                L.f32(tau_min), L.P(out), L.P(lse), L.stream()), "gdmae_sra_attention_fwd")
+        L.check(fn(L.P(qkv), L.P(lut), L.P(table.row_info), L.i64(N), d, nhead, L.P(tau), L.f32(tau_min), L.P(out), L.P(lse),
+                   L.stream()), "gdmae_sra_attention_fwd")
     return out, lse
 
 
@@ -299,24 +304,35 @@ class GatherRows(torch.autograd.Function):
     @staticmethod
     @_fwd
     def forward(ctx, x, fwd_map, bwd_map, mirror):
-        x = x.contiguous()
-        N, K = fwd_map.shape
-        C = x.shape[1]
-        col = torch.empty((N, K * C), dtype=F32, device=_dev(x))
-        L.check(L.lib().gdmae_gather_rows(L.P(x), L.P(fwd_map), L.i64(N), K, C, L.P(col), L.stream()), "gdmae_gather_rows")
+        col = gather_rows(x.contiguous(), fwd_map, F32)
         ctx.save_for_backward(bwd_map)
-        ctx.mirror, ctx.n_src, ctx.C, ctx.K = mirror, x.shape[0], C, K
+        ctx.mirror, ctx.n_src = mirror, x.shape[0]
         return col
 
     @staticmethod
     @_bwd
     def backward(ctx, dcol):
         (bwd_map,) = ctx.saved_tensors
-        dcol = dcol.contiguous()
-        dx = torch.empty((ctx.n_src, ctx.C), dtype=F32, device=dcol.device)
-        L.check(L.lib().gdmae_gather_rows_transposed(L.P(dcol), L.P(bwd_map), L.i64(ctx.n_src), ctx.K, ctx.C,
-                                                     int(ctx.mirror), L.P(dx), L.stream()), "gdmae_gather_rows_transposed")
-        return dx, None, None, None
+        return gather_rows_transposed(dcol.contiguous(), bwd_map, ctx.n_src, ctx.mirror), None, None, None
+
+
+def gather_rows(x, fwd_map, out_dtype):
+    """col (N, K*C) = rows of x through the neighbour map (0 where empty), fp32 or bf16."""
+    N, K = fwd_map.shape
+    C = x.shape[1]
+    col = torch.empty((N, K * C), dtype=out_dtype, device=_dev(x))
+    L.check(L.lib().gdmae_gather_rows(L.P(x), L.P(fwd_map), L.i64(N), K, C, L.P(col), _DT[out_dtype], L.stream()),
+            "gdmae_gather_rows")
+    return col
+
+
+def gather_rows_transposed(dcol, bwd_map, n_src, mirror):
+    K = bwd_map.shape[1]
+    C = dcol.shape[1] // K
+    dx = torch.empty((n_src, C), dtype=F32, device=dcol.device)
+    L.check(L.lib().gdmae_gather_rows_transposed(L.P(dcol), _DT[dcol.dtype], L.P(bwd_map), L.i64(n_src), K, C, int(mirror), L.P(dx),
+                                                 L.stream()), "gdmae_gather_rows_transposed")
+    return dx
 
 
 # ----------------------------------------------------------------------------- SRA attention core

@@ -98,14 +98,13 @@ class SparseConvolution(SparseModule):
         nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
 
     def forward(self, x):
-        w = self.weight.view(self.out_channels, 9 * self.in_channels)
+        from ... import fused as _fused
         if self.subm:
             nbr = x.subm_map()
-            col = _ops.GatherRows.apply(x.features, nbr, nbr, True)
-            return x.replace_feature(F.linear(col, w))
+            return x.replace_feature(_fused.SparseConvFunction.apply(x.features, self.weight, nbr, nbr, True))
         d = x.down()
-        col = _ops.GatherRows.apply(x.features, d.nbr_down, d.nbr_up, False)
-        return SparseConvTensor(F.linear(col, w), d.indices, d.spatial_shape, x.batch_size, d.struct)
+        y = _fused.SparseConvFunction.apply(x.features, self.weight, d.nbr_down, d.nbr_up, False)
+        return SparseConvTensor(y, d.indices, d.spatial_shape, x.batch_size, d.struct)
 
 
 class SubMConv2d(SparseConvolution):

@@ -109,10 +109,11 @@ int gdmae_down_neighbor_maps(const int32_t* in_indices, int64_t N, const int32_t
                              const int32_t* out_indices, int64_t No, const int32_t* out_rank_grid,
                              int32_t* out_nbr_down, int32_t* out_nbr_up, void* stream);
 /* out (N, K*C) = rows of src (.., C) gathered through map (N, K); 0 where map < 0 */
-int gdmae_gather_rows(const float* src, const int32_t* map, int64_t N, int K, int C, float* out, void* stream);
-/* dsrc (N, C) = sum_k dcol[tmap[i, mirror ? K-1-k : k], k*C:(k+1)*C] */
-int gdmae_gather_rows_transposed(const float* dcol, const int32_t* tmap, int64_t N, int K, int C, int mirror,
-                                 float* dsrc, void* stream);
+int gdmae_gather_rows(const float* src, const int32_t* map, int64_t N, int K, int C, void* out,
+                      int out_dtype /* 0 fp32, 1 bf16 */, void* stream);
+/* dsrc (N, C) = sum_k dcol[tmap[i, mirror ? K-1-k : k], k*C:(k+1)*C]; dcol fp32 (0) or bf16 (1) */
+int gdmae_gather_rows_transposed(const void* dcol, int in_dtype, const int32_t* tmap, int64_t N, int K, int C,
+                                 int mirror, float* dsrc, void* stream);
 
 /* ---- a10-a16 window tables -------------------------------------------------------------------
  * replaces sst_utils.get_window_coors (pcdet/models/model_utils/sst_utils.py:6-47),
@@ -135,6 +136,9 @@ int gdmae_window_table(const int32_t* indices, int64_t N, int B, int H, int W, i
  * out (N, d) pre out-proj; lse (N, 8).  nhead == 8, d in {128, 256}. */
 int gdmae_sra_attention_fwd(const float* qkv, const float* lut, const int32_t* row_info, int64_t N, int d, int nhead,
                             const float* tau, float tau_min, float* out, float* lse, void* stream);
+/* same operator, QK^T and PV on the tensor cores (TF32 mma, fp32 accumulate, softmax in fp32) */
+int gdmae_sra_attention_fwd_tc(const float* qkv, const float* lut, const int32_t* row_info, int64_t N, int d, int nhead,
+                               const float* tau, float tau_min, float* out, float* lse, void* stream);
 int gdmae_sra_attention_bwd(const float* qkv, const float* lut, const int32_t* row_info, int64_t N, int d, int nhead,
                             const float* tau, float tau_min, const float* out, const float* lse, const float* dout,
                             float* dqkv, double* dtau_sum, float* work_D, void* stream);

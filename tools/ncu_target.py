@@ -19,11 +19,9 @@ ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--batch", type=int, default=8)
 ap.add_argument("--dtype", default="bf16")
 args = ap.parse_args()
-torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = args.dtype != "fp32"
 cfg = config.builtin_cfg("waymo_ssl")
 model = config.build_mae_model(cfg).cuda()
-if args.dtype == "bf16":
-    model.backbone_3d.decoder_dtype = torch.bfloat16
+config.set_precision(model, args.dtype)
 trainer = MAETrainer(model, cfg.OPTIMIZATION, total_steps=100)
 pts = torch.from_numpy(O.synth_batch(list(range(args.batch)), O.make_cfg("waymo_ssl"))).cuda()
 for _ in range(args.steps):

@@ -19,15 +19,13 @@ ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--batch", type=int, default=8)
 args = ap.parse_args()
 torch.backends.cudnn.benchmark = True
-torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = args.dtype != "fp32"
 cfg = config.builtin_cfg("waymo_ssl")
 model = config.build_mae_model(cfg).cuda()
 trainer = MAETrainer(model, cfg.OPTIMIZATION, total_steps=100)
 pts = torch.from_numpy(O.synth_batch(list(range(args.batch)), O.make_cfg("waymo_ssl"))).cuda()
 import contextlib  # noqa: E402
 ac = contextlib.nullcontext()
-if args.dtype == "bf16":
-    model.backbone_3d.decoder_dtype = torch.bfloat16
+config.set_precision(model, args.dtype)
 for _ in range(4):
     with ac:
         trainer.step({"points": pts, "batch_size": args.batch})
