@@ -199,3 +199,66 @@ class SparseConvFunction(torch.autograd.Function):
         dcol = torch.mm(dyg, w)                              # operand dtype (bf16 in the bf16 configuration)
         dx = _ops.gather_rows_transposed(dcol, bwd_map, ctx.n_src, ctx.mirror)
         return dx, dw, None, None, None
+
+
+class BatchNormReLUFunction(torch.autograd.Function):
+    """Training-mode BatchNorm over the rows of (N, C) + ReLU, statistics over ``count`` >= N rows (the
+    missing rows are zeros: the empty cells of the decoder's dense map).  Returns (out, bg) where
+    bg (C) = relu(BN(0)) is the value every missing row would take.  Running buffers are updated in
+    the kernel.  Two passes forward, two backward (csrc/batchnorm.cu)."""
+
+    @staticmethod
+    @_ops._fwd
+    def forward(ctx, y, gamma, beta, running_mean, running_var, momentum, eps, count, relu):
+        y = y.contiguous()
+        N, C = y.shape
+        dev = y.device
+        out = torch.empty_like(y)
+        mean = torch.empty((C,), dtype=F32, device=dev)
+        rstd = torch.empty((C,), dtype=F32, device=dev)
+        lib = L.lib()
+        ws = L.workspace(lib.gdmae_batchnorm_workspace_bytes(C), dev)
+        L.check(lib.gdmae_batchnorm_relu_fwd(L.P(y), L.P(gamma), L.P(beta), L.i64(N), C, ctypes.c_double(count), L.f32(eps),
+                                             L.f32(momentum), int(relu), L.P(out), L.P(mean), L.P(rstd), L.P(running_mean),
+                                             L.P(running_var), L.P(ws), ctypes.c_size_t(ws.numel()), L.stream()),
+                "gdmae_batchnorm_relu_fwd")
+        shift = beta - mean * rstd * gamma
+        bg = torch.relu(shift) if relu else shift
+        ctx.save_for_backward(y, out, gamma, mean, rstd, shift)
+        ctx.count, ctx.relu = count, relu
+        return out, bg
+
+    @staticmethod
+    @_ops._bwd
+    def backward(ctx, dout, dbg):
+        y, out, gamma, mean, rstd, shift = ctx.saved_tensors
+        N, C = y.shape
+        dev = y.device
+        e_db = e_dg = None
+        if ctx.count > N and dbg is not None:
+            e_db = (dbg * (shift > 0)) if ctx.relu else dbg
+            e_db = e_db.contiguous().float()
+            e_dg = (e_db * (-mean * rstd)).contiguous()
+        dy = torch.empty_like(y)
+        dgamma = torch.empty((C,), dtype=F32, device=dev)
+        dbeta = torch.empty((C,), dtype=F32, device=dev)
+        lib = L.lib()
+        ws = L.workspace(lib.gdmae_batchnorm_workspace_bytes(C), dev)
+        L.check(lib.gdmae_batchnorm_relu_bwd(L.P(y), L.P(out), L.P(dout.contiguous()), L.P(gamma), L.P(mean), L.P(rstd), L.i64(N), C,
+                                             ctypes.c_double(ctx.count), int(ctx.relu), L.P(e_db), L.P(e_dg), L.P(dy), L.P(dgamma),
+                                             L.P(dbeta), L.P(ws), ctypes.c_size_t(ws.numel()), L.stream()),
+                "gdmae_batchnorm_relu_bwd")
+        return dy, dgamma, dbeta, None, None, None, None, None, None
+
+
+def batchnorm_relu(bn, y, training, relu=True, count=None):
+    """BatchNorm1d/2d module ``bn`` (+ ReLU) applied to the rows of y (N, C); -> (out, bg)."""
+    if not training:
+        scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+        shift = bn.bias - bn.running_mean * scale
+        out = y * scale + shift
+        return (torch.relu(out), torch.relu(shift)) if relu else (out, shift)
+    out, bg = BatchNormReLUFunction.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps,
+                                          float(y.shape[0] if count is None else count), relu)
+    bn.num_batches_tracked += 1
+    return out, bg

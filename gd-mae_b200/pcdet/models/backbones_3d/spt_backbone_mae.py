@@ -10,6 +10,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .... import fused as _fused
 from .... import ops as _ops
 from ...utils.spconv_utils import spconv, plan_pyramid
 from .spt_backbone import SSTBlockV1
@@ -88,19 +89,8 @@ class SPTBackboneMAE(nn.Module):
         c_out = deconv.out_channels
         w = deconv.weight.permute(0, 2, 3, 1).reshape(deconv.in_channels, k * k * c_out)  # (C_in, [a, b, c_out])
         u = (sp.features @ w).view(-1, c_out)                                                 # (N*k*k, c_out)
-        n_act = u.shape[0]
-        mean = u.sum(0) / n_cells_total
-        var = ((u - mean) ** 2).sum(0) / n_cells_total + (float(n_cells_total - n_act) / n_cells_total) * mean ** 2
-        if self.training:
-            with torch.no_grad():
-                bn.running_mean.mul_(1 - bn.momentum).add_(bn.momentum * mean)
-                bn.running_var.mul_(1 - bn.momentum).add_(bn.momentum * var * (n_cells_total / max(n_cells_total - 1, 1)))
-                bn.num_batches_tracked += 1
-        else:
-            mean, var = bn.running_mean, bn.running_var
-        scale = bn.weight * torch.rsqrt(var + bn.eps)
-        shift = bn.bias - mean * scale
-        return F.relu(u * scale + shift), F.relu(shift)
+        # fused BN(batch statistics over all B*Y*X cells, zeros included)+ReLU on the sparse rows; bg = value of an empty cell
+        return _fused.batchnorm_relu(bn, u, self.training, relu=True, count=n_cells_total)
 
     def forward(self, batch_dict):
         all_voxel_features, all_voxel_coords = batch_dict['voxel_features'], batch_dict['voxel_coords']

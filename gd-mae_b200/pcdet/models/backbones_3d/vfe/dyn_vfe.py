@@ -8,6 +8,7 @@ from functools import partial
 import torch
 import torch.nn as nn
 
+from ..... import fused as _fused
 from ..... import ops as _ops
 from ...model_utils.network_utils import make_fc_layers
 
@@ -48,7 +49,9 @@ class DynVFE(VFETemplate):
         mean = _ops.segment_mean(ps.points, 1, n_feat, ps.seg_offsets, ps.seg_points, ps.n_pillars)
         x = _ops.vfe_point_features(ps, mean, self.point_cloud_range, self.voxel_size)
         with torch.autocast("cuda", enabled=False):  # absolute coordinates (|x| up to 75 m) stay fp32
-            x = self.dvfe_mlps[0](x)  # Linear -> BN1d(train: batch statistics) -> ReLU, twice (cuBLAS / ATen)
+            mlp = self.dvfe_mlps[0]                   # Linear (cuBLAS) -> fused BN1d(batch statistics)+ReLU, twice
+            for k in range(0, len(mlp), 3):
+                x = _fused.batchnorm_relu(mlp[k + 1], mlp[k](x), self.training and mlp[k + 1].training)[0]
         x = _ops.SegmentMax.apply(x, ps.seg_offsets, ps.seg_points, ps.n_pillars)
 
         batch_dict['points'] = ps.points

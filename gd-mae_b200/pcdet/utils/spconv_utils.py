@@ -119,8 +119,21 @@ class SparseConv2d(SparseConvolution):
 
 class SparseSequential(nn.Sequential):
     def forward(self, x):
-        for m in self:
-            x = m(x) if isinstance(m, SparseModule) else x.replace_feature(m(x.features))
+        from ... import fused as _fused
+        mods = list(self)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, SparseModule):
+                x = m(x)
+            elif (isinstance(m, nn.BatchNorm1d) and i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU) and x.features.is_cuda
+                  and m.track_running_stats):
+                # BatchNorm1d(train: batch statistics) + ReLU as one fused kernel pair (csrc/batchnorm.cu)
+                x = x.replace_feature(_fused.batchnorm_relu(m, x.features, self.training and m.training)[0])
+                i += 1
+            else:
+                x = x.replace_feature(m(x.features))
+            i += 1
         return x
 
 

@@ -160,6 +160,20 @@ int gdmae_bias_gelu_bwd(const float* h, const float* bias, const float* dg, int6
 int gdmae_colsum(const float* x, int64_t N, int ld, int col0, int C, float* out, int accumulate, void* workspace,
                  size_t ws_bytes, void* stream);
 
+/* ---- a5/a9/a21/a22 training-mode BatchNorm (+ReLU) over (N, C) rows ------------------------------
+ * replaces norm_fn + nn.ReLU of post_act_block (pcdet/utils/spconv_utils.py:50-54), of make_fc_layers
+ * (pcdet/models/model_utils/network_utils.py:7-21) and BatchNorm2d + ReLU of the decoder deblocks evaluated
+ * on their sparse rows (spt_backbone_mae.py:31-43).  `count` >= N rows enter the statistics (missing rows
+ * are zeros); running buffers (nullable) get the momentum / unbiased-variance update. */
+size_t gdmae_batchnorm_workspace_bytes(int C);
+int gdmae_batchnorm_relu_fwd(const float* y, const float* gamma, const float* beta, int64_t N, int C, double count,
+                             float eps, float momentum, int relu, float* out, float* mean, float* rstd,
+                             float* running_mean, float* running_var, void* workspace, size_t ws_bytes, void* stream);
+int gdmae_batchnorm_relu_bwd(const float* y, const float* out, const float* dout, const float* gamma, const float* mean,
+                             const float* rstd, int64_t N, int C, double count, int relu, const float* extra_dbeta,
+                             const float* extra_dgamma, float* dy, float* dgamma, float* dbeta, void* workspace,
+                             size_t ws_bytes, void* stream);
+
 /* ---- a22/a23 decoder dense fill and pillar gather --------------------------------------------
  * replaces SparseConvTensor.dense() + ConvTranspose2d(k=s) + BatchNorm2d + ReLU + torch.cat
  * (spt_backbone_mae.py:125-132) once the per-site GEMM/BN is done on the sparse rows, and the
