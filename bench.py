@@ -262,7 +262,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames_per_gpu": B_PER_GPU, "global_batch": frames, "points_per_batch": pts_per_batch,
-                   "grid": "468x468x1", "parallelism": f"dp{world}", "params": trainer.n_all,
+                   "grid": "468x468x1", "parallelism": f"dp{world}", "params": trainer.n_params,
                    "l2": "per-step working set (>2 GB of activations) exceeds the 126 MB L2; input batch changes every step"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(pts_per_batch * 6 * 4), "d2h_bytes_per_step": 4 + 2 * 4 * (4 + B_PER_GPU + 1)},

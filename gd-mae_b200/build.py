@@ -39,7 +39,9 @@ def build(force=False, verbose=False):
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
     if force or _stale(LIB, objs):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        # cuBLAS (plain library GEMMs, csrc/gemm.cu); at run time the libcublas.so.12 torch already loaded is reused
+        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcublasLt",
+                                                     "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
         if verbose:
             print(" ".join(cmd))
         subprocess.run(cmd, check=True)

@@ -112,7 +112,7 @@ def build_mae_model(cfg):
     return build_network(cfg.MODEL, len(ds.class_names), ds)
 
 
-def set_precision(model, dtype, matmul="high", gemm_bf16=False):
+def set_precision(model, dtype, matmul="high", gemm_bf16=True):
     """One switch for the numeric configuration of the step.
     'fp32' : parity configuration - fp32 everywhere, TF32 off, fp32 SIMT attention.
     'tf32' : TF32 GEMMs/conv, TF32 tensor-core attention, fp32 decoder map.
@@ -127,9 +127,9 @@ def set_precision(model, dtype, matmul="high", gemm_bf16=False):
     torch.set_float32_matmul_precision(matmul if fast else "highest")
     from . import fused
     ops.SRA_TENSOR_CORES = False  # r1: the TF32 mma variant is not faster than the fp32 kernel (tools/bench_sra.py)
-    # r1 measurement: bf16 operand copies + torch.mm(out_dtype=fp32) cut GEMM GPU time 14 -> 9 ms/step but
-    # triple the host time per GEMM call (cublasLt path), making the step host-bound (57 vs 53.6 ms);
-    # the encoder / sparse-conv GEMMs therefore stay TF32 until activations are bf16 end to end.
+    # bf16 GEMM operands are written by the hand-written kernels themselves (no cast passes) and the GEMMs go
+    # through gdmae_gemm (cublasGemmEx bf16 x bf16 -> fp32); torch.mm(out_dtype=fp32) was measured to triple the
+    # host time per call (cublasLt path) and is not used.
     fused.GEMM_DTYPE = torch.bfloat16 if (dtype == "bf16" and gemm_bf16) else torch.float32
     model.backbone_3d.decoder_dtype = torch.bfloat16 if dtype == "bf16" else torch.float32
     return model

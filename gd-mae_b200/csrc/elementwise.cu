@@ -1,29 +1,52 @@
-// Fused row-wise kernels of the SRA encoder layer: residual + LayerNorm (fwd/bwd), bias + exact
-// GELU (fwd/bwd) and column sums (bias gradients).  All HBM-bound, 128-bit accesses, one warp per
-// token row, parameter gradients reduced deterministically in two stages (per-CTA partials, then a
-// fixed-order final sum) instead of float atomics.
+// Fused row-wise kernels of the SRA encoder layer: residual (+bias) + LayerNorm (fwd/bwd), bias +
+// exact GELU (fwd/bwd), column sums (bias gradients) and the positional gather-add.  All HBM-bound,
+// 128-bit accesses, one warp per token row, parameter gradients reduced deterministically in two
+// stages (per-CTA partials, then a fixed-order final sum) instead of float atomics.  Every kernel
+// can additionally (or instead) emit its result as bf16: those copies are the operands of the
+// cuBLAS GEMMs in the bf16 configuration, so no separate cast pass exists.
 //
 // Replaces (reference file:line, relative to /root/reference):
 //   src = norm1(src + src2); src = norm2(src + src2)        pcdet/models/model_utils/sst_basic_block.py:79-83
 //   activation(linear1(src)) with activation = F.gelu (erf)   pcdet/models/model_utils/sst_basic_block.py:81,117-125
+//   q = k = feat_3d + pos                                     pcdet/models/model_utils/sst_basic_block.py:39-46
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 #define EW_PART_BLOCKS (GDMAE_NUM_SMS * 2)
 
-// ------------------------------------------------------------------ y = LayerNorm(x + res)
-// VEC = d / 128 float4 per lane (d = 128 -> 1, d = 256 -> 2)
+__device__ __forceinline__ void store_bf16x4(__nv_bfloat16* p, long long i4, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<unsigned int*>(&a);
+  u.y = *reinterpret_cast<unsigned int*>(&b);
+  reinterpret_cast<uint2*>(p)[i4] = u;
+}
+__device__ __forceinline__ float4 load_bf16x4(const __nv_bfloat16* p, long long i4) {
+  uint2 u = __ldg(reinterpret_cast<const uint2*>(p) + i4);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&u.x), b = *reinterpret_cast<__nv_bfloat162*>(&u.y);
+  float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+
+// ------------------------------------------------------------------ y = LayerNorm(x + res + bias)
+// VEC = d / 128 float4 per lane (d = 128 -> 1, d = 256 -> 2); bias, y_bf16 nullable
 template <int VEC>
 __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ res,
-                                                         const float4* __restrict__ gamma, const float4* __restrict__ beta,
-                                                         long long N, float eps, float4* __restrict__ y,
+                                                         const float4* __restrict__ bias, const float4* __restrict__ gamma,
+                                                         const float4* __restrict__ beta, long long N, float eps,
+                                                         float4* __restrict__ y, __nv_bfloat16* __restrict__ y_bf16,
                                                          float* __restrict__ mean_out, float* __restrict__ rstd_out) {
   constexpr int D = VEC * 128;
   int lane = threadIdx.x & 31;
   long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  float4 g[VEC], b[VEC];
+  float4 g[VEC], b[VEC], bi[VEC];
 #pragma unroll
-  for (int v = 0; v < VEC; ++v) { g[v] = __ldg(gamma + v * 32 + lane); b[v] = __ldg(beta + v * 32 + lane); }
+  for (int v = 0; v < VEC; ++v) {
+    g[v] = __ldg(gamma + v * 32 + lane);
+    b[v] = __ldg(beta + v * 32 + lane);
+    bi[v] = bias ? __ldg(bias + v * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   for (long long row = warp; row < N; row += nwarps) {
     float4 z[VEC];
     float s = 0.f;
@@ -31,7 +54,7 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const float4* __restric
     for (int v = 0; v < VEC; ++v) {
       float4 a = __ldg(x + row * (D / 4) + v * 32 + lane);
       float4 r = __ldg(res + row * (D / 4) + v * 32 + lane);
-      z[v] = make_float4(a.x + r.x, a.y + r.y, a.z + r.z, a.w + r.w);
+      z[v] = make_float4(a.x + r.x + bi[v].x, a.y + r.y + bi[v].y, a.z + r.z + bi[v].z, a.w + r.w + bi[v].w);
       s += z[v].x + z[v].y + z[v].z + z[v].w;
     }
     float mean = warp_sum(s) * (1.f / D);
@@ -50,6 +73,7 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const float4* __restric
       o.z = (z[v].z - mean) * rstd * g[v].z + b[v].z;
       o.w = (z[v].w - mean) * rstd * g[v].w + b[v].w;
       y[row * (D / 4) + v * 32 + lane] = o;
+      if (y_bf16) store_bf16x4(y_bf16, row * (D / 4) + v * 32 + lane, o);
     }
     if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
   }
@@ -58,17 +82,19 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const float4* __restric
 // dz = rstd * (dy*gamma - mean(dy*gamma) - xhat * mean(dy*gamma*xhat));  partial dgamma/dbeta per CTA
 template <int VEC>
 __global__ void __launch_bounds__(256) add_ln_bwd_kernel(const float4* __restrict__ x, const float4* __restrict__ res,
-                                                         const float4* __restrict__ gamma, const float* __restrict__ mean_in,
-                                                         const float* __restrict__ rstd_in, const float4* __restrict__ dy,
-                                                         long long N, float4* __restrict__ dz, float* __restrict__ partial) {
+                                                         const float4* __restrict__ bias, const float4* __restrict__ gamma,
+                                                         const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                                                         const float4* __restrict__ dy, long long N, float4* __restrict__ dz,
+                                                         __nv_bfloat16* __restrict__ dz_bf16, float* __restrict__ partial) {
   constexpr int D = VEC * 128;
   int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  float4 g[VEC], dg[VEC], db[VEC];
+  float4 g[VEC], dg[VEC], db[VEC], bi[VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) {
     g[v] = __ldg(gamma + v * 32 + lane);
+    bi[v] = bias ? __ldg(bias + v * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
     dg[v] = make_float4(0.f, 0.f, 0.f, 0.f);
     db[v] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
@@ -81,7 +107,8 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(const float4* __restric
       float4 a = __ldg(x + row * (D / 4) + v * 32 + lane);
       float4 r = __ldg(res + row * (D / 4) + v * 32 + lane);
       float4 d = __ldg(dy + row * (D / 4) + v * 32 + lane);
-      xh[v] = make_float4((a.x + r.x - mean) * rstd, (a.y + r.y - mean) * rstd, (a.z + r.z - mean) * rstd, (a.w + r.w - mean) * rstd);
+      xh[v] = make_float4((a.x + r.x + bi[v].x - mean) * rstd, (a.y + r.y + bi[v].y - mean) * rstd,
+                          (a.z + r.z + bi[v].z - mean) * rstd, (a.w + r.w + bi[v].w - mean) * rstd);
       dxh[v] = make_float4(d.x * g[v].x, d.y * g[v].y, d.z * g[v].z, d.w * g[v].w);
       c1 += dxh[v].x + dxh[v].y + dxh[v].z + dxh[v].w;
       c2 += dxh[v].x * xh[v].x + dxh[v].y * xh[v].y + dxh[v].z * xh[v].z + dxh[v].w * xh[v].w;
@@ -98,6 +125,7 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(const float4* __restric
       o.z = rstd * (dxh[v].z - c1 - xh[v].z * c2);
       o.w = rstd * (dxh[v].w - c1 - xh[v].w * c2);
       dz[row * (D / 4) + v * 32 + lane] = o;
+      if (dz_bf16) store_bf16x4(dz_bf16, row * (D / 4) + v * 32 + lane, o);
     }
   }
   // CTA reduction over its 8 warps (fixed order), then one partial row [dgamma(D) | dbeta(D)] per CTA
@@ -146,31 +174,43 @@ static int ew_grid(long long rows) {
   return (int)(need < EW_PART_BLOCKS ? (need < 1 ? 1 : need) : EW_PART_BLOCKS);
 }
 
-// y = LayerNorm(x + res) * gamma + beta over rows of d in {128, 256}; mean/rstd (N) saved for backward.
-extern "C" int gdmae_add_layernorm_fwd(const float* x, const float* res, const float* gamma, const float* beta, int64_t N, int d,
-                                       float eps, float* y, float* mean, float* rstd, void* stream_) {
+// y = LayerNorm(x + res + bias) * gamma + beta over rows of d in {128, 256}; bias (d) and y_bf16 (N,d) may be
+// NULL; mean/rstd (N) saved for backward.
+extern "C" int gdmae_add_layernorm_fwd(const float* x, const float* res, const float* bias, const float* gamma, const float* beta,
+                                       int64_t N, int d, float eps, float* y, void* y_bf16, float* mean, float* rstd,
+                                       void* stream_) {
   GDMAE_CHECK_ARG(N >= 0 && (d == 128 || d == 256));
   if (N == 0) return GDMAE_OK;
   cudaStream_t st = (cudaStream_t)stream_;
   int grid = gdmae_grid(N * 32, 256, 8);
-  if (d == 128) add_ln_fwd_kernel<1><<<grid, 256, 0, st>>>((const float4*)x, (const float4*)res, (const float4*)gamma, (const float4*)beta, N, eps, (float4*)y, mean, rstd);
-  else add_ln_fwd_kernel<2><<<grid, 256, 0, st>>>((const float4*)x, (const float4*)res, (const float4*)gamma, (const float4*)beta, N, eps, (float4*)y, mean, rstd);
+  if (d == 128)
+    add_ln_fwd_kernel<1><<<grid, 256, 0, st>>>((const float4*)x, (const float4*)res, (const float4*)bias, (const float4*)gamma,
+                                               (const float4*)beta, N, eps, (float4*)y, (__nv_bfloat16*)y_bf16, mean, rstd);
+  else
+    add_ln_fwd_kernel<2><<<grid, 256, 0, st>>>((const float4*)x, (const float4*)res, (const float4*)bias, (const float4*)gamma,
+                                               (const float4*)beta, N, eps, (float4*)y, (__nv_bfloat16*)y_bf16, mean, rstd);
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;
 }
 
-// dz (N,d) = gradient w.r.t. (x + res); dgamma/dbeta (d) written (accumulate=0) or added to (accumulate=1).
-extern "C" int gdmae_add_layernorm_bwd(const float* x, const float* res, const float* gamma, const float* mean, const float* rstd,
-                                       const float* dy, int64_t N, int d, float* dz, float* dgamma, float* dbeta, int accumulate,
-                                       void* workspace, size_t ws_bytes, void* stream_) {
+// dz (N,d) = gradient w.r.t. (x + res + bias) (also emitted as bf16 when dz_bf16 != NULL); dgamma/dbeta (d)
+// written (accumulate=0) or added to (accumulate=1).
+extern "C" int gdmae_add_layernorm_bwd(const float* x, const float* res, const float* bias, const float* gamma, const float* mean,
+                                       const float* rstd, const float* dy, int64_t N, int d, float* dz, void* dz_bf16,
+                                       float* dgamma, float* dbeta, int accumulate, void* workspace, size_t ws_bytes,
+                                       void* stream_) {
   GDMAE_CHECK_ARG(N >= 0 && (d == 128 || d == 256));
   if (ws_bytes < gdmae_rowwise_workspace_bytes(d)) { gdmae_set_error("add_layernorm_bwd: workspace too small"); return GDMAE_ERR_WORKSPACE; }
   if (N == 0) return GDMAE_OK;
   cudaStream_t st = (cudaStream_t)stream_;
   float* partial = (float*)workspace;
   int grid = ew_grid(N);
-  if (d == 128) add_ln_bwd_kernel<1><<<grid, 256, 0, st>>>((const float4*)x, (const float4*)res, (const float4*)gamma, mean, rstd, (const float4*)dy, N, (float4*)dz, partial);
-  else add_ln_bwd_kernel<2><<<grid, 256, 0, st>>>((const float4*)x, (const float4*)res, (const float4*)gamma, mean, rstd, (const float4*)dy, N, (float4*)dz, partial);
+  if (d == 128)
+    add_ln_bwd_kernel<1><<<grid, 256, 0, st>>>((const float4*)x, (const float4*)res, (const float4*)bias, (const float4*)gamma, mean,
+                                               rstd, (const float4*)dy, N, (float4*)dz, (__nv_bfloat16*)dz_bf16, partial);
+  else
+    add_ln_bwd_kernel<2><<<grid, 256, 0, st>>>((const float4*)x, (const float4*)res, (const float4*)bias, (const float4*)gamma, mean,
+                                               rstd, (const float4*)dy, N, (float4*)dz, (__nv_bfloat16*)dz_bf16, partial);
   GDMAE_LAUNCH_CHECK();
   // every CTA left one partial row [dgamma(d) | dbeta(d)]
   partial_reduce_kernel<<<gdmae_div_up(d, 32), 128, 0, st>>>(partial, grid, 2 * d, d, dgamma, accumulate);
@@ -187,18 +227,22 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
 }
 
 __global__ void __launch_bounds__(256) bias_gelu_fwd_kernel(const float4* __restrict__ h, const float4* __restrict__ bias,
-                                                            long long n4, int C4, float4* __restrict__ out) {
+                                                            long long n4, int C4, float4* __restrict__ out,
+                                                            __nv_bfloat16* __restrict__ out_bf16) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 a = __ldg(h + i), b = __ldg(bias + (int)(i % C4));
-    out[i] = make_float4(gelu_f(a.x + b.x), gelu_f(a.y + b.y), gelu_f(a.z + b.z), gelu_f(a.w + b.w));
+    float4 o = make_float4(gelu_f(a.x + b.x), gelu_f(a.y + b.y), gelu_f(a.z + b.z), gelu_f(a.w + b.w));
+    if (out) out[i] = o;
+    if (out_bf16) store_bf16x4(out_bf16, i, o);
   }
 }
 
-// dh = dg * gelu'(h + b); partial column sums of dh (bias gradient).  blockDim.x == C/4 * rows_per_block is not
-// required: thread t owns float4 column (t % C4) of rows (t / C4), stepping whole CTAs.
+// dh = dg * gelu'(h + b); partial column sums of dh (bias gradient).  Thread t owns float4 column (t % C4) of
+// rows (t / C4), stepping whole CTAs.
 __global__ void __launch_bounds__(256) bias_gelu_bwd_kernel(const float4* __restrict__ h, const float4* __restrict__ bias,
                                                             const float4* __restrict__ dg, long long N, int C4,
-                                                            float4* __restrict__ dh, float* __restrict__ partial) {
+                                                            float4* __restrict__ dh, __nv_bfloat16* __restrict__ dh_bf16,
+                                                            float* __restrict__ partial) {
   int c = threadIdx.x % C4, rsub = threadIdx.x / C4, rper = blockDim.x / C4;
   float4 b = __ldg(bias + c);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -206,7 +250,8 @@ __global__ void __launch_bounds__(256) bias_gelu_bwd_kernel(const float4* __rest
     float4 a = __ldg(h + row * C4 + c), g = __ldg(dg + row * C4 + c);
     float4 o = make_float4(g.x * gelu_grad_f(a.x + b.x), g.y * gelu_grad_f(a.y + b.y), g.z * gelu_grad_f(a.z + b.z),
                            g.w * gelu_grad_f(a.w + b.w));
-    dh[row * C4 + c] = o;
+    if (dh) dh[row * C4 + c] = o;
+    if (dh_bf16) store_bf16x4(dh_bf16, row * C4 + c, o);
     acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
   }
   __shared__ float4 red[256];
@@ -221,18 +266,19 @@ __global__ void __launch_bounds__(256) bias_gelu_bwd_kernel(const float4* __rest
   }
 }
 
-extern "C" int gdmae_bias_gelu_fwd(const float* h, const float* bias, int64_t N, int C, float* out, void* stream_) {
-  GDMAE_CHECK_ARG(N >= 0 && C > 0 && (C % 4) == 0);
+// out / out_bf16 (N,C): either may be NULL
+extern "C" int gdmae_bias_gelu_fwd(const float* h, const float* bias, int64_t N, int C, float* out, void* out_bf16, void* stream_) {
+  GDMAE_CHECK_ARG(N >= 0 && C > 0 && (C % 4) == 0 && (out || out_bf16));
   if (N == 0) return GDMAE_OK;
-  bias_gelu_fwd_kernel<<<gdmae_grid(N * (C / 4), 256, 8), 256, 0, (cudaStream_t)stream_>>>((const float4*)h, (const float4*)bias,
-                                                                                         N * (C / 4), C / 4, (float4*)out);
+  bias_gelu_fwd_kernel<<<gdmae_grid(N * (C / 4), 256, 8), 256, 0, (cudaStream_t)stream_>>>(
+      (const float4*)h, (const float4*)bias, N * (C / 4), C / 4, (float4*)out, (__nv_bfloat16*)out_bf16);
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;
 }
 
-extern "C" int gdmae_bias_gelu_bwd(const float* h, const float* bias, const float* dg, int64_t N, int C, float* dh, float* dbias,
-                                   int accumulate, void* workspace, size_t ws_bytes, void* stream_) {
-  GDMAE_CHECK_ARG(N >= 0 && C > 0 && (C % 4) == 0 && (C / 4) <= 256 && 256 % (C / 4) == 0);
+extern "C" int gdmae_bias_gelu_bwd(const float* h, const float* bias, const float* dg, int64_t N, int C, float* dh, void* dh_bf16,
+                                   float* dbias, int accumulate, void* workspace, size_t ws_bytes, void* stream_) {
+  GDMAE_CHECK_ARG(N >= 0 && C > 0 && (C % 4) == 0 && (C / 4) <= 256 && 256 % (C / 4) == 0 && (dh || dh_bf16));
   if (ws_bytes < gdmae_rowwise_workspace_bytes(C)) { gdmae_set_error("bias_gelu_bwd: workspace too small"); return GDMAE_ERR_WORKSPACE; }
   if (N == 0) return GDMAE_OK;
   cudaStream_t st = (cudaStream_t)stream_;
@@ -240,7 +286,8 @@ extern "C" int gdmae_bias_gelu_bwd(const float* h, const float* bias, const floa
   long long need = (N + rper - 1) / rper;
   int grid = (int)(need < EW_PART_BLOCKS ? need : EW_PART_BLOCKS);
   float* partial = (float*)workspace;
-  bias_gelu_bwd_kernel<<<grid, 256, 0, st>>>((const float4*)h, (const float4*)bias, (const float4*)dg, N, C / 4, (float4*)dh, partial);
+  bias_gelu_bwd_kernel<<<grid, 256, 0, st>>>((const float4*)h, (const float4*)bias, (const float4*)dg, N, C / 4, (float4*)dh,
+                                             (__nv_bfloat16*)dh_bf16, partial);
   GDMAE_LAUNCH_CHECK();
   partial_reduce_kernel<<<gdmae_div_up(C, 32), 128, 0, st>>>(partial, grid, C, C, dbias, accumulate);
   GDMAE_LAUNCH_CHECK();
@@ -248,12 +295,13 @@ extern "C" int gdmae_bias_gelu_bwd(const float* h, const float* bias, const floa
 }
 
 // ------------------------------------------------------------------ column sums (bias gradients of the GEMMs)
-__global__ void __launch_bounds__(256) colsum_kernel(const float4* __restrict__ x, long long N, int ld4, int col4, int C4,
+template <bool BF16>
+__global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ x_, long long N, int ld4, int col4, int C4,
                                                      float* __restrict__ partial) {
   int c = threadIdx.x % C4, rsub = threadIdx.x / C4, rper = blockDim.x / C4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long row = (long long)blockIdx.x * rper + rsub; row < N; row += (long long)gridDim.x * rper) {
-    float4 a = __ldg(x + row * ld4 + col4 + c);
+    float4 a = BF16 ? load_bf16x4((const __nv_bfloat16*)x_, row * ld4 + col4 + c) : __ldg((const float4*)x_ + row * ld4 + col4 + c);
     acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
   }
   __shared__ float4 red[256];
@@ -268,9 +316,9 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float4* __restrict__ 
   }
 }
 
-// out (C) = (accumulate ? out : 0) + sum over rows of x (N, ld) columns [col0, col0 + C)
-extern "C" int gdmae_colsum(const float* x, int64_t N, int ld, int col0, int C, float* out, int accumulate, void* workspace,
-                            size_t ws_bytes, void* stream_) {
+// out (C) = (accumulate ? out : 0) + sum over rows of x (N, ld) columns [col0, col0 + C); x fp32 (dtype 0) or bf16 (1)
+extern "C" int gdmae_colsum(const void* x, int dtype, int64_t N, int ld, int col0, int C, float* out, int accumulate,
+                            void* workspace, size_t ws_bytes, void* stream_) {
   GDMAE_CHECK_ARG(N >= 0 && C > 0 && (C % 4) == 0 && (ld % 4) == 0 && (col0 % 4) == 0 && col0 + C <= ld && (C / 4) <= 256);
   if (ws_bytes < gdmae_rowwise_workspace_bytes(C)) { gdmae_set_error("colsum: workspace too small"); return GDMAE_ERR_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream_;
@@ -283,9 +331,35 @@ extern "C" int gdmae_colsum(const float* x, int64_t N, int ld, int col0, int C, 
   long long need = (N + rper - 1) / rper;
   int grid = (int)(need < EW_PART_BLOCKS ? need : EW_PART_BLOCKS);
   float* partial = (float*)workspace;
-  colsum_kernel<<<grid, C4 * rper, 0, st>>>((const float4*)x, N, ld / 4, col0 / 4, C4, partial);
+  if (dtype == 0) colsum_kernel<false><<<grid, C4 * rper, 0, st>>>(x, N, ld / 4, col0 / 4, C4, partial);
+  else colsum_kernel<true><<<grid, C4 * rper, 0, st>>>(x, N, ld / 4, col0 / 4, C4, partial);
   GDMAE_LAUNCH_CHECK();
   partial_reduce_kernel<<<gdmae_div_up(C, 32), 128, 0, st>>>(partial, grid, C, C, out, accumulate);
+  GDMAE_LAUNCH_CHECK();
+  return GDMAE_OK;
+}
+
+// ------------------------------------------------------------------ out[n] = x[n] + table[idx[n]]  (q = k = feat + pos)
+__global__ void __launch_bounds__(256) gather_add_kernel(const float4* __restrict__ x, const float4* __restrict__ table,
+                                                         const unsigned char* __restrict__ idx, long long n4, int C4,
+                                                         float4* __restrict__ out, __nv_bfloat16* __restrict__ out_bf16) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    long long row = i / C4;
+    int c = (int)(i % C4);
+    float4 a = __ldg(x + i), t = __ldg(table + (int)idx[row] * C4 + c);
+    float4 o = make_float4(a.x + t.x, a.y + t.y, a.z + t.z, a.w + t.w);
+    if (out) out[i] = o;
+    if (out_bf16) store_bf16x4(out_bf16, i, o);
+  }
+}
+
+// out / out_bf16 (N,C) = x (N,C) + table (64,C)[idx (N) uint8]; either output may be NULL
+extern "C" int gdmae_gather_add_rows(const float* x, const float* table, const uint8_t* idx, int64_t N, int C, float* out,
+                                     void* out_bf16, void* stream_) {
+  GDMAE_CHECK_ARG(N >= 0 && C > 0 && (C % 4) == 0 && (out || out_bf16));
+  if (N == 0) return GDMAE_OK;
+  gather_add_kernel<<<gdmae_grid(N * (C / 4), 256, 8), 256, 0, (cudaStream_t)stream_>>>(
+      (const float4*)x, (const float4*)table, idx, N * (C / 4), C / 4, (float4*)out, (__nv_bfloat16*)out_bf16);
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;
 }

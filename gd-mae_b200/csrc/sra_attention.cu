@@ -29,6 +29,7 @@
 //           shared memory (pitch SLICE+4 floats: rows of different windows hit different banks,
 //           partners of the same window are a broadcast).  No global load inside the loop.
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 #define SRA_EPS 1e-12f
 // tunables (overridable with -D for tools/bench_sra.py sweeps)
@@ -57,8 +58,10 @@ struct SraArgs {
   const float* lut;      // (64, 2d): pos_table Wq^T + bq | pos_table Wk^T + bk
   const int4* row_info;  // (N) per CSR row: token, first row of its window, one past its last row, in-window cell
   const float* tau;      // (1) learnable temperature
+  const float* bv;       // (d) value bias, nullable: o = sum_j p_j (v_j + bv) = sum_j p_j v_j + bv (qkv holds v WITHOUT bias)
   float tau_min;
   int N, d;
+  int io_bf16;           // 1: the attention output o and dqkv are bf16 (GEMM operands of the bf16 configuration)
 };
 
 struct SraSmem {
@@ -167,6 +170,34 @@ __device__ __forceinline__ void store_head(float* __restrict__ p, const float* v
 #pragma unroll
   for (int i = 0; i < HD / 4; ++i) p4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
+// head row stored as fp32 or bf16 (elem = element offset of the head's first channel)
+template <int HD>
+__device__ __forceinline__ void store_head_t(void* base, int bf16, long long elem, const float* v) {
+  if (!bf16) { store_head<HD>((float*)base + elem, v); return; }
+  uint4* p = reinterpret_cast<uint4*>((__nv_bfloat16*)base + elem);
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]), b = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]), e = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
+    uint4 u;
+    u.x = *reinterpret_cast<unsigned*>(&a); u.y = *reinterpret_cast<unsigned*>(&b);
+    u.z = *reinterpret_cast<unsigned*>(&c); u.w = *reinterpret_cast<unsigned*>(&e);
+    p[i] = u;
+  }
+}
+template <int HD>
+__device__ __forceinline__ void load_head_t(const void* base, int bf16, long long elem, float* v) {
+  if (!bf16) { load_head<HD>((const float*)base + elem, v); return; }
+  const uint4* p = reinterpret_cast<const uint4*>((const __nv_bfloat16*)base + elem);
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i) {
+    uint4 u = __ldg(p + i);
+    float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.x)), b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.y));
+    float2 c = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.z)), e = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.w));
+    v[8 * i] = a.x; v[8 * i + 1] = a.y; v[8 * i + 2] = b.x; v[8 * i + 3] = b.y;
+    v[8 * i + 4] = c.x; v[8 * i + 5] = c.y; v[8 * i + 6] = e.x; v[8 * i + 7] = e.y;
+  }
+}
 template <int HD>
 __device__ __forceinline__ float dot_smem(const float* __restrict__ sm, const float* r) {
   float acc0 = 0.f, acc1 = 0.f;
@@ -197,7 +228,7 @@ __device__ __forceinline__ float dot_reg(const float* a, const float* b) {
 
 // ------------------------------------------------------------------------------ forward
 template <int HD>
-__global__ void __launch_bounds__(SRA_FWD_THREADS, SRA_MIN_CTAS) sra_fwd_kernel(SraArgs a, float* __restrict__ out,
+__global__ void __launch_bounds__(SRA_FWD_THREADS, SRA_MIN_CTAS) sra_fwd_kernel(SraArgs a, void* __restrict__ out,
                                                                               float* __restrict__ lse) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SraSmem s = sra_carve(smem_raw);
@@ -251,7 +282,8 @@ __global__ void __launch_bounds__(SRA_FWD_THREADS, SRA_MIN_CTAS) sra_fwd_kernel(
     float il = 1.f / l;
 #pragma unroll
     for (int i = 0; i < HD; ++i) o[i] *= il;
-    store_head<HD>(out + (long long)inf.x * d + col + h * HD, o);
+    if (a.bv) add_head<HD>(a.bv + col + h * HD, o);
+    store_head_t<HD>(out, a.io_bf16, (long long)inf.x * d + col + h * HD, o);
     lse[(long long)inf.x * 8 + blockIdx.y * HS + h] = m + __logf(l);
   }
 }
@@ -259,10 +291,10 @@ __global__ void __launch_bounds__(SRA_FWD_THREADS, SRA_MIN_CTAS) sra_fwd_kernel(
 // ------------------------------------------------------------------------------ backward, query side
 // dq_t and D_t = dO_t . O_t ; accumulates sum_ij dS_ij S_ij for the temperature gradient.
 template <int HD>
-__global__ void __launch_bounds__(SRA_BWD_THREADS, SRA_MIN_CTAS) sra_bwd_q_kernel(SraArgs a, const float* __restrict__ out,
+__global__ void __launch_bounds__(SRA_BWD_THREADS, SRA_MIN_CTAS) sra_bwd_q_kernel(SraArgs a, const void* __restrict__ out,
                                                                                 const float* __restrict__ lse,
                                                                                 const float* __restrict__ dout,
-                                                                                float* __restrict__ dqkv, float* __restrict__ Dbuf,
+                                                                                void* __restrict__ dqkv, float* __restrict__ Dbuf,
                                                                                 double* __restrict__ dtau_acc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SraSmem s = sra_carve(smem_raw);
@@ -285,7 +317,13 @@ __global__ void __launch_bounds__(SRA_BWD_THREADS, SRA_MIN_CTAS) sra_bwd_q_kerne
     add_head<HD>(a.lut + inf.w * 2 * d + col + h * HD, q);
     load_head<HD>(dout + (long long)inf.x * d + col + h * HD, dO);
     float o[HD];
-    load_head<HD>(out + (long long)inf.x * d + col + h * HD, o);
+    load_head_t<HD>(out, a.io_bf16, (long long)inf.x * d + col + h * HD, o);
+    if (a.bv) {  // the staged v rows carry no bias: D must be taken against o - bv
+      float b[HD];
+      load_head<HD>(a.bv + col + h * HD, b);
+#pragma unroll
+      for (int i = 0; i < HD; ++i) o[i] -= b[i];
+    }
     Dt = dot_reg<HD>(dO, o);
     ls = lse[(long long)inf.x * 8 + blockIdx.y * HS + h];
   };
@@ -317,7 +355,7 @@ __global__ void __launch_bounds__(SRA_BWD_THREADS, SRA_MIN_CTAS) sra_bwd_q_kerne
     float proj = dot_reg<HD>(q, dq);
 #pragma unroll
     for (int i = 0; i < HD; ++i) dq[i] = (dq[i] - q[i] * proj) * iqn;
-    store_head<HD>(dqkv + (long long)inf.x * 3 * d + col + h * HD, dq);
+    store_head_t<HD>(dqkv, a.io_bf16, (long long)inf.x * 3 * d + col + h * HD, dq);
     Dbuf[(long long)inf.x * 8 + blockIdx.y * HS + h] = Dt;
   }
   tacc = warp_sum(tacc);
@@ -336,7 +374,7 @@ template <int HD>
 __global__ void __launch_bounds__(SRA_BWD_THREADS, SRA_MIN_CTAS) sra_bwd_kv_kernel(SraArgs a, const float* __restrict__ lse,
                                                                                  const float* __restrict__ dout,
                                                                                  const float* __restrict__ Dbuf,
-                                                                                 float* __restrict__ dqkv) {
+                                                                                 void* __restrict__ dqkv) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SraSmem s = sra_carve(smem_raw);
   constexpr int HS = SRA_SLICE / HD;
@@ -390,8 +428,8 @@ __global__ void __launch_bounds__(SRA_BWD_THREADS, SRA_MIN_CTAS) sra_bwd_kv_kern
     float proj = dot_reg<HD>(k, dk);
 #pragma unroll
     for (int i = 0; i < HD; ++i) dk[i] = (dk[i] - k[i] * proj) * ikn;
-    store_head<HD>(dqkv + (long long)inf.x * 3 * d + d + col + h * HD, dk);
-    store_head<HD>(dqkv + (long long)inf.x * 3 * d + 2 * d + col + h * HD, dv);
+    store_head_t<HD>(dqkv, a.io_bf16, (long long)inf.x * 3 * d + d + col + h * HD, dk);
+    store_head_t<HD>(dqkv, a.io_bf16, (long long)inf.x * 3 * d + 2 * d + col + h * HD, dv);
   }
 }
 
@@ -416,12 +454,14 @@ static int sra_smem_attrs() {
 }
 
 // o (N,d) = softmax_j( cos(q_i, k_j) / max(tau, tau_min) ) v_j over the tokens j of i's window; lse (N,8).
+// bv (d, nullable): value bias added to o.  io_bf16: out is bf16 instead of fp32.
 extern "C" int gdmae_sra_attention_fwd(const float* qkv, const float* lut, const int32_t* row_info, int64_t N, int d, int nhead,
-                                       const float* tau, float tau_min, float* out, float* lse, void* stream_) {
+                                       const float* tau, float tau_min, const float* bv, int io_bf16, void* out, float* lse,
+                                       void* stream_) {
   int rc = sra_check(N, d, nhead, row_info);
   if (rc) return rc;
   if (N == 0) return GDMAE_OK;
-  SraArgs a{qkv, lut, (const int4*)row_info, tau, tau_min, (int)N, d};
+  SraArgs a{qkv, lut, (const int4*)row_info, tau, bv, tau_min, (int)N, d, io_bf16};
   cudaStream_t st = (cudaStream_t)stream_;
   dim3 grid(gdmae_div_up(N, SRA_BIN), d / SRA_SLICE);
   if ((rc = sra_smem_attrs())) return rc;
@@ -433,13 +473,15 @@ extern "C" int gdmae_sra_attention_fwd(const float* qkv, const float* lut, const
 
 // dqkv (N,3d) = [dq | dk | dv]; dtau_sum (1, double, caller zeroes) accumulates sum dS*S
 // (d loss / d tau = -dtau_sum / tau_c when tau >= tau_min, else 0); work_D (N,8) scratch.
+// io_bf16: `out` (the forward output) and `dqkv` are bf16.
 extern "C" int gdmae_sra_attention_bwd(const float* qkv, const float* lut, const int32_t* row_info, int64_t N, int d, int nhead,
-                                       const float* tau, float tau_min, const float* out, const float* lse, const float* dout,
-                                       float* dqkv, double* dtau_sum, float* work_D, void* stream_) {
+                                       const float* tau, float tau_min, const float* bv, int io_bf16, const void* out,
+                                       const float* lse, const float* dout, void* dqkv, double* dtau_sum, float* work_D,
+                                       void* stream_) {
   int rc = sra_check(N, d, nhead, row_info);
   if (rc) return rc;
   if (N == 0) return GDMAE_OK;
-  SraArgs a{qkv, lut, (const int4*)row_info, tau, tau_min, (int)N, d};
+  SraArgs a{qkv, lut, (const int4*)row_info, tau, bv, tau_min, (int)N, d, io_bf16};
   cudaStream_t st = (cudaStream_t)stream_;
   dim3 grid(gdmae_div_up(N, SRA_BIN), d / SRA_SLICE);
   if ((rc = sra_smem_attrs())) return rc;

@@ -268,32 +268,39 @@ def window_table(indices, B, H, W, shifted):
 SRA_TENSOR_CORES = False
 
 
-def sra_fwd(qkv, lut, tau, table, tau_min, nhead):
-    """raw launch: -> (out (N,d), lse (N,nhead))"""
+def sra_fwd(qkv, lut, tau, table, tau_min, nhead, bv=None, out_dtype=torch.float32):
+    """raw launch: -> (out (N,d) fp32 or bf16, lse (N,nhead)).  bv (d): value bias added to the output
+    (then qkv holds v without bias)."""
     N, d3 = qkv.shape
     d = d3 // 3
-    out = torch.empty((N, d), dtype=F32, device=qkv.device)
+    out = torch.empty((N, d), dtype=out_dtype, device=qkv.device)
     lse = torch.empty((N, nhead), dtype=F32, device=qkv.device)
     # algorithmic bytes (SURVEY.md 8d, a18 minus projections): N*d*(3*s_in + s_out) + N*8
-    fn = L.lib().gdmae_sra_attention_fwd_tc if SRA_TENSOR_CORES else L.lib().gdmae_sra_attention_fwd
-    with L.timed(f"sra_fwd_d{d}", N * d * 16 + N * 8):
-        L.check(fn(L.P(qkv), L.P(lut), L.P(table.row_info), L.i64(N), d, nhead, L.P(tau), L.f32(tau_min), L.P(out), L.P(lse),
-                   L.stream()), "gdmae_sra_attention_fwd")
+    with L.timed(f"sra_fwd_d{d}", N * d * (12 + out.element_size()) + N * 8):
+        if SRA_TENSOR_CORES and bv is None and out_dtype == F32:
+            L.check(L.lib().gdmae_sra_attention_fwd_tc(L.P(qkv), L.P(lut), L.P(table.row_info), L.i64(N), d, nhead, L.P(tau),
+                                                       L.f32(tau_min), L.P(out), L.P(lse), L.stream()), "gdmae_sra_attention_fwd_tc")
+        else:
+            L.check(L.lib().gdmae_sra_attention_fwd(L.P(qkv), L.P(lut), L.P(table.row_info), L.i64(N), d, nhead, L.P(tau),
+                                                    L.f32(tau_min), L.P(bv), _DT[out_dtype], L.P(out), L.P(lse), L.stream()),
+                    "gdmae_sra_attention_fwd")
     return out, lse
 
 
-def sra_bwd(qkv, lut, tau, table, tau_min, nhead, out, lse, dout):
-    """raw launch: -> (dqkv (N,3d), dtau_sum (1) float64 = sum dS*S)"""
+def sra_bwd(qkv, lut, tau, table, tau_min, nhead, out, lse, dout, bv=None, io_dtype=torch.float32):
+    """raw launch: -> (dqkv (N,3d) in io_dtype, dtau_sum (1) float64 = sum dS*S); ``out`` is the forward output."""
     N, d3 = qkv.shape
     d = d3 // 3
-    dqkv = torch.empty_like(qkv)
+    assert out.dtype == io_dtype
+    dqkv = torch.empty((N, d3), dtype=io_dtype, device=qkv.device)
     dtau_sum = torch.zeros((1,), dtype=torch.float64, device=qkv.device)
     work = torch.empty((N, nhead), dtype=F32, device=qkv.device)
+    es = dqkv.element_size()
     # bwd algorithmic bytes: qkv + o + dO in, dqkv out
-    with L.timed(f"sra_bwd_d{d}", N * d * 4 * (3 + 1 + 1 + 3) + N * 8):
+    with L.timed(f"sra_bwd_d{d}", N * d * (12 + es + 4 + 3 * es) + N * 8):
         L.check(L.lib().gdmae_sra_attention_bwd(L.P(qkv), L.P(lut), L.P(table.row_info), L.i64(N), d, nhead, L.P(tau),
-                                                L.f32(tau_min), L.P(out), L.P(lse), L.P(dout), L.P(dqkv), L.P(dtau_sum), L.P(work),
-                                                L.stream()), "gdmae_sra_attention_bwd")
+                                                L.f32(tau_min), L.P(bv), _DT[io_dtype], L.P(out), L.P(lse), L.P(dout), L.P(dqkv),
+                                                L.P(dtau_sum), L.P(work), L.stream()), "gdmae_sra_attention_bwd")
     return dqkv, dtau_sum
 
 

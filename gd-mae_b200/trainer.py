@@ -61,10 +61,15 @@ class MAETrainer:
         opt_names = optimised_parameter_names(model)
         named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
         ordered = [(n, p) for n, p in named if n in opt_names] + [(n, p) for n, p in named if n not in opt_names]
-        self.n_opt = sum(p.numel() for n, p in ordered if n in opt_names)
-        self.n_all = sum(p.numel() for _, p in ordered)
+        # every tensor starts on a 256-byte boundary of the bucket (the kernels read parameters with 128-bit
+        # loads); the zero padding has zero gradient, so it neither moves nor contributes to the clip norm
+        ALIGN = 64
+        pad = lambda k: (k + ALIGN - 1) // ALIGN * ALIGN  # noqa: E731
+        self.n_params = sum(p.numel() for _, p in ordered)
+        self.n_opt = sum(pad(p.numel()) for n, p in ordered if n in opt_names)
+        self.n_all = sum(pad(p.numel()) for _, p in ordered)
         dev = ordered[0][1].device
-        self.flat_params = torch.empty(self.n_all, dtype=torch.float32, device=dev)
+        self.flat_params = torch.zeros(self.n_all, dtype=torch.float32, device=dev)
         self.flat_grads = torch.zeros(self.n_all, dtype=torch.float32, device=dev)
         off = 0
         self.slices = {}
@@ -74,7 +79,7 @@ class MAETrainer:
             p.data = self.flat_params[off:off + k].view_as(p)
             p.grad = self.flat_grads[off:off + k].view_as(p)
             self.slices[n] = (off, k)
-            off += k
+            off += pad(k)
         self.exp_avg = torch.zeros(self.n_opt, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(self.n_opt, dtype=torch.float32, device=dev)
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)

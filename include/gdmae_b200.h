@@ -132,33 +132,47 @@ int gdmae_window_table(const int32_t* indices, int64_t N, int B, int H, int W, i
  * replaces flat2window/window2flat (sst_utils.py:107-181), the per-level loop of
  * WindowAttention.forward (pcdet/models/model_utils/sst_basic_block.py:22-54) and
  * _scaled_cosine_attention (pcdet/models/model_utils/cosine_msa.py:114-176) incl. the -inf key mask.
- * qkv (N, 3d) = [x Wq^T | x Wk^T | x Wv^T + bv]; lut (64, 2d) = pos_table [Wq;Wk]^T + [bq;bk];
- * out (N, d) pre out-proj; lse (N, 8).  nhead == 8, d in {128, 256}. */
+ * qkv (N, 3d) = [x Wq^T | x Wk^T | x Wv^T] (no biases); lut (64, 2d) = pos_table [Wq;Wk]^T + [bq;bk];
+ * bv (d, nullable) = value bias, added to the output (softmax rows sum to 1);
+ * out (N, d) pre out-proj, fp32 or (io_bf16 = 1) bf16; lse (N, 8).  nhead == 8, d in {128, 256}.
+ * Backward: out as written by forward; dqkv (N, 3d) fp32 or bf16 (io_bf16); dtau_sum (1) double, caller
+ * zeroes, accumulates sum dS*S; work_D (N, 8) scratch. */
 int gdmae_sra_attention_fwd(const float* qkv, const float* lut, const int32_t* row_info, int64_t N, int d, int nhead,
-                            const float* tau, float tau_min, float* out, float* lse, void* stream);
-/* same operator, QK^T and PV on the tensor cores (TF32 mma, fp32 accumulate, softmax in fp32) */
+                            const float* tau, float tau_min, const float* bv, int io_bf16, void* out, float* lse,
+                            void* stream);
+/* same operator, QK^T and PV on the tensor cores (TF32 mma, fp32 accumulate, softmax in fp32); fp32 out, bv in qkv */
 int gdmae_sra_attention_fwd_tc(const float* qkv, const float* lut, const int32_t* row_info, int64_t N, int d, int nhead,
                                const float* tau, float tau_min, float* out, float* lse, void* stream);
 int gdmae_sra_attention_bwd(const float* qkv, const float* lut, const int32_t* row_info, int64_t N, int d, int nhead,
-                            const float* tau, float tau_min, const float* out, const float* lse, const float* dout,
-                            float* dqkv, double* dtau_sum, float* work_D, void* stream);
+                            const float* tau, float tau_min, const float* bv, int io_bf16, const void* out,
+                            const float* lse, const float* dout, void* dqkv, double* dtau_sum, float* work_D,
+                            void* stream);
 
 /* ---- a19 encoder-layer row kernels ------------------------------------------------------------
  * replace the residual + LayerNorm pairs and the GELU(linear1) of EncoderLayer.forward
- * (pcdet/models/model_utils/sst_basic_block.py:77-84) and the bias-gradient reductions of its
- * linears.  d in {128,256}; parameter gradients are written (accumulate=0) or added (accumulate=1).
- * workspace: gdmae_rowwise_workspace_bytes(max columns). */
+ * (pcdet/models/model_utils/sst_basic_block.py:77-84), the bias-gradient reductions of its linears and
+ * q = k = feat + pos (sst_basic_block.py:39-46).  d in {128,256}; parameter gradients are written
+ * (accumulate=0) or added (accumulate=1).  *_bf16 outputs (nullable) are bf16 copies = GEMM operands of
+ * the bf16 configuration.  workspace: gdmae_rowwise_workspace_bytes(max columns). */
 size_t gdmae_rowwise_workspace_bytes(int max_cols);
-int gdmae_add_layernorm_fwd(const float* x, const float* res, const float* gamma, const float* beta, int64_t N, int d,
-                            float eps, float* y, float* mean, float* rstd, void* stream);
-int gdmae_add_layernorm_bwd(const float* x, const float* res, const float* gamma, const float* mean, const float* rstd,
-                            const float* dy, int64_t N, int d, float* dz, float* dgamma, float* dbeta, int accumulate,
-                            void* workspace, size_t ws_bytes, void* stream);
-int gdmae_bias_gelu_fwd(const float* h, const float* bias, int64_t N, int C, float* out, void* stream);
-int gdmae_bias_gelu_bwd(const float* h, const float* bias, const float* dg, int64_t N, int C, float* dh, float* dbias,
-                        int accumulate, void* workspace, size_t ws_bytes, void* stream);
-int gdmae_colsum(const float* x, int64_t N, int ld, int col0, int C, float* out, int accumulate, void* workspace,
-                 size_t ws_bytes, void* stream);
+int gdmae_add_layernorm_fwd(const float* x, const float* res, const float* bias, const float* gamma, const float* beta,
+                            int64_t N, int d, float eps, float* y, void* y_bf16, float* mean, float* rstd, void* stream);
+int gdmae_add_layernorm_bwd(const float* x, const float* res, const float* bias, const float* gamma, const float* mean,
+                            const float* rstd, const float* dy, int64_t N, int d, float* dz, void* dz_bf16,
+                            float* dgamma, float* dbeta, int accumulate, void* workspace, size_t ws_bytes, void* stream);
+int gdmae_bias_gelu_fwd(const float* h, const float* bias, int64_t N, int C, float* out, void* out_bf16, void* stream);
+int gdmae_bias_gelu_bwd(const float* h, const float* bias, const float* dg, int64_t N, int C, float* dh, void* dh_bf16,
+                        float* dbias, int accumulate, void* workspace, size_t ws_bytes, void* stream);
+int gdmae_colsum(const void* x, int dtype /* 0 fp32, 1 bf16 */, int64_t N, int ld, int col0, int C, float* out,
+                 int accumulate, void* workspace, size_t ws_bytes, void* stream);
+int gdmae_gather_add_rows(const float* x, const float* table, const uint8_t* idx, int64_t N, int C, float* out,
+                          void* out_bf16, void* stream);
+
+/* ---- plain dense GEMM through cuBLAS (library GEMM) ------------------------------------------------
+ * row-major C (M,N) fp32 = op(A) op(B) + beta*C; A/B fp32 (TF32 math, ab_dtype 0) or bf16 (1).
+ * replaces F.linear of the projections / FFN / sparse-conv GEMMs (cosine_msa.py:57-62,431, sst_basic_block.py:81). */
+int gdmae_gemm(int transa, int transb, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
+               int64_t ldb, int ab_dtype, float* C, int64_t ldc, float beta, void* stream);
 
 /* ---- a5/a9/a21/a22 training-mode BatchNorm (+ReLU) over (N, C) rows ------------------------------
  * replaces norm_fn + nn.ReLU of post_act_block (pcdet/utils/spconv_utils.py:50-54), of make_fc_layers

@@ -35,10 +35,10 @@ def _worker(rank, world, port, q):
         # flat bucket: [optimised | never-optimised], parameters and grads are views of it
         names = [n for n, _ in model.named_parameters()]
         opt = optimised_parameter_names(model)
-        assert tr.n_all == sum(p.numel() for p in model.parameters())
-        assert tr.n_opt == sum(p.numel() for n, p in model.named_parameters() if n in opt)
+        assert tr.n_params == sum(p.numel() for p in model.parameters()) and tr.n_all >= tr.n_params
         for n, p in model.named_parameters():
             off, k = tr.slices[n]
+            assert off % 64 == 0  # 256-byte aligned: kernels read parameters with 128-bit loads
             assert p.data.data_ptr() == tr.flat_params[off:off + k].data_ptr()
             assert p.grad.data_ptr() == tr.flat_grads[off:off + k].data_ptr()
             assert (off < tr.n_opt) == (n in opt)
