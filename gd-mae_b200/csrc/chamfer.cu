@@ -6,9 +6,14 @@
 //   common_utils.get_voxel_centers, gt - centre             pcdet/utils/common_utils.py:130-145, spt_backbone_mae.py:67-72
 //   pytorch3d.loss.chamfer_distance(pred, gt, weights=mask) pcdet/models/backbones_3d/spt_backbone_mae.py:88 (third party)
 //
-// One warp per pillar: the 16 predicted points sit in registers of every lane, each lane owns
-// P2/32 ground-truth points.  The forward kernel also emits d(loss)/d(pred) (up to the global
-// 1/sum(w) factor), so the backward pass launches nothing.
+// One warp per pillar.  Lane l < 16 owns predicted point l, every lane owns P2/32 ground-truth
+// points.  The 16 x 64 distance table is never stored: predicted points are broadcast with
+// shuffles, the nearest ground-truth point of each prediction is ONE integer warp reduction
+// (distance bits with the point index in the low bits, REDUX.MIN), and the gt->pred assignments
+// go through 1 KB of shared memory so that the owner lanes accumulate their gradient in a fixed
+// order (deterministic, no float atomics).  ~40 registers per thread -> full occupancy; the
+// forward kernel also emits d(loss)/d(pred) (up to the global 1/sum(w) factor), so the backward
+// pass launches nothing.
 #include "common.cuh"
 
 struct CenterParams { float r0, r1, r2, v0, v1, v2; int n_cols; };
@@ -45,74 +50,98 @@ extern "C" int gdmae_group_points_centered(const float* points, int n_cols, cons
   return GDMAE_OK;
 }
 
-template <int P1>
+#define CH_P1 16
+#define CH_MAXG 4  // ground-truth points per lane: P2 <= 128
+
+// P2 <= 128 ground-truth points, 16 predicted points per item.
 __global__ void __launch_bounds__(256) chamfer_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
                                                       const float* __restrict__ w, long long N, int P2,
                                                       float* __restrict__ per_item, float* __restrict__ dpred) {
-  int lane = threadIdx.x & 31;
+  __shared__ float4 sg[8][32 * CH_MAXG];  // per warp: (gx, gy, gz, nearest pred index as float bits) per gt point
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float4* mine = sg[wib];
+  const int G = (P2 + 31) >> 5;  // gt points per lane (lane owns j = lane + 32 k)
   for (long long n = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; n < N;
        n += ((long long)gridDim.x * blockDim.x) >> 5) {
     float wn = w ? w[n] : 1.f;
     if (wn == 0.f) {  // visible pillar: contributes nothing (weights are the MAE mask)
       if (lane == 0) per_item[n] = 0.f;
-      for (int i = lane; i < P1 * 3; i += 32) dpred[n * P1 * 3 + i] = 0.f;
+      for (int i = lane; i < CH_P1 * 3; i += 32) dpred[n * CH_P1 * 3 + i] = 0.f;
       continue;
     }
-    float px[P1], py[P1], pz[P1];
-    const float* pr = pred + n * P1 * 3;
-#pragma unroll
-    for (int i = 0; i < P1; ++i) { px[i] = __ldg(pr + 3 * i); py[i] = __ldg(pr + 3 * i + 1); pz[i] = __ldg(pr + 3 * i + 2); }
-    float best_x[P1];   // min over this lane's gt points, per pred point
-    int arg_x[P1];
-#pragma unroll
-    for (int i = 0; i < P1; ++i) { best_x[i] = INFINITY; arg_x[i] = 0; }
-    float gx_acc[P1], gy_acc[P1], gz_acc[P1];  // gradient of the gt->pred term, per pred point (lane partial)
-#pragma unroll
-    for (int i = 0; i < P1; ++i) { gx_acc[i] = 0.f; gy_acc[i] = 0.f; gz_acc[i] = 0.f; }
-    float sum_y = 0.f;
+    float px = 0.f, py = 0.f, pz = 0.f;
+    if (lane < CH_P1) {
+      const float* pr = pred + n * CH_P1 * 3 + 3 * lane;
+      px = __ldg(pr); py = __ldg(pr + 1); pz = __ldg(pr + 2);
+    }
+    float gx[CH_MAXG], gy[CH_MAXG], gz[CH_MAXG], gbest[CH_MAXG];
+    int gidx[CH_MAXG];
     const float* g = gt + n * (long long)P2 * 3;
-    for (int j = lane; j < P2; j += 32) {
-      float x = __ldg(g + 3 * j), y = __ldg(g + 3 * j + 1), z = __ldg(g + 3 * j + 2);
-      float bmin = INFINITY;
-      int bi = 0;
 #pragma unroll
-      for (int i = 0; i < P1; ++i) {
-        float dx = px[i] - x, dy = py[i] - y, dz = pz[i] - z;
-        float d = dx * dx + dy * dy + dz * dz;
-        if (d < best_x[i]) { best_x[i] = d; arg_x[i] = j; }
-        if (d < bmin) { bmin = d; bi = i; }
+    for (int k = 0; k < CH_MAXG; ++k) {
+      int j = lane + 32 * k;
+      bool ok = k < G && j < P2;
+      gx[k] = ok ? __ldg(g + 3 * j) : 0.f;
+      gy[k] = ok ? __ldg(g + 3 * j + 1) : 0.f;
+      gz[k] = ok ? __ldg(g + 3 * j + 2) : 0.f;
+      gbest[k] = INFINITY;
+      gidx[k] = 0;
+    }
+    // pass 1: every predicted point against every gt point
+    unsigned my_key = 0xffffffffu;  // lane i < 16 ends up with the packed arg-min of prediction i
+#pragma unroll
+    for (int i = 0; i < CH_P1; ++i) {
+      float qx = __shfl_sync(0xffffffffu, px, i), qy = __shfl_sync(0xffffffffu, py, i), qz = __shfl_sync(0xffffffffu, pz, i);
+      unsigned dbits = 0xffffffffu, jmin = 0xffffffffu;  // this lane's nearest gt point to prediction i
+#pragma unroll
+      for (int k = 0; k < CH_MAXG; ++k) {
+        int j = lane + 32 * k;
+        if (k < G && j < P2) {
+          float dx = qx - gx[k], dy = qy - gy[k], dz = qz - gz[k];
+          float d = dx * dx + dy * dy + dz * dz;
+          if (d < gbest[k]) { gbest[k] = d; gidx[k] = i; }
+          unsigned b = __float_as_uint(d);  // distance >= 0: the bit pattern orders like the value
+          if (b < dbits) { dbits = b; jmin = (unsigned)j; }
+        }
       }
-      sum_y += bmin;
+      // exact warp arg-min in two integer reductions (REDUX): the minimum, then the lowest index attaining it
+      unsigned wmin = __reduce_min_sync(0xffffffffu, dbits);
+      unsigned wj = __reduce_min_sync(0xffffffffu, dbits == wmin ? jmin : 0xffffffffu);
+      if (lane == i) my_key = wj;
+    }
+    // gt -> pred term and hand-over of the assignments through shared memory
+    float sum_y = 0.f;
+    __syncwarp();
 #pragma unroll
-      for (int i = 0; i < P1; ++i) {
-        if (i == bi) { gx_acc[i] += px[i] - x; gy_acc[i] += py[i] - y; gz_acc[i] += pz[i] - z; }
+    for (int k = 0; k < CH_MAXG; ++k) {
+      int j = lane + 32 * k;
+      if (k < G && j < P2) {
+        sum_y += gbest[k];
+        mine[j] = make_float4(gx[k], gy[k], gz[k], __int_as_float(gidx[k]));
       }
     }
     sum_y = warp_sum(sum_y);
+    __syncwarp();
     float sum_x = 0.f;
-    float sx = 2.f * wn / (float)P1, sy = 2.f * wn / (float)P2;
-#pragma unroll
-    for (int i = 0; i < P1; ++i) {
-      // warp arg-min over lanes (ties: lowest gt index)
-      float v = best_x[i];
-      int idx = arg_x[i];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        float ov = __shfl_xor_sync(0xffffffffu, v, o);
-        int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-        if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    if (lane < CH_P1) {
+      // pred -> gt term: exact distance to the arg-min found above (the packed key dropped 7 mantissa bits)
+      float4 gm = mine[my_key & 127u];
+      float dx = px - gm.x, dy = py - gm.y, dz = pz - gm.z;
+      sum_x = dx * dx + dy * dy + dz * dz;
+      float sx = 2.f * wn / (float)CH_P1, sy = 2.f * wn / (float)P2;
+      float ax = 0.f, ay = 0.f, az = 0.f;
+      for (int j = 0; j < P2; ++j) {  // fixed order -> deterministic
+        float4 e = mine[j];
+        if (__float_as_int(e.w) == lane) { ax += px - e.x; ay += py - e.y; az += pz - e.z; }
       }
-      sum_x += v;
-      float ax = warp_sum(gx_acc[i]), ay = warp_sum(gy_acc[i]), az = warp_sum(gz_acc[i]);
-      if (lane == 0) {
-        float x = __ldg(g + 3 * idx), y = __ldg(g + 3 * idx + 1), z = __ldg(g + 3 * idx + 2);
-        float* d = dpred + n * P1 * 3 + 3 * i;
-        d[0] = sx * (px[i] - x) + sy * ax;
-        d[1] = sx * (py[i] - y) + sy * ay;
-        d[2] = sx * (pz[i] - z) + sy * az;
-      }
+      float* d = dpred + n * CH_P1 * 3 + 3 * lane;
+      d[0] = sx * dx + sy * ax;
+      d[1] = sx * dy + sy * ay;
+      d[2] = sx * dz + sy * az;
     }
-    if (lane == 0) per_item[n] = wn * (sum_x / (float)P1 + sum_y / (float)P2);
+    sum_x = warp_sum(sum_x);
+    if (lane == 0) per_item[n] = wn * (sum_x / (float)CH_P1 + sum_y / (float)P2);
+    __syncwarp();
   }
 }
 
@@ -120,9 +149,9 @@ __global__ void __launch_bounds__(256) chamfer_kernel(const float* __restrict__ 
 // dpred[n,i,:] = d per_item[n] / d pred[n,i,:].   loss = sum(per_item) / sum(w)  (done by the caller).
 extern "C" int gdmae_chamfer_fwd(const float* pred, const float* gt, const float* weights, int64_t N, int P1, int P2,
                                  float* per_item, float* dpred, void* stream_) {
-  GDMAE_CHECK_ARG(N >= 0 && P1 == 16 && P2 >= 1);
+  GDMAE_CHECK_ARG(N >= 0 && P1 == CH_P1 && P2 >= 1 && P2 <= 32 * CH_MAXG);
   if (N == 0) return GDMAE_OK;
-  chamfer_kernel<16><<<gdmae_grid(N * 32, 256, 8), 256, 0, (cudaStream_t)stream_>>>(pred, gt, weights, N, P2, per_item, dpred);
+  chamfer_kernel<<<gdmae_grid(N * 32, 256, 8), 256, 0, (cudaStream_t)stream_>>>(pred, gt, weights, N, P2, per_item, dpred);
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;
 }

@@ -113,29 +113,64 @@ struct DenseFillArgs {
   int B, Y, X, Cs;
 };
 
+// 8-channel packets: fp32 = two 16-byte stores, bf16 = one 16-byte store
+template <typename T> struct Pack8;
+template <> struct Pack8<float> {
+  static __device__ __forceinline__ void store(float* p, long long i8, float4 a, float4 b) {
+    __stcs(reinterpret_cast<float4*>(p) + 2 * i8, a);
+    __stcs(reinterpret_cast<float4*>(p) + 2 * i8 + 1, b);
+  }
+  static __device__ __forceinline__ void load(const float* p, long long i8, float4& a, float4& b) {
+    a = __ldcs(reinterpret_cast<const float4*>(p) + 2 * i8);
+    b = __ldcs(reinterpret_cast<const float4*>(p) + 2 * i8 + 1);
+  }
+};
+template <> struct Pack8<__nv_bfloat16> {
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, long long i8, float4 a, float4 b) {
+    __nv_bfloat162 x0 = __floats2bfloat162_rn(a.x, a.y), x1 = __floats2bfloat162_rn(a.z, a.w);
+    __nv_bfloat162 x2 = __floats2bfloat162_rn(b.x, b.y), x3 = __floats2bfloat162_rn(b.z, b.w);
+    float4 u;
+    u.x = __uint_as_float(*reinterpret_cast<unsigned*>(&x0)); u.y = __uint_as_float(*reinterpret_cast<unsigned*>(&x1));
+    u.z = __uint_as_float(*reinterpret_cast<unsigned*>(&x2)); u.w = __uint_as_float(*reinterpret_cast<unsigned*>(&x3));
+    __stcs(reinterpret_cast<float4*>(p) + i8, u);
+  }
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, long long i8, float4& a, float4& b) {
+    float4 u = __ldcs(reinterpret_cast<const float4*>(p) + i8);
+    unsigned w0 = __float_as_uint(u.x), w1 = __float_as_uint(u.y), w2 = __float_as_uint(u.z), w3 = __float_as_uint(u.w);
+    float2 f0 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w0)), f1 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w1));
+    float2 f2 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w2)), f3 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w3));
+    a = make_float4(f0.x, f0.y, f1.x, f1.y);
+    b = make_float4(f2.x, f2.y, f3.x, f3.y);
+  }
+};
+
+// one thread = 8 channels of one (cell, scale): a streaming 16-byte store per thread in bf16.
+// grid = (Y, B): a CTA walks one map row, 8 cells x 3 scales x C8 lanes per trip (the 8 cells' 6 KB are
+// contiguous in the output), four trips in flight.  Coordinates come from the block index; the only
+// per-trip index math is x += 8 and a shift (strides are powers of two).
 template <typename T>
-__global__ void dense_fill_kernel(DenseFillArgs a, T* __restrict__ out) {
-  int C4 = a.Cs >> 2;
-  long long total = (long long)a.B * a.Y * a.X * 3 * C4;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(t % C4);
-    long long r = t / C4;
-    int s = (int)(r % 3);
-    long long cell = r / 3;
-    int x = (int)(cell % a.X);
-    long long q = cell / a.X;
-    int y = (int)(q % a.Y), b = (int)(q / a.Y);
-    int k = a.k[s];
-    int gy = y / k, gx = x / k;
-    int rank = (gy < a.H[s] && gx < a.W[s]) ? __ldg(a.grid[s] + ((long long)b * a.H[s] + gy) * a.W[s] + gx) : -1;
-    float4 v;
-    if (rank >= 0) {
-      long long row = (long long)rank * k * k + (y - gy * k) * k + (x - gx * k);
-      v = __ldg(reinterpret_cast<const float4*>(a.rows[s]) + row * C4 + c);
-    } else {
-      v = __ldg(reinterpret_cast<const float4*>(a.bg[s]) + c);
-    }
-    Pack4<T>::store(out, t, v);
+__global__ void __launch_bounds__(384) dense_fill_kernel(DenseFillArgs a, T* __restrict__ out) {
+  const int C8 = a.Cs >> 3;                 // 16 for Cs = 128
+  const int per_cell = 3 * C8;
+  const int xl = threadIdx.x / per_cell, rem = threadIdx.x - xl * per_cell;
+  const int s = rem / C8, c = rem - s * C8;
+  const int y = blockIdx.x, b = blockIdx.y;
+  const int sh = a.k[s] == 1 ? 0 : (a.k[s] == 2 ? 1 : 2);
+  const int k = 1 << sh;
+  const int gy = y >> sh;
+  const bool row_ok = gy < a.H[s];
+  const int Ws = a.W[s];
+  const int* grow = a.grid[s] + ((long long)b * a.H[s] + gy) * Ws;
+  const float4* rows = reinterpret_cast<const float4*>(a.rows[s]);
+  const float4* bg = reinterpret_cast<const float4*>(a.bg[s]) + 2 * c;
+  const int suby = (y - (gy << sh)) * k;
+  const long long t0 = ((long long)b * a.Y + y) * a.X * per_cell + rem;
+#pragma unroll 4
+  for (int x = xl; x < a.X; x += 8) {
+    const int gx = x >> sh;
+    int rank = (row_ok && gx < Ws) ? __ldg(grow + gx) : -1;
+    const float4* src = rank >= 0 ? rows + ((long long)rank * k * k + suby + (x - (gx << sh))) * (2 * C8) + 2 * c : bg;
+    Pack8<T>::store(out, t0 + (long long)x * per_cell, __ldg(src), __ldg(src + 1));
   }
 }
 
@@ -159,45 +194,55 @@ __global__ void dense_fill_bwd_rows_kernel(DenseFillArgs a, int s, const int* __
   }
 }
 
-// column sums of dout over the cells NOT covered at scale s.  grid = (chunks, 3); block 256 =
-// 8 cell-lanes x 32 channel-lanes(float4); per-block partials are combined with float atomics
-// into dbg (3*Cs, caller zeroes) - 3*Cs*gridDim.x adds in total, negligible contention.
+// column sums of dout over the cells NOT covered at scale s.  grid = (Y*B / rows_per_cta, 3); block 256 =
+// 16 cell-lanes x 16 channel-lanes (8 channels = one 16-byte streaming load in bf16); a CTA walks whole map rows,
+// so the only per-cell index math is a shift.  Per-block partials are combined with float atomics into dbg
+// (3*Cs, caller zeroes).
 template <typename T>
 __global__ void __launch_bounds__(256) dense_fill_bwd_bg_kernel(DenseFillArgs a, const T* __restrict__ dout,
                                                                float* __restrict__ dbg) {
-  int C4 = a.Cs >> 2;  // == 32 for Cs = 128
-  int s = blockIdx.y;
-  int lane = threadIdx.x % C4, sub = threadIdx.x / C4, nsub = blockDim.x / C4;
-  long long n_cells = (long long)a.B * a.Y * a.X;
-  int k = a.k[s];
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (long long cell = (long long)blockIdx.x * nsub + sub; cell < n_cells; cell += (long long)gridDim.x * nsub) {
-    int x = (int)(cell % a.X);
-    long long q = cell / a.X;
-    int y = (int)(q % a.Y), b = (int)(q / a.Y);
-    int gy = y / k, gx = x / k;
-    int rank = (gy < a.H[s] && gx < a.W[s]) ? __ldg(a.grid[s] + ((long long)b * a.H[s] + gy) * a.W[s] + gx) : -1;
-    if (rank < 0) {
-      float4 v = Pack4<T>::load(dout, (cell * 3 + s) * C4 + lane);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  const int C8 = a.Cs >> 3;  // == 16 for Cs = 128
+  const int s = blockIdx.y;
+  const int lane = threadIdx.x % C8, sub = threadIdx.x / C8, nsub = blockDim.x / C8;
+  const int sh = a.k[s] == 1 ? 0 : (a.k[s] == 2 ? 1 : 2);
+  const int n_rows = a.B * a.Y;
+  float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+  for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
+    const int b = row / a.Y, y = row - b * a.Y;
+    const int gy = y >> sh;
+    const bool row_ok = gy < a.H[s];
+    const int* grow = a.grid[s] + ((long long)b * a.H[s] + gy) * a.W[s];
+    const long long base = (long long)row * a.X;
+    for (int x = sub; x < a.X; x += nsub) {
+      int gx = x >> sh;
+      int rank = (row_ok && gx < a.W[s]) ? __ldg(grow + gx) : -1;
+      if (rank < 0) {
+        float4 v0, v1;
+        Pack8<T>::load(dout, ((base + x) * 3 + s) * C8 + lane, v0, v1);
+        acc0.x += v0.x; acc0.y += v0.y; acc0.z += v0.z; acc0.w += v0.w;
+        acc1.x += v1.x; acc1.y += v1.y; acc1.z += v1.z; acc1.w += v1.w;
+      }
     }
   }
-  __shared__ float4 red[256];
-  red[threadIdx.x] = acc;
+  __shared__ float4 red[2][256];
+  red[0][threadIdx.x] = acc0;
+  red[1][threadIdx.x] = acc1;
   __syncthreads();
   if (sub == 0) {
     for (int j = 1; j < nsub; ++j) {
-      float4 v = red[j * C4 + lane];
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      float4 v0 = red[0][j * C8 + lane], v1 = red[1][j * C8 + lane];
+      acc0.x += v0.x; acc0.y += v0.y; acc0.z += v0.z; acc0.w += v0.w;
+      acc1.x += v1.x; acc1.y += v1.y; acc1.z += v1.z; acc1.w += v1.w;
     }
-    float* dst = dbg + s * a.Cs + 4 * lane;
-    atomicAdd(dst, acc.x); atomicAdd(dst + 1, acc.y); atomicAdd(dst + 2, acc.z); atomicAdd(dst + 3, acc.w);
+    float* dst = dbg + s * a.Cs + 8 * lane;
+    atomicAdd(dst, acc0.x); atomicAdd(dst + 1, acc0.y); atomicAdd(dst + 2, acc0.z); atomicAdd(dst + 3, acc0.w);
+    atomicAdd(dst + 4, acc1.x); atomicAdd(dst + 5, acc1.y); atomicAdd(dst + 6, acc1.z); atomicAdd(dst + 7, acc1.w);
   }
 }
 
 static int fill_args(DenseFillArgs& a, const float* const* rows, const float* const* bg, const int32_t* const* grids,
                      const int* strides, int B, int Y, int X, int Cs) {
-  GDMAE_CHECK_ARG(B >= 1 && Y >= 1 && X >= 1 && Cs > 0 && (Cs % 4) == 0 && 256 % (Cs / 4) == 0);
+  GDMAE_CHECK_ARG(B >= 1 && Y >= 1 && X >= 1 && Cs > 0 && (Cs % 8) == 0 && 256 % (Cs / 8) == 0);
   for (int s = 0; s < 3; ++s) {
     GDMAE_CHECK_ARG(strides[s] >= 1);
     a.rows[s] = rows ? rows[s] : nullptr;
@@ -219,8 +264,10 @@ static int dense_fill_impl(const float* const* rows, const float* const* bg, con
   DenseFillArgs a;
   int rc = fill_args(a, rows, bg, rank_grids, strides, B, Y, X, Cs);
   if (rc) return rc;
-  long long total = (long long)B * Y * X * 3 * (Cs / 4);
-  dense_fill_kernel<T><<<gdmae_grid(total, 256, 32), 256, 0, (cudaStream_t)stream_>>>(a, out);
+  GDMAE_CHECK_ARG(Cs == 128 && B < 65536);  // block = 8 cells x 3 scales x 16 lanes
+  for (int s = 0; s < 3; ++s) GDMAE_CHECK_ARG(strides[s] == 1 || strides[s] == 2 || strides[s] == 4);
+  dim3 grid(Y, B);
+  dense_fill_kernel<T><<<grid, 384, 0, (cudaStream_t)stream_>>>(a, out);
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;
 }
@@ -239,7 +286,7 @@ static int dense_fill_bwd_impl(const T* dout, const int32_t* const* rank_grids, 
     dense_fill_bwd_rows_kernel<T><<<gdmae_grid(total, 256, 32), 256, 0, st>>>(a, s, indices[s], n_sites[s], dout, (float4*)drows[s]);
     GDMAE_LAUNCH_CHECK();
   }
-  dim3 grid(GDMAE_NUM_SMS * 4, 3);
+  dim3 grid(GDMAE_NUM_SMS * 8, 3);
   dense_fill_bwd_bg_kernel<T><<<grid, 256, 0, st>>>(a, dout, dbg);
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;

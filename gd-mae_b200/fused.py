@@ -61,9 +61,9 @@ def _layout(t):
     return t, 0, t.stride(0)
 
 
-def gemm(a, b, out=None, beta=0.0):
-    """fp32 out (M,N) = a (M,K) @ b (K,N) (+ beta*out).  fp32 operands go through torch (cuBLAS, TF32 when
-    allowed); bf16 operands through gdmae_gemm (cuBLAS bf16 x bf16 -> fp32)."""
+def gemm(a, b, out=None, beta=0.0, out_dtype=F32):
+    """out (M,N) = a (M,K) @ b (K,N) (+ beta*out).  fp32 operands go through torch (cuBLAS, TF32 when
+    allowed); bf16 operands through gdmae_gemm (cublasLt bf16 x bf16 -> fp32 or bf16, cached algorithm)."""
     if a.dtype == F32:
         if out is None:
             return torch.mm(a, b)
@@ -71,11 +71,11 @@ def gemm(a, b, out=None, beta=0.0):
     M, K = a.shape
     N = b.shape[1]
     if out is None:
-        out = torch.empty((M, N), dtype=F32, device=a.device)
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
     a, ta, lda = _layout(a)
     b, tb, ldb = _layout(b)
     L.check(L.lib().gdmae_gemm(ta, tb, L.i64(M), L.i64(N), L.i64(K), _ptr(a), L.i64(lda), _ptr(b), L.i64(ldb), 1, _ptr(out),
-                               L.i64(out.stride(0)), L.f32(beta), L.stream()), "gdmae_gemm")
+                               L.i64(out.stride(0)), _ops._DT[out.dtype], L.f32(beta), L.stream()), "gdmae_gemm")
     return out
 
 
@@ -241,7 +241,7 @@ class SparseConvFunction(torch.autograd.Function):
         col, w, bwd_map = ctx.saved_tensors
         dyg = _g(dy.contiguous())
         dw = gemm(dyg.t(), col).view(ctx.wshape)
-        dcol = torch.mm(dyg, w)                              # operand dtype (bf16 output in the bf16 configuration)
+        dcol = gemm(dyg, w, out_dtype=GEMM_DTYPE)            # operand dtype (bf16 output in the bf16 configuration)
         dx = _ops.gather_rows_transposed(dcol, bwd_map, ctx.n_src, ctx.mirror)
         return dx, dw, None, None, None
 

@@ -277,9 +277,10 @@ def sra_fwd(qkv, lut, tau, table, tau_min, nhead, bv=None, out_dtype=torch.float
     lse = torch.empty((N, nhead), dtype=F32, device=qkv.device)
     # algorithmic bytes (SURVEY.md 8d, a18 minus projections): N*d*(3*s_in + s_out) + N*8
     with L.timed(f"sra_fwd_d{d}", N * d * (12 + out.element_size()) + N * 8):
-        if SRA_TENSOR_CORES and bv is None and out_dtype == F32:
+        if SRA_TENSOR_CORES:
             L.check(L.lib().gdmae_sra_attention_fwd_tc(L.P(qkv), L.P(lut), L.P(table.row_info), L.i64(N), d, nhead, L.P(tau),
-                                                       L.f32(tau_min), L.P(out), L.P(lse), L.stream()), "gdmae_sra_attention_fwd_tc")
+                                                       L.f32(tau_min), L.P(bv), _DT[out_dtype], L.P(out), L.P(lse), L.stream()),
+                    "gdmae_sra_attention_fwd_tc")
         else:
             L.check(L.lib().gdmae_sra_attention_fwd(L.P(qkv), L.P(lut), L.P(table.row_info), L.i64(N), d, nhead, L.P(tau),
                                                     L.f32(tau_min), L.P(bv), _DT[out_dtype], L.P(out), L.P(lse), L.stream()),

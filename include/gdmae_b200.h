@@ -140,9 +140,10 @@ int gdmae_window_table(const int32_t* indices, int64_t N, int B, int H, int W, i
 int gdmae_sra_attention_fwd(const float* qkv, const float* lut, const int32_t* row_info, int64_t N, int d, int nhead,
                             const float* tau, float tau_min, const float* bv, int io_bf16, void* out, float* lse,
                             void* stream);
-/* same operator, QK^T and PV on the tensor cores (TF32 mma, fp32 accumulate, softmax in fp32); fp32 out, bv in qkv */
+/* same operator and arguments, QK^T and PV on the tensor cores (TF32 mma, fp32 accumulate, softmax in fp32) */
 int gdmae_sra_attention_fwd_tc(const float* qkv, const float* lut, const int32_t* row_info, int64_t N, int d, int nhead,
-                               const float* tau, float tau_min, float* out, float* lse, void* stream);
+                               const float* tau, float tau_min, const float* bv, int io_bf16, void* out, float* lse,
+                               void* stream);
 int gdmae_sra_attention_bwd(const float* qkv, const float* lut, const int32_t* row_info, int64_t N, int d, int nhead,
                             const float* tau, float tau_min, const float* bv, int io_bf16, const void* out,
                             const float* lse, const float* dout, void* dqkv, double* dtau_sum, float* work_D,
@@ -169,10 +170,12 @@ int gdmae_gather_add_rows(const float* x, const float* table, const uint8_t* idx
                           void* out_bf16, void* stream);
 
 /* ---- plain dense GEMM through cuBLAS (library GEMM) ------------------------------------------------
- * row-major C (M,N) fp32 = op(A) op(B) + beta*C; A/B fp32 (TF32 math, ab_dtype 0) or bf16 (1).
+ * row-major C (M,N) = op(A) op(B) + beta*C; A/B fp32 (TF32 math, ab_dtype 0) or bf16 (1); C fp32 or bf16.
+ * Owns one cublasLt handle + 64 MB scratch per device (created on first use) and caches the selected
+ * algorithm per shape bucket: the heuristic costs ~200 us of host time per call otherwise.
  * replaces F.linear of the projections / FFN / sparse-conv GEMMs (cosine_msa.py:57-62,431, sst_basic_block.py:81). */
 int gdmae_gemm(int transa, int transb, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
-               int64_t ldb, int ab_dtype, float* C, int64_t ldc, float beta, void* stream);
+               int64_t ldb, int ab_dtype, void* C, int64_t ldc, int c_dtype /* 0 fp32, 1 bf16 */, float beta, void* stream);
 
 /* ---- a5/a9/a21/a22 training-mode BatchNorm (+ReLU) over (N, C) rows ------------------------------
  * replaces norm_fn + nn.ReLU of post_act_block (pcdet/utils/spconv_utils.py:50-54), of make_fc_layers

@@ -404,6 +404,15 @@ def test_sra_tensor_core_kernel_matches_simt(G, d):
         print(f"sra tc d={d} shift={shift}: rel err out {e_o:.2e} lse {e_l:.2e}")
         assert e_o < 4e-3, e_o      # TF32 operands (10-bit mantissa) on scores up to 1/tau = 1.4
         assert e_l < 4e-3, e_l
+        # value bias folded into the output, bf16 output (the bench configuration's call)
+        bv = torch.randn(d, generator=g).cuda()
+        o_ref, _ = G.ops.sra_fwd(qkv, lut, tau, table, 0.01, 8, bv=bv, out_dtype=torch.bfloat16)
+        G.ops.SRA_TENSOR_CORES = True
+        try:
+            o_tc, _ = G.ops.sra_fwd(qkv, lut, tau, table, 0.01, 8, bv=bv, out_dtype=torch.bfloat16)
+        finally:
+            G.ops.SRA_TENSOR_CORES = False
+        assert rel(o_tc.float(), o_ref.float()) < 8e-3
 
 
 def test_bf16_configuration_close_to_reference(G, golden):

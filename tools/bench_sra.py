@@ -22,12 +22,7 @@ from oracle import gdmae_oracle as O  # noqa: E402  (synthetic scene generator o
 CSRC = os.path.join(ROOT, "gd-mae_b200", "csrc")
 OUT = os.path.join(ROOT, "gpurun_out", "variants")
 VARIANTS = {  # name: (BIN, SLICE, FWD_THREADS, BWD_THREADS, MIN_CTAS)
-    "b32_s128_t256": (32, 128, 256, 128, 2),
-    "b16_s64_t128": (16, 64, 128, 128, 4),
-    "b32_s64_t128": (32, 64, 128, 128, 3),
-    "b16_s128_t256": (16, 128, 256, 128, 2),
     "b64_s64_t256": (64, 64, 256, 128, 2),
-    "b32_s128_t512": (32, 128, 512, 256, 1),
 }
 
 
@@ -105,12 +100,12 @@ def main():
             work = torch.empty(N, 8, device="cuda")
 
             def fwd():
-                rc = lib.gdmae_sra_attention_fwd(L.P(qkv), L.P(lut), L.P(t.row_info), L.i64(N), d, 8, L.P(tau), L.f32(0.01), L.P(out),
+                rc = lib.gdmae_sra_attention_fwd(L.P(qkv), L.P(lut), L.P(t.row_info), L.i64(N), d, 8, L.P(tau), L.f32(0.01), None, 0, L.P(out),
                                                  L.P(lse), st())
                 assert rc == 0, lib.gdmae_last_error()
 
             def bwd():
-                rc = lib.gdmae_sra_attention_bwd(L.P(qkv), L.P(lut), L.P(t.row_info), L.i64(N), d, 8, L.P(tau), L.f32(0.01), L.P(out),
+                rc = lib.gdmae_sra_attention_bwd(L.P(qkv), L.P(lut), L.P(t.row_info), L.i64(N), d, 8, L.P(tau), L.f32(0.01), None, 0, L.P(out),
                                                  L.P(lse), L.P(dout), L.P(dqkv), L.P(dts), L.P(work), st())
                 assert rc == 0, lib.gdmae_last_error()
 
@@ -127,7 +122,7 @@ def main():
         fn = L.lib().gdmae_sra_attention_fwd_tc
 
         def fwd_tc():
-            L.check(fn(L.P(qkv), L.P(lut), L.P(t.row_info), L.i64(N), d, 8, L.P(tau), L.f32(0.01), L.P(out), L.P(lse), st()), "tc")
+            L.check(fn(L.P(qkv), L.P(lut), L.P(t.row_info), L.i64(N), d, 8, L.P(tau), L.f32(0.01), None, 0, L.P(out), L.P(lse), st()), "tc")
 
         tf = timeit(fwd_tc, flush)
         print(f"   {'tensor-core fwd':16s} fwd {tf:7.1f} us ({fb / tf / 1e3 / 6538.3:.3f} of peak)   max|diff| {float((out - ref[0]).abs().max()):.2e}")
