@@ -41,10 +41,11 @@ static int lt_fail(const char* what, int st) {
   } while (0)
 
 // Row-major: C (M,N, ldc) = op(A) (M,K) * op(B) (K,N) + beta * C.  transa: A is stored (K,M) with leading
-// dimension lda; transb: B is stored (N,K).  ab_dtype: 0 fp32 (TF32 math), 1 bf16.  c_dtype: 0 fp32, 1 bf16 (bf16 operands only).
+// dimension lda; transb: B is stored (N,K).  ab_dtype: 0 fp32 (TF32 math), 1 bf16, 2 fp32 (fp32 math).  c_dtype: 0 fp32, 1 bf16
+// (bf16 operands only).
 extern "C" int gdmae_gemm(int transa, int transb, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
                           int64_t ldb, int ab_dtype, void* C, int64_t ldc, int c_dtype, float beta, void* stream_) {
-  GDMAE_CHECK_ARG(M >= 0 && N >= 0 && K >= 0 && (ab_dtype == 0 || ab_dtype == 1) && (c_dtype == 0 || (c_dtype == 1 && ab_dtype == 1)));
+  GDMAE_CHECK_ARG(M >= 0 && N >= 0 && K >= 0 && (ab_dtype >= 0 && ab_dtype <= 2) && (c_dtype == 0 || (c_dtype == 1 && ab_dtype == 1)));
   if (M == 0 || N == 0) return GDMAE_OK;
   int dev = 0;
   GDMAE_CHECK_CUDA(cudaGetDevice(&dev));
@@ -55,7 +56,7 @@ extern "C" int gdmae_gemm(int transa, int transb, int64_t M, int64_t N, int64_t 
     LT_CHECK(cublasLtCreate(&S.lt));
     GDMAE_CHECK_CUDA(cudaMalloc(&S.workspace, GEMM_WS_BYTES));
   }
-  cudaDataType_t ab = ab_dtype == 0 ? CUDA_R_32F : CUDA_R_16BF;
+  cudaDataType_t ab = ab_dtype == 1 ? CUDA_R_16BF : CUDA_R_32F;
   cublasComputeType_t ct = ab_dtype == 0 ? CUBLAS_COMPUTE_32F_FAST_TF32 : CUBLAS_COMPUTE_32F;
   // column-major view of the row-major problem: C^T (N,M) = op(B)^T op(A)^T
   cublasOperation_t op1 = transb ? CUBLAS_OP_T : CUBLAS_OP_N;  // applies to B's memory
@@ -70,7 +71,7 @@ extern "C" int gdmae_gemm(int transa, int transb, int64_t M, int64_t N, int64_t 
   LT_CHECK(cublasLtMatrixLayoutCreate(&lc, c_dtype == 0 ? CUDA_R_32F : CUDA_R_16BF, N, M, ldc));
   const float alpha = 1.f;
   auto bucket = [](long long v) { return v <= 4096 ? v : (v + 4095) / 4096 * 4096; };
-  auto key = std::make_tuple(transa, transb, ab_dtype + 2 * (beta != 0.f) + 4 * c_dtype, bucket(M), bucket(N), bucket(K));
+  auto key = std::make_tuple(transa, transb, ab_dtype + 4 * (beta != 0.f) + 8 * c_dtype, bucket(M), bucket(N), bucket(K));
   int rc = GDMAE_OK;
   for (int attempt = 0; attempt < 2; ++attempt) {
     auto it = S.algos.find(key);

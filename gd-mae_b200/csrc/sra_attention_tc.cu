@@ -1,342 +1,446 @@
-// Sparse Regional Attention forward on tensor cores (TF32 mma.sync m16n8k8, fp32 accumulate).
+// Sparse Regional Attention on the tensor cores: bf16 mma.sync m16n8k16 with fp32 accumulation,
+// operands fetched with ldmatrix - the kernel of the bf16 configuration.
 //
 // Same operator and data layout as sra_attention.cu (reference: cosine_msa.py:114-176,
 // sst_basic_block.py:22-54, sst_utils.py:107-181): flat tokens, CSR windows, 64-row positional
-// LUT, nothing padded in HBM.  The fp32 SIMT kernel is the parity path; at pyramid scales 2 and 3
-// (13-28 tokens per window) its partner loop is instruction bound (r1 ncu: 107 M warp
-// instructions for 16 M query-key-head triples) and each of its CTAs pays the whole
-// row_info -> q/k/v -> LUT dependent-load chain before any math.  This kernel
-//   * is persistent: one CTA per SM owns a 64-channel slice (2 heads of 32 or 4 heads of 16) and
-//     walks bins of 32 CSR rows (the windows that START in the bin, <= 95 rows).  The slice's 64 x 128
-//     positional LUT lives in shared memory for the whole kernel;
-//   * is software pipelined with cp.async: while bin k is normalised and multiplied, the raw q/k/v
-//     rows of bin k+1 and the row_info records of bin k+2 are in flight (two data buffers, three
-//     record buffers), so the dependent-load chain is off the critical path;
-//   * normalises in place: +LUT, L2-normalise q and k per head, fold 1/tau into q, round all three
-//     operands to TF32; 16 zero rows follow the bin so MMA tiles may overrun a window;
-//   * runs the two contractions of a window - S = Q K^T and O = P V - on the tensor cores, one warp
-//     per (window, head, 16-query tile).  S tiles stay in registers, the softmax runs on the C
-//     fragments (quad shuffles), and P feeds the second MMA straight from registers: the C->A
-//     fragment mismatch is absorbed by permuting the key index of the V fragment
-//     (A col t <-> key 2t, A col t+4 <-> key 2t+1), so P never touches shared memory;
-//   * pitch 68 floats: every fragment load is bank-conflict free.
-// TF32 operands (10-bit mantissa) put this kernel in the bf16/tf32 performance configuration;
-// parity tests use the fp32 kernel and hold this one to 4e-3.
+// LUT, nothing padded in HBM; here q/k/v arrive as bf16 (the in-projection GEMM writes them so).
+// The fp32 SIMT kernel is the parity path.  Its r1 profile: 107 M warp instructions per launch for
+// 16 M query-key-head triples, issue bound; every CTA pays the row_info -> q/k/v -> LUT dependent
+// load chain before any math.  This kernel removes both:
+//   * persistent, one CTA per SM, each owning a 64-channel slice (2 heads of 32 or 4 heads of 16) and
+//     walking bins of 64 CSR rows (the windows that START in the bin, <= 127 rows).  The slice of the
+//     positional LUT lives in shared memory (bf16) for the whole kernel;
+//   * warp specialised, three stage buffers: in iteration j the 8 "stager" warps take bin j (wait for
+//     its cp.async rows, build the work units, normalise q and k in place) while the 8 "math" warps
+//     run the MMAs of bin j-1 and the rows of bin j+1 / the row_info records of bins j+2, j+3 are in
+//     flight; work units are handed out through a shared-memory counter and the stagers join the math
+//     once their bin is staged; one CTA barrier per iteration;
+//   * one pass over q and k only: + LUT, L2-normalise per head, fold log2(e)/tau into q, back to
+//     bf16 in place.  v is used as it arrives;
+//   * work units are PACKED: a unit is either a run of whole small windows totalling <= 16 rows, or a
+//     16-row chunk of a large window; per-row key bounds (from row_info) give the block-diagonal
+//     mask.  A 3-token window therefore costs 3/16 of an MMA tile instead of a whole one;
+//   * one warp per (unit, head): S = Q K^T accumulates in registers (ldmatrix operands), the softmax
+//     runs on the C fragments with quad shuffles, P goes back into the second MMA as the A operand
+//     directly from registers, V comes in through ldmatrix.trans.  Row pitch 144 B makes every
+//     ldmatrix phase conflict free.  The unit body is compiled for 16 / 32 / 48 / 64 keys.
+// bf16 operands (8-bit mantissa): tests hold this kernel to 1e-2 against the fp32 kernel on the same
+// (bf16-rounded) inputs.
 #include "common.cuh"
 #include <cuda_bf16.h>
 
-#define TC_EPS 1e-12f
-#define TC_BIN 32
-#define TC_ROWS 112            // 95 rows + 16 zero pad rows + 1
-#define TC_INFO (TC_BIN + 64)  // row_info records cached per bin
-#define TC_SLICE 64
-#define TC_C4 (TC_SLICE / 4)
-#define TC_PITCH (TC_SLICE + 4)
-#define TC_THREADS 512
-#define TC_BUF_FLOATS (3 * TC_ROWS * TC_PITCH)
-#define TC_UNITS 192           // >= heads x 16-query tiles of one bin
-#define TC_SMEM_BYTES (64 * 2 * TC_SLICE * 4 + 2 * TC_BUF_FLOATS * 4 + 3 * TC_INFO * 16 + TC_UNITS * 4 + 64)
+#define MM_BIN 64
+#define MM_ROWS 144            // 127 rows + 16 rows of MMA overrun + 1
+#define MM_INFO 128            // row_info records cached per bin
+#define MM_SLICE 64
+#define MM_PITCH 72            // bf16 elements per smem row (144 B)
+#define MM_THREADS 512
+#define MM_GROUP 256           // threads per role
+#define MM_STAGES 3
+#define MM_NINFO 5
+#define MM_UNITS 48
+#define MM_ARR (MM_ROWS * MM_PITCH)
+#define MM_STAGE_ELEMS (3 * MM_ARR)
+#define MM_SMEM_BYTES (64 * 2 * MM_SLICE * 2 + MM_STAGES * MM_STAGE_ELEMS * 2 + MM_NINFO * MM_INFO * 16 + 2 * (MM_UNITS + 16) * 4)
 
-struct TcArgs {
-  const float* qkv;
-  const float* lut;
+typedef __nv_bfloat16 bf16;
+
+struct MmArgs {
+  const bf16* qkv;     // (N, 3d) bf16
+  const float* lut;    // (64, 2d)
   const int4* row_info;
   const float* tau;
-  const float* bv;   // (d) value bias added to the output, nullable
+  const float* bv;     // (d) value bias added to the output, nullable
   float tau_min;
   int N, d;
   int out_bf16;
 };
 
-__device__ __forceinline__ float to_tf32(float x) {
-  unsigned int u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
-}
-
-__device__ __forceinline__ void mma_tf32(float (&c)[4], const float (&a)[4], float b0, float b1) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
-                 "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
-}
-
-__device__ __forceinline__ void tc_cp_async16(void* smem_dst, const void* gmem_src) {
+__device__ __forceinline__ void mm_cp16(void* smem_dst, const void* gmem_src) {
   unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
 }
-__device__ __forceinline__ void tc_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tc_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void mm_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void mm_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+__device__ __forceinline__ void mm_bar_stagers() { asm volatile("bar.sync 1, %0;" ::"n"(MM_GROUP) : "memory"); }
 
-// rows [row0, row1) = the windows that start inside the bin; inf = records of rows bin .. bin+95
-__device__ __forceinline__ void tc_bin_range(const int4* inf, int bin, int N, int& row0, int& R) {
+__device__ __forceinline__ void ldsm_x4(unsigned (&r)[4], const bf16* p) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(sa));
+}
+__device__ __forceinline__ void ldsm_x4_t(unsigned (&r)[4], const bf16* p) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(sa));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ unsigned pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<unsigned*>(&v);
+}
+
+// rows [row0, row1) = the windows that start inside the bin; inf = records of rows bin .. bin+127
+__device__ __forceinline__ void mm_bin_range(const int4* inf, int bin, int N, int& row0, int& R) {
   int4 f = inf[0];
   row0 = (f.y == bin) ? bin : f.z;
   int row1 = N;
-  if (bin + TC_BIN < N) {
-    int4 l = inf[TC_BIN];
-    row1 = (l.y == bin + TC_BIN) ? bin + TC_BIN : l.z;
+  if (bin + MM_BIN < N) {
+    int4 l = inf[MM_BIN];
+    row1 = (l.y == bin + MM_BIN) ? bin + MM_BIN : l.z;
   }
   R = row1 - row0;
+  if (R < 0) R = 0;
 }
 
-__device__ __forceinline__ void tc_issue_info(int4* inf, const int4* row_info, int bin, int N, int tid) {
-  if (tid < TC_INFO && bin + tid < N) tc_cp_async16(inf + tid, row_info + bin + tid);
+// the stager group (MM_GROUP threads, index gt) issues all copies
+__device__ __forceinline__ void mm_issue_info(int4* inf, const int4* row_info, int bin, int N, int gt) {
+  if (gt < MM_INFO && bin + gt < N) mm_cp16(inf + gt, row_info + bin + gt);
 }
 
-__device__ __forceinline__ void tc_issue_rows(float* buf, const int4* inf, const float* qkv, int d, int col, int row0, int bin, int R,
-                                              int tid) {
+__device__ __forceinline__ void mm_issue_rows(bf16* stage, const int4* inf, const bf16* qkv, int d, int col, int bin, int N, int gt) {
+  int row0, R;
+  mm_bin_range(inf, bin, N, row0, R);
   const int shift = row0 - bin;
-  float* sq = buf;
-  float* sk = sq + TC_ROWS * TC_PITCH;
-  float* sv = sk + TC_ROWS * TC_PITCH;
-  for (int idx = tid; idx < R * TC_C4; idx += TC_THREADS) {
-    int r = idx / TC_C4, c4 = idx % TC_C4;
-    const float* base = qkv + (long long)inf[r + shift].x * 3 * d + col + 4 * c4;
-    tc_cp_async16(sq + r * TC_PITCH + 4 * c4, base);
-    tc_cp_async16(sk + r * TC_PITCH + 4 * c4, base + d);
-    tc_cp_async16(sv + r * TC_PITCH + 4 * c4, base + 2 * d);
+  for (int idx = gt; idx < R * 8; idx += MM_GROUP) {      // one 16-byte chunk of q, k and v each
+    const int r = idx >> 3, c8 = idx & 7;
+    const bf16* src = qkv + (long long)inf[r + shift].x * 3 * d + col + 8 * c8;
+    bf16* dst = stage + r * MM_PITCH + 8 * c8;
+    mm_cp16(dst, src);
+    mm_cp16(dst + MM_ARR, src + d);
+    mm_cp16(dst + 2 * MM_ARR, src + 2 * d);
+  }
+}
+
+// bits [pos, pos+32) of the 128-bit mask (m1:m0)
+__device__ __forceinline__ unsigned mm_bits(unsigned long long m0, unsigned long long m1, int pos) {
+  unsigned long long v;
+  if (pos >= 128) return 0u;
+  if (pos >= 64) v = m1 >> (pos - 64);
+  else v = (m0 >> pos) | (pos ? (m1 << (64 - pos)) : 0ull);
+  return (unsigned)v;
+}
+
+// One (unit, head) on one warp: S = Q K^T, masked softmax, O = P V, for NT2 8-key tiles (NT2 even).
+template <int HD, int NT2>
+__device__ __forceinline__ void mm_unit(const MmArgs& a, const bf16* sq, const bf16* sk, const bf16* sv, int q0, int qn, int k0,
+                                        int ch, int4 recA, int4 recB, int kbase, int lane, long long out_col, int lse_col,
+                                        void* __restrict__ out, float* __restrict__ lse) {
+  constexpr int KS = HD / 16, ND = HD / 8;
+  const int g = lane >> 2, t = lane & 3;
+  const int loA = recA.y - kbase, wA = recA.z - recA.y, loB = recB.y - kbase, wB = recB.z - recB.y;
+  unsigned qa[KS][4];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks)
+    ldsm_x4(qa[ks], sq + (q0 + (lane & 7) + 8 * ((lane >> 3) & 1)) * MM_PITCH + ch + 16 * ks + 8 * (lane >> 4));
+  float c[NT2][4];
+#pragma unroll
+  for (int nt = 0; nt < NT2; ++nt) c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;
+#pragma unroll
+  for (int np = 0; np < NT2 / 2; ++np) {
+    unsigned kb[4];
+    if (KS == 2) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        ldsm_x4(kb, sk + (k0 + 8 * (2 * np + u) + (lane & 7)) * MM_PITCH + ch + 8 * (lane >> 3));
+        mma_bf16(c[2 * np + u], qa[0], kb[0], kb[1]);
+        mma_bf16(c[2 * np + u], qa[KS - 1], kb[2], kb[3]);
+      }
+    } else {
+      ldsm_x4(kb, sk + (k0 + 16 * np + 8 * (lane >> 4) + (lane & 7)) * MM_PITCH + ch + 8 * ((lane >> 3) & 1));
+      mma_bf16(c[2 * np], qa[0], kb[0], kb[1]);
+      mma_bf16(c[2 * np + 1], qa[0], kb[2], kb[3]);
+    }
+  }
+  // block-diagonal mask + row max
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+  const int ka = 2 * t - loA, kb_ = 2 * t - loB;
+#pragma unroll
+  for (int nt = 0; nt < NT2; ++nt) {
+    if ((unsigned)(ka + 8 * nt) >= (unsigned)wA) c[nt][0] = -INFINITY;
+    if ((unsigned)(ka + 8 * nt + 1) >= (unsigned)wA) c[nt][1] = -INFINITY;
+    if ((unsigned)(kb_ + 8 * nt) >= (unsigned)wB) c[nt][2] = -INFINITY;
+    if ((unsigned)(kb_ + 8 * nt + 1) >= (unsigned)wB) c[nt][3] = -INFINITY;
+    mx0 = fmaxf(mx0, fmaxf(c[nt][0], c[nt][1]));
+    mx1 = fmaxf(mx1, fmaxf(c[nt][2], c[nt][3]));
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < NT2; ++nt) {
+    c[nt][0] = fast_exp2(c[nt][0] - mx0); c[nt][1] = fast_exp2(c[nt][1] - mx0);
+    c[nt][2] = fast_exp2(c[nt][2] - mx1); c[nt][3] = fast_exp2(c[nt][3] - mx1);
+    l0 += c[nt][0] + c[nt][1];
+    l1 += c[nt][2] + c[nt][3];
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  float o[ND][4];
+#pragma unroll
+  for (int nd = 0; nd < ND; ++nd) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
+#pragma unroll
+  for (int kt = 0; kt < NT2 / 2; ++kt) {
+    const unsigned pa[4] = {pack_bf16(c[2 * kt][0], c[2 * kt][1]), pack_bf16(c[2 * kt][2], c[2 * kt][3]),
+                            pack_bf16(c[2 * kt + 1][0], c[2 * kt + 1][1]), pack_bf16(c[2 * kt + 1][2], c[2 * kt + 1][3])};
+#pragma unroll
+    for (int np = 0; np < ND / 2; ++np) {
+      unsigned vb[4];
+      ldsm_x4_t(vb, sv + (k0 + 16 * kt + (lane & 7) + 8 * ((lane >> 3) & 1)) * MM_PITCH + ch + 16 * np + 8 * (lane >> 4));
+      mma_bf16(o[2 * np], pa, vb[0], vb[1]);
+      mma_bf16(o[2 * np + 1], pa, vb[2], vb[3]);
+    }
+  }
+  float2 bias[ND];
+#pragma unroll
+  for (int nd = 0; nd < ND; ++nd)
+    bias[nd] = a.bv ? __ldg(reinterpret_cast<const float2*>(a.bv + out_col + 8 * nd + 2 * t)) : make_float2(0.f, 0.f);
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    if (g + 8 * half < qn) {
+      const int tok = half ? recB.x : recA.x;
+      const float il = __fdividef(1.f, half ? l1 : l0);
+      const long long e0 = (long long)tok * a.d + out_col + 2 * t;
+#pragma unroll
+      for (int nd = 0; nd < ND; ++nd) {
+        const float x0 = fmaf(o[nd][2 * half], il, bias[nd].x), x1 = fmaf(o[nd][2 * half + 1], il, bias[nd].y);
+        if (a.out_bf16) *reinterpret_cast<unsigned*>((bf16*)out + e0 + 8 * nd) = pack_bf16(x0, x1);
+        else *reinterpret_cast<float2*>((float*)out + e0 + 8 * nd) = make_float2(x0, x1);
+      }
+      // natural-log lse of the scores S = cos / tau (the backward kernels expect it)
+      if (t == 0) lse[(long long)tok * 8 + lse_col] = ((half ? mx1 : mx0) + __log2f(half ? l1 : l0)) * 0.6931471805599453f;
+    }
   }
 }
 
 template <int HD>
-__global__ void __launch_bounds__(TC_THREADS, 1) sra_fwd_tc_kernel(TcArgs a, void* __restrict__ out, float* __restrict__ lse) {
+__global__ void __launch_bounds__(MM_THREADS, 1) sra_fwd_mma_kernel(MmArgs a, void* __restrict__ out, float* __restrict__ lse) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* slut = (float*)smem_raw;                            // [64][128]: q part | k part of this slice
-  float* sbuf = slut + 64 * 2 * TC_SLICE;                    // two data buffers
-  int4* sinfo_all = (int4*)(sbuf + 2 * TC_BUF_FLOATS);       // three record buffers
-  int* sunit = (int*)(sinfo_all + 3 * TC_INFO);              // work units of the current bin: window start | n | head | tile
-  int* hdr = sunit + TC_UNITS;                               // [0] number of units
-  constexpr int HS = TC_SLICE / HD;
-  constexpr int LPH = HD / 4;
-  constexpr int KS = HD / 8;    // k-steps of Q K^T, n-tiles of the output
+  bf16* slut = (bf16*)smem_raw;                               // [64][128]: q part | k part of this slice
+  bf16* sdata = slut + 64 * 2 * MM_SLICE;                     // MM_STAGES x {q, k, v} x [144][72]
+  int4* sinfo_all = (int4*)(sdata + MM_STAGES * MM_STAGE_ELEMS);
+  int* sunit_all = (int*)(sinfo_all + MM_NINFO * MM_INFO);    // 2 x { units: q0 | qn << 7 | k0 << 12 | kn << 19 ; [MM_UNITS] = count }
+  constexpr int HS = MM_SLICE / HD;
   const int d = a.d;
-  const int nsl = d / TC_SLICE;
+  const int nsl = d / MM_SLICE;
   const int sl = blockIdx.x % nsl, cta = blockIdx.x / nsl, ncta = gridDim.x / nsl;
-  const int col = sl * TC_SLICE;
+  const int col = sl * MM_SLICE;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nbins = (a.N + TC_BIN - 1) / TC_BIN;
-  const int nwarps = TC_THREADS >> 5;
-  const int g = lane >> 2, t = lane & 3;
+  const int nbins = (a.N + MM_BIN - 1) / MM_BIN;
+  constexpr int GW = MM_GROUP >> 5;                           // warps per role
+  const bool stager = warp < GW;
+  const int gt = tid & (MM_GROUP - 1), gw = warp & (GW - 1);
   if (cta >= nbins) return;
+  const int my_bins = (nbins - cta + ncta - 1) / ncta;        // bins cta, cta + ncta, ...
 
-  // ---- prologue: LUT slice, records of the first two bins, rows of the first bin
-  for (int idx = tid; idx < 64 * 2 * TC_C4; idx += TC_THREADS) {
-    int pos = idx / (2 * TC_C4), rem = idx % (2 * TC_C4);
-    int part = rem / TC_C4, c4 = rem % TC_C4;
-    tc_cp_async16(slut + pos * 2 * TC_SLICE + part * TC_SLICE + 4 * c4, a.lut + (long long)pos * 2 * d + part * d + col + 4 * c4);
+  // ---- prologue: zero the data buffers (overrun rows must hold finite values), LUT slice -> bf16, first records
+  for (int i = tid; i < MM_STAGES * MM_STAGE_ELEMS / 8; i += MM_THREADS) reinterpret_cast<uint4*>(sdata)[i] = make_uint4(0, 0, 0, 0);
+  for (int idx = tid; idx < 64 * MM_SLICE; idx += MM_THREADS) {      // one bf16 pair each
+    int pos = idx >> 6, c2 = idx & 63;
+    int part = c2 >> 5, cc = (c2 & 31) * 2;
+    float2 v = __ldg(reinterpret_cast<const float2*>(a.lut + (long long)pos * 2 * d + part * d + col + cc));
+    *reinterpret_cast<unsigned*>(slut + pos * 2 * MM_SLICE + part * MM_SLICE + cc) = pack_bf16(v.x, v.y);
   }
-  tc_issue_info(sinfo_all, a.row_info, cta * TC_BIN, a.N, tid);
-  if (cta + ncta < nbins) tc_issue_info(sinfo_all + TC_INFO, a.row_info, (cta + ncta) * TC_BIN, a.N, tid);
-  tc_commit();
-  tc_wait_all();
+  if (stager) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      if (j < my_bins) mm_issue_info(sinfo_all + j * MM_INFO, a.row_info, (cta + j * ncta) * MM_BIN, a.N, gt);
+    mm_commit();
+    mm_wait<0>();
+  }
   __syncthreads();
-  {
-    int row0, R;
-    tc_bin_range(sinfo_all, cta * TC_BIN, a.N, row0, R);
-    tc_issue_rows(sbuf, sinfo_all, a.qkv, d, col, row0, cta * TC_BIN, R, tid);
-    tc_commit();
+  if (stager) {
+    // the copy group committed at the end of iteration j holds the rows of bin j+1 and the records of bin j+3
+    mm_issue_rows(sdata, sinfo_all, a.qkv, d, col, cta * MM_BIN, a.N, gt);
+    mm_commit();
   }
-  const float inv_tau = 1.f / fmaxf(__ldg(a.tau), a.tau_min);
+  const float qscale = 1.4426950408889634f / fmaxf(__ldg(a.tau), a.tau_min);   // log2(e) / tau: softmax in base 2
 
-  for (int k = 0;; ++k) {
-    const int bi = cta + k * ncta;
-    if (bi >= nbins) break;
-    const int bin = bi * TC_BIN;
-    const int4* sinfo = sinfo_all + (k % 3) * TC_INFO;
-    float* sq = sbuf + (k & 1) * TC_BUF_FLOATS;
-    float* sk = sq + TC_ROWS * TC_PITCH;
-    float* sv = sk + TC_ROWS * TC_PITCH;
-    tc_wait_all();       // rows of bin k, records of bin k+1
-    __syncthreads();     // ... visible to all; everyone is done with bin k-1 (its buffers are free)
-    // ---- keep the pipe full: rows of bin k+1, records of bin k+2
-    if (bi + ncta < nbins) {
-      const int4* ninfo = sinfo_all + ((k + 1) % 3) * TC_INFO;
-      int nrow0, nR;
-      tc_bin_range(ninfo, (bi + ncta) * TC_BIN, a.N, nrow0, nR);
-      tc_issue_rows(sbuf + ((k + 1) & 1) * TC_BUF_FLOATS, ninfo, a.qkv, d, col, nrow0, (bi + ncta) * TC_BIN, nR, tid);
-      if (bi + 2 * ncta < nbins) tc_issue_info(sinfo_all + ((k + 2) % 3) * TC_INFO, a.row_info, (bi + 2 * ncta) * TC_BIN, a.N, tid);
-    }
-    tc_commit();
-
-    int row0, R;
-    tc_bin_range(sinfo, bin, a.N, row0, R);
-    if (R == 0) continue;
-    const int shift = row0 - bin;
-    // ---- work units of the bin: (window, head, 16-query tile), built by one warp while the others normalise
-    if (warp == nwarps - 1) {
-      int base = 0;
-      for (int r0 = 0; r0 < R; r0 += 32) {
-        int r = r0 + lane;
-        int4 rec = sinfo[min(r, R - 1) + shift];
-        bool st = r < R && rec.y == row0 + r;
-        int n = rec.z - rec.y;
-        int cnt = st ? HS * ((n + 15) >> 4) : 0;
-        int incl = cnt;
+  for (int j = 0; j <= my_bins; ++j) {
+    if (stager) {
+      // ================= stagers: bin j
+      if (j < my_bins) {
+        const int bin = (cta + j * ncta) * MM_BIN;
+        const int4* sinfo = sinfo_all + (j % MM_NINFO) * MM_INFO;
+        bf16* sq = sdata + (j % MM_STAGES) * MM_STAGE_ELEMS;
+        // rows of bin j+1 (needs the records of bin j+1: landed with the previous group) and records of bin j+3
+        if (j + 1 < my_bins)
+          mm_issue_rows(sdata + ((j + 1) % MM_STAGES) * MM_STAGE_ELEMS, sinfo_all + ((j + 1) % MM_NINFO) * MM_INFO, a.qkv, d, col,
+                        (cta + (j + 1) * ncta) * MM_BIN, a.N, gt);
+        if (j + 3 < my_bins)
+          mm_issue_info(sinfo_all + ((j + 3) % MM_NINFO) * MM_INFO, a.row_info, (cta + (j + 3) * ncta) * MM_BIN, a.N, gt);
+        mm_commit();
+        mm_wait<1>();          // everything but the group just committed: rows of bin j, records of bin j+2
+        mm_bar_stagers();      // ... from every stager thread
+        int row0, R;
+        mm_bin_range(sinfo, bin, a.N, row0, R);
+        const int shift = row0 - bin;
+        // ---- q and k in place: + LUT, L2-normalise per head, q also x log2(e)/tau; one task = 8 channels,
+        // two tasks per thread in flight
+        const int ntask = R * 16;
+        for (int base = 0; base < ntask; base += 2 * MM_GROUP) {
+          uint4 raw[2], lr[2];
+          bf16* p[2];
+          bool valid[2];
+          int part[2];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          int v = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += v;
-        }
-        int off = base + incl - cnt;
-        for (int j = 0; j < cnt; ++j) sunit[off + j] = r | (n << 8) | ((j % HS) << 16) | ((j / HS) << 20);
-        base += __shfl_sync(0xffffffffu, incl, 31);
-      }
-      if (lane == 0) hdr[0] = base;
-    }
-    // ---- in place: +LUT, normalise q (x 1/tau) and k per head, round q, k, v to TF32; zero 16 pad rows
-    {
-      const int Rp = min(R + 16, TC_ROWS);
-      const int steps = (Rp * TC_C4 + TC_THREADS - 1) / TC_THREADS;
-      for (int it = 0; it < steps; ++it) {
-        int idx = it * TC_THREADS + tid;
-        int r = idx / TC_C4, c4 = idx % TC_C4;
-        bool valid = r < R;
-        int rr = valid ? r : 0;
-        const float* lb = slut + sinfo[rr + shift].w * 2 * TC_SLICE + 4 * c4;
-        float4 q = *reinterpret_cast<const float4*>(sq + rr * TC_PITCH + 4 * c4);
-        float4 kk = *reinterpret_cast<const float4*>(sk + rr * TC_PITCH + 4 * c4);
-        float4 v = *reinterpret_cast<const float4*>(sv + rr * TC_PITCH + 4 * c4);
-        float4 lq = *reinterpret_cast<const float4*>(lb);
-        float4 lk = *reinterpret_cast<const float4*>(lb + TC_SLICE);
-        q.x += lq.x; q.y += lq.y; q.z += lq.z; q.w += lq.w;
-        kk.x += lk.x; kk.y += lk.y; kk.z += lk.z; kk.w += lk.w;
-        float sq2 = q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
-        float sk2 = kk.x * kk.x + kk.y * kk.y + kk.z * kk.z + kk.w * kk.w;
-#pragma unroll
-        for (int o = 1; o < LPH; o <<= 1) {
-          sq2 += __shfl_xor_sync(0xffffffffu, sq2, o);
-          sk2 += __shfl_xor_sync(0xffffffffu, sk2, o);
-        }
-        float fq = inv_tau / fmaxf(sqrtf(sq2), TC_EPS), fk = 1.f / fmaxf(sqrtf(sk2), TC_EPS);
-        if (r < Rp) {
-          float4 oq = make_float4(0.f, 0.f, 0.f, 0.f), ok = oq, ov = oq;
-          if (valid) {
-            oq = make_float4(to_tf32(q.x * fq), to_tf32(q.y * fq), to_tf32(q.z * fq), to_tf32(q.w * fq));
-            ok = make_float4(to_tf32(kk.x * fk), to_tf32(kk.y * fk), to_tf32(kk.z * fk), to_tf32(kk.w * fk));
-            ov = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+          for (int u = 0; u < 2; ++u) {
+            const int idx = base + u * MM_GROUP + gt;
+            valid[u] = idx < ntask;
+            const int r = valid[u] ? (idx >> 4) : 0;
+            part[u] = (idx >> 3) & 1;
+            const int c8 = idx & 7;
+            p[u] = sq + part[u] * MM_ARR + r * MM_PITCH + 8 * c8;
+            raw[u] = *reinterpret_cast<const uint4*>(p[u]);
+            lr[u] = *reinterpret_cast<const uint4*>(slut + sinfo[r + shift].w * 2 * MM_SLICE + part[u] * MM_SLICE + 8 * c8);
           }
-          *reinterpret_cast<float4*>(sq + r * TC_PITCH + 4 * c4) = oq;
-          *reinterpret_cast<float4*>(sk + r * TC_PITCH + 4 * c4) = ok;
-          *reinterpret_cast<float4*>(sv + r * TC_PITCH + 4 * c4) = ov;
-        }
-      }
-    }
-    __syncthreads();
-
-    // ---- one warp per (window, head, 16-query tile), round-robin
-    const int nunits = hdr[0];
-    for (int u = warp; u < nunits; u += nwarps) {
-      {
-        const int code = sunit[u];
-        const int s = code & 0xff, n = (code >> 8) & 0xff, h = (code >> 16) & 0xf, mt = code >> 20;
-        const int NT = (n + 7) >> 3;
-        const int ch = h * HD;
-        const int m0 = mt * 16;
-        float qa[KS][4];
-        const float* qr0 = sq + (s + m0 + g) * TC_PITCH + ch + t;
-        const float* qr1 = qr0 + 8 * TC_PITCH;
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-          qa[ks][0] = qr0[8 * ks];
-          qa[ks][1] = qr1[8 * ks];
-          qa[ks][2] = qr0[8 * ks + 4];
-          qa[ks][3] = qr1[8 * ks + 4];
-        }
-        float c[8][4];
+          for (int u = 0; u < 2; ++u) {
+            float x[8];
+            const unsigned rw[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w}, lw[4] = {lr[u].x, lr[u].y, lr[u].z, lr[u].w};
+            float ss = 0.f;
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;
-          if (nt < NT) {
-            const float* kr = sk + (s + 8 * nt + g) * TC_PITCH + ch + t;
-#pragma unroll
-            for (int ks = 0; ks < KS; ++ks) mma_tf32(c[nt], qa[ks], kr[8 * ks], kr[8 * ks + 4]);
-          }
-        }
-        float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          if (nt < NT) {
-            int k0 = 8 * nt + 2 * t;
-            if (k0 >= n) { c[nt][0] = -INFINITY; c[nt][2] = -INFINITY; }
-            if (k0 + 1 >= n) { c[nt][1] = -INFINITY; c[nt][3] = -INFINITY; }
-            mx0 = fmaxf(mx0, fmaxf(c[nt][0], c[nt][1]));
-            mx1 = fmaxf(mx1, fmaxf(c[nt][2], c[nt][3]));
-          }
-        }
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-        float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          if (nt < NT) {
-            c[nt][0] = __expf(c[nt][0] - mx0); c[nt][1] = __expf(c[nt][1] - mx0);
-            c[nt][2] = __expf(c[nt][2] - mx1); c[nt][3] = __expf(c[nt][3] - mx1);
-            l0 += c[nt][0] + c[nt][1];
-            l1 += c[nt][2] + c[nt][3];
-          }
-        }
-        l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-        l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-        l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-        l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-        float o[KS][4];
-#pragma unroll
-        for (int nd = 0; nd < KS; ++nd) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
-#pragma unroll
-        for (int kt = 0; kt < 8; ++kt) {
-          if (kt < NT) {
-            float pa[4] = {to_tf32(c[kt][0]), to_tf32(c[kt][2]), to_tf32(c[kt][1]), to_tf32(c[kt][3])};
-            const float* v0 = sv + (s + 8 * kt + 2 * t) * TC_PITCH + ch + g;
-            const float* v1 = v0 + TC_PITCH;
-#pragma unroll
-            for (int nd = 0; nd < KS; ++nd) mma_tf32(o[nd], pa, v0[8 * nd], v1[8 * nd]);
-          }
-        }
-        const float il0 = 1.f / l0, il1 = 1.f / l1;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int rq = m0 + g + 8 * half;
-          if (rq < n) {
-            const int tok = sinfo[s + rq + shift].x;
-            const float il = half ? il1 : il0;
-            const long long e0 = (long long)tok * d + col + ch + 2 * t;
-#pragma unroll
-            for (int nd = 0; nd < KS; ++nd) {
-              float x0 = o[nd][2 * half] * il, x1 = o[nd][2 * half + 1] * il;
-              if (a.bv) { x0 += __ldg(a.bv + col + ch + 8 * nd + 2 * t); x1 += __ldg(a.bv + col + ch + 8 * nd + 2 * t + 1); }
-              if (a.out_bf16) *reinterpret_cast<__nv_bfloat162*>((__nv_bfloat16*)out + e0 + 8 * nd) = __floats2bfloat162_rn(x0, x1);
-              else *reinterpret_cast<float2*>((float*)out + e0 + 8 * nd) = make_float2(x0, x1);
+            for (int i = 0; i < 4; ++i) {
+              x[2 * i] = __uint_as_float(rw[i] << 16) + __uint_as_float(lw[i] << 16);
+              x[2 * i + 1] = __uint_as_float(rw[i] & 0xffff0000u) + __uint_as_float(lw[i] & 0xffff0000u);
+              ss = fmaf(x[2 * i], x[2 * i], ss);
+              ss = fmaf(x[2 * i + 1], x[2 * i + 1], ss);
             }
-            if (t == 0) lse[(long long)tok * 8 + sl * HS + h] = (half ? mx1 : mx0) + __logf(half ? l1 : l0);
+            ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+            if (HD == 32) ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+            float f;
+            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(f) : "f"(fmaxf(ss, 1e-24f)));
+            if (part[u] == 0) f *= qscale;
+            if (valid[u]) {
+              uint4 o;
+              o.x = pack_bf16(x[0] * f, x[1] * f);
+              o.y = pack_bf16(x[2] * f, x[3] * f);
+              o.z = pack_bf16(x[4] * f, x[5] * f);
+              o.w = pack_bf16(x[6] * f, x[7] * f);
+              *reinterpret_cast<uint4*>(p[u]) = o;
+            }
           }
         }
       }
+    } else if (gw == 0 && j < my_bins) {
+      // ---- work units of bin j, built by one math warp (the records of bin j landed an iteration ago)
+      const int bin = (cta + j * ncta) * MM_BIN;
+      const int4* sinfo = sinfo_all + (j % MM_NINFO) * MM_INFO;
+      int* sunit = sunit_all + (j & 1) * (MM_UNITS + 16);
+      int row0, R;
+      mm_bin_range(sinfo, bin, a.N, row0, R);
+      const int shift = row0 - bin;
+      int nu = 0;
+      if (R > 0) {
+        unsigned long long m0 = 0, m1 = 0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          int r = 32 * w + lane;
+          bool st = r < R && sinfo[min(r, R - 1) + shift].y == row0 + r;
+          unsigned long long b = __ballot_sync(0xffffffffu, st);
+          if (w < 2) m0 |= b << (32 * w);
+          else m1 |= b << (32 * (w - 2));
+        }
+        if (R < 64) m0 |= 1ull << R;      // sentinel: one past the last row
+        else m1 |= 1ull << (R - 64);
+        int s = 0;
+        while (s < R && nu < MM_UNITS) {
+          unsigned w16 = mm_bits(m0, m1, s + 1) & 0xffffu;     // window starts at rows s+1 .. s+16
+          if (w16) {                                           // run of whole windows with <= 16 rows in total
+            int e = s + 32 - __clz(w16);
+            if (lane == 0) sunit[nu] = s | ((e - s) << 7) | (s << 12) | ((e - s) << 19);
+            ++nu;
+            s = e;
+          } else {                                             // a window of more than 16 rows: 16-row query chunks
+            unsigned lo = mm_bits(m0, m1, s + 17), hi = mm_bits(m0, m1, s + 49);
+            int n = lo ? 16 + __ffs(lo) : 48 + __ffs(hi);
+            for (int m = 0; m < n && nu < MM_UNITS; m += 16) {
+              if (lane == 0) sunit[nu] = (s + m) | (min(16, n - m) << 7) | (s << 12) | (n << 19);
+              ++nu;
+            }
+            s += n;
+          }
+        }
+      }
+      if (lane == 0) { sunit[MM_UNITS] = nu; sunit[MM_UNITS + 1] = 0; }   // count, work counter
     }
+    if (j > 0) {
+      // ================= bin j-1: the math warps start at once, the stagers join when bin j is staged;
+      // (unit, head) entries are handed out through a shared-memory counter
+      const int jb = j - 1;
+      const int bin = (cta + jb * ncta) * MM_BIN;
+      const int4* sinfo = sinfo_all + (jb % MM_NINFO) * MM_INFO;
+      const bf16* sq = sdata + (jb % MM_STAGES) * MM_STAGE_ELEMS;
+      const bf16* sk = sq + MM_ARR;
+      const bf16* sv = sk + MM_ARR;
+      int* sunit = sunit_all + (jb & 1) * (MM_UNITS + 16);
+      int row0, R;
+      mm_bin_range(sinfo, bin, a.N, row0, R);
+      const int shift = row0 - bin;
+      const int nent = sunit[MM_UNITS] * HS;
+      const int g = lane >> 2;
+      for (;;) {
+        int e = 0;
+        if (lane == 0) e = atomicAdd(sunit + MM_UNITS + 1, 1);
+        e = __shfl_sync(0xffffffffu, e, 0);
+        if (e >= nent) break;
+        const int code = sunit[e / HS];
+        const int h = e % HS;
+        const int q0 = code & 127, qn = (code >> 7) & 31, k0 = (code >> 12) & 127, kn = (code >> 19) & 127;
+        const int ch = h * HD;
+        const int4 recA = sinfo[min(q0 + g, R - 1) + shift], recB = sinfo[min(q0 + g + 8, R - 1) + shift];
+        const int kbase = row0 + k0;
+        const long long oc = col + ch;
+        const int lc = sl * HS + h;
+        if (kn <= 16) mm_unit<HD, 2>(a, sq, sk, sv, q0, qn, k0, ch, recA, recB, kbase, lane, oc, lc, out, lse);
+        else if (kn <= 32) mm_unit<HD, 4>(a, sq, sk, sv, q0, qn, k0, ch, recA, recB, kbase, lane, oc, lc, out, lse);
+        else if (kn <= 48) mm_unit<HD, 6>(a, sq, sk, sv, q0, qn, k0, ch, recA, recB, kbase, lane, oc, lc, out, lse);
+        else mm_unit<HD, 8>(a, sq, sk, sv, q0, qn, k0, ch, recA, recB, kbase, lane, oc, lc, out, lse);
+      }
+    }
+    __syncthreads();   // bin j is staged for the math warps; bin j-1's buffers are free for the copies of bin j+2
   }
-  tc_wait_all();
+  if (stager) mm_wait<0>();
 }
 
-// Tensor-core (TF32) variant of gdmae_sra_attention_fwd: same arguments, same outputs.
-extern "C" int gdmae_sra_attention_fwd_tc(const float* qkv, const float* lut, const int32_t* row_info, int64_t N, int d, int nhead,
+static int mm_attrs() {
+  static bool done = false;
+  if (!done) {
+    GDMAE_CHECK_CUDA(cudaFuncSetAttribute(sra_fwd_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
+    GDMAE_CHECK_CUDA(cudaFuncSetAttribute(sra_fwd_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
+    done = true;
+  }
+  return GDMAE_OK;
+}
+
+// Tensor-core variant of gdmae_sra_attention_fwd for bf16 q/k/v: qkv (N, 3d) bf16, otherwise the same arguments and outputs.
+extern "C" int gdmae_sra_attention_fwd_tc(const void* qkv_bf16, const float* lut, const int32_t* row_info, int64_t N, int d, int nhead,
                                           const float* tau, float tau_min, const float* bv, int io_bf16, void* out, float* lse,
                                           void* stream_) {
-  GDMAE_CHECK_ARG(N >= 0 && N < (1ll << 27) && nhead == 8 && (d == 128 || d == 256) && ((uintptr_t)row_info % 16) == 0 &&
-                  ((uintptr_t)qkv % 16) == 0 && ((uintptr_t)lut % 16) == 0);
+  GDMAE_CHECK_ARG(N >= 0 && N < (1ll << 27) && nhead == 8 && (d == 128 || d == 256));
+  GDMAE_CHECK_ARG(((uintptr_t)row_info % 16) == 0 && ((uintptr_t)qkv_bf16 % 16) == 0 && ((uintptr_t)lut % 8) == 0);
+  GDMAE_CHECK_ARG(bv == nullptr || ((uintptr_t)bv % 8) == 0);
   if (N == 0) return GDMAE_OK;
-  static bool attr_done = false;
-  if (!attr_done) {
-    GDMAE_CHECK_CUDA(cudaFuncSetAttribute(sra_fwd_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    GDMAE_CHECK_CUDA(cudaFuncSetAttribute(sra_fwd_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    attr_done = true;
-  }
-  TcArgs a{qkv, lut, (const int4*)row_info, tau, bv, tau_min, (int)N, d, io_bf16};
+  int rc = mm_attrs();
+  if (rc) return rc;
+  MmArgs a{(const bf16*)qkv_bf16, lut, (const int4*)row_info, tau, bv, tau_min, (int)N, d, io_bf16};
   cudaStream_t st = (cudaStream_t)stream_;
   // one CTA per SM; 148 is a multiple of the 2 (d = 128) and 4 (d = 256) channel slices
-  if (d == 128) sra_fwd_tc_kernel<16><<<GDMAE_NUM_SMS, TC_THREADS, TC_SMEM_BYTES, st>>>(a, out, lse);
-  else sra_fwd_tc_kernel<32><<<GDMAE_NUM_SMS, TC_THREADS, TC_SMEM_BYTES, st>>>(a, out, lse);
+  if (d == 128) sra_fwd_mma_kernel<16><<<GDMAE_NUM_SMS, MM_THREADS, MM_SMEM_BYTES, st>>>(a, out, lse);
+  else sra_fwd_mma_kernel<32><<<GDMAE_NUM_SMS, MM_THREADS, MM_SMEM_BYTES, st>>>(a, out, lse);
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;
 }

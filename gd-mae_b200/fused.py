@@ -148,74 +148,151 @@ def gather_add_rows(x, table, idx_u8):
 # bf16 copy of the previous layer's output (written by its LayerNorm kernel) handed to the next layer
 _LAST_OUT = (None, None)
 
+# bf16 shadows of parameters, keyed by the parameter's data pointer: the trainer keeps one bf16 mirror of its
+# flat parameter bucket (refreshed once per step) so no per-layer weight casts are launched.
+BF16_SHADOW = {}
+
+
+def _gw(w):
+    """GEMM-dtype copy of a weight: the trainer's bf16 shadow if registered, else a cast."""
+    if GEMM_DTYPE == F32:
+        return w
+    sh = BF16_SHADOW.get(w.data_ptr())
+    return sh if sh is not None else w.to(BF16)
+
+
+def gemm_mode():
+    """gdmae_gemm operand mode of the current configuration: 1 bf16, 0 fp32/TF32 math, 2 fp32/fp32 math."""
+    if GEMM_DTYPE == BF16:
+        return 1
+    return 0 if torch.backends.cuda.matmul.allow_tf32 else 2
+
+
+_VP = ctypes.c_void_p
+_EL_PTRS = ["x", "xg_in", "pos_table", "row_info", "pos_of_token",
+            "w_in", "b_in", "tau", "w_o", "b_o", "g1", "be1", "w1", "b1", "w2", "b2", "g2", "be2",
+            "w_in_g", "w_o_g", "w1_g", "w2_g",
+            "xg", "qkv", "lut", "o", "lse", "a", "x1", "x1g", "mean1", "rstd1", "h", "g", "f", "mean2", "rstd2", "x2", "x2g",
+            "dy", "dx", "d_w_in", "d_b_in", "d_tau", "d_w_o", "d_b_o", "d_g1", "d_be1", "d_w1", "d_b1", "d_w2", "d_b2", "d_g2",
+            "d_be2", "ws"]
+
+
+class EncoderLayerArgs(ctypes.Structure):
+    """mirror of gdmae_encoder_layer_args (include/gdmae_b200.h)"""
+    _fields_ = ([("N", ctypes.c_int64), ("d", ctypes.c_int), ("dff", ctypes.c_int), ("nhead", ctypes.c_int),
+                 ("gemm_mode", ctypes.c_int), ("sra_tensor_cores", ctypes.c_int), ("accumulate", ctypes.c_int),
+                 ("tau_min", ctypes.c_float), ("eps", ctypes.c_float)]
+                + [(n, _VP) for n in _EL_PTRS] + [("ws_bytes", ctypes.c_size_t), ("stream", _VP)])
+
+
+_PARAM_NAMES = ("w_in", "b_in", "tau", "w_o", "b_o", "g1", "be1", "w1", "b1", "w2", "b2", "g2", "be2")
+
+
+def _r64(n):
+    return (n + 63) & ~63
+
 
 class EncoderLayerFunction(torch.autograd.Function):
-    """x -> LN2( x1 + W2 gelu(W1 x1 + b1) + b2 ),  x1 = LN1( x + Wo SRA(x) + bo )."""
+    """x -> LN2( x1 + W2 gelu(W1 x1 + b1) + b2 ),  x1 = LN1( x + Wo SRA(x) + bo ).
+    Forward and backward are one C call each (csrc/encoder_layer.cu); this class only owns the buffers."""
 
     @staticmethod
     @_ops._fwd
-    def forward(ctx, x, pos_table, table, tau_min, nhead, w_in, b_in, tau, w_o, b_o, g1, be1, w1, b1, w2, b2, g2, be2):
+    def forward(ctx, x, pos_table, table, tau_min, nhead, eps, *params):
         global _LAST_OUT
         x = x.contiguous()
-        d = x.shape[1]
-        tau_c = tau.reshape(-1).contiguous()
-        w_in_g, w_o_g, w1_g, w2_g = _g(w_in), _g(w_o), _g(w1), _g(w2)
-        xg = _LAST_OUT[1] if _LAST_OUT[0] is x else _g(x)
-        qkv = gemm(xg, w_in_g.t())                                               # (N,3d): q, k, v without biases
-        lut = torch.addmm(b_in[:2 * d], pos_table, w_in[:2 * d].t())             # (64,2d): pos term + q/k biases
-        bv = b_in[2 * d:].contiguous()
-        o, lse = _ops.sra_fwd(qkv, lut, tau_c, table, tau_min, nhead, bv=bv, out_dtype=GEMM_DTYPE)
-        a = gemm(o, w_o_g.t())
-        x1, x1g, mean1, rstd1 = add_layernorm_fwd(x, a, b_o, g1, be1)
-        h = gemm(x1g, w1_g.t())
-        g = bias_gelu_fwd(h, b1)
-        f = gemm(g, w2_g.t())
-        x2, x2g, mean2, rstd2 = add_layernorm_fwd(x1, f, b2, g2, be2)
+        N, d = x.shape
+        dff = params[7].shape[0]
+        mode = gemm_mode()
+        bf = mode == 1
+        dev = x.device
+        A = EncoderLayerArgs()
+        A.N, A.d, A.dff, A.nhead, A.gemm_mode = N, d, dff, nhead, mode
+        A.sra_tensor_cores, A.accumulate, A.tau_min, A.eps = int(_ops.SRA_TENSOR_CORES), 0, tau_min, eps
+        A.x, A.pos_table, A.row_info, A.pos_of_token = x.data_ptr(), pos_table.data_ptr(), table.row_info.data_ptr(), \
+            table.pos_of_token.data_ptr()
+        keep = [x, pos_table, table.row_info, table.pos_of_token]
+        for name, p in zip(_PARAM_NAMES, params):
+            setattr(A, name, p.data_ptr())
+        for name, p in zip(("w_in_g", "w_o_g", "w1_g", "w2_g"), (params[0], params[3], params[7], params[9])):
+            pg = _gw(p)
+            keep.append(pg)
+            setattr(A, name, pg.data_ptr())
+        xg_in = _LAST_OUT[1] if (bf and _LAST_OUT[0] is x) else None
+        if xg_in is not None:
+            keep.append(xg_in)
+            A.xg_in = xg_in.data_ptr()
+        # ---- activations saved for backward: one fp32 and one bf16 buffer, carved here
+        Nd, Nf = _r64(N * d), _r64(N * dff)
+        n32 = 3 * Nd + 2 * Nd + Nf + Nd + _r64(N * 8) + 4 * _r64(N) + 128 * d + (0 if bf else Nd + Nf)
+        save32 = torch.empty((max(n32, 1),), dtype=F32, device=dev)
+        b = save32.data_ptr()
+        off = 0
+        for name, n in (("qkv", 3 * Nd), ("a", Nd), ("x1", Nd), ("h", Nf), ("f", Nd), ("lse", _r64(N * 8)), ("mean1", _r64(N)),
+                        ("rstd1", _r64(N)), ("mean2", _r64(N)), ("rstd2", _r64(N)), ("lut", 128 * d)):
+            setattr(A, name, b + 4 * off)
+            off += n
+        x2 = torch.empty((N, d), dtype=F32, device=dev)
+        A.x2 = x2.data_ptr()
+        save16 = x2g = None
+        if bf:
+            save16 = torch.empty((max(4 * Nd + Nf, 1),), dtype=BF16, device=dev)
+            b16 = save16.data_ptr()
+            A.xg, A.o, A.x1g, A.x2g, A.g = b16, b16 + 2 * Nd, b16 + 4 * Nd, b16 + 6 * Nd, b16 + 8 * Nd
+            x2g = save16[3 * Nd:3 * Nd + N * d].view(N, d)
+        else:
+            A.o, A.g = b + 4 * off, b + 4 * (off + Nd)
+        A.stream = torch.cuda.current_stream().cuda_stream
+        L.check(L.lib().gdmae_encoder_layer_fwd(ctypes.byref(A)), "gdmae_encoder_layer_fwd")
         _LAST_OUT = (x2, x2g)
-        ctx.save_for_backward(x, xg, pos_table, w_in_g, tau_c, bv, w_o_g, b_o, g1, w1_g, b1, w2_g, b2, g2, qkv, lut, o, lse, a, x1,
-                              x1g, mean1, rstd1, h, g, f, mean2, rstd2)
-        ctx.table, ctx.tau_min, ctx.nhead, ctx.tau_shape = table, tau_min, nhead, tau.shape
+        ctx.save_for_backward(x, save32, *params)
+        ctx.args, ctx.keep, ctx.save16 = A, keep, save16
+        ctx.params = params
         return x2
 
     @staticmethod
     @_ops._bwd
     def backward(ctx, dx2):
-        (x, xg, pos_table, w_in, tau_c, bv, w_o, b_o, g1, w1, b1, w2, b2, g2, qkv, lut, o, lse, a, x1, x1g, mean1, rstd1, h, g, f,
-         mean2, rstd2) = ctx.saved_tensors                       # w_*, xg, o, x1g, g are in the GEMM operand dtype
-        t = ctx.table
-        d = x.shape[1]
+        A, params = ctx.args, ctx.params
+        x = ctx.saved_tensors[0]
         dx2 = dx2.contiguous()
-        # ---- LN2 and the feed-forward
-        dz2, dz2g, dg2, dbe2 = add_layernorm_bwd(x1, f, b2, g2, mean2, rstd2, dx2)   # grad wrt f, b2 and (residual) x1
-        db2 = colsum(dz2)
-        dw2 = gemm(dz2g.t(), g)
-        dgl = gemm(dz2g, w2)
-        dh, db1 = bias_gelu_bwd(h, b1, dgl)
-        dw1 = gemm(dh.t(), x1g)
-        dx1 = gemm(dh, w1, out=dz2, beta=1.0)                                        # residual + through linear1, in place
-        # ---- LN1 and the attention
-        dz1, dz1g, dg1, dbe1 = add_layernorm_bwd(x, a, b_o, g1, mean1, rstd1, dx1)   # grad wrt a, b_o and (residual) x
-        db_o = colsum(dz1)
-        dw_o = gemm(dz1g.t(), o)
-        do = gemm(dz1g, w_o)
-        dqkv, dtau_sum = _ops.sra_bwd(qkv, lut, tau_c, t, ctx.tau_min, ctx.nhead, o, lse, do, bv=bv, io_dtype=GEMM_DTYPE)
-        # in-projection: q = (x + pos) Wq^T + bq, k likewise, v = x Wv^T + bv
-        xpos = gather_add_rows(x, pos_table, t.pos_of_token)
-        dw_in = torch.cat([gemm(dqkv[:, :2 * d].t(), xpos), gemm(dqkv[:, 2 * d:].t(), xg)])
-        db_in = torch.cat([colsum(dqkv, 0, 2 * d), colsum(dqkv, 2 * d, d)])
-        dx = gemm(dqkv, w_in, out=dz1, beta=1.0)
-        tau_eff = torch.clamp(tau_c, min=ctx.tau_min)
-        dtau = torch.where(tau_c >= ctx.tau_min, -(dtau_sum.float() / tau_eff), torch.zeros_like(tau_c)).reshape(ctx.tau_shape)
-        return (dx, None, None, None, None, dw_in, db_in, dtau, dw_o, db_o, dg1, dbe1, dw1, db1, dw2, db2, dg2, dbe2)
+        dev = x.device
+        N, d, dff = A.N, A.d, A.dff
+        dx = torch.empty((N, d), dtype=F32, device=dev)
+        A.dy, A.dx = dx2.data_ptr(), dx.data_ptr()
+        # parameter gradients: straight into .grad when the caller pre-allocated them (the trainer's flat bucket)
+        inplace = all(p.grad is not None and p.grad.dtype == F32 and p.grad.is_contiguous() for p in params)
+        if inplace:
+            grads = [p.grad for p in params]
+            A.accumulate = 1
+        else:
+            sizes = [_r64(p.numel()) for p in params]
+            flat = torch.empty((sum(sizes),), dtype=F32, device=dev)
+            grads, off = [], 0
+            for p, n in zip(params, sizes):
+                grads.append(flat[off:off + p.numel()].view(p.shape))
+                off += n
+            A.accumulate = 0
+        for name, g in zip(_PARAM_NAMES, grads):
+            setattr(A, "d_" + name, g.data_ptr())
+        nbytes = L.lib().gdmae_encoder_layer_bwd_workspace_bytes(L.i64(N), d, dff)
+        ws = L.workspace(nbytes, dev)
+        A.ws, A.ws_bytes = ws.data_ptr(), ws.numel()
+        A.stream = torch.cuda.current_stream().cuda_stream
+        L.check(L.lib().gdmae_encoder_layer_bwd(ctypes.byref(A)), "gdmae_encoder_layer_bwd")
+        ctx.keep = ctx.save16 = None
+        if inplace:
+            return (dx,) + (None,) * (5 + len(params))
+        return (dx, None, None, None, None, None) + tuple(grads)
 
 
 def encoder_layer(layer, x, pos_table, table):
     """Fused forward/backward of an EncoderLayer module (parameters read from the module)."""
     at = layer.win_attn.self_attn
-    return EncoderLayerFunction.apply(x, pos_table, table, at.tau_min, at.num_heads, at.in_proj_weight, at.in_proj_bias, at.tau,
-                                      at.out_proj.weight, at.out_proj.bias, layer.norm1.weight, layer.norm1.bias,
-                                      layer.linear1.weight, layer.linear1.bias, layer.linear2.weight, layer.linear2.bias,
-                                      layer.norm2.weight, layer.norm2.bias)
+    return EncoderLayerFunction.apply(x, pos_table, table, at.tau_min, at.num_heads, layer.norm1.eps, at.in_proj_weight,
+                                      at.in_proj_bias, at.tau, at.out_proj.weight, at.out_proj.bias, layer.norm1.weight,
+                                      layer.norm1.bias, layer.linear1.weight, layer.linear1.bias, layer.linear2.weight,
+                                      layer.linear2.bias, layer.norm2.weight, layer.norm2.bias)
 
 
 class SparseConvFunction(torch.autograd.Function):
@@ -228,7 +305,7 @@ class SparseConvFunction(torch.autograd.Function):
     @_ops._fwd
     def forward(ctx, x, weight, fwd_map, bwd_map, mirror):
         x = x.contiguous()
-        w = _g(weight.view(weight.shape[0], -1))            # (C_out, 9*C_in)
+        w = _gw(weight).view(weight.shape[0], -1)            # (C_out, 9*C_in)
         col = _ops.gather_rows(x, fwd_map, GEMM_DTYPE)
         y = gemm(col, w.t())
         ctx.save_for_backward(col, w, bwd_map)

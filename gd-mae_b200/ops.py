@@ -276,8 +276,8 @@ def sra_fwd(qkv, lut, tau, table, tau_min, nhead, bv=None, out_dtype=torch.float
     out = torch.empty((N, d), dtype=out_dtype, device=qkv.device)
     lse = torch.empty((N, nhead), dtype=F32, device=qkv.device)
     # algorithmic bytes (SURVEY.md 8d, a18 minus projections): N*d*(3*s_in + s_out) + N*8
-    with L.timed(f"sra_fwd_d{d}", N * d * (12 + out.element_size()) + N * 8):
-        if SRA_TENSOR_CORES:
+    with L.timed(f"sra_fwd_d{d}", N * d * (3 * qkv.element_size() + out.element_size()) + N * 8 * 4):
+        if qkv.dtype == torch.bfloat16:
             L.check(L.lib().gdmae_sra_attention_fwd_tc(L.P(qkv), L.P(lut), L.P(table.row_info), L.i64(N), d, nhead, L.P(tau),
                                                        L.f32(tau_min), L.P(bv), _DT[out_dtype], L.P(out), L.P(lse), L.stream()),
                     "gdmae_sra_attention_fwd_tc")

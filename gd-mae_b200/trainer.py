@@ -83,11 +83,27 @@ class MAETrainer:
         self.exp_avg = torch.zeros(self.n_opt, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(self.n_opt, dtype=torch.float32, device=dev)
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+        # bf16 mirror of the bucket for the bf16 GEMM configuration: refreshed once per step, its views are the
+        # GEMM-operand copies of the weights (fused.BF16_SHADOW), so no per-layer weight casts are launched
+        self.flat_bf16 = None
+        self._params = [p for _, p in ordered]
         self.it = 0       # accumulated_iter of train_one_epoch
         self.t = 0        # Adam step count
 
     def zero_grad(self):
         self.flat_grads.zero_()
+
+    def refresh_bf16_mirror(self):
+        from . import fused
+        if fused.GEMM_DTYPE != torch.bfloat16 or not self.flat_params.is_cuda:
+            return
+        if self.flat_bf16 is None:
+            self.flat_bf16 = torch.empty(self.n_all, dtype=torch.bfloat16, device=self.flat_params.device)
+            base = self.flat_params.data_ptr()
+            for p in self._params:
+                off = (p.data_ptr() - base) // 4
+                fused.BF16_SHADOW[p.data_ptr()] = self.flat_bf16[off:off + p.numel()].view(p.shape)
+        self.flat_bf16.copy_(self.flat_params)
 
     def reduce_gradients(self):
         """The only exchange step of the path: ONE all-reduce(SUM) of the flat gradient bucket (32.4 MB at
@@ -120,6 +136,7 @@ class MAETrainer:
         Returns the loss tensor (no host sync)."""
         self.model.train()
         self.zero_grad()
+        self.refresh_bf16_mirror()
         ret_dict, tb_dict, _ = self.model(batch_dict)
         loss = ret_dict['loss'].mean()
         loss.backward()

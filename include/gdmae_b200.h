@@ -140,8 +140,9 @@ int gdmae_window_table(const int32_t* indices, int64_t N, int B, int H, int W, i
 int gdmae_sra_attention_fwd(const float* qkv, const float* lut, const int32_t* row_info, int64_t N, int d, int nhead,
                             const float* tau, float tau_min, const float* bv, int io_bf16, void* out, float* lse,
                             void* stream);
-/* same operator and arguments, QK^T and PV on the tensor cores (TF32 mma, fp32 accumulate, softmax in fp32) */
-int gdmae_sra_attention_fwd_tc(const float* qkv, const float* lut, const int32_t* row_info, int64_t N, int d, int nhead,
+/* same operator for bf16 q/k/v (qkv_bf16 (N,3d) bf16): QK^T and PV on the tensor cores (bf16 mma, fp32 accumulate,
+ * softmax in fp32), persistent cp.async-pipelined kernel; other arguments and outputs as above */
+int gdmae_sra_attention_fwd_tc(const void* qkv_bf16, const float* lut, const int32_t* row_info, int64_t N, int d, int nhead,
                                const float* tau, float tau_min, const float* bv, int io_bf16, void* out, float* lse,
                                void* stream);
 int gdmae_sra_attention_bwd(const float* qkv, const float* lut, const int32_t* row_info, int64_t N, int d, int nhead,
@@ -168,6 +169,58 @@ int gdmae_colsum(const void* x, int dtype /* 0 fp32, 1 bf16 */, int64_t N, int l
                  int accumulate, void* workspace, size_t ws_bytes, void* stream);
 int gdmae_gather_add_rows(const float* x, const float* table, const uint8_t* idx, int64_t N, int C, float* out,
                           void* out_bf16, void* stream);
+
+/* ---- a13-a19 encoder-layer executor -------------------------------------------------------------
+ * One call = the whole forward (or the whole backward) of an SST EncoderLayer
+ * (pcdet/models/model_utils/sst_basic_block.py:60-92 with WindowAttention :22-54 and the
+ * CosineMultiheadAttention projections, cosine_msa.py:57-62,380-431): x -> LN2(x1 + W2 gelu(W1 x1 + b1) + b2),
+ * x1 = LN1(x + Wo SRA(x) + bo).  All buffers belong to the caller; "op" pointers are in the GEMM
+ * operand dtype (fp32 for gemm_mode 0/2, bf16 for gemm_mode 1).  Weights are the torch layouts:
+ * w_in (3d,d), w_o (d,d), w1 (dff,d), w2 (d,dff).  Backward writes (accumulate=0) or adds to
+ * (accumulate=1) the parameter gradients d_*; dx receives the input gradient. */
+typedef struct gdmae_encoder_layer_args {
+  int64_t N;
+  int d, dff, nhead;
+  int gemm_mode;        /* 0: fp32 operands, TF32 math; 1: bf16 operands; 2: fp32 operands, fp32 math */
+  int sra_tensor_cores; /* forward SRA kernel: 0 fp32 SIMT, 1 TF32 tensor cores */
+  int accumulate;
+  float tau_min, eps;
+  /* inputs */
+  const float* x;            /* (N,d) */
+  const void* xg_in;         /* (N,d) op copy of x handed over by the producer, or NULL */
+  const float* pos_table;    /* (64,d) */
+  const int32_t* row_info;   /* (N,4) from gdmae_window_table */
+  const uint8_t* pos_of_token;
+  /* parameters: fp32 masters and op-dtype copies of the four weights (same pointers when fp32) */
+  const float *w_in, *b_in, *tau, *w_o, *b_o, *g1, *be1, *w1, *b1, *w2, *b2, *g2, *be2;
+  const void *w_in_g, *w_o_g, *w1_g, *w2_g;
+  /* activations written by forward and read by backward */
+  void* xg;                  /* (N,d) op; used when xg_in == NULL and gemm_mode == 1 */
+  float* qkv;                /* (N,3d) */
+  float* lut;                /* (64,2d) */
+  void* o;                   /* (N,d) op */
+  float* lse;                /* (N,8) */
+  float* a;                  /* (N,d) */
+  float* x1;                 /* (N,d) */
+  void* x1g;                 /* (N,d) op (bf16 mode only) */
+  float *mean1, *rstd1;      /* (N) */
+  float* h;                  /* (N,dff) */
+  void* g;                   /* (N,dff) op */
+  float* f;                  /* (N,d) */
+  float *mean2, *rstd2;      /* (N) */
+  float* x2;                 /* (N,d) output */
+  void* x2g;                 /* (N,d) op copy of the output (bf16 mode only) */
+  /* backward */
+  const float* dy;           /* (N,d) gradient w.r.t. x2 */
+  float* dx;                 /* (N,d) gradient w.r.t. x */
+  float *d_w_in, *d_b_in, *d_tau, *d_w_o, *d_b_o, *d_g1, *d_be1, *d_w1, *d_b1, *d_w2, *d_b2, *d_g2, *d_be2;
+  void* ws;                  /* gdmae_encoder_layer_bwd_workspace_bytes(N, d, dff) */
+  size_t ws_bytes;
+  void* stream;
+} gdmae_encoder_layer_args;
+int gdmae_encoder_layer_fwd(const gdmae_encoder_layer_args* args);
+size_t gdmae_encoder_layer_bwd_workspace_bytes(int64_t N, int d, int dff);
+int gdmae_encoder_layer_bwd(const gdmae_encoder_layer_args* args);
 
 /* ---- plain dense GEMM through cuBLAS (library GEMM) ------------------------------------------------
  * row-major C (M,N) = op(A) op(B) + beta*C; A/B fp32 (TF32 math, ab_dtype 0) or bf16 (1); C fp32 or bf16.

@@ -382,37 +382,32 @@ def test_waymo_shape_properties(G):
 
 @pytest.mark.parametrize("d", [128, 256])
 def test_sra_tensor_core_kernel_matches_simt(G, d):
-    """TF32 tensor-core SRA forward vs the fp32 SIMT kernel on dense windows (all drop levels)."""
+    """bf16 tensor-core SRA forward (bf16 q/k/v) vs the fp32 SIMT kernel on the same rounded inputs;
+    windows of every size 1..64 and all drop levels, both shifts, ragged last bin."""
     g = torch.Generator().manual_seed(d)
     occ = torch.rand(3, 70, 61, generator=g) < 0.55
     occ[2, :, 30:] &= torch.rand(70, 31, generator=g) < 0.1
+    occ[1, 40:, :] &= torch.rand(30, 61, generator=g) < 0.04        # tiny windows (1-3 tokens)
     idx = torch.nonzero(occ).int().contiguous().cuda()  # nonzero() returns a column-major (N,3) tensor
     N = idx.shape[0]
-    qkv = torch.randn(N, 3 * d, generator=g).cuda()
+    qkv_b = torch.randn(N, 3 * d, generator=g).cuda().to(torch.bfloat16)
+    qkv = qkv_b.float()
     lut = (0.5 * torch.randn(64, 2 * d, generator=g)).cuda()
     tau = torch.tensor([0.7]).cuda()
+    bv = torch.randn(d, generator=g).cuda()
     for shift in (0, 1):
         table = G.ops.window_table(idx, 3, 70, 61, shift)
-        G.ops.SRA_TENSOR_CORES = False
         o_ref, lse_ref = G.ops.sra_fwd(qkv, lut, tau, table, 0.01, 8)
-        G.ops.SRA_TENSOR_CORES = True
-        try:
-            o_tc, lse_tc = G.ops.sra_fwd(qkv, lut, tau, table, 0.01, 8)
-        finally:
-            G.ops.SRA_TENSOR_CORES = False
+        o_tc, lse_tc = G.ops.sra_fwd(qkv_b, lut, tau, table, 0.01, 8)
+        assert torch.isfinite(o_tc).all() and torch.isfinite(lse_tc).all()
         e_o, e_l = rel(o_tc, o_ref), rel(lse_tc, lse_ref)
         print(f"sra tc d={d} shift={shift}: rel err out {e_o:.2e} lse {e_l:.2e}")
-        assert e_o < 4e-3, e_o      # TF32 operands (10-bit mantissa) on scores up to 1/tau = 1.4
-        assert e_l < 4e-3, e_l
+        assert e_o < 1e-2, e_o      # bf16 operands (8-bit mantissa): q, k, P and the LUT are rounded
+        assert e_l < 5e-3, e_l
         # value bias folded into the output, bf16 output (the bench configuration's call)
-        bv = torch.randn(d, generator=g).cuda()
         o_ref, _ = G.ops.sra_fwd(qkv, lut, tau, table, 0.01, 8, bv=bv, out_dtype=torch.bfloat16)
-        G.ops.SRA_TENSOR_CORES = True
-        try:
-            o_tc, _ = G.ops.sra_fwd(qkv, lut, tau, table, 0.01, 8, bv=bv, out_dtype=torch.bfloat16)
-        finally:
-            G.ops.SRA_TENSOR_CORES = False
-        assert rel(o_tc.float(), o_ref.float()) < 8e-3
+        o_tc, _ = G.ops.sra_fwd(qkv_b, lut, tau, table, 0.01, 8, bv=bv, out_dtype=torch.bfloat16)
+        assert rel(o_tc.float(), o_ref.float()) < 1.5e-2
 
 
 def test_bf16_configuration_close_to_reference(G, golden):

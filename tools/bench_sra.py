@@ -116,16 +116,20 @@ def main():
             err = max(float((out - ref[0]).abs().max()), float((dqkv - ref[1]).abs().max()))
             print(f"   {vn:16s} fwd {tf:7.1f} us ({fb / tf / 1e3 / 6538.3:.3f} of peak)   bwd {tb:7.1f} us ({bb / tb / 1e3 / 6538.3:.3f})   "
                   f"max|diff vs first| {err:.2e}")
-        # tensor-core forward of the main library
-        out = torch.empty(N, d, device="cuda")
+        # tensor-core forward of the main library: bf16 q/k/v in, bf16 out
+        qkv_b = qkv.to(torch.bfloat16)
+        out_b = torch.empty(N, d, device="cuda", dtype=torch.bfloat16)
         lse = torch.empty(N, 8, device="cuda")
         fn = L.lib().gdmae_sra_attention_fwd_tc
 
         def fwd_tc():
-            L.check(fn(L.P(qkv), L.P(lut), L.P(t.row_info), L.i64(N), d, 8, L.P(tau), L.f32(0.01), None, 0, L.P(out), L.P(lse), st()), "tc")
+            L.check(fn(L.P(qkv_b), L.P(lut), L.P(t.row_info), L.i64(N), d, 8, L.P(tau), L.f32(0.01), None, 1, L.P(out_b), L.P(lse), st()),
+                    "tc")
 
         tf = timeit(fwd_tc, flush)
-        print(f"   {'tensor-core fwd':16s} fwd {tf:7.1f} us ({fb / tf / 1e3 / 6538.3:.3f} of peak)   max|diff| {float((out - ref[0]).abs().max()):.2e}")
+        fbb = N * d * 8 + N * 32
+        print(f"   {'tensor-core fwd':16s} fwd {tf:7.1f} us ({fbb / tf / 1e3 / 6538.3:.3f} of peak, bf16 io {fbb / 1e6:.1f} MB)   "
+              f"max|diff| {float((out_b.float() - ref[0]).abs().max()):.2e}")
 
 
 if __name__ == "__main__":
