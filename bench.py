@@ -231,8 +231,20 @@ def main():
     barrier()
     sampler.start()
     _lib.KERNEL_TIMERS = {}
+    _lib.lib().gdmae_timing_enable(1)
     ms_step, last_loss, launches = timed(step_resident, args.steps, 0)
+    _lib.lib().gdmae_timing_enable(0)
     timers, _lib.KERNEL_TIMERS = _lib.KERNEL_TIMERS, None
+    # spans recorded inside the C executor (SRA forward / backward of every encoder layer)
+    import ctypes
+    cap = 64 * max(args.steps, 1)
+    meta = (ctypes.c_int64 * (4 * cap))()
+    span_ms = (ctypes.c_float * cap)()
+    n_span = _lib.lib().gdmae_timing_drain(meta, span_ms, cap)
+    c_spans = {}
+    for i in range(n_span):
+        name = f"sra_{'bwd' if meta[4 * i] else 'fwd'}_d{meta[4 * i + 1]}"
+        c_spans.setdefault(name, []).append((float(span_ms[i]), int(meta[4 * i + 3])))
     clocks = sampler.stop()
     # ---- end-to-end timing through the public API with host inputs
     ms_e2e, last_e2e, _ = timed(step_e2e, args.steps, 2)
@@ -249,13 +261,20 @@ def main():
         kernels[name] = {"launches_per_step": len(evs) / args.steps, "avg_us": 1e3 * float(np.mean(ms)),
                          "achieved_gbs": float(np.mean(gbs)), "frac": float(np.mean(gbs)) / pk["hbm_gbs"],
                          "share_of_step": float(np.sum(ms)) / (ms_step * args.steps)}
+    for name, sp in c_spans.items():
+        ms = [t for t, _ in sp]
+        gbs = [nb / (t * 1e-3) / 1e9 for t, nb in sp if t > 0]
+        kernels[name] = {"launches_per_step": len(sp) / args.steps, "avg_us": 1e3 * float(np.mean(ms)),
+                         "achieved_gbs": float(np.mean(gbs)), "frac": float(np.mean(gbs)) / pk["hbm_gbs"],
+                         "share_of_step": float(np.sum(ms)) / (ms_step * args.steps)}
     dom = "sra_fwd_d256" if "sra_fwd_d256" in kernels else next(iter(kernels), None)
     roofline = None
     if dom:
         k = kernels[dom]
         roofline = {"kernel": dom, "bound": "hbm", "achieved": k["achieved_gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": k["frac"], "traffic": None, "peak_source": pk_src, "avg_us": k["avg_us"],
-                    "bytes_def": "N*d*(3+1)*4 + N*8 per launch (q,k,v in, o out, fp32; SURVEY.md 8d)"}
+                    "bytes_def": "N*d*(3*s_qkv + s_o) + N*8*4 per launch (q,k,v in, o and lse out; s = 2 bytes in the bf16 "
+                                 "configuration, 4 in fp32; SURVEY.md 8d)"}
 
     out = {
         "metric": "mae_pretrain_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,

@@ -126,7 +126,9 @@ def set_precision(model, dtype, matmul="high", gemm_bf16=True):
     torch.backends.cuda.matmul.allow_tf32 = fast
     torch.set_float32_matmul_precision(matmul if fast else "highest")
     from . import fused
-    ops.SRA_TENSOR_CORES = False  # r1: the TF32 mma variant is not faster than the fp32 kernel (tools/bench_sra.py)
+    # bf16 configuration: q/k/v leave the in-projection GEMM as bf16 and the SRA forward/backward run on the tensor
+    # cores (csrc/sra_attention_tc.cu); fp32/tf32 keep the fp32 SIMT kernels
+    ops.SRA_TENSOR_CORES = dtype == "bf16" and gemm_bf16
     # bf16 GEMM operands are written by the hand-written kernels themselves (no cast passes) and the GEMMs go
     # through gdmae_gemm (cublasGemmEx bf16 x bf16 -> fp32); torch.mm(out_dtype=fp32) was measured to triple the
     # host time per call (cublasLt path) and is not used.

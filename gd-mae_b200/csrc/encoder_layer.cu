@@ -52,6 +52,27 @@ __global__ void dtau_kernel(const double* __restrict__ dtau_sum, const float* __
   dtau[0] = accumulate ? dtau[0] + g : g;
 }
 
+extern "C" int gdmae_timing_on(void);
+extern "C" void gdmae_timing_push(int kind, int d, int64_t n, int64_t bytes, void* e0, void* e1);
+// bench-only CUDA events around one launch sequence (no-op unless gdmae_timing_enable(1))
+struct ElSpan {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaStream_t st;
+  explicit ElSpan(cudaStream_t s) : st(s) {
+    if (gdmae_timing_on()) {
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+      cudaEventRecord(e0, st);
+    }
+  }
+  void end(int kind, int d, int64_t n, int64_t bytes) {
+    if (e0) {
+      cudaEventRecord(e1, st);
+      gdmae_timing_push(kind, d, n, bytes, e0, e1);
+    }
+  }
+};
+
 #define EL_CALL(expr)        \
   do {                       \
     int _rc = (expr);        \
@@ -61,6 +82,7 @@ __global__ void dtau_kernel(const double* __restrict__ dtau_sum, const float* __
 static int el_check(const gdmae_encoder_layer_args* a) {
   GDMAE_CHECK_ARG(a && a->N >= 0 && (a->d == 128 || a->d == 256) && a->dff > 0 && a->dff % 8 == 0 && a->nhead == 8);
   GDMAE_CHECK_ARG(a->gemm_mode >= 0 && a->gemm_mode <= 2);
+  GDMAE_CHECK_ARG(!a->sra_tensor_cores || a->gemm_mode == 1);   // the tensor-core SRA kernels take bf16 q/k/v
   return GDMAE_OK;
 }
 
@@ -88,15 +110,19 @@ extern "C" int gdmae_encoder_layer_fwd(const gdmae_encoder_layer_args* a) {
     }
   }
   // in-projection without biases; positional term + q/k biases go through the 64-row LUT, the v bias to the output
-  EL_CALL(el_gemm(a, 0, 1, N, 3 * d, d, xg, d, a->w_in_g, d, a->qkv, 3 * d, 0, 0.f));
+  const int tc = a->sra_tensor_cores ? 1 : 0;      // bf16 q/k/v straight from the GEMM epilogue for the tensor-core kernels
+  EL_CALL(el_gemm(a, 0, 1, N, 3 * d, d, xg, d, a->w_in_g, d, a->qkv, 3 * d, tc, 0.f));
   pos_lut_kernel<<<gdmae_div_up(64ll * 2 * d * 32, 256), 256, 0, st>>>(a->pos_table, a->w_in, a->b_in, d, a->lut);
   GDMAE_LAUNCH_CHECK();
-  if (a->sra_tensor_cores)
+  ElSpan span(st);
+  if (tc)
     EL_CALL(gdmae_sra_attention_fwd_tc(a->qkv, a->lut, a->row_info, N, d, a->nhead, a->tau, a->tau_min, a->b_in + 2 * d, bf, a->o,
                                        a->lse, a->stream));
   else
-    EL_CALL(gdmae_sra_attention_fwd(a->qkv, a->lut, a->row_info, N, d, a->nhead, a->tau, a->tau_min, a->b_in + 2 * d, bf, a->o,
+    EL_CALL(gdmae_sra_attention_fwd((const float*)a->qkv, a->lut, a->row_info, N, d, a->nhead, a->tau, a->tau_min, a->b_in + 2 * d, bf, a->o,
                                     a->lse, a->stream));
+  // algorithmic bytes (SURVEY.md 8d, a18 minus projections): q, k, v in, o out, lse out
+  span.end(0, d, N, N * d * (3 * (tc ? 2 : 4) + (bf ? 2 : 4)) + N * 32);
   EL_CALL(el_gemm(a, 0, 1, N, d, d, a->o, d, a->w_o_g, d, a->a, d, 0, 0.f));
   EL_CALL(gdmae_add_layernorm_fwd(a->x, a->a, a->b_o, a->g1, a->be1, N, d, a->eps, a->x1, bf ? a->x1g : nullptr, a->mean1, a->rstd1,
                                   a->stream));
@@ -159,10 +185,18 @@ extern "C" int gdmae_encoder_layer_bwd(const gdmae_encoder_layer_args* a) {
   const void* dz1_op = bf ? (const void*)dz1g : (const void*)dz1;
   EL_CALL(gdmae_colsum(dz1, 0, N, d, 0, d, a->d_b_o, acc, rw, rw_bytes, a->stream));
   EL_CALL(el_gemm(a, 1, 0, d, d, N, dz1_op, d, a->o, d, a->d_w_o, d, 0, wbeta));
-  EL_CALL(el_gemm(a, 0, 0, N, d, d, dz1_op, d, a->w_o_g, d, dout, d, 0, 0.f));
+  const int tc = a->sra_tensor_cores ? 1 : 0;
+  EL_CALL(el_gemm(a, 0, 0, N, d, d, dz1_op, d, a->w_o_g, d, dout, d, tc, 0.f));
   GDMAE_CHECK_CUDA(cudaMemsetAsync(dtau_sum, 0, sizeof(double), st));
-  EL_CALL(gdmae_sra_attention_bwd(a->qkv, a->lut, a->row_info, N, d, a->nhead, a->tau, a->tau_min, a->b_in + 2 * d, bf, a->o, a->lse,
-                                  dout, dqkv, dtau_sum, work, a->stream));
+  ElSpan span(st);
+  if (tc)
+    EL_CALL(gdmae_sra_attention_bwd_tc(a->qkv, a->lut, a->row_info, N, d, a->nhead, a->tau, a->tau_min, a->lse, dout, dqkv, dtau_sum,
+                                       a->stream));
+  else
+    EL_CALL(gdmae_sra_attention_bwd((const float*)a->qkv, a->lut, a->row_info, N, d, a->nhead, a->tau, a->tau_min, a->b_in + 2 * d, bf,
+                                    a->o, a->lse, dout, dqkv, dtau_sum, work, a->stream));
+  // q, k, v, dO (+ o for the SIMT kernels) in, dq, dk, dv out, lse in
+  span.end(1, d, N, tc ? N * d * (6 + 2 + 6) + N * 32 : N * d * (12 + (bf ? 2 : 4) + 4 + 3 * (bf ? 2 : 4)) + N * 32);
   dtau_kernel<<<1, 1, 0, st>>>(dtau_sum, a->tau, a->tau_min, acc, a->d_tau);
   GDMAE_LAUNCH_CHECK();
   // in-projection: q = (x + pos) Wq^T + bq, k likewise, v = x Wv^T + bv

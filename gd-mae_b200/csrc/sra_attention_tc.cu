@@ -416,11 +416,481 @@ __global__ void __launch_bounds__(MM_THREADS, 1) sra_fwd_mma_kernel(MmArgs a, vo
   if (stager) mm_wait<0>();
 }
 
+// =====================================================================================================
+// Backward.  Same bins, packing and operand staging as the forward kernel; four staged arrays
+// (Qs = q_hat * log2(e)/tau, K_hat, V, dO) in two stage buffers, all 16 warps share every phase:
+//   stage    : + LUT, normalise q and k in place, keep 1/|q|, 1/|k| per (row, head); lse rows by cp.async
+//   phase 1  : one warp per (unit, head), query side.  One sweep over the key tiles computes S' = Qs K^T and
+//              dP = dO V^T on the tensor cores, P = exp2(S' - lse), and the row sums D = sum P dP,
+//              T1 = sum P dP S', T2 = sum P S' (d tau needs sum dS S = T1 - D T2); P stays in registers as
+//              packed bf16, dP as fp32; then dS = P (dP - D) feeds G = dS K as the A operand and the
+//              normalisation backward dq = (G - Qs (Qs.G) / qscale^2) / (tau |q|) is applied on the fragments.
+//   phase 2  : key side, the same units with the roles swapped (attention inside a window is all-to-all, so the
+//              queries of a key tile are exactly the unit's key range): per 16-query step S'^T = K Qs^T,
+//              dP^T = V dO^T, P^T, dS^T = P^T (dP^T - D), then dV += P^T dO and H += dS^T Qs; nothing is held
+//              across steps.  dk = ln2 (H - K (K.H)) / |k|.
+// dq, dk, dv rows go straight from the fragments to dqkv (bf16); sum dS S is reduced per CTA into dtau_sum.
+#define MB_STAGES 2
+#define MB_NINFO 4
+#define MB_STAGE_ELEMS (4 * MM_ARR)
+#define MB_SCAL (MM_ROWS * 4)      // one fp32 per (row, head of the slice)
+#define MB_SMEM_BYTES (64 * 2 * MM_SLICE * 2 + MB_STAGES * MB_STAGE_ELEMS * 2 + MB_NINFO * MM_INFO * 16 + (MB_STAGES + 3) * MB_SCAL * 4 + (MM_UNITS + 16) * 4)
+
+struct MbArgs {
+  const bf16* qkv;     // (N, 3d) bf16
+  const float* lut;    // (64, 2d)
+  const int4* row_info;
+  const float* tau;
+  const float* lse;    // (N, 8)
+  const bf16* dout;    // (N, d) bf16
+  bf16* dqkv;          // (N, 3d) bf16
+  double* dtau_sum;
+  float tau_min;
+  int N, d;
+};
+
+__device__ __forceinline__ void mb_issue_rows(bf16* stage, float* slse, const int4* inf, const MbArgs& a, int col, int hs, int lse_col,
+                                              int bin, int tid) {
+  int row0, R;
+  mm_bin_range(inf, bin, a.N, row0, R);
+  const int shift = row0 - bin;
+  const int d = a.d;
+  for (int idx = tid; idx < R * 8; idx += MM_THREADS) {      // one 16-byte chunk of q, k, v and dO each
+    const int r = idx >> 3, c8 = idx & 7;
+    const long long tok = inf[r + shift].x;
+    const bf16* src = a.qkv + tok * 3 * d + col + 8 * c8;
+    bf16* dst = stage + r * MM_PITCH + 8 * c8;
+    mm_cp16(dst, src);
+    mm_cp16(dst + MM_ARR, src + d);
+    mm_cp16(dst + 2 * MM_ARR, src + 2 * d);
+    mm_cp16(dst + 3 * MM_ARR, a.dout + tok * d + col + 8 * c8);
+  }
+  for (int idx = tid; idx < R * hs; idx += MM_THREADS) {     // lse of the slice's heads, 4 bytes each
+    const int r = idx / hs, h = idx - r * hs;
+    unsigned sa = (unsigned)__cvta_generic_to_shared(slse + r * 4 + h);
+    const float* src = a.lse + (long long)inf[r + shift].x * 8 + lse_col + h;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(src) : "memory");
+  }
+}
+
+__device__ __forceinline__ float2 unpack_bf16(unsigned u) { return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
+
+// query side of one (unit, head): writes dq rows and sD, returns this lane's share of sum dS*S' (valid rows only)
+template <int HD, int NT2>
+__device__ __forceinline__ float mb_unit_q(const MbArgs& a, const bf16* sq, const bf16* sk, const bf16* sv, const bf16* sdo,
+                                           const float* slse, const float* srq, float* sD, int q0, int qn, int k0, int h, int4 recA,
+                                           int4 recB, int kbase, int lane, int col, float inv_tau, float inv_qs2) {
+  constexpr int KS = HD / 16, ND = HD / 8;
+  const int g = lane >> 2, t = lane & 3, ch = h * HD;
+  const int loA = recA.y - kbase, wA = recA.z - recA.y, loB = recB.y - kbase, wB = recB.z - recB.y;
+  const int ka = 2 * t - loA, kb_ = 2 * t - loB;
+  unsigned qa[KS][4], da[KS][4];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    const int off = (q0 + (lane & 7) + 8 * ((lane >> 3) & 1)) * MM_PITCH + ch + 16 * ks + 8 * (lane >> 4);
+    ldsm_x4(qa[ks], sq + off);
+    ldsm_x4(da[ks], sdo + off);
+  }
+  const float lA = slse[min(q0 + g, MM_ROWS - 1) * 4 + h] * 1.4426950408889634f;
+  const float lB = slse[min(q0 + g + 8, MM_ROWS - 1) * 4 + h] * 1.4426950408889634f;
+  unsigned pp[NT2][2];   // P packed bf16: [nt][0] = row g, [nt][1] = row g+8
+  float dp[NT2][4];
+  float D0 = 0.f, D1 = 0.f, T10 = 0.f, T11 = 0.f, T20 = 0.f, T21 = 0.f;
+#pragma unroll
+  for (int np = 0; np < NT2 / 2; ++np) {
+    float s[2][4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      s[u][0] = s[u][1] = s[u][2] = s[u][3] = 0.f;
+      dp[2 * np + u][0] = dp[2 * np + u][1] = dp[2 * np + u][2] = dp[2 * np + u][3] = 0.f;
+    }
+    unsigned kb[4], vb[4];
+    if (KS == 2) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int off = (k0 + 8 * (2 * np + u) + (lane & 7)) * MM_PITCH + ch + 8 * (lane >> 3);
+        ldsm_x4(kb, sk + off);
+        ldsm_x4(vb, sv + off);
+        mma_bf16(s[u], qa[0], kb[0], kb[1]);
+        mma_bf16(s[u], qa[KS - 1], kb[2], kb[3]);
+        mma_bf16(dp[2 * np + u], da[0], vb[0], vb[1]);
+        mma_bf16(dp[2 * np + u], da[KS - 1], vb[2], vb[3]);
+      }
+    } else {
+      const int off = (k0 + 16 * np + 8 * (lane >> 4) + (lane & 7)) * MM_PITCH + ch + 8 * ((lane >> 3) & 1);
+      ldsm_x4(kb, sk + off);
+      ldsm_x4(vb, sv + off);
+      mma_bf16(s[0], qa[0], kb[0], kb[1]);
+      mma_bf16(s[1], qa[0], kb[2], kb[3]);
+      mma_bf16(dp[2 * np], da[0], vb[0], vb[1]);
+      mma_bf16(dp[2 * np + 1], da[0], vb[2], vb[3]);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int nt = 2 * np + u;
+      float p[4];
+      p[0] = (unsigned)(ka + 8 * nt) < (unsigned)wA ? fast_exp2(s[u][0] - lA) : 0.f;
+      p[1] = (unsigned)(ka + 8 * nt + 1) < (unsigned)wA ? fast_exp2(s[u][1] - lA) : 0.f;
+      p[2] = (unsigned)(kb_ + 8 * nt) < (unsigned)wB ? fast_exp2(s[u][2] - lB) : 0.f;
+      p[3] = (unsigned)(kb_ + 8 * nt + 1) < (unsigned)wB ? fast_exp2(s[u][3] - lB) : 0.f;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float x0 = p[e] * dp[nt][e], x1 = p[2 + e] * dp[nt][2 + e];
+        D0 += x0; D1 += x1;
+        T10 = fmaf(x0, s[u][e], T10); T11 = fmaf(x1, s[u][2 + e], T11);
+        T20 = fmaf(p[e], s[u][e], T20); T21 = fmaf(p[2 + e], s[u][2 + e], T21);
+      }
+      pp[nt][0] = pack_bf16(p[0], p[1]);
+      pp[nt][1] = pack_bf16(p[2], p[3]);
+    }
+  }
+#pragma unroll
+  for (int o = 1; o <= 2; o <<= 1) {
+    D0 += __shfl_xor_sync(0xffffffffu, D0, o); D1 += __shfl_xor_sync(0xffffffffu, D1, o);
+    T10 += __shfl_xor_sync(0xffffffffu, T10, o); T11 += __shfl_xor_sync(0xffffffffu, T11, o);
+    T20 += __shfl_xor_sync(0xffffffffu, T20, o); T21 += __shfl_xor_sync(0xffffffffu, T21, o);
+  }
+  float dtau_part = 0.f;   // the quad holds identical sums: count each row once
+  if (t == 0) {
+    if (g < qn) { dtau_part += T10 - D0 * T20; sD[(q0 + g) * 4 + h] = D0; }
+    if (g + 8 < qn) { dtau_part += T11 - D1 * T21; sD[(q0 + g + 8) * 4 + h] = D1; }
+  }
+  // G = dS K_hat
+  float acc[ND][4];
+#pragma unroll
+  for (int nd = 0; nd < ND; ++nd) acc[nd][0] = acc[nd][1] = acc[nd][2] = acc[nd][3] = 0.f;
+#pragma unroll
+  for (int kt = 0; kt < NT2 / 2; ++kt) {
+    unsigned sa[4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int nt = 2 * kt + u;
+      const float2 pA = unpack_bf16(pp[nt][0]), pB = unpack_bf16(pp[nt][1]);
+      sa[2 * u] = pack_bf16(pA.x * (dp[nt][0] - D0), pA.y * (dp[nt][1] - D0));
+      sa[2 * u + 1] = pack_bf16(pB.x * (dp[nt][2] - D1), pB.y * (dp[nt][3] - D1));
+    }
+#pragma unroll
+    for (int np = 0; np < ND / 2; ++np) {
+      unsigned kb[4];
+      ldsm_x4_t(kb, sk + (k0 + 16 * kt + (lane & 7) + 8 * ((lane >> 3) & 1)) * MM_PITCH + ch + 16 * np + 8 * (lane >> 4));
+      mma_bf16(acc[2 * np], sa, kb[0], kb[1]);
+      mma_bf16(acc[2 * np + 1], sa, kb[2], kb[3]);
+    }
+  }
+  // normalisation backward on the fragments: dq = (G - Qs (Qs.G) / qscale^2) / (tau |q|)
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int row = q0 + g + 8 * half;
+    float2 qv[ND];
+    float dot = 0.f;
+#pragma unroll
+    for (int nd = 0; nd < ND; ++nd) {
+      qv[nd] = unpack_bf16(*reinterpret_cast<const unsigned*>(sq + row * MM_PITCH + ch + 8 * nd + 2 * t));
+      dot = fmaf(qv[nd].x, acc[nd][2 * half], dot);
+      dot = fmaf(qv[nd].y, acc[nd][2 * half + 1], dot);
+    }
+    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+    if (g + 8 * half < qn) {
+      const float f = srq[row * 4 + h] * inv_tau, c2 = dot * inv_qs2;
+      bf16* dst = a.dqkv + (long long)(half ? recB.x : recA.x) * 3 * a.d + col + ch + 2 * t;
+#pragma unroll
+      for (int nd = 0; nd < ND; ++nd)
+        *reinterpret_cast<unsigned*>(dst + 8 * nd) =
+            pack_bf16(f * (acc[nd][2 * half] - qv[nd].x * c2), f * (acc[nd][2 * half + 1] - qv[nd].y * c2));
+    }
+  }
+  return dtau_part;
+}
+
+// key side of one (unit, head): rows = the unit's 16-row tile as KEYS, columns = its key range as QUERIES
+template <int HD, int NT2>
+__device__ __forceinline__ void mb_unit_kv(const MbArgs& a, const bf16* sq, const bf16* sk, const bf16* sv, const bf16* sdo,
+                                           const float* slse, const float* srk, const float* sD, int q0, int qn, int k0, int h,
+                                           int4 recA, int4 recB, int kbase, int lane, int col) {
+  constexpr int KS = HD / 16, ND = HD / 8;
+  const int g = lane >> 2, t = lane & 3, ch = h * HD;
+  const int loA = recA.y - kbase, wA = recA.z - recA.y, loB = recB.y - kbase, wB = recB.z - recB.y;
+  const int ka = 2 * t - loA, kb_ = 2 * t - loB;
+  unsigned ka_f[KS][4], va_f[KS][4];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    const int off = (q0 + (lane & 7) + 8 * ((lane >> 3) & 1)) * MM_PITCH + ch + 16 * ks + 8 * (lane >> 4);
+    ldsm_x4(ka_f[ks], sk + off);
+    ldsm_x4(va_f[ks], sv + off);
+  }
+  float dv[ND][4], hk[ND][4];
+#pragma unroll
+  for (int nd = 0; nd < ND; ++nd) {
+    dv[nd][0] = dv[nd][1] = dv[nd][2] = dv[nd][3] = 0.f;
+    hk[nd][0] = hk[nd][1] = hk[nd][2] = hk[nd][3] = 0.f;
+  }
+#pragma unroll
+  for (int np = 0; np < NT2 / 2; ++np) {
+    float s[2][4], dp[2][4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      s[u][0] = s[u][1] = s[u][2] = s[u][3] = 0.f;
+      dp[u][0] = dp[u][1] = dp[u][2] = dp[u][3] = 0.f;
+    }
+    unsigned qb[4], ob[4];
+    if (KS == 2) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int off = (k0 + 8 * (2 * np + u) + (lane & 7)) * MM_PITCH + ch + 8 * (lane >> 3);
+        ldsm_x4(qb, sq + off);
+        ldsm_x4(ob, sdo + off);
+        mma_bf16(s[u], ka_f[0], qb[0], qb[1]);
+        mma_bf16(s[u], ka_f[KS - 1], qb[2], qb[3]);
+        mma_bf16(dp[u], va_f[0], ob[0], ob[1]);
+        mma_bf16(dp[u], va_f[KS - 1], ob[2], ob[3]);
+      }
+    } else {
+      const int off = (k0 + 16 * np + 8 * (lane >> 4) + (lane & 7)) * MM_PITCH + ch + 8 * ((lane >> 3) & 1);
+      ldsm_x4(qb, sq + off);
+      ldsm_x4(ob, sdo + off);
+      mma_bf16(s[0], ka_f[0], qb[0], qb[1]);
+      mma_bf16(s[1], ka_f[0], qb[2], qb[3]);
+      mma_bf16(dp[0], va_f[0], ob[0], ob[1]);
+      mma_bf16(dp[1], va_f[0], ob[2], ob[3]);
+    }
+    unsigned pa[4], sa[4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int nt = 2 * np + u;
+      // this lane's two query columns of the tile
+      const int qc = min(k0 + 8 * nt + 2 * t, MM_ROWS - 2);
+      const float l0 = slse[qc * 4 + h] * 1.4426950408889634f, l1 = slse[(qc + 1) * 4 + h] * 1.4426950408889634f;
+      const float d0 = sD[qc * 4 + h], d1 = sD[(qc + 1) * 4 + h];
+      const float p0 = (unsigned)(ka + 8 * nt) < (unsigned)wA ? fast_exp2(s[u][0] - l0) : 0.f;
+      const float p1 = (unsigned)(ka + 8 * nt + 1) < (unsigned)wA ? fast_exp2(s[u][1] - l1) : 0.f;
+      const float p2 = (unsigned)(kb_ + 8 * nt) < (unsigned)wB ? fast_exp2(s[u][2] - l0) : 0.f;
+      const float p3 = (unsigned)(kb_ + 8 * nt + 1) < (unsigned)wB ? fast_exp2(s[u][3] - l1) : 0.f;
+      pa[2 * u] = pack_bf16(p0, p1);
+      pa[2 * u + 1] = pack_bf16(p2, p3);
+      sa[2 * u] = pack_bf16(p0 * (dp[u][0] - d0), p1 * (dp[u][1] - d1));
+      sa[2 * u + 1] = pack_bf16(p2 * (dp[u][2] - d0), p3 * (dp[u][3] - d1));
+    }
+#pragma unroll
+    for (int nq = 0; nq < ND / 2; ++nq) {
+      unsigned ob2[4], qb2[4];
+      const int off = (k0 + 16 * np + (lane & 7) + 8 * ((lane >> 3) & 1)) * MM_PITCH + ch + 16 * nq + 8 * (lane >> 4);
+      ldsm_x4_t(ob2, sdo + off);
+      ldsm_x4_t(qb2, sq + off);
+      mma_bf16(dv[2 * nq], pa, ob2[0], ob2[1]);
+      mma_bf16(dv[2 * nq + 1], pa, ob2[2], ob2[3]);
+      mma_bf16(hk[2 * nq], sa, qb2[0], qb2[1]);
+      mma_bf16(hk[2 * nq + 1], sa, qb2[2], qb2[3]);
+    }
+  }
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int row = q0 + g + 8 * half;
+    float2 kv[ND];
+    float dot = 0.f;
+#pragma unroll
+    for (int nd = 0; nd < ND; ++nd) {
+      kv[nd] = unpack_bf16(*reinterpret_cast<const unsigned*>(sk + row * MM_PITCH + ch + 8 * nd + 2 * t));
+      dot = fmaf(kv[nd].x, hk[nd][2 * half], dot);
+      dot = fmaf(kv[nd].y, hk[nd][2 * half + 1], dot);
+    }
+    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+    if (g + 8 * half < qn) {
+      const float f = srk[row * 4 + h] * 0.6931471805599453f;
+      bf16* dst = a.dqkv + (long long)(half ? recB.x : recA.x) * 3 * a.d + a.d + col + ch + 2 * t;
+#pragma unroll
+      for (int nd = 0; nd < ND; ++nd) {
+        *reinterpret_cast<unsigned*>(dst + 8 * nd) =
+            pack_bf16(f * (hk[nd][2 * half] - kv[nd].x * dot), f * (hk[nd][2 * half + 1] - kv[nd].y * dot));
+        *reinterpret_cast<unsigned*>(dst + a.d + 8 * nd) = pack_bf16(dv[nd][2 * half], dv[nd][2 * half + 1]);
+      }
+    }
+  }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(MM_THREADS, 1) sra_bwd_mma_kernel(MbArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  bf16* slut = (bf16*)smem_raw;
+  bf16* sdata = slut + 64 * 2 * MM_SLICE;                     // MB_STAGES x {q, k, v, dO} x [144][72]
+  int4* sinfo_all = (int4*)(sdata + MB_STAGES * MB_STAGE_ELEMS);
+  float* slse_all = (float*)(sinfo_all + MB_NINFO * MM_INFO); // MB_STAGES x [144][4]
+  float* srq = slse_all + MB_STAGES * MB_SCAL;                // 1/|q| per (row, head)
+  float* srk = srq + MB_SCAL;
+  float* sD = srk + MB_SCAL;
+  int* sunit = (int*)(sD + MB_SCAL);
+  __shared__ float s_dtau[MM_THREADS / 32];
+  constexpr int HS = MM_SLICE / HD;
+  constexpr int NWARPS = MM_THREADS >> 5;
+  const int d = a.d;
+  const int nsl = d / MM_SLICE;
+  const int sl = blockIdx.x % nsl, cta = blockIdx.x / nsl, ncta = gridDim.x / nsl;
+  const int col = sl * MM_SLICE;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nbins = (a.N + MM_BIN - 1) / MM_BIN;
+  if (cta >= nbins) return;
+  const int my_bins = (nbins - cta + ncta - 1) / ncta;
+  const int lse_col = sl * HS;
+
+  for (int i = tid; i < MB_STAGES * MB_STAGE_ELEMS / 8; i += MM_THREADS) reinterpret_cast<uint4*>(sdata)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < (MB_STAGES + 3) * MB_SCAL; i += MM_THREADS) slse_all[i] = 0.f;
+  for (int idx = tid; idx < 64 * MM_SLICE; idx += MM_THREADS) {
+    int pos = idx >> 6, c2 = idx & 63;
+    int part = c2 >> 5, cc = (c2 & 31) * 2;
+    float2 v = __ldg(reinterpret_cast<const float2*>(a.lut + (long long)pos * 2 * d + part * d + col + cc));
+    *reinterpret_cast<unsigned*>(slut + pos * 2 * MM_SLICE + part * MM_SLICE + cc) = pack_bf16(v.x, v.y);
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+    if (j < my_bins) mm_issue_info(sinfo_all + j * MM_INFO, a.row_info, (cta + j * ncta) * MM_BIN, a.N, tid);
+  mm_commit();
+  mm_wait<0>();
+  __syncthreads();
+  mb_issue_rows(sdata, slse_all, sinfo_all, a, col, HS, lse_col, cta * MM_BIN, tid);
+  mm_commit();
+  const float tau_c = fmaxf(__ldg(a.tau), a.tau_min);
+  const float qscale = 1.4426950408889634f / tau_c, inv_tau = 1.f / tau_c, inv_qs2 = 1.f / (qscale * qscale);
+  float dtau_acc = 0.f;
+
+  for (int k = 0; k < my_bins; ++k) {
+    const int bin = (cta + k * ncta) * MM_BIN;
+    const int4* sinfo = sinfo_all + (k % MB_NINFO) * MM_INFO;
+    bf16* sq = sdata + (k % MB_STAGES) * MB_STAGE_ELEMS;
+    bf16* sk = sq + MM_ARR;
+    bf16* sv = sk + MM_ARR;
+    bf16* sdo = sv + MM_ARR;
+    float* slse = slse_all + (k % MB_STAGES) * MB_SCAL;
+    mm_wait<0>();        // rows of bin k, records of bin k+2
+    __syncthreads();     // ... visible; everyone is done with bin k-1
+    if (k + 1 < my_bins)
+      mb_issue_rows(sdata + ((k + 1) % MB_STAGES) * MB_STAGE_ELEMS, slse_all + ((k + 1) % MB_STAGES) * MB_SCAL,
+                    sinfo_all + ((k + 1) % MB_NINFO) * MM_INFO, a, col, HS, lse_col, (cta + (k + 1) * ncta) * MM_BIN, tid);
+    if (k + 3 < my_bins)
+      mm_issue_info(sinfo_all + ((k + 3) % MB_NINFO) * MM_INFO, a.row_info, (cta + (k + 3) * ncta) * MM_BIN, a.N, tid);
+    mm_commit();
+    int row0, R;
+    mm_bin_range(sinfo, bin, a.N, row0, R);
+    if (R == 0) continue;
+    const int shift = row0 - bin;
+    // ---- work units (last warp), q / k normalisation (everyone)
+    if (warp == NWARPS - 1) {
+      int nu = 0;
+      unsigned long long m0 = 0, m1 = 0;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        int r = 32 * w + lane;
+        bool st = r < R && sinfo[min(r, R - 1) + shift].y == row0 + r;
+        unsigned long long b = __ballot_sync(0xffffffffu, st);
+        if (w < 2) m0 |= b << (32 * w);
+        else m1 |= b << (32 * (w - 2));
+      }
+      if (R < 64) m0 |= 1ull << R;
+      else m1 |= 1ull << (R - 64);
+      int s = 0;
+      while (s < R && nu < MM_UNITS) {
+        unsigned w16 = mm_bits(m0, m1, s + 1) & 0xffffu;
+        if (w16) {
+          int e = s + 32 - __clz(w16);
+          if (lane == 0) sunit[nu] = s | ((e - s) << 7) | (s << 12) | ((e - s) << 19);
+          ++nu;
+          s = e;
+        } else {
+          unsigned lo = mm_bits(m0, m1, s + 17), hi = mm_bits(m0, m1, s + 49);
+          int n = lo ? 16 + __ffs(lo) : 48 + __ffs(hi);
+          for (int m = 0; m < n && nu < MM_UNITS; m += 16) {
+            if (lane == 0) sunit[nu] = (s + m) | (min(16, n - m) << 7) | (s << 12) | (n << 19);
+            ++nu;
+          }
+          s += n;
+        }
+      }
+      if (lane == 0) sunit[MM_UNITS] = nu;
+    }
+    {
+      const int ntask = R * 16;
+      for (int base = 0; base < ntask; base += MM_THREADS) {
+        const int idx = base + tid;
+        const bool valid = idx < ntask;
+        const int r = valid ? (idx >> 4) : 0;
+        const int part = (idx >> 3) & 1, c8 = idx & 7;
+        bf16* p = sq + part * MM_ARR + r * MM_PITCH + 8 * c8;
+        const uint4 raw = *reinterpret_cast<const uint4*>(p);
+        const uint4 lr = *reinterpret_cast<const uint4*>(slut + sinfo[r + shift].w * 2 * MM_SLICE + part * MM_SLICE + 8 * c8);
+        float x[8];
+        const unsigned rw[4] = {raw.x, raw.y, raw.z, raw.w}, lw[4] = {lr.x, lr.y, lr.z, lr.w};
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          x[2 * i] = __uint_as_float(rw[i] << 16) + __uint_as_float(lw[i] << 16);
+          x[2 * i + 1] = __uint_as_float(rw[i] & 0xffff0000u) + __uint_as_float(lw[i] & 0xffff0000u);
+          ss = fmaf(x[2 * i], x[2 * i], ss);
+          ss = fmaf(x[2 * i + 1], x[2 * i + 1], ss);
+        }
+        ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+        if (HD == 32) ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+        float rn;
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rn) : "f"(fmaxf(ss, 1e-24f)));
+        const float f = part == 0 ? rn * qscale : rn;
+        if (valid) {
+          uint4 o;
+          o.x = pack_bf16(x[0] * f, x[1] * f);
+          o.y = pack_bf16(x[2] * f, x[3] * f);
+          o.z = pack_bf16(x[4] * f, x[5] * f);
+          o.w = pack_bf16(x[6] * f, x[7] * f);
+          *reinterpret_cast<uint4*>(p) = o;
+          if ((c8 & (HD / 8 - 1)) == 0) (part == 0 ? srq : srk)[r * 4 + c8 / (HD / 8)] = rn;
+        }
+      }
+    }
+    __syncthreads();
+    const int nent = sunit[MM_UNITS] * HS;
+    const int g = lane >> 2;
+    // ---- phase 1: query side
+    for (int e = warp; e < nent; e += NWARPS) {
+      const int code = sunit[e / HS];
+      const int h = e % HS;
+      const int q0 = code & 127, qn = (code >> 7) & 31, k0 = (code >> 12) & 127, kn = (code >> 19) & 127;
+      const int4 recA = sinfo[min(q0 + g, R - 1) + shift], recB = sinfo[min(q0 + g + 8, R - 1) + shift];
+      const int kbase = row0 + k0;
+      if (kn <= 16) dtau_acc += mb_unit_q<HD, 2>(a, sq, sk, sv, sdo, slse, srq, sD, q0, qn, k0, h, recA, recB, kbase, lane, col, inv_tau, inv_qs2);
+      else if (kn <= 32) dtau_acc += mb_unit_q<HD, 4>(a, sq, sk, sv, sdo, slse, srq, sD, q0, qn, k0, h, recA, recB, kbase, lane, col, inv_tau, inv_qs2);
+      else if (kn <= 48) dtau_acc += mb_unit_q<HD, 6>(a, sq, sk, sv, sdo, slse, srq, sD, q0, qn, k0, h, recA, recB, kbase, lane, col, inv_tau, inv_qs2);
+      else dtau_acc += mb_unit_q<HD, 8>(a, sq, sk, sv, sdo, slse, srq, sD, q0, qn, k0, h, recA, recB, kbase, lane, col, inv_tau, inv_qs2);
+    }
+    __syncthreads();     // sD of every row of the bin is written
+    // ---- phase 2: key side
+    for (int e = warp; e < nent; e += NWARPS) {
+      const int code = sunit[e / HS];
+      const int h = e % HS;
+      const int q0 = code & 127, qn = (code >> 7) & 31, k0 = (code >> 12) & 127, kn = (code >> 19) & 127;
+      const int4 recA = sinfo[min(q0 + g, R - 1) + shift], recB = sinfo[min(q0 + g + 8, R - 1) + shift];
+      const int kbase = row0 + k0;
+      if (kn <= 16) mb_unit_kv<HD, 2>(a, sq, sk, sv, sdo, slse, srk, sD, q0, qn, k0, h, recA, recB, kbase, lane, col);
+      else if (kn <= 32) mb_unit_kv<HD, 4>(a, sq, sk, sv, sdo, slse, srk, sD, q0, qn, k0, h, recA, recB, kbase, lane, col);
+      else if (kn <= 48) mb_unit_kv<HD, 6>(a, sq, sk, sv, sdo, slse, srk, sD, q0, qn, k0, h, recA, recB, kbase, lane, col);
+      else mb_unit_kv<HD, 8>(a, sq, sk, sv, sdo, slse, srk, sD, q0, qn, k0, h, recA, recB, kbase, lane, col);
+    }
+  }
+  mm_wait<0>();
+  // sum dS*S of this CTA (natural-log scores: S = S' ln2)
+  dtau_acc = warp_sum(dtau_acc);
+  if (lane == 0) s_dtau[warp] = dtau_acc;
+  __syncthreads();
+  if (tid == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < NWARPS; ++w) tot += s_dtau[w];
+    atomicAdd(a.dtau_sum, (double)tot * 0.6931471805599453);
+  }
+}
+
 static int mm_attrs() {
   static bool done = false;
   if (!done) {
     GDMAE_CHECK_CUDA(cudaFuncSetAttribute(sra_fwd_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
     GDMAE_CHECK_CUDA(cudaFuncSetAttribute(sra_fwd_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
+    GDMAE_CHECK_CUDA(cudaFuncSetAttribute(sra_bwd_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_SMEM_BYTES));
+    GDMAE_CHECK_CUDA(cudaFuncSetAttribute(sra_bwd_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_SMEM_BYTES));
     done = true;
   }
   return GDMAE_OK;
@@ -441,6 +911,27 @@ extern "C" int gdmae_sra_attention_fwd_tc(const void* qkv_bf16, const float* lut
   // one CTA per SM; 148 is a multiple of the 2 (d = 128) and 4 (d = 256) channel slices
   if (d == 128) sra_fwd_mma_kernel<16><<<GDMAE_NUM_SMS, MM_THREADS, MM_SMEM_BYTES, st>>>(a, out, lse);
   else sra_fwd_mma_kernel<32><<<GDMAE_NUM_SMS, MM_THREADS, MM_SMEM_BYTES, st>>>(a, out, lse);
+  GDMAE_LAUNCH_CHECK();
+  return GDMAE_OK;
+}
+
+// Tensor-core backward for bf16 tensors: qkv (N,3d), dout (N,d) and dqkv (N,3d) are bf16; lse (N,8) from the forward;
+// dtau_sum (1, double, caller zeroes) accumulates sum dS*S as gdmae_sra_attention_bwd does.  The value bias and the
+// forward output are not needed (sum_j P dP replaces dO.(o - bv)).
+extern "C" int gdmae_sra_attention_bwd_tc(const void* qkv_bf16, const float* lut, const int32_t* row_info, int64_t N, int d, int nhead,
+                                          const float* tau, float tau_min, const float* lse, const void* dout_bf16, void* dqkv_bf16,
+                                          double* dtau_sum, void* stream_) {
+  GDMAE_CHECK_ARG(N >= 0 && N < (1ll << 27) && nhead == 8 && (d == 128 || d == 256));
+  GDMAE_CHECK_ARG(((uintptr_t)row_info % 16) == 0 && ((uintptr_t)qkv_bf16 % 16) == 0 && ((uintptr_t)lut % 8) == 0);
+  GDMAE_CHECK_ARG(((uintptr_t)dout_bf16 % 16) == 0 && ((uintptr_t)dqkv_bf16 % 16) == 0 && ((uintptr_t)lse % 4) == 0);
+  if (N == 0) return GDMAE_OK;
+  int rc = mm_attrs();
+  if (rc) return rc;
+  MbArgs a{(const bf16*)qkv_bf16, lut, (const int4*)row_info, tau, lse, (const bf16*)dout_bf16, (bf16*)dqkv_bf16, dtau_sum, tau_min,
+           (int)N, d};
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (d == 128) sra_bwd_mma_kernel<16><<<GDMAE_NUM_SMS, MM_THREADS, MB_SMEM_BYTES, st>>>(a);
+  else sra_bwd_mma_kernel<32><<<GDMAE_NUM_SMS, MM_THREADS, MB_SMEM_BYTES, st>>>(a);
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;
 }

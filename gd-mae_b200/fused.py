@@ -208,7 +208,8 @@ class EncoderLayerFunction(torch.autograd.Function):
         dev = x.device
         A = EncoderLayerArgs()
         A.N, A.d, A.dff, A.nhead, A.gemm_mode = N, d, dff, nhead, mode
-        A.sra_tensor_cores, A.accumulate, A.tau_min, A.eps = int(_ops.SRA_TENSOR_CORES), 0, tau_min, eps
+        tc = bool(_ops.SRA_TENSOR_CORES) and bf
+        A.sra_tensor_cores, A.accumulate, A.tau_min, A.eps = int(tc), 0, tau_min, eps
         A.x, A.pos_table, A.row_info, A.pos_of_token = x.data_ptr(), pos_table.data_ptr(), table.row_info.data_ptr(), \
             table.pos_of_token.data_ptr()
         keep = [x, pos_table, table.row_info, table.pos_of_token]
@@ -224,11 +225,11 @@ class EncoderLayerFunction(torch.autograd.Function):
             A.xg_in = xg_in.data_ptr()
         # ---- activations saved for backward: one fp32 and one bf16 buffer, carved here
         Nd, Nf = _r64(N * d), _r64(N * dff)
-        n32 = 3 * Nd + 2 * Nd + Nf + Nd + _r64(N * 8) + 4 * _r64(N) + 128 * d + (0 if bf else Nd + Nf)
+        n32 = (0 if tc else 3 * Nd) + 2 * Nd + Nf + Nd + _r64(N * 8) + 4 * _r64(N) + 128 * d + (0 if bf else Nd + Nf)
         save32 = torch.empty((max(n32, 1),), dtype=F32, device=dev)
         b = save32.data_ptr()
         off = 0
-        for name, n in (("qkv", 3 * Nd), ("a", Nd), ("x1", Nd), ("h", Nf), ("f", Nd), ("lse", _r64(N * 8)), ("mean1", _r64(N)),
+        for name, n in (("qkv", 0 if tc else 3 * Nd), ("a", Nd), ("x1", Nd), ("h", Nf), ("f", Nd), ("lse", _r64(N * 8)), ("mean1", _r64(N)),
                         ("rstd1", _r64(N)), ("mean2", _r64(N)), ("rstd2", _r64(N)), ("lut", 128 * d)):
             setattr(A, name, b + 4 * off)
             off += n
@@ -236,9 +237,11 @@ class EncoderLayerFunction(torch.autograd.Function):
         A.x2 = x2.data_ptr()
         save16 = x2g = None
         if bf:
-            save16 = torch.empty((max(4 * Nd + Nf, 1),), dtype=BF16, device=dev)
+            save16 = torch.empty((max(4 * Nd + Nf + (3 * Nd if tc else 0), 1),), dtype=BF16, device=dev)
             b16 = save16.data_ptr()
             A.xg, A.o, A.x1g, A.x2g, A.g = b16, b16 + 2 * Nd, b16 + 4 * Nd, b16 + 6 * Nd, b16 + 8 * Nd
+            if tc:
+                A.qkv = b16 + 2 * (4 * Nd + Nf)
             x2g = save16[3 * Nd:3 * Nd + N * d].view(N, d)
         else:
             A.o, A.g = b + 4 * off, b + 4 * (off + Nd)

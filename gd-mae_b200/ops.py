@@ -289,12 +289,21 @@ def sra_fwd(qkv, lut, tau, table, tau_min, nhead, bv=None, out_dtype=torch.float
 
 
 def sra_bwd(qkv, lut, tau, table, tau_min, nhead, out, lse, dout, bv=None, io_dtype=torch.float32):
-    """raw launch: -> (dqkv (N,3d) in io_dtype, dtau_sum (1) float64 = sum dS*S); ``out`` is the forward output."""
+    """raw launch: -> (dqkv (N,3d) in io_dtype, dtau_sum (1) float64 = sum dS*S); ``out`` is the forward output.
+    bf16 qkv (+ bf16 dout) selects the tensor-core kernel, which needs neither ``out`` nor ``bv``."""
     N, d3 = qkv.shape
     d = d3 // 3
+    dtau_sum = torch.zeros((1,), dtype=torch.float64, device=qkv.device)
+    if qkv.dtype == torch.bfloat16:
+        assert dout.dtype == torch.bfloat16
+        dqkv = torch.empty((N, d3), dtype=torch.bfloat16, device=qkv.device)
+        with L.timed(f"sra_bwd_d{d}", N * d * (6 + 2 + 6) + N * 8 * 4):
+            L.check(L.lib().gdmae_sra_attention_bwd_tc(L.P(qkv), L.P(lut), L.P(table.row_info), L.i64(N), d, nhead, L.P(tau),
+                                                       L.f32(tau_min), L.P(lse), L.P(dout), L.P(dqkv), L.P(dtau_sum), L.stream()),
+                    "gdmae_sra_attention_bwd_tc")
+        return dqkv, dtau_sum
     assert out.dtype == io_dtype
     dqkv = torch.empty((N, d3), dtype=io_dtype, device=qkv.device)
-    dtau_sum = torch.zeros((1,), dtype=torch.float64, device=qkv.device)
     work = torch.empty((N, nhead), dtype=F32, device=qkv.device)
     es = dqkv.element_size()
     # bwd algorithmic bytes: qkv + o + dO in, dqkv out

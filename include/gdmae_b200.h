@@ -27,6 +27,10 @@ const char* gdmae_last_error(void);
 int gdmae_version(void);
 int64_t gdmae_launch_count(void); /* hand-written kernels launched so far by this process */
 int gdmae_check_device(void); /* 0 iff the current device is sm_100 class; there is no fallback path */
+/* bench-only: CUDA events around the SRA launches issued inside the encoder-layer executor.
+ * drain: meta = 4 int64 per span (kind 0 fwd / 1 bwd, d, N, algorithmic bytes), ms = elapsed; returns the count */
+void gdmae_timing_enable(int on);
+int gdmae_timing_drain(int64_t* meta, float* ms, int cap);
 
 /* ---- a1/a2 dynamic voxelisation --------------------------------------------------------------
  * replaces common_utils.get_in_range_mask (pcdet/utils/common_utils.py:66-76) and the boolean
@@ -145,6 +149,11 @@ int gdmae_sra_attention_fwd(const float* qkv, const float* lut, const int32_t* r
 int gdmae_sra_attention_fwd_tc(const void* qkv_bf16, const float* lut, const int32_t* row_info, int64_t N, int d, int nhead,
                                const float* tau, float tau_min, const float* bv, int io_bf16, void* out, float* lse,
                                void* stream);
+/* tensor-core backward for bf16 tensors: qkv (N,3d), dout (N,d), dqkv (N,3d) all bf16; needs neither the forward
+ * output nor the value bias */
+int gdmae_sra_attention_bwd_tc(const void* qkv_bf16, const float* lut, const int32_t* row_info, int64_t N, int d, int nhead,
+                               const float* tau, float tau_min, const float* lse, const void* dout_bf16, void* dqkv_bf16,
+                               double* dtau_sum, void* stream);
 int gdmae_sra_attention_bwd(const float* qkv, const float* lut, const int32_t* row_info, int64_t N, int d, int nhead,
                             const float* tau, float tau_min, const float* bv, int io_bf16, const void* out,
                             const float* lse, const float* dout, void* dqkv, double* dtau_sum, float* work_D,
@@ -182,7 +191,7 @@ typedef struct gdmae_encoder_layer_args {
   int64_t N;
   int d, dff, nhead;
   int gemm_mode;        /* 0: fp32 operands, TF32 math; 1: bf16 operands; 2: fp32 operands, fp32 math */
-  int sra_tensor_cores; /* forward SRA kernel: 0 fp32 SIMT, 1 TF32 tensor cores */
+  int sra_tensor_cores; /* SRA kernels: 0 fp32 SIMT (fp32 qkv), 1 bf16 tensor cores (bf16 qkv; gemm_mode 1 only) */
   int accumulate;
   float tau_min, eps;
   /* inputs */
@@ -196,7 +205,7 @@ typedef struct gdmae_encoder_layer_args {
   const void *w_in_g, *w_o_g, *w1_g, *w2_g;
   /* activations written by forward and read by backward */
   void* xg;                  /* (N,d) op; used when xg_in == NULL and gemm_mode == 1 */
-  float* qkv;                /* (N,3d) */
+  void* qkv;                 /* (N,3d) fp32, or bf16 when sra_tensor_cores */
   float* lut;                /* (64,2d) */
   void* o;                   /* (N,d) op */
   float* lse;                /* (N,8) */

@@ -408,6 +408,19 @@ def test_sra_tensor_core_kernel_matches_simt(G, d):
         o_ref, _ = G.ops.sra_fwd(qkv, lut, tau, table, 0.01, 8, bv=bv, out_dtype=torch.bfloat16)
         o_tc, _ = G.ops.sra_fwd(qkv_b, lut, tau, table, 0.01, 8, bv=bv, out_dtype=torch.bfloat16)
         assert rel(o_tc.float(), o_ref.float()) < 1.5e-2
+        # backward: tensor-core kernel (bf16 qkv / dO / dqkv) vs the fp32 kernel on the same rounded inputs
+        do_b = torch.randn(N, d, generator=g).cuda().to(torch.bfloat16)
+        o32, lse32 = G.ops.sra_fwd(qkv, lut, tau, table, 0.01, 8, bv=bv)
+        dq_ref, dt_ref = G.ops.sra_bwd(qkv, lut, tau, table, 0.01, 8, o32, lse32, do_b.float(), bv=bv)
+        dq_tc, dt_tc = G.ops.sra_bwd(qkv_b, lut, tau, table, 0.01, 8, None, lse32, do_b)
+        assert torch.isfinite(dq_tc.float()).all()
+        for nm, c0, c1 in (("dq", 0, d), ("dk", d, 2 * d), ("dv", 2 * d, 3 * d)):
+            e = rel(dq_tc[:, c0:c1].float(), dq_ref[:, c0:c1])
+            print(f"sra tc bwd d={d} shift={shift}: {nm} rel err {e:.2e}")
+            assert e < 2e-2, (nm, e)
+        e_t = abs(float(dt_tc) - float(dt_ref)) / max(abs(float(dt_ref)), 1e-6)
+        print(f"   dtau_sum {float(dt_tc):.4f} vs {float(dt_ref):.4f}")
+        assert e_t < 3e-2, e_t
 
 
 def test_bf16_configuration_close_to_reference(G, golden):
