@@ -134,4 +134,6 @@ def set_precision(model, dtype, matmul="high", gemm_bf16=True):
     # host time per call (cublasLt path) and is not used.
     fused.GEMM_DTYPE = torch.bfloat16 if (dtype == "bf16" and gemm_bf16) else torch.float32
     model.backbone_3d.decoder_dtype = torch.bfloat16 if dtype == "bf16" else torch.float32
+    # performance configurations skip the second dense decoder map (only the pillar cells are read by the MAE head)
+    model.backbone_3d.dense_spatial_features = not fast
     return model

@@ -38,16 +38,26 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float4* __restrict_
 
 // mean, rstd from the partials (fp64 combine); count = number of rows that enter the statistics
 // (may exceed the rows present: zero rows of a sparse->dense map).  Updates the running buffers.
-__global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, double count, float eps, float momentum,
-                                   float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// one warp per channel: lanes stride over the per-block partials
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, double count, float eps,
+                                                          float momentum, float* __restrict__ mean, float* __restrict__ rstd,
+                                                          float* __restrict__ running_mean, float* __restrict__ running_var) {
+  int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
   double s = 0.0, q = 0.0;
-  for (int b = 0; b < nblocks; ++b) {
+  for (int b = lane; b < nblocks; b += 32) {
     s += (double)partial[(long long)b * 2 * C + c];
     q += (double)partial[(long long)b * 2 * C + C + c];
   }
+  s = warp_sum_f64(s);
+  q = warp_sum_f64(q);
+  if (lane != 0) return;
   double m = s / count;
   double var = q / count - m * m;
   if (var < 0.0) var = 0.0;
@@ -110,16 +120,21 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_stats_kernel(const float4* __
 
 // extra_dbeta / extra_dgamma (nullable): contributions of rows that are not materialised (the
 // constant background cells of the decoder map) to the two batch sums
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, const float* __restrict__ extra_dbeta,
-                                       const float* __restrict__ extra_dgamma, float* __restrict__ dbeta,
-                                       float* __restrict__ dgamma) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C,
+                                                              const float* __restrict__ extra_dbeta, const float* __restrict__ extra_dgamma,
+                                                              float* __restrict__ dbeta, float* __restrict__ dgamma) {
+  int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= C) return;
-  double s = extra_dbeta ? (double)extra_dbeta[c] : 0.0, q = extra_dgamma ? (double)extra_dgamma[c] : 0.0;
-  for (int b = 0; b < nblocks; ++b) {
+  double s = 0.0, q = 0.0;
+  for (int b = lane; b < nblocks; b += 32) {
     s += (double)partial[(long long)b * 2 * C + c];
     q += (double)partial[(long long)b * 2 * C + C + c];
   }
+  s = warp_sum_f64(s);
+  q = warp_sum_f64(q);
+  if (lane != 0) return;
+  if (extra_dbeta) s += (double)extra_dbeta[c];
+  if (extra_dgamma) q += (double)extra_dgamma[c];
   dbeta[c] = (float)s;
   dgamma[c] = (float)q;
 }
@@ -176,7 +191,7 @@ extern "C" int gdmae_batchnorm_relu_fwd(const float* y, const float* gamma, cons
     bn_stats_kernel<<<grid, threads, 0, st>>>((const float4*)y, N, C4, partial);
     GDMAE_LAUNCH_CHECK();
   }
-  bn_finalize_kernel<<<gdmae_div_up(C, 128), 128, 0, st>>>(partial, grid, C, count, eps, momentum, mean, rstd, running_mean, running_var);
+  bn_finalize_kernel<<<gdmae_div_up(C * 32, 256), 256, 0, st>>>(partial, grid, C, count, eps, momentum, mean, rstd, running_mean, running_var);
   GDMAE_LAUNCH_CHECK();
   if (N == 0) return GDMAE_OK;
   bn_relu_apply_kernel<<<gdmae_grid(N * C4, 256, 16), 256, 0, st>>>((const float4*)y, (const float4*)mean, (const float4*)rstd,
@@ -206,12 +221,239 @@ extern "C" int gdmae_batchnorm_relu_bwd(const float* y, const float* out, const 
                                                        (const float4*)rstd, N, C4, relu, partial);
     GDMAE_LAUNCH_CHECK();
   }
-  bn_bwd_finalize_kernel<<<gdmae_div_up(C, 128), 128, 0, st>>>(partial, grid, C, extra_dbeta, extra_dgamma, dbeta, dgamma);
+  bn_bwd_finalize_kernel<<<gdmae_div_up(C * 32, 256), 256, 0, st>>>(partial, grid, C, extra_dbeta, extra_dgamma, dbeta, dgamma);
   GDMAE_LAUNCH_CHECK();
   if (N == 0) return GDMAE_OK;
   bn_relu_bwd_apply_kernel<<<gdmae_grid(N * C4, 256, 16), 256, 0, st>>>(
       (const float4*)y, (const float4*)out, (const float4*)dout, (const float4*)mean, (const float4*)rstd, (const float4*)gamma,
       (const float4*)dbeta, (const float4*)dgamma, (float)(1.0 / count), N * C4, C4, relu, (float4*)dy);
+  GDMAE_LAUNCH_CHECK();
+  return GDMAE_OK;
+}
+
+// =====================================================================================================
+// Decoder tail: BatchNorm2d (training statistics over ALL B*Y*X cells) + ReLU of the dense decoder map,
+// evaluated only where the MAE head reads it - at the pillar cells - instead of materialising a second
+// dense map (reference: decoder_conv_out BN + ReLU, spt_backbone_mae.py:52-57, then the gather at
+// :141-143).  Forward = one read of the conv output for the statistics + a gather of M rows.
+// Backward = the two BN sums over the M pillar rows only (every other cell has zero upstream gradient)
+// + ONE dense pass that writes d(conv output) for all cells (the mean terms reach every cell).
+// y is the cuDNN conv output, NHWC, fp32 or bf16; C % 8 == 0, 256 % (C/8) == 0.
+#include <cuda_bf16.h>
+template <typename T> struct Row8;
+template <> struct Row8<float> {
+  static __device__ __forceinline__ void load(const float* p, long long i8, float (&v)[8]) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(p) + 2 * i8), b = __ldg(reinterpret_cast<const float4*>(p) + 2 * i8 + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ void store(float* p, long long i8, const float (&v)[8]) {
+    __stcs(reinterpret_cast<float4*>(p) + 2 * i8, make_float4(v[0], v[1], v[2], v[3]));
+    __stcs(reinterpret_cast<float4*>(p) + 2 * i8 + 1, make_float4(v[4], v[5], v[6], v[7]));
+  }
+};
+template <> struct Row8<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, long long i8, float (&v)[8]) {
+    uint4 u = __ldg(reinterpret_cast<const uint4*>(p) + i8);
+    const unsigned w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, long long i8, const float (&v)[8]) {
+    uint4 u;
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+    u.x = *reinterpret_cast<unsigned*>(&a); u.y = *reinterpret_cast<unsigned*>(&b);
+    u.z = *reinterpret_cast<unsigned*>(&c); u.w = *reinterpret_cast<unsigned*>(&d);
+    __stcs(reinterpret_cast<uint4*>(p) + i8, u);
+  }
+};
+
+// block-level combine of per-thread 8-channel sums s, q over the rows of the CTA -> partial[block] = [sum(C) | sumsq(C)]
+__device__ __forceinline__ void tail_block_reduce(float (&s)[8], float (&q)[8], int C8, float* __restrict__ partial) {
+  __shared__ float red[2][8][256];
+  const int c = threadIdx.x % C8, rsub = threadIdx.x / C8, rper = blockDim.x / C8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { red[0][i][threadIdx.x] = s[i]; red[1][i][threadIdx.x] = q[i]; }
+  __syncthreads();
+  if (rsub == 0) {
+    for (int j = 1; j < rper; ++j) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += red[0][i][j * C8 + c]; q[i] += red[1][i][j * C8 + c]; }
+    }
+    float* dst = partial + (long long)blockIdx.x * 16 * C8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { dst[8 * c + i] = s[i]; dst[8 * C8 + 8 * c + i] = q[i]; }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) tail_dense_stats_kernel(const T* __restrict__ y, long long n_cells, int C8, float* __restrict__ partial) {
+  const int c = threadIdx.x % C8, rsub = threadIdx.x / C8, rper = blockDim.x / C8;
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, q[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long long row = (long long)blockIdx.x * rper + rsub; row < n_cells; row += (long long)gridDim.x * rper) {
+    float v[8];
+    Row8<T>::load(y, row * C8 + c, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] += v[i]; q[i] = fmaf(v[i], v[i], q[i]); }
+  }
+  tail_block_reduce(s, q, C8, partial);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) tail_gather_apply_kernel(const T* __restrict__ y, const long long* __restrict__ vc, long long M,
+                                                                int Y, int X, int C8, const float* __restrict__ mean,
+                                                                const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, float* __restrict__ out) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < M * C8; t += (long long)gridDim.x * blockDim.x) {
+    const long long m = t / C8;
+    const int c = (int)(t - m * C8);
+    const long long cell = (vc[4 * m] * Y + vc[4 * m + 2]) * X + vc[4 * m + 3];
+    float v[8];
+    Row8<T>::load(y, cell * C8 + c, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int ch = 8 * c + i;
+      v[i] = fmaxf(fmaf((v[i] - __ldg(mean + ch)) * __ldg(rstd + ch), __ldg(gamma + ch), __ldg(beta + ch)), 0.f);
+    }
+    float4* o = reinterpret_cast<float4*>(out + m * 8 * C8 + 8 * c);
+    o[0] = make_float4(v[0], v[1], v[2], v[3]);
+    o[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
+// partial sums over the pillar rows: dbeta = sum g, dgamma = sum g * xhat, g = dout where out > 0
+template <typename T>
+__global__ void __launch_bounds__(256) tail_sparse_bwd_stats_kernel(const T* __restrict__ y, const long long* __restrict__ vc, long long M,
+                                                                    int Y, int X, int C8, const float* __restrict__ out,
+                                                                    const float* __restrict__ dout, const float* __restrict__ mean,
+                                                                    const float* __restrict__ rstd, float* __restrict__ partial) {
+  const int c = threadIdx.x % C8, rsub = threadIdx.x / C8, rper = blockDim.x / C8;
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, q[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float mu[8], rs[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { mu[i] = __ldg(mean + 8 * c + i); rs[i] = __ldg(rstd + 8 * c + i); }
+  for (long long m = (long long)blockIdx.x * rper + rsub; m < M; m += (long long)gridDim.x * rper) {
+    const long long cell = (vc[4 * m] * Y + vc[4 * m + 2]) * X + vc[4 * m + 3];
+    float v[8], o[8], g[8];
+    Row8<T>::load(y, cell * C8 + c, v);
+    Row8<float>::load(out, m * C8 + c, o);
+    Row8<float>::load(dout, m * C8 + c, g);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float gi = o[i] > 0.f ? g[i] : 0.f;
+      s[i] += gi;
+      q[i] = fmaf(gi, (v[i] - mu[i]) * rs[i], q[i]);
+    }
+  }
+  tail_block_reduce(s, q, C8, partial);
+}
+
+// dy[cell] = gamma * rstd * (g[cell] - dbeta / n - xhat[cell] * dgamma / n) for every cell; g = 0 off the pillars
+template <typename T>
+__global__ void __launch_bounds__(256) tail_dense_bwd_apply_kernel(const T* __restrict__ y, const int* __restrict__ cell2pillar,
+                                                                   long long n_cells, int C8, const float* __restrict__ out,
+                                                                   const float* __restrict__ dout, const float* __restrict__ mean,
+                                                                   const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                                   const float* __restrict__ dbeta, const float* __restrict__ dgamma,
+                                                                   float inv_n, T* __restrict__ dy) {
+  const int c = threadIdx.x % C8, rsub = threadIdx.x / C8, rper = blockDim.x / C8;
+  float mu[8], rs[8], a0[8], a1[8], a2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int ch = 8 * c + i;
+    mu[i] = __ldg(mean + ch);
+    rs[i] = __ldg(rstd + ch);
+    a0[i] = __ldg(gamma + ch) * rs[i];                 // dy = a0 * g - a1 - xhat * a2
+    a1[i] = a0[i] * __ldg(dbeta + ch) * inv_n;
+    a2[i] = a0[i] * __ldg(dgamma + ch) * inv_n;
+  }
+  for (long long cell = (long long)blockIdx.x * rper + rsub; cell < n_cells; cell += (long long)gridDim.x * rper) {
+    float v[8], r[8];
+    Row8<T>::load(y, cell * C8 + c, v);
+    const int m = __ldg(cell2pillar + cell);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = -a1[i] - (v[i] - mu[i]) * rs[i] * a2[i];
+    if (m >= 0) {
+      float o[8], g[8];
+      Row8<float>::load(out, (long long)m * C8 + c, o);
+      Row8<float>::load(dout, (long long)m * C8 + c, g);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r[i] = fmaf(a0[i], o[i] > 0.f ? g[i] : 0.f, r[i]);
+    }
+    Row8<T>::store(dy, cell * C8 + c, r);
+  }
+}
+
+static int tail_check(int B, int Y, int X, int C, int dtype, size_t ws_bytes) {
+  GDMAE_CHECK_ARG(B >= 1 && Y >= 1 && X >= 1 && C > 0 && (C % 8) == 0 && 256 % (C / 8) == 0 && (dtype == 0 || dtype == 1));
+  if (ws_bytes < gdmae_batchnorm_workspace_bytes(C)) { gdmae_set_error("decoder tail: workspace too small"); return GDMAE_ERR_WORKSPACE; }
+  return GDMAE_OK;
+}
+
+// out (M,C) fp32 = relu(BN(y))[pillar cells]; mean / rstd (C) kept for backward; running buffers updated (nullable).
+extern "C" int gdmae_decoder_tail_fwd(const void* y, int dtype, int B, int Y, int X, int C, const int64_t* voxel_coords, int64_t M,
+                                      const float* gamma, const float* beta, float eps, float momentum, float* out, float* mean,
+                                      float* rstd, float* running_mean, float* running_var, void* workspace, size_t ws_bytes,
+                                      void* stream_) {
+  int rc = tail_check(B, Y, X, C, dtype, ws_bytes);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream_;
+  float* partial = (float*)workspace;
+  const long long n_cells = (long long)B * Y * X;
+  const int C8 = C / 8, rper = 256 / C8;
+  const int grid = (int)min((long long)BN_PART_BLOCKS, (n_cells + rper - 1) / rper);
+  if (dtype == 0) tail_dense_stats_kernel<float><<<grid, 256, 0, st>>>((const float*)y, n_cells, C8, partial);
+  else tail_dense_stats_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)y, n_cells, C8, partial);
+  GDMAE_LAUNCH_CHECK();
+  bn_finalize_kernel<<<gdmae_div_up(C * 32, 256), 256, 0, st>>>(partial, grid, C, (double)n_cells, eps, momentum, mean, rstd, running_mean,
+                                                               running_var);
+  GDMAE_LAUNCH_CHECK();
+  if (M == 0) return GDMAE_OK;
+  const int g2 = gdmae_grid(M * C8, 256, 16);
+  if (dtype == 0)
+    tail_gather_apply_kernel<float><<<g2, 256, 0, st>>>((const float*)y, (const long long*)voxel_coords, M, Y, X, C8, mean, rstd, gamma,
+                                                        beta, out);
+  else
+    tail_gather_apply_kernel<__nv_bfloat16><<<g2, 256, 0, st>>>((const __nv_bfloat16*)y, (const long long*)voxel_coords, M, Y, X, C8,
+                                                                mean, rstd, gamma, beta, out);
+  GDMAE_LAUNCH_CHECK();
+  return GDMAE_OK;
+}
+
+// dy (B,Y,X,C) in y's dtype, dgamma / dbeta (C).  cell2pillar (B*Y*X): pillar row of every cell or -1 (gdmae_dynvox).
+extern "C" int gdmae_decoder_tail_bwd(const void* y, int dtype, int B, int Y, int X, int C, const int64_t* voxel_coords,
+                                      const int32_t* cell2pillar, int64_t M, const float* out, const float* dout, const float* gamma,
+                                      const float* mean, const float* rstd, void* dy, float* dgamma, float* dbeta, void* workspace,
+                                      size_t ws_bytes, void* stream_) {
+  int rc = tail_check(B, Y, X, C, dtype, ws_bytes);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream_;
+  float* partial = (float*)workspace;
+  const long long n_cells = (long long)B * Y * X;
+  const int C8 = C / 8, rper = 256 / C8;
+  int grid = (int)min((long long)BN_PART_BLOCKS, (long long)((M + rper - 1) / rper));
+  if (M == 0) {
+    GDMAE_CHECK_CUDA(cudaMemsetAsync(partial, 0, (size_t)2 * C * 4, st));
+    grid = 1;
+  } else {
+    if (dtype == 0)
+      tail_sparse_bwd_stats_kernel<float><<<grid, 256, 0, st>>>((const float*)y, (const long long*)voxel_coords, M, Y, X, C8, out, dout,
+                                                                mean, rstd, partial);
+    else
+      tail_sparse_bwd_stats_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)y, (const long long*)voxel_coords, M, Y, X,
+                                                                        C8, out, dout, mean, rstd, partial);
+    GDMAE_LAUNCH_CHECK();
+  }
+  bn_bwd_finalize_kernel<<<gdmae_div_up(C * 32, 256), 256, 0, st>>>(partial, grid, C, nullptr, nullptr, dbeta, dgamma);
+  GDMAE_LAUNCH_CHECK();
+  const int g2 = (int)min((long long)GDMAE_NUM_SMS * 16, (n_cells + rper - 1) / rper);
+  const float inv_n = (float)(1.0 / (double)n_cells);
+  if (dtype == 0)
+    tail_dense_bwd_apply_kernel<float><<<g2, 256, 0, st>>>((const float*)y, cell2pillar, n_cells, C8, out, dout, mean, rstd, gamma, dbeta,
+                                                           dgamma, inv_n, (float*)dy);
+  else
+    tail_dense_bwd_apply_kernel<__nv_bfloat16><<<g2, 256, 0, st>>>((const __nv_bfloat16*)y, cell2pillar, n_cells, C8, out, dout, mean, rstd,
+                                                                   gamma, dbeta, dgamma, inv_n, (__nv_bfloat16*)dy);
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;
 }

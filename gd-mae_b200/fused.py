@@ -161,6 +161,26 @@ def _gw(w):
     return sh if sh is not None else w.to(BF16)
 
 
+class _ShadowCast(torch.autograd.Function):
+    """weight -> its bf16 shadow (no cast kernel), gradient routed back to the fp32 master."""
+
+    @staticmethod
+    def forward(ctx, w, shadow):
+        return shadow
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.float(), None
+
+
+def cast_param(w, dtype):
+    """autograd-visible cast of a parameter for ATen consumers (the cuDNN decoder conv)."""
+    if w.dtype == dtype:
+        return w
+    sh = BF16_SHADOW.get(w.data_ptr()) if dtype == BF16 else None
+    return w.to(dtype) if sh is None else _ShadowCast.apply(w, sh)
+
+
 def gemm_mode():
     """gdmae_gemm operand mode of the current configuration: 1 bf16, 0 fp32/TF32 math, 2 fp32/fp32 math."""
     if GEMM_DTYPE == BF16:

@@ -440,6 +440,46 @@ class GatherNHWC(torch.autograd.Function):
         return dsrc, None
 
 
+class DecoderTail(torch.autograd.Function):
+    """relu(BatchNorm2d(y))[pillar cells] without the second dense map: statistics over all B*Y*X cells,
+    values only where the MAE head gathers them (spt_backbone_mae.py:52-57, 141-143).  y: conv output,
+    NHWC view (B, Y, X, C), fp32 or bf16."""
+
+    @staticmethod
+    def forward(ctx, y_nhwc, gamma, beta, running_mean, running_var, momentum, eps, training, voxel_coords, cell2pillar):
+        assert training, "DecoderTail implements the training-mode (batch statistics) path"
+        y = y_nhwc.contiguous()
+        B, Y, X, C = y.shape
+        M = voxel_coords.shape[0]
+        dev = y.device
+        out = torch.empty((M, C), dtype=F32, device=dev)
+        mean = torch.empty((C,), dtype=F32, device=dev)
+        rstd = torch.empty((C,), dtype=F32, device=dev)
+        lib = L.lib()
+        ws = L.workspace(lib.gdmae_batchnorm_workspace_bytes(C), dev)
+        L.check(lib.gdmae_decoder_tail_fwd(L.P(y), _DT[y.dtype], B, Y, X, C, L.P(voxel_coords), L.i64(M), L.P(gamma), L.P(beta),
+                                           L.f32(eps), L.f32(momentum), L.P(out), L.P(mean), L.P(rstd), L.P(running_mean),
+                                           L.P(running_var), L.P(ws), ctypes.c_size_t(ws.numel()), L.stream()), "gdmae_decoder_tail_fwd")
+        ctx.save_for_backward(y, gamma, mean, rstd, out, voxel_coords, cell2pillar)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        y, gamma, mean, rstd, out, voxel_coords, cell2pillar = ctx.saved_tensors
+        B, Y, X, C = y.shape
+        dev = y.device
+        dy = torch.empty_like(y)
+        dgamma = torch.empty((C,), dtype=F32, device=dev)
+        dbeta = torch.empty((C,), dtype=F32, device=dev)
+        lib = L.lib()
+        ws = L.workspace(lib.gdmae_batchnorm_workspace_bytes(C), dev)
+        L.check(lib.gdmae_decoder_tail_bwd(L.P(y), _DT[y.dtype], B, Y, X, C, L.P(voxel_coords), L.P(cell2pillar),
+                                           L.i64(voxel_coords.shape[0]), L.P(out), L.P(dout.contiguous().float()), L.P(gamma),
+                                           L.P(mean), L.P(rstd), L.P(dy), L.P(dgamma), L.P(dbeta), L.P(ws),
+                                           ctypes.c_size_t(ws.numel()), L.stream()), "gdmae_decoder_tail_bwd")
+        return dy, dgamma, dbeta, None, None, None, None, None, None, None
+
+
 # ----------------------------------------------------------------------------- chamfer head
 def group_points_centered(ps, pc_range, voxel_size, K):
     """gt_points - voxel_centers of target_assigner (spt_backbone_mae.py:67-72), (M, K, 3)."""

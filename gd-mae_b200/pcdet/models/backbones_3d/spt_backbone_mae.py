@@ -60,6 +60,9 @@ class SPTBackboneMAE(nn.Module):
         # dtype of the dense 384-channel BEV map and of the cuDNN decoder conv (fp32 = parity mode,
         # torch.bfloat16 = the bf16 configuration of BASELINE.json; BN statistics stay fp32 either way)
         self.decoder_dtype = torch.float32
+        # True: batch_dict['spatial_features'] holds the dense BN+ReLU map like the reference (finetune heads read it);
+        # False: the MAE step evaluates BN+ReLU only at the pillar cells its head gathers (ops.DecoderTail)
+        self.dense_spatial_features = True
 
     # ------------------------------------------------------------------ loss (spt_backbone_mae.py:83-89)
     def get_loss(self, tb_dict=None):
@@ -142,22 +145,30 @@ class SPTBackboneMAE(nn.Module):
         fused = _ops.DenseFill.apply(rows[0], rows[1], rows[2], bgs[0], bgs[1], bgs[2], [sp.rank_grid() for sp in srcs],
                                      [sp.indices for sp in srcs], self.fuse_strides, batch_size, Y, X, dt)  # (B,Y,X,384) NHWC
         conv, bn = self.decoder_conv_out[0], self.decoder_conv_out[1]
-        w = conv.weight if dt == torch.float32 else conv.weight.to(dt)
+        w = _fused.cast_param(conv.weight, dt)
         y = F.conv2d(fused.permute(0, 3, 1, 2), w.contiguous(memory_format=torch.channels_last), padding=1)  # cuDNN, NHWC
-        y = F.batch_norm(y, bn.running_mean, bn.running_var, bn.weight, bn.bias, self.training, bn.momentum, bn.eps)
+        fuse_tail = self.training and not self.dense_spatial_features and ps.cell2pillar.numel() == batch_size * Y * X
+        if fuse_tail:
+            # BN statistics over the whole map, BN + ReLU values only at the pillar cells the head gathers (ops.DecoderTail)
+            all_pyramid_voxel_features = _ops.DecoderTail.apply(y.permute(0, 2, 3, 1), bn.weight, bn.bias, bn.running_mean,
+                                                                bn.running_var, bn.momentum, bn.eps, True, all_voxel_coords,
+                                                                ps.cell2pillar)
+            spatial_features = None          # not materialised: nothing on the MAE path reads it
+        else:
+            y = F.batch_norm(y, bn.running_mean, bn.running_var, bn.weight, bn.bias, self.training, bn.momentum, bn.eps)
+            spatial_features = F.relu(y)                                                                     # (B, C, Y, X)
         if self.training:
             bn.num_batches_tracked += 1
-        spatial_features = F.relu(y)                                                                         # (B, C, Y, X)
         spatial_features_stride = multi_scale_3d_strides[self.model_cfg.FEATURES_SOURCE[0]] // self.fuse_strides[0]
 
         batch_dict['multi_scale_3d_features'] = multi_scale_3d_features
         batch_dict['multi_scale_3d_strides'] = multi_scale_3d_strides
         batch_dict['spatial_features'] = spatial_features
         batch_dict['spatial_features_stride'] = spatial_features_stride
-        assert spatial_features.shape[0] == batch_size and spatial_features.shape[2] == Y and spatial_features.shape[3] == X
-
         all_voxel_shuffle_inds = torch.arange(M, device=all_voxel_coords.device, dtype=torch.long)
-        all_pyramid_voxel_features = _ops.GatherNHWC.apply(spatial_features.permute(0, 2, 3, 1), all_voxel_coords)
+        if not fuse_tail:
+            assert spatial_features.shape[0] == batch_size and spatial_features.shape[2] == Y and spatial_features.shape[3] == X
+            all_pyramid_voxel_features = _ops.GatherNHWC.apply(spatial_features.permute(0, 2, 3, 1), all_voxel_coords)
         batch_dict.update({'voxel_features': all_pyramid_voxel_features, 'voxel_coords': all_voxel_coords,
                            'voxel_shuffle_inds': all_voxel_shuffle_inds})
         self.forward_ret_dict = self.target_assigner(batch_dict)

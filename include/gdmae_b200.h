@@ -269,6 +269,20 @@ int gdmae_gather_nhwc(const void* src, int dtype, const int64_t* voxel_coords, i
 int gdmae_scatter_nhwc(const float* dout, const int64_t* voxel_coords, int64_t M, int Y, int X, int C, void* dsrc,
                        int dtype, void* stream);
 
+/* ---- a21/a22 decoder tail -------------------------------------------------------------------------
+ * BatchNorm2d (training statistics over all B*Y*X cells) + ReLU of decoder_conv_out
+ * (pcdet/models/backbones_3d/spt_backbone_mae.py:52-57) evaluated at the pillar cells only, where the MAE head
+ * gathers it (spt_backbone_mae.py:141-143): y = conv output NHWC fp32 (dtype 0) or bf16 (1); out (M,C) fp32.
+ * Backward: dy (B,Y,X,C) in y's dtype for every cell, dgamma/dbeta (C); cell2pillar from gdmae_dynvox.
+ * workspace: gdmae_batchnorm_workspace_bytes(C). */
+int gdmae_decoder_tail_fwd(const void* y, int dtype, int B, int Y, int X, int C, const int64_t* voxel_coords, int64_t M,
+                           const float* gamma, const float* beta, float eps, float momentum, float* out, float* mean,
+                           float* rstd, float* running_mean, float* running_var, void* workspace, size_t ws_bytes, void* stream);
+int gdmae_decoder_tail_bwd(const void* y, int dtype, int B, int Y, int X, int C, const int64_t* voxel_coords,
+                           const int32_t* cell2pillar, int64_t M, const float* out, const float* dout, const float* gamma,
+                           const float* mean, const float* rstd, void* dy, float* dgamma, float* dbeta, void* workspace,
+                           size_t ws_bytes, void* stream);
+
 /* ---- a24-a26 chamfer head --------------------------------------------------------------------
  * gdmae_group_points_centered replaces sst_ops_utils.group_inner_inds + points[group_inds]
  * (pcdet/ops/sst_ops/sst_ops_utils.py:15-27) fused with get_voxel_centers

@@ -264,10 +264,14 @@ def test_chamfer_fwd_bwd(G):
 
 
 # ------------------------------------------------------------------------------ full step vs the reference's golden run
+@pytest.mark.parametrize("dense_map", [True, False])
 @pytest.mark.parametrize("name,mask_ratio,seed", [("mae_tiny_b2", 0.85, 1), ("mae_tiny_dense", 0.3, 2)])
-def test_full_mae_step_matches_reference(G, golden, name, mask_ratio, seed):
+def test_full_mae_step_matches_reference(G, golden, name, mask_ratio, seed, dense_map):
+    """dense_map=False: BN + ReLU of the decoder evaluated at the pillar cells only (ops.DecoderTail) - the
+    loss, the head inputs and every gradient must still match the reference's golden step."""
     K = golden(name)
     model, cfg, ocfg, P, Bf = build(G, "tiny", mask_ratio, seed)
+    model.backbone_3d.dense_spatial_features = dense_map
     model.train()
     B = int(K["batch_size"])
     bd = dict(points=torch.from_numpy(K["points_in"]).cuda(), batch_size=B,
@@ -285,8 +289,11 @@ def test_full_mae_step_matches_reference(G, golden, name, mask_ratio, seed):
     assert rel(bd["pillar_features"][::SUB], K["pillar_features.sub"]) < 1e-4
     assert rel(bd["voxel_features"][::SUB], K["voxel_features.sub"]) < 1e-3
     sf = bd["spatial_features"]
-    assert list(sf.shape) == list(K["spatial_features.shape"])
-    assert rel(sf[:, ::16, ::5, ::5], K["spatial_features.sub"]) < 1e-3
+    if dense_map:
+        assert list(sf.shape) == list(K["spatial_features.shape"])
+        assert rel(sf[:, ::16, ::5, ::5], K["spatial_features.sub"]) < 1e-3
+    else:
+        assert sf is None
     frd = model.backbone_3d.forward_ret_dict
     assert np.array_equal(frd["gt_points"][::SUB].cpu().numpy(), K["gt_points.sub"])
     assert rel(frd["pred_points"][::SUB], K["pred_points.sub"]) < 1e-3
@@ -429,6 +436,7 @@ def test_bf16_configuration_close_to_reference(G, golden):
     bf16 inputs alone move decoder features by ~1.6e-2 relative)."""
     K = golden("mae_tiny_dense")
     model, cfg, ocfg, P, Bf = build(G, "tiny", 0.3, 2)
+    from gd_mae_b200 import fused
     try:
         G.config.set_precision(model, "bf16", gemm_bf16=True)
         model.train()
@@ -443,5 +451,21 @@ def test_bf16_configuration_close_to_reference(G, golden):
         tot_ref = float(np.sqrt((K["grad_norms"] ** 2).sum()))
         tot = float(torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values())))
         assert abs(tot - tot_ref) / tot_ref < 5e-2
+        # the same configuration through the trainer (flat bucket, bf16 parameter mirror, in-place gradients):
+        # every parameter the reference's step gives a gradient must get one of the same size
+        from gd_mae_b200.trainer import MAETrainer
+        tr = MAETrainer(model, cfg.OPTIMIZATION, total_steps=10)
+        tr.zero_grad()
+        tr.refresh_bf16_mirror()
+        assert len(fused.BF16_SHADOW) > 0
+        bd = dict(points=torch.from_numpy(K["points_in"]).cuda(), batch_size=int(K["batch_size"]),
+                  voxel_mae_mask=torch.from_numpy(K["voxel_mae_mask"]).cuda())
+        ret, _, _ = model(bd)
+        ret["loss"].backward()
+        grads = {k: p.grad for k, p in model.named_parameters()}
+        for k, gn in zip([str(s) for s in K["grad_keys"]], K["grad_norms"]):
+            mine = float(grads[k].norm())
+            assert abs(mine - gn) <= 0.15 * gn + 1e-4 * tot_ref, (k, mine, gn)
     finally:
+        fused.BF16_SHADOW.clear()
         G.config.set_precision(model, "fp32")
