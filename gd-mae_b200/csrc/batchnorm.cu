@@ -8,8 +8,8 @@
 // ATen's path for the same work is batch_norm_collect_statistics + transform_input + a separate
 // ReLU forward, and threshold_backward + backward_reduce + backward_elemt backward.
 #include "common.cuh"
+#include "bn_common.cuh"
 
-#define BN_PART_BLOCKS (GDMAE_NUM_SMS * 4)
 
 // thread owns float4 column group (threadIdx.x % C4) and rows (threadIdx.x / C4) + k * rows_per_cta
 __global__ void __launch_bounds__(256) bn_stats_kernel(const float4* __restrict__ y, long long N, int C4, float* __restrict__ partial) {
@@ -38,38 +38,6 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float4* __restrict_
 
 // mean, rstd from the partials (fp64 combine); count = number of rows that enter the statistics
 // (may exceed the rows present: zero rows of a sparse->dense map).  Updates the running buffers.
-__device__ __forceinline__ double warp_sum_f64(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-// one warp per channel: lanes stride over the per-block partials
-__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, double count, float eps,
-                                                          float momentum, float* __restrict__ mean, float* __restrict__ rstd,
-                                                          float* __restrict__ running_mean, float* __restrict__ running_var) {
-  int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int b = lane; b < nblocks; b += 32) {
-    s += (double)partial[(long long)b * 2 * C + c];
-    q += (double)partial[(long long)b * 2 * C + C + c];
-  }
-  s = warp_sum_f64(s);
-  q = warp_sum_f64(q);
-  if (lane != 0) return;
-  double m = s / count;
-  double var = q / count - m * m;
-  if (var < 0.0) var = 0.0;
-  mean[c] = (float)m;
-  rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
-  if (running_mean) {
-    double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
-    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
-    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
-  }
-}
-
 __global__ void __launch_bounds__(256) bn_relu_apply_kernel(const float4* __restrict__ y, const float4* __restrict__ mean,
                                                             const float4* __restrict__ rstd, const float4* __restrict__ gamma,
                                                             const float4* __restrict__ beta, long long n4, int C4, int relu,
@@ -120,25 +88,6 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_stats_kernel(const float4* __
 
 // extra_dbeta / extra_dgamma (nullable): contributions of rows that are not materialised (the
 // constant background cells of the decoder map) to the two batch sums
-__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C,
-                                                              const float* __restrict__ extra_dbeta, const float* __restrict__ extra_dgamma,
-                                                              float* __restrict__ dbeta, float* __restrict__ dgamma) {
-  int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int b = lane; b < nblocks; b += 32) {
-    s += (double)partial[(long long)b * 2 * C + c];
-    q += (double)partial[(long long)b * 2 * C + C + c];
-  }
-  s = warp_sum_f64(s);
-  q = warp_sum_f64(q);
-  if (lane != 0) return;
-  if (extra_dbeta) s += (double)extra_dbeta[c];
-  if (extra_dgamma) q += (double)extra_dgamma[c];
-  dbeta[c] = (float)s;
-  dgamma[c] = (float)q;
-}
-
 // backward pass 2: dy = gamma * rstd * (g - dbeta / count - xhat * dgamma / count)
 __global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const float4* __restrict__ y, const float4* __restrict__ out,
                                                                 const float4* __restrict__ dout, const float4* __restrict__ mean,

@@ -14,6 +14,17 @@
 
 #define EW_PART_BLOCKS (GDMAE_NUM_SMS * 2)
 
+// Second stage of the column reductions, fused into the producing kernel: every CTA adds its column sums to the
+// output with fp32 atomics (RED.ADD) - about 300 adds per column, spread over the kernel's tail.  The summation order
+// is not fixed (last-bit run-to-run differences in bias / LayerNorm gradients, like the reference's atomics-based
+// scatter ops); a single-CTA fixed-order tail was measured 20-30 us slower per call.  accumulate = 0: the host
+// wrapper zeroes the output first.
+__device__ __forceinline__ void ew_cta_atomic_add(const float* __restrict__ row, int ncols, float* __restrict__ out0, int n0,
+                                                  float* __restrict__ out1) {
+  __syncthreads();
+  for (int c = threadIdx.x; c < ncols; c += blockDim.x) atomicAdd(c < n0 ? out0 + c : out1 + (c - n0), row[c]);
+}
+
 __device__ __forceinline__ void store_bf16x4(__nv_bfloat16* p, long long i4, float4 v) {
   __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
   uint2 u;
@@ -85,7 +96,8 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(const float4* __restric
                                                          const float4* __restrict__ bias, const float4* __restrict__ gamma,
                                                          const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                                                          const float4* __restrict__ dy, long long N, float4* __restrict__ dz,
-                                                         __nv_bfloat16* __restrict__ dz_bf16, float* __restrict__ partial) {
+                                                         __nv_bfloat16* __restrict__ dz_bf16, float* __restrict__ partial,
+                                                         float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
   constexpr int D = VEC * 128;
   int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
@@ -146,25 +158,7 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(const float4* __restric
       *reinterpret_cast<float4*>(partial + (long long)blockIdx.x * 2 * D + colbase) = acc;
     }
   }
-}
-
-// out[c] = sum_b partial[b * stride + c]   (fixed order)
-__global__ void partial_reduce_kernel(const float* __restrict__ partial, int nblocks, int stride, int C, float* __restrict__ out,
-                                      int accumulate) {
-  // blockDim = 128 = 32 columns x 4 row groups: coalesced over columns, 4 partial sums per column
-  // combined in a fixed order (deterministic)
-  int cg = threadIdx.x & 31, rg = threadIdx.x >> 5;
-  int c = blockIdx.x * 32 + cg;
-  float acc = 0.f;
-  if (c < C)
-    for (int b = rg; b < nblocks; b += 4) acc += partial[(long long)b * stride + c];
-  __shared__ float red[4][32];
-  red[rg][cg] = acc;
-  __syncthreads();
-  if (rg == 0 && c < C) {
-    float t = (red[0][cg] + red[1][cg]) + (red[2][cg] + red[3][cg]);
-    out[c] = accumulate ? out[c] + t : t;
-  }
+  ew_cta_atomic_add(partial + (long long)blockIdx.x * 2 * D, 2 * D, dgamma, D, dbeta);
 }
 
 extern "C" size_t gdmae_rowwise_workspace_bytes(int max_cols) { return (size_t)EW_PART_BLOCKS * 2 * max_cols * 4 + 256; }
@@ -205,18 +199,17 @@ extern "C" int gdmae_add_layernorm_bwd(const float* x, const float* res, const f
   cudaStream_t st = (cudaStream_t)stream_;
   float* partial = (float*)workspace;
   int grid = ew_grid(N);
+  if (!accumulate) {
+    GDMAE_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, (size_t)d * 4, st));
+    GDMAE_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, (size_t)d * 4, st));
+  }
   if (d == 128)
     add_ln_bwd_kernel<1><<<grid, 256, 0, st>>>((const float4*)x, (const float4*)res, (const float4*)bias, (const float4*)gamma, mean,
-                                               rstd, (const float4*)dy, N, (float4*)dz, (__nv_bfloat16*)dz_bf16, partial);
+                                               rstd, (const float4*)dy, N, (float4*)dz, (__nv_bfloat16*)dz_bf16, partial, dgamma, dbeta, accumulate);
   else
     add_ln_bwd_kernel<2><<<grid, 256, 0, st>>>((const float4*)x, (const float4*)res, (const float4*)bias, (const float4*)gamma, mean,
-                                               rstd, (const float4*)dy, N, (float4*)dz, (__nv_bfloat16*)dz_bf16, partial);
-  GDMAE_LAUNCH_CHECK();
-  // every CTA left one partial row [dgamma(d) | dbeta(d)]
-  partial_reduce_kernel<<<gdmae_div_up(d, 32), 128, 0, st>>>(partial, grid, 2 * d, d, dgamma, accumulate);
-  GDMAE_LAUNCH_CHECK();
-  partial_reduce_kernel<<<gdmae_div_up(d, 32), 128, 0, st>>>(partial + d, grid, 2 * d, d, dbeta, accumulate);
-  GDMAE_LAUNCH_CHECK();
+                                               rstd, (const float4*)dy, N, (float4*)dz, (__nv_bfloat16*)dz_bf16, partial, dgamma, dbeta, accumulate);
+  GDMAE_LAUNCH_CHECK();   // the last CTA combines the per-CTA partial rows [dgamma(d) | dbeta(d)]
   return GDMAE_OK;
 }
 
@@ -242,7 +235,7 @@ __global__ void __launch_bounds__(256) bias_gelu_fwd_kernel(const float4* __rest
 __global__ void __launch_bounds__(256) bias_gelu_bwd_kernel(const float4* __restrict__ h, const float4* __restrict__ bias,
                                                             const float4* __restrict__ dg, long long N, int C4,
                                                             float4* __restrict__ dh, __nv_bfloat16* __restrict__ dh_bf16,
-                                                            float* __restrict__ partial) {
+                                                            float* __restrict__ partial, float* __restrict__ dbias, int accumulate) {
   int c = threadIdx.x % C4, rsub = threadIdx.x / C4, rper = blockDim.x / C4;
   float4 b = __ldg(bias + c);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -264,6 +257,7 @@ __global__ void __launch_bounds__(256) bias_gelu_bwd_kernel(const float4* __rest
     }
     *reinterpret_cast<float4*>(partial + (long long)blockIdx.x * 4 * C4 + 4 * c) = acc;
   }
+  ew_cta_atomic_add(partial + (long long)blockIdx.x * 4 * C4, 4 * C4, dbias, 4 * C4, nullptr);
 }
 
 // out / out_bf16 (N,C): either may be NULL
@@ -286,10 +280,9 @@ extern "C" int gdmae_bias_gelu_bwd(const float* h, const float* bias, const floa
   long long need = (N + rper - 1) / rper;
   int grid = (int)(need < EW_PART_BLOCKS ? need : EW_PART_BLOCKS);
   float* partial = (float*)workspace;
+  if (!accumulate) GDMAE_CHECK_CUDA(cudaMemsetAsync(dbias, 0, (size_t)C * 4, st));
   bias_gelu_bwd_kernel<<<grid, 256, 0, st>>>((const float4*)h, (const float4*)bias, (const float4*)dg, N, C / 4, (float4*)dh,
-                                             (__nv_bfloat16*)dh_bf16, partial);
-  GDMAE_LAUNCH_CHECK();
-  partial_reduce_kernel<<<gdmae_div_up(C, 32), 128, 0, st>>>(partial, grid, C, C, dbias, accumulate);
+                                             (__nv_bfloat16*)dh_bf16, partial, dbias, accumulate);
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;
 }
@@ -297,7 +290,7 @@ extern "C" int gdmae_bias_gelu_bwd(const float* h, const float* bias, const floa
 // ------------------------------------------------------------------ column sums (bias gradients of the GEMMs)
 template <bool BF16>
 __global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ x_, long long N, int ld4, int col4, int C4,
-                                                     float* __restrict__ partial) {
+                                                     float* __restrict__ partial, float* __restrict__ out, int accumulate) {
   int c = threadIdx.x % C4, rsub = threadIdx.x / C4, rper = blockDim.x / C4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long row = (long long)blockIdx.x * rper + rsub; row < N; row += (long long)gridDim.x * rper) {
@@ -314,6 +307,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ x_
     }
     *reinterpret_cast<float4*>(partial + (long long)blockIdx.x * 4 * C4 + 4 * c) = acc;
   }
+  ew_cta_atomic_add(partial + (long long)blockIdx.x * 4 * C4, 4 * C4, out, 4 * C4, nullptr);
 }
 
 // out (C) = (accumulate ? out : 0) + sum over rows of x (N, ld) columns [col0, col0 + C); x fp32 (dtype 0) or bf16 (1)
@@ -331,10 +325,9 @@ extern "C" int gdmae_colsum(const void* x, int dtype, int64_t N, int ld, int col
   long long need = (N + rper - 1) / rper;
   int grid = (int)(need < EW_PART_BLOCKS ? need : EW_PART_BLOCKS);
   float* partial = (float*)workspace;
-  if (dtype == 0) colsum_kernel<false><<<grid, C4 * rper, 0, st>>>(x, N, ld / 4, col0 / 4, C4, partial);
-  else colsum_kernel<true><<<grid, C4 * rper, 0, st>>>(x, N, ld / 4, col0 / 4, C4, partial);
-  GDMAE_LAUNCH_CHECK();
-  partial_reduce_kernel<<<gdmae_div_up(C, 32), 128, 0, st>>>(partial, grid, C, C, out, accumulate);
+  if (!accumulate) GDMAE_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)C * 4, st));
+  if (dtype == 0) colsum_kernel<false><<<grid, C4 * rper, 0, st>>>(x, N, ld / 4, col0 / 4, C4, partial, out, accumulate);
+  else colsum_kernel<true><<<grid, C4 * rper, 0, st>>>(x, N, ld / 4, col0 / 4, C4, partial, out, accumulate);
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;
 }

@@ -318,6 +318,98 @@ def encoder_layer(layer, x, pos_table, table):
                                       layer.linear2.bias, layer.norm2.weight, layer.norm2.bias)
 
 
+_VFE_PTRS = ["x", "seg_offsets", "seg_points", "W1", "g1", "b1", "g2", "b2", "W2_g", "running_mean1", "running_var1", "running_mean2",
+             "running_var2", "h1", "y2", "mean1", "rstd1", "mean2", "rstd2", "out", "argmax", "dout", "dy2", "dh1", "tmp_dbeta1",
+             "tmp_dgamma1", "tmp_dbeta2", "tmp_dgamma2", "d_W1", "d_g1", "d_b1", "d_W2", "d_g2", "d_b2", "ws"]
+
+
+class VfeMlpArgs(ctypes.Structure):
+    """mirror of gdmae_vfe_mlp_args (include/gdmae_b200.h)"""
+    _fields_ = ([("Np", ctypes.c_int64), ("M", ctypes.c_int64), ("K", ctypes.c_int), ("C1", ctypes.c_int), ("C2", ctypes.c_int),
+                 ("gemm_mode", ctypes.c_int), ("accumulate", ctypes.c_int), ("eps", ctypes.c_float), ("momentum", ctypes.c_float)]
+                + [(n, _VP) for n in _VFE_PTRS] + [("ws_bytes", ctypes.c_size_t), ("stream", _VP)])
+
+
+class VfeMlpFunction(torch.autograd.Function):
+    """pillar features (M,128) = scatter_max(relu(bn2(relu(bn1(x W1^T)) W2^T))) - the whole DynVFE MLP in one node
+    (csrc/vfe_mlp.cu): point-sized intermediates are recomputed or never formed."""
+
+    @staticmethod
+    @_ops._fwd
+    def forward(ctx, x, seg_offsets, seg_points, M, eps, momentum, rm1, rv1, rm2, rv2, W1, g1, b1, W2, g2, b2):
+        x = x.contiguous()
+        Np, K = x.shape
+        dev = x.device
+        mode = gemm_mode()
+        opdt = BF16 if mode == 1 else F32
+        A = VfeMlpArgs()
+        A.Np, A.M, A.K, A.C1, A.C2, A.gemm_mode, A.accumulate, A.eps, A.momentum = Np, M, K, 64, 128, mode, 0, eps, momentum
+        W2g = _gw(W2)
+        h1 = torch.empty((Np, 64), dtype=opdt, device=dev)
+        y2 = torch.empty((Np, 128), dtype=opdt, device=dev)
+        stats = torch.empty((4 * 128 + 4 * 128,), dtype=F32, device=dev)      # mean1 rstd1 mean2 rstd2 | 4 scratch rows
+        out = torch.empty((M, 128), dtype=F32, device=dev)
+        arg = torch.empty((M, 128), dtype=torch.int32, device=dev)
+        for name, t in (("x", x), ("seg_offsets", seg_offsets), ("seg_points", seg_points), ("W1", W1), ("g1", g1), ("b1", b1),
+                        ("g2", g2), ("b2", b2), ("W2_g", W2g), ("running_mean1", rm1), ("running_var1", rv1), ("running_mean2", rm2),
+                        ("running_var2", rv2), ("h1", h1), ("y2", y2), ("out", out), ("argmax", arg)):
+            setattr(A, name, t.data_ptr())
+        sb = stats.data_ptr()
+        for i, name in enumerate(("mean1", "rstd1", "mean2", "rstd2", "tmp_dbeta1", "tmp_dgamma1", "tmp_dbeta2", "tmp_dgamma2")):
+            setattr(A, name, sb + 4 * 128 * i)
+        lib = L.lib()
+        ws = L.workspace(lib.gdmae_vfe_mlp_workspace_bytes(K), dev)
+        A.ws, A.ws_bytes, A.stream = ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream
+        L.check(lib.gdmae_vfe_mlp_fwd(ctypes.byref(A)), "gdmae_vfe_mlp_fwd")
+        ctx.save_for_backward(x, seg_offsets, seg_points, W1, g1, b1, W2, g2, b2)
+        ctx.args, ctx.keep = A, (W2g, h1, y2, stats, out, arg)
+        ctx.params = (W1, g1, b1, W2, g2, b2)
+        return out
+
+    @staticmethod
+    @_ops._bwd
+    def backward(ctx, dout):
+        A, params = ctx.args, ctx.params
+        x = ctx.saved_tensors[0]
+        dev = x.device
+        dout = dout.contiguous().float()
+        opdt = BF16 if A.gemm_mode == 1 else F32
+        dy2 = torch.empty((A.Np, 128), dtype=opdt, device=dev)
+        dh1 = torch.empty((A.Np, 64), dtype=opdt, device=dev)
+        inplace = all(p.grad is not None and p.grad.dtype == F32 and p.grad.is_contiguous() for p in params)
+        grads = [p.grad for p in params] if inplace else [torch.empty_like(p) for p in params]
+        A.accumulate = int(inplace)
+        A.dout, A.dy2, A.dh1 = dout.data_ptr(), dy2.data_ptr(), dh1.data_ptr()
+        for name, g in zip(("d_W1", "d_g1", "d_b1", "d_W2", "d_g2", "d_b2"), grads):
+            setattr(A, name, g.data_ptr())
+        lib = L.lib()
+        ws = L.workspace(lib.gdmae_vfe_mlp_workspace_bytes(A.K), dev)
+        A.ws, A.ws_bytes, A.stream = ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream
+        L.check(lib.gdmae_vfe_mlp_bwd(ctypes.byref(A)), "gdmae_vfe_mlp_bwd")
+        ctx.keep = None
+        if inplace:
+            return (None,) * 16
+        return (None,) * 10 + tuple(grads)
+
+
+def vfe_mlp_supported(mlp, x):
+    """the fused node covers the shipped configs: Linear(K<=16, 64) -> BN -> ReLU -> Linear(64, 128) -> BN -> ReLU, no biases"""
+    import torch.nn as nn
+    return (len(mlp) == 6 and isinstance(mlp[0], nn.Linear) and isinstance(mlp[3], nn.Linear) and mlp[0].bias is None
+            and mlp[3].bias is None and mlp[0].out_features == 64 and mlp[3].in_features == 64 and mlp[3].out_features == 128
+            and x.shape[1] <= 16 and mlp[1].eps == mlp[4].eps and mlp[1].momentum == mlp[4].momentum and x.shape[0] > 0)
+
+
+def vfe_mlp(mlp, x, ps):
+    bn1, bn2 = mlp[1], mlp[4]
+    out = VfeMlpFunction.apply(x, ps.seg_offsets, ps.seg_points, ps.n_pillars, bn1.eps, bn1.momentum, bn1.running_mean,
+                               bn1.running_var, bn2.running_mean, bn2.running_var, mlp[0].weight, bn1.weight, bn1.bias,
+                               mlp[3].weight, bn2.weight, bn2.bias)
+    bn1.num_batches_tracked += 1
+    bn2.num_batches_tracked += 1
+    return out
+
+
 class SparseConvFunction(torch.autograd.Function):
     """3x3 sparse conv as gather -> ONE GEMM (spconv SubMConv2d / SparseConv2d, spconv_utils.py:37-56),
     manual backward: dW = dy^T col, dcol = dy W, dx = transposed gather (no atomics).  In the bf16

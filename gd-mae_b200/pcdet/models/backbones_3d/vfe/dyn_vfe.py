@@ -38,6 +38,7 @@ class DynVFE(VFETemplate):
         self.voxel_size = [float(v) for v in voxel_size]
         self.point_cloud_range = [float(v) for v in point_cloud_range]
         self.grid_size = [int(g) for g in grid_size]
+        self.fused_mlp = True   # one autograd node for the MLP + scatter_max (fused.VfeMlpFunction); False = op by op
 
     def get_output_feature_dim(self):
         return self.num_point_features
@@ -48,11 +49,14 @@ class DynVFE(VFETemplate):
         n_feat = points.shape[1] - 1
         mean = _ops.segment_mean(ps.points, 1, n_feat, ps.seg_offsets, ps.seg_points, ps.n_pillars)
         x = _ops.vfe_point_features(ps, mean, self.point_cloud_range, self.voxel_size)
-        with torch.autocast("cuda", enabled=False):  # absolute coordinates (|x| up to 75 m) stay fp32
-            mlp = self.dvfe_mlps[0]                   # Linear (cuBLAS) -> fused BN1d(batch statistics)+ReLU, twice
-            for k in range(0, len(mlp), 3):
-                x = _fused.batchnorm_relu(mlp[k + 1], mlp[k](x), self.training and mlp[k + 1].training)[0]
-        x = _ops.SegmentMax.apply(x, ps.seg_offsets, ps.seg_points, ps.n_pillars)
+        mlp = self.dvfe_mlps[0]
+        if self.fused_mlp and self.training and _fused.vfe_mlp_supported(mlp, x) and ps.n_pillars > 0:
+            x = _fused.vfe_mlp(mlp, x, ps)            # Linear-BN-ReLU x2 + scatter_max as one node (csrc/vfe_mlp.cu)
+        else:
+            with torch.autocast("cuda", enabled=False):  # absolute coordinates (|x| up to 75 m) stay fp32
+                for k in range(0, len(mlp), 3):          # Linear (cuBLAS) -> fused BN1d(batch statistics)+ReLU, twice
+                    x = _fused.batchnorm_relu(mlp[k + 1], mlp[k](x), self.training and mlp[k + 1].training)[0]
+            x = _ops.SegmentMax.apply(x, ps.seg_offsets, ps.seg_points, ps.n_pillars)
 
         batch_dict['points'] = ps.points
         batch_dict['point_coords'] = ps.point_coords

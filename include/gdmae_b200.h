@@ -179,6 +179,43 @@ int gdmae_colsum(const void* x, int dtype /* 0 fp32, 1 bf16 */, int64_t N, int l
 int gdmae_gather_add_rows(const float* x, const float* table, const uint8_t* idx, int64_t N, int C, float* out,
                           void* out_bf16, void* stream);
 
+/* ---- a5/a6 pillar feature encoder MLP ----------------------------------------------------------------
+ * One call = DynVFE's dvfe_mlps (Linear(K,64,no bias) -> BatchNorm1d(train) -> ReLU -> Linear(64,128,no bias) ->
+ * BatchNorm1d(train) -> ReLU) followed by torch_scatter.scatter_max over the pillars
+ * (pcdet/models/backbones_3d/vfe/dyn_vfe.py:105-111, network_utils.py:7-21), forward or backward.
+ * x (Np,K) fp32 point features; seg_offsets/seg_points = pillar CSR from gdmae_dynvox; "op" buffers are fp32
+ * (gemm_mode 0/2) or bf16 (gemm_mode 1).  Backward writes (accumulate=0) or adds to (accumulate=1) d_*. */
+typedef struct gdmae_vfe_mlp_args {
+  int64_t Np, M;
+  int K, C1, C2;          /* C1 == 64, C2 == 128, K <= 16 */
+  int gemm_mode;          /* as gdmae_gemm's ab_dtype */
+  int accumulate;
+  float eps, momentum;
+  const float* x;
+  const int32_t *seg_offsets, *seg_points;
+  const float *W1, *g1, *b1, *g2, *b2;      /* W1 (64,K); BatchNorm weights / biases */
+  const void* W2_g;                          /* (128,64) op */
+  float *running_mean1, *running_var1, *running_mean2, *running_var2;   /* nullable */
+  /* written by forward, read by backward */
+  void* h1;               /* (Np,64) op */
+  void* y2;               /* (Np,128) op */
+  float *mean1, *rstd1, *mean2, *rstd2;
+  float* out;             /* (M,128) pillar features */
+  int32_t* argmax;        /* (M,128) point row of each maximum */
+  /* backward */
+  const float* dout;      /* (M,128) */
+  void* dy2;              /* (Np,128) op scratch */
+  void* dh1;              /* (Np,64) op scratch */
+  float *tmp_dbeta1, *tmp_dgamma1, *tmp_dbeta2, *tmp_dgamma2;   /* (64),(64),(128),(128) scratch */
+  float *d_W1, *d_g1, *d_b1, *d_W2, *d_g2, *d_b2;
+  void* ws;               /* gdmae_vfe_mlp_workspace_bytes(K) */
+  size_t ws_bytes;
+  void* stream;
+} gdmae_vfe_mlp_args;
+size_t gdmae_vfe_mlp_workspace_bytes(int K);
+int gdmae_vfe_mlp_fwd(const gdmae_vfe_mlp_args* args);
+int gdmae_vfe_mlp_bwd(const gdmae_vfe_mlp_args* args);
+
 /* ---- a13-a19 encoder-layer executor -------------------------------------------------------------
  * One call = the whole forward (or the whole backward) of an SST EncoderLayer
  * (pcdet/models/model_utils/sst_basic_block.py:60-92 with WindowAttention :22-54 and the
