@@ -175,13 +175,22 @@ __global__ void __launch_bounds__(V_THREADS) vfe1_bwd_stats_kernel(const float* 
     l1_load_tile(xs, x, tile * V_TILE, Np, K);
     __syncthreads();
     const int nrow = (int)min((long long)V_TILE, Np - tile * V_TILE);
-    for (int r = wid; r < nrow; r += 8) {
-      float y0, y1;
-      l1_y(c, xs + r * K, K, y0, y1);
-      const float2 g = VT<T>::load2(dh1, (tile * V_TILE + r) * (V_C1 / 2) + lane);
-      const float g0 = fmaf(y0 - m0, a0, b0) > 0.f ? g.x : 0.f, g1 = fmaf(y1 - m1, a1, b1) > 0.f ? g.y : 0.f;
-      s0 += g0; s1 += g1;
-      q0 = fmaf(g0, (y0 - m0) * r0, q0); q1 = fmaf(g1, (y1 - m1) * r1, q1);
+    float2 gv[V_TILE / 8];
+#pragma unroll
+    for (int i = 0; i < V_TILE / 8; ++i) {
+      const int r = wid + 8 * i;
+      gv[i] = r < nrow ? VT<T>::load2(dh1, (tile * V_TILE + r) * (V_C1 / 2) + lane) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < V_TILE / 8; ++i) {
+      const int r = wid + 8 * i;
+      if (r < nrow) {
+        float y0, y1;
+        l1_y(c, xs + r * K, K, y0, y1);
+        const float g0 = fmaf(y0 - m0, a0, b0) > 0.f ? gv[i].x : 0.f, g1 = fmaf(y1 - m1, a1, b1) > 0.f ? gv[i].y : 0.f;
+        s0 += g0; s1 += g1;
+        q0 = fmaf(g0, (y0 - m0) * r0, q0); q1 = fmaf(g1, (y1 - m1) * r1, q1);
+      }
     }
   }
   l1_block_partial(s0, s1, q0, q1, partial);
@@ -214,18 +223,27 @@ __global__ void __launch_bounds__(V_THREADS) vfe1_bwd_wgrad_kernel(const float* 
     l1_load_tile(xs, x, tile * V_TILE, Np, K);
     __syncthreads();
     const int nrow = (int)min((long long)V_TILE, Np - tile * V_TILE);
-    for (int r = wid; r < nrow; r += 8) {
-      const float* xr = xs + r * K;
-      float y0, y1;
-      l1_y(c, xr, K, y0, y1);
-      const float2 g = VT<T>::load2(dh1, (tile * V_TILE + r) * (V_C1 / 2) + lane);
-      const float g0 = fmaf(y0 - m0, a0, b0) > 0.f ? g.x : 0.f, g1 = fmaf(y1 - m1, a1, b1) > 0.f ? g.y : 0.f;
-      const float d0 = a0 * g0 - c10 - (y0 - m0) * r0 * c20, d1 = a1 * g1 - c11 - (y1 - m1) * r1 * c21;
+    float2 gv[V_TILE / 8];
 #pragma unroll
-      for (int k = 0; k < V_KMAX; ++k) {
-        if (k < K) {
-          acc0[k] = fmaf(d0, xr[k], acc0[k]);
-          acc1[k] = fmaf(d1, xr[k], acc1[k]);
+    for (int i = 0; i < V_TILE / 8; ++i) {       // the warp's 8 rows of the tile: all loads in flight before the math
+      const int r = wid + 8 * i;
+      gv[i] = r < nrow ? VT<T>::load2(dh1, (tile * V_TILE + r) * (V_C1 / 2) + lane) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < V_TILE / 8; ++i) {
+      const int r = wid + 8 * i;
+      if (r < nrow) {
+        const float* xr = xs + r * K;
+        float y0, y1;
+        l1_y(c, xr, K, y0, y1);
+        const float g0 = fmaf(y0 - m0, a0, b0) > 0.f ? gv[i].x : 0.f, g1 = fmaf(y1 - m1, a1, b1) > 0.f ? gv[i].y : 0.f;
+        const float d0 = a0 * g0 - c10 - (y0 - m0) * r0 * c20, d1 = a1 * g1 - c11 - (y1 - m1) * r1 * c21;
+#pragma unroll
+        for (int k = 0; k < V_KMAX; ++k) {
+          if (k < K) {
+            acc0[k] = fmaf(d0, xr[k], acc0[k]);
+            acc1[k] = fmaf(d1, xr[k], acc1[k]);
+          }
         }
       }
     }
@@ -477,7 +495,7 @@ extern "C" int gdmae_vfe_mlp_bwd(const gdmae_vfe_mlp_args* a) {
   bn_bwd_finalize_kernel<<<gdmae_div_up(V_C1 * 32, 256), 256, 0, st>>>(partial, g1, V_C1, nullptr, nullptr, a->tmp_dbeta1, a->tmp_dgamma1);
   GDMAE_LAUNCH_CHECK();
   if (!acc) GDMAE_CHECK_CUDA(cudaMemsetAsync(a->d_W1, 0, (size_t)V_C1 * K * 4, st));
-  const int gw = (int)min((long long)GDMAE_NUM_SMS * 2, ntile);
+  const int gw = (int)min((long long)GDMAE_NUM_SMS * 4, ntile);
   if (bf)
     vfe1_bwd_wgrad_kernel<vbf16><<<gw, V_THREADS, 0, st>>>(a->x, Np, K, a->W1, a->mean1, a->rstd1, a->g1, a->b1, (const vbf16*)a->dh1,
                                                            a->tmp_dbeta1, a->tmp_dgamma1, inv_n, a->d_W1);
