@@ -20,9 +20,10 @@
 // scatter ops); a single-CTA fixed-order tail was measured 20-30 us slower per call.  accumulate = 0: the host
 // wrapper zeroes the output first.
 __device__ __forceinline__ void ew_cta_atomic_add(const float* __restrict__ row, int ncols, float* __restrict__ out0, int n0,
-                                                  float* __restrict__ out1) {
+                                                  float* __restrict__ out1, float* __restrict__ out2 = nullptr) {
   __syncthreads();
-  for (int c = threadIdx.x; c < ncols; c += blockDim.x) atomicAdd(c < n0 ? out0 + c : out1 + (c - n0), row[c]);
+  for (int c = threadIdx.x; c < ncols; c += blockDim.x)
+    atomicAdd(c < n0 ? out0 + c : (c < 2 * n0 ? out1 + (c - n0) : out2 + (c - 2 * n0)), row[c]);
 }
 
 __device__ __forceinline__ void store_bf16x4(__nv_bfloat16* p, long long i4, float4 v) {
@@ -41,8 +42,8 @@ __device__ __forceinline__ float4 load_bf16x4(const __nv_bfloat16* p, long long 
 
 // ------------------------------------------------------------------ y = LayerNorm(x + res + bias)
 // VEC = d / 128 float4 per lane (d = 128 -> 1, d = 256 -> 2); bias, y_bf16 nullable
-template <int VEC>
-__global__ void __launch_bounds__(256) add_ln_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ res,
+template <int VEC, bool RESBF>
+__global__ void __launch_bounds__(256) add_ln_fwd_kernel(const float4* __restrict__ x, const void* __restrict__ res,
                                                          const float4* __restrict__ bias, const float4* __restrict__ gamma,
                                                          const float4* __restrict__ beta, long long N, float eps,
                                                          float4* __restrict__ y, __nv_bfloat16* __restrict__ y_bf16,
@@ -64,7 +65,8 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const float4* __restric
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
       float4 a = __ldg(x + row * (D / 4) + v * 32 + lane);
-      float4 r = __ldg(res + row * (D / 4) + v * 32 + lane);
+      float4 r = RESBF ? load_bf16x4((const __nv_bfloat16*)res, row * (D / 4) + v * 32 + lane)
+                       : __ldg((const float4*)res + row * (D / 4) + v * 32 + lane);
       z[v] = make_float4(a.x + r.x + bi[v].x, a.y + r.y + bi[v].y, a.z + r.z + bi[v].z, a.w + r.w + bi[v].w);
       s += z[v].x + z[v].y + z[v].z + z[v].w;
     }
@@ -91,24 +93,27 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const float4* __restric
 }
 
 // dz = rstd * (dy*gamma - mean(dy*gamma) - xhat * mean(dy*gamma*xhat));  partial dgamma/dbeta per CTA
-template <int VEC>
-__global__ void __launch_bounds__(256) add_ln_bwd_kernel(const float4* __restrict__ x, const float4* __restrict__ res,
+template <int VEC, bool RESBF, bool DBIAS>
+__global__ void __launch_bounds__(256) add_ln_bwd_kernel(const float4* __restrict__ x, const void* __restrict__ res,
                                                          const float4* __restrict__ bias, const float4* __restrict__ gamma,
                                                          const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                                                          const float4* __restrict__ dy, long long N, float4* __restrict__ dz,
                                                          __nv_bfloat16* __restrict__ dz_bf16, float* __restrict__ partial,
-                                                         float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
+                                                         float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                         float* __restrict__ dbias, int accumulate) {
   constexpr int D = VEC * 128;
+  constexpr int NACC = DBIAS ? 3 : 2;
   int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  float4 g[VEC], dg[VEC], db[VEC], bi[VEC];
+  float4 g[VEC], dg[VEC], db[VEC], bi[VEC], ds[VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) {
     g[v] = __ldg(gamma + v * 32 + lane);
     bi[v] = bias ? __ldg(bias + v * 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
     dg[v] = make_float4(0.f, 0.f, 0.f, 0.f);
     db[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ds[v] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (long long row = warp; row < N; row += nwarps) {
     float mean = mean_in[row], rstd = rstd_in[row];
@@ -117,7 +122,8 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(const float4* __restric
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
       float4 a = __ldg(x + row * (D / 4) + v * 32 + lane);
-      float4 r = __ldg(res + row * (D / 4) + v * 32 + lane);
+      float4 r = RESBF ? load_bf16x4((const __nv_bfloat16*)res, row * (D / 4) + v * 32 + lane)
+                       : __ldg((const float4*)res + row * (D / 4) + v * 32 + lane);
       float4 d = __ldg(dy + row * (D / 4) + v * 32 + lane);
       xh[v] = make_float4((a.x + r.x + bi[v].x - mean) * rstd, (a.y + r.y + bi[v].y - mean) * rstd,
                           (a.z + r.z + bi[v].z - mean) * rstd, (a.w + r.w + bi[v].w - mean) * rstd);
@@ -138,27 +144,32 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(const float4* __restric
       o.w = rstd * (dxh[v].w - c1 - xh[v].w * c2);
       dz[row * (D / 4) + v * 32 + lane] = o;
       if (dz_bf16) store_bf16x4(dz_bf16, row * (D / 4) + v * 32 + lane, o);
+      if (DBIAS) { ds[v].x += o.x; ds[v].y += o.y; ds[v].z += o.z; ds[v].w += o.w; }
     }
   }
-  // CTA reduction over its 8 warps (fixed order), then one partial row [dgamma(D) | dbeta(D)] per CTA
-  __shared__ float4 red[8][2 * VEC][32];
+  // CTA reduction over its 8 warps (fixed order), then one partial row [dgamma(D) | dbeta(D) | dbias(D)] per CTA
+  __shared__ float4 red[8][NACC * VEC][32];
 #pragma unroll
-  for (int v = 0; v < VEC; ++v) { red[wid][v][lane] = dg[v]; red[wid][VEC + v][lane] = db[v]; }
+  for (int v = 0; v < VEC; ++v) {
+    red[wid][v][lane] = dg[v];
+    red[wid][VEC + v][lane] = db[v];
+    if (DBIAS) red[wid][2 * VEC + v][lane] = ds[v];
+  }
   __syncthreads();
   if (wid == 0) {
 #pragma unroll
-    for (int v = 0; v < 2 * VEC; ++v) {
+    for (int v = 0; v < NACC * VEC; ++v) {
       float4 acc = red[0][v][lane];
       for (int w = 1; w < 8; ++w) {
         float4 t = red[w][v][lane];
         acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
       }
-      // v < VEC: dgamma columns [128 v + 4 lane ..]; v >= VEC: dbeta
-      int colbase = (v < VEC ? 0 : D) + (v % VEC) * 128 + 4 * lane;
-      *reinterpret_cast<float4*>(partial + (long long)blockIdx.x * 2 * D + colbase) = acc;
+      // v < VEC: dgamma columns [128 v + 4 lane ..]; then dbeta; then dbias
+      int colbase = (v / VEC) * D + (v % VEC) * 128 + 4 * lane;
+      *reinterpret_cast<float4*>(partial + (long long)blockIdx.x * NACC * D + colbase) = acc;
     }
   }
-  ew_cta_atomic_add(partial + (long long)blockIdx.x * 2 * D, 2 * D, dgamma, D, dbeta);
+  ew_cta_atomic_add(partial + (long long)blockIdx.x * NACC * D, NACC * D, dgamma, D, dbeta, dbias);
 }
 
 extern "C" size_t gdmae_rowwise_workspace_bytes(int max_cols) { return (size_t)EW_PART_BLOCKS * 2 * max_cols * 4 + 256; }
@@ -169,48 +180,70 @@ static int ew_grid(long long rows) {
 }
 
 // y = LayerNorm(x + res + bias) * gamma + beta over rows of d in {128, 256}; bias (d) and y_bf16 (N,d) may be
-// NULL; mean/rstd (N) saved for backward.
-extern "C" int gdmae_add_layernorm_fwd(const float* x, const float* res, const float* bias, const float* gamma, const float* beta,
-                                       int64_t N, int d, float eps, float* y, void* y_bf16, float* mean, float* rstd,
-                                       void* stream_) {
+// NULL; mean/rstd (N) saved for backward.  Internal form: res may be a bf16 tensor (a GEMM output of the bf16
+// configuration).
+int ew_add_layernorm_fwd(const float* x, const void* res, int res_bf16, const float* bias, const float* gamma, const float* beta,
+                         int64_t N, int d, float eps, float* y, void* y_bf16, float* mean, float* rstd, void* stream_) {
   GDMAE_CHECK_ARG(N >= 0 && (d == 128 || d == 256));
   if (N == 0) return GDMAE_OK;
   cudaStream_t st = (cudaStream_t)stream_;
   int grid = gdmae_grid(N * 32, 256, 8);
-  if (d == 128)
-    add_ln_fwd_kernel<1><<<grid, 256, 0, st>>>((const float4*)x, (const float4*)res, (const float4*)bias, (const float4*)gamma,
-                                               (const float4*)beta, N, eps, (float4*)y, (__nv_bfloat16*)y_bf16, mean, rstd);
-  else
-    add_ln_fwd_kernel<2><<<grid, 256, 0, st>>>((const float4*)x, (const float4*)res, (const float4*)bias, (const float4*)gamma,
-                                               (const float4*)beta, N, eps, (float4*)y, (__nv_bfloat16*)y_bf16, mean, rstd);
+#define EW_LN_FWD(V, RB)                                                                                                        \
+  add_ln_fwd_kernel<V, RB><<<grid, 256, 0, st>>>((const float4*)x, res, (const float4*)bias, (const float4*)gamma,              \
+                                                 (const float4*)beta, N, eps, (float4*)y, (__nv_bfloat16*)y_bf16, mean, rstd)
+  if (d == 128) { if (res_bf16) EW_LN_FWD(1, true); else EW_LN_FWD(1, false); }
+  else { if (res_bf16) EW_LN_FWD(2, true); else EW_LN_FWD(2, false); }
+#undef EW_LN_FWD
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;
 }
 
+extern "C" int gdmae_add_layernorm_fwd(const float* x, const float* res, const float* bias, const float* gamma, const float* beta,
+                                       int64_t N, int d, float eps, float* y, void* y_bf16, float* mean, float* rstd,
+                                       void* stream_) {
+  return ew_add_layernorm_fwd(x, res, 0, bias, gamma, beta, N, d, eps, y, y_bf16, mean, rstd, stream_);
+}
+
 // dz (N,d) = gradient w.r.t. (x + res + bias) (also emitted as bf16 when dz_bf16 != NULL); dgamma/dbeta (d)
-// written (accumulate=0) or added to (accumulate=1).
+// written (accumulate=0) or added to (accumulate=1).  Internal form: res may be bf16; dbias (d, nullable) receives
+// the column sums of dz - the gradient of the bias inside the LayerNorm argument - from the same pass.
+int ew_add_layernorm_bwd(const float* x, const void* res, int res_bf16, const float* bias, const float* gamma, const float* mean,
+                         const float* rstd, const float* dy, int64_t N, int d, float* dz, void* dz_bf16, float* dgamma,
+                         float* dbeta, float* dbias, int accumulate, void* workspace, size_t ws_bytes, void* stream_) {
+  GDMAE_CHECK_ARG(N >= 0 && (d == 128 || d == 256));
+  if (ws_bytes < gdmae_rowwise_workspace_bytes(dbias ? 2 * d : d)) { gdmae_set_error("add_layernorm_bwd: workspace too small"); return GDMAE_ERR_WORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (!accumulate) {
+    GDMAE_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, (size_t)d * 4, st));
+    GDMAE_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, (size_t)d * 4, st));
+    if (dbias) GDMAE_CHECK_CUDA(cudaMemsetAsync(dbias, 0, (size_t)d * 4, st));
+  }
+  if (N == 0) return GDMAE_OK;
+  float* partial = (float*)workspace;
+  int grid = ew_grid(N);
+#define EW_LN_BWD(V, RB, DB)                                                                                                     \
+  add_ln_bwd_kernel<V, RB, DB><<<grid, 256, 0, st>>>((const float4*)x, res, (const float4*)bias, (const float4*)gamma, mean, rstd, \
+                                                     (const float4*)dy, N, (float4*)dz, (__nv_bfloat16*)dz_bf16, partial, dgamma, \
+                                                     dbeta, dbias, accumulate)
+#define EW_LN_BWD_V(V)                                          \
+  do {                                                          \
+    if (res_bf16) { if (dbias) EW_LN_BWD(V, true, true); else EW_LN_BWD(V, true, false); }   \
+    else { if (dbias) EW_LN_BWD(V, false, true); else EW_LN_BWD(V, false, false); }          \
+  } while (0)
+  if (d == 128) EW_LN_BWD_V(1);
+  else EW_LN_BWD_V(2);
+#undef EW_LN_BWD_V
+#undef EW_LN_BWD
+  GDMAE_LAUNCH_CHECK();
+  return GDMAE_OK;
+}
+
 extern "C" int gdmae_add_layernorm_bwd(const float* x, const float* res, const float* bias, const float* gamma, const float* mean,
                                        const float* rstd, const float* dy, int64_t N, int d, float* dz, void* dz_bf16,
                                        float* dgamma, float* dbeta, int accumulate, void* workspace, size_t ws_bytes,
                                        void* stream_) {
-  GDMAE_CHECK_ARG(N >= 0 && (d == 128 || d == 256));
-  if (ws_bytes < gdmae_rowwise_workspace_bytes(d)) { gdmae_set_error("add_layernorm_bwd: workspace too small"); return GDMAE_ERR_WORKSPACE; }
-  if (N == 0) return GDMAE_OK;
-  cudaStream_t st = (cudaStream_t)stream_;
-  float* partial = (float*)workspace;
-  int grid = ew_grid(N);
-  if (!accumulate) {
-    GDMAE_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, (size_t)d * 4, st));
-    GDMAE_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, (size_t)d * 4, st));
-  }
-  if (d == 128)
-    add_ln_bwd_kernel<1><<<grid, 256, 0, st>>>((const float4*)x, (const float4*)res, (const float4*)bias, (const float4*)gamma, mean,
-                                               rstd, (const float4*)dy, N, (float4*)dz, (__nv_bfloat16*)dz_bf16, partial, dgamma, dbeta, accumulate);
-  else
-    add_ln_bwd_kernel<2><<<grid, 256, 0, st>>>((const float4*)x, (const float4*)res, (const float4*)bias, (const float4*)gamma, mean,
-                                               rstd, (const float4*)dy, N, (float4*)dz, (__nv_bfloat16*)dz_bf16, partial, dgamma, dbeta, accumulate);
-  GDMAE_LAUNCH_CHECK();   // the last CTA combines the per-CTA partial rows [dgamma(d) | dbeta(d)]
-  return GDMAE_OK;
+  return ew_add_layernorm_bwd(x, res, 0, bias, gamma, mean, rstd, dy, N, d, dz, dz_bf16, dgamma, dbeta, nullptr, accumulate, workspace,
+                              ws_bytes, stream_);
 }
 
 // ------------------------------------------------------------------ g = gelu_erf(h + b)
@@ -219,11 +252,12 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   return 0.5f * (1.f + erff(x * 0.70710678118654752440f)) + x * 0.39894228040143267794f * __expf(-0.5f * x * x);
 }
 
-__global__ void __launch_bounds__(256) bias_gelu_fwd_kernel(const float4* __restrict__ h, const float4* __restrict__ bias,
+template <bool HBF>
+__global__ void __launch_bounds__(256) bias_gelu_fwd_kernel(const void* __restrict__ h, const float4* __restrict__ bias,
                                                             long long n4, int C4, float4* __restrict__ out,
                                                             __nv_bfloat16* __restrict__ out_bf16) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    float4 a = __ldg(h + i), b = __ldg(bias + (int)(i % C4));
+    float4 a = HBF ? load_bf16x4((const __nv_bfloat16*)h, i) : __ldg((const float4*)h + i), b = __ldg(bias + (int)(i % C4));
     float4 o = make_float4(gelu_f(a.x + b.x), gelu_f(a.y + b.y), gelu_f(a.z + b.z), gelu_f(a.w + b.w));
     if (out) out[i] = o;
     if (out_bf16) store_bf16x4(out_bf16, i, o);
@@ -232,15 +266,17 @@ __global__ void __launch_bounds__(256) bias_gelu_fwd_kernel(const float4* __rest
 
 // dh = dg * gelu'(h + b); partial column sums of dh (bias gradient).  Thread t owns float4 column (t % C4) of
 // rows (t / C4), stepping whole CTAs.
-__global__ void __launch_bounds__(256) bias_gelu_bwd_kernel(const float4* __restrict__ h, const float4* __restrict__ bias,
-                                                            const float4* __restrict__ dg, long long N, int C4,
+template <bool HBF>
+__global__ void __launch_bounds__(256) bias_gelu_bwd_kernel(const void* __restrict__ h, const float4* __restrict__ bias,
+                                                            const void* __restrict__ dg, long long N, int C4,
                                                             float4* __restrict__ dh, __nv_bfloat16* __restrict__ dh_bf16,
                                                             float* __restrict__ partial, float* __restrict__ dbias, int accumulate) {
   int c = threadIdx.x % C4, rsub = threadIdx.x / C4, rper = blockDim.x / C4;
   float4 b = __ldg(bias + c);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long row = (long long)blockIdx.x * rper + rsub; row < N; row += (long long)gridDim.x * rper) {
-    float4 a = __ldg(h + row * C4 + c), g = __ldg(dg + row * C4 + c);
+    float4 a = HBF ? load_bf16x4((const __nv_bfloat16*)h, row * C4 + c) : __ldg((const float4*)h + row * C4 + c);
+    float4 g = HBF ? load_bf16x4((const __nv_bfloat16*)dg, row * C4 + c) : __ldg((const float4*)dg + row * C4 + c);
     float4 o = make_float4(g.x * gelu_grad_f(a.x + b.x), g.y * gelu_grad_f(a.y + b.y), g.z * gelu_grad_f(a.z + b.z),
                            g.w * gelu_grad_f(a.w + b.w));
     if (dh) dh[row * C4 + c] = o;
@@ -260,18 +296,27 @@ __global__ void __launch_bounds__(256) bias_gelu_bwd_kernel(const float4* __rest
   ew_cta_atomic_add(partial + (long long)blockIdx.x * 4 * C4, 4 * C4, dbias, 4 * C4, nullptr);
 }
 
-// out / out_bf16 (N,C): either may be NULL
-extern "C" int gdmae_bias_gelu_fwd(const float* h, const float* bias, int64_t N, int C, float* out, void* out_bf16, void* stream_) {
+// out / out_bf16 (N,C): either may be NULL.  Internal form: h (and dg in the backward) may be bf16 tensors.
+int ew_bias_gelu_fwd(const void* h, int h_bf16, const float* bias, int64_t N, int C, float* out, void* out_bf16, void* stream_) {
   GDMAE_CHECK_ARG(N >= 0 && C > 0 && (C % 4) == 0 && (out || out_bf16));
   if (N == 0) return GDMAE_OK;
-  bias_gelu_fwd_kernel<<<gdmae_grid(N * (C / 4), 256, 8), 256, 0, (cudaStream_t)stream_>>>(
-      (const float4*)h, (const float4*)bias, N * (C / 4), C / 4, (float4*)out, (__nv_bfloat16*)out_bf16);
+  const int grid = gdmae_grid(N * (C / 4), 256, 8);
+  if (h_bf16)
+    bias_gelu_fwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream_>>>(h, (const float4*)bias, N * (C / 4), C / 4, (float4*)out,
+                                                                        (__nv_bfloat16*)out_bf16);
+  else
+    bias_gelu_fwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream_>>>(h, (const float4*)bias, N * (C / 4), C / 4, (float4*)out,
+                                                                         (__nv_bfloat16*)out_bf16);
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;
 }
 
-extern "C" int gdmae_bias_gelu_bwd(const float* h, const float* bias, const float* dg, int64_t N, int C, float* dh, void* dh_bf16,
-                                   float* dbias, int accumulate, void* workspace, size_t ws_bytes, void* stream_) {
+extern "C" int gdmae_bias_gelu_fwd(const float* h, const float* bias, int64_t N, int C, float* out, void* out_bf16, void* stream_) {
+  return ew_bias_gelu_fwd(h, 0, bias, N, C, out, out_bf16, stream_);
+}
+
+int ew_bias_gelu_bwd(const void* h, const void* dg, int hdg_bf16, const float* bias, int64_t N, int C, float* dh, void* dh_bf16,
+                     float* dbias, int accumulate, void* workspace, size_t ws_bytes, void* stream_) {
   GDMAE_CHECK_ARG(N >= 0 && C > 0 && (C % 4) == 0 && (C / 4) <= 256 && 256 % (C / 4) == 0 && (dh || dh_bf16));
   if (ws_bytes < gdmae_rowwise_workspace_bytes(C)) { gdmae_set_error("bias_gelu_bwd: workspace too small"); return GDMAE_ERR_WORKSPACE; }
   if (N == 0) return GDMAE_OK;
@@ -281,10 +326,19 @@ extern "C" int gdmae_bias_gelu_bwd(const float* h, const float* bias, const floa
   int grid = (int)(need < EW_PART_BLOCKS ? need : EW_PART_BLOCKS);
   float* partial = (float*)workspace;
   if (!accumulate) GDMAE_CHECK_CUDA(cudaMemsetAsync(dbias, 0, (size_t)C * 4, st));
-  bias_gelu_bwd_kernel<<<grid, 256, 0, st>>>((const float4*)h, (const float4*)bias, (const float4*)dg, N, C / 4, (float4*)dh,
-                                             (__nv_bfloat16*)dh_bf16, partial, dbias, accumulate);
+  if (hdg_bf16)
+    bias_gelu_bwd_kernel<true><<<grid, 256, 0, st>>>(h, (const float4*)bias, dg, N, C / 4, (float4*)dh, (__nv_bfloat16*)dh_bf16, partial,
+                                                     dbias, accumulate);
+  else
+    bias_gelu_bwd_kernel<false><<<grid, 256, 0, st>>>(h, (const float4*)bias, dg, N, C / 4, (float4*)dh, (__nv_bfloat16*)dh_bf16, partial,
+                                                      dbias, accumulate);
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;
+}
+
+extern "C" int gdmae_bias_gelu_bwd(const float* h, const float* bias, const float* dg, int64_t N, int C, float* dh, void* dh_bf16,
+                                   float* dbias, int accumulate, void* workspace, size_t ws_bytes, void* stream_) {
+  return ew_bias_gelu_bwd(h, dg, 0, bias, N, C, dh, dh_bf16, dbias, accumulate, workspace, ws_bytes, stream_);
 }
 
 // ------------------------------------------------------------------ column sums (bias gradients of the GEMMs)

@@ -52,6 +52,16 @@ __global__ void dtau_kernel(const double* __restrict__ dtau_sum, const float* __
   dtau[0] = accumulate ? dtau[0] + g : g;
 }
 
+// internal forms of the row kernels (elementwise.cu): bf16 GEMM outputs as inputs, bias gradient fused into the LayerNorm backward
+int ew_add_layernorm_fwd(const float* x, const void* res, int res_bf16, const float* bias, const float* gamma, const float* beta,
+                         int64_t N, int d, float eps, float* y, void* y_bf16, float* mean, float* rstd, void* stream_);
+int ew_add_layernorm_bwd(const float* x, const void* res, int res_bf16, const float* bias, const float* gamma, const float* mean,
+                         const float* rstd, const float* dy, int64_t N, int d, float* dz, void* dz_bf16, float* dgamma,
+                         float* dbeta, float* dbias, int accumulate, void* workspace, size_t ws_bytes, void* stream_);
+int ew_bias_gelu_fwd(const void* h, int h_bf16, const float* bias, int64_t N, int C, float* out, void* out_bf16, void* stream_);
+int ew_bias_gelu_bwd(const void* h, const void* dg, int hdg_bf16, const float* bias, int64_t N, int C, float* dh, void* dh_bf16,
+                     float* dbias, int accumulate, void* workspace, size_t ws_bytes, void* stream_);
+
 extern "C" int gdmae_timing_on(void);
 extern "C" void gdmae_timing_push(int kind, int d, int64_t n, int64_t bytes, void* e0, void* e1);
 // bench-only CUDA events around one launch sequence (no-op unless gdmae_timing_enable(1))
@@ -123,14 +133,16 @@ extern "C" int gdmae_encoder_layer_fwd(const gdmae_encoder_layer_args* a) {
                                     a->lse, a->stream));
   // algorithmic bytes (SURVEY.md 8d, a18 minus projections): q, k, v in, o out, lse out
   span.end(0, d, N, N * d * (3 * (tc ? 2 : 4) + (bf ? 2 : 4)) + N * 32);
-  EL_CALL(el_gemm(a, 0, 1, N, d, d, a->o, d, a->w_o_g, d, a->a, d, 0, 0.f));
-  EL_CALL(gdmae_add_layernorm_fwd(a->x, a->a, a->b_o, a->g1, a->be1, N, d, a->eps, a->x1, bf ? a->x1g : nullptr, a->mean1, a->rstd1,
-                                  a->stream));
-  EL_CALL(el_gemm(a, 0, 1, N, dff, d, bf ? a->x1g : (const void*)a->x1, d, a->w1_g, d, a->h, dff, 0, 0.f));
-  EL_CALL(gdmae_bias_gelu_fwd(a->h, a->b1, N, dff, bf ? nullptr : (float*)a->g, bf ? a->g : nullptr, a->stream));
-  EL_CALL(el_gemm(a, 0, 1, N, d, dff, a->g, dff, a->w2_g, dff, a->f, d, 0, 0.f));
-  EL_CALL(gdmae_add_layernorm_fwd(a->x1, a->f, a->b2, a->g2, a->be2, N, d, a->eps, a->x2, bf ? a->x2g : nullptr, a->mean2, a->rstd2,
-                                  a->stream));
+  // bf16 configuration: the GEMM outputs that only feed a row kernel (a, h, f) leave the GEMM epilogue as bf16
+  const int ob = bf ? 1 : 0;
+  EL_CALL(el_gemm(a, 0, 1, N, d, d, a->o, d, a->w_o_g, d, a->a, d, ob, 0.f));
+  EL_CALL(ew_add_layernorm_fwd(a->x, a->a, ob, a->b_o, a->g1, a->be1, N, d, a->eps, a->x1, bf ? a->x1g : nullptr, a->mean1, a->rstd1,
+                               a->stream));
+  EL_CALL(el_gemm(a, 0, 1, N, dff, d, bf ? a->x1g : (const void*)a->x1, d, a->w1_g, d, a->h, dff, ob, 0.f));
+  EL_CALL(ew_bias_gelu_fwd(a->h, ob, a->b1, N, dff, bf ? nullptr : (float*)a->g, bf ? a->g : nullptr, a->stream));
+  EL_CALL(el_gemm(a, 0, 1, N, d, dff, a->g, dff, a->w2_g, dff, a->f, d, ob, 0.f));
+  EL_CALL(ew_add_layernorm_fwd(a->x1, a->f, ob, a->b2, a->g2, a->be2, N, d, a->eps, a->x2, bf ? a->x2g : nullptr, a->mean2, a->rstd2,
+                               a->stream));
   return GDMAE_OK;
 }
 
@@ -170,20 +182,19 @@ extern "C" int gdmae_encoder_layer_bwd(const gdmae_encoder_layer_args* a) {
   const size_t es = bf ? 2 : 4;
 
   // ---- LayerNorm 2 and the feed-forward
-  EL_CALL(gdmae_add_layernorm_bwd(a->x1, a->f, a->b2, a->g2, a->mean2, a->rstd2, a->dy, N, d, dz2, bf ? dz2g : nullptr, a->d_g2,
-                                  a->d_be2, acc, rw, rw_bytes, a->stream));
+  const int ob = bf ? 1 : 0;   // a, h, f (forward) and dgl are bf16 GEMM outputs in the bf16 configuration
+  EL_CALL(ew_add_layernorm_bwd(a->x1, a->f, ob, a->b2, a->g2, a->mean2, a->rstd2, a->dy, N, d, dz2, bf ? dz2g : nullptr, a->d_g2,
+                               a->d_be2, a->d_b2, acc, rw, rw_bytes, a->stream));   // d_b2 = column sums of dz2, same pass
   const void* dz2_op = bf ? (const void*)dz2g : (const void*)dz2;
-  EL_CALL(gdmae_colsum(dz2, 0, N, d, 0, d, a->d_b2, acc, rw, rw_bytes, a->stream));
   EL_CALL(el_gemm(a, 1, 0, d, dff, N, dz2_op, d, a->g, dff, a->d_w2, dff, 0, wbeta));
-  EL_CALL(el_gemm(a, 0, 0, N, dff, d, dz2_op, d, a->w2_g, dff, dgl, dff, 0, 0.f));
-  EL_CALL(gdmae_bias_gelu_bwd(a->h, a->b1, dgl, N, dff, bf ? nullptr : dh, bf ? dh : nullptr, a->d_b1, acc, rw, rw_bytes, a->stream));
+  EL_CALL(el_gemm(a, 0, 0, N, dff, d, dz2_op, d, a->w2_g, dff, dgl, dff, ob, 0.f));
+  EL_CALL(ew_bias_gelu_bwd(a->h, dgl, ob, a->b1, N, dff, bf ? nullptr : dh, bf ? dh : nullptr, a->d_b1, acc, rw, rw_bytes, a->stream));
   EL_CALL(el_gemm(a, 1, 0, dff, d, N, dh, dff, x1g, d, a->d_w1, d, 0, wbeta));
   EL_CALL(el_gemm(a, 0, 0, N, d, dff, dh, dff, a->w1_g, d, dz2, d, 0, 1.f));   // dz2 := gradient w.r.t. x1
   // ---- LayerNorm 1 and the attention
-  EL_CALL(gdmae_add_layernorm_bwd(a->x, a->a, a->b_o, a->g1, a->mean1, a->rstd1, dz2, N, d, dz1, bf ? dz1g : nullptr, a->d_g1,
-                                  a->d_be1, acc, rw, rw_bytes, a->stream));
+  EL_CALL(ew_add_layernorm_bwd(a->x, a->a, ob, a->b_o, a->g1, a->mean1, a->rstd1, dz2, N, d, dz1, bf ? dz1g : nullptr, a->d_g1,
+                               a->d_be1, a->d_b_o, acc, rw, rw_bytes, a->stream));  // d_b_o = column sums of dz1
   const void* dz1_op = bf ? (const void*)dz1g : (const void*)dz1;
-  EL_CALL(gdmae_colsum(dz1, 0, N, d, 0, d, a->d_b_o, acc, rw, rw_bytes, a->stream));
   EL_CALL(el_gemm(a, 1, 0, d, d, N, dz1_op, d, a->o, d, a->d_w_o, d, 0, wbeta));
   const int tc = a->sra_tensor_cores ? 1 : 0;
   EL_CALL(el_gemm(a, 0, 0, N, d, d, dz1_op, d, a->w_o_g, d, dout, d, tc, 0.f));

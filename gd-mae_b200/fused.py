@@ -245,11 +245,13 @@ class EncoderLayerFunction(torch.autograd.Function):
             A.xg_in = xg_in.data_ptr()
         # ---- activations saved for backward: one fp32 and one bf16 buffer, carved here
         Nd, Nf = _r64(N * d), _r64(N * dff)
-        n32 = (0 if tc else 3 * Nd) + 2 * Nd + Nf + Nd + _r64(N * 8) + 4 * _r64(N) + 128 * d + (0 if bf else Nd + Nf)
+        # a, h, f (GEMM outputs that only feed a row kernel) are bf16 in the bf16 configuration: half the 32-bit words
+        Na, Nh = (Nd // 2, Nf // 2) if bf else (Nd, Nf)
+        n32 = (0 if tc else 3 * Nd) + 2 * Na + Nh + Nd + _r64(N * 8) + 4 * _r64(N) + 128 * d + (0 if bf else Nd + Nf)
         save32 = torch.empty((max(n32, 1),), dtype=F32, device=dev)
         b = save32.data_ptr()
         off = 0
-        for name, n in (("qkv", 0 if tc else 3 * Nd), ("a", Nd), ("x1", Nd), ("h", Nf), ("f", Nd), ("lse", _r64(N * 8)), ("mean1", _r64(N)),
+        for name, n in (("qkv", 0 if tc else 3 * Nd), ("a", Na), ("x1", Nd), ("h", Nh), ("f", Na), ("lse", _r64(N * 8)), ("mean1", _r64(N)),
                         ("rstd1", _r64(N)), ("mean2", _r64(N)), ("rstd2", _r64(N)), ("lut", 128 * d)):
             setattr(A, name, b + 4 * off)
             off += n

@@ -246,13 +246,13 @@ typedef struct gdmae_encoder_layer_args {
   float* lut;                /* (64,2d) */
   void* o;                   /* (N,d) op */
   float* lse;                /* (N,8) */
-  float* a;                  /* (N,d) */
+  void* a;                   /* (N,d) out-projection output: fp32, bf16 when gemm_mode == 1 */
   float* x1;                 /* (N,d) */
   void* x1g;                 /* (N,d) op (bf16 mode only) */
   float *mean1, *rstd1;      /* (N) */
-  float* h;                  /* (N,dff) */
+  void* h;                   /* (N,dff) FFN pre-activation: fp32, bf16 when gemm_mode == 1 */
   void* g;                   /* (N,dff) op */
-  float* f;                  /* (N,d) */
+  void* f;                   /* (N,d) FFN output: fp32, bf16 when gemm_mode == 1 */
   float *mean2, *rstd2;      /* (N) */
   float* x2;                 /* (N,d) output */
   void* x2g;                 /* (N,d) op copy of the output (bf16 mode only) */

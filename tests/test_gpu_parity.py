@@ -469,3 +469,60 @@ def test_bf16_configuration_close_to_reference(G, golden):
     finally:
         fused.BF16_SHADOW.clear()
         G.config.set_precision(model, "fp32")
+
+
+# ------------------------------------------------------------------------------ BASELINE config 0 (KITTI) on the GPU
+def test_kitti_c1_matches_reference_golden(G, golden):
+    """KITTI gd_mae.yaml shape (216x248 grid, 4 point features -> VFE input 10), batch 1: DynVFE + sst_block_x1
+    forward through the plugin classes against the unmodified reference's outputs (tests/golden/kitti_c1.npz)."""
+    from gd_mae_b200.pcdet.utils.spconv_utils import spconv
+    K = golden("kitti_c1")
+    model, cfg, ocfg, P, Bf = build(G, "kitti", 0.85, int(K["param_seed"]))
+    assert [int(v) for v in cfg.GRID_SIZE] == [216, 248, 1]
+    model.train()
+    with torch.no_grad():
+        bd = model.vfe(dict(points=torch.from_numpy(K["points_in"]).cuda(), batch_size=1))
+        assert np.array_equal(bd["voxel_coords"].cpu().numpy(), K["voxel_coords"])
+        assert np.array_equal(bd["point_inverse_indices"].cpu().numpy(), K["inverse"])
+        assert rel(bd["voxel_features"][::SUB], K["pillar_features_sub"]) < 1e-4
+        vc = bd["voxel_coords"]
+        sp = spconv.SparseConvTensor(bd["voxel_features"], vc[:, [0, 2, 3]].contiguous().int(), [248, 216], 1)
+        y = model.backbone_3d.sst_blocks[0](sp)
+        assert rel(y.features[::SUB], K["block_out_sub"]) < 1e-3   # north_star: 1e-3 relative fp32
+
+
+# ------------------------------------------------------------------------------ BASELINE config 4 (ONCE) dense stress
+def test_once_dense_stress_step_matches_oracle(G):
+    """ONCE SSL shape (z in [-5,3], voxel z 8.0, 4 point features, 468x468 grid), one frame whose points crowd the
+    sensor: hundreds of pillars hold more than NUM_GT_POINTS=64 points (ground-truth truncation in group_inner_inds)
+    and, at mask ratio 0.3, windows of all three drop levels (16/32/64 tokens) occur at every scale.  One full
+    iteration (fwd + loss + bwd + clip + AdamOneCycle) against the CPU oracle, fp32 configuration."""
+    from gd_mae_b200.trainer import MAETrainer
+    model, cfg, ocfg, P, Bf = build(G, "once_ssl", 0.3, 11)
+    G.config.set_precision(model, "fp32")
+    model.backbone_3d.dense_spatial_features = False
+    r = np.random.RandomState(5)
+    n = 80000
+    az = r.uniform(-np.pi, np.pi, n)
+    rr = 2 + r.exponential(3.0, n)
+    pts = np.stack([np.zeros(n), rr * np.cos(az), rr * np.sin(az), r.uniform(-4.5, 2.5, n), r.uniform(0, 1, n)], 1).astype(np.float32)
+    pts = torch.from_numpy(pts)
+    _, opts, _, ovc, oinv = O.voxelize(pts, ocfg)
+    counts = torch.bincount(oinv)
+    assert int((counts > 64).sum()) >= 50, int((counts > 64).sum())
+    noise = torch.rand(ovc.shape[0], generator=torch.Generator().manual_seed(4))
+    # all three drop levels present among the visible pillars of the first scale
+    mask = O.mae_mask(ovc, 1, noise, 0.3)
+    vis = ovc[mask == 0]
+    info = O.window_info(vis, ocfg["grid"], (8, 8, 1), 128, 1000.0)
+    assert sorted(torch.unique(info[0]["lvl"]).tolist()) == [0, 1, 2]
+    opt = O.AdamOneCycle(P, ocfg, 10)
+    P0 = {k: v.clone() for k, v in P.items()}
+    lo, Gr, _ = O.train_step(P, Bf, opt, pts, 1, ocfg, noise, 0)
+    trainer = MAETrainer(model, cfg.OPTIMIZATION, total_steps=10)
+    lc = float(trainer.step(dict(points=pts.cuda(), batch_size=1, voxel_mae_noise=noise.cuda())))
+    assert abs(lc - lo) / abs(lo) < 1e-3, (lc, lo)
+    sd = model.state_dict()
+    num = sum(float(((sd[k].cpu().double() - P[k].double()) ** 2).sum()) for k in P)
+    den = sum(float(((P[k].double() - P0[k].double()) ** 2).sum()) for k in P)
+    assert (num / den) ** 0.5 < 5e-2, (num / den) ** 0.5
