@@ -95,7 +95,7 @@ def run_reference(args):
     cfg = O.make_cfg("waymo_ssl")
     P, Bf = O.init_params(cfg, 0)
     total = max(args.steps + args.warmup, 2)
-    opt = O.AdamOneCycle(P, cfg, total)
+    opt = O.AdamOneCycle(P, cfg, max(total, 10))   # the one-cycle schedule needs a few steps per phase
     frames = [torch.from_numpy(O.synth_batch([s], cfg)) for s in range(min(total, 4))]
     g = torch.Generator().manual_seed(666)
 

@@ -39,7 +39,7 @@ def lib():
         L.gdmae_last_error.restype = ctypes.c_char_p
         for name in exported_symbols_from_header():
             fn = getattr(L, name)
-            if name.endswith("_workspace_bytes"):
+            if name.endswith("_bytes"):
                 fn.restype = ctypes.c_size_t
             elif name == "gdmae_launch_count":
                 fn.restype = ctypes.c_int64

@@ -126,7 +126,7 @@ extern "C" int gdmae_encoder_layer_fwd(const gdmae_encoder_layer_args* a) {
   GDMAE_LAUNCH_CHECK();
   ElSpan span(st);
   if (tc)
-    EL_CALL(gdmae_sra_attention_fwd_tc(a->qkv, a->lut, a->row_info, N, d, a->nhead, a->tau, a->tau_min, a->b_in + 2 * d, bf, a->o,
+    EL_CALL(gdmae_sra_attention_fwd_tc(a->qkv, a->lut, a->row_info, a->bin_units, N, d, a->nhead, a->tau, a->tau_min, a->b_in + 2 * d, bf, a->o,
                                        a->lse, a->stream));
   else
     EL_CALL(gdmae_sra_attention_fwd((const float*)a->qkv, a->lut, a->row_info, N, d, a->nhead, a->tau, a->tau_min, a->b_in + 2 * d, bf, a->o,
@@ -201,7 +201,7 @@ extern "C" int gdmae_encoder_layer_bwd(const gdmae_encoder_layer_args* a) {
   GDMAE_CHECK_CUDA(cudaMemsetAsync(dtau_sum, 0, sizeof(double), st));
   ElSpan span(st);
   if (tc)
-    EL_CALL(gdmae_sra_attention_bwd_tc(a->qkv, a->lut, a->row_info, N, d, a->nhead, a->tau, a->tau_min, a->lse, dout, dqkv, dtau_sum,
+    EL_CALL(gdmae_sra_attention_bwd_tc(a->qkv, a->lut, a->row_info, a->bin_units, N, d, a->nhead, a->tau, a->tau_min, a->lse, dout, dqkv, dtau_sum,
                                        a->stream));
   else
     EL_CALL(gdmae_sra_attention_bwd((const float*)a->qkv, a->lut, a->row_info, N, d, a->nhead, a->tau, a->tau_min, a->b_in + 2 * d, bf,

@@ -39,9 +39,11 @@
 #define MM_STAGES 3
 #define MM_NINFO 5
 #define MM_UNITS 48
+#define MM_UNIT_STRIDE 64      // ints per bin in the unit table: [0, 48) units, [48] count, [49] work counter (0), pad
+#define MM_UNIT_CHUNKS 13      // 16-byte chunks copied per bin (52 ints)
 #define MM_ARR (MM_ROWS * MM_PITCH)
 #define MM_STAGE_ELEMS (3 * MM_ARR)
-#define MM_SMEM_BYTES (64 * 2 * MM_SLICE * 2 + MM_STAGES * MM_STAGE_ELEMS * 2 + MM_NINFO * MM_INFO * 16 + 2 * (MM_UNITS + 16) * 4)
+#define MM_SMEM_BYTES (64 * 2 * MM_SLICE * 2 + MM_STAGES * MM_STAGE_ELEMS * 2 + MM_NINFO * MM_INFO * 16 + MM_NINFO * MM_UNIT_STRIDE * 4)
 
 typedef __nv_bfloat16 bf16;
 
@@ -49,6 +51,7 @@ struct MmArgs {
   const bf16* qkv;     // (N, 3d) bf16
   const float* lut;    // (64, 2d)
   const int4* row_info;
+  const int* bin_units; // (ceil(N/64), 64) work units per bin (gdmae_sra_bin_units)
   const float* tau;
   const float* bv;     // (d) value bias added to the output, nullable
   float tau_min;
@@ -103,8 +106,12 @@ __device__ __forceinline__ void mm_bin_range(const int4* inf, int bin, int N, in
 }
 
 // the stager group (MM_GROUP threads, index gt) issues all copies
-__device__ __forceinline__ void mm_issue_info(int4* inf, const int4* row_info, int bin, int N, int gt) {
-  if (gt < MM_INFO && bin + gt < N) mm_cp16(inf + gt, row_info + bin + gt);
+__device__ __forceinline__ void mm_issue_info(int4* inf, int* units, const int4* row_info, const int* bin_units, int bin, int N, int gt) {
+  if (gt < MM_INFO) {
+    if (bin + gt < N) mm_cp16(inf + gt, row_info + bin + gt);
+  } else if (gt < MM_INFO + MM_UNIT_CHUNKS) {
+    mm_cp16(units + 4 * (gt - MM_INFO), bin_units + (long long)(bin / MM_BIN) * MM_UNIT_STRIDE + 4 * (gt - MM_INFO));
+  }
 }
 
 __device__ __forceinline__ void mm_issue_rows(bf16* stage, const int4* inf, const bf16* qkv, int d, int col, int bin, int N, int gt) {
@@ -128,6 +135,42 @@ __device__ __forceinline__ unsigned mm_bits(unsigned long long m0, unsigned long
   if (pos >= 64) v = m1 >> (pos - 64);
   else v = (m0 >> pos) | (pos ? (m1 << (64 - pos)) : 0ull);
   return (unsigned)v;
+}
+
+// Staging of one 8-channel group of a q or k row, in place: + LUT (packed bf16 add), L2 norm of the head in fp32
+// (the 8-channel groups of a head sit in adjacent lanes: 2 lanes for 16-channel heads, 4 for 32), scale, back to bf16.
+// Returns 1/|x| of the head.
+template <int HD>
+__device__ __forceinline__ float mm_stage_task(bf16* p, const bf16* lut_row, float extra_scale, bool valid) {
+  uint4 raw = *reinterpret_cast<const uint4*>(p);
+  const uint4 lr = *reinterpret_cast<const uint4*>(lut_row);
+  unsigned w[4] = {raw.x, raw.y, raw.z, raw.w};
+  const unsigned l[4] = {lr.x, lr.y, lr.z, lr.w};
+  float x[8];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 sum = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]), *reinterpret_cast<const __nv_bfloat162*>(&l[i]));
+    const unsigned u = *reinterpret_cast<unsigned*>(&sum);
+    x[2 * i] = __uint_as_float(u << 16);
+    x[2 * i + 1] = __uint_as_float(u & 0xffff0000u);
+    ss = fmaf(x[2 * i], x[2 * i], ss);
+    ss = fmaf(x[2 * i + 1], x[2 * i + 1], ss);
+  }
+  ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+  if (HD == 32) ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+  float rn;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rn) : "f"(fmaxf(ss, 1e-24f)));
+  const float f = rn * extra_scale;
+  if (valid) {
+    uint4 o;
+    o.x = pack_bf16(x[0] * f, x[1] * f);
+    o.y = pack_bf16(x[2] * f, x[3] * f);
+    o.z = pack_bf16(x[4] * f, x[5] * f);
+    o.w = pack_bf16(x[6] * f, x[7] * f);
+    *reinterpret_cast<uint4*>(p) = o;
+  }
+  return rn;
 }
 
 // One (unit, head) on one warp: S = Q K^T, masked softmax, O = P V, for NT2 8-key tiles (NT2 even).
@@ -232,7 +275,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) sra_fwd_mma_kernel(MmArgs a, vo
   bf16* slut = (bf16*)smem_raw;                               // [64][128]: q part | k part of this slice
   bf16* sdata = slut + 64 * 2 * MM_SLICE;                     // MM_STAGES x {q, k, v} x [144][72]
   int4* sinfo_all = (int4*)(sdata + MM_STAGES * MM_STAGE_ELEMS);
-  int* sunit_all = (int*)(sinfo_all + MM_NINFO * MM_INFO);    // 2 x { units: q0 | qn << 7 | k0 << 12 | kn << 19 ; [MM_UNITS] = count }
+  int* sunit_all = (int*)(sinfo_all + MM_NINFO * MM_INFO);    // MM_NINFO x { units: q0 | qn << 7 | k0 << 12 | kn << 19 ; [MM_UNITS] = count, [+1] = work counter }
   constexpr int HS = MM_SLICE / HD;
   const int d = a.d;
   const int nsl = d / MM_SLICE;
@@ -242,7 +285,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) sra_fwd_mma_kernel(MmArgs a, vo
   const int nbins = (a.N + MM_BIN - 1) / MM_BIN;
   constexpr int GW = MM_GROUP >> 5;                           // warps per role
   const bool stager = warp < GW;
-  const int gt = tid & (MM_GROUP - 1), gw = warp & (GW - 1);
+  const int gt = tid & (MM_GROUP - 1);
   if (cta >= nbins) return;
   const int my_bins = (nbins - cta + ncta - 1) / ncta;        // bins cta, cta + ncta, ...
 
@@ -257,7 +300,8 @@ __global__ void __launch_bounds__(MM_THREADS, 1) sra_fwd_mma_kernel(MmArgs a, vo
   if (stager) {
 #pragma unroll
     for (int j = 0; j < 3; ++j)
-      if (j < my_bins) mm_issue_info(sinfo_all + j * MM_INFO, a.row_info, (cta + j * ncta) * MM_BIN, a.N, gt);
+      if (j < my_bins)
+        mm_issue_info(sinfo_all + j * MM_INFO, sunit_all + j * MM_UNIT_STRIDE, a.row_info, a.bin_units, (cta + j * ncta) * MM_BIN, a.N, gt);
     mm_commit();
     mm_wait<0>();
   }
@@ -281,101 +325,32 @@ __global__ void __launch_bounds__(MM_THREADS, 1) sra_fwd_mma_kernel(MmArgs a, vo
           mm_issue_rows(sdata + ((j + 1) % MM_STAGES) * MM_STAGE_ELEMS, sinfo_all + ((j + 1) % MM_NINFO) * MM_INFO, a.qkv, d, col,
                         (cta + (j + 1) * ncta) * MM_BIN, a.N, gt);
         if (j + 3 < my_bins)
-          mm_issue_info(sinfo_all + ((j + 3) % MM_NINFO) * MM_INFO, a.row_info, (cta + (j + 3) * ncta) * MM_BIN, a.N, gt);
+          mm_issue_info(sinfo_all + ((j + 3) % MM_NINFO) * MM_INFO, sunit_all + ((j + 3) % MM_NINFO) * MM_UNIT_STRIDE, a.row_info,
+                        a.bin_units, (cta + (j + 3) * ncta) * MM_BIN, a.N, gt);
         mm_commit();
-        mm_wait<1>();          // everything but the group just committed: rows of bin j, records of bin j+2
+        mm_wait<1>();          // everything but the group just committed: rows of bin j, records + units of bin j+2
         mm_bar_stagers();      // ... from every stager thread
         int row0, R;
         mm_bin_range(sinfo, bin, a.N, row0, R);
         const int shift = row0 - bin;
-        // ---- q and k in place: + LUT, L2-normalise per head, q also x log2(e)/tau; one task = 8 channels,
-        // two tasks per thread in flight
-        const int ntask = R * 16;
-        for (int base = 0; base < ntask; base += 2 * MM_GROUP) {
-          uint4 raw[2], lr[2];
-          bf16* p[2];
-          bool valid[2];
-          int part[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int idx = base + u * MM_GROUP + gt;
-            valid[u] = idx < ntask;
-            const int r = valid[u] ? (idx >> 4) : 0;
-            part[u] = (idx >> 3) & 1;
-            const int c8 = idx & 7;
-            p[u] = sq + part[u] * MM_ARR + r * MM_PITCH + 8 * c8;
-            raw[u] = *reinterpret_cast<const uint4*>(p[u]);
-            lr[u] = *reinterpret_cast<const uint4*>(slut + sinfo[r + shift].w * 2 * MM_SLICE + part[u] * MM_SLICE + 8 * c8);
-          }
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            float x[8];
-            const unsigned rw[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w}, lw[4] = {lr[u].x, lr[u].y, lr[u].z, lr[u].w};
-            float ss = 0.f;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              x[2 * i] = __uint_as_float(rw[i] << 16) + __uint_as_float(lw[i] << 16);
-              x[2 * i + 1] = __uint_as_float(rw[i] & 0xffff0000u) + __uint_as_float(lw[i] & 0xffff0000u);
-              ss = fmaf(x[2 * i], x[2 * i], ss);
-              ss = fmaf(x[2 * i + 1], x[2 * i + 1], ss);
-            }
-            ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-            if (HD == 32) ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-            float f;
-            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(f) : "f"(fmaxf(ss, 1e-24f)));
-            if (part[u] == 0) f *= qscale;
-            if (valid[u]) {
-              uint4 o;
-              o.x = pack_bf16(x[0] * f, x[1] * f);
-              o.y = pack_bf16(x[2] * f, x[3] * f);
-              o.z = pack_bf16(x[4] * f, x[5] * f);
-              o.w = pack_bf16(x[6] * f, x[7] * f);
-              *reinterpret_cast<uint4*>(p[u]) = o;
-            }
+        // ---- q and k in place: + LUT, L2-normalise per head, q also x log2(e)/tau.  A thread keeps its 8-channel
+        // group (c8) and array (q or k) for the whole bin and walks rows 16 at a time, two rows in flight.
+        {
+          const int c8 = gt & 7, part = (gt >> 3) & 1, rsub = gt >> 4;
+          const float sc = part == 0 ? qscale : 1.f;
+          bf16* base = sq + part * MM_ARR + 8 * c8;
+          const int4* inf = sinfo + shift;
+          const bf16* lutc = slut + part * MM_SLICE + 8 * c8;
+          for (int rb = 0; rb < R; rb += 32) {                 // uniform trip count: the task shuffles inside the warp
+            const int r0 = rb + rsub, r1 = r0 + 16;
+            const bool v0 = r0 < R, v1 = r1 < R;
+            const int c0 = v0 ? r0 : 0, c1 = v1 ? r1 : 0;
+            const int pos0 = inf[c0].w, pos1 = inf[c1].w;
+            mm_stage_task<HD>(base + c0 * MM_PITCH, lutc + pos0 * 2 * MM_SLICE, sc, v0);
+            mm_stage_task<HD>(base + c1 * MM_PITCH, lutc + pos1 * 2 * MM_SLICE, sc, v1);
           }
         }
       }
-    } else if (gw == 0 && j < my_bins) {
-      // ---- work units of bin j, built by one math warp (the records of bin j landed an iteration ago)
-      const int bin = (cta + j * ncta) * MM_BIN;
-      const int4* sinfo = sinfo_all + (j % MM_NINFO) * MM_INFO;
-      int* sunit = sunit_all + (j & 1) * (MM_UNITS + 16);
-      int row0, R;
-      mm_bin_range(sinfo, bin, a.N, row0, R);
-      const int shift = row0 - bin;
-      int nu = 0;
-      if (R > 0) {
-        unsigned long long m0 = 0, m1 = 0;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          int r = 32 * w + lane;
-          bool st = r < R && sinfo[min(r, R - 1) + shift].y == row0 + r;
-          unsigned long long b = __ballot_sync(0xffffffffu, st);
-          if (w < 2) m0 |= b << (32 * w);
-          else m1 |= b << (32 * (w - 2));
-        }
-        if (R < 64) m0 |= 1ull << R;      // sentinel: one past the last row
-        else m1 |= 1ull << (R - 64);
-        int s = 0;
-        while (s < R && nu < MM_UNITS) {
-          unsigned w16 = mm_bits(m0, m1, s + 1) & 0xffffu;     // window starts at rows s+1 .. s+16
-          if (w16) {                                           // run of whole windows with <= 16 rows in total
-            int e = s + 32 - __clz(w16);
-            if (lane == 0) sunit[nu] = s | ((e - s) << 7) | (s << 12) | ((e - s) << 19);
-            ++nu;
-            s = e;
-          } else {                                             // a window of more than 16 rows: 16-row query chunks
-            unsigned lo = mm_bits(m0, m1, s + 17), hi = mm_bits(m0, m1, s + 49);
-            int n = lo ? 16 + __ffs(lo) : 48 + __ffs(hi);
-            for (int m = 0; m < n && nu < MM_UNITS; m += 16) {
-              if (lane == 0) sunit[nu] = (s + m) | (min(16, n - m) << 7) | (s << 12) | (n << 19);
-              ++nu;
-            }
-            s += n;
-          }
-        }
-      }
-      if (lane == 0) { sunit[MM_UNITS] = nu; sunit[MM_UNITS + 1] = 0; }   // count, work counter
     }
     if (j > 0) {
       // ================= bin j-1: the math warps start at once, the stagers join when bin j is staged;
@@ -386,7 +361,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) sra_fwd_mma_kernel(MmArgs a, vo
       const bf16* sq = sdata + (jb % MM_STAGES) * MM_STAGE_ELEMS;
       const bf16* sk = sq + MM_ARR;
       const bf16* sv = sk + MM_ARR;
-      int* sunit = sunit_all + (jb & 1) * (MM_UNITS + 16);
+      int* sunit = sunit_all + (jb % MM_NINFO) * MM_UNIT_STRIDE;
       int row0, R;
       mm_bin_range(sinfo, bin, a.N, row0, R);
       const int shift = row0 - bin;
@@ -434,12 +409,13 @@ __global__ void __launch_bounds__(MM_THREADS, 1) sra_fwd_mma_kernel(MmArgs a, vo
 #define MB_NINFO 4
 #define MB_STAGE_ELEMS (4 * MM_ARR)
 #define MB_SCAL (MM_ROWS * 4)      // one fp32 per (row, head of the slice)
-#define MB_SMEM_BYTES (64 * 2 * MM_SLICE * 2 + MB_STAGES * MB_STAGE_ELEMS * 2 + MB_NINFO * MM_INFO * 16 + (MB_STAGES + 3) * MB_SCAL * 4 + (MM_UNITS + 16) * 4)
+#define MB_SMEM_BYTES (64 * 2 * MM_SLICE * 2 + MB_STAGES * MB_STAGE_ELEMS * 2 + MB_NINFO * MM_INFO * 16 + (MB_STAGES + 3) * MB_SCAL * 4 + MB_NINFO * MM_UNIT_STRIDE * 4 + 128 * 4 * 4)
 
 struct MbArgs {
   const bf16* qkv;     // (N, 3d) bf16
   const float* lut;    // (64, 2d)
   const int4* row_info;
+  const int* bin_units; // (ceil(N/64), 64) work units per bin (gdmae_sra_bin_units)
   const float* tau;
   const float* lse;    // (N, 8)
   const bf16* dout;    // (N, d) bf16
@@ -719,7 +695,8 @@ __global__ void __launch_bounds__(MM_THREADS, 1) sra_bwd_mma_kernel(MbArgs a) {
   float* srq = slse_all + MB_STAGES * MB_SCAL;                // 1/|q| per (row, head)
   float* srk = srq + MB_SCAL;
   float* sD = srk + MB_SCAL;
-  int* sunit = (int*)(sD + MB_SCAL);
+  int* sunit_all = (int*)(sD + MB_SCAL);
+  int* sdone = sunit_all + MB_NINFO * MM_UNIT_STRIDE;         // [128 window start rows][4 heads]: query-side entries finished
   __shared__ float s_dtau[MM_THREADS / 32];
   constexpr int HS = MM_SLICE / HD;
   constexpr int NWARPS = MM_THREADS >> 5;
@@ -743,7 +720,8 @@ __global__ void __launch_bounds__(MM_THREADS, 1) sra_bwd_mma_kernel(MbArgs a) {
   }
 #pragma unroll
   for (int j = 0; j < 3; ++j)
-    if (j < my_bins) mm_issue_info(sinfo_all + j * MM_INFO, a.row_info, (cta + j * ncta) * MM_BIN, a.N, tid);
+    if (j < my_bins)
+      mm_issue_info(sinfo_all + j * MM_INFO, sunit_all + j * MM_UNIT_STRIDE, a.row_info, a.bin_units, (cta + j * ncta) * MM_BIN, a.N, tid);
   mm_commit();
   mm_wait<0>();
   __syncthreads();
@@ -767,109 +745,73 @@ __global__ void __launch_bounds__(MM_THREADS, 1) sra_bwd_mma_kernel(MbArgs a) {
       mb_issue_rows(sdata + ((k + 1) % MB_STAGES) * MB_STAGE_ELEMS, slse_all + ((k + 1) % MB_STAGES) * MB_SCAL,
                     sinfo_all + ((k + 1) % MB_NINFO) * MM_INFO, a, col, HS, lse_col, (cta + (k + 1) * ncta) * MM_BIN, tid);
     if (k + 3 < my_bins)
-      mm_issue_info(sinfo_all + ((k + 3) % MB_NINFO) * MM_INFO, a.row_info, (cta + (k + 3) * ncta) * MM_BIN, a.N, tid);
+      mm_issue_info(sinfo_all + ((k + 3) % MB_NINFO) * MM_INFO, sunit_all + ((k + 3) % MB_NINFO) * MM_UNIT_STRIDE, a.row_info, a.bin_units,
+                    (cta + (k + 3) * ncta) * MM_BIN, a.N, tid);
     mm_commit();
     int row0, R;
     mm_bin_range(sinfo, bin, a.N, row0, R);
     if (R == 0) continue;
     const int shift = row0 - bin;
-    // ---- work units (last warp), q / k normalisation (everyone)
-    if (warp == NWARPS - 1) {
-      int nu = 0;
-      unsigned long long m0 = 0, m1 = 0;
-#pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        int r = 32 * w + lane;
-        bool st = r < R && sinfo[min(r, R - 1) + shift].y == row0 + r;
-        unsigned long long b = __ballot_sync(0xffffffffu, st);
-        if (w < 2) m0 |= b << (32 * w);
-        else m1 |= b << (32 * (w - 2));
-      }
-      if (R < 64) m0 |= 1ull << R;
-      else m1 |= 1ull << (R - 64);
-      int s = 0;
-      while (s < R && nu < MM_UNITS) {
-        unsigned w16 = mm_bits(m0, m1, s + 1) & 0xffffu;
-        if (w16) {
-          int e = s + 32 - __clz(w16);
-          if (lane == 0) sunit[nu] = s | ((e - s) << 7) | (s << 12) | ((e - s) << 19);
-          ++nu;
-          s = e;
-        } else {
-          unsigned lo = mm_bits(m0, m1, s + 17), hi = mm_bits(m0, m1, s + 49);
-          int n = lo ? 16 + __ffs(lo) : 48 + __ffs(hi);
-          for (int m = 0; m < n && nu < MM_UNITS; m += 16) {
-            if (lane == 0) sunit[nu] = (s + m) | (min(16, n - m) << 7) | (s << 12) | (n << 19);
-            ++nu;
-          }
-          s += n;
-        }
-      }
-      if (lane == 0) sunit[MM_UNITS] = nu;
-    }
+    // ---- q / k staging in place (+ LUT, normalise, keep 1/|q|, 1/|k| per (row, head)); the work units of the bin came
+    // with its records (gdmae_sra_bin_units)
+    int* sunit = sunit_all + (k % MB_NINFO) * MM_UNIT_STRIDE;
+    sdone[tid] = 0;      // MM_THREADS == 128 * 4
     {
-      const int ntask = R * 16;
-      for (int base = 0; base < ntask; base += MM_THREADS) {
-        const int idx = base + tid;
-        const bool valid = idx < ntask;
-        const int r = valid ? (idx >> 4) : 0;
-        const int part = (idx >> 3) & 1, c8 = idx & 7;
-        bf16* p = sq + part * MM_ARR + r * MM_PITCH + 8 * c8;
-        const uint4 raw = *reinterpret_cast<const uint4*>(p);
-        const uint4 lr = *reinterpret_cast<const uint4*>(slut + sinfo[r + shift].w * 2 * MM_SLICE + part * MM_SLICE + 8 * c8);
-        float x[8];
-        const unsigned rw[4] = {raw.x, raw.y, raw.z, raw.w}, lw[4] = {lr.x, lr.y, lr.z, lr.w};
-        float ss = 0.f;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          x[2 * i] = __uint_as_float(rw[i] << 16) + __uint_as_float(lw[i] << 16);
-          x[2 * i + 1] = __uint_as_float(rw[i] & 0xffff0000u) + __uint_as_float(lw[i] & 0xffff0000u);
-          ss = fmaf(x[2 * i], x[2 * i], ss);
-          ss = fmaf(x[2 * i + 1], x[2 * i + 1], ss);
-        }
-        ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-        if (HD == 32) ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-        float rn;
-        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rn) : "f"(fmaxf(ss, 1e-24f)));
-        const float f = part == 0 ? rn * qscale : rn;
-        if (valid) {
-          uint4 o;
-          o.x = pack_bf16(x[0] * f, x[1] * f);
-          o.y = pack_bf16(x[2] * f, x[3] * f);
-          o.z = pack_bf16(x[4] * f, x[5] * f);
-          o.w = pack_bf16(x[6] * f, x[7] * f);
-          *reinterpret_cast<uint4*>(p) = o;
-          if ((c8 & (HD / 8 - 1)) == 0) (part == 0 ? srq : srk)[r * 4 + c8 / (HD / 8)] = rn;
-        }
+      const int c8 = tid & 7, part = (tid >> 3) & 1, rsub = tid >> 4;     // 32 rows per pass
+      const float sc = part == 0 ? qscale : 1.f;
+      bf16* base = sq + part * MM_ARR + 8 * c8;
+      const int4* inf = sinfo + shift;
+      const bf16* lutc = slut + part * MM_SLICE + 8 * c8;
+      float* srn = part == 0 ? srq : srk;
+      for (int rb = 0; rb < R; rb += 32) {
+        const int r = rb + rsub;
+        const bool v = r < R;
+        const int c = v ? r : 0;
+        const float rn = mm_stage_task<HD>(base + c * MM_PITCH, lutc + inf[c].w * 2 * MM_SLICE, sc, v);
+        if (v && (c8 & (HD / 8 - 1)) == 0) srn[r * 4 + c8 / (HD / 8)] = rn;
       }
     }
     __syncthreads();
     const int nent = sunit[MM_UNITS] * HS;
     const int g = lane >> 2;
-    // ---- phase 1: query side
-    for (int e = warp; e < nent; e += NWARPS) {
+    // ---- entries [0, nent): query side; [nent, 2 nent): key side, handed out in this order through the work counter
+    // that arrived (zero) with the unit list.  A key-side entry needs D of every query row of its window: it waits
+    // until the query-side entries covering the window (one for a packed unit, ceil(rows/16) chunks for a large
+    // window) have signalled.  Every query-side entry is pulled before any key-side entry and never blocks, so the
+    // wait cannot deadlock; no CTA barrier separates the two sides.
+    for (;;) {
+      int e = 0;
+      if (lane == 0) e = atomicAdd(sunit + MM_UNITS + 1, 1);
+      e = __shfl_sync(0xffffffffu, e, 0);
+      if (e >= 2 * nent) break;
+      const bool key_side = e >= nent;
+      if (key_side) e -= nent;
       const int code = sunit[e / HS];
       const int h = e % HS;
       const int q0 = code & 127, qn = (code >> 7) & 31, k0 = (code >> 12) & 127, kn = (code >> 19) & 127;
       const int4 recA = sinfo[min(q0 + g, R - 1) + shift], recB = sinfo[min(q0 + g + 8, R - 1) + shift];
       const int kbase = row0 + k0;
-      if (kn <= 16) dtau_acc += mb_unit_q<HD, 2>(a, sq, sk, sv, sdo, slse, srq, sD, q0, qn, k0, h, recA, recB, kbase, lane, col, inv_tau, inv_qs2);
-      else if (kn <= 32) dtau_acc += mb_unit_q<HD, 4>(a, sq, sk, sv, sdo, slse, srq, sD, q0, qn, k0, h, recA, recB, kbase, lane, col, inv_tau, inv_qs2);
-      else if (kn <= 48) dtau_acc += mb_unit_q<HD, 6>(a, sq, sk, sv, sdo, slse, srq, sD, q0, qn, k0, h, recA, recB, kbase, lane, col, inv_tau, inv_qs2);
-      else dtau_acc += mb_unit_q<HD, 8>(a, sq, sk, sv, sdo, slse, srq, sD, q0, qn, k0, h, recA, recB, kbase, lane, col, inv_tau, inv_qs2);
-    }
-    __syncthreads();     // sD of every row of the bin is written
-    // ---- phase 2: key side
-    for (int e = warp; e < nent; e += NWARPS) {
-      const int code = sunit[e / HS];
-      const int h = e % HS;
-      const int q0 = code & 127, qn = (code >> 7) & 31, k0 = (code >> 12) & 127, kn = (code >> 19) & 127;
-      const int4 recA = sinfo[min(q0 + g, R - 1) + shift], recB = sinfo[min(q0 + g + 8, R - 1) + shift];
-      const int kbase = row0 + k0;
-      if (kn <= 16) mb_unit_kv<HD, 2>(a, sq, sk, sv, sdo, slse, srk, sD, q0, qn, k0, h, recA, recB, kbase, lane, col);
-      else if (kn <= 32) mb_unit_kv<HD, 4>(a, sq, sk, sv, sdo, slse, srk, sD, q0, qn, k0, h, recA, recB, kbase, lane, col);
-      else if (kn <= 48) mb_unit_kv<HD, 6>(a, sq, sk, sv, sdo, slse, srk, sD, q0, qn, k0, h, recA, recB, kbase, lane, col);
-      else mb_unit_kv<HD, 8>(a, sq, sk, sv, sdo, slse, srk, sD, q0, qn, k0, h, recA, recB, kbase, lane, col);
+      if (!key_side) {
+        if (kn <= 16) dtau_acc += mb_unit_q<HD, 2>(a, sq, sk, sv, sdo, slse, srq, sD, q0, qn, k0, h, recA, recB, kbase, lane, col, inv_tau, inv_qs2);
+        else if (kn <= 32) dtau_acc += mb_unit_q<HD, 4>(a, sq, sk, sv, sdo, slse, srq, sD, q0, qn, k0, h, recA, recB, kbase, lane, col, inv_tau, inv_qs2);
+        else if (kn <= 48) dtau_acc += mb_unit_q<HD, 6>(a, sq, sk, sv, sdo, slse, srq, sD, q0, qn, k0, h, recA, recB, kbase, lane, col, inv_tau, inv_qs2);
+        else dtau_acc += mb_unit_q<HD, 8>(a, sq, sk, sv, sdo, slse, srq, sD, q0, qn, k0, h, recA, recB, kbase, lane, col, inv_tau, inv_qs2);
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) atomicAdd(sdone + k0 * 4 + h, 1);
+      } else {
+        const int need = kn > 16 ? (kn + 15) >> 4 : 1;
+        if (lane == 0) {
+          const volatile int* flag = sdone + k0 * 4 + h;
+          for (int spin = 0; *flag < need && spin < (1 << 20); ++spin) {}   // bounded: a logic error must not hang the GPU
+        }
+        __syncwarp();
+        __threadfence_block();
+        if (kn <= 16) mb_unit_kv<HD, 2>(a, sq, sk, sv, sdo, slse, srk, sD, q0, qn, k0, h, recA, recB, kbase, lane, col);
+        else if (kn <= 32) mb_unit_kv<HD, 4>(a, sq, sk, sv, sdo, slse, srk, sD, q0, qn, k0, h, recA, recB, kbase, lane, col);
+        else if (kn <= 48) mb_unit_kv<HD, 6>(a, sq, sk, sv, sdo, slse, srk, sD, q0, qn, k0, h, recA, recB, kbase, lane, col);
+        else mb_unit_kv<HD, 8>(a, sq, sk, sv, sdo, slse, srk, sD, q0, qn, k0, h, recA, recB, kbase, lane, col);
+      }
     }
   }
   mm_wait<0>();
@@ -882,6 +824,72 @@ __global__ void __launch_bounds__(MM_THREADS, 1) sra_bwd_mma_kernel(MbArgs a) {
     for (int w = 0; w < NWARPS; ++w) tot += s_dtau[w];
     atomicAdd(a.dtau_sum, (double)tot * 0.6931471805599453);
   }
+}
+
+// =====================================================================================================
+// Work units of every 64-row bin, built once per window table (a table serves 2 encoder layers, forward and
+// backward) instead of by one warp of every CTA for every bin of every launch.  One warp per bin.
+// units[bin][0..47] = q0 | qn << 7 | k0 << 12 | kn << 19 (rows relative to the first window that starts in the bin),
+// [48] = number of units, [49] = 0 (the kernels' work counter lands on it), rest padding.
+__global__ void __launch_bounds__(256) sra_bin_units_kernel(const int4* __restrict__ row_info, int N, int* __restrict__ units) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nbins = (N + MM_BIN - 1) / MM_BIN;
+  if (warp >= nbins) return;
+  const int bin = warp * MM_BIN;
+  int* out = units + (long long)warp * MM_UNIT_STRIDE;
+  const int4 f = __ldg(row_info + bin);
+  const int row0 = (f.y == bin) ? bin : f.z;
+  int row1 = N;
+  if (bin + MM_BIN < N) {
+    const int4 l = __ldg(row_info + bin + MM_BIN);
+    row1 = (l.y == bin + MM_BIN) ? bin + MM_BIN : l.z;
+  }
+  const int R = max(row1 - row0, 0);
+  int nu = 0;
+  if (R > 0) {
+    unsigned long long m0 = 0, m1 = 0;     // bit r: row row0 + r starts a window
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int r = 32 * w + lane;
+      const bool st = r < R && __ldg(row_info + row0 + min(r, R - 1)).y == row0 + r;
+      const unsigned long long b = __ballot_sync(0xffffffffu, st);
+      if (w < 2) m0 |= b << (32 * w);
+      else m1 |= b << (32 * (w - 2));
+    }
+    if (R < 64) m0 |= 1ull << R;           // sentinel: one past the last row
+    else m1 |= 1ull << (R - 64);
+    int s = 0;
+    while (s < R && nu < MM_UNITS) {
+      const unsigned w16 = mm_bits(m0, m1, s + 1) & 0xffffu;     // window starts at rows s+1 .. s+16
+      if (w16) {                                                 // run of whole windows with <= 16 rows in total
+        const int e = s + 32 - __clz(w16);
+        if (lane == 0) out[nu] = s | ((e - s) << 7) | (s << 12) | ((e - s) << 19);
+        ++nu;
+        s = e;
+      } else {                                                   // a window of more than 16 rows: 16-row query chunks
+        const unsigned lo = mm_bits(m0, m1, s + 17), hi = mm_bits(m0, m1, s + 49);
+        const int n = lo ? 16 + __ffs(lo) : 48 + __ffs(hi);
+        for (int m = 0; m < n && nu < MM_UNITS; m += 16) {
+          if (lane == 0) out[nu] = (s + m) | (min(16, n - m) << 7) | (s << 12) | (n << 19);
+          ++nu;
+        }
+        s += n;
+      }
+    }
+  }
+  if (lane < MM_UNIT_STRIDE - MM_UNITS) out[MM_UNITS + lane] = lane == 0 ? nu : 0;
+}
+
+extern "C" size_t gdmae_sra_bin_units_bytes(int64_t N) { return (size_t)((N + MM_BIN - 1) / MM_BIN + 1) * MM_UNIT_STRIDE * 4; }
+
+// bin_units (gdmae_sra_bin_units_bytes(N), 16-byte aligned) <- work units of the CSR rows described by row_info (N,4)
+extern "C" int gdmae_sra_bin_units(const int32_t* row_info, int64_t N, int32_t* bin_units, void* stream_) {
+  GDMAE_CHECK_ARG(N >= 0 && N < (1ll << 27) && ((uintptr_t)row_info % 16) == 0 && ((uintptr_t)bin_units % 16) == 0);
+  if (N == 0) return GDMAE_OK;
+  const long long nbins = (N + MM_BIN - 1) / MM_BIN;
+  sra_bin_units_kernel<<<(unsigned)((nbins * 32 + 255) / 256), 256, 0, (cudaStream_t)stream_>>>((const int4*)row_info, (int)N, bin_units);
+  GDMAE_LAUNCH_CHECK();
+  return GDMAE_OK;
 }
 
 static int mm_attrs() {
@@ -897,16 +905,17 @@ static int mm_attrs() {
 }
 
 // Tensor-core variant of gdmae_sra_attention_fwd for bf16 q/k/v: qkv (N, 3d) bf16, otherwise the same arguments and outputs.
-extern "C" int gdmae_sra_attention_fwd_tc(const void* qkv_bf16, const float* lut, const int32_t* row_info, int64_t N, int d, int nhead,
-                                          const float* tau, float tau_min, const float* bv, int io_bf16, void* out, float* lse,
-                                          void* stream_) {
+extern "C" int gdmae_sra_attention_fwd_tc(const void* qkv_bf16, const float* lut, const int32_t* row_info, const int32_t* bin_units,
+                                          int64_t N, int d, int nhead, const float* tau, float tau_min, const float* bv, int io_bf16,
+                                          void* out, float* lse, void* stream_) {
+  GDMAE_CHECK_ARG(bin_units != nullptr && ((uintptr_t)bin_units % 16) == 0);
   GDMAE_CHECK_ARG(N >= 0 && N < (1ll << 27) && nhead == 8 && (d == 128 || d == 256));
   GDMAE_CHECK_ARG(((uintptr_t)row_info % 16) == 0 && ((uintptr_t)qkv_bf16 % 16) == 0 && ((uintptr_t)lut % 8) == 0);
   GDMAE_CHECK_ARG(bv == nullptr || ((uintptr_t)bv % 8) == 0);
   if (N == 0) return GDMAE_OK;
   int rc = mm_attrs();
   if (rc) return rc;
-  MmArgs a{(const bf16*)qkv_bf16, lut, (const int4*)row_info, tau, bv, tau_min, (int)N, d, io_bf16};
+  MmArgs a{(const bf16*)qkv_bf16, lut, (const int4*)row_info, bin_units, tau, bv, tau_min, (int)N, d, io_bf16};
   cudaStream_t st = (cudaStream_t)stream_;
   // one CTA per SM; 148 is a multiple of the 2 (d = 128) and 4 (d = 256) channel slices
   if (d == 128) sra_fwd_mma_kernel<16><<<GDMAE_NUM_SMS, MM_THREADS, MM_SMEM_BYTES, st>>>(a, out, lse);
@@ -918,16 +927,17 @@ extern "C" int gdmae_sra_attention_fwd_tc(const void* qkv_bf16, const float* lut
 // Tensor-core backward for bf16 tensors: qkv (N,3d), dout (N,d) and dqkv (N,3d) are bf16; lse (N,8) from the forward;
 // dtau_sum (1, double, caller zeroes) accumulates sum dS*S as gdmae_sra_attention_bwd does.  The value bias and the
 // forward output are not needed (sum_j P dP replaces dO.(o - bv)).
-extern "C" int gdmae_sra_attention_bwd_tc(const void* qkv_bf16, const float* lut, const int32_t* row_info, int64_t N, int d, int nhead,
-                                          const float* tau, float tau_min, const float* lse, const void* dout_bf16, void* dqkv_bf16,
-                                          double* dtau_sum, void* stream_) {
+extern "C" int gdmae_sra_attention_bwd_tc(const void* qkv_bf16, const float* lut, const int32_t* row_info, const int32_t* bin_units,
+                                          int64_t N, int d, int nhead, const float* tau, float tau_min, const float* lse,
+                                          const void* dout_bf16, void* dqkv_bf16, double* dtau_sum, void* stream_) {
+  GDMAE_CHECK_ARG(bin_units != nullptr && ((uintptr_t)bin_units % 16) == 0);
   GDMAE_CHECK_ARG(N >= 0 && N < (1ll << 27) && nhead == 8 && (d == 128 || d == 256));
   GDMAE_CHECK_ARG(((uintptr_t)row_info % 16) == 0 && ((uintptr_t)qkv_bf16 % 16) == 0 && ((uintptr_t)lut % 8) == 0);
   GDMAE_CHECK_ARG(((uintptr_t)dout_bf16 % 16) == 0 && ((uintptr_t)dqkv_bf16 % 16) == 0 && ((uintptr_t)lse % 4) == 0);
   if (N == 0) return GDMAE_OK;
   int rc = mm_attrs();
   if (rc) return rc;
-  MbArgs a{(const bf16*)qkv_bf16, lut, (const int4*)row_info, tau, lse, (const bf16*)dout_bf16, (bf16*)dqkv_bf16, dtau_sum, tau_min,
+  MbArgs a{(const bf16*)qkv_bf16, lut, (const int4*)row_info, bin_units, tau, lse, (const bf16*)dout_bf16, (bf16*)dqkv_bf16, dtau_sum, tau_min,
            (int)N, d};
   cudaStream_t st = (cudaStream_t)stream_;
   if (d == 128) sra_bwd_mma_kernel<16><<<GDMAE_NUM_SMS, MM_THREADS, MB_SMEM_BYTES, st>>>(a);

@@ -189,7 +189,7 @@ def gemm_mode():
 
 
 _VP = ctypes.c_void_p
-_EL_PTRS = ["x", "xg_in", "pos_table", "row_info", "pos_of_token",
+_EL_PTRS = ["x", "xg_in", "pos_table", "row_info", "bin_units", "pos_of_token",
             "w_in", "b_in", "tau", "w_o", "b_o", "g1", "be1", "w1", "b1", "w2", "b2", "g2", "be2",
             "w_in_g", "w_o_g", "w1_g", "w2_g",
             "xg", "qkv", "lut", "o", "lse", "a", "x1", "x1g", "mean1", "rstd1", "h", "g", "f", "mean2", "rstd2", "x2", "x2g",
@@ -233,6 +233,10 @@ class EncoderLayerFunction(torch.autograd.Function):
         A.x, A.pos_table, A.row_info, A.pos_of_token = x.data_ptr(), pos_table.data_ptr(), table.row_info.data_ptr(), \
             table.pos_of_token.data_ptr()
         keep = [x, pos_table, table.row_info, table.pos_of_token]
+        if tc:
+            units = table.bin_units()
+            A.bin_units = units.data_ptr()
+            keep.append(units)
         for name, p in zip(_PARAM_NAMES, params):
             setattr(A, name, p.data_ptr())
         for name, p in zip(("w_in_g", "w_o_g", "w1_g", "w2_g"), (params[0], params[3], params[7], params[9])):

@@ -228,7 +228,18 @@ class WindowTable:
     """Window bookkeeping of one shift (replaces batch_win_inds / coors_in_win / drop levels /
     flat2win_inds / key masks / pos dict of SSTInputLayer.forward, spt_backbone.py:106-135)."""
     __slots__ = ("win_of_token", "pos_of_token", "inner", "level", "win_mask", "win_off", "win_tok", "lvl_rank",
-                 "lvl_counts", "row_info", "n_windows", "nWx", "nWy", "N", "_pos_long")
+                 "lvl_counts", "row_info", "n_windows", "nWx", "nWy", "N", "_pos_long", "_bin_units")
+
+    def bin_units(self):
+        """work units of the tensor-core SRA kernels (gdmae_sra_bin_units), built on first use and cached: one table
+        serves two encoder layers, forward and backward"""
+        if getattr(self, "_bin_units", None) is None:
+            lib = L.lib()
+            n = lib.gdmae_sra_bin_units_bytes(L.i64(self.N))
+            u = torch.empty((n // 4,), dtype=I32, device=self.row_info.device)
+            L.check(lib.gdmae_sra_bin_units(L.P(self.row_info), L.i64(self.N), L.P(u), L.stream()), "gdmae_sra_bin_units")
+            self._bin_units = u
+        return self._bin_units
 
     def pos_long(self):
         """in-window cell per token as int64 (index for torch gathers), cached"""
@@ -255,6 +266,7 @@ def window_table(indices, B, H, W, shifted):
     t.lvl_counts = torch.empty((3,), dtype=I32, device=dev)
     t.row_info = torch.empty((max(N, 1), 4), dtype=I32, device=dev)[:N]
     t._pos_long = None
+    t._bin_units = None
     lib = L.lib()
     ws = L.workspace(lib.gdmae_window_table_workspace_bytes(L.i64(nW)), dev)
     L.check(lib.gdmae_window_table(L.P(indices), L.i64(N), B, H, W, int(bool(shifted)), L.P(t.win_of_token),
@@ -278,7 +290,7 @@ def sra_fwd(qkv, lut, tau, table, tau_min, nhead, bv=None, out_dtype=torch.float
     # algorithmic bytes (SURVEY.md 8d, a18 minus projections): N*d*(3*s_in + s_out) + N*8
     with L.timed(f"sra_fwd_d{d}", N * d * (3 * qkv.element_size() + out.element_size()) + N * 8 * 4):
         if qkv.dtype == torch.bfloat16:
-            L.check(L.lib().gdmae_sra_attention_fwd_tc(L.P(qkv), L.P(lut), L.P(table.row_info), L.i64(N), d, nhead, L.P(tau),
+            L.check(L.lib().gdmae_sra_attention_fwd_tc(L.P(qkv), L.P(lut), L.P(table.row_info), L.P(table.bin_units()), L.i64(N), d, nhead, L.P(tau),
                                                        L.f32(tau_min), L.P(bv), _DT[out_dtype], L.P(out), L.P(lse), L.stream()),
                     "gdmae_sra_attention_fwd_tc")
         else:
@@ -298,7 +310,7 @@ def sra_bwd(qkv, lut, tau, table, tau_min, nhead, out, lse, dout, bv=None, io_dt
         assert dout.dtype == torch.bfloat16
         dqkv = torch.empty((N, d3), dtype=torch.bfloat16, device=qkv.device)
         with L.timed(f"sra_bwd_d{d}", N * d * (6 + 2 + 6) + N * 8 * 4):
-            L.check(L.lib().gdmae_sra_attention_bwd_tc(L.P(qkv), L.P(lut), L.P(table.row_info), L.i64(N), d, nhead, L.P(tau),
+            L.check(L.lib().gdmae_sra_attention_bwd_tc(L.P(qkv), L.P(lut), L.P(table.row_info), L.P(table.bin_units()), L.i64(N), d, nhead, L.P(tau),
                                                        L.f32(tau_min), L.P(lse), L.P(dout), L.P(dqkv), L.P(dtau_sum), L.stream()),
                     "gdmae_sra_attention_bwd_tc")
         return dqkv, dtau_sum

@@ -146,14 +146,19 @@ int gdmae_sra_attention_fwd(const float* qkv, const float* lut, const int32_t* r
                             void* stream);
 /* same operator for bf16 q/k/v (qkv_bf16 (N,3d) bf16): QK^T and PV on the tensor cores (bf16 mma, fp32 accumulate,
  * softmax in fp32), persistent cp.async-pipelined kernel; other arguments and outputs as above */
-int gdmae_sra_attention_fwd_tc(const void* qkv_bf16, const float* lut, const int32_t* row_info, int64_t N, int d, int nhead,
-                               const float* tau, float tau_min, const float* bv, int io_bf16, void* out, float* lse,
-                               void* stream);
+int gdmae_sra_attention_fwd_tc(const void* qkv_bf16, const float* lut, const int32_t* row_info, const int32_t* bin_units,
+                               int64_t N, int d, int nhead, const float* tau, float tau_min, const float* bv, int io_bf16,
+                               void* out, float* lse, void* stream);
+/* work units of the tensor-core kernels, built once per window table: bin_units (gdmae_sra_bin_units_bytes(N) bytes,
+ * 16-byte aligned) <- for every 64-row bin of the CSR rows the packed (query tile, key range) units of the windows that
+ * start in the bin (a run of whole small windows totalling <= 16 rows, or a 16-row chunk of a larger window) */
+size_t gdmae_sra_bin_units_bytes(int64_t N);
+int gdmae_sra_bin_units(const int32_t* row_info, int64_t N, int32_t* bin_units, void* stream);
 /* tensor-core backward for bf16 tensors: qkv (N,3d), dout (N,d), dqkv (N,3d) all bf16; needs neither the forward
  * output nor the value bias */
-int gdmae_sra_attention_bwd_tc(const void* qkv_bf16, const float* lut, const int32_t* row_info, int64_t N, int d, int nhead,
-                               const float* tau, float tau_min, const float* lse, const void* dout_bf16, void* dqkv_bf16,
-                               double* dtau_sum, void* stream);
+int gdmae_sra_attention_bwd_tc(const void* qkv_bf16, const float* lut, const int32_t* row_info, const int32_t* bin_units,
+                               int64_t N, int d, int nhead, const float* tau, float tau_min, const float* lse,
+                               const void* dout_bf16, void* dqkv_bf16, double* dtau_sum, void* stream);
 int gdmae_sra_attention_bwd(const float* qkv, const float* lut, const int32_t* row_info, int64_t N, int d, int nhead,
                             const float* tau, float tau_min, const float* bv, int io_bf16, const void* out,
                             const float* lse, const float* dout, void* dqkv, double* dtau_sum, float* work_D,
@@ -236,6 +241,7 @@ typedef struct gdmae_encoder_layer_args {
   const void* xg_in;         /* (N,d) op copy of x handed over by the producer, or NULL */
   const float* pos_table;    /* (64,d) */
   const int32_t* row_info;   /* (N,4) from gdmae_window_table */
+  const int32_t* bin_units;  /* from gdmae_sra_bin_units; required when sra_tensor_cores */
   const uint8_t* pos_of_token;
   /* parameters: fp32 masters and op-dtype copies of the four weights (same pointers when fp32) */
   const float *w_in, *b_in, *tau, *w_o, *b_o, *g1, *be1, *w1, *b1, *w2, *b2, *g2, *be2;

@@ -123,7 +123,7 @@ def main():
         fn = L.lib().gdmae_sra_attention_fwd_tc
 
         def fwd_tc():
-            L.check(fn(L.P(qkv_b), L.P(lut), L.P(t.row_info), L.i64(N), d, 8, L.P(tau), L.f32(0.01), None, 1, L.P(out_b), L.P(lse), st()),
+            L.check(fn(L.P(qkv_b), L.P(lut), L.P(t.row_info), L.P(t.bin_units()), L.i64(N), d, 8, L.P(tau), L.f32(0.01), None, 1, L.P(out_b), L.P(lse), st()),
                     "tc")
 
         tf = timeit(fwd_tc, flush)
