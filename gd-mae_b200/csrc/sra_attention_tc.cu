@@ -35,7 +35,25 @@
 #define MM_SLICE 64
 #define MM_PITCH 72            // bf16 elements per smem row (144 B)
 #define MM_THREADS 512
-#define MM_GROUP 256           // threads per role
+#ifndef MM_STAGER_WARPS
+#define MM_STAGER_WARPS 6      // forward: warps that copy and stage bins; the other 16 - MM_STAGER_WARPS run the MMAs
+#endif
+// forward: heads one math warp runs interleaved per work entry.  Measured (tools/sweep_sra_tc.py, r1): two heads win for the
+// 16-channel heads of d = 128 (28.7 vs 30.7 us), one head for the 32-channel heads of d = 256 (78 vs 89 us: the two-head body
+// sits at the 128-register cap and halves the entries the math warps can share)
+#ifdef MM_HPE
+#define MM_HEADS_PER_ENTRY(HD) (MM_HPE)
+#else
+#define MM_HEADS_PER_ENTRY(HD) ((HD) == 16 ? 2 : 1)
+#endif
+#ifndef MM_STAGE_ILP
+#define MM_STAGE_ILP 4         // forward: rows a stager thread keeps in flight
+#endif
+#ifndef MF_THREADS
+#define MF_THREADS 512         // forward CTA size (the register cap follows: 65536 / MF_THREADS)
+#endif
+#define MM_GROUP (32 * MM_STAGER_WARPS)   // stager threads (forward)
+#define MM_MATH_WARPS (MF_THREADS / 32 - MM_STAGER_WARPS)
 #define MM_STAGES 3
 #define MM_NINFO 5
 #define MM_UNITS 48
@@ -67,6 +85,27 @@ __device__ __forceinline__ void mm_commit() { asm volatile("cp.async.commit_grou
 template <int N_>
 __device__ __forceinline__ void mm_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
 __device__ __forceinline__ void mm_bar_stagers() { asm volatile("bar.sync 1, %0;" ::"n"(MM_GROUP) : "memory"); }
+
+// ---- mbarriers (shared::cta): producer/consumer hand-over of stage buffers without CTA-wide barriers
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+// waits for the completion of the phase with the given parity.  try_wait carries a suspend-time hint: the warp sleeps in
+// hardware until the phase completes (a polling loop without it was measured to burn a third of the SM's issue slots and
+// starve the producer warps).  Bounded (about a second) so that a logic error ends in wrong results that the tests catch,
+// not in a hung GPU.
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+  for (int spin = 0; spin < 50000; ++spin) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(addr), "r"(parity), "r"(20000u) : "memory");
+    if (ok) return;
+  }
+}
 
 __device__ __forceinline__ void ldsm_x4(unsigned (&r)[4], const bf16* p) {
   unsigned sa = (unsigned)__cvta_generic_to_shared(p);
@@ -137,145 +176,264 @@ __device__ __forceinline__ unsigned mm_bits(unsigned long long m0, unsigned long
   return (unsigned)v;
 }
 
-// Staging of one 8-channel group of a q or k row, in place: + LUT (packed bf16 add), L2 norm of the head in fp32
-// (the 8-channel groups of a head sit in adjacent lanes: 2 lanes for 16-channel heads, 4 for 32), scale, back to bf16.
-// Returns 1/|x| of the head.
-template <int HD>
-__device__ __forceinline__ float mm_stage_task(bf16* p, const bf16* lut_row, float extra_scale, bool valid) {
-  uint4 raw = *reinterpret_cast<const uint4*>(p);
-  const uint4 lr = *reinterpret_cast<const uint4*>(lut_row);
-  unsigned w[4] = {raw.x, raw.y, raw.z, raw.w};
-  const unsigned l[4] = {lr.x, lr.y, lr.z, lr.w};
-  float x[8];
-  float ss = 0.f;
+// Staging of U 8-channel groups (U rows, same channels) of q or k, in place: + LUT (packed bf16 add), L2 norm of the
+// head in fp32 (the 8-channel groups of a head sit in adjacent lanes: 2 lanes for 16-channel heads, 4 for 32), scale,
+// back to bf16.  All loads come first and all stores last so that the U dependency chains overlap.  rn[u] = 1/|x|.
+template <int HD, int U>
+__device__ __forceinline__ void mm_stage_tasks(bf16* const (&p)[U], const bf16* const (&lut_row)[U], float extra_scale,
+                                               const bool (&valid)[U], float (&rn)[U]) {
+  uint4 raw[U], lr[U];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    __nv_bfloat162 sum = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]), *reinterpret_cast<const __nv_bfloat162*>(&l[i]));
-    const unsigned u = *reinterpret_cast<unsigned*>(&sum);
-    x[2 * i] = __uint_as_float(u << 16);
-    x[2 * i + 1] = __uint_as_float(u & 0xffff0000u);
-    ss = fmaf(x[2 * i], x[2 * i], ss);
-    ss = fmaf(x[2 * i + 1], x[2 * i + 1], ss);
+  for (int u = 0; u < U; ++u) {
+    raw[u] = *reinterpret_cast<const uint4*>(p[u]);
+    lr[u] = *reinterpret_cast<const uint4*>(lut_row[u]);
   }
-  ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-  if (HD == 32) ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-  float rn;
-  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rn) : "f"(fmaxf(ss, 1e-24f)));
-  const float f = rn * extra_scale;
-  if (valid) {
-    uint4 o;
-    o.x = pack_bf16(x[0] * f, x[1] * f);
-    o.y = pack_bf16(x[2] * f, x[3] * f);
-    o.z = pack_bf16(x[4] * f, x[5] * f);
-    o.w = pack_bf16(x[6] * f, x[7] * f);
-    *reinterpret_cast<uint4*>(p) = o;
+  float x[U][8], ss[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const unsigned w[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+    const unsigned l[4] = {lr[u].x, lr[u].y, lr[u].z, lr[u].w};
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 sum = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]), *reinterpret_cast<const __nv_bfloat162*>(&l[i]));
+      const unsigned v = *reinterpret_cast<unsigned*>(&sum);
+      x[u][2 * i] = __uint_as_float(v << 16);
+      x[u][2 * i + 1] = __uint_as_float(v & 0xffff0000u);
+      s0 = fmaf(x[u][2 * i], x[u][2 * i], s0);
+      s1 = fmaf(x[u][2 * i + 1], x[u][2 * i + 1], s1);
+    }
+    ss[u] = s0 + s1;
   }
-  return rn;
+#pragma unroll
+  for (int u = 0; u < U; ++u) ss[u] += __shfl_xor_sync(0xffffffffu, ss[u], 1);
+  if (HD == 32) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) ss[u] += __shfl_xor_sync(0xffffffffu, ss[u], 2);
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaxf(ss[u], 1e-24f)));
+    rn[u] = r;
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const float f = rn[u] * extra_scale;
+    if (valid[u]) {
+      uint4 o;
+      o.x = pack_bf16(x[u][0] * f, x[u][1] * f);
+      o.y = pack_bf16(x[u][2] * f, x[u][3] * f);
+      o.z = pack_bf16(x[u][4] * f, x[u][5] * f);
+      o.w = pack_bf16(x[u][6] * f, x[u][7] * f);
+      *reinterpret_cast<uint4*>(p[u]) = o;
+    }
+  }
 }
 
-// One (unit, head) on one warp: S = Q K^T, masked softmax, O = P V, for NT2 8-key tiles (NT2 even).
-template <int HD, int NT2>
+// The staging pass of one bin: NT threads (index t) own the 8-channel group t & 7 of array (t >> 3) & 1 (q or k) and walk
+// the rows U * NT / 16 at a time.  srq / srk (nullable): 1/|q|, 1/|k| per (row, head) for the backward.
+template <int HD, int U, int NT>
+__device__ __forceinline__ void mm_stage_bin(bf16* sq, const bf16* slut, const int4* inf, int R, float qscale, int t, float* srq,
+                                             float* srk) {
+  constexpr int RP = NT / 16;                                 // rows per sub-pass
+  const int c8 = t & 7, part = (t >> 3) & 1, rsub = t >> 4;
+  const float sc = part == 0 ? qscale : 1.f;
+  bf16* base = sq + part * MM_ARR + 8 * c8;
+  const bf16* lutc = slut + part * MM_SLICE + 8 * c8;
+  float* srn = part == 0 ? srq : srk;
+  for (int rb = 0; rb < R; rb += U * RP) {                    // uniform trip count: the tasks shuffle inside the warp
+    bf16* p[U];
+    const bf16* l[U];
+    bool valid[U];
+    float rn[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int r = rb + rsub + u * RP;
+      valid[u] = r < R;
+      const int c = valid[u] ? r : 0;
+      p[u] = base + c * MM_PITCH;
+      l[u] = lutc + inf[c].w * 2 * MM_SLICE;
+    }
+    mm_stage_tasks<HD, U>(p, l, sc, valid, rn);
+    if (srn != nullptr && (c8 & (HD / 8 - 1)) == 0) {
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (valid[u]) srn[(rb + rsub + u * RP) * 4 + c8 / (HD / 8)] = rn[u];
+    }
+  }
+}
+
+// One unit and NH adjacent heads on one warp: S = Q K^T, masked softmax, O = P V, for NT2 8-key tiles (NT2 even).  The NH
+// heads are independent instruction streams over the same rows and masks; every step is written as a loop over the heads
+// so that their dependency chains (ldmatrix -> mma -> shuffle -> exp2 -> mma) overlap in the one warp.
+template <int HD, int NT2, int NH>
 __device__ __forceinline__ void mm_unit(const MmArgs& a, const bf16* sq, const bf16* sk, const bf16* sv, int q0, int qn, int k0,
                                         int ch, int4 recA, int4 recB, int kbase, int lane, long long out_col, int lse_col,
                                         void* __restrict__ out, float* __restrict__ lse) {
   constexpr int KS = HD / 16, ND = HD / 8;
   const int g = lane >> 2, t = lane & 3;
   const int loA = recA.y - kbase, wA = recA.z - recA.y, loB = recB.y - kbase, wB = recB.z - recB.y;
-  unsigned qa[KS][4];
+  unsigned qa[NH][KS][4];
 #pragma unroll
   for (int ks = 0; ks < KS; ++ks)
-    ldsm_x4(qa[ks], sq + (q0 + (lane & 7) + 8 * ((lane >> 3) & 1)) * MM_PITCH + ch + 16 * ks + 8 * (lane >> 4));
-  float c[NT2][4];
 #pragma unroll
-  for (int nt = 0; nt < NT2; ++nt) c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;
+    for (int hh = 0; hh < NH; ++hh)
+      ldsm_x4(qa[hh][ks], sq + (q0 + (lane & 7) + 8 * ((lane >> 3) & 1)) * MM_PITCH + ch + hh * HD + 16 * ks + 8 * (lane >> 4));
+  float c[NH][NT2][4];
+#pragma unroll
+  for (int hh = 0; hh < NH; ++hh)
+#pragma unroll
+    for (int nt = 0; nt < NT2; ++nt) c[hh][nt][0] = c[hh][nt][1] = c[hh][nt][2] = c[hh][nt][3] = 0.f;
 #pragma unroll
   for (int np = 0; np < NT2 / 2; ++np) {
-    unsigned kb[4];
     if (KS == 2) {
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        ldsm_x4(kb, sk + (k0 + 8 * (2 * np + u) + (lane & 7)) * MM_PITCH + ch + 8 * (lane >> 3));
-        mma_bf16(c[2 * np + u], qa[0], kb[0], kb[1]);
-        mma_bf16(c[2 * np + u], qa[KS - 1], kb[2], kb[3]);
+        unsigned kb[NH][4];
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh)
+          ldsm_x4(kb[hh], sk + (k0 + 8 * (2 * np + u) + (lane & 7)) * MM_PITCH + ch + hh * HD + 8 * (lane >> 3));
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh) mma_bf16(c[hh][2 * np + u], qa[hh][0], kb[hh][0], kb[hh][1]);
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh) mma_bf16(c[hh][2 * np + u], qa[hh][KS - 1], kb[hh][2], kb[hh][3]);
       }
     } else {
-      ldsm_x4(kb, sk + (k0 + 16 * np + 8 * (lane >> 4) + (lane & 7)) * MM_PITCH + ch + 8 * ((lane >> 3) & 1));
-      mma_bf16(c[2 * np], qa[0], kb[0], kb[1]);
-      mma_bf16(c[2 * np + 1], qa[0], kb[2], kb[3]);
+      unsigned kb[NH][4];
+#pragma unroll
+      for (int hh = 0; hh < NH; ++hh)
+        ldsm_x4(kb[hh], sk + (k0 + 16 * np + 8 * (lane >> 4) + (lane & 7)) * MM_PITCH + ch + hh * HD + 8 * ((lane >> 3) & 1));
+#pragma unroll
+      for (int hh = 0; hh < NH; ++hh) {
+        mma_bf16(c[hh][2 * np], qa[hh][0], kb[hh][0], kb[hh][1]);
+        mma_bf16(c[hh][2 * np + 1], qa[hh][0], kb[hh][2], kb[hh][3]);
+      }
     }
   }
-  // block-diagonal mask + row max
-  float mx0 = -INFINITY, mx1 = -INFINITY;
+  // block-diagonal mask (shared by the heads) + row max
+  float mx0[NH], mx1[NH];
+#pragma unroll
+  for (int hh = 0; hh < NH; ++hh) mx0[hh] = mx1[hh] = -INFINITY;
   const int ka = 2 * t - loA, kb_ = 2 * t - loB;
 #pragma unroll
   for (int nt = 0; nt < NT2; ++nt) {
-    if ((unsigned)(ka + 8 * nt) >= (unsigned)wA) c[nt][0] = -INFINITY;
-    if ((unsigned)(ka + 8 * nt + 1) >= (unsigned)wA) c[nt][1] = -INFINITY;
-    if ((unsigned)(kb_ + 8 * nt) >= (unsigned)wB) c[nt][2] = -INFINITY;
-    if ((unsigned)(kb_ + 8 * nt + 1) >= (unsigned)wB) c[nt][3] = -INFINITY;
-    mx0 = fmaxf(mx0, fmaxf(c[nt][0], c[nt][1]));
-    mx1 = fmaxf(mx1, fmaxf(c[nt][2], c[nt][3]));
-  }
-  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-  float l0 = 0.f, l1 = 0.f;
+    const bool m0 = (unsigned)(ka + 8 * nt) >= (unsigned)wA, m1 = (unsigned)(ka + 8 * nt + 1) >= (unsigned)wA;
+    const bool m2 = (unsigned)(kb_ + 8 * nt) >= (unsigned)wB, m3 = (unsigned)(kb_ + 8 * nt + 1) >= (unsigned)wB;
 #pragma unroll
-  for (int nt = 0; nt < NT2; ++nt) {
-    c[nt][0] = fast_exp2(c[nt][0] - mx0); c[nt][1] = fast_exp2(c[nt][1] - mx0);
-    c[nt][2] = fast_exp2(c[nt][2] - mx1); c[nt][3] = fast_exp2(c[nt][3] - mx1);
-    l0 += c[nt][0] + c[nt][1];
-    l1 += c[nt][2] + c[nt][3];
-  }
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  float o[ND][4];
-#pragma unroll
-  for (int nd = 0; nd < ND; ++nd) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.f;
-#pragma unroll
-  for (int kt = 0; kt < NT2 / 2; ++kt) {
-    const unsigned pa[4] = {pack_bf16(c[2 * kt][0], c[2 * kt][1]), pack_bf16(c[2 * kt][2], c[2 * kt][3]),
-                            pack_bf16(c[2 * kt + 1][0], c[2 * kt + 1][1]), pack_bf16(c[2 * kt + 1][2], c[2 * kt + 1][3])};
-#pragma unroll
-    for (int np = 0; np < ND / 2; ++np) {
-      unsigned vb[4];
-      ldsm_x4_t(vb, sv + (k0 + 16 * kt + (lane & 7) + 8 * ((lane >> 3) & 1)) * MM_PITCH + ch + 16 * np + 8 * (lane >> 4));
-      mma_bf16(o[2 * np], pa, vb[0], vb[1]);
-      mma_bf16(o[2 * np + 1], pa, vb[2], vb[3]);
+    for (int hh = 0; hh < NH; ++hh) {
+      if (m0) c[hh][nt][0] = -INFINITY;
+      if (m1) c[hh][nt][1] = -INFINITY;
+      if (m2) c[hh][nt][2] = -INFINITY;
+      if (m3) c[hh][nt][3] = -INFINITY;
+      mx0[hh] = fmaxf(mx0[hh], fmaxf(c[hh][nt][0], c[hh][nt][1]));
+      mx1[hh] = fmaxf(mx1[hh], fmaxf(c[hh][nt][2], c[hh][nt][3]));
     }
   }
-  float2 bias[ND];
 #pragma unroll
-  for (int nd = 0; nd < ND; ++nd)
-    bias[nd] = a.bv ? __ldg(reinterpret_cast<const float2*>(a.bv + out_col + 8 * nd + 2 * t)) : make_float2(0.f, 0.f);
+  for (int o_ = 1; o_ <= 2; o_ <<= 1)
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    if (g + 8 * half < qn) {
-      const int tok = half ? recB.x : recA.x;
-      const float il = __fdividef(1.f, half ? l1 : l0);
-      const long long e0 = (long long)tok * a.d + out_col + 2 * t;
+    for (int hh = 0; hh < NH; ++hh) {
+      mx0[hh] = fmaxf(mx0[hh], __shfl_xor_sync(0xffffffffu, mx0[hh], o_));
+      mx1[hh] = fmaxf(mx1[hh], __shfl_xor_sync(0xffffffffu, mx1[hh], o_));
+    }
+  float l0[NH], l1[NH];
 #pragma unroll
-      for (int nd = 0; nd < ND; ++nd) {
-        const float x0 = fmaf(o[nd][2 * half], il, bias[nd].x), x1 = fmaf(o[nd][2 * half + 1], il, bias[nd].y);
-        if (a.out_bf16) *reinterpret_cast<unsigned*>((bf16*)out + e0 + 8 * nd) = pack_bf16(x0, x1);
-        else *reinterpret_cast<float2*>((float*)out + e0 + 8 * nd) = make_float2(x0, x1);
+  for (int hh = 0; hh < NH; ++hh) l0[hh] = l1[hh] = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < NT2; ++nt)
+#pragma unroll
+    for (int hh = 0; hh < NH; ++hh) {
+      c[hh][nt][0] = fast_exp2(c[hh][nt][0] - mx0[hh]); c[hh][nt][1] = fast_exp2(c[hh][nt][1] - mx0[hh]);
+      c[hh][nt][2] = fast_exp2(c[hh][nt][2] - mx1[hh]); c[hh][nt][3] = fast_exp2(c[hh][nt][3] - mx1[hh]);
+      l0[hh] += c[hh][nt][0] + c[hh][nt][1];
+      l1[hh] += c[hh][nt][2] + c[hh][nt][3];
+    }
+#pragma unroll
+  for (int o_ = 1; o_ <= 2; o_ <<= 1)
+#pragma unroll
+    for (int hh = 0; hh < NH; ++hh) {
+      l0[hh] += __shfl_xor_sync(0xffffffffu, l0[hh], o_);
+      l1[hh] += __shfl_xor_sync(0xffffffffu, l1[hh], o_);
+    }
+  float o[NH][ND][4];
+#pragma unroll
+  for (int hh = 0; hh < NH; ++hh)
+#pragma unroll
+    for (int nd = 0; nd < ND; ++nd) o[hh][nd][0] = o[hh][nd][1] = o[hh][nd][2] = o[hh][nd][3] = 0.f;
+#pragma unroll
+  for (int kt = 0; kt < NT2 / 2; ++kt) {
+    unsigned pa[NH][4];
+#pragma unroll
+    for (int hh = 0; hh < NH; ++hh) {
+      pa[hh][0] = pack_bf16(c[hh][2 * kt][0], c[hh][2 * kt][1]);
+      pa[hh][1] = pack_bf16(c[hh][2 * kt][2], c[hh][2 * kt][3]);
+      pa[hh][2] = pack_bf16(c[hh][2 * kt + 1][0], c[hh][2 * kt + 1][1]);
+      pa[hh][3] = pack_bf16(c[hh][2 * kt + 1][2], c[hh][2 * kt + 1][3]);
+    }
+#pragma unroll
+    for (int np = 0; np < ND / 2; ++np) {
+      unsigned vb[NH][4];
+#pragma unroll
+      for (int hh = 0; hh < NH; ++hh)
+        ldsm_x4_t(vb[hh], sv + (k0 + 16 * kt + (lane & 7) + 8 * ((lane >> 3) & 1)) * MM_PITCH + ch + hh * HD + 16 * np + 8 * (lane >> 4));
+#pragma unroll
+      for (int hh = 0; hh < NH; ++hh) {
+        mma_bf16(o[hh][2 * np], pa[hh], vb[hh][0], vb[hh][1]);
+        mma_bf16(o[hh][2 * np + 1], pa[hh], vb[hh][2], vb[hh][3]);
       }
-      // natural-log lse of the scores S = cos / tau (the backward kernels expect it)
-      if (t == 0) lse[(long long)tok * 8 + lse_col] = ((half ? mx1 : mx0) + __log2f(half ? l1 : l0)) * 0.6931471805599453f;
+    }
+  }
+#pragma unroll
+  for (int hh = 0; hh < NH; ++hh) {
+    float2 bias[ND];
+#pragma unroll
+    for (int nd = 0; nd < ND; ++nd)
+      bias[nd] = a.bv ? __ldg(reinterpret_cast<const float2*>(a.bv + out_col + hh * HD + 8 * nd + 2 * t)) : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      if (g + 8 * half < qn) {
+        const int tok = half ? recB.x : recA.x;
+        const float il = __fdividef(1.f, half ? l1[hh] : l0[hh]);
+        const long long e0 = (long long)tok * a.d + out_col + hh * HD + 2 * t;
+#pragma unroll
+        for (int nd = 0; nd < ND; ++nd) {
+          const float x0 = fmaf(o[hh][nd][2 * half], il, bias[nd].x), x1 = fmaf(o[hh][nd][2 * half + 1], il, bias[nd].y);
+          if (a.out_bf16) *reinterpret_cast<unsigned*>((bf16*)out + e0 + 8 * nd) = pack_bf16(x0, x1);
+          else *reinterpret_cast<float2*>((float*)out + e0 + 8 * nd) = make_float2(x0, x1);
+        }
+        // natural-log lse of the scores S = cos / tau (the backward kernels expect it)
+        if (t == 0)
+          lse[(long long)tok * 8 + lse_col + hh] = ((half ? mx1[hh] : mx0[hh]) + __log2f(half ? l1[hh] : l0[hh])) * 0.6931471805599453f;
+      }
     }
   }
 }
 
+#ifdef MM_PROFILE
+// development build only (tools/sweep_sra_tc.py -DMM_PROFILE): cycle counters of one stager warp and one math warp per CTA
+__device__ unsigned long long g_mm_prof[16];
+#define MM_PROF_T(var) const long long var = clock64()
+#define MM_PROF_ADD(slot, cycles) do { if (lane == 0) atomicAdd(&g_mm_prof[slot], (unsigned long long)(cycles)); } while (0)
+extern "C" int gdmae_sra_prof_read(unsigned long long* out16, int reset) {
+  cudaMemcpyFromSymbol(out16, g_mm_prof, sizeof(g_mm_prof));
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_mm_prof, z, sizeof(z)); }
+  return 0;
+}
+#else
+#define MM_PROF_T(var)
+#define MM_PROF_ADD(slot, cycles)
+#endif
+
 template <int HD>
-__global__ void __launch_bounds__(MM_THREADS, 1) sra_fwd_mma_kernel(MmArgs a, void* __restrict__ out, float* __restrict__ lse) {
+__global__ void __launch_bounds__(MF_THREADS, 1) sra_fwd_mma_kernel(MmArgs a, void* __restrict__ out, float* __restrict__ lse) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   bf16* slut = (bf16*)smem_raw;                               // [64][128]: q part | k part of this slice
   bf16* sdata = slut + 64 * 2 * MM_SLICE;                     // MM_STAGES x {q, k, v} x [144][72]
   int4* sinfo_all = (int4*)(sdata + MM_STAGES * MM_STAGE_ELEMS);
   int* sunit_all = (int*)(sinfo_all + MM_NINFO * MM_INFO);    // MM_NINFO x { units: q0 | qn << 7 | k0 << 12 | kn << 19 ; [MM_UNITS] = count, [+1] = work counter }
+  __shared__ unsigned long long s_full[MM_STAGES], s_empty[MM_STAGES];   // bin staged / bin consumed
+  static_assert(MM_GROUP >= MM_INFO + MM_UNIT_CHUNKS && MM_MATH_WARPS >= 1, "stager group too small for the record copies");
   constexpr int HS = MM_SLICE / HD;
   const int d = a.d;
   const int nsl = d / MM_SLICE;
@@ -283,112 +441,177 @@ __global__ void __launch_bounds__(MM_THREADS, 1) sra_fwd_mma_kernel(MmArgs a, vo
   const int col = sl * MM_SLICE;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nbins = (a.N + MM_BIN - 1) / MM_BIN;
-  constexpr int GW = MM_GROUP >> 5;                           // warps per role
-  const bool stager = warp < GW;
-  const int gt = tid & (MM_GROUP - 1);
+  const bool stager = warp < MM_STAGER_WARPS;
+  const int gt = tid;                                         // index inside the stager group (stagers are warps 0 ..)
   if (cta >= nbins) return;
   const int my_bins = (nbins - cta + ncta - 1) / ncta;        // bins cta, cta + ncta, ...
+  MM_PROF_T(k0_);
 
-  // ---- prologue: zero the data buffers (overrun rows must hold finite values), LUT slice -> bf16, first records
-  for (int i = tid; i < MM_STAGES * MM_STAGE_ELEMS / 8; i += MM_THREADS) reinterpret_cast<uint4*>(sdata)[i] = make_uint4(0, 0, 0, 0);
-  for (int idx = tid; idx < 64 * MM_SLICE; idx += MM_THREADS) {      // one bf16 pair each
-    int pos = idx >> 6, c2 = idx & 63;
-    int part = c2 >> 5, cc = (c2 & 31) * 2;
-    float2 v = __ldg(reinterpret_cast<const float2*>(a.lut + (long long)pos * 2 * d + part * d + col + cc));
-    *reinterpret_cast<unsigned*>(slut + pos * 2 * MM_SLICE + part * MM_SLICE + cc) = pack_bf16(v.x, v.y);
-  }
+  // ---- prologue: first records (their latency hides behind the rest), LUT slice -> bf16 (loads batched), zeroed data
+  // buffers (overrun rows must hold finite values), barriers
   if (stager) {
 #pragma unroll
     for (int j = 0; j < 3; ++j)
       if (j < my_bins)
         mm_issue_info(sinfo_all + j * MM_INFO, sunit_all + j * MM_UNIT_STRIDE, a.row_info, a.bin_units, (cta + j * ncta) * MM_BIN, a.N, gt);
     mm_commit();
-    mm_wait<0>();
   }
-  __syncthreads();
-  if (stager) {
-    // the copy group committed at the end of iteration j holds the rows of bin j+1 and the records of bin j+3
-    mm_issue_rows(sdata, sinfo_all, a.qkv, d, col, cta * MM_BIN, a.N, gt);
-    mm_commit();
-  }
-  const float qscale = 1.4426950408889634f / fmaxf(__ldg(a.tau), a.tau_min);   // log2(e) / tau: softmax in base 2
-
-  for (int j = 0; j <= my_bins; ++j) {
-    if (stager) {
-      // ================= stagers: bin j
-      if (j < my_bins) {
-        const int bin = (cta + j * ncta) * MM_BIN;
-        const int4* sinfo = sinfo_all + (j % MM_NINFO) * MM_INFO;
-        bf16* sq = sdata + (j % MM_STAGES) * MM_STAGE_ELEMS;
-        // rows of bin j+1 (needs the records of bin j+1: landed with the previous group) and records of bin j+3
-        if (j + 1 < my_bins)
-          mm_issue_rows(sdata + ((j + 1) % MM_STAGES) * MM_STAGE_ELEMS, sinfo_all + ((j + 1) % MM_NINFO) * MM_INFO, a.qkv, d, col,
-                        (cta + (j + 1) * ncta) * MM_BIN, a.N, gt);
-        if (j + 3 < my_bins)
-          mm_issue_info(sinfo_all + ((j + 3) % MM_NINFO) * MM_INFO, sunit_all + ((j + 3) % MM_NINFO) * MM_UNIT_STRIDE, a.row_info,
-                        a.bin_units, (cta + (j + 3) * ncta) * MM_BIN, a.N, gt);
-        mm_commit();
-        mm_wait<1>();          // everything but the group just committed: rows of bin j, records + units of bin j+2
-        mm_bar_stagers();      // ... from every stager thread
-        int row0, R;
-        mm_bin_range(sinfo, bin, a.N, row0, R);
-        const int shift = row0 - bin;
-        // ---- q and k in place: + LUT, L2-normalise per head, q also x log2(e)/tau.  A thread keeps its 8-channel
-        // group (c8) and array (q or k) for the whole bin and walks rows 16 at a time, two rows in flight.
-        {
-          const int c8 = gt & 7, part = (gt >> 3) & 1, rsub = gt >> 4;
-          const float sc = part == 0 ? qscale : 1.f;
-          bf16* base = sq + part * MM_ARR + 8 * c8;
-          const int4* inf = sinfo + shift;
-          const bf16* lutc = slut + part * MM_SLICE + 8 * c8;
-          for (int rb = 0; rb < R; rb += 32) {                 // uniform trip count: the task shuffles inside the warp
-            const int r0 = rb + rsub, r1 = r0 + 16;
-            const bool v0 = r0 < R, v1 = r1 < R;
-            const int c0 = v0 ? r0 : 0, c1 = v1 ? r1 : 0;
-            const int pos0 = inf[c0].w, pos1 = inf[c1].w;
-            mm_stage_task<HD>(base + c0 * MM_PITCH, lutc + pos0 * 2 * MM_SLICE, sc, v0);
-            mm_stage_task<HD>(base + c1 * MM_PITCH, lutc + pos1 * 2 * MM_SLICE, sc, v1);
-          }
-        }
-      }
+  {
+    constexpr int NL = (64 * MM_SLICE + MF_THREADS - 1) / MF_THREADS;   // bf16 pairs per thread
+    float2 v[NL];
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+      const int idx = tid + i * MF_THREADS;
+      const int pos = idx >> 6, c2 = idx & 63;
+      const int part = c2 >> 5, cc = (c2 & 31) * 2;
+      v[i] = idx < 64 * MM_SLICE ? __ldg(reinterpret_cast<const float2*>(a.lut + (long long)pos * 2 * d + part * d + col + cc))
+                                 : make_float2(0.f, 0.f);
     }
-    if (j > 0) {
-      // ================= bin j-1: the math warps start at once, the stagers join when bin j is staged;
-      // (unit, head) entries are handed out through a shared-memory counter
-      const int jb = j - 1;
-      const int bin = (cta + jb * ncta) * MM_BIN;
-      const int4* sinfo = sinfo_all + (jb % MM_NINFO) * MM_INFO;
-      const bf16* sq = sdata + (jb % MM_STAGES) * MM_STAGE_ELEMS;
-      const bf16* sk = sq + MM_ARR;
-      const bf16* sv = sk + MM_ARR;
-      int* sunit = sunit_all + (jb % MM_NINFO) * MM_UNIT_STRIDE;
+    for (int i = tid; i < MM_STAGES * MM_STAGE_ELEMS / 8; i += MF_THREADS) reinterpret_cast<uint4*>(sdata)[i] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+      const int idx = tid + i * MF_THREADS;
+      const int pos = idx >> 6, c2 = idx & 63;
+      const int part = c2 >> 5, cc = (c2 & 31) * 2;
+      if (idx < 64 * MM_SLICE) *reinterpret_cast<unsigned*>(slut + pos * 2 * MM_SLICE + part * MM_SLICE + cc) = pack_bf16(v[i].x, v[i].y);
+    }
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int st = 0; st < MM_STAGES; ++st) {
+      mbar_init(&s_full[st], MM_STAGER_WARPS);   // every stager warp arrives once its share of the bin is staged (one
+                                                 // arrival per thread was measured at ~900 cycles per bin on the stagers)
+      mbar_init(&s_empty[st], MM_MATH_WARPS);    // every math warp arrives once it has no more work in the bin
+    }
+  }
+  if (stager) mm_wait<0>();
+  __syncthreads();     // the only CTA-wide barrier: from here the two roles meet through the mbarriers
+  MM_PROF_T(k1_);
+
+  if (stager) {
+    // ================= stagers: stage bin j in place and hand it over, then start the copies of bin j+2 (rows) and
+    // bin j+4 (records + units) into the buffers the math warps release with bin j-1.  Staging never waits for the math
+    // warps; only the copies do.  (cp.async per thread: 1-D TMA bulk copies of the 128-byte row pieces were measured at
+    // ~60 cycles of issue per copy from one warp - 11.6 k cycles per bin - and dropped.)
+    const float qscale = 1.4426950408889634f / fmaxf(__ldg(a.tau), a.tau_min);   // log2(e) / tau: softmax in base 2
+    mm_issue_rows(sdata, sinfo_all, a.qkv, d, col, cta * MM_BIN, a.N, gt);
+    mm_commit();                                                                  // group 0: rows of bin 0
+    if (1 < my_bins)
+      mm_issue_rows(sdata + MM_STAGE_ELEMS, sinfo_all + MM_INFO, a.qkv, d, col, (cta + ncta) * MM_BIN, a.N, gt);
+    if (3 < my_bins)
+      mm_issue_info(sinfo_all + 3 * MM_INFO, sunit_all + 3 * MM_UNIT_STRIDE, a.row_info, a.bin_units, (cta + 3 * ncta) * MM_BIN, a.N, gt);
+    mm_commit();                                                                  // group 1: rows of bin 1, records of bin 3
+    for (int j = 0; j < my_bins; ++j) {
+      const int bin = (cta + j * ncta) * MM_BIN;
+      const int4* sinfo = sinfo_all + (j % MM_NINFO) * MM_INFO;
+      bf16* sq = sdata + (j % MM_STAGES) * MM_STAGE_ELEMS;
+      MM_PROF_T(t0);
+      mm_wait<1>();          // everything but the latest group: rows of bin j, records + units of bin j+2
+      mm_bar_stagers();      // ... from every stager thread
+      MM_PROF_T(t1);
       int row0, R;
       mm_bin_range(sinfo, bin, a.N, row0, R);
       const int shift = row0 - bin;
-      const int nent = sunit[MM_UNITS] * HS;
-      const int g = lane >> 2;
+#ifndef MM_DEBUG_NO_STAGE
+      mm_stage_bin<HD, MM_STAGE_ILP, MM_GROUP>(sq, slut, sinfo + shift, R, qscale, gt, nullptr, nullptr);
+#endif
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_full[j % MM_STAGES]);     // release: the warp's copies (waited above) and staged rows
+      MM_PROF_T(t2);
+      if (j + 2 < my_bins) {
+        // the buffer of bin j+2 held bin j-1 (and the record slot bin j+4 takes is bin j-1's): math must be done with it
+        if (j + 2 >= MM_STAGES) mbar_wait(&s_empty[(j + 2) % MM_STAGES], (((j + 2) / MM_STAGES) - 1) & 1);
+      }
+      MM_PROF_T(t3);
+      if (j + 2 < my_bins)
+        mm_issue_rows(sdata + ((j + 2) % MM_STAGES) * MM_STAGE_ELEMS, sinfo_all + ((j + 2) % MM_NINFO) * MM_INFO, a.qkv, d, col,
+                      (cta + (j + 2) * ncta) * MM_BIN, a.N, gt);
+      if (j + 4 < my_bins)
+        mm_issue_info(sinfo_all + ((j + 4) % MM_NINFO) * MM_INFO, sunit_all + ((j + 4) % MM_NINFO) * MM_UNIT_STRIDE, a.row_info,
+                      a.bin_units, (cta + (j + 4) * ncta) * MM_BIN, a.N, gt);
+      mm_commit();
+#ifdef MM_PROFILE
+      if (warp == 0) {
+        MM_PROF_T(t4);
+        MM_PROF_ADD(0, t3 - t2); MM_PROF_ADD(1, t4 - t3); MM_PROF_ADD(2, t1 - t0); MM_PROF_ADD(4, t2 - t1); MM_PROF_ADD(5, 1);
+      }
+#endif
+    }
+    mm_wait<0>();
+  } else {
+    // ================= math warps: entries of bin j (a unit and one or two heads), handed out through the bin's
+    // work counter; a warp that finds the bin exhausted signals and moves on to bin j+1 without waiting for the others
+    const int g = lane >> 2;
+    for (int j = 0; j < my_bins; ++j) {
+      const int bin = (cta + j * ncta) * MM_BIN;
+      const int4* sinfo = sinfo_all + (j % MM_NINFO) * MM_INFO;
+      const bf16* sq = sdata + (j % MM_STAGES) * MM_STAGE_ELEMS;
+      const bf16* sk = sq + MM_ARR;
+      const bf16* sv = sk + MM_ARR;
+      int* sunit = sunit_all + (j % MM_NINFO) * MM_UNIT_STRIDE;
+      MM_PROF_T(m0);
+      mbar_wait(&s_full[j % MM_STAGES], (j / MM_STAGES) & 1);
+      MM_PROF_T(m1);
+#ifdef MM_PROFILE
+      int n_done = 0;
+#endif
+      int row0, R;
+      mm_bin_range(sinfo, bin, a.N, row0, R);
+      const int shift = row0 - bin;
+      constexpr int HPE = MM_HEADS_PER_ENTRY(HD);
+      constexpr int EPU = HS / HPE;                           // entries per unit
+#ifdef MM_DEBUG_NO_MATH
+      const int nent = 0;
+#else
+      const int nent = sunit[MM_UNITS] * EPU;
+#endif
       for (;;) {
         int e = 0;
         if (lane == 0) e = atomicAdd(sunit + MM_UNITS + 1, 1);
         e = __shfl_sync(0xffffffffu, e, 0);
         if (e >= nent) break;
-        const int code = sunit[e / HS];
-        const int h = e % HS;
+#ifdef MM_PROFILE
+        ++n_done;
+#endif
+        const int code = sunit[e / EPU];
+        const int h = (e % EPU) * HPE;
         const int q0 = code & 127, qn = (code >> 7) & 31, k0 = (code >> 12) & 127, kn = (code >> 19) & 127;
         const int ch = h * HD;
         const int4 recA = sinfo[min(q0 + g, R - 1) + shift], recB = sinfo[min(q0 + g + 8, R - 1) + shift];
         const int kbase = row0 + k0;
         const long long oc = col + ch;
         const int lc = sl * HS + h;
-        if (kn <= 16) mm_unit<HD, 2>(a, sq, sk, sv, q0, qn, k0, ch, recA, recB, kbase, lane, oc, lc, out, lse);
-        else if (kn <= 32) mm_unit<HD, 4>(a, sq, sk, sv, q0, qn, k0, ch, recA, recB, kbase, lane, oc, lc, out, lse);
-        else if (kn <= 48) mm_unit<HD, 6>(a, sq, sk, sv, q0, qn, k0, ch, recA, recB, kbase, lane, oc, lc, out, lse);
-        else mm_unit<HD, 8>(a, sq, sk, sv, q0, qn, k0, ch, recA, recB, kbase, lane, oc, lc, out, lse);
+        if (kn <= 16) mm_unit<HD, 2, HPE>(a, sq, sk, sv, q0, qn, k0, ch, recA, recB, kbase, lane, oc, lc, out, lse);
+        else if (kn <= 32) mm_unit<HD, 4, HPE>(a, sq, sk, sv, q0, qn, k0, ch, recA, recB, kbase, lane, oc, lc, out, lse);
+        else {
+          // large windows: one head at a time (the two-head body would spill at the register cap)
+#pragma unroll 1
+          for (int hh = 0; hh < HPE; ++hh) {
+            if (kn <= 48) mm_unit<HD, 6, 1>(a, sq, sk, sv, q0, qn, k0, ch + hh * HD, recA, recB, kbase, lane, oc + hh * HD, lc + hh, out, lse);
+            else mm_unit<HD, 8, 1>(a, sq, sk, sv, q0, qn, k0, ch + hh * HD, recA, recB, kbase, lane, oc + hh * HD, lc + hh, out, lse);
+          }
+        }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[j % MM_STAGES]);
+#ifdef MM_PROFILE
+      if (warp == MM_STAGER_WARPS || warp == MF_THREADS / 32 - 1) {
+        MM_PROF_T(m2);
+        const int o = warp == MM_STAGER_WARPS ? 6 : 10;
+        MM_PROF_ADD(o, m1 - m0); MM_PROF_ADD(o + 1, m2 - m1); MM_PROF_ADD(o + 2, n_done);
+        if (o == 6) MM_PROF_ADD(9, nent);
+      }
+#endif
     }
-    __syncthreads();   // bin j is staged for the math warps; bin j-1's buffers are free for the copies of bin j+2
+#ifdef MM_PROFILE
+    if (warp == MF_THREADS / 32 - 1 && lane == 0) {
+      const long long k2_ = clock64();
+      atomicAdd(&g_mm_prof[13], (unsigned long long)(k2_ - k0_));
+      atomicMax(&g_mm_prof[14], (unsigned long long)(k2_ - k0_));
+      atomicAdd(&g_mm_prof[15], (unsigned long long)(k1_ - k0_));
+    }
+#endif
   }
-  if (stager) mm_wait<0>();
 }
 
 // =====================================================================================================
@@ -409,7 +632,13 @@ __global__ void __launch_bounds__(MM_THREADS, 1) sra_fwd_mma_kernel(MmArgs a, vo
 #define MB_NINFO 4
 #define MB_STAGE_ELEMS (4 * MM_ARR)
 #define MB_SCAL (MM_ROWS * 4)      // one fp32 per (row, head of the slice)
-#define MB_SMEM_BYTES (64 * 2 * MM_SLICE * 2 + MB_STAGES * MB_STAGE_ELEMS * 2 + MB_NINFO * MM_INFO * 16 + (MB_STAGES + 3) * MB_SCAL * 4 + MB_NINFO * MM_UNIT_STRIDE * 4 + 128 * 4 * 4)
+#ifndef MB_STAGER_WARPS
+#define MB_STAGER_WARPS 5      // backward: warps that copy and stage bins (>= 5: 141 threads copy records + units)
+#endif
+#define MB_GROUP (32 * MB_STAGER_WARPS)
+#define MB_MATH_WARPS (MM_THREADS / 32 - MB_STAGER_WARPS)
+// LUT | stages x {q,k,v,dO} | records | per stage: lse, 1/|q|, 1/|k|, D | units | per stage: query-side completion counters
+#define MB_SMEM_BYTES (64 * 2 * MM_SLICE * 2 + MB_STAGES * MB_STAGE_ELEMS * 2 + MB_NINFO * MM_INFO * 16 + MB_STAGES * 4 * MB_SCAL * 4 + MB_NINFO * MM_UNIT_STRIDE * 4 + MB_STAGES * 128 * 4 * 4)
 
 struct MbArgs {
   const bf16* qkv;     // (N, 3d) bf16
@@ -425,13 +654,14 @@ struct MbArgs {
   int N, d;
 };
 
+template <int NT>
 __device__ __forceinline__ void mb_issue_rows(bf16* stage, float* slse, const int4* inf, const MbArgs& a, int col, int hs, int lse_col,
                                               int bin, int tid) {
   int row0, R;
   mm_bin_range(inf, bin, a.N, row0, R);
   const int shift = row0 - bin;
   const int d = a.d;
-  for (int idx = tid; idx < R * 8; idx += MM_THREADS) {      // one 16-byte chunk of q, k, v and dO each
+  for (int idx = tid; idx < R * 8; idx += NT) {              // one 16-byte chunk of q, k, v and dO each
     const int r = idx >> 3, c8 = idx & 7;
     const long long tok = inf[r + shift].x;
     const bf16* src = a.qkv + tok * 3 * d + col + 8 * c8;
@@ -441,7 +671,7 @@ __device__ __forceinline__ void mb_issue_rows(bf16* stage, float* slse, const in
     mm_cp16(dst + 2 * MM_ARR, src + 2 * d);
     mm_cp16(dst + 3 * MM_ARR, a.dout + tok * d + col + 8 * c8);
   }
-  for (int idx = tid; idx < R * hs; idx += MM_THREADS) {     // lse of the slice's heads, 4 bytes each
+  for (int idx = tid; idx < R * hs; idx += NT) {             // lse of the slice's heads, 4 bytes each
     const int r = idx / hs, h = idx - r * hs;
     unsigned sa = (unsigned)__cvta_generic_to_shared(slse + r * 4 + h);
     const float* src = a.lse + (long long)inf[r + shift].x * 8 + lse_col + h;
@@ -691,15 +921,13 @@ __global__ void __launch_bounds__(MM_THREADS, 1) sra_bwd_mma_kernel(MbArgs a) {
   bf16* slut = (bf16*)smem_raw;
   bf16* sdata = slut + 64 * 2 * MM_SLICE;                     // MB_STAGES x {q, k, v, dO} x [144][72]
   int4* sinfo_all = (int4*)(sdata + MB_STAGES * MB_STAGE_ELEMS);
-  float* slse_all = (float*)(sinfo_all + MB_NINFO * MM_INFO); // MB_STAGES x [144][4]
-  float* srq = slse_all + MB_STAGES * MB_SCAL;                // 1/|q| per (row, head)
-  float* srk = srq + MB_SCAL;
-  float* sD = srk + MB_SCAL;
-  int* sunit_all = (int*)(sD + MB_SCAL);
-  int* sdone = sunit_all + MB_NINFO * MM_UNIT_STRIDE;         // [128 window start rows][4 heads]: query-side entries finished
+  float* sscal_all = (float*)(sinfo_all + MB_NINFO * MM_INFO); // MB_STAGES x { lse, 1/|q|, 1/|k|, D } x [144][4]
+  int* sunit_all = (int*)(sscal_all + MB_STAGES * 4 * MB_SCAL);
+  int* sdone_all = sunit_all + MB_NINFO * MM_UNIT_STRIDE;     // MB_STAGES x [128 window start rows][4 heads]: query-side entries finished
   __shared__ float s_dtau[MM_THREADS / 32];
+  __shared__ unsigned long long b_full[MB_STAGES], b_empty[MB_STAGES];   // bin staged / bin consumed
+  static_assert(MB_GROUP >= MM_INFO + MM_UNIT_CHUNKS && MB_MATH_WARPS >= 1, "stager group too small for the record copies");
   constexpr int HS = MM_SLICE / HD;
-  constexpr int NWARPS = MM_THREADS >> 5;
   const int d = a.d;
   const int nsl = d / MM_SLICE;
   const int sl = blockIdx.x % nsl, cta = blockIdx.x / nsl, ncta = gridDim.x / nsl;
@@ -709,119 +937,153 @@ __global__ void __launch_bounds__(MM_THREADS, 1) sra_bwd_mma_kernel(MbArgs a) {
   if (cta >= nbins) return;
   const int my_bins = (nbins - cta + ncta - 1) / ncta;
   const int lse_col = sl * HS;
+  const bool stager = warp < MB_STAGER_WARPS;
 
-  for (int i = tid; i < MB_STAGES * MB_STAGE_ELEMS / 8; i += MM_THREADS) reinterpret_cast<uint4*>(sdata)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < (MB_STAGES + 3) * MB_SCAL; i += MM_THREADS) slse_all[i] = 0.f;
-  for (int idx = tid; idx < 64 * MM_SLICE; idx += MM_THREADS) {
-    int pos = idx >> 6, c2 = idx & 63;
-    int part = c2 >> 5, cc = (c2 & 31) * 2;
-    float2 v = __ldg(reinterpret_cast<const float2*>(a.lut + (long long)pos * 2 * d + part * d + col + cc));
-    *reinterpret_cast<unsigned*>(slut + pos * 2 * MM_SLICE + part * MM_SLICE + cc) = pack_bf16(v.x, v.y);
-  }
+  // ---- prologue: first records, LUT slice -> bf16 (loads batched), zeroed buffers (overrun rows and scalars must be finite)
+  if (stager) {
 #pragma unroll
-  for (int j = 0; j < 3; ++j)
-    if (j < my_bins)
-      mm_issue_info(sinfo_all + j * MM_INFO, sunit_all + j * MM_UNIT_STRIDE, a.row_info, a.bin_units, (cta + j * ncta) * MM_BIN, a.N, tid);
-  mm_commit();
-  mm_wait<0>();
-  __syncthreads();
-  mb_issue_rows(sdata, slse_all, sinfo_all, a, col, HS, lse_col, cta * MM_BIN, tid);
-  mm_commit();
+    for (int j = 0; j < 3; ++j)
+      if (j < my_bins)
+        mm_issue_info(sinfo_all + j * MM_INFO, sunit_all + j * MM_UNIT_STRIDE, a.row_info, a.bin_units, (cta + j * ncta) * MM_BIN, a.N, tid);
+    mm_commit();
+  }
+  {
+    constexpr int NL = (64 * MM_SLICE + MM_THREADS - 1) / MM_THREADS;   // bf16 pairs per thread
+    float2 v[NL];
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+      const int idx = tid + i * MM_THREADS;
+      const int pos = idx >> 6, c2 = idx & 63;
+      const int part = c2 >> 5, cc = (c2 & 31) * 2;
+      v[i] = idx < 64 * MM_SLICE ? __ldg(reinterpret_cast<const float2*>(a.lut + (long long)pos * 2 * d + part * d + col + cc))
+                                 : make_float2(0.f, 0.f);
+    }
+    for (int i = tid; i < MB_STAGES * MB_STAGE_ELEMS / 8; i += MM_THREADS) reinterpret_cast<uint4*>(sdata)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < MB_STAGES * 4 * MB_SCAL; i += MM_THREADS) sscal_all[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+      const int idx = tid + i * MM_THREADS;
+      const int pos = idx >> 6, c2 = idx & 63;
+      const int part = c2 >> 5, cc = (c2 & 31) * 2;
+      if (idx < 64 * MM_SLICE) *reinterpret_cast<unsigned*>(slut + pos * 2 * MM_SLICE + part * MM_SLICE + cc) = pack_bf16(v[i].x, v[i].y);
+    }
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int st = 0; st < MB_STAGES; ++st) {
+      mbar_init(&b_full[st], MB_STAGER_WARPS);
+      mbar_init(&b_empty[st], MB_MATH_WARPS);
+    }
+  }
+  if (stager) mm_wait<0>();
+  __syncthreads();     // from here the two roles meet through the mbarriers (and once more for the d tau sum)
   const float tau_c = fmaxf(__ldg(a.tau), a.tau_min);
   const float qscale = 1.4426950408889634f / tau_c, inv_tau = 1.f / tau_c, inv_qs2 = 1.f / (qscale * qscale);
   float dtau_acc = 0.f;
 
-  for (int k = 0; k < my_bins; ++k) {
-    const int bin = (cta + k * ncta) * MM_BIN;
-    const int4* sinfo = sinfo_all + (k % MB_NINFO) * MM_INFO;
-    bf16* sq = sdata + (k % MB_STAGES) * MB_STAGE_ELEMS;
-    bf16* sk = sq + MM_ARR;
-    bf16* sv = sk + MM_ARR;
-    bf16* sdo = sv + MM_ARR;
-    float* slse = slse_all + (k % MB_STAGES) * MB_SCAL;
-    mm_wait<0>();        // rows of bin k, records of bin k+2
-    __syncthreads();     // ... visible; everyone is done with bin k-1
-    if (k + 1 < my_bins)
-      mb_issue_rows(sdata + ((k + 1) % MB_STAGES) * MB_STAGE_ELEMS, slse_all + ((k + 1) % MB_STAGES) * MB_SCAL,
-                    sinfo_all + ((k + 1) % MB_NINFO) * MM_INFO, a, col, HS, lse_col, (cta + (k + 1) * ncta) * MM_BIN, tid);
-    if (k + 3 < my_bins)
-      mm_issue_info(sinfo_all + ((k + 3) % MB_NINFO) * MM_INFO, sunit_all + ((k + 3) % MB_NINFO) * MM_UNIT_STRIDE, a.row_info, a.bin_units,
-                    (cta + (k + 3) * ncta) * MM_BIN, a.N, tid);
+  if (stager) {
+    // ================= stagers: stage bin k in place (+ LUT, normalise, keep 1/|q|, 1/|k| per (row, head)), hand it over, then
+    // copy bin k+1 (rows, lse) and the records + units of bin k+3 into the buffers the math warps release with bin k-1
+    mb_issue_rows<MB_GROUP>(sdata, sscal_all, sinfo_all, a, col, HS, lse_col, cta * MM_BIN, tid);
     mm_commit();
-    int row0, R;
-    mm_bin_range(sinfo, bin, a.N, row0, R);
-    if (R == 0) continue;
-    const int shift = row0 - bin;
-    // ---- q / k staging in place (+ LUT, normalise, keep 1/|q|, 1/|k| per (row, head)); the work units of the bin came
-    // with its records (gdmae_sra_bin_units)
-    int* sunit = sunit_all + (k % MB_NINFO) * MM_UNIT_STRIDE;
-    sdone[tid] = 0;      // MM_THREADS == 128 * 4
-    {
-      const int c8 = tid & 7, part = (tid >> 3) & 1, rsub = tid >> 4;     // 32 rows per pass
-      const float sc = part == 0 ? qscale : 1.f;
-      bf16* base = sq + part * MM_ARR + 8 * c8;
-      const int4* inf = sinfo + shift;
-      const bf16* lutc = slut + part * MM_SLICE + 8 * c8;
-      float* srn = part == 0 ? srq : srk;
-      for (int rb = 0; rb < R; rb += 32) {
-        const int r = rb + rsub;
-        const bool v = r < R;
-        const int c = v ? r : 0;
-        const float rn = mm_stage_task<HD>(base + c * MM_PITCH, lutc + inf[c].w * 2 * MM_SLICE, sc, v);
-        if (v && (c8 & (HD / 8 - 1)) == 0) srn[r * 4 + c8 / (HD / 8)] = rn;
+    for (int k = 0; k < my_bins; ++k) {
+      const int bin = (cta + k * ncta) * MM_BIN;
+      const int st = k % MB_STAGES;
+      const int4* sinfo = sinfo_all + (k % MB_NINFO) * MM_INFO;
+      bf16* sq = sdata + st * MB_STAGE_ELEMS;
+      float* sscal = sscal_all + st * 4 * MB_SCAL;
+      mm_wait<0>();        // rows of bin k, records + units of bin k+2
+      asm volatile("bar.sync 1, %0;" ::"n"(MB_GROUP) : "memory");   // ... from every stager thread
+      int row0, R;
+      mm_bin_range(sinfo, bin, a.N, row0, R);
+      const int shift = row0 - bin;
+      for (int i = tid; i < 128 * 4; i += MB_GROUP) sdone_all[st * 512 + i] = 0;
+      mm_stage_bin<HD, 4, MB_GROUP>(sq, slut, sinfo + shift, R, qscale, tid, sscal + MB_SCAL, sscal + 2 * MB_SCAL);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&b_full[st]);
+      if (k + 1 < my_bins) {
+        const int sn = (k + 1) % MB_STAGES;
+        if (k + 1 >= MB_STAGES) mbar_wait(&b_empty[sn], (((k + 1) / MB_STAGES) - 1) & 1);   // math is done with bin k-1
+        mb_issue_rows<MB_GROUP>(sdata + sn * MB_STAGE_ELEMS, sscal_all + sn * 4 * MB_SCAL, sinfo_all + ((k + 1) % MB_NINFO) * MM_INFO, a, col, HS,
+                                lse_col, (cta + (k + 1) * ncta) * MM_BIN, tid);
       }
+      if (k + 3 < my_bins)
+        mm_issue_info(sinfo_all + ((k + 3) % MB_NINFO) * MM_INFO, sunit_all + ((k + 3) % MB_NINFO) * MM_UNIT_STRIDE, a.row_info, a.bin_units,
+                      (cta + (k + 3) * ncta) * MM_BIN, a.N, tid);
+      mm_commit();
     }
-    __syncthreads();
-    const int nent = sunit[MM_UNITS] * HS;
+    mm_wait<0>();
+  } else {
+    // ================= math warps.  Entries [0, nent): query side; [nent, 2 nent): key side, handed out in this order through the
+    // work counter that arrived (zero) with the unit list.  A key-side entry needs D of every query row of its window: it waits
+    // until the query-side entries covering the window (one for a packed unit, ceil(rows/16) chunks for a large window) have
+    // signalled.  Every query-side entry is pulled before any key-side entry and never blocks, so the wait cannot deadlock.  A
+    // warp that finds the bin exhausted signals and moves on to bin k+1 without waiting for the others.
     const int g = lane >> 2;
-    // ---- entries [0, nent): query side; [nent, 2 nent): key side, handed out in this order through the work counter
-    // that arrived (zero) with the unit list.  A key-side entry needs D of every query row of its window: it waits
-    // until the query-side entries covering the window (one for a packed unit, ceil(rows/16) chunks for a large
-    // window) have signalled.  Every query-side entry is pulled before any key-side entry and never blocks, so the
-    // wait cannot deadlock; no CTA barrier separates the two sides.
-    for (;;) {
-      int e = 0;
-      if (lane == 0) e = atomicAdd(sunit + MM_UNITS + 1, 1);
-      e = __shfl_sync(0xffffffffu, e, 0);
-      if (e >= 2 * nent) break;
-      const bool key_side = e >= nent;
-      if (key_side) e -= nent;
-      const int code = sunit[e / HS];
-      const int h = e % HS;
-      const int q0 = code & 127, qn = (code >> 7) & 31, k0 = (code >> 12) & 127, kn = (code >> 19) & 127;
-      const int4 recA = sinfo[min(q0 + g, R - 1) + shift], recB = sinfo[min(q0 + g + 8, R - 1) + shift];
-      const int kbase = row0 + k0;
-      if (!key_side) {
-        if (kn <= 16) dtau_acc += mb_unit_q<HD, 2>(a, sq, sk, sv, sdo, slse, srq, sD, q0, qn, k0, h, recA, recB, kbase, lane, col, inv_tau, inv_qs2);
-        else if (kn <= 32) dtau_acc += mb_unit_q<HD, 4>(a, sq, sk, sv, sdo, slse, srq, sD, q0, qn, k0, h, recA, recB, kbase, lane, col, inv_tau, inv_qs2);
-        else if (kn <= 48) dtau_acc += mb_unit_q<HD, 6>(a, sq, sk, sv, sdo, slse, srq, sD, q0, qn, k0, h, recA, recB, kbase, lane, col, inv_tau, inv_qs2);
-        else dtau_acc += mb_unit_q<HD, 8>(a, sq, sk, sv, sdo, slse, srq, sD, q0, qn, k0, h, recA, recB, kbase, lane, col, inv_tau, inv_qs2);
-        __threadfence_block();
-        __syncwarp();
-        if (lane == 0) atomicAdd(sdone + k0 * 4 + h, 1);
-      } else {
-        const int need = kn > 16 ? (kn + 15) >> 4 : 1;
-        if (lane == 0) {
-          const volatile int* flag = sdone + k0 * 4 + h;
-          for (int spin = 0; *flag < need && spin < (1 << 20); ++spin) {}   // bounded: a logic error must not hang the GPU
+    for (int k = 0; k < my_bins; ++k) {
+      const int bin = (cta + k * ncta) * MM_BIN;
+      const int st = k % MB_STAGES;
+      const int4* sinfo = sinfo_all + (k % MB_NINFO) * MM_INFO;
+      const bf16* sq = sdata + st * MB_STAGE_ELEMS;
+      const bf16* sk = sq + MM_ARR;
+      const bf16* sv = sk + MM_ARR;
+      const bf16* sdo = sv + MM_ARR;
+      float* slse = sscal_all + st * 4 * MB_SCAL;
+      float* srq = slse + MB_SCAL;
+      float* srk = srq + MB_SCAL;
+      float* sD = srk + MB_SCAL;
+      int* sdone = sdone_all + st * 512;
+      int* sunit = sunit_all + (k % MB_NINFO) * MM_UNIT_STRIDE;
+      mbar_wait(&b_full[st], (k / MB_STAGES) & 1);
+      int row0, R;
+      mm_bin_range(sinfo, bin, a.N, row0, R);
+      const int shift = row0 - bin;
+      const int nent = sunit[MM_UNITS] * HS;
+      for (;;) {
+        int e = 0;
+        if (lane == 0) e = atomicAdd(sunit + MM_UNITS + 1, 1);
+        e = __shfl_sync(0xffffffffu, e, 0);
+        if (e >= 2 * nent) break;
+        const bool key_side = e >= nent;
+        if (key_side) e -= nent;
+        const int code = sunit[e / HS];
+        const int h = e % HS;
+        const int q0 = code & 127, qn = (code >> 7) & 31, k0 = (code >> 12) & 127, kn = (code >> 19) & 127;
+        const int4 recA = sinfo[min(q0 + g, R - 1) + shift], recB = sinfo[min(q0 + g + 8, R - 1) + shift];
+        const int kbase = row0 + k0;
+        if (!key_side) {
+          if (kn <= 16) dtau_acc += mb_unit_q<HD, 2>(a, sq, sk, sv, sdo, slse, srq, sD, q0, qn, k0, h, recA, recB, kbase, lane, col, inv_tau, inv_qs2);
+          else if (kn <= 32) dtau_acc += mb_unit_q<HD, 4>(a, sq, sk, sv, sdo, slse, srq, sD, q0, qn, k0, h, recA, recB, kbase, lane, col, inv_tau, inv_qs2);
+          else if (kn <= 48) dtau_acc += mb_unit_q<HD, 6>(a, sq, sk, sv, sdo, slse, srq, sD, q0, qn, k0, h, recA, recB, kbase, lane, col, inv_tau, inv_qs2);
+          else dtau_acc += mb_unit_q<HD, 8>(a, sq, sk, sv, sdo, slse, srq, sD, q0, qn, k0, h, recA, recB, kbase, lane, col, inv_tau, inv_qs2);
+          __threadfence_block();
+          __syncwarp();
+          if (lane == 0) atomicAdd(sdone + k0 * 4 + h, 1);
+        } else {
+          const int need = kn > 16 ? (kn + 15) >> 4 : 1;
+          if (lane == 0) {
+            const volatile int* flag = sdone + k0 * 4 + h;
+            for (int spin = 0; *flag < need && spin < (1 << 20); ++spin) __nanosleep(32);   // bounded: a logic error must not hang the GPU
+          }
+          __syncwarp();
+          __threadfence_block();
+          if (kn <= 16) mb_unit_kv<HD, 2>(a, sq, sk, sv, sdo, slse, srk, sD, q0, qn, k0, h, recA, recB, kbase, lane, col);
+          else if (kn <= 32) mb_unit_kv<HD, 4>(a, sq, sk, sv, sdo, slse, srk, sD, q0, qn, k0, h, recA, recB, kbase, lane, col);
+          else if (kn <= 48) mb_unit_kv<HD, 6>(a, sq, sk, sv, sdo, slse, srk, sD, q0, qn, k0, h, recA, recB, kbase, lane, col);
+          else mb_unit_kv<HD, 8>(a, sq, sk, sv, sdo, slse, srk, sD, q0, qn, k0, h, recA, recB, kbase, lane, col);
         }
-        __syncwarp();
-        __threadfence_block();
-        if (kn <= 16) mb_unit_kv<HD, 2>(a, sq, sk, sv, sdo, slse, srk, sD, q0, qn, k0, h, recA, recB, kbase, lane, col);
-        else if (kn <= 32) mb_unit_kv<HD, 4>(a, sq, sk, sv, sdo, slse, srk, sD, q0, qn, k0, h, recA, recB, kbase, lane, col);
-        else if (kn <= 48) mb_unit_kv<HD, 6>(a, sq, sk, sv, sdo, slse, srk, sD, q0, qn, k0, h, recA, recB, kbase, lane, col);
-        else mb_unit_kv<HD, 8>(a, sq, sk, sv, sdo, slse, srk, sD, q0, qn, k0, h, recA, recB, kbase, lane, col);
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&b_empty[st]);
     }
   }
-  mm_wait<0>();
   // sum dS*S of this CTA (natural-log scores: S = S' ln2)
   dtau_acc = warp_sum(dtau_acc);
   if (lane == 0) s_dtau[warp] = dtau_acc;
   __syncthreads();
   if (tid == 0) {
     float tot = 0.f;
-    for (int w = 0; w < NWARPS; ++w) tot += s_dtau[w];
+    for (int w = 0; w < MM_THREADS / 32; ++w) tot += s_dtau[w];
     atomicAdd(a.dtau_sum, (double)tot * 0.6931471805599453);
   }
 }
@@ -918,8 +1180,8 @@ extern "C" int gdmae_sra_attention_fwd_tc(const void* qkv_bf16, const float* lut
   MmArgs a{(const bf16*)qkv_bf16, lut, (const int4*)row_info, bin_units, tau, bv, tau_min, (int)N, d, io_bf16};
   cudaStream_t st = (cudaStream_t)stream_;
   // one CTA per SM; 148 is a multiple of the 2 (d = 128) and 4 (d = 256) channel slices
-  if (d == 128) sra_fwd_mma_kernel<16><<<GDMAE_NUM_SMS, MM_THREADS, MM_SMEM_BYTES, st>>>(a, out, lse);
-  else sra_fwd_mma_kernel<32><<<GDMAE_NUM_SMS, MM_THREADS, MM_SMEM_BYTES, st>>>(a, out, lse);
+  if (d == 128) sra_fwd_mma_kernel<16><<<GDMAE_NUM_SMS, MF_THREADS, MM_SMEM_BYTES, st>>>(a, out, lse);
+  else sra_fwd_mma_kernel<32><<<GDMAE_NUM_SMS, MF_THREADS, MM_SMEM_BYTES, st>>>(a, out, lse);
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;
 }
