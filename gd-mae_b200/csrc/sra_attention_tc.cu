@@ -10,17 +10,20 @@
 //   * persistent, one CTA per SM, each owning a 64-channel slice (2 heads of 32 or 4 heads of 16) and
 //     walking bins of 64 CSR rows (the windows that START in the bin, <= 127 rows).  The slice of the
 //     positional LUT lives in shared memory (bf16) for the whole kernel;
-//   * warp specialised, three stage buffers: in iteration j the 8 "stager" warps take bin j (wait for
-//     its cp.async rows, build the work units, normalise q and k in place) while the 8 "math" warps
-//     run the MMAs of bin j-1 and the rows of bin j+1 / the row_info records of bins j+2, j+3 are in
-//     flight; work units are handed out through a shared-memory counter and the stagers join the math
-//     once their bin is staged; one CTA barrier per iteration;
+//   * warp specialised and decoupled: "stager" warps copy the rows of a bin with cp.async (three stage buffers) and
+//     normalise q and k in place, "math" warps run the MMAs; the two roles meet only through mbarriers (bin staged /
+//     bin consumed) - no CTA barrier inside the bin loop, a math warp that runs out of work in bin j moves on to bin
+//     j+1 on its own.  try_wait carries a suspend hint: a polling wait was measured to burn a third of the issue slots;
+//   * the work units of every bin are built ONCE per window table (gdmae_sra_bin_units: a table serves two layers,
+//     forward and backward) and arrive with the bin's row records; (unit, head) entries are handed out through a
+//     shared-memory counter that arrives zeroed with them;
 //   * one pass over q and k only: + LUT, L2-normalise per head, fold log2(e)/tau into q, back to
 //     bf16 in place.  v is used as it arrives;
 //   * work units are PACKED: a unit is either a run of whole small windows totalling <= 16 rows, or a
 //     16-row chunk of a large window; per-row key bounds (from row_info) give the block-diagonal
 //     mask.  A 3-token window therefore costs 3/16 of an MMA tile instead of a whole one;
-//   * one warp per (unit, head): S = Q K^T accumulates in registers (ldmatrix operands), the softmax
+//   * one warp per (unit, head) - per (unit, head pair) for 16-channel heads, the two heads interleaved as independent
+//     instruction streams: S = Q K^T accumulates in registers (ldmatrix operands), the softmax
 //     runs on the C fragments with quad shuffles, P goes back into the second MMA as the A operand
 //     directly from registers, V comes in through ldmatrix.trans.  Row pitch 144 B makes every
 //     ldmatrix phase conflict free.  The unit body is compiled for 16 / 32 / 48 / 64 keys.
@@ -615,9 +618,11 @@ __global__ void __launch_bounds__(MF_THREADS, 1) sra_fwd_mma_kernel(MmArgs a, vo
 }
 
 // =====================================================================================================
-// Backward.  Same bins, packing and operand staging as the forward kernel; four staged arrays
-// (Qs = q_hat * log2(e)/tau, K_hat, V, dO) in two stage buffers, all 16 warps share every phase:
+// Backward.  Same bins, packing, operand staging and stager / math decoupling as the forward kernel; four staged arrays
+// (Qs = q_hat * log2(e)/tau, K_hat, V, dO) in two stage buffers, scalars (lse, 1/|q|, 1/|k|, D) per stage:
 //   stage    : + LUT, normalise q and k in place, keep 1/|q|, 1/|k| per (row, head); lse rows by cp.async
+//   entries  : query side of every (unit, head), then key side, from one work queue; a key-side entry waits on a
+//              shared-memory counter for the query-side entries of its window (they produce D), not on a barrier
 //   phase 1  : one warp per (unit, head), query side.  One sweep over the key tiles computes S' = Qs K^T and
 //              dP = dO V^T on the tensor cores, P = exp2(S' - lse), and the row sums D = sum P dP,
 //              T1 = sum P dP S', T2 = sum P S' (d tau needs sum dS S = T1 - D T2); P stays in registers as
