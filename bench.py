@@ -242,8 +242,9 @@ def main():
     span_ms = (ctypes.c_float * cap)()
     n_span = _lib.lib().gdmae_timing_drain(meta, span_ms, cap)
     c_spans = {}
+    span_names = {0: "sra_fwd_d{d}", 1: "sra_bwd_d{d}", 2: "pillar_scatter_max_c{d}"}
     for i in range(n_span):
-        name = f"sra_{'bwd' if meta[4 * i] else 'fwd'}_d{meta[4 * i + 1]}"
+        name = span_names[int(meta[4 * i])].format(d=int(meta[4 * i + 1]))
         c_spans.setdefault(name, []).append((float(span_ms[i]), int(meta[4 * i + 3])))
     clocks = sampler.stop()
     # ---- end-to-end timing through the public API with host inputs
@@ -271,8 +272,16 @@ def main():
     roofline = None
     if dom:
         k = kernels[dom]
+        # DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture (profiles/r1_ncu_traffic.json)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get(dom, {}).get("dram_bytes_per_launch")
         roofline = {"kernel": dom, "bound": "hbm", "achieved": k["achieved_gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
-                    "frac": k["frac"], "traffic": None, "peak_source": pk_src, "avg_us": k["avg_us"],
+                    "frac": k["frac"], "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu, cold cache)",
+                    "algorithmic_bytes": float(np.mean([nb for _, nb in c_spans[dom]])) if dom in c_spans else None,
+                    "peak_source": pk_src, "avg_us": k["avg_us"],
                     "bytes_def": "N*d*(3*s_qkv + s_o) + N*8*4 per launch (q,k,v in, o and lse out; s = 2 bytes in the bf16 "
                                  "configuration, 4 in fp32; SURVEY.md 8d)"}
 

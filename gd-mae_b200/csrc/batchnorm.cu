@@ -52,18 +52,20 @@ __global__ void __launch_bounds__(256) bn_relu_apply_kernel(const float4* __rest
   }
 }
 
-// backward pass 1: partial column sums of g = dout * [out > 0] and g * xhat
-__global__ void __launch_bounds__(256) bn_relu_bwd_stats_kernel(const float4* __restrict__ y, const float4* __restrict__ out,
-                                                                const float4* __restrict__ dout, const float4* __restrict__ mean,
-                                                                const float4* __restrict__ rstd, long long N, int C4, int relu,
-                                                                float* __restrict__ partial) {
+// backward pass 1: partial column sums of g = dout * [out > 0] and g * xhat.  The ReLU mask is recomputed from y with the
+// forward's expression instead of reading the saved output (one tensor less per pass).
+__global__ void __launch_bounds__(256) bn_relu_bwd_stats_kernel(const float4* __restrict__ y, const float4* __restrict__ gamma,
+                                                                const float4* __restrict__ beta, const float4* __restrict__ dout,
+                                                                const float4* __restrict__ mean, const float4* __restrict__ rstd,
+                                                                long long N, int C4, int relu, float* __restrict__ partial) {
   int c = threadIdx.x % C4, rsub = threadIdx.x / C4, rper = blockDim.x / C4;
-  float4 m = __ldg(mean + c), r = __ldg(rstd + c);
+  float4 m = __ldg(mean + c), r = __ldg(rstd + c), ga = __ldg(gamma + c), be = __ldg(beta + c);
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
   for (long long row = (long long)blockIdx.x * rper + rsub; row < N; row += (long long)gridDim.x * rper) {
     float4 v = __ldg(y + row * C4 + c), g = __ldg(dout + row * C4 + c);
     if (relu) {
-      float4 o = __ldg(out + row * C4 + c);
+      float4 o = make_float4((v.x - m.x) * r.x * ga.x + be.x, (v.y - m.y) * r.y * ga.y + be.y, (v.z - m.z) * r.z * ga.z + be.z,
+                             (v.w - m.w) * r.w * ga.w + be.w);
       g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
     }
     s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
@@ -89,7 +91,7 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_stats_kernel(const float4* __
 // extra_dbeta / extra_dgamma (nullable): contributions of rows that are not materialised (the
 // constant background cells of the decoder map) to the two batch sums
 // backward pass 2: dy = gamma * rstd * (g - dbeta / count - xhat * dgamma / count)
-__global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const float4* __restrict__ y, const float4* __restrict__ out,
+__global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const float4* __restrict__ y, const float4* __restrict__ beta,
                                                                 const float4* __restrict__ dout, const float4* __restrict__ mean,
                                                                 const float4* __restrict__ rstd, const float4* __restrict__ gamma,
                                                                 const float4* __restrict__ dbeta, const float4* __restrict__ dgamma,
@@ -100,7 +102,9 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const float4* __
     float4 v = __ldg(y + i), g = __ldg(dout + i), m = __ldg(mean + c), r = __ldg(rstd + c), ga = __ldg(gamma + c);
     float4 db = __ldg(dbeta + c), dg = __ldg(dgamma + c);
     if (relu) {
-      float4 o = __ldg(out + i);
+      float4 be = __ldg(beta + c);
+      float4 o = make_float4((v.x - m.x) * r.x * ga.x + be.x, (v.y - m.y) * r.y * ga.y + be.y, (v.z - m.z) * r.z * ga.z + be.z,
+                             (v.w - m.w) * r.w * ga.w + be.w);
       g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
     }
     float4 d;
@@ -150,9 +154,10 @@ extern "C" int gdmae_batchnorm_relu_fwd(const float* y, const float* gamma, cons
   return GDMAE_OK;
 }
 
-// dy (N,C), dgamma (C), dbeta (C) from dout; `out` is the forward output (ReLU mask), count as in forward.
+// dy (N,C), dgamma (C), dbeta (C) from dout; beta (C) with gamma / mean / rstd rebuilds the ReLU mask from y (the forward
+// output is not read), count as in forward.
 // extra_dbeta / extra_dgamma (C, nullable) are added to the batch sums (rows that exist only implicitly).
-extern "C" int gdmae_batchnorm_relu_bwd(const float* y, const float* out, const float* dout, const float* gamma, const float* mean,
+extern "C" int gdmae_batchnorm_relu_bwd(const float* y, const float* beta, const float* dout, const float* gamma, const float* mean,
                                         const float* rstd, int64_t N, int C, double count, int relu, const float* extra_dbeta,
                                         const float* extra_dgamma, float* dy, float* dgamma, float* dbeta, void* workspace,
                                         size_t ws_bytes, void* stream_) {
@@ -166,15 +171,15 @@ extern "C" int gdmae_batchnorm_relu_bwd(const float* y, const float* out, const 
     GDMAE_CHECK_CUDA(cudaMemsetAsync(partial, 0, (size_t)2 * C * 4, st));
     grid = 1;
   } else {
-    bn_relu_bwd_stats_kernel<<<grid, threads, 0, st>>>((const float4*)y, (const float4*)out, (const float4*)dout, (const float4*)mean,
-                                                       (const float4*)rstd, N, C4, relu, partial);
+    bn_relu_bwd_stats_kernel<<<grid, threads, 0, st>>>((const float4*)y, (const float4*)gamma, (const float4*)beta, (const float4*)dout,
+                                                       (const float4*)mean, (const float4*)rstd, N, C4, relu, partial);
     GDMAE_LAUNCH_CHECK();
   }
   bn_bwd_finalize_kernel<<<gdmae_div_up(C * 32, 256), 256, 0, st>>>(partial, grid, C, extra_dbeta, extra_dgamma, dbeta, dgamma);
   GDMAE_LAUNCH_CHECK();
   if (N == 0) return GDMAE_OK;
   bn_relu_bwd_apply_kernel<<<gdmae_grid(N * C4, 256, 16), 256, 0, st>>>(
-      (const float4*)y, (const float4*)out, (const float4*)dout, (const float4*)mean, (const float4*)rstd, (const float4*)gamma,
+      (const float4*)y, (const float4*)beta, (const float4*)dout, (const float4*)mean, (const float4*)rstd, (const float4*)gamma,
       (const float4*)dbeta, (const float4*)dgamma, (float)(1.0 / count), N * C4, C4, relu, (float4*)dy);
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;

@@ -82,3 +82,25 @@ __device__ __forceinline__ float warp_min(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+extern "C" int gdmae_timing_on(void);
+extern "C" void gdmae_timing_push(int kind, int d, int64_t n, int64_t bytes, void* e0, void* e1);
+// bench-only CUDA events around one launch sequence (no-op unless gdmae_timing_enable(1))
+struct GdmaeSpan {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaStream_t st;
+  explicit GdmaeSpan(cudaStream_t s) : st(s) {
+    if (gdmae_timing_on()) {
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+      cudaEventRecord(e0, st);
+    }
+  }
+  void end(int kind, int d, int64_t n, int64_t bytes) {
+    if (e0) {
+      cudaEventRecord(e1, st);
+      gdmae_timing_push(kind, d, n, bytes, e0, e1);
+    }
+  }
+};
+
+

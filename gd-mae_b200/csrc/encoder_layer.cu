@@ -62,27 +62,6 @@ int ew_bias_gelu_fwd(const void* h, int h_bf16, const float* bias, int64_t N, in
 int ew_bias_gelu_bwd(const void* h, const void* dg, int hdg_bf16, const float* bias, int64_t N, int C, float* dh, void* dh_bf16,
                      float* dbias, int accumulate, void* workspace, size_t ws_bytes, void* stream_);
 
-extern "C" int gdmae_timing_on(void);
-extern "C" void gdmae_timing_push(int kind, int d, int64_t n, int64_t bytes, void* e0, void* e1);
-// bench-only CUDA events around one launch sequence (no-op unless gdmae_timing_enable(1))
-struct ElSpan {
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  cudaStream_t st;
-  explicit ElSpan(cudaStream_t s) : st(s) {
-    if (gdmae_timing_on()) {
-      cudaEventCreate(&e0);
-      cudaEventCreate(&e1);
-      cudaEventRecord(e0, st);
-    }
-  }
-  void end(int kind, int d, int64_t n, int64_t bytes) {
-    if (e0) {
-      cudaEventRecord(e1, st);
-      gdmae_timing_push(kind, d, n, bytes, e0, e1);
-    }
-  }
-};
-
 #define EL_CALL(expr)        \
   do {                       \
     int _rc = (expr);        \
@@ -124,7 +103,7 @@ extern "C" int gdmae_encoder_layer_fwd(const gdmae_encoder_layer_args* a) {
   EL_CALL(el_gemm(a, 0, 1, N, 3 * d, d, xg, d, a->w_in_g, d, a->qkv, 3 * d, tc, 0.f));
   pos_lut_kernel<<<gdmae_div_up(64ll * 2 * d * 32, 256), 256, 0, st>>>(a->pos_table, a->w_in, a->b_in, d, a->lut);
   GDMAE_LAUNCH_CHECK();
-  ElSpan span(st);
+  GdmaeSpan span(st);
   if (tc)
     EL_CALL(gdmae_sra_attention_fwd_tc(a->qkv, a->lut, a->row_info, a->bin_units, N, d, a->nhead, a->tau, a->tau_min, a->b_in + 2 * d, bf, a->o,
                                        a->lse, a->stream));
@@ -199,7 +178,7 @@ extern "C" int gdmae_encoder_layer_bwd(const gdmae_encoder_layer_args* a) {
   const int tc = a->sra_tensor_cores ? 1 : 0;
   EL_CALL(el_gemm(a, 0, 0, N, d, d, dz1_op, d, a->w_o_g, d, dout, d, tc, 0.f));
   GDMAE_CHECK_CUDA(cudaMemsetAsync(dtau_sum, 0, sizeof(double), st));
-  ElSpan span(st);
+  GdmaeSpan span(st);
   if (tc)
     EL_CALL(gdmae_sra_attention_bwd_tc(a->qkv, a->lut, a->row_info, a->bin_units, N, d, a->nhead, a->tau, a->tau_min, a->lse, dout, dqkv, dtau_sum,
                                        a->stream));

@@ -289,7 +289,11 @@ __global__ void __launch_bounds__(256) vfe2_stats_kernel(const T* __restrict__ y
 
 // bn2 + ReLU + per-pillar max / argmax in one pass over y2: one warp per pillar, lane = 4 channels.
 // Ties keep the lowest point index (CSR rows ascend), like the stand-alone segment max.
-template <typename T>
+// SORTED: the point rows are already in pillar (CSR) order (seg_pts == NULL, pillar m owns rows [seg_off[m], seg_off[m+1])):
+// no index indirection, the rows of a pillar are independent loads (four in flight) and the next pillar's offsets are
+// fetched while the current one is reduced.  Unsorted rows chain seg_pts[k] -> row and are latency bound (r1: 184 us for
+// 475 MB; a four-rows-in-flight variant of the unsorted loop was slower still, 236 us).
+template <typename T, bool SORTED>
 __global__ void __launch_bounds__(256) vfe2_apply_max_kernel(const T* __restrict__ y, const int* __restrict__ seg_off,
                                                              const int* __restrict__ seg_pts, int M, const float* __restrict__ mean,
                                                              const float* __restrict__ rstd, const float* __restrict__ gamma,
@@ -299,24 +303,53 @@ __global__ void __launch_bounds__(256) vfe2_apply_max_kernel(const T* __restrict
   const float4 mu = __ldg(reinterpret_cast<const float4*>(mean) + lane), rs = __ldg(reinterpret_cast<const float4*>(rstd) + lane);
   const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + lane), be = __ldg(reinterpret_cast<const float4*>(beta) + lane);
   const float4 a = make_float4(rs.x * ga.x, rs.y * ga.y, rs.z * ga.z, rs.w * ga.w);
-  for (int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < M; m += (gridDim.x * blockDim.x) >> 5) {
-    const int s = seg_off[m], e = seg_off[m + 1];
+  const int stride = (gridDim.x * blockDim.x) >> 5;
+  int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int s = m < M ? __ldg(seg_off + m) : 0, e = m < M ? __ldg(seg_off + m + 1) : 0;
+  while (m < M) {
+    const int mn = m + stride;
+    const int sn = mn < M ? __ldg(seg_off + mn) : 0, en = mn < M ? __ldg(seg_off + mn + 1) : 0;
     float4 best = make_float4(0.f, 0.f, 0.f, 0.f);
     int4 bi = make_int4(-1, -1, -1, -1);
-    for (int k = s; k < e; ++k) {
-      const int pnt = seg_pts[k];
-      float4 v = VT<T>::load4(y, (long long)pnt * (V_C2 / 4) + lane);
-      v.x = fmaxf(fmaf(v.x - mu.x, a.x, be.x), 0.f);
-      v.y = fmaxf(fmaf(v.y - mu.y, a.y, be.y), 0.f);
-      v.z = fmaxf(fmaf(v.z - mu.z, a.z, be.z), 0.f);
-      v.w = fmaxf(fmaf(v.w - mu.w, a.w, be.w), 0.f);
-      if (k == s || v.x > best.x) { best.x = v.x; bi.x = pnt; }
-      if (k == s || v.y > best.y) { best.y = v.y; bi.y = pnt; }
-      if (k == s || v.z > best.z) { best.z = v.z; bi.z = pnt; }
-      if (k == s || v.w > best.w) { best.w = v.w; bi.w = pnt; }
+    if (SORTED) {
+      for (int k = s; k < e; k += 4) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (k + u < e) v[u] = VT<T>::load4(y, (long long)(k + u) * (V_C2 / 4) + lane);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (k + u < e) {
+            const int pnt = k + u;
+            float4 w;
+            w.x = fmaxf(fmaf(v[u].x - mu.x, a.x, be.x), 0.f);
+            w.y = fmaxf(fmaf(v[u].y - mu.y, a.y, be.y), 0.f);
+            w.z = fmaxf(fmaf(v[u].z - mu.z, a.z, be.z), 0.f);
+            w.w = fmaxf(fmaf(v[u].w - mu.w, a.w, be.w), 0.f);
+            if (pnt == s || w.x > best.x) { best.x = w.x; bi.x = pnt; }
+            if (pnt == s || w.y > best.y) { best.y = w.y; bi.y = pnt; }
+            if (pnt == s || w.z > best.z) { best.z = w.z; bi.z = pnt; }
+            if (pnt == s || w.w > best.w) { best.w = w.w; bi.w = pnt; }
+          }
+        }
+      }
+    } else {
+      for (int k = s; k < e; ++k) {
+        const int pnt = seg_pts[k];
+        float4 v = VT<T>::load4(y, (long long)pnt * (V_C2 / 4) + lane);
+        v.x = fmaxf(fmaf(v.x - mu.x, a.x, be.x), 0.f);
+        v.y = fmaxf(fmaf(v.y - mu.y, a.y, be.y), 0.f);
+        v.z = fmaxf(fmaf(v.z - mu.z, a.z, be.z), 0.f);
+        v.w = fmaxf(fmaf(v.w - mu.w, a.w, be.w), 0.f);
+        if (k == s || v.x > best.x) { best.x = v.x; bi.x = pnt; }
+        if (k == s || v.y > best.y) { best.y = v.y; bi.y = pnt; }
+        if (k == s || v.z > best.z) { best.z = v.z; bi.z = pnt; }
+        if (k == s || v.w > best.w) { best.w = v.w; bi.w = pnt; }
+      }
     }
     reinterpret_cast<float4*>(out)[(long long)m * (V_C2 / 4) + lane] = best;
     reinterpret_cast<int4*>(arg)[(long long)m * (V_C2 / 4) + lane] = bi;
+    m = mn; s = sn; e = en;
   }
 }
 
@@ -350,7 +383,7 @@ __global__ void __launch_bounds__(256) vfe2_bwd_stats_kernel(int M, const float*
 }
 
 // dy2[p] = gamma rstd (g[p] - dbeta/n - xhat[p] dgamma/n), g[p, c] = dout[m, c] iff p is pillar m's argmax for c
-template <typename T>
+template <typename T, bool SORTED>
 __global__ void __launch_bounds__(256) vfe2_bwd_apply_kernel(const T* __restrict__ y, const int* __restrict__ seg_off,
                                                              const int* __restrict__ seg_pts, int M, const float* __restrict__ out,
                                                              const int* __restrict__ arg, const float* __restrict__ dout,
@@ -366,12 +399,14 @@ __global__ void __launch_bounds__(256) vfe2_bwd_apply_kernel(const T* __restrict
   const float4 a2 = make_float4(a0.x * dg.x * inv_n, a0.y * dg.y * inv_n, a0.z * dg.z * inv_n, a0.w * dg.w * inv_n);
   for (int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < M; m += (gridDim.x * blockDim.x) >> 5) {
     const int s = seg_off[m], e = seg_off[m + 1];
+    // (r1, sorted rows: recomputing the arg-max here instead of reading it - two sweeps over the pillar's rows - cost 377 us
+    // against 259 us, and a four-rows-in-flight body 259 us against this loop's ~240 us: kept simple)
     const float4 o = __ldg(reinterpret_cast<const float4*>(out) + (long long)m * (V_C2 / 4) + lane);
     float4 g = __ldg(reinterpret_cast<const float4*>(dout) + (long long)m * (V_C2 / 4) + lane);
     const int4 ai = __ldg(reinterpret_cast<const int4*>(arg) + (long long)m * (V_C2 / 4) + lane);
     g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
     for (int k = s; k < e; ++k) {
-      const int pnt = seg_pts[k];
+      const int pnt = SORTED ? k : seg_pts[k];
       const float4 v = VT<T>::load4(y, (long long)pnt * (V_C2 / 4) + lane);
       float4 r;
       r.x = a0.x * (ai.x == pnt ? g.x : 0.f) - a1.x - (v.x - mu.x) * rs.x * a2.x;
@@ -448,13 +483,17 @@ extern "C" int gdmae_vfe_mlp_fwd(const gdmae_vfe_mlp_args* a) {
                                                                   a->running_mean2, a->running_var2);
   GDMAE_LAUNCH_CHECK();
   const int g3 = gdmae_grid((long long)a->M * 32, 256, 16);
-  if (bf)
-    vfe2_apply_max_kernel<vbf16><<<g3, 256, 0, st>>>((const vbf16*)a->y2, a->seg_offsets, a->seg_points, (int)a->M, a->mean2, a->rstd2,
-                                                     a->g2, a->b2, a->out, a->argmax);
-  else
-    vfe2_apply_max_kernel<float><<<g3, 256, 0, st>>>((const float*)a->y2, a->seg_offsets, a->seg_points, (int)a->M, a->mean2, a->rstd2,
-                                                     a->g2, a->b2, a->out, a->argmax);
+  GdmaeSpan span(st);
+#define VFE_APPLY_MAX(T, S)                                                                                                        \
+  vfe2_apply_max_kernel<T, S><<<g3, 256, 0, st>>>((const T*)a->y2, a->seg_offsets, a->seg_points, (int)a->M, a->mean2, a->rstd2, a->g2, \
+                                                  a->b2, a->out, a->argmax)
+  const bool sorted = a->seg_points == nullptr;      // point rows already in pillar order
+  if (bf) { if (sorted) VFE_APPLY_MAX(vbf16, true); else VFE_APPLY_MAX(vbf16, false); }
+  else { if (sorted) VFE_APPLY_MAX(float, true); else VFE_APPLY_MAX(float, false); }
+#undef VFE_APPLY_MAX
   GDMAE_LAUNCH_CHECK();
+  // pillar scatter-max, algorithmic bytes: point rows in, segment index in, pillar rows out
+  span.end(2, V_C2, Np, Np * V_C2 * (bf ? 2 : 4) + Np * 4 + a->M * V_C2 * 4);
   return GDMAE_OK;
 }
 
@@ -476,12 +515,13 @@ extern "C" int gdmae_vfe_mlp_bwd(const gdmae_vfe_mlp_args* a) {
   bn_bwd_finalize_kernel<<<gdmae_div_up(V_C2 * 32, 256), 256, 0, st>>>(partial, gs, V_C2, nullptr, nullptr, a->tmp_dbeta2, a->tmp_dgamma2);
   GDMAE_LAUNCH_CHECK();
   const int g3 = gdmae_grid((long long)M * 32, 256, 16);
-  if (bf)
-    vfe2_bwd_apply_kernel<vbf16><<<g3, 256, 0, st>>>((const vbf16*)a->y2, a->seg_offsets, a->seg_points, M, a->out, a->argmax, a->dout,
-                                                     a->mean2, a->rstd2, a->g2, a->tmp_dbeta2, a->tmp_dgamma2, inv_n, (vbf16*)a->dy2);
-  else
-    vfe2_bwd_apply_kernel<float><<<g3, 256, 0, st>>>((const float*)a->y2, a->seg_offsets, a->seg_points, M, a->out, a->argmax, a->dout,
-                                                     a->mean2, a->rstd2, a->g2, a->tmp_dbeta2, a->tmp_dgamma2, inv_n, (float*)a->dy2);
+#define VFE_BWD_APPLY(T, S)                                                                                                        \
+  vfe2_bwd_apply_kernel<T, S><<<g3, 256, 0, st>>>((const T*)a->y2, a->seg_offsets, a->seg_points, M, a->out, a->argmax, a->dout, a->mean2, \
+                                                  a->rstd2, a->g2, a->tmp_dbeta2, a->tmp_dgamma2, inv_n, (T*)a->dy2)
+  const bool sorted = a->seg_points == nullptr;
+  if (bf) { if (sorted) VFE_BWD_APPLY(vbf16, true); else VFE_BWD_APPLY(vbf16, false); }
+  else { if (sorted) VFE_BWD_APPLY(float, true); else VFE_BWD_APPLY(float, false); }
+#undef VFE_BWD_APPLY
   GDMAE_LAUNCH_CHECK();
   // ---- linear 2: dW2 (C2, C1) = dy2^T h1, dh1 (Np, C1) = dy2 W2
   VFE_CALL(gdmae_gemm(1, 0, V_C2, V_C1, Np, a->dy2, V_C2, a->h1, V_C1, a->gemm_mode, a->d_W2, V_C1, 0, acc ? 1.f : 0.f, a->stream));

@@ -359,7 +359,7 @@ class VfeMlpFunction(torch.autograd.Function):
         for name, t in (("x", x), ("seg_offsets", seg_offsets), ("seg_points", seg_points), ("W1", W1), ("g1", g1), ("b1", b1),
                         ("g2", g2), ("b2", b2), ("W2_g", W2g), ("running_mean1", rm1), ("running_var1", rv1), ("running_mean2", rm2),
                         ("running_var2", rv2), ("h1", h1), ("y2", y2), ("out", out), ("argmax", arg)):
-            setattr(A, name, t.data_ptr())
+            setattr(A, name, None if t is None else t.data_ptr())      # seg_points None: rows of x already in pillar order
         sb = stats.data_ptr()
         for i, name in enumerate(("mean1", "rstd1", "mean2", "rstd2", "tmp_dbeta1", "tmp_dgamma1", "tmp_dbeta2", "tmp_dgamma2")):
             setattr(A, name, sb + 4 * 128 * i)
@@ -367,8 +367,8 @@ class VfeMlpFunction(torch.autograd.Function):
         ws = L.workspace(lib.gdmae_vfe_mlp_workspace_bytes(K), dev)
         A.ws, A.ws_bytes, A.stream = ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream
         L.check(lib.gdmae_vfe_mlp_fwd(ctypes.byref(A)), "gdmae_vfe_mlp_fwd")
-        ctx.save_for_backward(x, seg_offsets, seg_points, W1, g1, b1, W2, g2, b2)
-        ctx.args, ctx.keep = A, (W2g, h1, y2, stats, out, arg)
+        ctx.save_for_backward(x, seg_offsets, W1, g1, b1, W2, g2, b2)
+        ctx.args, ctx.keep = A, (W2g, h1, y2, stats, out, arg, seg_points)
         ctx.params = (W1, g1, b1, W2, g2, b2)
         return out
 
@@ -408,7 +408,13 @@ def vfe_mlp_supported(mlp, x):
 
 def vfe_mlp(mlp, x, ps):
     bn1, bn2 = mlp[1], mlp[4]
-    out = VfeMlpFunction.apply(x, ps.seg_offsets, ps.seg_points, ps.n_pillars, bn1.eps, bn1.momentum, bn1.running_mean,
+    # Point rows in pillar (CSR) order: every point-sized tensor of the node (h1, y2, their gradients) is then walked
+    # sequentially by the per-pillar kernels (seg_points = None selects their sorted mode): the pillar scatter-max and
+    # its backward stream contiguous rows instead of chasing seg_points[k] -> row.  x is 10/11 floats per point, so this
+    # one gather is cheap; the per-pillar results
+    # do not depend on the row order (BatchNorm sums change in the last bits only).
+    x = x.index_select(0, ps.seg_points)
+    out = VfeMlpFunction.apply(x, ps.seg_offsets, None, ps.n_pillars, bn1.eps, bn1.momentum, bn1.running_mean,
                                bn1.running_var, bn2.running_mean, bn2.running_var, mlp[0].weight, bn1.weight, bn1.bias,
                                mlp[3].weight, bn2.weight, bn2.bias)
     bn1.num_batches_tracked += 1
@@ -467,14 +473,14 @@ class BatchNormReLUFunction(torch.autograd.Function):
                 "gdmae_batchnorm_relu_fwd")
         shift = beta - mean * rstd * gamma
         bg = torch.relu(shift) if relu else shift
-        ctx.save_for_backward(y, out, gamma, mean, rstd, shift)
+        ctx.save_for_backward(y, beta, gamma, mean, rstd, shift)    # the ReLU mask is rebuilt from y: `out` is not kept
         ctx.count, ctx.relu = count, relu
         return out, bg
 
     @staticmethod
     @_ops._bwd
     def backward(ctx, dout, dbg):
-        y, out, gamma, mean, rstd, shift = ctx.saved_tensors
+        y, beta, gamma, mean, rstd, shift = ctx.saved_tensors
         N, C = y.shape
         dev = y.device
         e_db = e_dg = None
@@ -487,7 +493,7 @@ class BatchNormReLUFunction(torch.autograd.Function):
         dbeta = torch.empty((C,), dtype=F32, device=dev)
         lib = L.lib()
         ws = L.workspace(lib.gdmae_batchnorm_workspace_bytes(C), dev)
-        L.check(lib.gdmae_batchnorm_relu_bwd(L.P(y), L.P(out), L.P(dout.contiguous()), L.P(gamma), L.P(mean), L.P(rstd), L.i64(N), C,
+        L.check(lib.gdmae_batchnorm_relu_bwd(L.P(y), L.P(beta), L.P(dout.contiguous()), L.P(gamma), L.P(mean), L.P(rstd), L.i64(N), C,
                                              ctypes.c_double(ctx.count), int(ctx.relu), L.P(e_db), L.P(e_dg), L.P(dy), L.P(dgamma),
                                              L.P(dbeta), L.P(ws), ctypes.c_size_t(ws.numel()), L.stream()),
                 "gdmae_batchnorm_relu_bwd")

@@ -188,7 +188,9 @@ int gdmae_gather_add_rows(const float* x, const float* table, const uint8_t* idx
  * One call = DynVFE's dvfe_mlps (Linear(K,64,no bias) -> BatchNorm1d(train) -> ReLU -> Linear(64,128,no bias) ->
  * BatchNorm1d(train) -> ReLU) followed by torch_scatter.scatter_max over the pillars
  * (pcdet/models/backbones_3d/vfe/dyn_vfe.py:105-111, network_utils.py:7-21), forward or backward.
- * x (Np,K) fp32 point features; seg_offsets/seg_points = pillar CSR from gdmae_dynvox; "op" buffers are fp32
+ * x (Np,K) fp32 point features; seg_offsets/seg_points = pillar CSR from gdmae_dynvox (seg_points == NULL: the rows of x
+ * are already in pillar order, pillar m owns rows [seg_offsets[m], seg_offsets[m+1]) - the per-pillar kernels then stream
+ * contiguous rows and argmax holds row numbers in that order); "op" buffers are fp32
  * (gemm_mode 0/2) or bf16 (gemm_mode 1).  Backward writes (accumulate=0) or adds to (accumulate=1) d_*. */
 typedef struct gdmae_vfe_mlp_args {
   int64_t Np, M;
@@ -291,7 +293,7 @@ size_t gdmae_batchnorm_workspace_bytes(int C);
 int gdmae_batchnorm_relu_fwd(const float* y, const float* gamma, const float* beta, int64_t N, int C, double count,
                              float eps, float momentum, int relu, float* out, float* mean, float* rstd,
                              float* running_mean, float* running_var, void* workspace, size_t ws_bytes, void* stream);
-int gdmae_batchnorm_relu_bwd(const float* y, const float* out, const float* dout, const float* gamma, const float* mean,
+int gdmae_batchnorm_relu_bwd(const float* y, const float* beta, const float* dout, const float* gamma, const float* mean,
                              const float* rstd, int64_t N, int C, double count, int relu, const float* extra_dbeta,
                              const float* extra_dgamma, float* dy, float* dgamma, float* dbeta, void* workspace,
                              size_t ws_bytes, void* stream);
