@@ -197,10 +197,29 @@ def main():
         with autocast:
             return trainer.step({"points": dev_batches[i % n_pool], "batch_size": B_PER_GPU})
 
+    # e2e: every step copies its input batch from pinned host memory and reads its loss back.  The copy of step i+1 is
+    # issued on a side stream while step i computes (the double buffering a DataLoader with pin_memory gives), so the
+    # 30 MB H2D transfer overlaps compute instead of preceding it; all copies lie inside the timed region.
+    copy_stream = torch.cuda.Stream(device=dev)
+    pending = {}
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            t = host_batches[i % n_pool].to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        pending[i] = (t, ev)
+
     def step_e2e(i):
-        bd = {"points": host_batches[i % n_pool].to(dev, non_blocking=True), "batch_size": B_PER_GPU}
+        if i not in pending:
+            prefetch(i)
+        pts, ev = pending.pop(i)
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev)
+        pts.record_stream(cur)
+        prefetch(i + 1)
         with autocast:
-            loss = trainer.step(bd)
+            loss = trainer.step({"points": pts, "batch_size": B_PER_GPU})
         return loss.item()  # D2H read of the step's result
 
     def barrier():
@@ -293,7 +312,8 @@ def main():
                    "grid": "468x468x1", "parallelism": f"dp{world}", "params": trainer.n_params,
                    "l2": "per-step working set (>2 GB of activations) exceeds the 126 MB L2; input batch changes every step"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(pts_per_batch * 6 * 4), "d2h_bytes_per_step": 4 + 2 * 4 * (4 + B_PER_GPU + 1)},
+                "h2d_bytes_per_step": int(pts_per_batch * 6 * 4), "d2h_bytes_per_step": 4 + 2 * 4 * (4 + B_PER_GPU + 1),
+                "input_pipeline": "pinned host batch of step i+1 copied on a side stream during step i; loss.item() every step"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
         "final_loss": float(last_loss), "final_loss_e2e": float(last_e2e), "host_cores": len(os.sched_getaffinity(0)),
     }
