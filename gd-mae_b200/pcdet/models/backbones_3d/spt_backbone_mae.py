@@ -12,7 +12,7 @@ import torch.nn.functional as F
 
 from .... import fused as _fused
 from .... import ops as _ops
-from ...utils.spconv_utils import spconv, plan_pyramid
+from ...utils.spconv_utils import plan_pyramid_launch, plan_pyramid_finish, spconv, plan_pyramid
 from .spt_backbone import SSTBlockV1
 
 
@@ -96,7 +96,7 @@ class SPTBackboneMAE(nn.Module):
         return _fused.batchnorm_relu(bn, u, self.training, relu=True, count=n_cells_total)
 
     def forward(self, batch_dict):
-        all_voxel_features, all_voxel_coords = batch_dict['voxel_features'], batch_dict['voxel_coords']
+        all_voxel_coords = batch_dict['voxel_coords']
         batch_size = batch_dict['batch_size']
         ps = batch_dict.get('pillar_set', None)
         if ps is None:
@@ -120,10 +120,17 @@ class SPTBackboneMAE(nn.Module):
         batch_dict['voxel_mae_mask'] = voxel_mae_mask
 
         vis_idx, indices, rank_grid, _ = _ops.visible_sites(all_voxel_coords, voxel_mae_mask, n_visible, batch_size, Y, X)
-        input_sp_tensor = spconv.SparseConvTensor(all_voxel_features[vis_idx.long()], indices, self.sparse_shape, batch_size,
-                                                  {"rank_grid": rank_grid})
+        input_sp_tensor = spconv.SparseConvTensor(None, indices, self.sparse_shape, batch_size, {"rank_grid": rank_grid})
         n_down = sum(1 for b in self.sst_blocks if b.conv_down is not None)
-        plan_pyramid(input_sp_tensor, n_down)  # all site sets of the pyramid, one host sync
+        plan = plan_pyramid_launch(input_sp_tensor, n_down)  # all site sets of the pyramid, counts copied asynchronously
+        # the index kernels above need voxel_coords only: a DynVFE that deferred its feature pass runs it now, so that its
+        # kernels cover the count read and the host-side structure building that follows
+        deferred = batch_dict.get('deferred_vfe', None)
+        if deferred is not None:
+            deferred()
+        all_voxel_features = batch_dict['voxel_features']
+        input_sp_tensor = input_sp_tensor.replace_feature(all_voxel_features.index_select(0, vis_idx))
+        plan_pyramid_finish(plan)                            # the one host sync of the backbone
 
         x = input_sp_tensor
         x_hidden = []

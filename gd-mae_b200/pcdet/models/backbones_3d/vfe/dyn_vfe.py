@@ -46,7 +46,22 @@ class DynVFE(VFETemplate):
     def forward(self, batch_dict, **kwargs):
         points = batch_dict['points']
         ps = _ops.dynamic_voxelize(points, self.point_cloud_range, self.voxel_size, self.grid_size, batch_dict['batch_size'])
-        n_feat = points.shape[1] - 1
+        batch_dict['points'] = ps.points
+        batch_dict['point_coords'] = ps.point_coords
+        batch_dict['point_inverse_indices'] = ps.inverse
+        batch_dict['voxel_coords'] = ps.voxel_coords
+        batch_dict['pillar_set'] = ps  # extra key: CSR / batch offsets reused by SPTBackboneMAE
+        if batch_dict.pop('defer_vfe_features', False):
+            # GDMAE.forward asks for this when the next module is SPTBackboneMAE: the backbone first launches its own index kernels
+            # (mask, visible sites, pyramid site sets - they need voxel_coords only), then calls this closure, then reads the
+            # site counts back.  The feature pass (~0.8 ms of GPU work) thus covers the host work that follows the count
+            # read, during which the GPU queue would otherwise run dry.
+            batch_dict['pillar_features'] = batch_dict['voxel_features'] = None
+            batch_dict['deferred_vfe'] = lambda: self._features(batch_dict, ps, points.shape[1] - 1)
+            return batch_dict
+        return self._features(batch_dict, ps, points.shape[1] - 1)
+
+    def _features(self, batch_dict, ps, n_feat):
         mean = _ops.segment_mean(ps.points, 1, n_feat, ps.seg_offsets, ps.seg_points, ps.n_pillars)
         x = _ops.vfe_point_features(ps, mean, self.point_cloud_range, self.voxel_size)
         mlp = self.dvfe_mlps[0]
@@ -57,12 +72,7 @@ class DynVFE(VFETemplate):
                 for k in range(0, len(mlp), 3):          # Linear (cuBLAS) -> fused BN1d(batch statistics)+ReLU, twice
                     x = _fused.batchnorm_relu(mlp[k + 1], mlp[k](x), self.training and mlp[k + 1].training)[0]
             x = _ops.SegmentMax.apply(x, ps.seg_offsets, ps.seg_points, ps.n_pillars)
-
-        batch_dict['points'] = ps.points
-        batch_dict['point_coords'] = ps.point_coords
-        batch_dict['point_inverse_indices'] = ps.inverse
-        batch_dict['voxel_coords'] = ps.voxel_coords
         batch_dict['pillar_features'] = x
         batch_dict['voxel_features'] = x
-        batch_dict['pillar_set'] = ps  # extra key: CSR / batch offsets reused by SPTBackboneMAE
+        batch_dict.pop('deferred_vfe', None)
         return batch_dict

@@ -65,7 +65,14 @@ class GDMAE(Detector3DTemplate):
         self.module_list = self.build_networks()
 
     def forward(self, batch_dict):
-        for cur_module in self.module_list:
+        # DynVFE followed by SPTBackboneMAE: let the backbone schedule the VFE's feature pass after its own index kernels
+        # (see DynVFE.forward); any other module order runs every module to completion like the reference
+        from ..backbones_3d.spt_backbone_mae import SPTBackboneMAE
+        from ..backbones_3d.vfe.dyn_vfe import DynVFE
+        mods = self.module_list
+        if len(mods) >= 2 and isinstance(mods[0], DynVFE) and isinstance(mods[1], SPTBackboneMAE):
+            batch_dict['defer_vfe_features'] = True
+        for cur_module in mods:
             batch_dict = cur_module(batch_dict)
         if self.training:
             loss, tb_dict, disp_dict = self.get_training_loss()

@@ -62,9 +62,13 @@ class SparseConvTensor:
         return out.permute(0, 3, 1, 2).contiguous() if channels_first else out
 
 
-def plan_pyramid(sp, n_levels):
-    """Site sets of ``n_levels`` successive stride-2 sparse convs starting at ``sp`` with ONE host
-    sync for all their counts; attaches the result to each level's structure cache."""
+_PINNED = {}
+
+
+def plan_pyramid_launch(sp, n_levels):
+    """First half of plan_pyramid: launches the site-set kernels of ``n_levels`` successive stride-2 sparse convs and an
+    asynchronous copy of their counts into pinned memory; returns a handle for plan_pyramid_finish.  GPU work enqueued
+    between the two calls runs while the host waits for the counts and builds the structures that depend on them."""
     B = sp.batch_size
     H, W = sp.spatial_shape
     idx, n_rows = sp.indices, sp.indices.shape[0]
@@ -73,7 +77,24 @@ def plan_pyramid(sp, n_levels):
         out_idx, grid, count, Ho, Wo = _ops.down_sites(idx, n_rows, B, H, W)
         pending.append((out_idx, grid, count, H, W, Ho, Wo))
         idx, n_rows, H, W = out_idx, out_idx.shape[0], Ho, Wo
-    counts = torch.cat([p[2] for p in pending]).cpu().tolist()  # the one sync
+    if not pending:
+        return sp, pending, None, None
+    host = _PINNED.get(n_levels)
+    if host is None:
+        host = _PINNED[n_levels] = torch.empty((n_levels,), dtype=torch.int32).pin_memory()
+    host.copy_(torch.cat([p[2] for p in pending]), non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    return sp, pending, host, ev
+
+
+def plan_pyramid_finish(handle):
+    sp, pending, host, ev = handle
+    if not pending:
+        return
+    ev.synchronize()                       # the one sync: waits for the count copy only, not for work enqueued after it
+    counts = host.tolist()
+    B = sp.batch_size
     cur = sp
     for (out_idx, grid, _, H, W, Ho, Wo), n in zip(pending, counts):
         out_idx = out_idx[:n]
@@ -82,6 +103,12 @@ def plan_pyramid(sp, n_levels):
         cur._struct["down"] = SimpleNamespace(indices=out_idx, spatial_shape=[Ho, Wo], nbr_down=nbr_down, nbr_up=nbr_up,
                                               struct=nxt_struct)
         cur = SparseConvTensor(None, out_idx, [Ho, Wo], B, nxt_struct)
+
+
+def plan_pyramid(sp, n_levels):
+    """Site sets of ``n_levels`` successive stride-2 sparse convs starting at ``sp`` with ONE host
+    sync for all their counts; attaches the result to each level's structure cache."""
+    plan_pyramid_finish(plan_pyramid_launch(sp, n_levels))
 
 
 class SparseModule(nn.Module):

@@ -1,0 +1,58 @@
+"""Where the GPU idles inside one training step: kernel timeline of the bench workload (torch profiler / CUPTI), gaps between
+consecutive kernels on the stream, attributed to the kernel that FOLLOWS the gap (the one the host was late to launch).
+usage: python tools/gpu_gaps.py > gpurun_out/gpu_gaps.txt"""
+import collections
+import json
+import os
+import sys
+import tempfile
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import gd_mae_b200  # noqa: E402,F401
+from gd_mae_b200 import config  # noqa: E402
+from gd_mae_b200.trainer import MAETrainer  # noqa: E402
+from oracle import gdmae_oracle as O  # noqa: E402  (synthetic scene generator only)
+
+torch.backends.cudnn.benchmark = True
+cfg = config.builtin_cfg("waymo_ssl")
+model = config.build_mae_model(cfg).cuda()
+config.set_precision(model, "bf16")
+trainer = MAETrainer(model, cfg.OPTIMIZATION, total_steps=100)
+pts = torch.from_numpy(O.synth_batch(list(range(8)), O.make_cfg("waymo_ssl"))).cuda()
+for _ in range(5):
+    trainer.step({"points": pts, "batch_size": 8})
+torch.cuda.synchronize()
+from torch.profiler import ProfilerActivity, profile  # noqa: E402
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+    for _ in range(3):
+        trainer.step({"points": pts, "batch_size": 8})
+    torch.cuda.synchronize()
+path = os.path.join(tempfile.gettempdir(), "trace.json")
+prof.export_chrome_trace(path)
+ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset") and "ts" in e]
+ev.sort(key=lambda e: e["ts"])
+adam = [i for i, e in enumerate(ev) if e["name"].startswith("adam")]
+seg = ev[adam[-2] + 1: adam[-1] + 1]          # the last full step
+busy = sum(e["dur"] for e in seg)
+span = seg[-1]["ts"] + seg[-1]["dur"] - seg[0]["ts"]
+print(f"last step: {len(seg)} GPU activities, busy {busy / 1e3:.2f} ms, span {span / 1e3:.2f} ms, idle {(span - busy) / 1e3:.2f} ms")
+gaps = collections.defaultdict(lambda: [0, 0.0])
+big = []
+end = seg[0]["ts"] + seg[0]["dur"]
+for prev, e in zip(seg, seg[1:]):
+    g = e["ts"] - end
+    if g > 2:
+        k = e["name"][:70]
+        gaps[k][0] += 1
+        gaps[k][1] += g
+        big.append((g, prev["name"][:50], e["name"][:50]))
+    end = max(end, e["ts"] + e["dur"])
+print("gap time by the kernel that follows the gap:")
+for k, (c, t) in sorted(gaps.items(), key=lambda x: -x[1][1])[:25]:
+    print(f"  {t:8.1f} us  {c:4d}x  {k}")
+print("largest single gaps (us, after -> before):")
+for g, a, b in sorted(big, reverse=True)[:25]:
+    print(f"  {g:8.1f}  {a}  ->  {b}")
