@@ -1,5 +1,5 @@
 // Encoder-layer executor: the whole forward (and the whole hand-written backward) of one SST
-// EncoderLayer issued from ONE C call - 4 cuBLASLt GEMMs + 6 kernels forward, 10 GEMMs + 11 kernels
+// EncoderLayer issued from ONE C call - 4 cuBLASLt GEMMs + 6 kernels forward, 10 GEMMs + 8 kernels
 // backward, all on the caller's stream.
 //
 // Replaces (reference file:line, relative to /root/reference):
@@ -193,8 +193,7 @@ extern "C" int gdmae_encoder_layer_bwd(const gdmae_encoder_layer_args* a) {
   EL_CALL(gdmae_gather_add_rows(a->x, a->pos_table, a->pos_of_token, N, d, bf ? nullptr : xpos, bf ? xpos : nullptr, a->stream));
   EL_CALL(el_gemm(a, 1, 0, 2 * d, d, N, dqkv, 3 * d, xpos, d, a->d_w_in, d, 0, wbeta));
   EL_CALL(el_gemm(a, 1, 0, d, d, N, (const char*)dqkv + (size_t)2 * d * es, 3 * d, xg, d, a->d_w_in + (size_t)2 * d * d, d, 0, wbeta));
-  EL_CALL(gdmae_colsum(dqkv, bf, N, 3 * d, 0, 2 * d, a->d_b_in, acc, rw, rw_bytes, a->stream));
-  EL_CALL(gdmae_colsum(dqkv, bf, N, 3 * d, 2 * d, d, a->d_b_in + 2 * d, acc, rw, rw_bytes, a->stream));
+  EL_CALL(gdmae_colsum(dqkv, bf, N, 3 * d, 0, 3 * d, a->d_b_in, acc, rw, rw_bytes, a->stream));   // q, k and v biases in one pass
   EL_CALL(el_gemm(a, 0, 0, N, d, 3 * d, dqkv, 3 * d, a->w_in_g, d, dz1, d, 0, 1.f));   // dx = residual + through the projection
   return GDMAE_OK;
 }

@@ -526,3 +526,44 @@ def test_once_dense_stress_step_matches_oracle(G):
     num = sum(float(((sd[k].cpu().double() - P[k].double()) ** 2).sum()) for k in P)
     den = sum(float(((P[k].double() - P0[k].double()) ** 2).sum()) for k in P)
     assert (num / den) ** 0.5 < 5e-2, (num / den) ** 0.5
+
+
+# ------------------------------------------------------------------------------ work units of the tensor-core SRA kernels
+def test_sra_bin_units_cover_every_row(G, golden):
+    """gdmae_sra_bin_units: per 64-row bin the packed (query tile, key range) units of the windows that START in the bin.
+    Every CSR row must be a query row of exactly one unit; a packed unit holds whole windows totalling <= 16 rows and
+    attends exactly to itself; the chunks of a larger window tile it and share its full key range."""
+    K = golden("window_kat")
+    g = torch.Generator().manual_seed(11)
+    cases = [(torch.from_numpy(K["b1.coords"])[:, [0, 2, 3]].int(), 2) + tuple(int(v) for v in K["b1.grid"][:2])[::-1]]
+    dense = torch.nonzero(torch.rand(2, 90, 70, generator=g) < 0.45).int()      # windows of every size up to 64
+    cases.append((dense, 2, 90, 70))
+    for idx, B, Y, X in cases:
+        for shifted in (0, 1):
+            t = G.ops.window_table(idx.cuda(), B, Y, X, shifted)
+            N = t.N
+            units = t.bin_units().cpu().view(-1, 64)
+            info = t.row_info.cpu()
+            start, end = info[:, 1].long(), info[:, 2].long()                    # window extent [start, end) of every CSR row
+            nbins = (N + 63) // 64
+            assert units.shape[0] >= nbins
+            seen = torch.zeros(N, dtype=torch.int32)
+            for b in range(nbins):
+                bin0 = 64 * b
+                row0 = bin0 if int(start[bin0]) == bin0 else int(end[bin0])      # first window that starts in the bin
+                nu = int(units[b, 48])
+                assert 0 <= nu <= 48 and int(units[b, 49]) == 0
+                for u in range(nu):
+                    code = int(units[b, u])
+                    q0, qn, k0, kn = code & 127, (code >> 7) & 31, (code >> 12) & 127, (code >> 19) & 127
+                    rows = torch.arange(row0 + q0, row0 + q0 + qn)
+                    seen[rows] += 1
+                    assert 1 <= qn <= 16 and row0 + k0 + kn <= N
+                    # the key range covers exactly the windows of the query rows
+                    assert int(start[rows].min()) == row0 + k0 and int(end[rows].max()) == row0 + k0 + kn
+                    if kn <= 16:
+                        assert (q0, qn) == (k0, kn)                              # packed run of whole windows
+                    else:
+                        assert int(start[rows[0]]) == row0 + k0 and int(end[rows[-1]]) == row0 + k0 + kn and (q0 - k0) % 16 == 0
+                        assert qn == min(16, k0 + kn - q0)
+            assert bool((seen == 1).all()), (int((seen == 0).sum()), int((seen > 1).sum()))
