@@ -224,11 +224,29 @@ def down_neighbor_maps(in_indices, in_grid, H, W, out_indices, out_grid):
     return down, up
 
 
+def _al(n):
+    return (n + 15) & ~15
+
+
 class WindowTable:
     """Window bookkeeping of one shift (replaces batch_win_inds / coors_in_win / drop levels /
-    flat2win_inds / key masks / pos dict of SSTInputLayer.forward, spt_backbone.py:106-135)."""
-    __slots__ = ("win_of_token", "pos_of_token", "inner", "level", "win_mask", "win_off", "win_tok", "lvl_rank",
-                 "lvl_counts", "row_info", "n_windows", "nWx", "nWy", "N", "_pos_long", "_bin_units")
+    flat2win_inds / key masks / pos dict of SSTInputLayer.forward, spt_backbone.py:106-135).
+    All arrays live in ONE device buffer; ``row_info`` and ``pos_of_token`` (the two the encoder layers read) are
+    views made up front, the others (``win_of_token``, ``inner``, ``level``, ``win_tok``, ``win_off``, ``lvl_rank``,
+    ``lvl_counts``, ``win_mask`` - used by the sst_utils mirrors and the tests) are made on first access: a step
+    builds six tables and the host was the bottleneck while it did so."""
+    __slots__ = ("_buf", "_fields", "_views", "row_info", "pos_of_token", "n_windows", "nWx", "nWy", "N", "_pos_long", "_bin_units")
+
+    def __getattr__(self, name):
+        # only reached for names without a slot value: the lazily viewed arrays
+        fields = object.__getattribute__(self, "_fields")
+        if name not in fields:
+            raise AttributeError(name)
+        views = object.__getattribute__(self, "_views")
+        if name not in views:
+            off, nbytes, dtype, shape = fields[name]
+            views[name] = self._buf[off:off + nbytes].view(dtype).view(shape)
+        return views[name]
 
     def bin_units(self):
         """work units of the tensor-core SRA kernels (gdmae_sra_bin_units), built on first use and cached: one table
@@ -255,23 +273,29 @@ def window_table(indices, B, H, W, shifted):
     nW = B * nWx * nWy
     t = WindowTable()
     t.N, t.n_windows, t.nWx, t.nWy = N, nW, nWx, nWy
-    t.win_of_token = torch.empty((max(N, 1),), dtype=I32, device=dev)[:N]
-    t.pos_of_token = torch.empty((max(N, 1),), dtype=torch.uint8, device=dev)[:N]
-    t.inner = torch.empty((max(N, 1),), dtype=I32, device=dev)[:N]
-    t.level = torch.empty((max(N, 1),), dtype=I32, device=dev)[:N]
-    t.win_mask = torch.empty((nW,), dtype=I64, device=dev)
-    t.win_off = torch.empty((nW + 1,), dtype=I32, device=dev)
-    t.win_tok = torch.empty((max(N, 1),), dtype=I32, device=dev)[:N]
-    t.lvl_rank = torch.empty((nW,), dtype=I32, device=dev)
-    t.lvl_counts = torch.empty((3,), dtype=I32, device=dev)
-    t.row_info = torch.empty((max(N, 1), 4), dtype=I32, device=dev)[:N]
+    fields, off = {}, 0
+    for name, count, dtype, width, shape in (("row_info", 4 * N, I32, 4, (N, 4)), ("win_of_token", N, I32, 4, (N,)),
+                                             ("inner", N, I32, 4, (N,)), ("level", N, I32, 4, (N,)), ("win_tok", N, I32, 4, (N,)),
+                                             ("win_off", nW + 1, I32, 4, (nW + 1,)), ("lvl_rank", nW, I32, 4, (nW,)),
+                                             ("lvl_counts", 3, I32, 4, (3,)), ("win_mask", nW, I64, 8, (nW,)),
+                                             ("pos_of_token", N, torch.uint8, 1, (N,))):
+        fields[name] = (off, count * width, dtype, shape)
+        off += _al(max(count, 1) * width)
+    buf = torch.empty((off,), dtype=torch.uint8, device=dev)
+    t._buf, t._fields, t._views = buf, fields, {}
+    base = buf.data_ptr()
+    ptr = {k: ctypes.c_void_p(base + v[0]) for k, v in fields.items()}
+    o, nb, dt, sh = fields["row_info"]
+    t.row_info = buf[o:o + nb].view(dt).view(sh)
+    o, nb, dt, sh = fields["pos_of_token"]
+    t.pos_of_token = buf[o:o + nb]
     t._pos_long = None
     t._bin_units = None
     lib = L.lib()
     ws = L.workspace(lib.gdmae_window_table_workspace_bytes(L.i64(nW)), dev)
-    L.check(lib.gdmae_window_table(L.P(indices), L.i64(N), B, H, W, int(bool(shifted)), L.P(t.win_of_token),
-                                   L.P(t.pos_of_token), L.P(t.inner), L.P(t.level), L.P(t.win_mask), L.P(t.win_off),
-                                   L.P(t.win_tok), L.P(t.lvl_rank), L.P(t.lvl_counts), L.P(t.row_info), L.P(ws),
+    L.check(lib.gdmae_window_table(L.P(indices), L.i64(N), B, H, W, int(bool(shifted)), ptr["win_of_token"],
+                                   ptr["pos_of_token"], ptr["inner"], ptr["level"], ptr["win_mask"], ptr["win_off"],
+                                   ptr["win_tok"], ptr["lvl_rank"], ptr["lvl_counts"], ptr["row_info"], L.P(ws),
                                    ctypes.c_size_t(ws.numel()), L.stream()), "gdmae_window_table")
     return t
 

@@ -12,7 +12,7 @@ import torch.nn.functional as F
 
 from .... import fused as _fused
 from .... import ops as _ops
-from ...utils.spconv_utils import plan_pyramid_launch, plan_pyramid_finish, spconv, plan_pyramid
+from ...utils.spconv_utils import plan_pyramid_launch, plan_pyramid_finish, prebuild_structures, spconv, plan_pyramid
 from .spt_backbone import SSTBlockV1
 
 
@@ -131,6 +131,9 @@ class SPTBackboneMAE(nn.Module):
         all_voxel_features = batch_dict['voxel_features']
         input_sp_tensor = input_sp_tensor.replace_feature(all_voxel_features.index_select(0, vis_idx))
         plan_pyramid_finish(plan)                            # the one host sync of the backbone
+        if self.training:
+            # window tables, neighbour maps and SRA work units of all three scales now, while the VFE kernels run
+            prebuild_structures(input_sp_tensor, n_down, tensor_core_units=bool(_ops.SRA_TENSOR_CORES))
 
         x = input_sp_tensor
         x_hidden = []

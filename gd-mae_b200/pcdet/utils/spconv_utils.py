@@ -111,6 +111,22 @@ def plan_pyramid(sp, n_levels):
     plan_pyramid_finish(plan_pyramid_launch(sp, n_levels))
 
 
+def prebuild_structures(sp, n_levels, tensor_core_units=False):
+    """Builds every index structure the ``n_levels`` + 1 pyramid levels below ``sp`` will ask for - submanifold neighbour
+    maps, both window tables (and the work units of the tensor-core SRA kernels) - in one go.  They depend on the site sets
+    only, so a caller that has GPU work in flight (SPTBackboneMAE right after it enqueued the VFE feature pass) gets all the
+    host-side table building done while the GPU is busy, instead of in front of each block with the queue empty."""
+    cur = sp
+    for lvl in range(n_levels + 1):
+        cur.subm_map()
+        for t in cur.window_tables():
+            if tensor_core_units:
+                t.bin_units()
+        if lvl < n_levels:
+            d = cur.down()
+            cur = SparseConvTensor(None, d.indices, d.spatial_shape, cur.batch_size, d.struct)
+
+
 class SparseModule(nn.Module):
     pass
 

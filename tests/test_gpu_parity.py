@@ -540,7 +540,7 @@ def test_sra_bin_units_cover_every_row(G, golden):
     cases.append((dense, 2, 90, 70))
     for idx, B, Y, X in cases:
         for shifted in (0, 1):
-            t = G.ops.window_table(idx.cuda(), B, Y, X, shifted)
+            t = G.ops.window_table(idx.contiguous().cuda(), B, Y, X, shifted)
             N = t.N
             units = t.bin_units().cpu().view(-1, 64)
             info = t.row_info.cpu()
