@@ -114,8 +114,9 @@ _workspaces = {}
 
 
 def workspace(nbytes, device):
-    """Grow-only scratch buffer per device (the C ABI never allocates)."""
-    key = (device.index if device.index is not None else torch.cuda.current_device())
+    """Grow-only scratch buffer per (device, stream) - the C ABI never allocates; work issued on a side stream
+    (GDMAE.prefetch_index) must not share scratch with the main stream."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)

@@ -95,7 +95,8 @@ class SPTBackboneMAE(nn.Module):
         # fused BN(batch statistics over all B*Y*X cells, zeros included)+ReLU on the sparse rows; bg = value of an empty cell
         return _fused.batchnorm_relu(bn, u, self.training, relu=True, count=n_cells_total)
 
-    def forward(self, batch_dict):
+    def _mask_and_sites(self, batch_dict):
+        """random masking per frame (spt_backbone_mae.py:96-100), the visible site set and the launch of the pyramid plan"""
         all_voxel_coords = batch_dict['voxel_coords']
         batch_size = batch_dict['batch_size']
         ps = batch_dict.get('pillar_set', None)
@@ -105,8 +106,6 @@ class SPTBackboneMAE(nn.Module):
             raise AssertionError("pillar grids only: z extent must be 1 (spt_backbone_mae.py:94)")
         Y, X = self.sparse_shape
         M = all_voxel_coords.shape[0]
-
-        # random masking, per frame (spt_backbone_mae.py:96-100)
         if 'voxel_mae_mask' in batch_dict and batch_dict['voxel_mae_mask'] is not None:
             voxel_mae_mask = batch_dict['voxel_mae_mask'].float().contiguous()
             n_visible = int((voxel_mae_mask == 0).sum().item())
@@ -118,22 +117,46 @@ class SPTBackboneMAE(nn.Module):
             n_visible = sum(int((ps.batch_offsets[b + 1] - ps.batch_offsets[b]) * (1 - self.mask_ratio))
                             for b in range(batch_size))
         batch_dict['voxel_mae_mask'] = voxel_mae_mask
-
         vis_idx, indices, rank_grid, _ = _ops.visible_sites(all_voxel_coords, voxel_mae_mask, n_visible, batch_size, Y, X)
-        input_sp_tensor = spconv.SparseConvTensor(None, indices, self.sparse_shape, batch_size, {"rank_grid": rank_grid})
+        sp = spconv.SparseConvTensor(None, indices, self.sparse_shape, batch_size, {"rank_grid": rank_grid})
         n_down = sum(1 for b in self.sst_blocks if b.conv_down is not None)
-        plan = plan_pyramid_launch(input_sp_tensor, n_down)  # all site sets of the pyramid, counts copied asynchronously
-        # the index kernels above need voxel_coords only: a DynVFE that deferred its feature pass runs it now, so that its
-        # kernels cover the count read and the host-side structure building that follows
+        plan = plan_pyramid_launch(sp, n_down)  # all site sets of the pyramid, counts copied asynchronously
+        return vis_idx, sp, n_down, plan
+
+    def index_pass(self, batch_dict):
+        """Everything of forward() that depends on voxel_coords only - mask, visible sites, pyramid site sets, neighbour
+        maps, window tables, SRA work units - stored under batch_dict['mae_index'].  GDMAE.prefetch_index runs it for the
+        NEXT batch on a side stream; forward() then has no host sync and no table building left."""
+        vis_idx, sp, n_down, plan = self._mask_and_sites(batch_dict)
+        plan_pyramid_finish(plan)
+        prebuild_structures(sp, n_down, tensor_core_units=bool(_ops.SRA_TENSOR_CORES))
+        batch_dict['mae_index'] = (vis_idx, sp)
+        return batch_dict
+
+    def forward(self, batch_dict):
+        batch_size = batch_dict['batch_size']
+        Y, X = self.sparse_shape
         deferred = batch_dict.get('deferred_vfe', None)
-        if deferred is not None:
-            deferred()
+        if batch_dict.get('mae_index', None) is not None:
+            vis_idx, input_sp_tensor = batch_dict['mae_index']     # prefetched one step ahead
+            if deferred is not None:
+                deferred()
+        else:
+            vis_idx, input_sp_tensor, n_down, plan = self._mask_and_sites(batch_dict)
+            # the index kernels above need voxel_coords only: a DynVFE that deferred its feature pass runs it now, so that
+            # its kernels cover the count read and the host-side structure building that follows
+            if deferred is not None:
+                deferred()
+            plan_pyramid_finish(plan)                            # the one host sync of the backbone
+            if self.training:
+                # window tables, neighbour maps and SRA work units of all three scales now, while the VFE kernels run
+                prebuild_structures(input_sp_tensor, n_down, tensor_core_units=bool(_ops.SRA_TENSOR_CORES))
+        all_voxel_coords = batch_dict['voxel_coords']
+        ps = batch_dict['pillar_set']
+        M = all_voxel_coords.shape[0]
+        voxel_mae_mask = batch_dict['voxel_mae_mask']
         all_voxel_features = batch_dict['voxel_features']
         input_sp_tensor = input_sp_tensor.replace_feature(all_voxel_features.index_select(0, vis_idx))
-        plan_pyramid_finish(plan)                            # the one host sync of the backbone
-        if self.training:
-            # window tables, neighbour maps and SRA work units of all three scales now, while the VFE kernels run
-            prebuild_structures(input_sp_tensor, n_down, tensor_core_units=bool(_ops.SRA_TENSOR_CORES))
 
         x = input_sp_tensor
         x_hidden = []

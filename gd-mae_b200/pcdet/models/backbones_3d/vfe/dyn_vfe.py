@@ -43,7 +43,9 @@ class DynVFE(VFETemplate):
     def get_output_feature_dim(self):
         return self.num_point_features
 
-    def forward(self, batch_dict, **kwargs):
+    def index_pass(self, batch_dict):
+        """Dynamic voxelisation only (one host sync for the counts): everything of forward() that does not touch the
+        parameters.  GDMAE.prefetch_index runs it for the NEXT batch on a side stream while this step's backward is queued."""
         points = batch_dict['points']
         ps = _ops.dynamic_voxelize(points, self.point_cloud_range, self.voxel_size, self.grid_size, batch_dict['batch_size'])
         batch_dict['points'] = ps.points
@@ -51,15 +53,22 @@ class DynVFE(VFETemplate):
         batch_dict['point_inverse_indices'] = ps.inverse
         batch_dict['voxel_coords'] = ps.voxel_coords
         batch_dict['pillar_set'] = ps  # extra key: CSR / batch offsets reused by SPTBackboneMAE
+        return batch_dict
+
+    def forward(self, batch_dict, **kwargs):
+        if batch_dict.get('pillar_set', None) is None:
+            self.index_pass(batch_dict)
+        ps = batch_dict['pillar_set']
+        n_feat = batch_dict['points'].shape[1] - 1
         if batch_dict.pop('defer_vfe_features', False):
             # GDMAE.forward asks for this when the next module is SPTBackboneMAE: the backbone first launches its own index kernels
             # (mask, visible sites, pyramid site sets - they need voxel_coords only), then calls this closure, then reads the
             # site counts back.  The feature pass (~0.8 ms of GPU work) thus covers the host work that follows the count
             # read, during which the GPU queue would otherwise run dry.
             batch_dict['pillar_features'] = batch_dict['voxel_features'] = None
-            batch_dict['deferred_vfe'] = lambda: self._features(batch_dict, ps, points.shape[1] - 1)
+            batch_dict['deferred_vfe'] = lambda: self._features(batch_dict, ps, n_feat)
             return batch_dict
-        return self._features(batch_dict, ps, points.shape[1] - 1)
+        return self._features(batch_dict, ps, n_feat)
 
     def _features(self, batch_dict, ps, n_feat):
         mean = _ops.segment_mean(ps.points, 1, n_feat, ps.seg_offsets, ps.seg_points, ps.n_pillars)

@@ -64,7 +64,66 @@ class GDMAE(Detector3DTemplate):
         super().__init__(model_cfg=model_cfg, num_class=num_class, dataset=dataset, logger=logger)
         self.module_list = self.build_networks()
 
+    # ------------------------------------------------------------------ index pipeline one step ahead
+    def prefetch_index(self, batch_dict, ready_event=None):
+        """Runs the parameter-free half of the forward pass for ``batch_dict`` - dynamic voxelisation, MAE mask, visible
+        sites, pyramid site sets, neighbour maps, window tables, SRA work units - on a side stream, typically for the NEXT
+        batch while this step's backward is still queued (MAETrainer.step(batch, next_batch=...)).  Its two count reads then
+        wait for the side stream only, and the later forward(batch_dict) has no host sync and no table building left: the
+        main stream never drains between steps.  ``ready_event``: recorded when batch_dict['points'] is on the device."""
+        from ..backbones_3d.spt_backbone_mae import SPTBackboneMAE
+        from ..backbones_3d.vfe.dyn_vfe import DynVFE
+        mods = self.module_list
+        if not (len(mods) >= 2 and isinstance(mods[0], DynVFE) and isinstance(mods[1], SPTBackboneMAE)):
+            return batch_dict
+        import torch
+        dev = batch_dict['points'].device
+        if getattr(self, '_side_stream', None) is None:
+            self._side_stream = torch.cuda.Stream(device=dev, priority=-1)
+        side = self._side_stream
+        if ready_event is not None:
+            side.wait_event(ready_event)
+        batch_dict['points'].record_stream(side)     # allocated on the caller's stream, read (and released) here
+        with torch.cuda.stream(side):
+            mods[0].index_pass(batch_dict)
+            mods[1].index_pass(batch_dict)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        batch_dict['_index_event'] = ev
+        return batch_dict
+
+    @staticmethod
+    def _record_stream(obj, stream, seen):
+        """every tensor reachable from obj was allocated on the side stream and is about to be used on ``stream``"""
+        import torch
+        if obj is None or isinstance(obj, (int, float, str, bool)) or id(obj) in seen:
+            return
+        seen.add(id(obj))
+        if isinstance(obj, torch.Tensor):
+            if obj.is_cuda:
+                obj.record_stream(stream)
+        elif isinstance(obj, dict):
+            for v in obj.values():
+                GDMAE._record_stream(v, stream, seen)
+        elif isinstance(obj, (list, tuple)):
+            for v in obj:
+                GDMAE._record_stream(v, stream, seen)
+        elif hasattr(obj, '__dict__') or hasattr(obj, '__slots__'):
+            names = list(getattr(obj, '__dict__', {}).keys()) + list(getattr(type(obj), '__slots__', ()))
+            for n in names:
+                try:
+                    v = object.__getattribute__(obj, n)
+                except AttributeError:
+                    continue
+                GDMAE._record_stream(v, stream, seen)
+
     def forward(self, batch_dict):
+        ev = batch_dict.pop('_index_event', None)
+        if ev is not None:
+            import torch
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ev)                       # the prefetched index structures are complete
+            self._record_stream(batch_dict, cur, set())
         # DynVFE followed by SPTBackboneMAE: let the backbone schedule the VFE's feature pass after its own index kernels
         # (see DynVFE.forward); any other module order runs every module to completion like the reference
         from ..backbones_3d.spt_backbone_mae import SPTBackboneMAE

@@ -131,9 +131,11 @@ class MAETrainer:
         self.it += 1
         return lr, mom
 
-    def step(self, batch_dict):
+    def step(self, batch_dict, next_batch=None, next_ready_event=None):
         """One iteration (train_utils.py:34-53): zero_grad, forward, backward, all-reduce, clip, update.
-        Returns the loss tensor (no host sync)."""
+        Returns the loss tensor (no host sync).  ``next_batch``: the batch_dict of the following iteration (its points already
+        on the device, or arriving - ``next_ready_event``); its index structures are built on a side stream once this
+        iteration is enqueued (GDMAE.prefetch_index), so the next call to step(next_batch) starts without a host sync."""
         self.model.train()
         self.zero_grad()
         self.refresh_bf16_mirror()
@@ -141,6 +143,8 @@ class MAETrainer:
         loss = ret_dict['loss'].mean()
         loss.backward()
         self.optimizer_step()
+        if next_batch is not None and hasattr(self.model, 'prefetch_index'):
+            self.model.prefetch_index(next_batch, next_ready_event)
         if hasattr(self.model, 'update_global_step'):
             self.model.update_global_step()
         return loss.detach()

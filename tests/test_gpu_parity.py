@@ -567,3 +567,43 @@ def test_sra_bin_units_cover_every_row(G, golden):
                         assert int(start[rows[0]]) == row0 + k0 and int(end[rows[-1]]) == row0 + k0 + kn and (q0 - k0) % 16 == 0
                         assert qn == min(16, k0 + kn - q0)
             assert bool((seen == 1).all()), (int((seen == 0).sum()), int((seen > 1).sum()))
+
+
+# ------------------------------------------------------------------------------ index pipeline one step ahead
+def test_prefetched_index_pipeline_matches_inline(G):
+    """GDMAE.prefetch_index (voxelisation, mask, site sets, window tables of the NEXT batch on a side stream, used by
+    MAETrainer.step(batch, next_batch)) must give the same step as building them inside forward()."""
+    from gd_mae_b200.trainer import MAETrainer
+    model, cfg, ocfg, P, Bf = build(G, "tiny", 0.85, 9)
+    model.train()
+    r = np.random.RandomState(3)
+    batches = []
+    for it in range(3):
+        n = 2500
+        pts = np.concatenate([r.randint(0, 2, (n, 1)), r.normal(0, 3, (n, 2)), r.uniform(-2, 4, (n, 1)), r.uniform(0, 1, (n, 2))], 1)
+        pts = torch.from_numpy(pts[np.argsort(pts[:, 0], kind="stable")].astype(np.float32)).cuda()
+        _, _, _, ovc, _ = O.voxelize(pts.cpu(), ocfg)
+        noise = torch.rand(ovc.shape[0], generator=torch.Generator().manual_seed(it)).cuda()
+        batches.append((pts, noise))
+
+    def run(prefetch):
+        m, *_ = build(G, "tiny", 0.85, 9)
+        tr = MAETrainer(m, cfg.OPTIMIZATION, total_steps=20)
+        bds = [dict(points=p.clone(), batch_size=2, voxel_mae_noise=nz) for p, nz in batches]
+        losses = []
+        for i, bd in enumerate(bds):
+            nxt = bds[i + 1] if (prefetch and i + 1 < len(bds)) else None
+            losses.append(float(tr.step(bd, next_batch=nxt)))
+            if prefetch and i > 0:
+                assert '_index_event' not in bd and bd.get('mae_index') is not None   # the prefetched structures were consumed
+        return losses, {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+    l0, s0 = run(False)
+    l1, s1 = run(True)
+    for a, b in zip(l0, l1):
+        assert abs(a - b) <= 1e-5 * abs(a), (l0, l1)
+    # Adam's first steps move every element by ~lr * sign(g): elements whose gradient is at noise level (float atomics
+    # order) may flip, so compare the update as a whole, like test_mask_from_noise_inside_model_and_trainer_steps
+    num = sum(float(((s1[k].double() - s0[k].double()) ** 2).sum()) for k in P)
+    den = sum(float(((s0[k].double().cpu() - P[k].double()) ** 2).sum()) for k in P)
+    assert (num / den) ** 0.5 < 5e-2, (num / den) ** 0.5

@@ -22,13 +22,24 @@ model = config.build_mae_model(cfg).cuda()
 config.set_precision(model, "bf16")
 trainer = MAETrainer(model, cfg.OPTIMIZATION, total_steps=100)
 pts = torch.from_numpy(O.synth_batch(list(range(8)), O.make_cfg("waymo_ssl"))).cuda()
+PREFETCH = "--no-prefetch" not in sys.argv
+nxt = {"points": pts, "batch_size": 8}
+
+
+def one_step():
+    """like bench.py: the next batch's index structures are prefetched while this step's backward is queued"""
+    global nxt
+    bd, nxt = nxt, {"points": pts, "batch_size": 8}
+    trainer.step(bd, next_batch=nxt if PREFETCH else None)
+
+
 for _ in range(5):
-    trainer.step({"points": pts, "batch_size": 8})
+    one_step()
 torch.cuda.synchronize()
 from torch.profiler import ProfilerActivity, profile  # noqa: E402
 with profile(activities=[ProfilerActivity.CUDA]) as prof:      # GPU activity only: CPU-side op recording would slow the host
     for _ in range(3):
-        trainer.step({"points": pts, "batch_size": 8})
+        one_step()
     torch.cuda.synchronize()
 path = os.path.join(tempfile.gettempdir(), "trace.json")
 prof.export_chrome_trace(path)
