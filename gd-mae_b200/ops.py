@@ -228,6 +228,18 @@ def _al(n):
     return (n + 15) & ~15
 
 
+def world_augment(points, params, src_index=None):
+    """World flip / rotation / scaling (+ shuffle) of a collated batch on the device (csrc/augment.cu; reference:
+    data_augmentor.py:55-143, data_processor.py:92-102).  points (N, 1 + C) fp32, params (B, 6) fp32 rows
+    [flip_x, flip_y, cos, sin, scale, 0], src_index (N) int32 or None -> new (N, 1 + C) tensor."""
+    _dev(points)
+    points = points.contiguous()
+    out = torch.empty_like(points)
+    L.check(L.lib().gdmae_world_augment(L.P(points), L.i64(points.shape[0]), points.shape[1], L.P(params.contiguous()),
+                                        params.shape[0], L.P(src_index), L.P(out), L.stream()), "gdmae_world_augment")
+    return out
+
+
 class WindowTable:
     """Window bookkeeping of one shift (replaces batch_win_inds / coors_in_win / drop levels /
     flat2win_inds / key masks / pos dict of SSTInputLayer.forward, spt_backbone.py:106-135).

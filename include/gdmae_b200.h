@@ -348,6 +348,15 @@ int gdmae_adam_onecycle_step(float* params, const float* grads, float* exp_avg, 
                              const double* sumsq, float clip, float decay, float mom, float beta2, float eps,
                              float step_size, float bc2_sqrt, float grad_scale, void* stream);
 
+/* ---- input side: world augmentation + shuffle of a collated batch -------------------------
+ * replaces DataAugmentor.random_world_flip / random_world_rotation / random_world_scaling
+ * (pcdet/datasets/augmentor/data_augmentor.py:55-143, common_utils.rotate_points_along_z common_utils.py:99-121) and
+ * DataProcessor.shuffle_points (pcdet/datasets/processor/data_processor.py:92-102) applied to the whole batch on the device.
+ * points / out (N, n_cols) fp32, column 0 = frame index, 1..3 = x, y, z; params (B, 6) device fp32 per frame:
+ * flip_x (negates y), flip_y (negates x), cos, sin, scale, 0; src_index (N) int32 nullable: out[i] <- T(points[src_index[i]]). */
+int gdmae_world_augment(const float* points, int64_t N, int n_cols, const float* params, int B, const int32_t* src_index,
+                        float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

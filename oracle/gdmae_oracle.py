@@ -641,6 +641,48 @@ def train_step(P, Bf, opt, points, batch_size, cfg, noise, it):
 
 
 # --------------------------------------------------------------------------------------
+# input side: world augmentation + point shuffle of one frame
+# --------------------------------------------------------------------------------------
+
+def draw_world_aug_params(flip_axes=("x", "y"), flip_p=0.5, rot_p=1.0, rot_range=(-0.78539816, 0.78539816), scale_p=1.0,
+                          scale_range=(0.95, 1.05), n_points=None):
+    """The numpy RNG draws of DataAugmentor.random_world_flip / random_world_rotation / random_world_scaling in queue
+    order (data_augmentor.py:61-64, 99-102, 128-131; gd_mae_ssl.yaml:18-31) followed by shuffle_points' permutation
+    (data_processor.py:98).  Uses the global numpy RNG like the reference: seed it to reproduce a worker's stream."""
+    flips = []
+    for _ in flip_axes:
+        flips.append(bool(np.random.choice([False, True], replace=False, p=[1 - flip_p, flip_p])))
+    enable = np.random.choice([False, True], replace=False, p=[1 - rot_p, rot_p])
+    rr = rot_range if enable else [0.0, 0.0]
+    rotation = np.random.uniform(rr[0], rr[1])
+    enable = np.random.choice([False, True], replace=False, p=[1 - scale_p, scale_p])
+    sr = scale_range if enable else [1.0, 1.0]
+    scaling = np.random.uniform(sr[0], sr[1])
+    perm = np.random.permutation(n_points) if n_points is not None else None
+    fl = dict(zip(flip_axes, flips))
+    return dict(flip_x=fl.get("x", False), flip_y=fl.get("y", False), rotation=float(rotation), scaling=float(scaling), perm=perm)
+
+
+def world_augment(points, flip_x, flip_y, rotation, scaling, perm=None):
+    """points (N, 3 + C) float32 numpy -> augmented copy.  flip 'x' negates y, flip 'y' negates x
+    (data_augmentor.py:68-77); rotation about z with fp32 matrix [[c, s, 0], [-s, c, 0], [0, 0, 1]] applied as p @ R
+    (common_utils.py:99-121); xyz *= scale in fp32 (data_augmentor.py:134); then points[perm] (data_processor.py:99)."""
+    p = np.array(points, dtype=np.float32, copy=True)
+    if flip_x:
+        p[:, 1] = -p[:, 1]
+    if flip_y:
+        p[:, 0] = -p[:, 0]
+    ang = torch.from_numpy(np.array([rotation]))                      # float64, like check_numpy_to_torch(np.array([...]))
+    c, s_ = torch.cos(ang), torch.sin(ang)
+    z, o = ang.new_zeros(1), ang.new_ones(1)
+    R = torch.stack((c, s_, z, -s_, c, z, z, z, o), dim=1).view(-1, 3, 3).float()
+    t = torch.from_numpy(p)[None]
+    p = torch.cat((torch.matmul(t[:, :, 0:3], R), t[:, :, 3:]), dim=-1)[0].numpy()
+    p[:, :3] *= np.float32(scaling)
+    return p if perm is None else p[perm]
+
+
+# --------------------------------------------------------------------------------------
 # synthetic scenes (SURVEY.md 8d, config C2) - shared by tests and bench
 # --------------------------------------------------------------------------------------
 

@@ -206,6 +206,34 @@ def golden_kitti_c1(name):
     print(name, "Np", pts.shape[0], "M", vc.shape[0])
 
 
+def golden_augment(name):
+    """SURVEY 8f rank 3 (input side): the reference's DataAugmentor (random_world_flip / rotation / scaling of
+    tools/cfgs/waymo_models/gd_mae_ssl.yaml:18-31) applied frame by frame the way a dataset worker does, then
+    data_processor.shuffle_points (data_processor.py:92-102), with numpy seeded; stores inputs, drawn parameters, outputs."""
+    m = RH.ref_data_augmentor()
+    acfg = RH.load_model_cfg("tools/cfgs/waymo_models/gd_mae_ssl.yaml").DATA_CONFIG.DATA_AUGMENTOR
+    aug = m.DataAugmentor(None, acfg, ['Vehicle', 'Pedestrian', 'Cyclist'], logger=None)
+    r = np.random.RandomState(21)
+    out = {}
+    np.random.seed(1234)
+    for f in range(3):
+        n = 1500 + 200 * f
+        pts = np.concatenate([r.uniform(-70, 70, (n, 2)), r.uniform(-2, 4, (n, 1)), r.uniform(0, 1, (n, 2))], 1).astype(np.float32)
+        out[f"f{f}.points_in"] = pts.copy()
+        d = aug.forward({"points": pts.copy()})
+        p3 = d["transformation_3d_params"]
+        out[f"f{f}.flip_x"] = np.int64("x" in p3["random_world_flip"])
+        out[f"f{f}.flip_y"] = np.int64("y" in p3["random_world_flip"])
+        out[f"f{f}.rotation"] = np.float64(p3["random_world_rotation"])
+        out[f"f{f}.scaling"] = np.float64(p3["random_world_scaling"])
+        out[f"f{f}.points_aug"] = np.asarray(d["points"], dtype=np.float32)
+        perm = np.random.permutation(n)                      # data_processor.py:98
+        out[f"f{f}.perm"] = perm.astype(np.int64)
+        out[f"f{f}.points_out"] = out[f"f{f}.points_aug"][perm]
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "written", len(out), "arrays")
+
+
 if __name__ == "__main__":
     cfg = O.make_cfg("tiny")
     pts = tiny_points(7, cfg, 1500, 2)
@@ -220,3 +248,4 @@ if __name__ == "__main__":
     golden_mae("mae_tiny_dense", cfg2, "tools/cfgs/waymo_models/gd_mae_ssl.yaml", dense, 2, seed=2)
     golden_window("window_kat", model, bd)
     golden_kitti_c1("kitti_c1")
+    golden_augment("augment_kat")

@@ -228,6 +228,20 @@ def ref_modules():
     return AttrDict({k: importlib.import_module(v) for k, v in names.items()})
 
 
+def ref_data_augmentor():
+    """The reference's pcdet/datasets/augmentor/data_augmentor.py, unmodified.  ``database_sampler`` (gt_sampling, not on the
+    SSL path, imports SharedArray and the CUDA iou ops) is replaced by an empty stand-in; package __init__s are bypassed."""
+    install()
+    for pkg in ["pcdet.datasets", "pcdet.datasets.augmentor"]:
+        if pkg not in sys.modules:
+            _stub(pkg, REF + "/" + pkg.replace(".", "/"))
+    if "pcdet.datasets.augmentor.database_sampler" not in sys.modules:
+        ds = _stub("pcdet.datasets.augmentor.database_sampler")
+        ds.DataBaseSampler = object
+        sys.modules["pcdet.datasets.augmentor"].database_sampler = ds
+    return importlib.import_module("pcdet.datasets.augmentor.data_augmentor")
+
+
 def load_model_cfg(rel_yaml):
     import yaml
     with open(REF + "/" + rel_yaml) as f:

@@ -607,3 +607,35 @@ def test_prefetched_index_pipeline_matches_inline(G):
     num = sum(float(((s1[k].double() - s0[k].double()) ** 2).sum()) for k in P)
     den = sum(float(((s0[k].double().cpu() - P[k].double()) ** 2).sum()) for k in P)
     assert (num / den) ** 0.5 < 5e-2, (num / den) ** 0.5
+
+
+# ------------------------------------------------------------------------------ input side
+def test_world_augmentation_matches_reference_kat(G, golden):
+    """The device DataAugmentor (+ shuffle) on a collated 3-frame batch against the reference's DataAugmentor /
+    shuffle_points run frame by frame (tests/golden/augment_kat.npz): same numpy stream -> same parameters and permutations
+    (exact), points within fp32 rounding of the reference's matmul (1e-6 of the coordinate range)."""
+    from gd_mae_b200.pcdet.datasets.augmentor.data_augmentor import DataAugmentor
+    K = golden("augment_kat")
+    acfg = G.config.to_attr({"DISABLE_AUG_LIST": ["placeholder"], "AUG_CONFIG_LIST": [
+        {"NAME": "random_world_flip", "PROBABILITY": 0.5, "ALONG_AXIS_LIST": ["x", "y"]},
+        {"NAME": "random_world_rotation", "PROBABILITY": 1.0, "WORLD_ROT_ANGLE": [-0.78539816, 0.78539816]},
+        {"NAME": "random_world_scaling", "PROBABILITY": 1.0, "WORLD_SCALE_RANGE": [0.95, 1.05]}]})
+    aug = DataAugmentor(None, acfg, ["Vehicle", "Pedestrian", "Cyclist"])
+    frames = [K[f"f{f}.points_in"] for f in range(3)]
+    batch = np.concatenate([np.concatenate([np.full((p.shape[0], 1), f, np.float32), p], 1) for f, p in enumerate(frames)], 0)
+    np.random.seed(1234)
+    dd = aug.forward({"points": torch.from_numpy(batch).cuda(), "batch_size": 3}, shuffle=True)
+    out = dd["points"].cpu().numpy()
+    off = 0
+    for f in range(3):
+        prm = dd["transformation_3d_params"][f]
+        assert ("x" in prm["random_world_flip"]) == bool(K[f"f{f}.flip_x"]) and ("y" in prm["random_world_flip"]) == bool(K[f"f{f}.flip_y"])
+        assert prm["random_world_rotation"] == float(K[f"f{f}.rotation"]) and prm["random_world_scaling"] == float(K[f"f{f}.scaling"])
+        n = frames[f].shape[0]
+        mine, ref = out[off:off + n], K[f"f{f}.points_out"]
+        assert np.all(mine[:, 0] == f)
+        assert np.array_equal(mine[:, 4:], ref[:, 3:])                       # untouched features follow the permutation exactly
+        assert np.abs(mine[:, 1:4] - ref[:, :3]).max() <= 1e-6 * np.abs(ref[:, :3]).max()
+        off += n
+    with pytest.raises(Exception):
+        G.ops.world_augment(torch.from_numpy(batch), torch.zeros(3, 6))      # CPU tensor: no fallback

@@ -137,3 +137,18 @@ def test_param_count_matches_survey():
     assert sum(v.numel() for v in P.values()) == 8091516
     assert sum(v.numel() for k, v in P.items() if O.in_optimizer(k)) == 6314352
     assert len(P) + len(Bf) == 224  # Appendix A: 224 state_dict entries (global_step is added by the detector shell)
+
+
+def test_world_augmentation_kat(golden):
+    """the oracle's world augmentation + shuffle against the reference's DataAugmentor / shuffle_points run
+    (tests/golden/make_golden.py::golden_augment): same numpy stream -> same parameters, bit-identical points."""
+    K = golden("augment_kat")
+    np.random.seed(1234)
+    for f in range(3):
+        pts = K[f"f{f}.points_in"]
+        prm = O.draw_world_aug_params(n_points=pts.shape[0])
+        assert prm["flip_x"] == bool(K[f"f{f}.flip_x"]) and prm["flip_y"] == bool(K[f"f{f}.flip_y"])
+        assert prm["rotation"] == float(K[f"f{f}.rotation"]) and prm["scaling"] == float(K[f"f{f}.scaling"])
+        assert np.array_equal(prm["perm"], K[f"f{f}.perm"])
+        out = O.world_augment(pts, prm["flip_x"], prm["flip_y"], prm["rotation"], prm["scaling"], prm["perm"])
+        assert np.array_equal(out, K[f"f{f}.points_out"])
