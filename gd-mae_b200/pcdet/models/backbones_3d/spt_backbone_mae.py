@@ -78,7 +78,9 @@ class SPTBackboneMAE(nn.Module):
         K = self.mask_cfg.NUM_GT_POINTS
         if ps is None:
             raise _ops.L.GdmaeError("SPTBackboneMAE needs batch_dict['pillar_set'] written by gd-mae_b200's DynVFE")
-        norm_gt_points = _ops.group_points_centered(ps, self.point_cloud_range, self.voxel_size, K)
+        norm_gt_points = batch_dict.get('mae_gt_points', None)      # prefetched by index_pass, else built here
+        if norm_gt_points is None:
+            norm_gt_points = _ops.group_points_centered(ps, self.point_cloud_range, self.voxel_size, K)
         pred_points = self.decoder_pred(voxel_features).view(voxel_features.shape[0], -1, 3)
         return {'pred_points': pred_points, 'gt_points': norm_gt_points, 'mask': batch_dict['voxel_mae_mask']}
 
@@ -131,6 +133,9 @@ class SPTBackboneMAE(nn.Module):
         plan_pyramid_finish(plan)
         prebuild_structures(sp, n_down, tensor_core_units=bool(_ops.SRA_TENSOR_CORES))
         batch_dict['mae_index'] = (vis_idx, sp)
+        # the reconstruction targets (first K points of every pillar, centred) depend on the points only
+        batch_dict['mae_gt_points'] = _ops.group_points_centered(batch_dict['pillar_set'], self.point_cloud_range, self.voxel_size,
+                                                                 self.mask_cfg.NUM_GT_POINTS)
         return batch_dict
 
     def forward(self, batch_dict):

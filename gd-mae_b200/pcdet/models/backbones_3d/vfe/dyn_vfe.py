@@ -53,6 +53,10 @@ class DynVFE(VFETemplate):
         batch_dict['point_inverse_indices'] = ps.inverse
         batch_dict['voxel_coords'] = ps.voxel_coords
         batch_dict['pillar_set'] = ps  # extra key: CSR / batch offsets reused by SPTBackboneMAE
+        # the point features (pillar mean, offsets to centre / cluster) are parameter-free too: built here, in pillar order
+        n_feat = points.shape[1] - 1
+        mean = _ops.segment_mean(ps.points, 1, n_feat, ps.seg_offsets, ps.seg_points, ps.n_pillars)
+        batch_dict['vfe_point_features'] = _ops.vfe_point_features(ps, mean, self.point_cloud_range, self.voxel_size)
         return batch_dict
 
     def forward(self, batch_dict, **kwargs):
@@ -71,8 +75,10 @@ class DynVFE(VFETemplate):
         return self._features(batch_dict, ps, n_feat)
 
     def _features(self, batch_dict, ps, n_feat):
-        mean = _ops.segment_mean(ps.points, 1, n_feat, ps.seg_offsets, ps.seg_points, ps.n_pillars)
-        x = _ops.vfe_point_features(ps, mean, self.point_cloud_range, self.voxel_size)
+        x = batch_dict.pop('vfe_point_features', None)
+        if x is None:
+            mean = _ops.segment_mean(ps.points, 1, n_feat, ps.seg_offsets, ps.seg_points, ps.n_pillars)
+            x = _ops.vfe_point_features(ps, mean, self.point_cloud_range, self.voxel_size)
         mlp = self.dvfe_mlps[0]
         if self.fused_mlp and self.training and _fused.vfe_mlp_supported(mlp, x) and ps.n_pillars > 0:
             x = _fused.vfe_mlp(mlp, x, ps)            # Linear-BN-ReLU x2 + scatter_max as one node (csrc/vfe_mlp.cu)
