@@ -115,9 +115,11 @@ def build_mae_model(cfg):
 def set_precision(model, dtype, matmul="high", gemm_bf16=True):
     """One switch for the numeric configuration of the step.
     'fp32' : parity configuration - fp32 everywhere, TF32 off, fp32 SIMT attention.
-    'tf32' : TF32 GEMMs/conv, TF32 tensor-core attention, fp32 decoder map.
-    'bf16' : the BASELINE.json configuration - as 'tf32' plus the dense decoder map / 3x3 conv in bf16
-             (BatchNorm statistics, softmax, LayerNorm, losses and the optimizer stay fp32)."""
+    'tf32' : TF32 GEMMs/conv, fp32 SIMT attention, fp32 decoder map.
+    'bf16' : the BASELINE.json configuration - bf16 GEMM operands written by the producing kernels, bf16 q/k/v and
+             tensor-core SRA kernels, bf16 row-kernel inputs (a / h / f / dgl), dense decoder map / 3x3 conv in bf16
+             (the residual stream, BatchNorm / LayerNorm / softmax statistics, losses, gradients of the parameters
+             and the optimizer stay fp32)."""
     import torch
     from . import ops
     assert dtype in ("fp32", "tf32", "bf16")

@@ -312,7 +312,7 @@ def window_table(indices, B, H, W, shifted):
     return t
 
 
-# False: fp32 SIMT kernel (parity configuration).  True: TF32 tensor-core kernel (bf16/tf32 configuration).
+# False: fp32 SIMT kernels (parity / tf32 configurations).  True: bf16 tensor-core kernels (bf16 configuration, bf16 q/k/v).
 SRA_TENSOR_CORES = False
 
 
