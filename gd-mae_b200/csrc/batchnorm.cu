@@ -175,7 +175,7 @@ extern "C" int gdmae_batchnorm_relu_bwd(const float* y, const float* beta, const
                                                        (const float4*)mean, (const float4*)rstd, N, C4, relu, partial);
     GDMAE_LAUNCH_CHECK();
   }
-  bn_bwd_finalize_kernel<<<gdmae_div_up(C * 32, 256), 256, 0, st>>>(partial, grid, C, extra_dbeta, extra_dgamma, dbeta, dgamma);
+  bn_bwd_finalize_kernel<<<gdmae_div_up(C, 32), 256, 0, st>>>(partial, grid, C, extra_dbeta, extra_dgamma, dbeta, dgamma);
   GDMAE_LAUNCH_CHECK();
   if (N == 0) return GDMAE_OK;
   bn_relu_bwd_apply_kernel<<<gdmae_grid(N * C4, 256, 16), 256, 0, st>>>(
@@ -398,7 +398,7 @@ extern "C" int gdmae_decoder_tail_bwd(const void* y, int dtype, int B, int Y, in
                                                                         C8, out, dout, mean, rstd, partial);
     GDMAE_LAUNCH_CHECK();
   }
-  bn_bwd_finalize_kernel<<<gdmae_div_up(C * 32, 256), 256, 0, st>>>(partial, grid, C, nullptr, nullptr, dbeta, dgamma);
+  bn_bwd_finalize_kernel<<<gdmae_div_up(C, 32), 256, 0, st>>>(partial, grid, C, nullptr, nullptr, dbeta, dgamma);
   GDMAE_LAUNCH_CHECK();
   const int g2 = (int)min((long long)GDMAE_NUM_SMS * 16, (n_cells + rper - 1) / rper);
   const float inv_n = (float)(1.0 / (double)n_cells);

@@ -37,19 +37,28 @@ static __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __
   }
 }
 
+// One CTA per 32 channels: lane = channel (coalesced 128-byte reads of the partial rows), the 8 warps take the rows
+// b = warp, warp + 8, ... and meet in shared memory; fp64 accumulation like the forward statistics.  (The first version -
+// one warp per channel, lanes striding over the rows - read 32 sectors per load and took ~22 us per call, 0.24 ms per step.)
+// Launch with gdmae_div_up(C, 32) CTAs of 256 threads: CTA i owns channels [32 i, 32 i + 32).
 static __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C,
                                                               const float* __restrict__ extra_dbeta, const float* __restrict__ extra_dgamma,
                                                               float* __restrict__ dbeta, float* __restrict__ dgamma) {
-  int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (c >= C) return;
+  __shared__ double red[2][8][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
   double s = 0.0, q = 0.0;
-  for (int b = lane; b < nblocks; b += 32) {
-    s += (double)partial[(long long)b * 2 * C + c];
-    q += (double)partial[(long long)b * 2 * C + C + c];
+  if (c < C) {
+    for (int b = wid; b < nblocks; b += 8) {
+      s += (double)__ldg(partial + (long long)b * 2 * C + c);
+      q += (double)__ldg(partial + (long long)b * 2 * C + C + c);
+    }
   }
-  s = warp_sum_f64(s);
-  q = warp_sum_f64(q);
-  if (lane != 0) return;
+  red[0][wid][lane] = s;
+  red[1][wid][lane] = q;
+  __syncthreads();
+  if (wid != 0 || c >= C) return;
+  for (int w = 1; w < 8; ++w) { s += red[0][w][lane]; q += red[1][w][lane]; }
   if (extra_dbeta) s += (double)extra_dbeta[c];
   if (extra_dgamma) q += (double)extra_dgamma[c];
   dbeta[c] = (float)s;

@@ -347,7 +347,19 @@ __global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ x_
                                                      float* __restrict__ partial, float* __restrict__ out, int accumulate) {
   int c = threadIdx.x % C4, rsub = threadIdx.x / C4, rper = blockDim.x / C4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (long long row = (long long)blockIdx.x * rper + rsub; row < N; row += (long long)gridDim.x * rper) {
+  // four rows in flight per thread: with one 8/16-byte load per iteration the kernel sat at 0.24 of the HBM rate
+  const long long step = (long long)gridDim.x * rper;
+  long long row = (long long)blockIdx.x * rper + rsub;
+  for (; row + 3 * step < N; row += 4 * step) {
+    float4 a[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      a[u] = BF16 ? load_bf16x4((const __nv_bfloat16*)x_, (row + u * step) * ld4 + col4 + c)
+                  : __ldg((const float4*)x_ + (row + u * step) * ld4 + col4 + c);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { acc.x += a[u].x; acc.y += a[u].y; acc.z += a[u].z; acc.w += a[u].w; }
+  }
+  for (; row < N; row += step) {
     float4 a = BF16 ? load_bf16x4((const __nv_bfloat16*)x_, row * ld4 + col4 + c) : __ldg((const float4*)x_ + row * ld4 + col4 + c);
     acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
   }

@@ -512,7 +512,7 @@ extern "C" int gdmae_vfe_mlp_bwd(const gdmae_vfe_mlp_args* a) {
   vfe2_bwd_stats_kernel<<<gs, 256, 0, st>>>(M, a->out, a->dout, a->g2, a->b2, partial);
   GDMAE_LAUNCH_CHECK();
   // this step's sums go to tmp_* (the apply passes need them alone); they reach the parameter gradients at the end
-  bn_bwd_finalize_kernel<<<gdmae_div_up(V_C2 * 32, 256), 256, 0, st>>>(partial, gs, V_C2, nullptr, nullptr, a->tmp_dbeta2, a->tmp_dgamma2);
+  bn_bwd_finalize_kernel<<<gdmae_div_up(V_C2, 32), 256, 0, st>>>(partial, gs, V_C2, nullptr, nullptr, a->tmp_dbeta2, a->tmp_dgamma2);
   GDMAE_LAUNCH_CHECK();
   const int g3 = gdmae_grid((long long)M * 32, 256, 16);
 #define VFE_BWD_APPLY(T, S)                                                                                                        \
@@ -532,7 +532,7 @@ extern "C" int gdmae_vfe_mlp_bwd(const gdmae_vfe_mlp_args* a) {
   if (bf) vfe1_bwd_stats_kernel<vbf16><<<g1, V_THREADS, 0, st>>>(a->x, Np, K, a->W1, a->mean1, a->rstd1, a->g1, a->b1, (const vbf16*)a->dh1, partial);
   else vfe1_bwd_stats_kernel<float><<<g1, V_THREADS, 0, st>>>(a->x, Np, K, a->W1, a->mean1, a->rstd1, a->g1, a->b1, (const float*)a->dh1, partial);
   GDMAE_LAUNCH_CHECK();
-  bn_bwd_finalize_kernel<<<gdmae_div_up(V_C1 * 32, 256), 256, 0, st>>>(partial, g1, V_C1, nullptr, nullptr, a->tmp_dbeta1, a->tmp_dgamma1);
+  bn_bwd_finalize_kernel<<<gdmae_div_up(V_C1, 32), 256, 0, st>>>(partial, g1, V_C1, nullptr, nullptr, a->tmp_dbeta1, a->tmp_dgamma1);
   GDMAE_LAUNCH_CHECK();
   if (!acc) GDMAE_CHECK_CUDA(cudaMemsetAsync(a->d_W1, 0, (size_t)V_C1 * K * 4, st));
   const int gw = (int)min((long long)GDMAE_NUM_SMS * 4, ntile);
