@@ -327,6 +327,9 @@ def main():
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
         "final_loss": float(last_loss), "final_loss_e2e": float(last_e2e), "host_cores": len(os.sched_getaffinity(0)),
     }
+    from gd_mae_b200 import ops as _ops
+    n_to = _ops.sra_wait_timeouts()
+    assert n_to == 0, f"{n_to} bounded waits inside the SRA kernels timed out: results are invalid"
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_leg(O)

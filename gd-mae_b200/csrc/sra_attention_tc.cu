@@ -96,6 +96,10 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
+// bounded waits that ran out (a logic error or a lost signal): counted here so that the host can fail loudly
+// (gdmae_sra_wait_timeouts; bench.py and smoke() assert it stays 0) instead of silently continuing with wrong data
+__device__ unsigned int g_sra_wait_timeouts;
+
 // waits for the completion of the phase with the given parity.  try_wait carries a suspend-time hint: the warp sleeps in
 // hardware until the phase completes (a polling loop without it was measured to burn a third of the SM's issue slots and
 // starve the producer warps).  Bounded (about a second) so that a logic error ends in wrong results that the tests catch,
@@ -108,6 +112,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
                  : "=r"(ok) : "r"(addr), "r"(parity), "r"(20000u) : "memory");
     if (ok) return;
   }
+  atomicAdd(&g_sra_wait_timeouts, 1u);
 }
 
 __device__ __forceinline__ void ldsm_x4(unsigned (&r)[4], const bf16* p) {
@@ -1068,7 +1073,9 @@ __global__ void __launch_bounds__(MM_THREADS, 1) sra_bwd_mma_kernel(MbArgs a) {
           const int need = kn > 16 ? (kn + 15) >> 4 : 1;
           if (lane == 0) {
             const volatile int* flag = sdone + k0 * 4 + h;
-            for (int spin = 0; *flag < need && spin < (1 << 20); ++spin) __nanosleep(32);   // bounded: a logic error must not hang the GPU
+            int spin = 0;
+            for (; *flag < need && spin < (1 << 20); ++spin) __nanosleep(32);   // bounded: a logic error must not hang the GPU
+            if (spin == (1 << 20)) atomicAdd(&g_sra_wait_timeouts, 1u);
           }
           __syncwarp();
           __threadfence_block();
@@ -1156,6 +1163,16 @@ extern "C" int gdmae_sra_bin_units(const int32_t* row_info, int64_t N, int32_t* 
   const long long nbins = (N + MM_BIN - 1) / MM_BIN;
   sra_bin_units_kernel<<<(unsigned)((nbins * 32 + 255) / 256), 256, 0, (cudaStream_t)stream_>>>((const int4*)row_info, (int)N, bin_units);
   GDMAE_LAUNCH_CHECK();
+  return GDMAE_OK;
+}
+
+// number of bounded waits inside the tensor-core SRA kernels that timed out since the library was loaded (synchronises
+// the device; 0 in a healthy run)
+extern "C" int gdmae_sra_wait_timeouts(int* out) {
+  unsigned int v = 0;
+  GDMAE_CHECK_ARG(out != nullptr);
+  GDMAE_CHECK_CUDA(cudaMemcpyFromSymbol(&v, g_sra_wait_timeouts, sizeof(v)));
+  *out = (int)v;
   return GDMAE_OK;
 }
 

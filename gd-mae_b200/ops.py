@@ -316,6 +316,13 @@ def window_table(indices, B, H, W, shifted):
 SRA_TENSOR_CORES = False
 
 
+def sra_wait_timeouts():
+    """bounded waits inside the tensor-core SRA kernels that timed out since the library was loaded (0 in a healthy run)"""
+    out = ctypes.c_int(0)
+    L.check(L.lib().gdmae_sra_wait_timeouts(ctypes.byref(out)), "gdmae_sra_wait_timeouts")
+    return int(out.value)
+
+
 def sra_fwd(qkv, lut, tau, table, tau_min, nhead, bv=None, out_dtype=torch.float32):
     """raw launch: -> (out (N,d) fp32 or bf16, lse (N,nhead)).  bv (d): value bias added to the output
     (then qkv holds v without bias)."""

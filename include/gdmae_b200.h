@@ -152,6 +152,8 @@ int gdmae_sra_attention_fwd_tc(const void* qkv_bf16, const float* lut, const int
 /* work units of the tensor-core kernels, built once per window table: bin_units (gdmae_sra_bin_units_bytes(N) bytes,
  * 16-byte aligned) <- for every 64-row bin of the CSR rows the packed (query tile, key range) units of the windows that
  * start in the bin (a run of whole small windows totalling <= 16 rows, or a 16-row chunk of a larger window) */
+/* the kernels' internal waits are bounded; *out <- how many ran out since load (device sync; must be 0) */
+int gdmae_sra_wait_timeouts(int* out);
 size_t gdmae_sra_bin_units_bytes(int64_t N);
 int gdmae_sra_bin_units(const int32_t* row_info, int64_t N, int32_t* bin_units, void* stream);
 /* tensor-core backward for bf16 tensors: qkv (N,3d), dout (N,d), dqkv (N,3d) all bf16; needs neither the forward

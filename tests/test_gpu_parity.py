@@ -607,6 +607,7 @@ def test_prefetched_index_pipeline_matches_inline(G):
     num = sum(float(((s1[k].double() - s0[k].double()) ** 2).sum()) for k in P)
     den = sum(float(((s0[k].double().cpu() - P[k].double()) ** 2).sum()) for k in P)
     assert (num / den) ** 0.5 < 5e-2, (num / den) ** 0.5
+    assert G.ops.sra_wait_timeouts() == 0      # no bounded wait inside the SRA kernels ran out anywhere in this test session
 
 
 # ------------------------------------------------------------------------------ input side
