@@ -112,7 +112,7 @@ def build_mae_model(cfg):
     return build_network(cfg.MODEL, len(ds.class_names), ds)
 
 
-def set_precision(model, dtype, matmul="high", gemm_bf16=True):
+def set_precision(model, dtype, matmul="high", gemm_bf16=True, dense_spatial_features=None):
     """One switch for the numeric configuration of the step.
     'fp32' : parity configuration - fp32 everywhere, TF32 off, fp32 SIMT attention.
     'tf32' : TF32 GEMMs/conv, fp32 SIMT attention, fp32 decoder map.
@@ -136,6 +136,9 @@ def set_precision(model, dtype, matmul="high", gemm_bf16=True):
     # host time per call (cublasLt path) and is not used.
     fused.GEMM_DTYPE = torch.bfloat16 if (dtype == "bf16" and gemm_bf16) else torch.float32
     model.backbone_3d.decoder_dtype = torch.bfloat16 if dtype == "bf16" else torch.float32
-    # performance configurations skip the second dense decoder map (only the pillar cells are read by the MAE head)
-    model.backbone_3d.dense_spatial_features = not fast
+    # batch_dict['spatial_features'] (the dense BN+ReLU map the reference always writes) is a contract of its own, not a
+    # precision matter: it stays on unless the caller opts out explicitly (the MAE pre-train step reads the map only at
+    # the pillar cells, so bench.py / MAE training pass dense_spatial_features=False)
+    if dense_spatial_features is not None:
+        model.backbone_3d.dense_spatial_features = bool(dense_spatial_features)
     return model

@@ -96,14 +96,19 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
-// bounded waits that ran out (a logic error or a lost signal): counted here so that the host can fail loudly
-// (gdmae_sra_wait_timeouts; bench.py and smoke() assert it stays 0) instead of silently continuing with wrong data
+// bounded waits that ran out (a logic error or a lost signal) are FATAL: the counter is bumped (gdmae_sra_wait_timeouts
+// tells the host why) and the kernel traps, so the launch ends in a sticky CUDA error that the next stream
+// synchronisation / loss read raises - a training run can never continue on unstaged buffers.
 __device__ unsigned int g_sra_wait_timeouts;
+__device__ __noinline__ void sra_wait_timed_out() {
+  atomicAdd(&g_sra_wait_timeouts, 1u);
+  __threadfence_system();
+  __trap();
+}
 
 // waits for the completion of the phase with the given parity.  try_wait carries a suspend-time hint: the warp sleeps in
 // hardware until the phase completes (a polling loop without it was measured to burn a third of the SM's issue slots and
-// starve the producer warps).  Bounded (about a second) so that a logic error ends in wrong results that the tests catch,
-// not in a hung GPU.
+// starve the producer warps).  Bounded (about a second) so that a logic error ends in a trapped launch, not in a hung GPU.
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
   const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
   for (int spin = 0; spin < 50000; ++spin) {
@@ -112,7 +117,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
                  : "=r"(ok) : "r"(addr), "r"(parity), "r"(20000u) : "memory");
     if (ok) return;
   }
-  atomicAdd(&g_sra_wait_timeouts, 1u);
+  sra_wait_timed_out();
 }
 
 __device__ __forceinline__ void ldsm_x4(unsigned (&r)[4], const bf16* p) {
@@ -1075,7 +1080,7 @@ __global__ void __launch_bounds__(MM_THREADS, 1) sra_bwd_mma_kernel(MbArgs a) {
             const volatile int* flag = sdone + k0 * 4 + h;
             int spin = 0;
             for (; *flag < need && spin < (1 << 20); ++spin) __nanosleep(32);   // bounded: a logic error must not hang the GPU
-            if (spin == (1 << 20)) atomicAdd(&g_sra_wait_timeouts, 1u);
+            if (spin == (1 << 20)) sra_wait_timed_out();
           }
           __syncwarp();
           __threadfence_block();

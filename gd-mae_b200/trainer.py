@@ -89,6 +89,31 @@ class MAETrainer:
         self._params = [p for _, p in ordered]
         self.it = 0       # accumulated_iter of train_one_epoch
         self.t = 0        # Adam step count
+        # the VFE's gradients are the last ones backward produces: everything after them in the bucket is complete when the
+        # gradient of `pillar_features` arrives, and is all-reduced on a side stream while the VFE backward runs
+        vfe_end = 0
+        for n, p in ordered:
+            if n.startswith('vfe.'):
+                vfe_end = max(vfe_end, self.slices[n][0] + pad(p.numel()))
+        self.early_split = vfe_end if 0 < vfe_end < self.n_opt else 0
+        # float buffers (BatchNorm running statistics) in one flat tensor: DDP (tools/train.py:146, broadcast_buffers=True)
+        # hands every rank rank 0's buffers at each forward; here that is ONE small broadcast per step
+        fbufs = [(n, b) for n, b in model.named_buffers() if b.dtype == torch.float32]
+        self.flat_buffers = torch.zeros(sum(pad(b.numel()) for _, b in fbufs), dtype=torch.float32, device=dev)
+        off = 0
+        for n, b in fbufs:
+            k = b.numel()
+            self.flat_buffers[off:off + k].copy_(b.data.reshape(-1))
+            b.data = self.flat_buffers[off:off + k].view_as(b)
+            off += pad(k)
+        self._comm_stream = None
+        self._early_work = None
+        self._late_works = []
+        if self.world_size > 1 and dist.is_available() and dist.is_initialized():
+            # DDP construction semantics: every rank starts from rank 0's parameters and buffers
+            dist.broadcast(self.flat_params, 0)
+            if self.flat_buffers.numel():
+                dist.broadcast(self.flat_buffers, 0)
 
     def zero_grad(self):
         self.flat_grads.zero_()
@@ -105,11 +130,65 @@ class MAETrainer:
                 fused.BF16_SHADOW[p.data_ptr()] = self.flat_bf16[off:off + p.numel()].view(p.shape)
         self.flat_bf16.copy_(self.flat_params)
 
+    def _comm(self):
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=self.flat_grads.device, priority=-1)
+        return self._comm_stream
+
+    def _reduce_early(self, grad):
+        """Tensor hook on `pillar_features`: the backbone's backward is enqueued, its gradients (bucket[early_split:]) are
+        final.  Their all-reduce starts on the side stream now and overlaps the VFE backward (DDP's bucket overlap,
+        tools/train.py:146)."""
+        if self._early_work is None and self.early_split:
+            ev = torch.cuda.Event()
+            ev.record()
+            side = self._comm()
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                self._early_work = dist.all_reduce(self.flat_grads[self.early_split:], op=dist.ReduceOp.SUM, async_op=True)
+        return grad
+
+    def sync_buffers(self):
+        """rank 0's BatchNorm running statistics to every rank (DDP broadcast_buffers), asynchronously on the side stream."""
+        if self.world_size > 1 and self.flat_buffers.numel() and self.flat_buffers.is_cuda:
+            ev = torch.cuda.Event()
+            ev.record()
+            side = self._comm()
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                self._late_works.append(dist.broadcast(self.flat_buffers, 0, async_op=True))
+
     def reduce_gradients(self):
-        """The only exchange step of the path: ONE all-reduce(SUM) of the flat gradient bucket (32.4 MB at
-        Waymo); the 1/world_size averaging is folded into the clip/Adam kernel (grad_scale)."""
-        if self.world_size > 1:
+        """The only exchange step of the path: all-reduce(SUM) of the flat gradient bucket (32.4 MB at Waymo), as one
+        message, or as two when the early part was already started from the backward hook; the 1/world_size averaging is
+        folded into the clip/Adam kernel (grad_scale)."""
+        if self.world_size <= 1:
+            return
+        if self._early_work is not None:
+            w = dist.all_reduce(self.flat_grads[:self.early_split], op=dist.ReduceOp.SUM, async_op=True)
+            self._early_work.wait()      # stream-level: the current stream waits for NCCL's, the host does not block
+            w.wait()
+            self._early_work = None
+        else:
             dist.all_reduce(self.flat_grads, op=dist.ReduceOp.SUM)
+
+    def state_dict(self):
+        """Optimizer state of the path (train_utils.checkpoint_state: optimizer_state + it; the Adam moments and both
+        counters), independent of the bucket layout: keyed by parameter name."""
+        out = {'it': self.it, 't': self.t, 'total_steps': self.total_steps, 'exp_avg': {}, 'exp_avg_sq': {}}
+        for n, (off, k) in self.slices.items():
+            if off < self.n_opt:
+                out['exp_avg'][n] = self.exp_avg[off:off + k].detach().cpu().clone()
+                out['exp_avg_sq'][n] = self.exp_avg_sq[off:off + k].detach().cpu().clone()
+        return out
+
+    def load_state_dict(self, sd):
+        self.it, self.t = int(sd['it']), int(sd['t'])
+        self.total_steps = int(sd.get('total_steps', self.total_steps))
+        for n, (off, k) in self.slices.items():
+            if off < self.n_opt:
+                self.exp_avg[off:off + k].copy_(sd['exp_avg'][n].reshape(-1))
+                self.exp_avg_sq[off:off + k].copy_(sd['exp_avg_sq'][n].reshape(-1))
 
     def optimizer_step(self):
         lr, mom = onecycle(self.it, self.total_steps, self.cfg.LR, list(self.cfg.MOMS), self.cfg.DIV_FACTOR, self.cfg.PCT_START)
@@ -137,11 +216,27 @@ class MAETrainer:
         on the device, or arriving - ``next_ready_event``); its index structures are built on a side stream once this
         iteration is enqueued (GDMAE.prefetch_index), so the next call to step(next_batch) starts without a host sync."""
         self.model.train()
+        if next_batch is not None and next_ready_event is None and self.flat_grads.is_cuda:
+            # the producer of next_batch['points'] (an H2D copy, the device augmentor) was enqueued by the caller on the current
+            # stream before this call: the side stream that builds the index structures must not start before it
+            next_ready_event = torch.cuda.Event()
+            next_ready_event.record()
+        for w in self._late_works:       # last step's buffer broadcast is complete before this forward updates the buffers
+            w.wait()
+        self._late_works = []
         self.zero_grad()
         self.refresh_bf16_mirror()
         ret_dict, tb_dict, _ = self.model(batch_dict)
         loss = ret_dict['loss'].mean()
+        self.sync_buffers()              # running statistics only change in the forward pass: broadcast overlaps backward
+        hook = None
+        if self.world_size > 1 and self.early_split and self.flat_grads.is_cuda:
+            pf = batch_dict.get('pillar_features', None)
+            if isinstance(pf, torch.Tensor) and pf.requires_grad:
+                hook = pf.register_hook(self._reduce_early)
         loss.backward()
+        if hook is not None:
+            hook.remove()
         self.optimizer_step()
         if next_batch is not None and hasattr(self.model, 'prefetch_index'):
             self.model.prefetch_index(next_batch, next_ready_event)

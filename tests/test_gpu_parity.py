@@ -438,7 +438,7 @@ def test_bf16_configuration_close_to_reference(G, golden):
     model, cfg, ocfg, P, Bf = build(G, "tiny", 0.3, 2)
     from gd_mae_b200 import fused
     try:
-        G.config.set_precision(model, "bf16", gemm_bf16=True)
+        G.config.set_precision(model, "bf16", gemm_bf16=True, dense_spatial_features=False)
         model.train()
         bd = dict(points=torch.from_numpy(K["points_in"]).cuda(), batch_size=int(K["batch_size"]),
                   voxel_mae_mask=torch.from_numpy(K["voxel_mae_mask"]).cuda())

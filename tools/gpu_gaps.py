@@ -19,7 +19,7 @@ from oracle import gdmae_oracle as O  # noqa: E402  (synthetic scene generator o
 torch.backends.cudnn.benchmark = True
 cfg = config.builtin_cfg("waymo_ssl")
 model = config.build_mae_model(cfg).cuda()
-config.set_precision(model, "bf16")
+config.set_precision(model, "bf16", dense_spatial_features=False)
 trainer = MAETrainer(model, cfg.OPTIMIZATION, total_steps=100)
 pts = torch.from_numpy(O.synth_batch(list(range(8)), O.make_cfg("waymo_ssl"))).cuda()
 PREFETCH = "--no-prefetch" not in sys.argv

@@ -21,7 +21,7 @@ ap.add_argument("--dtype", default="bf16")
 args = ap.parse_args()
 cfg = config.builtin_cfg("waymo_ssl")
 model = config.build_mae_model(cfg).cuda()
-config.set_precision(model, args.dtype)
+config.set_precision(model, args.dtype, dense_spatial_features=args.dtype == "fp32")
 trainer = MAETrainer(model, cfg.OPTIMIZATION, total_steps=100)
 pts = torch.from_numpy(O.synth_batch(list(range(args.batch)), O.make_cfg("waymo_ssl"))).cuda()
 for _ in range(args.steps):

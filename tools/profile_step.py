@@ -25,7 +25,7 @@ trainer = MAETrainer(model, cfg.OPTIMIZATION, total_steps=100)
 pts = torch.from_numpy(O.synth_batch(list(range(args.batch)), O.make_cfg("waymo_ssl"))).cuda()
 import contextlib  # noqa: E402
 ac = contextlib.nullcontext()
-config.set_precision(model, args.dtype)
+config.set_precision(model, args.dtype, dense_spatial_features=args.dtype == "fp32")
 for _ in range(4):
     with ac:
         trainer.step({"points": pts, "batch_size": args.batch})

@@ -21,7 +21,7 @@ args = ap.parse_args()
 torch.backends.cudnn.benchmark = True
 cfg = config.builtin_cfg("waymo_ssl")
 model = config.build_mae_model(cfg).cuda()
-config.set_precision(model, "bf16")
+config.set_precision(model, "bf16", dense_spatial_features=False)
 trainer = MAETrainer(model, cfg.OPTIMIZATION, total_steps=200)
 ocfg = O.make_cfg("waymo_ssl")
 batches = [torch.from_numpy(O.synth_batch([8 * k + i for i in range(8)], ocfg)).cuda() for k in range(4)]
