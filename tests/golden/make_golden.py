@@ -234,7 +234,61 @@ def golden_augment(name):
     print(name, "written", len(out), "arrays")
 
 
+def golden_optimizer(name):
+    """adam_onecycle of the path: the reference's build_optimizer / build_scheduler (tools/train_utils/optimization/
+    __init__.py:11-66, fastai_optim.py:104-152 OptimWrapper, learning_schedules_fastai.py:44-77 OneCycle), imported
+    unmodified, driven the way train_one_epoch does (train_utils.py:34-53: scheduler.step(it), zero_grad, backward,
+    clip_grad_norm_(all parameters, 10), optimizer.step()) for 5 iterations on the tiny MAE model with seeded synthetic
+    gradients.  Pins which parameters are updated (leaf modules only: in_proj_* / tau never move), the two weight-decay
+    groups (bn_wd=True: BatchNorm too), the lr / momentum schedule and the Adam arithmetic."""
+    sys.path.insert(0, RH.REF + "/tools")
+    import train_utils.optimization as RO  # noqa: E402  (tools/train_utils has no __init__: namespace package)
+    from torch.nn.utils import clip_grad_norm_
+    cfg = O.make_cfg("tiny")
+    model, P, Bf = build_ref(cfg, "tools/cfgs/waymo_models/gd_mae_ssl.yaml", 4)
+    ocfg = RH.load_model_cfg("tools/cfgs/waymo_models/gd_mae_ssl.yaml").OPTIMIZATION
+    total_steps = 12
+    opt = RO.build_optimizer(model, ocfg)
+    sched, _ = RO.build_scheduler(opt, total_iters_each_epoch=total_steps, total_epochs=1, last_epoch=-1, optim_cfg=ocfg)
+    names = [k for k, _ in model.named_parameters()]
+    watch = ["vfe.dvfe_mlps.0.0.weight", "vfe.dvfe_mlps.0.1.weight", "vfe.dvfe_mlps.0.1.bias",
+             "backbone_3d.sst_blocks.0.encoder_blocks.0.encoder_list.0.win_attn.self_attn.in_proj_weight",
+             "backbone_3d.sst_blocks.0.encoder_blocks.0.encoder_list.0.win_attn.self_attn.tau",
+             "backbone_3d.sst_blocks.0.encoder_blocks.0.encoder_list.0.win_attn.self_attn.out_proj.weight",
+             "backbone_3d.sst_blocks.1.encoder_blocks.1.encoder_list.1.norm2.weight",
+             "backbone_3d.sst_blocks.1.conv_down.0.weight", "backbone_3d.sst_blocks.2.conv_out.1.bias",
+             "backbone_3d.decoder_deblocks.2.0.weight", "backbone_3d.decoder_conv_out.1.weight", "backbone_3d.decoder_pred.bias"]
+    out = {"param_seed": np.int64(4), "total_steps": np.int64(total_steps), "n_iters": np.int64(5), "watch": np.array(watch),
+           "clip": np.float64(ocfg.GRAD_NORM_CLIP)}
+    lrs, moms, norms = [], [], []
+    params = dict(model.named_parameters())
+    for it in range(5):
+        sched.step(it)
+        lrs.append(float(opt.lr))
+        moms.append(float(opt.mom))
+        opt.zero_grad()
+        g = torch.Generator().manual_seed(900 + it)
+        scale = 30.0 if it == 1 else 1.0          # iteration 1 exceeds the clip norm, the others do not
+        for k in names:
+            params[k].grad = torch.randn(params[k].shape, generator=g) * (0.002 * scale)
+        norms.append(float(clip_grad_norm_(model.parameters(), ocfg.GRAD_NORM_CLIP)))
+        opt.step()
+        for k in watch:
+            flat = params[k].detach().reshape(-1)
+            out[f"it{it}.{k}"] = t2n(flat[::max(1, flat.numel() // 1500)]).copy()   # every stride-th element (<= ~1500 per tensor)
+    out["lr"], out["mom"], out["total_norm"] = np.array(lrs), np.array(moms), np.array(norms)
+    # the whole parameter vector after 5 iterations, as per-tensor sums / L2 norms (compact, covers every tensor)
+    out["final_keys"] = np.array(names)
+    out["final_sum"] = np.array([float(params[k].double().sum()) for k in names])
+    out["final_norm"] = np.array([float(params[k].double().norm()) for k in names])
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "lr", lrs, "mom", moms, "norms", norms)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "optimizer":
+        golden_optimizer("optimizer_kat")
+        sys.exit(0)
     cfg = O.make_cfg("tiny")
     pts = tiny_points(7, cfg, 1500, 2)
     model, bd = golden_mae("mae_tiny_b2", cfg, "tools/cfgs/waymo_models/gd_mae_ssl.yaml", pts, 2, seed=1)
@@ -249,3 +303,4 @@ if __name__ == "__main__":
     golden_window("window_kat", model, bd)
     golden_kitti_c1("kitti_c1")
     golden_augment("augment_kat")
+    golden_optimizer("optimizer_kat")

@@ -640,3 +640,262 @@ def test_world_augmentation_matches_reference_kat(G, golden):
         off += n
     with pytest.raises(Exception):
         G.ops.world_augment(torch.from_numpy(batch), torch.zeros(3, 6))      # CPU tensor: no fallback
+
+
+# ------------------------------------------------------------------------------ r2: parity at the benched size / precision
+def _oracle_sra(qkv32, lutb, tau, bv, coords4, H, W, shift, d):
+    """The reference's windowed cosine attention (flat2window -> _scaled_cosine_attention -> window2flat) on the oracle's
+    window bookkeeping, written on q = qkv_q + lut[pos], k = qkv_k + lut[pos], v = qkv_v (+ bv on the output), the split the
+    kernels take.  Returns (out (N,d), drop levels present)."""
+    win, ciw, _ = O.get_window_coors(coords4, [W, H, 1], (8, 8, 1), shift == 1)
+    keep, lvl = O.drop_single_shift(win)
+    assert bool(keep.all())
+    f2w = O.get_flat2win_inds(win, lvl)
+    pos = ciw[:, 1] * 8 + ciw[:, 2]
+    q = qkv32[:, :d] + lutb[pos, :d]
+    k = qkv32[:, d:2 * d] + lutb[pos, d:]
+    v = qkv32[:, 2 * d:]
+    q3, k3, v3 = O.flat2window(q, f2w), O.flat2window(k, f2w), O.flat2window(v, f2w)
+    ones3 = O.flat2window(torch.ones((q.shape[0], 1), dtype=torch.bool), f2w)
+    out3 = {}
+    for dl in q3:
+        key_pad = ones3[dl].logical_not().squeeze(2)
+        out3[dl] = O.cosine_attention_core(q3[dl], k3[dl], v3[dl], key_pad, tau, 0.01, 8)
+    return O.window2flat(out3, f2w, q.shape[0]) + bv, sorted(f2w.keys())
+
+
+@pytest.mark.parametrize("d", [128, 256])
+def test_sra_tensor_core_kernels_match_oracle(G, d):
+    """the bf16 tensor-core SRA forward AND backward directly against the oracle's window attention
+    (autograd for the backward), not against the repo's own SIMT kernel.  All three drop levels occur in both shifts.
+    Inputs are bf16-representable on both sides (q/k/v, dO and the positional LUT are what the kernel reads), so the
+    differences are the kernel's own rounding: normalised q/k and the probabilities P are bf16 tensor-core operands
+    (2^-9 relative each, two chained products) -> 1e-2 of the output range forward, 2e-2 backward; tau gradient 3e-2."""
+    g = torch.Generator().manual_seed(70 + d)
+    B, H, W = 2, 52, 45
+    occ = torch.rand(B, H, W, generator=g) < 0.6                     # dense: windows of 32..64 tokens (level 2)
+    occ[1, :, 24:] &= torch.rand(H, 21, generator=g) < 0.45          # level 1
+    occ[0, 30:, :] &= torch.rand(22, W, generator=g) < 0.08          # level 0, down to single-token windows
+    idx = torch.nonzero(occ).int().contiguous()
+    N = idx.shape[0]
+    coords4 = torch.stack([idx[:, 0], torch.zeros(N, dtype=torch.int32), idx[:, 1], idx[:, 2]], 1).long()
+    qkv_b = torch.randn(N, 3 * d, generator=g).to(torch.bfloat16)
+    lutb = (0.5 * torch.randn(64, 2 * d, generator=g)).to(torch.bfloat16).float()
+    do_b = torch.randn(N, d, generator=g).to(torch.bfloat16)
+    bv = torch.randn(d, generator=g)
+    for shift in (0, 1):
+        qkv32 = qkv_b.float().requires_grad_(True)
+        tau = torch.tensor([0.7], requires_grad=True)
+        o_ref, levels = _oracle_sra(qkv32, lutb, tau, bv, coords4, H, W, shift, d)
+        assert levels == [0, 1, 2], levels
+        (o_ref * do_b.float()).sum().backward()
+        table = G.ops.window_table(idx.cuda(), B, H, W, shift)
+        tau_c = torch.tensor([0.7]).cuda()
+        o_tc, lse = G.ops.sra_fwd(qkv_b.cuda(), lutb.cuda(), tau_c, table, 0.01, 8, bv=bv.cuda())
+        e_o = rel(o_tc, o_ref)
+        dqkv, dts = G.ops.sra_bwd(qkv_b.cuda(), lutb.cuda(), tau_c, table, 0.01, 8, None, lse, do_b.cuda())
+        errs = {nm: rel(dqkv[:, c0:c1].float(), qkv32.grad[:, c0:c1]) for nm, c0, c1 in (("dq", 0, d), ("dk", d, 2 * d), ("dv", 2 * d, 3 * d))}
+        dtau_tc = -float(dts) / 0.7                                   # dS/dtau = -S / tau  (csrc/encoder_layer.cu dtau_kernel)
+        e_t = abs(dtau_tc - float(tau.grad)) / max(abs(float(tau.grad)), 1e-6)
+        print(f"sra tc vs oracle d={d} shift={shift}: out {e_o:.2e} {({k: f'{v:.2e}' for k, v in errs.items()})} dtau {e_t:.2e}")
+        assert e_o < 1e-2, e_o
+        for nm, e in errs.items():
+            assert e < 2e-2, (nm, e)
+        assert e_t < 3e-2, (dtau_tc, float(tau.grad))
+
+
+@pytest.fixture(scope="module")
+def waymo_frame_oracle():
+    """One full-size Waymo-shape frame (BASELINE config C2 at B=1, ~159 k points) through the CPU oracle's training step:
+    indices, loss and every parameter gradient (a few seconds of CPU time, shared by the fp32 and the bf16 test)."""
+    ocfg = O.make_cfg("waymo_ssl")
+    pts = torch.from_numpy(O.synth_batch([7], ocfg))
+    P, Bf = O.init_params(ocfg, 11)
+    keep, opts, ocoords, ovc, oinv = O.voxelize(pts, ocfg)
+    noise = torch.rand(ovc.shape[0], generator=torch.Generator().manual_seed(666))
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in P.items()}
+    trace = {}
+    loss, _ = O.mae_forward(leaves, pts, 1, ocfg, noise=noise, stats={k: v.clone() for k, v in Bf.items()}, trace=trace)
+    loss.backward()
+    grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaves.items()}
+    return dict(pts=pts, P=P, Bf=Bf, noise=noise, loss=float(loss), grads=grads, voxel_coords=ovc, inverse=oinv,
+                n_tokens=[trace[f"x_conv{i + 1}.indices"].shape[0] for i in range(3)],
+                x_idx=[trace[f"x_conv{i + 1}.indices"] for i in range(3)], voxel_features=trace["voxel_features"].detach(),
+                pillar_features=trace["pillar_features"].detach())
+
+
+def _waymo_model(G, W):
+    cfg = G.config.builtin_cfg("waymo_ssl")
+    model = G.config.build_mae_model(cfg).cuda()
+    sd = dict(W["P"])
+    sd.update(W["Bf"])
+    missing = model.load_state_dict(sd, strict=False)
+    assert missing.missing_keys == ["global_step"] and not missing.unexpected_keys
+    return model.train(), cfg
+
+
+def _grad_report(model, W):
+    grads = {k: p.grad for k, p in model.named_parameters()}
+    tot_ref = float(torch.sqrt(sum((g.double() ** 2).sum() for g in W["grads"].values())))
+    tot = float(torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values())))
+    worst = []
+    for k, gr in W["grads"].items():
+        a, b = float(grads[k].norm()), float(gr.norm())
+        worst.append((abs(a - b) / max(b, 1e-3 * tot_ref), k, a, b))
+    worst.sort(reverse=True)
+    return tot, tot_ref, worst
+
+
+def test_waymo_size_full_step_fp32_matches_oracle(G, waymo_frame_oracle):
+    """full MAE step at the Waymo C2 frame size (B=1, ~159 k points, 35 k pillars, 468x468 grid) in
+    the fp32 parity configuration against the oracle: indices bit-exact, loss <= 1e-3 (north_star), token counts equal,
+    features <= 1e-3, every parameter's gradient norm <= 5e-3 (relative to max(its norm, 1e-3 of the total norm))."""
+    W = waymo_frame_oracle
+    model, cfg = _waymo_model(G, W)
+    G.config.set_precision(model, "fp32", dense_spatial_features=True)
+    bd = dict(points=W["pts"].cuda(), batch_size=1, voxel_mae_noise=W["noise"].cuda())
+    ret, _, _ = model(bd)
+    ret["loss"].backward()
+    assert torch.equal(bd["voxel_coords"].cpu(), W["voxel_coords"])
+    assert torch.equal(bd["point_inverse_indices"].cpu(), W["inverse"])
+    for i in range(3):
+        sp = bd["multi_scale_3d_features"][f"x_conv{i + 1}"]
+        assert torch.equal(sp.indices.cpu().long(), W["x_idx"][i].long()), i
+    assert rel(bd["pillar_features"][::SUB], W["pillar_features"][::SUB]) < 1e-4
+    assert rel(bd["voxel_features"][::SUB], W["voxel_features"][::SUB]) < 1e-3
+    e_loss = abs(float(ret["loss"]) - W["loss"]) / W["loss"]
+    tot, tot_ref, worst = _grad_report(model, W)
+    print(f"waymo fp32: loss {float(ret['loss']):.6f} vs {W['loss']:.6f} ({e_loss:.1e}); |g| {tot:.5f} vs {tot_ref:.5f}; worst {worst[:3]}")
+    assert e_loss < 1e-3
+    assert abs(tot - tot_ref) / tot_ref < 2e-3
+    for e, k, a, b in worst:
+        assert e < (5e-2 if k.endswith(".tau") else 5e-3), (k, a, b)
+
+
+def test_waymo_size_full_step_bf16_close_to_oracle(G, waymo_frame_oracle):
+    """the same frame in the BENCHED configuration (bf16 GEMM operands / attention / decoder map,
+    fp32 accumulation and statistics) against the fp32 oracle.  Indices stay bit-exact.  Stated tolerances and why:
+    loss 5e-3 (SURVEY 7 probe: the reference itself under bf16 autocast moves the loss by 1.1e-4 and decoder features by
+    1.6e-2 relative L2; here q/k/v, the attention output and four GEMM outputs per layer are bf16 as well); decoder
+    features at the pillars 5e-2 of their range; total gradient norm 3e-2; per-parameter gradient norms 10 % of
+    max(own norm, 1e-2 of the total) - bf16 dO / dqkv quantisation is the dominant term for the small in_proj biases."""
+    from gd_mae_b200 import fused
+    W = waymo_frame_oracle
+    model, cfg = _waymo_model(G, W)
+    try:
+        G.config.set_precision(model, "bf16", dense_spatial_features=False)
+        bd = dict(points=W["pts"].cuda(), batch_size=1, voxel_mae_noise=W["noise"].cuda())
+        ret, _, _ = model(bd)
+        ret["loss"].backward()
+        assert torch.equal(bd["voxel_coords"].cpu(), W["voxel_coords"])
+        assert torch.equal(bd["point_inverse_indices"].cpu(), W["inverse"])
+        for i in range(3):
+            sp = bd["multi_scale_3d_features"][f"x_conv{i + 1}"]
+            assert torch.equal(sp.indices.cpu().long(), W["x_idx"][i].long()), i
+        e_loss = abs(float(ret["loss"]) - W["loss"]) / W["loss"]
+        e_vf = rel(bd["voxel_features"][::SUB].float(), W["voxel_features"][::SUB])
+        tot, tot_ref, _ = _grad_report(model, W)
+        grads = {k: p.grad for k, p in model.named_parameters()}
+        worst = sorted(((abs(float(grads[k].norm()) - float(g.norm())) / max(float(g.norm()), 1e-2 * tot_ref), k)
+                        for k, g in W["grads"].items()), reverse=True)
+        print(f"waymo bf16: loss {float(ret['loss']):.6f} vs {W['loss']:.6f} ({e_loss:.1e}); voxel_features {e_vf:.1e}; "
+              f"|g| {tot:.5f} vs {tot_ref:.5f}; worst {worst[:4]}")
+        assert e_loss < 5e-3
+        assert e_vf < 5e-2
+        assert abs(tot - tot_ref) / tot_ref < 3e-2
+        for e, k in worst:
+            assert e < 0.10, (k, e)
+        assert G.ops.sra_wait_timeouts() == 0
+    finally:
+        fused.BF16_SHADOW.clear()
+        G.config.set_precision(model, "fp32")
+
+
+def test_trainer_matches_reference_optimizer_golden(G, golden):
+    """The CUDA trainer's clip + adam_onecycle update (flat bucket, fused kernel) on the gradients of
+    tests/golden/optimizer_kat.npz, against the REFERENCE's OptimWrapper / OneCycle run stored there (5 iterations)."""
+    from gd_mae_b200.trainer import MAETrainer
+    K = golden("optimizer_kat")
+    model, cfg, ocfg, P, Bf = build(G, "tiny", 0.85, int(K["param_seed"]))
+    trainer = MAETrainer(model, cfg.OPTIMIZATION, total_steps=int(K["total_steps"]))
+    params = dict(model.named_parameters())
+    P0 = {k: v.clone() for k, v in P.items()}
+    watch = [str(k) for k in K["watch"]]
+    for it in range(int(K["n_iters"])):
+        g = torch.Generator().manual_seed(900 + it)
+        scale = 30.0 if it == 1 else 1.0
+        for k, v in P.items():
+            params[k].grad.copy_((torch.randn(v.shape, generator=g) * (0.002 * scale)).cuda())
+        lr, mom = trainer.optimizer_step()
+        assert abs(lr - float(K["lr"][it])) <= 1e-9 * lr + 1e-12 and abs(mom - float(K["mom"][it])) <= 1e-12
+        assert abs(float(trainer.sumsq.sqrt()) - float(K["total_norm"][it])) / float(K["total_norm"][it]) < 1e-5
+        for k in watch:
+            flat = params[k].detach().reshape(-1)
+            mine = flat[::max(1, flat.numel() // 1500)].cpu()
+            if O.in_optimizer(k):
+                assert rel(mine, K[f"it{it}.{k}"]) < 2e-5, (it, k)
+            else:
+                assert np.array_equal(mine.numpy(), K[f"it{it}.{k}"]), (it, k)
+    for k, n in zip([str(s) for s in K["final_keys"]], K["final_norm"]):
+        assert abs(float(params[k].double().norm()) - n) <= 2e-5 * max(n, 1e-6), k
+        if not O.in_optimizer(k):
+            assert torch.equal(params[k].detach().cpu(), P0[k]), k
+
+
+def test_prefetch_waits_for_late_points(G):
+    """MAETrainer.step(batch, next_batch=nxt) WITHOUT a ready event while next_batch['points'] is still being
+    produced by work queued on the main stream.  The index side stream must wait for it (an event recorded at step entry);
+    it used to start at once and voxelise whatever the buffer held (here: NaNs -> no pillars)."""
+    from gd_mae_b200.trainer import MAETrainer
+    model, cfg, ocfg, P, Bf = build(G, "tiny", 0.85, 9)
+    tr = MAETrainer(model, cfg.OPTIMIZATION, total_steps=20)
+    r = np.random.RandomState(5)
+    n = 2500
+    pts = np.concatenate([r.randint(0, 2, (n, 1)), r.normal(0, 3, (n, 2)), r.uniform(-2, 4, (n, 1)), r.uniform(0, 1, (n, 2))], 1)
+    pts = torch.from_numpy(pts[np.argsort(pts[:, 0], kind="stable")].astype(np.float32))
+    _, _, _, ovc, _ = O.voxelize(pts, ocfg)
+    cur = dict(points=pts.cuda(), batch_size=2)
+    late = torch.full(pts.shape, float("nan"), device="cuda")
+    big = torch.randn(6144, 6144, device="cuda")
+    torch.cuda.synchronize()
+    for _ in range(12):                      # ~tens of ms of queued main-stream work ahead of the producer of `late`
+        big = (big @ big) * 1e-4
+    late.copy_(pts.cuda())                   # the producer: enqueued on the main stream, far from done when step() is called
+    nxt = dict(points=late, batch_size=2)
+    tr.step(cur, next_batch=nxt)
+    torch.cuda.synchronize()
+    assert torch.equal(nxt["voxel_coords"].cpu(), ovc)
+    assert nxt.get("mae_index") is not None
+    loss = tr.step(nxt)
+    assert torch.isfinite(loss)
+
+
+def test_trainer_state_dict_roundtrip(G):
+    """optimizer state (Adam moments + both counters) survives state_dict -> load_state_dict into a fresh trainer:
+    the resumed trainer takes the same next step (train_utils.checkpoint_state / load_params_with_optimizer semantics)."""
+    from gd_mae_b200.trainer import MAETrainer
+    model, cfg, ocfg, P, Bf = build(G, "tiny", 0.85, 3)
+    tr = MAETrainer(model, cfg.OPTIMIZATION, total_steps=20)
+    g = torch.Generator().manual_seed(1)
+    params = dict(model.named_parameters())
+
+    def fake_step(trainer, prm):
+        for k in P:
+            prm[k].grad.copy_((torch.randn(P[k].shape, generator=g) * 1e-3).cuda())
+        trainer.optimizer_step()
+
+    fake_step(tr, params)
+    fake_step(tr, params)
+    sd_opt, sd_model = tr.state_dict(), {k: v.detach().clone() for k, v in model.state_dict().items()}
+    g_state = g.get_state()
+    fake_step(tr, params)
+    want = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model2, *_ = build(G, "tiny", 0.85, 3)
+    model2.load_state_dict(sd_model)
+    tr2 = MAETrainer(model2, cfg.OPTIMIZATION, total_steps=20)
+    tr2.load_state_dict(sd_opt)
+    assert (tr2.it, tr2.t) == (2, 2)
+    g.set_state(g_state)
+    fake_step(tr2, dict(model2.named_parameters()))
+    for k, v in model2.state_dict().items():
+        assert torch.equal(v, want[k]), k

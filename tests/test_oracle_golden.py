@@ -152,3 +152,40 @@ def test_world_augmentation_kat(golden):
         assert np.array_equal(prm["perm"], K[f"f{f}.perm"])
         out = O.world_augment(pts, prm["flip_x"], prm["flip_y"], prm["rotation"], prm["scaling"], prm["perm"])
         assert np.array_equal(out, K[f"f{f}.points_out"])
+
+
+def _optimizer_kat_grads(P, it):
+    """the seeded synthetic gradients of tests/golden/make_golden.py::golden_optimizer (named_parameters order = P's order)"""
+    g = torch.Generator().manual_seed(900 + it)
+    scale = 30.0 if it == 1 else 1.0
+    return {k: torch.randn(v.shape, generator=g) * (0.002 * scale) for k, v in P.items()}
+
+
+def test_adam_onecycle_matches_reference_optimizer(golden):
+    """O.AdamOneCycle / O.onecycle against the reference's OptimWrapper + OneCycle (fastai_optim.py:104-152,
+    learning_schedules_fastai.py:44-77) run for 5 iterations by make_golden.py: schedule values, clip norm, watched tensors
+    after every iteration (1e-6 relative), never-optimised in_proj_* / tau bit-identical, every tensor's sum / norm at the end."""
+    K = golden("optimizer_kat")
+    cfg = O.make_cfg("tiny")
+    P, _ = O.init_params(cfg, int(K["param_seed"]))
+    assert list(P.keys()) == [str(k) for k in K["final_keys"]]
+    P0 = {k: v.clone() for k, v in P.items()}
+    opt = O.AdamOneCycle(P, cfg, int(K["total_steps"]))
+    watch = [str(k) for k in K["watch"]]
+    for it in range(int(K["n_iters"])):
+        G = _optimizer_kat_grads(P, it)
+        norm, lr, mom = opt.step(P, G, it)
+        assert abs(lr - float(K["lr"][it])) <= 1e-12 + 1e-9 * lr and abs(mom - float(K["mom"][it])) <= 1e-12
+        assert abs(norm - float(K["total_norm"][it])) / float(K["total_norm"][it]) < 1e-5
+        for k in watch:
+            flat = P[k].reshape(-1)
+            mine = flat[::max(1, flat.numel() // 1500)]
+            if O.in_optimizer(k):
+                assert rel(mine, K[f"it{it}.{k}"]) < 1e-6, (it, k)
+            else:
+                assert np.array_equal(mine.numpy(), K[f"it{it}.{k}"]), (it, k)
+    for k, s, n in zip(P.keys(), K["final_sum"], K["final_norm"]):
+        assert abs(float(P[k].double().norm()) - n) <= 1e-6 * max(n, 1e-6), k
+        assert abs(float(P[k].double().sum()) - s) <= 1e-5 * max(n, 1e-6), k
+        if not O.in_optimizer(k):
+            assert torch.equal(P[k], P0[k]), k
