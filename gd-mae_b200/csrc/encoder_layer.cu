@@ -75,8 +75,13 @@ static int el_check(const gdmae_encoder_layer_args* a) {
   return GDMAE_OK;
 }
 
+// bf16 configuration: every contraction of the layer runs on the own tcgen05 / TMA kernel (csrc/tc_gemm.cu); the weight
+// gradients (transposed A, K = tokens) split K across the SMs and reduce into the gradient bucket.  The fp32 parity
+// configurations keep the library GEMM (strict fp32 / TF32 math has no tcgen05 kind::f16 equivalent).
 static inline int el_gemm(const gdmae_encoder_layer_args* a, int ta, int tb, int64_t M, int64_t N, int64_t K, const void* A,
                           int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int c_bf16, float beta) {
+  if (a->gemm_mode == 1)
+    return gdmae_tc_gemm(ta, tb, M, N, K, A, lda, B, ldb, C, ldc, c_bf16, beta, ta ? 1 : 0, nullptr, a->stream);
   return gdmae_gemm(ta, tb, M, N, K, A, lda, B, ldb, a->gemm_mode, C, ldc, c_bf16, beta, a->stream);
 }
 
@@ -114,14 +119,28 @@ extern "C" int gdmae_encoder_layer_fwd(const gdmae_encoder_layer_args* a) {
   span.end(0, d, N, N * d * (3 * (tc ? 2 : 4) + (bf ? 2 : 4)) + N * 32);
   // bf16 configuration: the GEMM outputs that only feed a row kernel (a, h, f) leave the GEMM epilogue as bf16
   const int ob = bf ? 1 : 0;
+  if (bf) {
+    // three GEMMs, no row kernels: residual + bias + LayerNorm and bias + GELU run in the GEMM epilogues on the
+    // accumulator rows in tensor memory; a / h / f (bf16) are still written because the backward pass reads them
+    gdmae_tc_epilogue e1 = {};
+    e1.mode = 2; e1.bias = a->b_o; e1.res = a->x; e1.gamma = a->g1; e1.beta_ln = a->be1; e1.eps = a->eps;
+    e1.y32 = a->x1; e1.y16 = a->x1g; e1.mean = a->mean1; e1.rstd = a->rstd1;
+    EL_CALL(gdmae_tc_gemm(0, 1, N, d, d, a->o, d, a->w_o_g, d, a->a, d, 1, 0.f, 0, &e1, a->stream));
+    gdmae_tc_epilogue e2 = {};
+    e2.mode = 1; e2.bias = a->b1; e2.c2 = a->g; e2.ldc2 = dff;
+    EL_CALL(gdmae_tc_gemm(0, 1, N, dff, d, a->x1g, d, a->w1_g, d, a->h, dff, 1, 0.f, 0, &e2, a->stream));
+    gdmae_tc_epilogue e3 = {};
+    e3.mode = 2; e3.bias = a->b2; e3.res = a->x1; e3.gamma = a->g2; e3.beta_ln = a->be2; e3.eps = a->eps;
+    e3.y32 = a->x2; e3.y16 = a->x2g; e3.mean = a->mean2; e3.rstd = a->rstd2;
+    EL_CALL(gdmae_tc_gemm(0, 1, N, d, dff, a->g, dff, a->w2_g, dff, a->f, d, 1, 0.f, 0, &e3, a->stream));
+    return GDMAE_OK;
+  }
   EL_CALL(el_gemm(a, 0, 1, N, d, d, a->o, d, a->w_o_g, d, a->a, d, ob, 0.f));
-  EL_CALL(ew_add_layernorm_fwd(a->x, a->a, ob, a->b_o, a->g1, a->be1, N, d, a->eps, a->x1, bf ? a->x1g : nullptr, a->mean1, a->rstd1,
-                               a->stream));
-  EL_CALL(el_gemm(a, 0, 1, N, dff, d, bf ? a->x1g : (const void*)a->x1, d, a->w1_g, d, a->h, dff, ob, 0.f));
-  EL_CALL(ew_bias_gelu_fwd(a->h, ob, a->b1, N, dff, bf ? nullptr : (float*)a->g, bf ? a->g : nullptr, a->stream));
+  EL_CALL(ew_add_layernorm_fwd(a->x, a->a, ob, a->b_o, a->g1, a->be1, N, d, a->eps, a->x1, nullptr, a->mean1, a->rstd1, a->stream));
+  EL_CALL(el_gemm(a, 0, 1, N, dff, d, (const void*)a->x1, d, a->w1_g, d, a->h, dff, ob, 0.f));
+  EL_CALL(ew_bias_gelu_fwd(a->h, ob, a->b1, N, dff, (float*)a->g, nullptr, a->stream));
   EL_CALL(el_gemm(a, 0, 1, N, d, dff, a->g, dff, a->w2_g, dff, a->f, d, ob, 0.f));
-  EL_CALL(ew_add_layernorm_fwd(a->x1, a->f, ob, a->b2, a->g2, a->be2, N, d, a->eps, a->x2, bf ? a->x2g : nullptr, a->mean2, a->rstd2,
-                               a->stream));
+  EL_CALL(ew_add_layernorm_fwd(a->x1, a->f, ob, a->b2, a->g2, a->be2, N, d, a->eps, a->x2, nullptr, a->mean2, a->rstd2, a->stream));
   return GDMAE_OK;
 }
 

@@ -474,7 +474,9 @@ extern "C" int gdmae_vfe_mlp_fwd(const gdmae_vfe_mlp_args* a) {
   else vfe1_apply_kernel<float><<<g1a, V_THREADS, 0, st>>>(a->x, Np, K, a->W1, a->mean1, a->rstd1, a->g1, a->b1, (float*)a->h1);
   GDMAE_LAUNCH_CHECK();
   // y2 (Np, C2) = h1 (Np, C1) W2^T, operand dtype in and out
-  VFE_CALL(gdmae_gemm(0, 1, Np, V_C2, V_C1, a->h1, V_C1, a->W2_g, V_C1, a->gemm_mode, a->y2, V_C2, bf ? 1 : 0, 0.f, a->stream));
+  // layer 2 (64 -> 128): own tcgen05 / TMA GEMM in the bf16 configuration, library GEMM in the fp32 parity configurations
+  if (bf) VFE_CALL(gdmae_tc_gemm(0, 1, Np, V_C2, V_C1, a->h1, V_C1, a->W2_g, V_C1, a->y2, V_C2, 1, 0.f, 0, nullptr, a->stream));
+  else VFE_CALL(gdmae_gemm(0, 1, Np, V_C2, V_C1, a->h1, V_C1, a->W2_g, V_C1, a->gemm_mode, a->y2, V_C2, 0, 0.f, a->stream));
   const int g2 = (int)min((long long)BN_PART_BLOCKS, (Np + 7) / 8);
   if (bf) vfe2_stats_kernel<vbf16><<<g2, 256, 0, st>>>((const vbf16*)a->y2, Np, partial);
   else vfe2_stats_kernel<float><<<g2, 256, 0, st>>>((const float*)a->y2, Np, partial);
@@ -524,8 +526,13 @@ extern "C" int gdmae_vfe_mlp_bwd(const gdmae_vfe_mlp_args* a) {
 #undef VFE_BWD_APPLY
   GDMAE_LAUNCH_CHECK();
   // ---- linear 2: dW2 (C2, C1) = dy2^T h1, dh1 (Np, C1) = dy2 W2
-  VFE_CALL(gdmae_gemm(1, 0, V_C2, V_C1, Np, a->dy2, V_C2, a->h1, V_C1, a->gemm_mode, a->d_W2, V_C1, 0, acc ? 1.f : 0.f, a->stream));
-  VFE_CALL(gdmae_gemm(0, 0, Np, V_C1, V_C2, a->dy2, V_C2, a->W2_g, V_C1, a->gemm_mode, a->dh1, V_C1, bf ? 1 : 0, 0.f, a->stream));
+  if (bf) {
+    VFE_CALL(gdmae_tc_gemm(1, 0, V_C2, V_C1, Np, a->dy2, V_C2, a->h1, V_C1, a->d_W2, V_C1, 0, acc ? 1.f : 0.f, 1, nullptr, a->stream));
+    VFE_CALL(gdmae_tc_gemm(0, 0, Np, V_C1, V_C2, a->dy2, V_C2, a->W2_g, V_C1, a->dh1, V_C1, 1, 0.f, 0, nullptr, a->stream));
+  } else {
+    VFE_CALL(gdmae_gemm(1, 0, V_C2, V_C1, Np, a->dy2, V_C2, a->h1, V_C1, a->gemm_mode, a->d_W2, V_C1, 0, acc ? 1.f : 0.f, a->stream));
+    VFE_CALL(gdmae_gemm(0, 0, Np, V_C1, V_C2, a->dy2, V_C2, a->W2_g, V_C1, a->gemm_mode, a->dh1, V_C1, 0, 0.f, a->stream));
+  }
   // ---- BN1 + linear 1 from x
   const long long ntile = (Np + V_TILE - 1) / V_TILE;
   const int g1 = (int)min((long long)BN_PART_BLOCKS, ntile);

@@ -61,13 +61,20 @@ def _layout(t):
     return t, 0, t.stride(0)
 
 
-def gemm(a, b, out=None, beta=0.0, out_dtype=F32):
-    """out (M,N) = a (M,K) @ b (K,N) (+ beta*out).  fp32 operands go through torch (cuBLAS, TF32 when
-    allowed); bf16 operands through gdmae_gemm (cublasLt bf16 x bf16 -> fp32 or bf16, cached algorithm)."""
+# True: bf16 contractions run on the own tcgen05 / TMA kernel (csrc/tc_gemm.cu).  False (debug only): cuBLASLt.
+TC_GEMM = True
+
+
+def gemm(a, b, out=None, beta=0.0, out_dtype=F32, wgrad=False):
+    """out (M,N) = a (M,K) @ b (K,N) (+ beta*out).  bf16 operands: the own tcgen05 / TMA GEMM (``wgrad``: K = tokens, split
+    over the SMs, fp32 reductions into ``out``); fp32 operands (parity configurations) go through torch (cuBLAS, TF32
+    when allowed)."""
     if a.dtype == F32:
         if out is None:
             return torch.mm(a, b)
         return out.addmm_(a, b) if beta == 1.0 else torch.mm(a, b, out=out)
+    if TC_GEMM and b.shape[1] % 64 == 0:
+        return tc_gemm(a, b, out=out, beta=beta, out_dtype=out_dtype, split_k=wgrad)
     M, K = a.shape
     N = b.shape[1]
     if out is None:
@@ -444,7 +451,7 @@ class SparseConvFunction(torch.autograd.Function):
     def backward(ctx, dy):
         col, w, bwd_map = ctx.saved_tensors
         dyg = _g(dy.contiguous())
-        dw = gemm(dyg.t(), col).view(ctx.wshape)
+        dw = gemm(dyg.t(), col, wgrad=True).view(ctx.wshape)
         dcol = gemm(dyg, w, out_dtype=GEMM_DTYPE)            # operand dtype (bf16 output in the bf16 configuration)
         dx = _ops.gather_rows_transposed(dcol, bwd_map, ctx.n_src, ctx.mirror)
         return dx, dw, None, None, None
@@ -511,3 +518,25 @@ def batchnorm_relu(bn, y, training, relu=True, count=None):
                                           float(y.shape[0] if count is None else count), relu)
     bn.num_batches_tracked += 1
     return out, bg
+
+
+# ----------------------------------------------------------------------------- own tcgen05 GEMM (csrc/tc_gemm.cu)
+class TcEpilogue(ctypes.Structure):
+    """mirror of gdmae_tc_epilogue (include/gdmae_b200.h)"""
+    _fields_ = [("mode", ctypes.c_int), ("bias", _VP), ("c2", _VP), ("ldc2", ctypes.c_int64), ("res", _VP), ("gamma", _VP),
+                ("beta_ln", _VP), ("eps", ctypes.c_float), ("y32", _VP), ("y16", _VP), ("mean", _VP), ("rstd", _VP)]
+
+
+def tc_gemm(a, b, out=None, beta=0.0, out_dtype=F32, split_k=False, epilogue=None):
+    """out (M,N) = a (M,K) @ b (K,N) on the tcgen05 / TMA kernel; a, b bf16 (any of the two row-major layouts each)."""
+    assert a.dtype == BF16 and b.dtype == BF16
+    M, K = a.shape
+    N = b.shape[1]
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    a, ta, lda = _layout(a)
+    b, tb, ldb = _layout(b)
+    L.check(L.lib().gdmae_tc_gemm(ta, tb, L.i64(M), L.i64(N), L.i64(K), _ptr(a), L.i64(lda), _ptr(b), L.i64(ldb), _ptr(out),
+                                  L.i64(out.stride(0)), _ops._DT[out.dtype], L.f32(beta), int(bool(split_k)),
+                                  ctypes.byref(epilogue) if epilogue is not None else None, L.stream()), "gdmae_tc_gemm")
+    return out

@@ -286,6 +286,35 @@ int gdmae_encoder_layer_bwd(const gdmae_encoder_layer_args* args);
 int gdmae_gemm(int transa, int transb, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
                int64_t ldb, int ab_dtype, void* C, int64_t ldc, int c_dtype /* 0 fp32, 1 bf16 */, float beta, void* stream);
 
+/* ---- own Blackwell GEMM: tcgen05.mma + TMEM accumulators + TMA, fused epilogues (csrc/tc_gemm.cu) -----------------
+ * row-major C (M,N) = op(A) (M,K) op(B) (K,N), bf16 operands, fp32 accumulation; transa: A stored (K,M); transb: B
+ * stored (N,K).  N a multiple of 64, leading dimensions multiples of 8 elements, 16-byte aligned pointers.
+ * c_dtype 0 fp32 (beta 0 or 1) / 1 bf16.  split_k_atomic: the K range is split across the SMs and partial tiles are
+ * added to C with fp32 reductions (weight gradients, K = tokens; beta 0 zero-fills C first, needs ldc == N).
+ * epilogue (nullable = mode 0):
+ *   mode 1  C = acc (bf16, kept for backward), c2 = gelu(acc + bias) (bf16)          - linear1 + GELU, sst_basic_block.py:81
+ *   mode 2  z = acc + bias + res; y32/y16 = LayerNorm(z) * gamma + beta_ln, mean, rstd; N in {128, 256}; C (nullable, bf16) = acc
+ *                                                                                     - out_proj / linear2 + residual + norm, :78-83
+ * replaces F.linear of cosine_msa.py:57-62,431 / sst_basic_block.py:77-84 and the spconv / deblock / VFE GEMMs. */
+typedef struct gdmae_tc_epilogue {
+  int mode;
+  const float* bias;         /* (N) */
+  void* c2;                  /* mode 1: (M, ldc2) bf16 */
+  int64_t ldc2;
+  const float* res;          /* mode 2: (M, N) fp32 residual */
+  const float* gamma;        /* mode 2: (N) */
+  const float* beta_ln;      /* mode 2: (N) */
+  float eps;
+  float* y32;                /* mode 2: (M, N) fp32 */
+  void* y16;                 /* mode 2: (M, N) bf16, nullable */
+  float* mean;               /* mode 2: (M) */
+  float* rstd;               /* mode 2: (M) */
+} gdmae_tc_epilogue;
+int gdmae_tc_gemm(int transa, int transb, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
+                  int64_t ldb, void* C, int64_t ldc, int c_dtype, float beta, int split_k_atomic,
+                  const gdmae_tc_epilogue* epilogue, void* stream);
+int gdmae_tc_gemm_timeouts(int* out);
+
 /* ---- a5/a9/a21/a22 training-mode BatchNorm (+ReLU) over (N, C) rows ------------------------------
  * replaces norm_fn + nn.ReLU of post_act_block (pcdet/utils/spconv_utils.py:50-54), of make_fc_layers
  * (pcdet/models/model_utils/network_utils.py:7-21) and BatchNorm2d + ReLU of the decoder deblocks evaluated

@@ -774,11 +774,13 @@ def test_waymo_size_full_step_fp32_matches_oracle(G, waymo_frame_oracle):
 
 def test_waymo_size_full_step_bf16_close_to_oracle(G, waymo_frame_oracle):
     """the same frame in the BENCHED configuration (bf16 GEMM operands / attention / decoder map,
-    fp32 accumulation and statistics) against the fp32 oracle.  Indices stay bit-exact.  Stated tolerances and why:
-    loss 5e-3 (SURVEY 7 probe: the reference itself under bf16 autocast moves the loss by 1.1e-4 and decoder features by
-    1.6e-2 relative L2; here q/k/v, the attention output and four GEMM outputs per layer are bf16 as well); decoder
-    features at the pillars 5e-2 of their range; total gradient norm 3e-2; per-parameter gradient norms 10 % of
-    max(own norm, 1e-2 of the total) - bf16 dO / dqkv quantisation is the dominant term for the small in_proj biases."""
+    fp32 accumulation and statistics) against the fp32 oracle.  Indices stay bit-exact.  Stated tolerances and why
+    (measured on a B200, r2: loss 1.3e-5, features 8.0e-3, total gradient norm 1.6e-4, worst parameter 1.2e-2):
+    loss 1e-3 (north_star's figure; SURVEY 7 probe: the reference itself under bf16 autocast moves the loss by 1.1e-4 and
+    decoder features by 1.6e-2 relative L2 - here q/k/v, the attention output and four GEMM outputs per layer are bf16 as
+    well); decoder features at the pillars 2e-2 of their range (bf16 map: 2^-9 per value, a 3x3x384 reduction of them);
+    total gradient norm 5e-3; per-parameter gradient norms 5 % of max(own norm, 1e-2 of the total) - bf16 dO / dqkv
+    quantisation is the dominant term for the VFE weights at the end of the backward chain."""
     from gd_mae_b200 import fused
     W = waymo_frame_oracle
     model, cfg = _waymo_model(G, W)
@@ -800,11 +802,11 @@ def test_waymo_size_full_step_bf16_close_to_oracle(G, waymo_frame_oracle):
                         for k, g in W["grads"].items()), reverse=True)
         print(f"waymo bf16: loss {float(ret['loss']):.6f} vs {W['loss']:.6f} ({e_loss:.1e}); voxel_features {e_vf:.1e}; "
               f"|g| {tot:.5f} vs {tot_ref:.5f}; worst {worst[:4]}")
-        assert e_loss < 5e-3
-        assert e_vf < 5e-2
-        assert abs(tot - tot_ref) / tot_ref < 3e-2
+        assert e_loss < 1e-3
+        assert e_vf < 2e-2
+        assert abs(tot - tot_ref) / tot_ref < 5e-3
         for e, k in worst:
-            assert e < 0.10, (k, e)
+            assert e < 0.05, (k, e)
         assert G.ops.sra_wait_timeouts() == 0
     finally:
         fused.BF16_SHADOW.clear()
