@@ -388,6 +388,22 @@ int gdmae_adam_onecycle_step(float* params, const float* grads, float* exp_avg, 
 int gdmae_world_augment(const float* points, int64_t N, int n_cols, const float* params, int B, const int32_t* src_index,
                         float* out, void* stream);
 
+/* ---- rotated BEV overlap / IoU / NMS (csrc/iou3d_nms.cu) ------------------------------------------
+ * boxes (N,7) fp32 [x, y, z, dx, dy, dz, heading].
+ * gdmae_boxes_overlap_bev / gdmae_boxes_iou_bev: ans (na, nb) fp32, replace iou3d_nms_cuda.boxes_overlap_bev_gpu /
+ *   boxes_iou_bev_gpu (pcdet/ops/iou3d_nms/src/iou3d_nms.cpp:47-87, kernels iou3d_nms_kernel.cu:238-266).
+ * gdmae_nms_bev / gdmae_nms_normal: boxes sorted by descending score; keep (n) int64 and num_out (1) int32 on the DEVICE,
+ *   workspace = gdmae_nms_workspace_bytes(n) (the suppression matrix).  Replace iou3d_nms_cuda.nms_gpu / nms_normal_gpu
+ *   (iou3d_nms.cpp:88-187: cudaMalloc + mask copy to the host + host loop; here everything stays on the device).
+ * gdmae_boxes_iou_bev_cpu: HOST pointers, the counterpart of iou3d_nms_cuda.boxes_iou_bev_cpu (iou3d_cpu.cpp:222-252). */
+int gdmae_boxes_overlap_bev(const float* boxes_a, int na, const float* boxes_b, int nb, float* ans_overlap, void* stream);
+int gdmae_boxes_iou_bev(const float* boxes_a, int na, const float* boxes_b, int nb, float* ans_iou, void* stream);
+size_t gdmae_nms_workspace_bytes(int n);
+int gdmae_nms_bev(const float* boxes, int n, float thresh, void* workspace, size_t ws_bytes, int64_t* keep, int* num_out, void* stream);
+int gdmae_nms_normal(const float* boxes, int n, float thresh, void* workspace, size_t ws_bytes, int64_t* keep, int* num_out,
+                     void* stream);
+int gdmae_boxes_iou_bev_cpu(const float* boxes_a, int na, const float* boxes_b, int nb, float* ans_iou);
+
 #ifdef __cplusplus
 }
 #endif
