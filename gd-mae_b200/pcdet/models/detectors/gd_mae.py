@@ -59,6 +59,78 @@ class Detector3DTemplate(nn.Module):
         return m, model_info_dict
 
 
+    # ------------------------------------------------------------------ checkpoint interop (detector3d_template.py:361-442)
+    def _load_state_dict(self, model_state_disk, *, strict=True):
+        """Copies every tensor of a reference-format ``model_state`` whose key and shape match into this model.  Sparse-conv
+        weights stored in another spconv layout are adapted first (detector3d_template.py:361-380): spconv 1.x keeps
+        (k.., C_in, C_out); this model keeps spconv 2.x's (C_out, k.., C_in).  The reference handles the
+        transposed (k.., C_out, C_in) form and the 5-D (3-D conv) implicit form; the 4-D case of this model's 2-D convs
+        (kH, kW, C_in, C_out) -> (C_out, kH, kW, C_in) is the same permutation one dimension lower and is accepted too."""
+        from ...utils.spconv_utils import find_all_spconv_keys
+        state_dict = self.state_dict()
+        spconv_keys = find_all_spconv_keys(self)
+        update_model_state = {}
+        for key, val in model_state_disk.items():
+            if key in spconv_keys and key in state_dict and state_dict[key].shape != val.shape:
+                val_native = val.transpose(-1, -2)                 # (k.., c_in, c_out) -> (k.., c_out, c_in)
+                if val_native.shape == state_dict[key].shape:
+                    val = val_native.contiguous()
+                else:
+                    assert val.dim() in (4, 5), 'sparse-conv weights are 4-D (2-D conv) or 5-D (3-D conv)'
+                    val_implicit = val.permute(val.dim() - 1, *range(val.dim() - 1))   # -> (c_out, k.., c_in)
+                    if val_implicit.shape == state_dict[key].shape:
+                        val = val_implicit.contiguous()
+            if key in state_dict and state_dict[key].shape == val.shape:
+                update_model_state[key] = val
+        if strict:
+            self.load_state_dict(update_model_state)
+        else:
+            # in-place copies: parameters that live in a trainer's flat bucket stay views of it
+            with torch.no_grad():
+                for key, val in update_model_state.items():
+                    state_dict[key].copy_(val)
+        return state_dict, update_model_state
+
+    def load_params_from_file(self, filename, logger=None, to_cpu=False):
+        """pre-trained weights only (SSL -> finetune transfer: whatever matches by key and shape), :393-412"""
+        import os
+        if not os.path.isfile(filename):
+            raise FileNotFoundError
+        loc_type = torch.device('cpu') if to_cpu else None
+        checkpoint = torch.load(filename, map_location=loc_type, weights_only=False)
+        state_dict, update_model_state = self._load_state_dict(checkpoint['model_state'], strict=False)
+        if logger is not None:
+            for key in state_dict:
+                if key not in update_model_state:
+                    logger.info('Not updated weight %s: %s' % (key, str(state_dict[key].shape)))
+            logger.info('==> Done (loaded %d/%d)' % (len(update_model_state), len(state_dict)))
+        return len(update_model_state), len(state_dict)
+
+    def load_params_with_optimizer(self, filename, to_cpu=False, optimizer=None, logger=None):
+        """resume: strict weights + optimizer state (+ the `_optim` side file), -> (it, epoch), :414-442.  ``optimizer`` is a
+        MAETrainer (``load_state_dict`` takes the reference's torch-Adam ``optimizer_state`` as well as its own format)."""
+        import os
+        if not os.path.isfile(filename):
+            raise FileNotFoundError
+        loc_type = torch.device('cpu') if to_cpu else None
+        checkpoint = torch.load(filename, map_location=loc_type, weights_only=False)
+        epoch, it = checkpoint.get('epoch', -1), checkpoint.get('it', 0.0)
+        self._load_state_dict(checkpoint['model_state'], strict=True)
+        if optimizer is not None:
+            if checkpoint.get('optimizer_state', None) is not None:
+                optimizer.load_state_dict(checkpoint['optimizer_state'])
+            else:
+                assert filename[-4] == '.', filename
+                optimizer_filename = '%s_optim.%s' % (filename[:-4], filename[-3:])
+                if os.path.exists(optimizer_filename):
+                    optimizer.load_state_dict(torch.load(optimizer_filename, map_location=loc_type, weights_only=False)['optimizer_state'])
+            if hasattr(optimizer, 'it'):
+                optimizer.it = int(it)
+        if logger is not None:
+            logger.info('==> Done')
+        return it, epoch
+
+
 class GDMAE(Detector3DTemplate):
     def __init__(self, model_cfg, num_class, dataset, logger=None):
         super().__init__(model_cfg=model_cfg, num_class=num_class, dataset=dataset, logger=logger)

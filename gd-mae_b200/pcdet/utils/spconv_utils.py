@@ -185,6 +185,18 @@ spconv = SimpleNamespace(SparseConvTensor=SparseConvTensor, SubMConv2d=SubMConv2
                          conv=SimpleNamespace(SparseConvolution=SparseConvolution))
 
 
+def find_all_spconv_keys(model, prefix=""):
+    """state_dict keys of every sparse-convolution weight below ``model`` (pcdet/utils/spconv_utils.py:11-26): the keys
+    whose layout differs between spconv versions and may need adapting when a checkpoint is loaded."""
+    found = set()
+    for name, child in model.named_children():
+        new_prefix = f"{prefix}.{name}" if prefix != "" else name
+        if isinstance(child, SparseConvolution):
+            found.add(f"{new_prefix}.weight")
+        found.update(find_all_spconv_keys(child, prefix=new_prefix))
+    return found
+
+
 def replace_feature(out, new_features):
     return out.replace_feature(new_features)
 

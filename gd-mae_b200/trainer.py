@@ -55,6 +55,20 @@ def optimised_parameter_names(model):
     return names
 
 
+def reference_param_groups(model):
+    """Parameter NAMES in the order the reference's optimizer indexes them: build_optimizer flattens the model into its leaf
+    modules, split_bn_bias puts the non-BatchNorm ones into group 0 and the BatchNorm ones into group 1
+    (optimization/__init__.py:19-32, fastai_optim.py:17-29, 115-121); torch numbers the parameters group after group."""
+    import torch.nn as nn
+    bn_types = (nn.BatchNorm1d, nn.BatchNorm2d, nn.BatchNorm3d, nn.SyncBatchNorm)
+    name_of = {id(p): n for n, p in model.named_parameters()}
+    leaves = [m for m in model.modules() if len(list(m.children())) == 0]
+    groups = []
+    for pick_bn in (False, True):
+        groups.append([name_of[id(p)] for m in leaves if isinstance(m, bn_types) == pick_bn for p in m.parameters() if p.requires_grad])
+    return groups
+
+
 class MAETrainer:
     def __init__(self, model, optim_cfg, total_steps, world_size=1):
         self.model, self.cfg, self.total_steps, self.world_size = model, optim_cfg, int(total_steps), world_size
@@ -172,9 +186,30 @@ class MAETrainer:
         else:
             dist.all_reduce(self.flat_grads, op=dist.ReduceOp.SUM)
 
-    def state_dict(self):
-        """Optimizer state of the path (train_utils.checkpoint_state: optimizer_state + it; the Adam moments and both
-        counters), independent of the bucket layout: keyed by parameter name."""
+    def state_dict(self, reference_format=False):
+        """Optimizer state of the path (train_utils.checkpoint_state: optimizer_state + it): the Adam moments and both
+        counters, keyed by parameter name - or, with ``reference_format``, laid out as the ``optimizer_state`` the reference
+        saves (the state_dict of the torch Adam inside its OptimWrapper: per-index state + the two param groups), so that a
+        checkpoint written here resumes in the reference and the other way round."""
+        if reference_format:
+            groups = reference_param_groups(self.model)
+            template = torch.optim.Adam([{'params': [torch.nn.Parameter(torch.zeros(1))], 'lr': 0}], betas=(0.9, 0.99)).state_dict()
+            lr, mom = onecycle(max(self.it - 1, 0), self.total_steps, self.cfg.LR, list(self.cfg.MOMS), self.cfg.DIV_FACTOR,
+                               self.cfg.PCT_START)
+            state, pgs, idx = {}, [], 0
+            for names in groups:
+                pg = dict(template['param_groups'][0])
+                pg.update(lr=lr, betas=(mom, 0.99), weight_decay=0, params=list(range(idx, idx + len(names))))
+                pgs.append(pg)
+                for n in names:
+                    off, k = self.slices[n]
+                    if self.t > 0:
+                        shape = dict(self.model.named_parameters())[n].shape
+                        state[idx] = {'step': torch.tensor(float(self.t)),
+                                      'exp_avg': self.exp_avg[off:off + k].detach().cpu().clone().view(shape),
+                                      'exp_avg_sq': self.exp_avg_sq[off:off + k].detach().cpu().clone().view(shape)}
+                    idx += 1
+            return {'state': state, 'param_groups': pgs}
         out = {'it': self.it, 't': self.t, 'total_steps': self.total_steps, 'exp_avg': {}, 'exp_avg_sq': {}}
         for n, (off, k) in self.slices.items():
             if off < self.n_opt:
@@ -183,6 +218,27 @@ class MAETrainer:
         return out
 
     def load_state_dict(self, sd):
+        """own format (state_dict()) or the reference's ``optimizer_state`` (detected by its 'param_groups' key;
+        detector3d_template.py:425-436 / train.py resume path)"""
+        if 'param_groups' in sd:
+            names = [n for g in reference_param_groups(self.model) for n in g]
+            assert sum(len(g['params']) for g in sd['param_groups']) == len(names), "optimizer_state does not belong to this model"
+            order = [i for g in sd['param_groups'] for i in g['params']]
+            steps = set()
+            for i, n in zip(order, names):
+                st = sd['state'].get(i, None)
+                off, k = self.slices[n]
+                if st is None:
+                    self.exp_avg[off:off + k].zero_()
+                    self.exp_avg_sq[off:off + k].zero_()
+                    continue
+                self.exp_avg[off:off + k].copy_(st['exp_avg'].reshape(-1))
+                self.exp_avg_sq[off:off + k].copy_(st['exp_avg_sq'].reshape(-1))
+                steps.add(int(st['step']))
+            assert len(steps) <= 1, "parameters with different Adam step counts"
+            self.t = steps.pop() if steps else 0
+            self.it = self.t
+            return
         self.it, self.t = int(sd['it']), int(sd['t'])
         self.total_steps = int(sd.get('total_steps', self.total_steps))
         for n, (off, k) in self.slices.items():

@@ -930,17 +930,15 @@ def test_iou3d_kernels_match_oracle_and_reference_golden(G, golden):
 @pytest.mark.parametrize("n,spread", [(1, 5.0), (63, 4.0), (64, 4.0), (65, 4.0), (1000, 15.0), (4096, 30.0)])
 def test_nms_kernels_match_oracle(G, n, spread):
     """rotated and axis-aligned NMS (mask kernel + on-device sweep) against the oracle's sweep: identical kept indices.
-    A pair whose IoU lies within 1e-4 of the threshold could legitimately flip between device and host libm; the seeds
-    below have none (asserted), so the comparison is exact.  Sizes straddle the 64-box word boundary."""
+    A pair whose IoU lies within 1e-4 of the threshold could legitimately flip between device and host libm; the threshold
+    is chosen so that no pair of the case does, so the comparison is exact.  Sizes straddle the 64-box word boundary."""
     from gd_mae_b200.pcdet.ops.iou3d_nms import iou3d_nms_utils as U
     from oracle import iou3d_oracle as IO
     boxes = IO.random_boxes(n, 100 + n, spread=spread)
     scores = np.random.RandomState(n).uniform(0, 1, n).astype(np.float32)
-    thresh = 0.25
     bc, sc = torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda()
-    if n <= 1000:
-        iou = IO.boxes_iou_bev(boxes, boxes)
-        assert not ((np.abs(iou - thresh) < 1e-4) & (iou > 0)).any()
+    iou, iou_n = IO.boxes_iou_bev(boxes, boxes), None
+    thresh = next(t for t in (0.25, 0.26, 0.27, 0.28, 0.29, 0.3, 0.31, 0.32) if not (np.abs(iou - t) < 1e-4).any())
     keep, _ = U.nms_gpu(bc, sc, thresh)
     assert np.array_equal(keep.cpu().numpy(), IO.nms(boxes, scores, thresh))
     keep, _ = U.nms_gpu(bc, sc, thresh, pre_maxsize=max(n // 3, 1))
