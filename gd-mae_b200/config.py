@@ -65,10 +65,36 @@ def _sst_block(name, d, dff, stride):
                         "ACTIVATION": "gelu", "LAYER_CFG": {"cosine": True, "tau_min": 0.01}}}
 
 
+def _finetune_heads():
+    """BACKBONE_2D + DENSE_HEAD of tools/cfgs/waymo_models/gd_mae_iou.yaml:199-254 (CenterPoint detector)"""
+    conv = lambda dil: {"out_channels": 128, "kernel_size": 3, "dilation": dil, "padding": dil, "stride": 1}  # noqa: E731
+    backbone_2d = {"NAME": "SSTBEVBackbone", "NUM_FILTER": 128, "CONV_KWARGS": [conv(1), conv(1), conv(2), conv(1)],
+                   "CONV_SHORTCUT": [0, 1, 2]}
+    head = {"out_channels": None, "num_conv": 2}
+    dense_head = {
+        "NAME": "CenterHead", "CLASS_AGNOSTIC": False, "CLASS_NAMES_EACH_HEAD": [["Vehicle", "Pedestrian", "Cyclist"]],
+        "SHARED_CONV_CHANNEL": 64, "USE_BIAS_BEFORE_NORM": True, "NUM_HM_CONV": 2,
+        "SEPARATE_HEAD_CFG": {"HEAD_ORDER": ["center", "center_z", "dim", "rot"],
+                              "HEAD_DICT": {"center": dict(head, out_channels=2), "center_z": dict(head, out_channels=1),
+                                            "dim": dict(head, out_channels=3), "rot": dict(head, out_channels=2),
+                                            "iou": dict(head, out_channels=1)}},
+        "TARGET_ASSIGNER_CONFIG": {"FEATURE_MAP_STRIDE": 1, "NUM_MAX_OBJS": 500, "GAUSSIAN_OVERLAP": 0.1, "MIN_RADIUS": 2},
+        "LOSS_CONFIG": {"LOSS_WEIGHTS": {"cls_weight": 1.0, "iou_weight": 1.0, "loc_weight": 2.0, "code_weights": [1.0] * 8}},
+        "POST_PROCESSING": {"SCORE_THRESH": 0.1, "POST_CENTER_LIMIT_RANGE": [-75.2, -75.2, -2, 75.2, 75.2, 4], "MAX_OBJ_PER_SAMPLE": 500,
+                            "NMS_CONFIG": {"NMS_TYPE": "multi_class_nms", "NMS_THRESH": [0.8, 0.55, 0.55],
+                                           "NMS_PRE_MAXSIZE": [2048, 1024, 1024], "NMS_POST_MAXSIZE": [200, 150, 150],
+                                           "IOU_RECTIFIER": [0.5, 0.71, 0.65]}}}
+    return backbone_2d, dense_head
+
+
 def builtin_cfg(name="waymo_ssl"):
     """Model + data hyper-parameters of the named configs, restated (not copied) from
     tools/cfgs/waymo_models/gd_mae_ssl.yaml, tools/cfgs/once_models/gd_mae_ssl.yaml and
-    tools/cfgs/kitti_models/gd_mae.yaml. ``tiny`` is a 40x48-pillar grid for tests."""
+    tools/cfgs/kitti_models/gd_mae.yaml. ``tiny`` is a 40x48-pillar grid for tests.  ``waymo_iou`` / ``tiny_iou``: the
+    finetune detector of tools/cfgs/waymo_models/gd_mae_iou.yaml (CenterPoint: SPTBackbone + SSTBEVBackbone + CenterHead)."""
+    finetune = name.endswith("_iou")
+    if finetune:
+        name = {"waymo_iou": "waymo_ssl", "tiny_iou": "tiny"}[name]
     data = {"waymo_ssl": ([-74.88, -74.88, -2.0, 74.88, 74.88, 4.0], [0.32, 0.32, 6.0], 5),
             "once_ssl": ([-74.88, -74.88, -5.0, 74.88, 74.88, 3.0], [0.32, 0.32, 8.0], 4),
             "kitti": ([0.0, -39.68, -3.0, 69.12, 39.68, 1.0], [0.32, 0.32, 4.0], 4),
@@ -87,6 +113,12 @@ def builtin_cfg(name="waymo_ssl"):
                              "FUSE_LAYER": {"x_conv1": {"UPSAMPLE_STRIDE": 1, "NUM_FILTER": 128, "NUM_UPSAMPLE_FILTER": 128},
                                             "x_conv2": {"UPSAMPLE_STRIDE": 2, "NUM_FILTER": 256, "NUM_UPSAMPLE_FILTER": 128},
                                             "x_conv3": {"UPSAMPLE_STRIDE": 4, "NUM_FILTER": 256, "NUM_UPSAMPLE_FILTER": 128}}}}
+    if finetune:
+        model["NAME"] = "CenterPoint"
+        model["BACKBONE_3D"]["NAME"] = "SPTBackbone"
+        del model["BACKBONE_3D"]["MASK_CONFIG"]
+        model["BACKBONE_2D"], model["DENSE_HEAD"] = _finetune_heads()
+        model["POST_PROCESSING"] = {"RECALL_THRESH_LIST": [0.3, 0.5, 0.7], "EVAL_METRIC": "waymo_custom"}
     optim = {"BATCH_SIZE_PER_GPU": 8, "NUM_EPOCHS": 30, "OPTIMIZER": "adam_onecycle", "LR": 0.003, "WEIGHT_DECAY": 0.01,
              "MOMENTUM": 0.9, "MOMS": [0.95, 0.85], "PCT_START": 0.4, "DIV_FACTOR": 10, "GRAD_NORM_CLIP": 10}
     return to_attr({"MODEL": model, "OPTIMIZATION": optim, "POINT_CLOUD_RANGE": pc_range, "VOXEL_SIZE": voxel,
@@ -106,7 +138,8 @@ class SyntheticDataset:
 
 
 def build_mae_model(cfg):
-    """GDMAE built the way tools/train.py does (build_network(model_cfg, num_class, dataset))."""
+    """The detector named by cfg.MODEL.NAME (GDMAE, CenterPoint) built the way tools/train.py does
+    (build_network(model_cfg, num_class, dataset))."""
     from .pcdet.models import build_network
     ds = SyntheticDataset(cfg)
     return build_network(cfg.MODEL, len(ds.class_names), ds)
@@ -136,6 +169,8 @@ def set_precision(model, dtype, matmul="high", gemm_bf16=True, dense_spatial_fea
     # host time per call (cublasLt path) and is not used.
     fused.GEMM_DTYPE = torch.bfloat16 if (dtype == "bf16" and gemm_bf16) else torch.float32
     model.backbone_3d.decoder_dtype = torch.bfloat16 if dtype == "bf16" else torch.float32
+    if not hasattr(model.backbone_3d, "dense_spatial_features"):
+        return model                       # finetune backbone (SPTBackbone): the dense map is always materialised
     # batch_dict['spatial_features'] (the dense BN+ReLU map the reference always writes) is a contract of its own, not a
     # precision matter: it stays on unless the caller opts out explicitly (the MAE pre-train step reads the map only at
     # the pillar cells, so bench.py / MAE training pass dense_spatial_features=False)

@@ -574,3 +574,54 @@ def chamfer_distance(x, y, weights=None):
     if weights is None:
         weights = torch.ones((x.shape[0],), dtype=F32, device=x.device)
     return ChamferLoss.apply(x, y, weights), None
+
+
+# ----------------------------------------------------------------------------- CenterHead on the device
+def center_assign_targets(gt_boxes, class_map, num_classes_head, feature_map_hw, pc_range, voxel_size, stride, num_max_objs=500,
+                          gaussian_overlap=0.1, min_radius=2):
+    """CenterHead.assign_targets for one head (center_head.py:105-231) without leaving the device.
+    gt_boxes (B, M, 8) with the 1-based class id last; class_map (n_class_total + 1) int32: class id -> id inside the head.
+    -> heatmap (B, C, H, W), target_boxes (B, K, 8), iou_boxes (B, K, 7), inds (B, K) int64, mask (B, K) int64."""
+    dev = _dev(gt_boxes)
+    gt_boxes = gt_boxes.contiguous().float()
+    if gt_boxes.shape[-1] != 8:
+        raise L.GdmaeError("center_assign_targets handles (x, y, z, dx, dy, dz, heading, class) boxes (no velocity columns)")
+    B, M = gt_boxes.shape[0], gt_boxes.shape[1]
+    H, W = int(feature_map_hw[0]), int(feature_map_hw[1])
+    K, C = int(num_max_objs), int(num_classes_head)
+    heat = torch.empty((B, C, H, W), dtype=F32, device=dev)
+    tgt = torch.empty((B, K, 8), dtype=F32, device=dev)
+    iou_boxes = torch.empty((B, K, 7), dtype=F32, device=dev)
+    inds = torch.empty((B, K), dtype=I64, device=dev)
+    mask = torch.empty((B, K), dtype=I64, device=dev)
+    L.check(L.lib().gdmae_center_assign_targets(L.P(gt_boxes), B, M, L.P(class_map), class_map.numel() - 1, C, H, W, K, int(min_radius),
+                                                int(stride), L.farr([pc_range[0], pc_range[1], voxel_size[0], voxel_size[1]]),
+                                                L.f32(gaussian_overlap), L.P(heat), L.P(tgt), L.P(iou_boxes), L.P(inds), L.P(mask),
+                                                L.stream()), "gdmae_center_assign_targets")
+    return heat, tgt, iou_boxes, inds, mask
+
+
+class CenterFocalLoss(torch.autograd.Function):
+    """FocalLossCenterNet(clamp(sigmoid(logits)), target) as one pass over the map (csrc/center_head.cu)"""
+
+    @staticmethod
+    @_fwd
+    def forward(ctx, logits, target):
+        logits, target = logits.contiguous(), target.contiguous()
+        graw = torch.empty_like(logits)
+        sums = torch.empty((3,), dtype=torch.float64, device=logits.device)
+        L.check(L.lib().gdmae_center_focal_loss(L.P(logits), L.P(target), L.i64(logits.numel()), L.P(graw), L.P(sums), L.stream()),
+                "gdmae_center_focal_loss")
+        num_pos = sums[2]
+        # -neg when there is no positive, else -(pos + neg) / num_pos (loss_utils.py:304-308), without a host sync
+        scale = torch.where(num_pos == 0, torch.ones_like(num_pos), 1.0 / torch.clamp_min(num_pos, 1.0))
+        pos = torch.where(num_pos == 0, torch.zeros_like(num_pos), sums[0])
+        ctx.save_for_backward(graw, scale)
+        return (-(pos + sums[1]) * scale).float()
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, dloss):
+        graw, scale = ctx.saved_tensors
+        # positions with gt == 1 contribute through `pos`, which is dropped when num_pos == 0 - then there are none
+        return graw * (-(dloss.double() * scale)).float(), None

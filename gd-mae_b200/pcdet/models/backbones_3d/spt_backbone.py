@@ -114,3 +114,89 @@ class SSTBlockV1(nn.Module):
         encoded = self.encoder_forward(sp_tensor)
         sp_tensor = replace_feature(sp_tensor, sp_tensor.features + encoded)
         return self.conv_out(sp_tensor)
+
+
+class SPTBackbone(nn.Module):
+    """Mirror of pcdet/models/backbones_3d/spt_backbone.py:267-347: the Sparse Pyramid Transformer of the finetune /
+    detection configs (tools/cfgs/*/gd_mae_iou.yaml) - the three SST blocks on ALL pillars (no masking: 35 k / 25.6 k /
+    11 k tokens per Waymo frame, windows of all three drop levels), three deblocks, concat, 3x3 conv -> the dense
+    ``spatial_features`` map the BEV backbone and CenterHead read.  Same state_dict names (``sst_blocks.*``,
+    ``deblocks.{i}.{0,1}``, ``conv_out.{0,1}``) and batch_dict keys.  Every kernel is the one the MAE path uses; the deblocks
+    run on the sparse rows and ``ops.DenseFill`` writes the 384-channel map once (see SPTBackboneMAE)."""
+
+    def __init__(self, model_cfg, input_channels, grid_size, voxel_size, point_cloud_range, **kwargs):
+        super().__init__()
+        self.model_cfg = model_cfg
+        self.grid_size = [int(g) for g in grid_size]
+        self.voxel_size = [float(v) for v in voxel_size]
+        self.point_cloud_range = [float(v) for v in point_cloud_range]
+        self.sparse_shape = [self.grid_size[1], self.grid_size[0]]
+        in_channels = input_channels
+        self.sst_blocks = nn.ModuleList()
+        for cfg in model_cfg.SST_BLOCK_LIST:
+            self.sst_blocks.append(SSTBlockV1(cfg, in_channels, cfg.NAME))
+            in_channels = cfg.ENCODER.D_MODEL
+        in_channels = 0
+        self.deblocks = nn.ModuleList()
+        self.fuse_strides = []
+        for src in model_cfg.FEATURES_SOURCE:
+            c = model_cfg.FUSE_LAYER[src]
+            self.deblocks.append(nn.Sequential(
+                nn.ConvTranspose2d(c.NUM_FILTER, c.NUM_UPSAMPLE_FILTER, c.UPSAMPLE_STRIDE, stride=c.UPSAMPLE_STRIDE, bias=False),
+                nn.BatchNorm2d(c.NUM_UPSAMPLE_FILTER, eps=1e-3, momentum=0.01), nn.ReLU(inplace=True)))
+            in_channels += c.NUM_UPSAMPLE_FILTER
+            self.fuse_strides.append(int(c.UPSAMPLE_STRIDE))
+        n_src = len(self.deblocks)
+        if n_src != 3 or len({m[0].out_channels for m in self.deblocks}) != 1:
+            raise NotImplementedError("the B200 decoder fill handles the three equal-width pyramid sources of the GD-MAE configs")
+        self.conv_out = nn.Sequential(nn.Conv2d(in_channels, in_channels // n_src, 3, padding=1, bias=False),
+                                      nn.BatchNorm2d(in_channels // n_src, eps=1e-3, momentum=0.01), nn.ReLU(inplace=True))
+        self.num_point_features = in_channels // n_src
+        self.decoder_dtype = torch.float32     # torch.bfloat16: dense map and 3x3 conv in bf16 (config.set_precision)
+
+    def _deblock_rows(self, i, sp, n_cells_total):
+        from .... import fused as _fused
+        deconv, bn = self.deblocks[i][0], self.deblocks[i][1]
+        k = self.fuse_strides[i]
+        w = deconv.weight.permute(0, 2, 3, 1).reshape(deconv.in_channels, k * k * deconv.out_channels)
+        u = (sp.features @ w).view(-1, deconv.out_channels)
+        return _fused.batchnorm_relu(bn, u, self.training, relu=True, count=n_cells_total)
+
+    def forward(self, batch_dict):
+        import torch.nn.functional as F
+        from .... import fused as _fused
+        from .... import ops as _ops
+        from ...utils.spconv_utils import spconv
+        voxel_features, voxel_coords = batch_dict['voxel_features'], batch_dict['voxel_coords']
+        batch_size = batch_dict['batch_size']
+        if self.grid_size[2] != 1:
+            raise AssertionError("pillar grids only: z extent must be 1 (spt_backbone.py:308)")
+        Y, X = self.sparse_shape
+        indices = voxel_coords[:, [0, 2, 3]].contiguous().int()
+        x = spconv.SparseConvTensor(voxel_features, indices, self.sparse_shape, batch_size)
+        x_hidden = []
+        for blk in self.sst_blocks:
+            x = blk(x)
+            x_hidden.append(x)
+        batch_dict.update({'encoded_spconv_tensor': x_hidden[-1], 'encoded_spconv_tensor_stride': 2 ** len(x_hidden)})
+        feats = {f'x_conv{i + 1}': x_hidden[i] for i in range(len(x_hidden))}
+        strides = {f'x_conv{i + 1}': 2 ** (i + 1) for i in range(len(x_hidden))}
+        srcs = [feats[s] for s in self.model_cfg.FEATURES_SOURCE]
+        n_cells_total = batch_size * Y * X
+        rows, bgs = zip(*[self._deblock_rows(i, sp, n_cells_total) for i, sp in enumerate(srcs)])
+        dt = self.decoder_dtype
+        fused_map = _ops.DenseFill.apply(rows[0], rows[1], rows[2], bgs[0], bgs[1], bgs[2], [sp.rank_grid() for sp in srcs],
+                                         [sp.indices for sp in srcs], self.fuse_strides, batch_size, Y, X, dt)     # (B, Y, X, 384)
+        conv, bn = self.conv_out[0], self.conv_out[1]
+        w = _fused.cast_param(conv.weight, dt)
+        y = F.conv2d(fused_map.permute(0, 3, 1, 2), w.contiguous(memory_format=torch.channels_last), padding=1)
+        y = F.batch_norm(y.float(), bn.running_mean, bn.running_var, bn.weight, bn.bias, self.training, bn.momentum, bn.eps)
+        if self.training:
+            bn.num_batches_tracked += 1
+        spatial_features = F.relu(y)
+        assert spatial_features.shape[0] == batch_size and spatial_features.shape[2] == Y and spatial_features.shape[3] == X
+        batch_dict['multi_scale_3d_features'] = feats
+        batch_dict['multi_scale_3d_strides'] = strides
+        batch_dict['spatial_features'] = spatial_features
+        batch_dict['spatial_features_stride'] = strides[self.model_cfg.FEATURES_SOURCE[0]] // self.fuse_strides[0]
+        return batch_dict

@@ -404,6 +404,21 @@ int gdmae_nms_normal(const float* boxes, int n, float thresh, void* workspace, s
                      void* stream);
 int gdmae_boxes_iou_bev_cpu(const float* boxes_a, int na, const float* boxes_b, int nb, float* ans_iou);
 
+/* ---- CenterHead targets and heat-map loss on the device (csrc/center_head.cu) ----------------------
+ * gdmae_center_assign_targets: replaces the CPU Python loop of CenterHead.assign_targets / assign_target_of_single_head
+ *   (pcdet/models/dense_heads/center_head.py:105-231) and centernet_utils.gaussian_radius / draw_gaussian_to_heatmap
+ *   (pcdet/models/model_utils/centernet_utils.py:9-72) for ONE head.  gt_boxes (B, M, 8) fp32, last column = 1-based class id
+ *   (0 = padding); class_map (n_class_total + 1) int32 on the device: class id -> 1-based id inside the head, 0 = not in it;
+ *   range_xy_voxel_xy = HOST {x_min, y_min, voxel_x, voxel_y}.  Outputs (zero-filled here): heatmap (B, C, H, W),
+ *   target_boxes (B, max_objs, 8) [dx, dy, z, log dims, cos, sin], iou_boxes (B, max_objs, 7), inds / mask (B, max_objs) int64.
+ * gdmae_center_focal_loss: FocalLossCenterNet on clamp(sigmoid(logits), 1e-4, 1 - 1e-4) (pcdet/utils/loss_utils.py:273-309,
+ *   center_head.py:233-235): sums3 = {sum of positive terms, sum of negative terms, number of positives} (device, double),
+ *   grad_raw (n) = d(pos + neg)/dlogits. */
+int gdmae_center_assign_targets(const float* gt_boxes, int B, int M, const int* class_map, int n_class_total, int C, int H, int W,
+                                int max_objs, int min_radius, int stride, const float* range_xy_voxel_xy, float overlap, float* heatmap,
+                                float* target_boxes, float* iou_boxes, int64_t* inds, int64_t* mask, void* stream);
+int gdmae_center_focal_loss(const float* logits, const float* gt, int64_t n, float* grad_raw, double* sums3, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -715,3 +715,35 @@ def synth_batch(seeds, cfg, n=160000):
         p = synth_frame(s, cfg, n)
         rows.append(np.concatenate([np.full((p.shape[0], 1), b, np.float32), p], axis=1))
     return np.concatenate(rows, axis=0)
+
+
+# --------------------------------------------------------------------------------------
+# finetune path: deterministic weights for the BEV backbone / CenterHead of the parity harness
+# --------------------------------------------------------------------------------------
+
+def finetune_head_state(shapes, seed=0):
+    """Deterministic tensors for the ``backbone_2d.*`` / ``dense_head.*`` entries of a CenterPoint state_dict, a function of
+    (key, shape, seed) only, so that the reference model (tests/golden/make_golden_finetune.py) and the CUDA model receive
+    identical weights without storing them: conv weights ~ N(0, 2 / fan_in) (the heads' kaiming_normal_, center_head.py:33),
+    BatchNorm weight 1 + 0.1 N(0,1), biases 0.1 N(0,1) except the heat-map bias -2.19 (center_head.py:29), running stats 0 / 1."""
+    import zlib
+    out = OrderedDict()
+    for k, shape in shapes.items():
+        g = torch.Generator().manual_seed((zlib.crc32(k.encode()) + 7919 * seed) % (2 ** 31))
+        shape = tuple(shape)
+        if k.endswith("num_batches_tracked"):
+            out[k] = torch.zeros(shape, dtype=torch.int64)
+        elif k.endswith("running_mean"):
+            out[k] = torch.zeros(shape)
+        elif k.endswith("running_var"):
+            out[k] = torch.ones(shape)
+        elif len(shape) == 4:
+            fan_in = shape[1] * shape[2] * shape[3]
+            out[k] = torch.randn(shape, generator=g) * math.sqrt(2.0 / fan_in)
+        elif k.endswith(".weight"):
+            out[k] = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        elif ".hm." in k and k.endswith(".bias") and shape[0] <= 8:
+            out[k] = torch.full(shape, -2.19)
+        else:
+            out[k] = 0.1 * torch.randn(shape, generator=g)
+    return out

@@ -267,3 +267,79 @@ class RefMAE(nn.Module):
         batch_dict = self.backbone_3d(batch_dict)
         loss, _ = self.backbone_3d.get_loss()
         return loss, batch_dict
+
+
+# ------------------------------------------------------------------ finetune path
+def install_finetune():
+    """Additional stand-ins so that the reference's CenterPoint-path files import unchanged on this CPU-only container:
+    * ``pcdet.ops.iou3d_nms.iou3d_nms_cuda``: the GPU entry points are replaced by the C oracle (oracle/iou3d_oracle.c, itself
+      pinned bit-exact to the reference's own iou3d_cpu.cpp) working on CPU tensors;
+    * ``pcdet.ops.roiaware_pool3d.roiaware_pool3d_cuda``: imported by box_utils, not used on this path - empty module."""
+    install()
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    from oracle import iou3d_oracle as IO
+    for pkg in ["pcdet.models.backbones_2d", "pcdet.models.dense_heads", "pcdet.ops.iou3d_nms", "pcdet.ops.roiaware_pool3d"]:
+        if pkg not in sys.modules:
+            _stub(pkg, REF + "/" + pkg.replace(".", "/"))
+    if "pcdet.ops.iou3d_nms.iou3d_nms_cuda" not in sys.modules:
+        m = _stub("pcdet.ops.iou3d_nms.iou3d_nms_cuda")
+
+        def boxes_overlap_bev_gpu(a, b, out):
+            out.copy_(torch.from_numpy(IO.boxes_overlap_bev(a.detach().numpy(), b.detach().numpy())))
+            return 1
+
+        def boxes_iou_bev_gpu(a, b, out):
+            out.copy_(torch.from_numpy(IO.boxes_iou_bev(a.detach().numpy(), b.detach().numpy())))
+            return 1
+
+        m.boxes_overlap_bev_gpu, m.boxes_iou_bev_gpu = boxes_overlap_bev_gpu, boxes_iou_bev_gpu
+        sys.modules["pcdet.ops.iou3d_nms"].iou3d_nms_cuda = m
+        r = _stub("pcdet.ops.roiaware_pool3d.roiaware_pool3d_cuda")
+        sys.modules["pcdet.ops.roiaware_pool3d"].roiaware_pool3d_cuda = r
+
+
+class _CpuAsCuda:
+    """``tensor.cuda()`` / ``torch.cuda.FloatTensor`` are hard-coded in center_head.py:66 and iou3d_nms_utils.py:41,66: inside
+    this context they return CPU tensors (the container has no GPU)."""
+
+    def __enter__(self):
+        self._cuda = torch.Tensor.cuda
+        torch.Tensor.cuda = lambda t, *a, **k: t
+        self._ft = getattr(torch.cuda, "FloatTensor", None)
+        torch.cuda.FloatTensor = lambda size: torch.empty(size, dtype=torch.float32)
+        return self
+
+    def __exit__(self, *exc):
+        torch.Tensor.cuda = self._cuda
+        if self._ft is not None:
+            torch.cuda.FloatTensor = self._ft
+        return False
+
+
+class RefCenterPoint(nn.Module):
+    """The reference's DynVFE + SPTBackbone + SSTBEVBackbone + CenterHead wired the way Detector3DTemplate.build_networks
+    does for tools/cfgs/waymo_models/gd_mae_iou.yaml (detector3d_template.py:70-157), with CenterPoint's module names."""
+
+    def __init__(self, model_cfg, n_feat, voxel_size, pc_range, grid_size, class_names):
+        super().__init__()
+        install_finetune()
+        R = ref_modules()
+        bev = importlib.import_module("pcdet.models.backbones_2d.sst_bev_backbone")
+        ch = importlib.import_module("pcdet.models.dense_heads.center_head")
+        self.vfe = R.dyn_vfe.DynVFE(model_cfg=model_cfg.VFE, num_point_features=n_feat, voxel_size=voxel_size,
+                                    point_cloud_range=pc_range, grid_size=grid_size)
+        self.backbone_3d = R.spt_backbone.SPTBackbone(model_cfg=model_cfg.BACKBONE_3D, input_channels=self.vfe.get_output_feature_dim(),
+                                                      grid_size=grid_size, voxel_size=voxel_size, point_cloud_range=pc_range)
+        self.backbone_2d = bev.SSTBEVBackbone(model_cfg=model_cfg.BACKBONE_2D, input_channels=None)
+        with _CpuAsCuda():
+            self.dense_head = ch.CenterHead(model_cfg=model_cfg.DENSE_HEAD, input_channels=self.backbone_2d.num_bev_features,
+                                            num_class=len(class_names), class_names=class_names, grid_size=grid_size,
+                                            point_cloud_range=pc_range, predict_boxes_when_training=False, voxel_size=voxel_size)
+
+    def forward(self, batch_dict):
+        with _CpuAsCuda():
+            for m in (self.vfe, self.backbone_3d, self.backbone_2d, self.dense_head):
+                batch_dict = m(batch_dict)
+            loss, tb_dict = self.dense_head.get_loss()
+        return loss, tb_dict, batch_dict

@@ -945,3 +945,133 @@ def test_nms_kernels_match_oracle(G, n, spread):
     assert np.array_equal(keep.cpu().numpy(), IO.nms(boxes, scores, thresh, pre_maxsize=max(n // 3, 1)))
     keep, _ = U.nms_normal_gpu(bc, sc, thresh)
     assert np.array_equal(keep.cpu().numpy(), IO.nms_normal(boxes, scores, thresh))
+
+
+# ------------------------------------------------------------------------------ finetune path (config 4)
+def _build_finetune(G, name, K):
+    cfg = G.config.builtin_cfg(name)
+    model = G.config.build_mae_model(cfg).cuda()
+    ocfg = O.make_cfg("tiny" if name.startswith("tiny") else "waymo_ssl")
+    P, Bf = O.init_params(ocfg, int(K["param_seed"]) if K is not None else 7)
+    sd = {k: v for k, v in model.state_dict().items()}
+    new = {}
+    for k, v in list(P.items()) + list(Bf.items()):
+        k2 = k.replace("backbone_3d.decoder_deblocks", "backbone_3d.deblocks").replace("backbone_3d.decoder_conv_out", "backbone_3d.conv_out")
+        if k2 in sd and sd[k2].shape == v.shape:
+            new[k2] = v
+    new.update(O.finetune_head_state({k: v.shape for k, v in sd.items() if k.startswith(("backbone_2d.", "dense_head."))},
+                                     seed=int(K["head_seed"]) if K is not None else 3))
+    missing = model.load_state_dict(new, strict=False)
+    assert missing.missing_keys == ["global_step"] and not missing.unexpected_keys, missing
+    return model, cfg, ocfg
+
+
+def test_center_assign_targets_kernel_matches_oracle_and_golden(G, golden):
+    """ops.center_assign_targets (one launch, on the device) against the reference's CPU loop (golden) and the oracle on a
+    larger random case: heat map, indices, masks, IoU boxes exact; regression targets 1e-6 (device logf / cosf / sinf)."""
+    from oracle import center_oracle as CO
+    K = golden("finetune_tiny")
+    cfg = O.make_cfg("tiny")
+    X, Y, _ = cfg["grid"]
+    cmap = torch.tensor([0, 1, 2, 3], dtype=torch.int32).cuda()
+    heat, tgt, iou_boxes, inds, mask = G.ops.center_assign_targets(torch.from_numpy(K["gt_boxes"]).cuda(), cmap, 3, (Y, X), cfg["pc_range"],
+                                                                   cfg["voxel"], 1)
+    ref_heat = np.zeros(int(np.prod(K["heatmap.shape"])), dtype=np.float32)
+    ref_heat[K["heatmap.nz_index"]] = K["heatmap.nz_value"]
+    assert np.abs(heat.cpu().numpy().reshape(-1) - ref_heat).max() <= 1e-7
+    assert np.array_equal(inds.cpu().numpy(), K["inds"]) and np.array_equal(mask.cpu().numpy(), K["masks"])
+    assert np.array_equal(iou_boxes.cpu().numpy(), K["iou_boxes"])
+    assert np.abs(tgt.cpu().numpy() - K["target_boxes"]).max() <= 1e-6
+    # Waymo-size map, 300 boxes in 3 frames incl. zero padding, a class outside the head, more boxes than slots
+    wcfg = O.make_cfg("waymo_ssl")
+    r = np.random.RandomState(0)
+    n = 300
+    cls = r.randint(0, 4, (3, n)).astype(np.float32)
+    dims = np.array([[1, 1, 1], [4.7, 2.1, 1.7], [0.9, 0.9, 1.7], [1.8, 0.8, 1.7]])[cls.astype(int)] * r.uniform(0.8, 1.2, (3, n, 3))
+    gt = np.concatenate([r.uniform(-76, 76, (3, n, 2)), r.uniform(-1, 2, (3, n, 1)), dims, r.uniform(-3.2, 3.2, (3, n, 1)), cls[..., None]], 2)
+    gt[cls == 0] = 0
+    gt = torch.from_numpy(gt.astype(np.float32))
+    cm = [0, 1, 0, 2]                                   # the head covers classes 1 and 3 only
+    want = CO.assign_targets(gt, cm, 2, 468, 468, wcfg["pc_range"], wcfg["voxel"], max_objs=120)
+    got = G.ops.center_assign_targets(gt.cuda(), torch.tensor(cm, dtype=torch.int32).cuda(), 2, (468, 468), wcfg["pc_range"], wcfg["voxel"], 1,
+                                      num_max_objs=120)
+    assert np.abs(got[0].cpu().numpy() - want[0].numpy()).max() <= 1e-7
+    assert torch.equal(got[3].cpu(), want[3]) and torch.equal(got[4].cpu(), want[4]) and torch.equal(got[2].cpu(), want[2])
+    assert int(want[4].sum()) == 3 * 120 or int(want[4].sum()) > 200
+    assert (got[1].cpu() - want[1]).abs().max() <= 1e-6
+
+
+def test_center_focal_loss_kernel_matches_oracle(G):
+    from oracle import center_oracle as CO
+    g = torch.Generator().manual_seed(0)
+    logits = (torch.randn(2, 3, 40, 48, generator=g) * 4).requires_grad_(True)      # +-12: both clamp sides are hit
+    heat = torch.rand(2, 3, 40, 48, generator=g) ** 6
+    heat[0, 1, 5, 7] = heat[1, 2, 30, 40] = heat[1, 0, 0, 0] = 1.0
+    for gt in (heat, heat.clamp(max=0.99)):                                        # second case: no positive at all
+        want = CO.focal_loss_from_logits(logits, gt)
+        gw, = torch.autograd.grad(want, logits)
+        lc = logits.detach().cuda().requires_grad_(True)
+        got = G.ops.CenterFocalLoss.apply(lc, gt.cuda())
+        gg, = torch.autograd.grad(got, lc)
+        assert abs(float(got) - float(want)) <= 1e-5 * abs(float(want))
+        assert rel(gg, gw) < 1e-5
+
+
+def test_finetune_step_matches_reference_golden(G, golden):
+    """BASELINE config 4 on the tiny grid: DynVFE + SPTBackbone (no masking, all three drop levels) + SSTBEVBackbone +
+    CenterHead, forward + loss + backward in the fp32 parity configuration against the unmodified reference's run
+    (tests/golden/finetune_tiny.npz): indices exact, features / predictions 1e-3, loss terms 1e-3, gradient norms 5e-3."""
+    K = golden("finetune_tiny")
+    model, cfg, ocfg = _build_finetune(G, "tiny_iou", K)
+    assert [str(k) for k in K["state_keys"]] == [k for k in model.state_dict().keys() if k != "global_step"] or \
+        set(str(k) for k in K["state_keys"]) == set(model.state_dict().keys()) - {"global_step"}
+    G.config.set_precision(model, "fp32")
+    model.train()
+    bd = dict(points=torch.from_numpy(K["points_in"]).cuda(), batch_size=int(K["batch_size"]), gt_boxes=torch.from_numpy(K["gt_boxes"]).cuda())
+    ret, tb, _ = model(bd)
+    ret["loss"].backward()
+    for i in range(3):
+        sp = bd["multi_scale_3d_features"][f"x_conv{i + 1}"]
+        assert np.array_equal(sp.indices.cpu().numpy(), K[f"x_conv{i + 1}.indices"])
+        assert rel(sp.features[::SUB], K[f"x_conv{i + 1}.features.sub"]) < 1e-3
+    assert rel(bd["spatial_features"][:, ::16, ::5, ::5], K["spatial_features.sub"]) < 1e-3
+    assert rel(bd["spatial_features_2d"][:, ::16, ::5, ::5], K["spatial_features_2d.sub"]) < 1e-3
+    pd = model.dense_head.forward_ret_dict["pred_dicts"][0]
+    for k, v in pd.items():
+        assert rel(v[:, :, ::5, ::5], K["pred." + k + ".sub"]) < 2e-3, k
+    td = model.dense_head.forward_ret_dict["target_dicts"]
+    assert np.array_equal(td["inds"][0].cpu().numpy(), K["inds"]) and np.array_equal(td["masks"][0].cpu().numpy(), K["masks"])
+    for k in ("hm_loss_head_0", "loc_loss_head_0", "iou_loss_head_0"):
+        assert abs(float(tb[k]) - float(K["tb." + k])) <= 1e-3 * abs(float(K["tb." + k])) + 1e-5, (k, float(tb[k]), float(K["tb." + k]))
+    assert abs(float(ret["loss"]) - float(K["loss"])) / float(K["loss"]) < 1e-3
+    grads = {k: p.grad for k, p in model.named_parameters()}
+    tot_ref = float(np.sqrt((K["grad_norms"] ** 2).sum()))
+    for k, gn in zip([str(s) for s in K["grad_keys"]], K["grad_norms"]):
+        mine = float(grads[k].norm()) if grads[k] is not None else 0.0
+        rtol = 5e-2 if k.endswith(".tau") else 5e-3
+        assert abs(mine - gn) <= rtol * max(gn, 1e-4 * tot_ref) + 1e-7, (k, mine, gn)
+
+
+def test_finetune_eval_decodes_and_suppresses(G, golden):
+    """eval path of CenterHead (generate_predicted_boxes: top-K decode, range / score filter, IoU-rectified multi-class
+    rotated NMS through the own NMS kernels): structural checks - boxes inside the limit range, labels 1..3, scores sorted
+    per class by the NMS, no surviving pair of one class above its IoU threshold."""
+    from gd_mae_b200.pcdet.ops.iou3d_nms import iou3d_nms_utils as U
+    K = golden("finetune_tiny")
+    model, cfg, ocfg = _build_finetune(G, "tiny_iou", K)
+    G.config.set_precision(model, "fp32")
+    model.eval()
+    with torch.no_grad():
+        preds, _ = model(dict(points=torch.from_numpy(K["points_in"]).cuda(), batch_size=int(K["batch_size"])))
+    assert len(preds) == int(K["batch_size"])
+    th = cfg.MODEL.DENSE_HEAD.POST_PROCESSING.NMS_CONFIG.NMS_THRESH
+    for p in preds:
+        assert p["pred_boxes"].shape[1] == 7 and p["pred_boxes"].shape[0] == p["pred_scores"].shape[0] == p["pred_labels"].shape[0]
+        if p["pred_boxes"].shape[0] == 0:
+            continue
+        assert int(p["pred_labels"].min()) >= 1 and int(p["pred_labels"].max()) <= 3
+        for c in (1, 2, 3):
+            b = p["pred_boxes"][p["pred_labels"] == c]
+            if b.shape[0] > 1:
+                iou = U.boxes_iou_bev(b.contiguous(), b.contiguous())
+                assert float(torch.triu(iou, 1).max()) <= th[c - 1] + 1e-4

@@ -248,3 +248,20 @@ def test_iou3d_host_entry_point_matches_reference_golden(golden):
         assert np.abs(iou - K[name + ".iou"]).max() <= 1e-6, name
     with pytest.raises(Exception):
         U.boxes_iou_bev(torch.zeros(2, 7), torch.zeros(2, 7))          # CPU tensors on the GPU entry point: no fallback
+
+
+# ------------------------------------------------------------------------------ CenterHead oracle
+def test_center_head_oracle_matches_reference_golden(golden):
+    """oracle/center_oracle.py against the targets the unmodified reference CenterHead assigned in
+    tests/golden/finetune_tiny.npz: heat map, indices and masks bit-exact, regression targets to float rounding."""
+    from oracle import center_oracle as CO
+    K = golden("finetune_tiny")
+    cfg = O.make_cfg("tiny")
+    X, Y, _ = cfg["grid"]
+    heat, tgt, iou_boxes, inds, mask = CO.assign_targets(torch.from_numpy(K["gt_boxes"]), [0, 1, 2, 3], 3, Y, X, cfg["pc_range"], cfg["voxel"])
+    ref_heat = np.zeros(int(np.prod(K["heatmap.shape"])), dtype=np.float32)
+    ref_heat[K["heatmap.nz_index"]] = K["heatmap.nz_value"]
+    assert np.array_equal(heat.numpy().reshape(-1), ref_heat)
+    assert np.array_equal(inds.numpy(), K["inds"]) and np.array_equal(mask.numpy(), K["masks"])
+    assert int(mask.sum()) == 16 and np.array_equal(iou_boxes.numpy(), K["iou_boxes"])
+    assert np.abs(tgt.numpy() - K["target_boxes"]).max() <= 1e-6
