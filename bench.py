@@ -8,9 +8,9 @@ own B=8 synthetic frames per step (weak scaling, frame sharded, one NCCL all-red
 gradient bucket per step).  ``value`` = frames/s with the inputs already resident in HBM;
 ``e2e`` = the same step driven through the public API with HOST (pinned) input batches, H2D copy
 and a D2H read of the loss inside the timed region.
-Reference arm (--impl reference): the reference algorithm on the box's host cores - the CPU
-oracle port (oracle/gdmae_oracle.py; the reference is Python and cannot travel to the GPU box,
-see DESIGN.md) - on a bounded sample (B=1 frame per step) of the same workload.
+Reference arm (--impl reference): the reference's own Python for the path on the box's host cores -
+the unmodified files under baseline/_ref/ (tools/install_reference.py; oracle port only if they are
+absent) - on a bounded sample (B=1 frame per step) of the same workload.
 """
 import argparse
 import json
@@ -116,62 +116,101 @@ def make_batches(n_batches, rank, cfg_o, O):
     return out
 
 
+class CpuReference:
+    """The reference's own Python for the path (DynVFE + SPTBackboneMAE forward, loss, backward, clip_grad_norm_, OptimWrapper
+    adam_onecycle step - train_utils.py:34-53) on the host CPUs: the UNMODIFIED files under baseline/_ref/ (byte-identical
+    copies placed by tools/install_reference.py; /root/reference itself does not exist on the GPU box) imported through
+    tests/golden/ref_harness.py, whose stand-ins cover only the third-party packages missing from the image.  ``kind`` is
+    "reference" then; if the copies are absent (a checkout that never ran build() next to the reference) the oracle port
+    runs instead and ``kind`` is "port"."""
+
+    def __init__(self, total_steps):
+        from oracle import gdmae_oracle as O
+        self.O, self.cfg = O, O.make_cfg("waymo_ssl")
+        self.cores = len(os.sched_getaffinity(0))
+        torch.set_num_threads(self.cores)
+        self.g = torch.Generator().manual_seed(666)
+        ref_root = os.path.join(ROOT, "baseline", "_ref")
+        if os.path.exists(os.path.join(ref_root, "MANIFEST.json")) or os.path.isdir("/root/reference"):
+            sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+            import ref_harness as RH
+            mcfg = RH.load_model_cfg("tools/cfgs/waymo_models/gd_mae_ssl.yaml")
+            torch.manual_seed(666)
+            self.model = RH.RefMAE(mcfg.MODEL, self.cfg["n_feat"], self.cfg["voxel"], np.array(self.cfg["pc_range"], dtype=np.float32),
+                                   np.array(self.cfg["grid"], dtype=np.int64)).train()
+            sys.path.insert(0, RH.REF + "/tools")
+            import train_utils.optimization as RO
+            self.opt = RO.build_optimizer(self.model, mcfg.OPTIMIZATION)
+            self.sched, _ = RO.build_scheduler(self.opt, total_iters_each_epoch=max(total_steps, 10), total_epochs=1, last_epoch=-1,
+                                               optim_cfg=mcfg.OPTIMIZATION)
+            self.clip = mcfg.OPTIMIZATION.GRAD_NORM_CLIP
+            self.kind = "reference"
+        else:
+            self.P, self.Bf = O.init_params(self.cfg, 0)
+            self.opt = O.AdamOneCycle(self.P, self.cfg, max(total_steps, 10))
+            self.kind = "port"
+
+    def step(self, pts, it):
+        if self.kind == "reference":
+            from torch.nn.utils import clip_grad_norm_
+            self.sched.step(it)
+            self.opt.zero_grad()
+            loss, _ = self.model(dict(points=pts, batch_size=1))
+            loss.backward()
+            clip_grad_norm_(self.model.parameters(), self.clip)
+            self.opt.step()
+            return float(loss.detach())
+        O = self.O
+        _, _, _, vc, _ = O.voxelize(pts, self.cfg)
+        return O.train_step(self.P, self.Bf, self.opt, pts, 1, self.cfg, torch.rand(vc.shape[0], generator=self.g), it)[0]
+
+    def describe(self):
+        what = ("the reference's own Python (baseline/_ref, unmodified) through its DynVFE / SPTBackboneMAE / OptimWrapper"
+                if self.kind == "reference" else "torch CPU oracle port")
+        return f"B=1 frame (~159k points) per step of the same synthetic Waymo-shape generator; fwd+loss+bwd+clip+adam_onecycle, fp32, {what}"
+
+
 def run_reference(args):
-    """The reference algorithm on the host CPUs (oracle port), bounded sample: B=1 frame per step."""
-    from oracle import gdmae_oracle as O
+    """The reference's CPU implementation of the path on the host cores, bounded sample: B=1 frame per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = len(os.sched_getaffinity(0))
-    torch.set_num_threads(cores)
-    cfg = O.make_cfg("waymo_ssl")
-    P, Bf = O.init_params(cfg, 0)
+    import warnings
+    warnings.filterwarnings("ignore")
     total = max(args.steps + args.warmup, 2)
-    opt = O.AdamOneCycle(P, cfg, max(total, 10))   # the one-cycle schedule needs a few steps per phase
-    frames = [torch.from_numpy(O.synth_batch([s], cfg)) for s in range(min(total, 4))]
-    g = torch.Generator().manual_seed(666)
-
-    def one(it):
-        pts = frames[it % len(frames)]
-        _, _, _, vc, _ = O.voxelize(pts, cfg)
-        return O.train_step(P, Bf, opt, pts, 1, cfg, torch.rand(vc.shape[0], generator=g), it)[0]
-
+    R = CpuReference(total)
+    frames = [torch.from_numpy(R.O.synth_batch([s], R.cfg)) for s in range(min(total, 4))]
     for it in range(args.warmup):
-        one(it)
+        R.step(frames[it % len(frames)], it)
     t0 = time.perf_counter()
     for it in range(args.steps):
-        loss = one(args.warmup + it)
+        loss = R.step(frames[(args.warmup + it) % len(frames)], args.warmup + it)
     dt = time.perf_counter() - t0
     v = args.steps / dt
-    sample = "B=1 frame (~159k points) per step of the same synthetic Waymo-shape generator; fwd+loss+bwd+clip+AdamOneCycle, fp32"
+    sample = R.describe()
     print(json.dumps({
         "impl": "reference", "metric": "mae_pretrain_frames_per_sec", "value": v, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": R.cores, "kind": R.kind, "sample": sample},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "final_loss": float(loss)}))
 
 
-def cpu_baseline_leg(O, budget_s=25.0):
-    """Rank 0, N=1: the oracle on the host cores for a bounded sample of the same workload."""
-    cores = len(os.sched_getaffinity(0))
-    torch.set_num_threads(cores)
-    cfg = O.make_cfg("waymo_ssl")
-    P, Bf = O.init_params(cfg, 0)
-    opt = O.AdamOneCycle(P, cfg, 10)
-    pts = torch.from_numpy(O.synth_batch([0], cfg))
-    _, _, _, vc, _ = O.voxelize(pts, cfg)
-    g = torch.Generator().manual_seed(666)
-    O.train_step(P, Bf, opt, pts, 1, cfg, torch.rand(vc.shape[0], generator=g), 0)  # warm-up
+def cpu_baseline_leg(budget_s=25.0):
+    """Rank 0, N=1: the reference's CPU implementation on the host cores for a bounded sample of the same workload."""
+    import warnings
+    warnings.filterwarnings("ignore")
+    R = CpuReference(10)
+    pts = torch.from_numpy(R.O.synth_batch([0], R.cfg))
+    R.step(pts, 0)  # warm-up
     n, t0 = 0, time.perf_counter()
     while n < 3 or (time.perf_counter() - t0 < budget_s and n < 8):
-        O.train_step(P, Bf, opt, pts, 1, cfg, torch.rand(vc.shape[0], generator=g), n + 1)
+        R.step(pts, n + 1)
         n += 1
     dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": f"{n} iterations of B=1 frame (~159k points): fwd+loss+bwd+clip+AdamOneCycle, fp32, torch CPU oracle"}
+    return {"value": n / dt, "unit": "frames/s", "cores": R.cores, "kind": R.kind, "sample": f"{n} iterations of " + R.describe()}
 
 
 def main():
@@ -380,7 +419,7 @@ def main():
     assert n_to == 0, f"{n_to} bounded waits inside the SRA kernels timed out: results are invalid"
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline_leg(O)
+            out["cpu_baseline"] = cpu_baseline_leg()
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -23,7 +23,12 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-REF = "/root/reference"
+import os
+
+# the reference checkout in the build container; on the GPU box the byte-identical copies under baseline/_ref/
+# (tools/install_reference.py) - bench.py's reference arm runs from there
+_LOCAL = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "baseline", "_ref")
+REF = os.environ.get("GDMAE_REF_ROOT") or ("/root/reference" if os.path.isdir("/root/reference") else _LOCAL)
 
 
 class AttrDict(dict):

@@ -80,15 +80,18 @@ def test_record_stream_walker_visits_nested_structures():
 
 
 def test_bench_reference_arm_prints_the_contract_line():
-    """bench.py --impl reference (the oracle port on the host cores, bounded sample) - one step, checks the JSON keys"""
+    """bench.py --impl reference (the reference's own Python from baseline/_ref on the host cores - the oracle port only when
+    those copies are absent -, bounded sample) - one step, checks the JSON keys"""
     env = dict(os.environ, OMP_NUM_THREADS="8")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "mae_pretrain_frames_per_sec" and line["unit"] == "frames/s"
-    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["higher_is_better"] is True
+    have_ref = os.path.exists(os.path.join(ROOT, "baseline", "_ref", "MANIFEST.json")) or os.path.isdir("/root/reference")
+    assert line["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")
     # other ranks of a torchrun launch exit 0 without work
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
                          capture_output=True, text=True, timeout=120, env=dict(env, RANK="1", WORLD_SIZE="2"), cwd=ROOT)
