@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256) center_focal_kernel(const float* __restri
     const float xv = x[i], g = gt[i];
     const float s = 1.f / (1.f + expf(-xv));
     const float p = fminf(fmaxf(s, 1e-4f), 1.f - 1e-4f);
-    const float dpdx = (s > 1e-4f && s < 1.f - 1e-4f) ? s * (1.f - s) : 0.f;
+    const float dpdx = (s >= 1e-4f && s <= 1.f - 1e-4f) ? s * (1.f - s) : 0.f;   // torch.clamp passes the gradient on [min, max]
     float dldp;
     if (g == 1.f) {
       const float q = 1.f - p, lp = logf(p);

@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(256) vfe2_apply_max_kernel(const T* __restrict
                                                              const int* __restrict__ seg_pts, int M, const float* __restrict__ mean,
                                                              const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, float* __restrict__ out,
-                                                             int* __restrict__ arg) {
+                                                             unsigned char* __restrict__ arg) {
   const int lane = threadIdx.x & 31;
   const float4 mu = __ldg(reinterpret_cast<const float4*>(mean) + lane), rs = __ldg(reinterpret_cast<const float4*>(rstd) + lane);
   const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + lane), be = __ldg(reinterpret_cast<const float4*>(beta) + lane);
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(256) vfe2_apply_max_kernel(const T* __restrict
     const int mn = m + stride;
     const int sn = mn < M ? __ldg(seg_off + mn) : 0, en = mn < M ? __ldg(seg_off + mn + 1) : 0;
     float4 best = make_float4(0.f, 0.f, 0.f, 0.f);
-    int4 bi = make_int4(-1, -1, -1, -1);
+    int4 bi = make_int4(0, 0, 0, 0);
     if (SORTED) {
       for (int k = s; k < e; k += 4) {
         float4 v[4];
@@ -326,10 +326,10 @@ __global__ void __launch_bounds__(256) vfe2_apply_max_kernel(const T* __restrict
             w.y = fmaxf(fmaf(v[u].y - mu.y, a.y, be.y), 0.f);
             w.z = fmaxf(fmaf(v[u].z - mu.z, a.z, be.z), 0.f);
             w.w = fmaxf(fmaf(v[u].w - mu.w, a.w, be.w), 0.f);
-            if (pnt == s || w.x > best.x) { best.x = w.x; bi.x = pnt; }
-            if (pnt == s || w.y > best.y) { best.y = w.y; bi.y = pnt; }
-            if (pnt == s || w.z > best.z) { best.z = w.z; bi.z = pnt; }
-            if (pnt == s || w.w > best.w) { best.w = w.w; bi.w = pnt; }
+            if (pnt == s || w.x > best.x) { best.x = w.x; bi.x = pnt - s; }
+            if (pnt == s || w.y > best.y) { best.y = w.y; bi.y = pnt - s; }
+            if (pnt == s || w.z > best.z) { best.z = w.z; bi.z = pnt - s; }
+            if (pnt == s || w.w > best.w) { best.w = w.w; bi.w = pnt - s; }
           }
         }
       }
@@ -341,14 +341,18 @@ __global__ void __launch_bounds__(256) vfe2_apply_max_kernel(const T* __restrict
         v.y = fmaxf(fmaf(v.y - mu.y, a.y, be.y), 0.f);
         v.z = fmaxf(fmaf(v.z - mu.z, a.z, be.z), 0.f);
         v.w = fmaxf(fmaf(v.w - mu.w, a.w, be.w), 0.f);
-        if (k == s || v.x > best.x) { best.x = v.x; bi.x = pnt; }
-        if (k == s || v.y > best.y) { best.y = v.y; bi.y = pnt; }
-        if (k == s || v.z > best.z) { best.z = v.z; bi.z = pnt; }
-        if (k == s || v.w > best.w) { best.w = v.w; bi.w = pnt; }
+        if (k == s || v.x > best.x) { best.x = v.x; bi.x = k - s; }
+        if (k == s || v.y > best.y) { best.y = v.y; bi.y = k - s; }
+        if (k == s || v.z > best.z) { best.z = v.z; bi.z = k - s; }
+        if (k == s || v.w > best.w) { best.w = v.w; bi.w = k - s; }
       }
     }
     reinterpret_cast<float4*>(out)[(long long)m * (V_C2 / 4) + lane] = best;
-    reinterpret_cast<int4*>(arg)[(long long)m * (V_C2 / 4) + lane] = bi;
+    // the arg-max is kept as ONE BYTE per (pillar, channel): the position inside the pillar's CSR segment, saturated at 255
+    // (r1 stored the int32 row: 108-126 MB of extra writes per step, 1.21x the algorithmic bytes of this kernel).  Pillars
+    // with more than 255 points are rare (Waymo: max ~70); the backward pass recomputes their arg-max instead of reading it.
+    reinterpret_cast<uchar4*>(arg)[(long long)m * (V_C2 / 4) + lane] =
+        make_uchar4((unsigned char)min(bi.x, 255), (unsigned char)min(bi.y, 255), (unsigned char)min(bi.z, 255), (unsigned char)min(bi.w, 255));
     m = mn; s = sn; e = en;
   }
 }
@@ -386,10 +390,11 @@ __global__ void __launch_bounds__(256) vfe2_bwd_stats_kernel(int M, const float*
 template <typename T, bool SORTED>
 __global__ void __launch_bounds__(256) vfe2_bwd_apply_kernel(const T* __restrict__ y, const int* __restrict__ seg_off,
                                                              const int* __restrict__ seg_pts, int M, const float* __restrict__ out,
-                                                             const int* __restrict__ arg, const float* __restrict__ dout,
+                                                             const unsigned char* __restrict__ arg, const float* __restrict__ dout,
                                                              const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                             const float* __restrict__ gamma, const float* __restrict__ dbeta,
-                                                             const float* __restrict__ dgamma, float inv_n, T* __restrict__ dy) {
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             const float* __restrict__ dbeta, const float* __restrict__ dgamma,
+                                                             float inv_n, T* __restrict__ dy) {
   const int lane = threadIdx.x & 31;
   const float4 mu = __ldg(reinterpret_cast<const float4*>(mean) + lane), rs = __ldg(reinterpret_cast<const float4*>(rstd) + lane);
   const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + lane);
@@ -403,16 +408,33 @@ __global__ void __launch_bounds__(256) vfe2_bwd_apply_kernel(const T* __restrict
     // against 259 us, and a four-rows-in-flight body 259 us against this loop's ~240 us: kept simple)
     const float4 o = __ldg(reinterpret_cast<const float4*>(out) + (long long)m * (V_C2 / 4) + lane);
     float4 g = __ldg(reinterpret_cast<const float4*>(dout) + (long long)m * (V_C2 / 4) + lane);
-    const int4 ai = __ldg(reinterpret_cast<const int4*>(arg) + (long long)m * (V_C2 / 4) + lane);
+    const uchar4 a8 = __ldg(reinterpret_cast<const uchar4*>(arg) + (long long)m * (V_C2 / 4) + lane);
+    int4 ai = make_int4(a8.x, a8.y, a8.z, a8.w);          // position of the arg-max row inside the pillar's segment
+    if (e - s > 255) {
+      // a byte cannot address this pillar's rows: recompute the arg-max (first maximum of relu(bn(y)), as the forward did)
+      float4 best = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = s; k < e; ++k) {
+        const int pnt = SORTED ? k : seg_pts[k];
+        const float4 v = VT<T>::load4(y, (long long)pnt * (V_C2 / 4) + lane);
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta) + lane);
+        const float wx = fmaxf(fmaf(v.x - mu.x, a0.x, b4.x), 0.f), wy = fmaxf(fmaf(v.y - mu.y, a0.y, b4.y), 0.f);
+        const float wz = fmaxf(fmaf(v.z - mu.z, a0.z, b4.z), 0.f), ww = fmaxf(fmaf(v.w - mu.w, a0.w, b4.w), 0.f);
+        if (k == s || wx > best.x) { best.x = wx; ai.x = k - s; }
+        if (k == s || wy > best.y) { best.y = wy; ai.y = k - s; }
+        if (k == s || wz > best.z) { best.z = wz; ai.z = k - s; }
+        if (k == s || ww > best.w) { best.w = ww; ai.w = k - s; }
+      }
+    }
     g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f; g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
     for (int k = s; k < e; ++k) {
       const int pnt = SORTED ? k : seg_pts[k];
+      const int off = k - s;
       const float4 v = VT<T>::load4(y, (long long)pnt * (V_C2 / 4) + lane);
       float4 r;
-      r.x = a0.x * (ai.x == pnt ? g.x : 0.f) - a1.x - (v.x - mu.x) * rs.x * a2.x;
-      r.y = a0.y * (ai.y == pnt ? g.y : 0.f) - a1.y - (v.y - mu.y) * rs.y * a2.y;
-      r.z = a0.z * (ai.z == pnt ? g.z : 0.f) - a1.z - (v.z - mu.z) * rs.z * a2.z;
-      r.w = a0.w * (ai.w == pnt ? g.w : 0.f) - a1.w - (v.w - mu.w) * rs.w * a2.w;
+      r.x = a0.x * (ai.x == off ? g.x : 0.f) - a1.x - (v.x - mu.x) * rs.x * a2.x;
+      r.y = a0.y * (ai.y == off ? g.y : 0.f) - a1.y - (v.y - mu.y) * rs.y * a2.y;
+      r.z = a0.z * (ai.z == off ? g.z : 0.f) - a1.z - (v.z - mu.z) * rs.z * a2.z;
+      r.w = a0.w * (ai.w == off ? g.w : 0.f) - a1.w - (v.w - mu.w) * rs.w * a2.w;
       VT<T>::store4(dy, (long long)pnt * (V_C2 / 4) + lane, r);
     }
   }
@@ -519,7 +541,7 @@ extern "C" int gdmae_vfe_mlp_bwd(const gdmae_vfe_mlp_args* a) {
   const int g3 = gdmae_grid((long long)M * 32, 256, 16);
 #define VFE_BWD_APPLY(T, S)                                                                                                        \
   vfe2_bwd_apply_kernel<T, S><<<g3, 256, 0, st>>>((const T*)a->y2, a->seg_offsets, a->seg_points, M, a->out, a->argmax, a->dout, a->mean2, \
-                                                  a->rstd2, a->g2, a->tmp_dbeta2, a->tmp_dgamma2, inv_n, (T*)a->dy2)
+                                                  a->rstd2, a->g2, a->b2, a->tmp_dbeta2, a->tmp_dgamma2, inv_n, (T*)a->dy2)
   const bool sorted = a->seg_points == nullptr;
   if (bf) { if (sorted) VFE_BWD_APPLY(vbf16, true); else VFE_BWD_APPLY(vbf16, false); }
   else { if (sorted) VFE_BWD_APPLY(float, true); else VFE_BWD_APPLY(float, false); }

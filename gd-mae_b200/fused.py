@@ -362,7 +362,7 @@ class VfeMlpFunction(torch.autograd.Function):
         y2 = torch.empty((Np, 128), dtype=opdt, device=dev)
         stats = torch.empty((4 * 128 + 4 * 128,), dtype=F32, device=dev)      # mean1 rstd1 mean2 rstd2 | 4 scratch rows
         out = torch.empty((M, 128), dtype=F32, device=dev)
-        arg = torch.empty((M, 128), dtype=torch.int32, device=dev)
+        arg = torch.empty((M, 128), dtype=torch.uint8, device=dev)   # position inside the pillar's segment (csrc/vfe_mlp.cu)
         for name, t in (("x", x), ("seg_offsets", seg_offsets), ("seg_points", seg_points), ("W1", W1), ("g1", g1), ("b1", b1),
                         ("g2", g2), ("b2", b2), ("W2_g", W2g), ("running_mean1", rm1), ("running_var1", rv1), ("running_mean2", rm2),
                         ("running_var2", rv2), ("h1", h1), ("y2", y2), ("out", out), ("argmax", arg)):

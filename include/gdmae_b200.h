@@ -210,7 +210,7 @@ typedef struct gdmae_vfe_mlp_args {
   void* y2;               /* (Np,128) op */
   float *mean1, *rstd1, *mean2, *rstd2;
   float* out;             /* (M,128) pillar features */
-  int32_t* argmax;        /* (M,128) point row of each maximum */
+  uint8_t* argmax;        /* (M,128) position of each maximum inside its pillar's segment, saturated at 255 (then recomputed) */
   /* backward */
   const float* dout;      /* (M,128) */
   void* dy2;              /* (Np,128) op scratch */
