@@ -27,24 +27,18 @@ sst_ops_cuda = _SstOpsCuda()
 
 
 def get_inner_win_inds(group_inds):
-    """
-    Args:
-        group_inds: (N,)
-    """
-    out_inds = torch.zeros_like(group_inds) - 1
-    sst_ops_cuda.ingroup_inds_wrapper(group_inds.contiguous(), out_inds)
-    return out_inds
+    """(N,) group id of every element -> (N,) its running index inside the group, in ascending element order
+    (sst_ops_utils.py:5-12; the reference's atomic counter leaves the order to arrival)."""
+    running = torch.full_like(group_inds, -1)
+    sst_ops_cuda.ingroup_inds_wrapper(group_inds.contiguous(), running)
+    return running
 
 
 def group_inner_inds(points, inverse_inds, K):
-    """
-    Args:
-        points: (N, C)
-        inverse_inds: (N, )
-    Return:
-        group_points: (valid_voxel_num + 1, K, C)
-    """
-    valid_voxel_num = inverse_inds.max().item()
-    group_inds = torch.full((valid_voxel_num + 1, K), -1, dtype=torch.long, device=points.device)
-    sst_ops_cuda.group_inner_inds_wrapper(inverse_inds.contiguous(), group_inds)
-    return points[group_inds]
+    """points (N, C), inverse_inds (N,) pillar of every point -> (n_pillars, K, C): the first K points of every pillar,
+    cyclically repeated when a pillar holds fewer (sst_ops_utils.py:15-27).  The pillar count is read from the device
+    (one host sync, as in the reference); SPTBackboneMAE uses ops.group_points_centered on the CSR instead."""
+    n_groups = int(inverse_inds.max()) + 1
+    slots = torch.full((n_groups, K), -1, dtype=torch.long, device=points.device)
+    sst_ops_cuda.group_inner_inds_wrapper(inverse_inds.contiguous(), slots)
+    return points[slots]

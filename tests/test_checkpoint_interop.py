@@ -118,3 +118,41 @@ def test_optimizer_state_interop_with_reference_optimizer():
         if p in opt.opt.state:
             assert torch.equal(opt2.opt.state[p]["exp_avg"], opt.opt.state[p]["exp_avg"])
             assert float(opt2.opt.state[p]["step"]) == 2.0
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="needs the reference checkout (build container only)")
+@pytest.mark.parametrize("yaml_rel,builtin", [("tools/cfgs/waymo_models/gd_mae_ssl.yaml", "waymo_ssl"), ("tools/cfgs/once_models/gd_mae_ssl.yaml", "once_ssl"),
+                                              ("tools/cfgs/kitti_models/gd_mae.yaml", "kitti"), ("tools/cfgs/waymo_models/gd_mae_iou.yaml", "waymo_iou")])
+def test_yaml_loader_and_builtin_configs_against_reference_yamls(yaml_rel, builtin):
+    """config.cfg_from_yaml_file (pcdet/config.py:71-85 incl. _BASE_CONFIG_ merging) on the reference's own yaml files, and the
+    restated built-in configs against what the files say: every MODEL hyper-parameter the built-in carries, the point-cloud
+    range, voxel size and the optimizer block.  (The yaml files are read where they lie; none is copied into the repo.)"""
+    cfg = config.cfg_from_yaml_file(os.path.join(REF, yaml_rel), root=os.path.join(REF, "tools"))
+    mine = config.builtin_cfg(builtin)
+    assert "DATA_CONFIG" in cfg and "POINT_CLOUD_RANGE" in cfg.DATA_CONFIG                      # merged from the _BASE_CONFIG_ file
+    assert [float(np.float32(v)) for v in cfg.DATA_CONFIG.POINT_CLOUD_RANGE] == [float(v) for v in mine.POINT_CLOUD_RANGE]   # stored as float32
+    vox = [p for p in cfg.DATA_CONFIG.DATA_PROCESSOR if "VOXEL_SIZE" in p][0].VOXEL_SIZE       # calculate_grid_size / transform_points_to_voxels
+    assert [float(v) for v in vox] == [float(v) for v in mine.VOXEL_SIZE]
+
+    def covered(a, b, path):
+        """every key the built-in carries must exist in the yaml with the same value"""
+        if isinstance(a, dict):
+            for k, v in a.items():
+                assert k in b, path + "." + k
+                covered(v, b[k], path + "." + k)
+        elif isinstance(a, (list, tuple)):
+            assert len(a) == len(b), path
+            for i, (x, y) in enumerate(zip(a, b)):
+                covered(x, y, f"{path}[{i}]")
+        elif isinstance(a, float) or isinstance(b, float):
+            assert abs(float(a) - float(b)) <= 1e-9 * max(1.0, abs(float(b))), (path, a, b)
+        else:
+            assert a == b, (path, a, b)
+
+    if builtin == "kitti":          # the KITTI yaml is the detection config: only its VFE and first SST block are on the C1 plumbing path
+        covered(mine.MODEL.VFE, cfg.MODEL.VFE, "MODEL.VFE")
+        covered(mine.MODEL.BACKBONE_3D.SST_BLOCK_LIST[0], cfg.MODEL.BACKBONE_3D.SST_BLOCK_LIST[0], "SST_BLOCK_LIST[0]")
+    else:
+        covered(mine.MODEL, cfg.MODEL, "MODEL")
+        covered({k: v for k, v in mine.OPTIMIZATION.items() if k in cfg.OPTIMIZATION}, cfg.OPTIMIZATION, "OPTIMIZATION")
+        assert mine.OPTIMIZATION.OPTIMIZER == cfg.OPTIMIZATION.OPTIMIZER == "adam_onecycle"
