@@ -1058,6 +1058,8 @@ def test_finetune_step_matches_reference_golden(G, golden):
     assert rel(bd["spatial_features_2d"][:, ::16, ::5, ::5], K["spatial_features_2d.sub"]) < 1e-3
     pd = model.dense_head.forward_ret_dict["pred_dicts"][0]
     for k, v in pd.items():
+        if k == "hm":      # the reference's get_loss replaces pred_dict['hm'] by its clamped sigmoid in place (center_head.py:246)
+            v = torch.clamp(v.sigmoid(), min=1e-4, max=1 - 1e-4)
         assert rel(v[:, :, ::5, ::5], K["pred." + k + ".sub"]) < 2e-3, k
     td = model.dense_head.forward_ret_dict["target_dicts"]
     assert np.array_equal(td["inds"][0].cpu().numpy(), K["inds"]) and np.array_equal(td["masks"][0].cpu().numpy(), K["masks"])
