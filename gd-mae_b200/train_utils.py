@@ -13,6 +13,8 @@ def model_state_to_cpu(model_state):
 
 def checkpoint_state(model=None, optimizer=None, epoch=None, it=None):
     """``optimizer``: a MAETrainer; its Adam moments are stored in the reference's ``optimizer_state`` layout"""
+    if optimizer is not None and hasattr(optimizer, 'sync_buffers'):
+        optimizer.sync_buffers()            # every rank saves rank 0's BatchNorm statistics (what DDP's broadcast_buffers leaves)
     optim_state = optimizer.state_dict(reference_format=True) if optimizer is not None else None
     model_state = model_state_to_cpu(model.state_dict()) if model is not None else None
     return {'epoch': epoch, 'it': it, 'model_state': model_state, 'optimizer_state': optim_state, 'version': VERSION}
