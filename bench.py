@@ -309,6 +309,7 @@ def main():
         torch.cuda.synchronize()
 
     sampler = ClockSampler(dev)
+    device_allocs = []      # cudaMalloc calls of the caching allocator inside each timed leg (0 in a steady-state loop)
 
     def timed(fn, steps, warmup, sample=True):
         """W untimed steps, then exactly `steps` steps between barrier+synchronize on both sides, CUDA events on the
@@ -318,6 +319,7 @@ def main():
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = _lib.lib().gdmae_launch_count()
+        mallocs0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
         if sample:
             sampler.start()
         e0.record()
@@ -329,6 +331,7 @@ def main():
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        device_allocs.append(torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - mallocs0)
         return float(ms) / steps, last, _lib.lib().gdmae_launch_count() - l0
 
     # ---- leg 1: device-resident timing (`value`)
@@ -412,7 +415,8 @@ def main():
                                   "prefetched (MAETrainer.step(batch, next_batch)); loss.item() every step"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "rooflines": rooflines, "kernels": kernels,
         "instrumented_pass": {"steps": n_prof + 1, "ms_per_step": ms_prof, "note": "separate pass after both timed legs; CUDA events around the kernels listed in `kernels`"},
-        "final_loss": float(last_loss), "final_loss_e2e": float(last_e2e), "host_cores": len(os.sched_getaffinity(0)),
+        "final_loss": float(last_loss), "final_loss_e2e": float(last_e2e),
+        "cuda_mallocs_in_timed_legs": {"value": device_allocs[0], "e2e": device_allocs[1]}, "host_cores": len(os.sched_getaffinity(0)),
     }
     from gd_mae_b200 import ops as _ops
     n_to = _ops.sra_wait_timeouts()

@@ -185,8 +185,17 @@ extern "C" int gdmae_encoder_layer_bwd(const gdmae_encoder_layer_args* a) {
                                a->d_be2, a->d_b2, acc, rw, rw_bytes, a->stream));   // d_b2 = column sums of dz2, same pass
   const void* dz2_op = bf ? (const void*)dz2g : (const void*)dz2;
   EL_CALL(el_gemm(a, 1, 0, d, dff, N, dz2_op, d, a->g, dff, a->d_w2, dff, 0, wbeta));
-  EL_CALL(el_gemm(a, 0, 0, N, dff, d, dz2_op, d, a->w2_g, dff, dgl, dff, ob, 0.f));
-  EL_CALL(ew_bias_gelu_bwd(a->h, dgl, ob, a->b1, N, dff, bf ? nullptr : dh, bf ? dh : nullptr, a->d_b1, acc, rw, rw_bytes, a->stream));
+  if (bf) {
+    // dgl = dz2 W2 never leaves the GEMM: its epilogue multiplies by gelu'(h + b1), writes dh (bf16) and adds the column
+    // sums (the gradient of b1) to d_b1
+    if (!acc) GDMAE_CHECK_CUDA(cudaMemsetAsync(a->d_b1, 0, (size_t)dff * sizeof(float), st));
+    gdmae_tc_epilogue eg = {};
+    eg.mode = 3; eg.bias = a->b1; eg.h16 = a->h; eg.ldh = dff; eg.colsum = a->d_b1;
+    EL_CALL(gdmae_tc_gemm(0, 0, N, dff, d, dz2_op, d, a->w2_g, dff, dh, dff, 1, 0.f, 0, &eg, a->stream));
+  } else {
+    EL_CALL(el_gemm(a, 0, 0, N, dff, d, dz2_op, d, a->w2_g, dff, dgl, dff, ob, 0.f));
+    EL_CALL(ew_bias_gelu_bwd(a->h, dgl, ob, a->b1, N, dff, dh, nullptr, a->d_b1, acc, rw, rw_bytes, a->stream));
+  }
   EL_CALL(el_gemm(a, 1, 0, dff, d, N, dh, dff, x1g, d, a->d_w1, d, 0, wbeta));
   EL_CALL(el_gemm(a, 0, 0, N, d, dff, dh, dff, a->w1_g, d, dz2, d, 0, 1.f));   // dz2 := gradient w.r.t. x1
   // ---- LayerNorm 1 and the attention

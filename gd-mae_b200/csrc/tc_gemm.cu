@@ -49,6 +49,7 @@ struct TcgParams {
   void* C; long long ldc; int c_bf16; int beta_one; int atomic;
   const float* bias; void* C2; long long ldc2;
   const float* res; const float* gamma; const float* beta_ln; float eps; float* y32; void* y16; float* mean; float* rstd;
+  const void* h16; long long ldh; float* colsum;      // GELU-backward epilogue
 };
 
 __device__ unsigned int g_tcg_wait_timeouts;
@@ -237,7 +238,50 @@ __device__ __forceinline__ float gelu_fast(float v) {
   return v * 0.5f * (1.f + copysignf(erf_abs, v));
 }
 
-enum { EPI_PLAIN = 0, EPI_GELU = 1, EPI_LN = 2 };
+// d GELU(v) / dv = Phi(v) + v phi(v), same approximation
+__device__ __forceinline__ float gelu_grad_fast(float v) {
+  const float z = fabsf(v) * 0.70710678118654752440f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+  const float e = __expf(-0.5f * v * v);
+  const float poly = fmaf(fmaf(fmaf(fmaf(1.061405429f, t, -1.453152027f), t, 1.421413741f), t, -0.284496736f), t, 0.254829592f) * t;
+  const float cdf = 0.5f * (1.f + copysignf(fmaf(-poly, e, 1.f), v));
+  return fmaf(v, 0.39894228040143267794f * e, cdf);
+}
+// 32 rows x 32 bf16 columns of a global matrix, coalesced (8 rows x 64 bytes per warp instruction), requested early
+__device__ __forceinline__ void prefetch_bf16(const __nv_bfloat16* base, long long ld, int r0, int col, int M, int lane, uint4 (&pre)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = (lane >> 2) + 8 * i, j = lane & 3;
+    pre[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (r0 + r < M) pre[i] = *reinterpret_cast<const uint4*>(base + (long long)(r0 + r) * ld + col + j * 8);
+  }
+}
+// the prefetched unit, transposed through the buffer: this thread's row as 32 floats
+__device__ __forceinline__ void take_prefetched_bf16(uint8_t* buf, int lane, const uint4 (&pre)[4], float (&out)[32]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(buf + bf16_slot((lane >> 2) + 8 * i, lane & 3)) = pre[i];
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint4 u = *reinterpret_cast<const uint4*>(buf + bf16_slot(lane, i));
+    const unsigned w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      out[8 * i + 2 * k] = __uint_as_float(w[k] << 16);
+      out[8 * i + 2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+    }
+  }
+  __syncwarp();
+}
+// column sums of a staged fp32 unit (32 rows): lane = column
+__device__ __forceinline__ float unit_colsum(const uint8_t* buf, int lane) {
+  float t = 0.f;
+#pragma unroll
+  for (int r = 0; r < 32; ++r) t += *reinterpret_cast<const float*>(buf + f32_slot(r, lane >> 2) + (lane & 3) * 4);
+  return t;
+}
+
+enum { EPI_PLAIN = 0, EPI_GELU = 1, EPI_LN = 2, EPI_GELU_BWD = 3 };
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tcg_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -408,6 +452,33 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tcg_gemm_kernel(const __grid_c
           stage_bf16(buf, lane, v);
           flush_bf16(buf, lane, reinterpret_cast<__nv_bfloat16*>(p.C2), p.ldc2, r0, col0 + c * 32, p.M);
         }
+      } else if (EPI == EPI_GELU_BWD) {
+        // acc = dg (gradient w.r.t. gelu(h + bias)); C = dh = dg * gelu'(h + bias) (bf16) and its column sums (the
+        // gradient of the bias) are added to p.colsum.  h (bf16) of chunk c + 1 is requested while chunk c is processed.
+        uint4 pre[4];
+        float hv[32];
+        prefetch_bf16(reinterpret_cast<const __nv_bfloat16*>(p.h16), p.ldh, r0, col0, p.M, lane, pre);
+        mbar_wait(tfull + acc, acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < HC / 32; ++c) {
+          tmem_ld32(taddr + c * 32, v);
+          take_prefetched_bf16(buf, lane, pre, hv);
+          if (c + 1 < HC / 32) prefetch_bf16(reinterpret_cast<const __nv_bfloat16*>(p.h16), p.ldh, r0, col0 + (c + 1) * 32, p.M, lane, pre);
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + col0 + c * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(bp + j);
+            v[4 * j] *= gelu_grad_fast(hv[4 * j] + b.x); v[4 * j + 1] *= gelu_grad_fast(hv[4 * j + 1] + b.y);
+            v[4 * j + 2] *= gelu_grad_fast(hv[4 * j + 2] + b.z); v[4 * j + 3] *= gelu_grad_fast(hv[4 * j + 3] + b.w);
+          }
+          stage_f32(buf, lane, v);               // rows past M hold zeros (their A rows were zero-filled by TMA)
+          __syncwarp();
+          atomicAdd(p.colsum + col0 + c * 32 + lane, unit_colsum(buf, lane));
+          __syncwarp();
+          stage_bf16(buf, lane, v);
+          flush_bf16(buf, lane, reinterpret_cast<__nv_bfloat16*>(p.C), p.ldc, r0, col0 + c * 32, p.M);
+        }
       } else {
         // z = acc + bias + residual row; y = LayerNorm(z) * gamma + beta.  N == BN: the tile holds whole rows, shared by
         // the two warps of a lane quarter (column halves), which exchange their partial sums through shared memory.  z
@@ -566,7 +637,7 @@ extern "C" int gdmae_tc_gemm(int transa, int transb, int64_t M, int64_t N, int64
   GDMAE_CHECK_ARG(beta == 0.f || (beta == 1.f && c_dtype == 0));
   if (M == 0) return GDMAE_OK;
   const int mode = epi ? epi->mode : 0;
-  GDMAE_CHECK_ARG(mode >= 0 && mode <= 2);
+  GDMAE_CHECK_ARG(mode >= 0 && mode <= 3);
   GDMAE_CHECK_ARG(N % 64 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0);
   GDMAE_CHECK_ARG(mode == EPI_LN || (C && ((uintptr_t)C & 15) == 0 && ldc % 8 == 0));
   GDMAE_CHECK_ARG(!transa || M % 64 == 0);           // MN-major A is loaded as 64-wide boxes
@@ -577,6 +648,8 @@ extern "C" int gdmae_tc_gemm(int transa, int transb, int64_t M, int64_t N, int64
     GDMAE_CHECK_ARG(((uintptr_t)epi->y32 & 15) == 0 && ((uintptr_t)epi->y16 & 15) == 0 && ((uintptr_t)epi->res & 15) == 0);
     BN = (int)N;
   }
+  if (mode == EPI_GELU_BWD)
+    GDMAE_CHECK_ARG(epi->bias && epi->h16 && epi->colsum && c_dtype == 1 && N % 128 == 0 && epi->ldh % 8 == 0 && ((uintptr_t)epi->h16 & 15) == 0);
   if (mode == EPI_GELU) GDMAE_CHECK_ARG(epi->bias && epi->c2 && c_dtype == 1 && N % 128 == 0 && epi->ldc2 % 8 == 0 && ((uintptr_t)epi->c2 & 15) == 0);
   TcgParams p = {};
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
@@ -604,6 +677,7 @@ extern "C" int gdmae_tc_gemm(int transa, int transb, int64_t M, int64_t N, int64
   if (epi) {
     p.bias = epi->bias; p.C2 = epi->c2; p.ldc2 = epi->ldc2; p.res = epi->res; p.gamma = epi->gamma; p.beta_ln = epi->beta_ln;
     p.eps = epi->eps; p.y32 = epi->y32; p.y16 = epi->y16; p.mean = epi->mean; p.rstd = epi->rstd;
+    p.h16 = epi->h16; p.ldh = epi->ldh; p.colsum = epi->colsum;
   }
   CUtensorMap ta, tb, tc;
   int rc;
@@ -625,6 +699,10 @@ extern "C" int gdmae_tc_gemm(int transa, int transb, int64_t M, int64_t N, int64
     if (BN == 256) return launch<256, EPI_PLAIN>(ta, tb, tc, p, st);
     if (BN == 128) return launch<128, EPI_PLAIN>(ta, tb, tc, p, st);
     return launch<64, EPI_PLAIN>(ta, tb, tc, p, st);
+  }
+  if (mode == EPI_GELU_BWD) {
+    if (BN == 256) return launch<256, EPI_GELU_BWD>(ta, tb, tc, p, st);
+    return launch<128, EPI_GELU_BWD>(ta, tb, tc, p, st);
   }
   if (mode == EPI_GELU) {
     if (BN == 256) return launch<256, EPI_GELU>(ta, tb, tc, p, st);

@@ -259,6 +259,201 @@ __global__ void __launch_bounds__(V_THREADS) vfe1_bwd_wgrad_kernel(const float* 
   }
 }
 
+// ---------------------------------------------------------------------------------- layer 1 through the input moments (r2)
+// y1 = W1 x is linear in x, so every point-sized reduction of layer 1 that does not involve a ReLU mask follows from the
+// first two moments of x alone:  S1 = sum_p x_p (K),  S2 = sum_p x_p x_p^T (K x K, upper triangle).
+//   forward   mean(y1_c) = w_c . S1 / n,   E[y1_c^2] = w_c^T S2 w_c / n                       (replaces vfe1_stats_kernel)
+//   backward  dW1 = sum_p dy1_p x_p^T with dy1 = a (g - dbeta/n - xhat dgamma/n), a = rstd gamma, g = dh1 [h1 > 0]:
+//             dW1[c, k] = a_c G[c, k] - a_c dbeta_c / n S1[k] - a_c dgamma_c / n rstd_c (w_c . S2[:, k] - mean_c S1[k])
+//             where only G = sum_p g_p x_p^T needs the data - and the same pass yields dbeta = sum g, dgamma = sum g xhat with
+//             xhat = (h1 - beta) / gamma wherever the ReLU is active (g = 0 elsewhere): ONE pass over h1, dh1, x replaces
+//             vfe1_bwd_stats_kernel + vfe1_bwd_wgrad_kernel, which each recomputed the K = 10 product per point and ran at
+//             0.06-0.09 of the HBM rate (r2 ncu: 309 + 385 us, issue-bound).
+// The moments are accumulated in fp32 per thread over a handful of rows and combined in fp64.
+template <int K>
+struct Mom {
+  static constexpr int NM = K + K * (K + 1) / 2;
+};
+
+template <int K>
+__global__ void __launch_bounds__(256) vfe1_moments_kernel(const float* __restrict__ x, long long Np, double* __restrict__ partial) {
+  constexpr int NM = Mom<K>::NM;
+  float acc[NM];
+#pragma unroll
+  for (int e = 0; e < NM; ++e) acc[e] = 0.f;
+  for (long long row = blockIdx.x * 256ll + threadIdx.x; row < Np; row += gridDim.x * 256ll) {
+    float v[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = __ldg(x + row * K + k);
+    int e = K;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      acc[i] += v[i];
+#pragma unroll
+      for (int j = i; j < K; ++j) {
+        acc[e] = fmaf(v[i], v[j], acc[e]);
+        ++e;
+      }
+    }
+  }
+  __shared__ double red[8][NM];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int e = 0; e < NM; ++e) {
+    double d = (double)acc[e];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    if (lane == 0) red[wid][e] = d;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < NM; e += 256) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w][e];
+    partial[(long long)blockIdx.x * NM + e] = t;
+  }
+}
+
+// moments[0:K] = S1, moments[K:] = upper triangle of S2 (row-major, j >= i); then BatchNorm statistics of y1 = W1 x
+template <int K>
+__global__ void __launch_bounds__(256) vfe1_moments_finalize_kernel(const double* __restrict__ partial, int nblocks, const float* __restrict__ W1,
+                                                                    double count, float eps, float momentum, double* __restrict__ moments,
+                                                                    float* __restrict__ mean, float* __restrict__ rstd,
+                                                                    float* __restrict__ running_mean, float* __restrict__ running_var) {
+  constexpr int NM = Mom<K>::NM;
+  __shared__ double mom[NM];
+  for (int e = threadIdx.x; e < NM; e += 256) {
+    double t = 0.0;
+    for (int b = 0; b < nblocks; ++b) t += partial[(long long)b * NM + e];
+    mom[e] = t;
+    moments[e] = t;
+  }
+  __syncthreads();
+  const int c = threadIdx.x;
+  if (c >= V_C1) return;
+  double m = 0.0, sq = 0.0;
+  int e = K;
+  for (int i = 0; i < K; ++i) {
+    const double wi = (double)W1[c * K + i];
+    m += wi * mom[i];
+    for (int j = i; j < K; ++j, ++e) sq += (i == j ? 1.0 : 2.0) * wi * (double)W1[c * K + j] * mom[e];
+  }
+  m /= count;
+  double var = sq / count - m * m;
+  if (var < 0.0) var = 0.0;
+  mean[c] = (float)m;
+  rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// one pass over h1, dh1, x: per CTA partial[block] = [ s (64) | q (64) | G (64 x K) ].  Thread = 4 channels of one row.
+template <typename T, int K>
+__global__ void __launch_bounds__(256) vfe1_bwd_pass_kernel(const float* __restrict__ x, const T* __restrict__ h1, const T* __restrict__ dh1,
+                                                            long long Np, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            float* __restrict__ partial) {
+  constexpr int W = 2 + K;                       // values per channel
+  const int cg = threadIdx.x & 15, rsub = threadIdx.x >> 4;
+  float ig[4], be[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float g = gamma[4 * cg + j];
+    ig[j] = fabsf(g) > 1e-20f ? 1.f / g : 0.f;
+    be[j] = beta[4 * cg + j];
+  }
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f}, G[4][K];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int k = 0; k < K; ++k) G[j][k] = 0.f;
+  for (long long row = blockIdx.x * 16ll + rsub; row < Np; row += gridDim.x * 16ll) {
+    const float4 h = VT<T>::load4(h1, row * (V_C1 / 4) + cg), d = VT<T>::load4(dh1, row * (V_C1 / 4) + cg);
+    float xv[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) xv[k] = __ldg(x + row * K + k);
+    const float hv[4] = {h.x, h.y, h.z, h.w}, dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float g = hv[j] > 0.f ? dv[j] : 0.f;
+      s[j] += g;
+      q[j] = fmaf(g, (hv[j] - be[j]) * ig[j], q[j]);
+#pragma unroll
+      for (int k = 0; k < K; ++k) G[j][k] = fmaf(g, xv[k], G[j][k]);
+    }
+  }
+  // the two rows of a warp meet by shuffle, the eight warps in shared memory
+  __shared__ float red[8][V_C1 * W];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    s[j] += __shfl_xor_sync(0xffffffffu, s[j], 16);
+    q[j] += __shfl_xor_sync(0xffffffffu, q[j], 16);
+#pragma unroll
+    for (int k = 0; k < K; ++k) G[j][k] += __shfl_xor_sync(0xffffffffu, G[j][k], 16);
+  }
+  if (lane < 16) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ch = 4 * cg + j;
+      red[wid][ch] = s[j];
+      red[wid][V_C1 + ch] = q[j];
+#pragma unroll
+      for (int k = 0; k < K; ++k) red[wid][2 * V_C1 + ch * K + k] = G[j][k];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < V_C1 * W; i += 256) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w][i];
+    partial[(long long)blockIdx.x * (V_C1 * W) + i] = t;
+  }
+}
+
+// sums the per-CTA partials (fp64) and finishes: tmp_dbeta1, tmp_dgamma1 and dW1 (closed form above)
+template <int K>
+__global__ void __launch_bounds__(1024) vfe1_bwd_finish_kernel(const float* __restrict__ partial, int nblocks, const double* __restrict__ moments,
+                                                               const float* __restrict__ W1, const float* __restrict__ mean,
+                                                               const float* __restrict__ rstd, const float* __restrict__ gamma, double count,
+                                                               int accumulate, float* __restrict__ dbeta, float* __restrict__ dgamma,
+                                                               float* __restrict__ dW1) {
+  constexpr int W = 2 + K, NV = V_C1 * W;
+  __shared__ double tot[NV];
+  for (int i = threadIdx.x; i < NV; i += 1024) {
+    double t = 0.0;
+    int b = 0;
+    for (; b + 8 <= nblocks; b += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(partial + (long long)(b + u) * NV + i);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t += (double)v[u];
+    }
+    for (; b < nblocks; ++b) t += (double)__ldg(partial + (long long)b * NV + i);
+    tot[i] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < V_C1) {
+    dbeta[threadIdx.x] = (float)tot[threadIdx.x];
+    dgamma[threadIdx.x] = (float)tot[V_C1 + threadIdx.x];
+  }
+  for (int i = threadIdx.x; i < V_C1 * K; i += 1024) {
+    const int c = i / K, k = i - c * K;
+    const double a = (double)rstd[c] * (double)gamma[c];
+    const double c1 = a * tot[c] / count, c2 = a * tot[V_C1 + c] / count;
+    // w_c . S2[:, k] with S2 stored as the upper triangle
+    double ws2 = 0.0;
+    for (int j = 0; j < K; ++j) {
+      const int lo = j < k ? j : k, hi = j < k ? k : j;
+      const int e = K + lo * K - lo * (lo - 1) / 2 + (hi - lo);
+      ws2 += (double)W1[c * K + j] * moments[e];
+    }
+    const double val = a * tot[2 * V_C1 + i] - c1 * moments[k] - c2 * (double)rstd[c] * (ws2 - (double)mean[c] * moments[k]);
+    dW1[i] = accumulate ? dW1[i] + (float)val : (float)val;
+  }
+}
+
 // ---------------------------------------------------------------------------------- layer 2
 // statistics of y2 (Np, C2): thread = 8 channels, 16 rows per CTA pass
 template <typename T>
@@ -463,8 +658,10 @@ static int vfe_check(const gdmae_vfe_mlp_args* a) {
 }
 
 extern "C" size_t gdmae_vfe_mlp_workspace_bytes(int K) {
-  size_t a = (size_t)BN_PART_BLOCKS * 2 * V_C2 * 4, b = (size_t)BN_PART_BLOCKS * V_C1 * (K > 0 ? K : 1) * 4;
-  return (a > b ? a : b) + 256;
+  size_t a = (size_t)BN_PART_BLOCKS * 2 * V_C2 * 4, b = (size_t)BN_PART_BLOCKS * V_C1 * ((K > 0 ? K : 1) + 2) * 4;
+  size_t c = (size_t)BN_PART_BLOCKS * 160 * 8;        // fp64 moment partials
+  a = a > b ? a : b;
+  return (a > c ? a : c) + 256;
 }
 
 #define VFE_CALL(expr)       \
@@ -486,11 +683,26 @@ extern "C" int gdmae_vfe_mlp_fwd(const gdmae_vfe_mlp_args* a) {
   }
   const long long ntile = (Np + V_TILE - 1) / V_TILE;
   const int g1 = (int)min((long long)BN_PART_BLOCKS, ntile);
-  vfe1_stats_kernel<<<g1, V_THREADS, 0, st>>>(a->x, Np, K, a->W1, partial);
-  GDMAE_LAUNCH_CHECK();
-  bn_finalize_kernel<<<gdmae_div_up(V_C1 * 32, 256), 256, 0, st>>>(partial, g1, V_C1, (double)Np, a->eps, a->momentum, a->mean1, a->rstd1,
-                                                                  a->running_mean1, a->running_var1);
-  GDMAE_LAUNCH_CHECK();
+  if ((K == 10 || K == 11) && a->moments) {
+    // BatchNorm-1 statistics from the first two moments of x (y1 = W1 x is linear): one light pass over x, kept for backward
+    const int gm = (int)min((long long)BN_PART_BLOCKS, (Np + 255) / 256);
+    if (K == 10) vfe1_moments_kernel<10><<<gm, 256, 0, st>>>(a->x, Np, (double*)a->ws);
+    else vfe1_moments_kernel<11><<<gm, 256, 0, st>>>(a->x, Np, (double*)a->ws);
+    GDMAE_LAUNCH_CHECK();
+    if (K == 10)
+      vfe1_moments_finalize_kernel<10><<<1, 256, 0, st>>>((const double*)a->ws, gm, a->W1, (double)Np, a->eps, a->momentum, a->moments, a->mean1,
+                                                          a->rstd1, a->running_mean1, a->running_var1);
+    else
+      vfe1_moments_finalize_kernel<11><<<1, 256, 0, st>>>((const double*)a->ws, gm, a->W1, (double)Np, a->eps, a->momentum, a->moments, a->mean1,
+                                                          a->rstd1, a->running_mean1, a->running_var1);
+    GDMAE_LAUNCH_CHECK();
+  } else {
+    vfe1_stats_kernel<<<g1, V_THREADS, 0, st>>>(a->x, Np, K, a->W1, partial);
+    GDMAE_LAUNCH_CHECK();
+    bn_finalize_kernel<<<gdmae_div_up(V_C1 * 32, 256), 256, 0, st>>>(partial, g1, V_C1, (double)Np, a->eps, a->momentum, a->mean1, a->rstd1,
+                                                                    a->running_mean1, a->running_var1);
+    GDMAE_LAUNCH_CHECK();
+  }
   const int g1a = (int)min((long long)GDMAE_NUM_SMS * 8, ntile);
   if (bf) vfe1_apply_kernel<vbf16><<<g1a, V_THREADS, 0, st>>>(a->x, Np, K, a->W1, a->mean1, a->rstd1, a->g1, a->b1, (vbf16*)a->h1);
   else vfe1_apply_kernel<float><<<g1a, V_THREADS, 0, st>>>(a->x, Np, K, a->W1, a->mean1, a->rstd1, a->g1, a->b1, (float*)a->h1);
@@ -555,23 +767,40 @@ extern "C" int gdmae_vfe_mlp_bwd(const gdmae_vfe_mlp_args* a) {
     VFE_CALL(gdmae_gemm(1, 0, V_C2, V_C1, Np, a->dy2, V_C2, a->h1, V_C1, a->gemm_mode, a->d_W2, V_C1, 0, acc ? 1.f : 0.f, a->stream));
     VFE_CALL(gdmae_gemm(0, 0, Np, V_C1, V_C2, a->dy2, V_C2, a->W2_g, V_C1, a->gemm_mode, a->dh1, V_C1, 0, 0.f, a->stream));
   }
-  // ---- BN1 + linear 1 from x
-  const long long ntile = (Np + V_TILE - 1) / V_TILE;
-  const int g1 = (int)min((long long)BN_PART_BLOCKS, ntile);
-  if (bf) vfe1_bwd_stats_kernel<vbf16><<<g1, V_THREADS, 0, st>>>(a->x, Np, K, a->W1, a->mean1, a->rstd1, a->g1, a->b1, (const vbf16*)a->dh1, partial);
-  else vfe1_bwd_stats_kernel<float><<<g1, V_THREADS, 0, st>>>(a->x, Np, K, a->W1, a->mean1, a->rstd1, a->g1, a->b1, (const float*)a->dh1, partial);
-  GDMAE_LAUNCH_CHECK();
-  bn_bwd_finalize_kernel<<<gdmae_div_up(V_C1, 32), 256, 0, st>>>(partial, g1, V_C1, nullptr, nullptr, a->tmp_dbeta1, a->tmp_dgamma1);
-  GDMAE_LAUNCH_CHECK();
-  if (!acc) GDMAE_CHECK_CUDA(cudaMemsetAsync(a->d_W1, 0, (size_t)V_C1 * K * 4, st));
-  const int gw = (int)min((long long)GDMAE_NUM_SMS * 4, ntile);
-  if (bf)
-    vfe1_bwd_wgrad_kernel<vbf16><<<gw, V_THREADS, 0, st>>>(a->x, Np, K, a->W1, a->mean1, a->rstd1, a->g1, a->b1, (const vbf16*)a->dh1,
-                                                           a->tmp_dbeta1, a->tmp_dgamma1, inv_n, a->d_W1);
-  else
-    vfe1_bwd_wgrad_kernel<float><<<gw, V_THREADS, 0, st>>>(a->x, Np, K, a->W1, a->mean1, a->rstd1, a->g1, a->b1, (const float*)a->dh1,
-                                                           a->tmp_dbeta1, a->tmp_dgamma1, inv_n, a->d_W1);
-  GDMAE_LAUNCH_CHECK();
+  // ---- BN1 + linear 1
+  if ((K == 10 || K == 11) && a->moments) {
+    // one pass over h1, dh1, x; everything else in closed form from the moments of x saved by the forward pass
+    const int gp = (int)min((long long)GDMAE_NUM_SMS * 3, (Np + 15) / 16);
+#define VFE_BWD_PASS(T, KK) vfe1_bwd_pass_kernel<T, KK><<<gp, 256, 0, st>>>(a->x, (const T*)a->h1, (const T*)a->dh1, Np, a->g1, a->b1, partial)
+    if (bf) { if (K == 10) VFE_BWD_PASS(vbf16, 10); else VFE_BWD_PASS(vbf16, 11); }
+    else { if (K == 10) VFE_BWD_PASS(float, 10); else VFE_BWD_PASS(float, 11); }
+#undef VFE_BWD_PASS
+    GDMAE_LAUNCH_CHECK();
+    if (K == 10)
+      vfe1_bwd_finish_kernel<10><<<1, 1024, 0, st>>>(partial, gp, a->moments, a->W1, a->mean1, a->rstd1, a->g1, (double)Np, acc, a->tmp_dbeta1,
+                                                     a->tmp_dgamma1, a->d_W1);
+    else
+      vfe1_bwd_finish_kernel<11><<<1, 1024, 0, st>>>(partial, gp, a->moments, a->W1, a->mean1, a->rstd1, a->g1, (double)Np, acc, a->tmp_dbeta1,
+                                                     a->tmp_dgamma1, a->d_W1);
+    GDMAE_LAUNCH_CHECK();
+  } else {
+    const long long ntile = (Np + V_TILE - 1) / V_TILE;
+    const int g1 = (int)min((long long)BN_PART_BLOCKS, ntile);
+    if (bf) vfe1_bwd_stats_kernel<vbf16><<<g1, V_THREADS, 0, st>>>(a->x, Np, K, a->W1, a->mean1, a->rstd1, a->g1, a->b1, (const vbf16*)a->dh1, partial);
+    else vfe1_bwd_stats_kernel<float><<<g1, V_THREADS, 0, st>>>(a->x, Np, K, a->W1, a->mean1, a->rstd1, a->g1, a->b1, (const float*)a->dh1, partial);
+    GDMAE_LAUNCH_CHECK();
+    bn_bwd_finalize_kernel<<<gdmae_div_up(V_C1, 32), 256, 0, st>>>(partial, g1, V_C1, nullptr, nullptr, a->tmp_dbeta1, a->tmp_dgamma1);
+    GDMAE_LAUNCH_CHECK();
+    if (!acc) GDMAE_CHECK_CUDA(cudaMemsetAsync(a->d_W1, 0, (size_t)V_C1 * K * 4, st));
+    const int gw = (int)min((long long)GDMAE_NUM_SMS * 4, ntile);
+    if (bf)
+      vfe1_bwd_wgrad_kernel<vbf16><<<gw, V_THREADS, 0, st>>>(a->x, Np, K, a->W1, a->mean1, a->rstd1, a->g1, a->b1, (const vbf16*)a->dh1,
+                                                             a->tmp_dbeta1, a->tmp_dgamma1, inv_n, a->d_W1);
+    else
+      vfe1_bwd_wgrad_kernel<float><<<gw, V_THREADS, 0, st>>>(a->x, Np, K, a->W1, a->mean1, a->rstd1, a->g1, a->b1, (const float*)a->dh1,
+                                                             a->tmp_dbeta1, a->tmp_dgamma1, inv_n, a->d_W1);
+    GDMAE_LAUNCH_CHECK();
+  }
   vfe_bn_grads_kernel<<<1, 256, 0, st>>>(a->tmp_dbeta1, a->tmp_dgamma1, a->tmp_dbeta2, a->tmp_dgamma2, a->d_b1, a->d_g1, a->d_b2, a->d_g2, acc);
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;

@@ -333,7 +333,7 @@ def encoder_layer(layer, x, pos_table, table):
 
 _VFE_PTRS = ["x", "seg_offsets", "seg_points", "W1", "g1", "b1", "g2", "b2", "W2_g", "running_mean1", "running_var1", "running_mean2",
              "running_var2", "h1", "y2", "mean1", "rstd1", "mean2", "rstd2", "out", "argmax", "dout", "dy2", "dh1", "tmp_dbeta1",
-             "tmp_dgamma1", "tmp_dbeta2", "tmp_dgamma2", "d_W1", "d_g1", "d_b1", "d_W2", "d_g2", "d_b2", "ws"]
+             "tmp_dgamma1", "tmp_dbeta2", "tmp_dgamma2", "d_W1", "d_g1", "d_b1", "d_W2", "d_g2", "d_b2", "moments", "ws"]
 
 
 class VfeMlpArgs(ctypes.Structure):
@@ -360,7 +360,7 @@ class VfeMlpFunction(torch.autograd.Function):
         W2g = _gw(W2)
         h1 = torch.empty((Np, 64), dtype=opdt, device=dev)
         y2 = torch.empty((Np, 128), dtype=opdt, device=dev)
-        stats = torch.empty((4 * 128 + 4 * 128,), dtype=F32, device=dev)      # mean1 rstd1 mean2 rstd2 | 4 scratch rows
+        stats = torch.empty((4 * 128 + 4 * 128 + 2 * 160,), dtype=F32, device=dev)   # mean1 rstd1 mean2 rstd2 | 4 scratch rows | moments (fp64)
         out = torch.empty((M, 128), dtype=F32, device=dev)
         arg = torch.empty((M, 128), dtype=torch.uint8, device=dev)   # position inside the pillar's segment (csrc/vfe_mlp.cu)
         for name, t in (("x", x), ("seg_offsets", seg_offsets), ("seg_points", seg_points), ("W1", W1), ("g1", g1), ("b1", b1),
@@ -370,6 +370,7 @@ class VfeMlpFunction(torch.autograd.Function):
         sb = stats.data_ptr()
         for i, name in enumerate(("mean1", "rstd1", "mean2", "rstd2", "tmp_dbeta1", "tmp_dgamma1", "tmp_dbeta2", "tmp_dgamma2")):
             setattr(A, name, sb + 4 * 128 * i)
+        A.moments = sb + 4 * 128 * 8
         lib = L.lib()
         ws = L.workspace(lib.gdmae_vfe_mlp_workspace_bytes(K), dev)
         A.ws, A.ws_bytes, A.stream = ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream
@@ -524,7 +525,8 @@ def batchnorm_relu(bn, y, training, relu=True, count=None):
 class TcEpilogue(ctypes.Structure):
     """mirror of gdmae_tc_epilogue (include/gdmae_b200.h)"""
     _fields_ = [("mode", ctypes.c_int), ("bias", _VP), ("c2", _VP), ("ldc2", ctypes.c_int64), ("res", _VP), ("gamma", _VP),
-                ("beta_ln", _VP), ("eps", ctypes.c_float), ("y32", _VP), ("y16", _VP), ("mean", _VP), ("rstd", _VP)]
+                ("beta_ln", _VP), ("eps", ctypes.c_float), ("y32", _VP), ("y16", _VP), ("mean", _VP), ("rstd", _VP),
+                ("h16", _VP), ("ldh", ctypes.c_int64), ("colsum", _VP)]
 
 
 def tc_gemm(a, b, out=None, beta=0.0, out_dtype=F32, split_k=False, epilogue=None):

@@ -120,6 +120,11 @@ class MAETrainer:
             self.flat_buffers[off:off + k].copy_(b.data.reshape(-1))
             b.data = self.flat_buffers[off:off + k].view_as(b)
             off += pad(k)
+        # the host may enqueue at most `max_steps_in_flight` iterations ahead of the device: without a bound a loop that never
+        # reads the loss queues dozens of steps, and the caching allocator - whose blocks shared with the index side stream
+        # are only reusable once their recorded events have passed - falls back to cudaMalloc in the middle of the run
+        self.max_steps_in_flight = 2
+        self._inflight = []
         self._comm_stream = None
         self._early_work = None
         self._late_works = []
@@ -322,4 +327,10 @@ class MAETrainer:
             self.model.prefetch_index(next_batch, next_ready_event)
         if hasattr(self.model, 'update_global_step'):
             self.model.update_global_step()
+        if self.flat_grads.is_cuda and self.max_steps_in_flight:
+            ev = torch.cuda.Event()
+            ev.record()
+            self._inflight.append(ev)
+            if len(self._inflight) > self.max_steps_in_flight:
+                self._inflight.pop(0).synchronize()
         return loss.detach()

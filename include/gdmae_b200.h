@@ -217,6 +217,7 @@ typedef struct gdmae_vfe_mlp_args {
   void* dh1;              /* (Np,64) op scratch */
   float *tmp_dbeta1, *tmp_dgamma1, *tmp_dbeta2, *tmp_dgamma2;   /* (64),(64),(128),(128) scratch */
   float *d_W1, *d_g1, *d_b1, *d_W2, *d_g2, *d_b2;
+  double* moments;        /* (K + K(K+1)/2 <= 152) first / second moments of x: written by forward, read by backward */
   void* ws;               /* gdmae_vfe_mlp_workspace_bytes(K) */
   size_t ws_bytes;
   void* stream;
@@ -295,6 +296,8 @@ int gdmae_gemm(int transa, int transb, int64_t M, int64_t N, int64_t K, const vo
  *   mode 1  C = acc (bf16, kept for backward), c2 = gelu(acc + bias) (bf16)          - linear1 + GELU, sst_basic_block.py:81
  *   mode 2  z = acc + bias + res; y32/y16 = LayerNorm(z) * gamma + beta_ln, mean, rstd; N in {128, 256}; C (nullable, bf16) = acc
  *                                                                                     - out_proj / linear2 + residual + norm, :78-83
+ *   mode 3  acc = gradient w.r.t. gelu(h + bias): C = acc * gelu'(h16 + bias) (bf16) and colsum (N, fp32) += its column sums
+ *                                                                                     - backward of linear1's bias + GELU
  * replaces F.linear of cosine_msa.py:57-62,431 / sst_basic_block.py:77-84 and the spconv / deblock / VFE GEMMs. */
 typedef struct gdmae_tc_epilogue {
   int mode;
@@ -309,6 +312,9 @@ typedef struct gdmae_tc_epilogue {
   void* y16;                 /* mode 2: (M, N) bf16, nullable */
   float* mean;               /* mode 2: (M) */
   float* rstd;               /* mode 2: (M) */
+  const void* h16;           /* mode 3: (M, ldh) bf16 pre-activation saved by mode 1 */
+  int64_t ldh;
+  float* colsum;             /* mode 3: (N) fp32, accumulated into */
 } gdmae_tc_epilogue;
 int gdmae_tc_gemm(int transa, int transb, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
                   int64_t ldb, void* C, int64_t ldc, int c_dtype, float beta, int split_k_atomic,
