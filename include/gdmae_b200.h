@@ -425,6 +425,18 @@ int gdmae_center_assign_targets(const float* gt_boxes, int B, int M, const int* 
                                 float* target_boxes, float* iou_boxes, int64_t* inds, int64_t* mask, void* stream);
 int gdmae_center_focal_loss(const float* logits, const float* gt, int64_t n, float* grad_raw, double* sums3, void* stream);
 
+/* ---- (modulated) deformable convolution sampling kernels (csrc/dcn.cu) -------------------------------
+ * The building blocks behind the reference's five pybind entry points (pcdet/ops/dcn/src/deform_conv_cuda.cpp:687-701:
+ * deform_conv_forward_cuda, deform_conv_backward_input_cuda, deform_conv_backward_parameters_cuda,
+ * modulated_deform_conv_cuda_forward, modulated_deform_conv_cuda_backward), which gd-mae_b200/pcdet/ops/dcn/deform_conv.py
+ * rebuilds under the same names on these launchers plus library GEMMs.  Kernels replaced: deform_conv_cuda_kernel.cu:84-470
+ * and 570-866.  input (B,C,H,W), offset (B, dg*2*kh*kw, Ho, Wo), mask (B, dg*kh*kw, Ho, Wo) or NULL (= plain deformable conv),
+ * columns (B, C*kh*kw, Ho*Wo); all fp32.  geom: HOST int[13] {B,C,H,W,kh,kw,pad_h,pad_w,stride_h,stride_w,dil_h,dil_w,dg}. */
+int gdmae_deform_im2col(const float* input, const float* offset, const float* mask, const int* geom, float* columns, void* stream);
+int gdmae_deform_col2im(const float* grad_columns, const float* offset, const float* mask, const int* geom, float* grad_input, void* stream);
+int gdmae_deform_col2im_coord(const float* grad_columns, const float* input, const float* offset, const float* mask, const int* geom,
+                              float* grad_offset, float* grad_mask, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

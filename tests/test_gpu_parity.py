@@ -1125,3 +1125,38 @@ def test_vfe_node_with_pillars_beyond_byte_argmax(G):
     for k, v in leaves.items():
         g = dict(model.named_parameters())[k].grad
         assert rel(g, v.grad) < 2e-3, (k, rel(g, v.grad))
+
+
+# ------------------------------------------------------------------------------ dcn
+@pytest.mark.parametrize("modulated,groups,dg,stride,dil", [(False, 1, 1, 1, 1), (True, 1, 1, 1, 1), (True, 2, 2, 2, 1), (False, 1, 4, 1, 2)])
+def test_deform_conv_matches_oracle(G, modulated, groups, dg, stride, dil):
+    """pcdet.ops.dcn (deform_conv / modulated_deform_conv through the reference-named deform_conv_cuda entry points) against the
+    torch-CPU oracle: output and the gradients w.r.t. input, offsets, masks, weight, bias (autograd on the oracle side).
+    Offsets reach outside the plane, so the zero-padding rules of the sampler are exercised.  fp32, 1e-4 of the range
+    (the GEMMs run with TF32 off in this test session)."""
+    from gd_mae_b200.pcdet.ops.dcn import deform_conv, modulated_deform_conv
+    from oracle import dcn_oracle as DO
+    g = torch.Generator().manual_seed(3 + groups + dg)
+    B, C, H, W, Cout, k = 2, 8, 11, 13, 12, 3
+    pad = dil
+    x = torch.randn(B, C, H, W, generator=g)
+    Ho, Wo = (H + 2 * pad - (dil * (k - 1) + 1)) // stride + 1, (W + 2 * pad - (dil * (k - 1) + 1)) // stride + 1
+    offset = torch.randn(B, dg * 2 * k * k, Ho, Wo, generator=g) * 1.7
+    mask = torch.rand(B, dg * k * k, Ho, Wo, generator=g) if modulated else None
+    weight = torch.randn(Cout, C // groups, k, k, generator=g) * 0.2
+    bias = torch.randn(Cout, generator=g) if modulated else None
+    go = torch.randn(B, Cout, Ho, Wo, generator=g)
+    leaves = [t.clone().requires_grad_(True) for t in (x, offset, weight)] + ([mask.clone().requires_grad_(True), bias.clone().requires_grad_(True)] if modulated else [])
+    ref = DO.deform_conv2d(leaves[0], leaves[1], leaves[3] if modulated else None, leaves[2], leaves[4] if modulated else None, stride, pad, dil, groups, dg)
+    ref.backward(go)
+    cl = [t.clone().cuda().requires_grad_(True) for t in (x, offset, weight)] + ([mask.clone().cuda().requires_grad_(True), bias.clone().cuda().requires_grad_(True)] if modulated else [])
+    if modulated:
+        out = modulated_deform_conv(cl[0], cl[1], cl[3], cl[2], cl[4], stride, pad, dil, groups, dg)
+    else:
+        out = deform_conv(cl[0], cl[1], cl[2], stride, pad, dil, groups, dg)
+    out.backward(go.cuda())
+    assert rel(out, ref) < 1e-4
+    for name, a, b in zip(("input", "offset", "weight", "mask", "bias"), cl, leaves):
+        assert rel(a.grad, b.grad) < 2e-4, (name, rel(a.grad, b.grad))
+    with pytest.raises(NotImplementedError):
+        deform_conv(x, offset, weight, stride, pad, dil, groups, dg)               # CPU tensors: like the reference, no CPU path
