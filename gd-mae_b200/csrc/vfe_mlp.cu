@@ -552,6 +552,52 @@ __global__ void __launch_bounds__(256) vfe2_apply_max_kernel(const T* __restrict
   }
 }
 
+// bf16 rows in pillar order (the benched configuration), r2: relu(a (y - mu) + beta) is monotone in y for a fixed channel, so
+// the per-pillar maximum follows from the pillar's largest y (a >= 0) or smallest y (a < 0).  The pass therefore only keeps a
+// running max and min of the RAW bf16 values with packed bf16x2 compares (exact: no arithmetic on them) - 4 instructions per row
+// and lane instead of ~28 for convert + normalise + ReLU + max + arg-max per element (r2 ncu: the pass was issue-bound at 53 %
+// issue-active, 3.4 TB/s) - and applies BatchNorm + ReLU once per pillar.  No arg-max is stored: the backward pass recognises
+// the arg-max row as the first row whose activation equals the stored maximum (same arithmetic, bit-equal).
+__global__ void __launch_bounds__(256) vfe2_apply_max_packed_kernel(const vbf16* __restrict__ y, const int* __restrict__ seg_off, int M,
+                                                                    const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                    float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const float4 mu = __ldg(reinterpret_cast<const float4*>(mean) + lane), rs = __ldg(reinterpret_cast<const float4*>(rstd) + lane);
+  const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + lane), be = __ldg(reinterpret_cast<const float4*>(beta) + lane);
+  const float4 a = make_float4(rs.x * ga.x, rs.y * ga.y, rs.z * ga.z, rs.w * ga.w);
+  const uint2* rows = reinterpret_cast<const uint2*>(y);
+  const int stride = (gridDim.x * blockDim.x) >> 5;
+  int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int s = m < M ? __ldg(seg_off + m) : 0, e = m < M ? __ldg(seg_off + m + 1) : 0;
+  while (m < M) {
+    const int mn = m + stride;
+    const int sn = mn < M ? __ldg(seg_off + mn) : 0, en = mn < M ? __ldg(seg_off + mn + 1) : 0;
+    uint2 first = __ldg(rows + (long long)s * (V_C2 / 4) + lane);
+    __nv_bfloat162 mx0 = *reinterpret_cast<__nv_bfloat162*>(&first.x), mx1 = *reinterpret_cast<__nv_bfloat162*>(&first.y);
+    __nv_bfloat162 mi0 = mx0, mi1 = mx1;
+    for (int k = s + 1; k < e; k += 8) {
+      uint2 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = k + u < e ? __ldg(rows + (long long)(k + u) * (V_C2 / 4) + lane) : first;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const __nv_bfloat162 p0 = *reinterpret_cast<__nv_bfloat162*>(&v[u].x), p1 = *reinterpret_cast<__nv_bfloat162*>(&v[u].y);
+        mx0 = __hmax2(mx0, p0); mx1 = __hmax2(mx1, p1);
+        mi0 = __hmin2(mi0, p0); mi1 = __hmin2(mi1, p1);
+      }
+    }
+    const float2 hx0 = __bfloat1622float2(mx0), hx1 = __bfloat1622float2(mx1), lo0 = __bfloat1622float2(mi0), lo1 = __bfloat1622float2(mi1);
+    float4 best;
+    best.x = fmaxf(fmaf((a.x >= 0.f ? hx0.x : lo0.x) - mu.x, a.x, be.x), 0.f);
+    best.y = fmaxf(fmaf((a.y >= 0.f ? hx0.y : lo0.y) - mu.y, a.y, be.y), 0.f);
+    best.z = fmaxf(fmaf((a.z >= 0.f ? hx1.x : lo1.x) - mu.z, a.z, be.z), 0.f);
+    best.w = fmaxf(fmaf((a.w >= 0.f ? hx1.y : lo1.y) - mu.w, a.w, be.w), 0.f);
+    reinterpret_cast<float4*>(out)[(long long)m * (V_C2 / 4) + lane] = best;
+    m = mn; s = sn; e = en;
+  }
+}
+
 // backward sums of BN2 over the argmax entries only (every other element of d h2 is zero).  xhat at the argmax is
 // recovered from the stored maximum itself: out = xhat * gamma + beta wherever out > 0 (no gather of y2).
 __global__ void __launch_bounds__(256) vfe2_bwd_stats_kernel(int M, const float* __restrict__ out, const float* __restrict__ dout,
@@ -582,7 +628,7 @@ __global__ void __launch_bounds__(256) vfe2_bwd_stats_kernel(int M, const float*
 }
 
 // dy2[p] = gamma rstd (g[p] - dbeta/n - xhat[p] dgamma/n), g[p, c] = dout[m, c] iff p is pillar m's argmax for c
-template <typename T, bool SORTED>
+template <typename T, bool SORTED, bool BYEQ>
 __global__ void __launch_bounds__(256) vfe2_bwd_apply_kernel(const T* __restrict__ y, const int* __restrict__ seg_off,
                                                              const int* __restrict__ seg_pts, int M, const float* __restrict__ out,
                                                              const unsigned char* __restrict__ arg, const float* __restrict__ dout,
@@ -603,9 +649,12 @@ __global__ void __launch_bounds__(256) vfe2_bwd_apply_kernel(const T* __restrict
     // against 259 us, and a four-rows-in-flight body 259 us against this loop's ~240 us: kept simple)
     const float4 o = __ldg(reinterpret_cast<const float4*>(out) + (long long)m * (V_C2 / 4) + lane);
     float4 g = __ldg(reinterpret_cast<const float4*>(dout) + (long long)m * (V_C2 / 4) + lane);
-    const uchar4 a8 = __ldg(reinterpret_cast<const uchar4*>(arg) + (long long)m * (V_C2 / 4) + lane);
-    int4 ai = make_int4(a8.x, a8.y, a8.z, a8.w);          // position of the arg-max row inside the pillar's segment
-    if (e - s > 255) {
+    int4 ai = make_int4(-1, -1, -1, -1);                   // position of the arg-max row inside the pillar's segment
+    if (!BYEQ) {
+      const uchar4 a8 = __ldg(reinterpret_cast<const uchar4*>(arg) + (long long)m * (V_C2 / 4) + lane);
+      ai = make_int4(a8.x, a8.y, a8.z, a8.w);
+    }
+    if (!BYEQ && e - s > 255) {
       // a byte cannot address this pillar's rows: recompute the arg-max (first maximum of relu(bn(y)), as the forward did)
       float4 best = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int k = s; k < e; ++k) {
@@ -625,6 +674,14 @@ __global__ void __launch_bounds__(256) vfe2_bwd_apply_kernel(const T* __restrict
       const int pnt = SORTED ? k : seg_pts[k];
       const int off = k - s;
       const float4 v = VT<T>::load4(y, (long long)pnt * (V_C2 / 4) + lane);
+      if (BYEQ) {
+        // the arg-max row is the first one whose activation equals the stored maximum (bit-equal: same arithmetic as forward)
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta) + lane);
+        if (ai.x < 0 && fmaxf(fmaf(v.x - mu.x, a0.x, b4.x), 0.f) == o.x) ai.x = off;
+        if (ai.y < 0 && fmaxf(fmaf(v.y - mu.y, a0.y, b4.y), 0.f) == o.y) ai.y = off;
+        if (ai.z < 0 && fmaxf(fmaf(v.z - mu.z, a0.z, b4.z), 0.f) == o.z) ai.z = off;
+        if (ai.w < 0 && fmaxf(fmaf(v.w - mu.w, a0.w, b4.w), 0.f) == o.w) ai.w = off;
+      }
       float4 r;
       r.x = a0.x * (ai.x == off ? g.x : 0.f) - a1.x - (v.x - mu.x) * rs.x * a2.x;
       r.y = a0.y * (ai.y == off ? g.y : 0.f) - a1.y - (v.y - mu.y) * rs.y * a2.y;
@@ -724,8 +781,11 @@ extern "C" int gdmae_vfe_mlp_fwd(const gdmae_vfe_mlp_args* a) {
   vfe2_apply_max_kernel<T, S><<<g3, 256, 0, st>>>((const T*)a->y2, a->seg_offsets, a->seg_points, (int)a->M, a->mean2, a->rstd2, a->g2, \
                                                   a->b2, a->out, a->argmax)
   const bool sorted = a->seg_points == nullptr;      // point rows already in pillar order
-  if (bf) { if (sorted) VFE_APPLY_MAX(vbf16, true); else VFE_APPLY_MAX(vbf16, false); }
-  else { if (sorted) VFE_APPLY_MAX(float, true); else VFE_APPLY_MAX(float, false); }
+  if (sorted && bf)      // no arg-max array in this configuration: the backward pass finds the row by equality
+    vfe2_apply_max_packed_kernel<<<g3, 256, 0, st>>>((const vbf16*)a->y2, a->seg_offsets, (int)a->M, a->mean2, a->rstd2, a->g2, a->b2, a->out);
+  else if (sorted) VFE_APPLY_MAX(float, true);
+  else if (bf) VFE_APPLY_MAX(vbf16, false);
+  else VFE_APPLY_MAX(float, false);
 #undef VFE_APPLY_MAX
   GDMAE_LAUNCH_CHECK();
   // pillar scatter-max, algorithmic bytes: point rows in, segment index in, pillar rows out
@@ -752,7 +812,7 @@ extern "C" int gdmae_vfe_mlp_bwd(const gdmae_vfe_mlp_args* a) {
   GDMAE_LAUNCH_CHECK();
   const int g3 = gdmae_grid((long long)M * 32, 256, 16);
 #define VFE_BWD_APPLY(T, S)                                                                                                        \
-  vfe2_bwd_apply_kernel<T, S><<<g3, 256, 0, st>>>((const T*)a->y2, a->seg_offsets, a->seg_points, M, a->out, a->argmax, a->dout, a->mean2, \
+  vfe2_bwd_apply_kernel<T, S, (S && sizeof(T) == 2)><<<g3, 256, 0, st>>>((const T*)a->y2, a->seg_offsets, a->seg_points, M, a->out, a->argmax, a->dout, a->mean2, \
                                                   a->rstd2, a->g2, a->b2, a->tmp_dbeta2, a->tmp_dgamma2, inv_n, (T*)a->dy2)
   const bool sorted = a->seg_points == nullptr;
   if (bf) { if (sorted) VFE_BWD_APPLY(vbf16, true); else VFE_BWD_APPLY(vbf16, false); }
