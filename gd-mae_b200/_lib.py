@@ -41,7 +41,7 @@ def lib():
             fn = getattr(L, name)
             if name.endswith("_bytes"):
                 fn.restype = ctypes.c_size_t
-            elif name == "gdmae_launch_count":
+            elif name == "gdmae_launch_count" or name.endswith("_offset"):
                 fn.restype = ctypes.c_int64
             elif name != "gdmae_last_error":
                 fn.restype = ctypes.c_int

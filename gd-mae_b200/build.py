@@ -24,7 +24,7 @@ def _stale(target, sources):
 def build(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
-    hdrs = sorted(glob.glob(os.path.join(CSRC, "*.cuh")))
+    hdrs = sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + sorted(glob.glob(os.path.join(os.path.dirname(HERE), "include", "*.h")))
     objs = []
 
     def compile_one(src):

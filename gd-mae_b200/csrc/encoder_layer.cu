@@ -104,14 +104,22 @@ extern "C" int gdmae_encoder_layer_fwd(const gdmae_encoder_layer_args* a) {
     }
   }
   // in-projection without biases; positional term + q/k biases go through the 64-row LUT, the v bias to the output
-  const int tc = a->sra_tensor_cores ? 1 : 0;      // bf16 q/k/v straight from the GEMM epilogue for the tensor-core kernels
-  EL_CALL(el_gemm(a, 0, 1, N, 3 * d, d, xg, d, a->w_in_g, d, a->qkv, 3 * d, tc, 0.f));
+  const int tc = a->sra_tensor_cores ? 1 : 0;
   pos_lut_kernel<<<gdmae_div_up(64ll * 2 * d * 32, 256), 256, 0, st>>>(a->pos_table, a->w_in, a->b_in, d, a->lut);
   GDMAE_LAUNCH_CHECK();
+  if (tc) {
+    // tensor-core kernels: the GEMM epilogue adds the LUT row, normalises q and k per head and writes q^, k^, v (bf16) in
+    // CSR (window) order - the attention kernel then fetches whole bins of windows with TMA boxes
+    gdmae_tc_epilogue e0 = {};
+    e0.mode = 4; e0.tok_info = a->bin_units + gdmae_sra_tok_info_offset(N); e0.lut = a->lut; e0.tau = a->tau; e0.tau_min = a->tau_min;
+    e0.lrr = a->lse;
+    EL_CALL(gdmae_tc_gemm(0, 1, N, 3 * d, d, xg, d, a->w_in_g, d, a->qkv, 3 * d, 1, 0.f, 0, &e0, a->stream));
+  } else {
+    EL_CALL(el_gemm(a, 0, 1, N, 3 * d, d, xg, d, a->w_in_g, d, a->qkv, 3 * d, 0, 0.f));
+  }
   GdmaeSpan span(st);
   if (tc)
-    EL_CALL(gdmae_sra_attention_fwd_tc(a->qkv, a->lut, a->row_info, a->bin_units, N, d, a->nhead, a->tau, a->tau_min, a->b_in + 2 * d, bf, a->o,
-                                       a->lse, a->stream));
+    EL_CALL(gdmae_sra_fwd_win(a->qkv, a->bin_units, N, d, a->b_in + 2 * d, bf, a->o, a->lse, 1, a->stream));
   else
     EL_CALL(gdmae_sra_attention_fwd((const float*)a->qkv, a->lut, a->row_info, N, d, a->nhead, a->tau, a->tau_min, a->b_in + 2 * d, bf, a->o,
                                     a->lse, a->stream));
@@ -204,12 +212,18 @@ extern "C" int gdmae_encoder_layer_bwd(const gdmae_encoder_layer_args* a) {
   const void* dz1_op = bf ? (const void*)dz1g : (const void*)dz1;
   EL_CALL(el_gemm(a, 1, 0, d, d, N, dz1_op, d, a->o, d, a->d_w_o, d, 0, wbeta));
   const int tc = a->sra_tensor_cores ? 1 : 0;
-  EL_CALL(el_gemm(a, 0, 0, N, d, d, dz1_op, d, a->w_o_g, d, dout, d, tc, 0.f));
+  if (tc) {
+    // dO = dz1 Wo leaves the GEMM as bf16 rows in CSR (window) order: the fourth tensor of the window-major array
+    gdmae_tc_epilogue e5 = {};
+    e5.mode = 5; e5.tok_info = a->bin_units + gdmae_sra_tok_info_offset(N); e5.plane0 = 3 * (d / 64);
+    EL_CALL(gdmae_tc_gemm(0, 0, N, d, d, dz1_op, d, a->w_o_g, d, a->qkv, d, 1, 0.f, 0, &e5, a->stream));
+  } else {
+    EL_CALL(el_gemm(a, 0, 0, N, d, d, dz1_op, d, a->w_o_g, d, dout, d, 0, 0.f));
+  }
   GDMAE_CHECK_CUDA(cudaMemsetAsync(dtau_sum, 0, sizeof(double), st));
   GdmaeSpan span(st);
   if (tc)
-    EL_CALL(gdmae_sra_attention_bwd_tc(a->qkv, a->lut, a->row_info, a->bin_units, N, d, a->nhead, a->tau, a->tau_min, a->lse, dout, dqkv, dtau_sum,
-                                       a->stream));
+    EL_CALL(gdmae_sra_bwd_win(a->qkv, a->lse, a->bin_units, N, d, a->tau, a->tau_min, dqkv, dtau_sum, a->stream));
   else
     EL_CALL(gdmae_sra_attention_bwd((const float*)a->qkv, a->lut, a->row_info, N, d, a->nhead, a->tau, a->tau_min, a->b_in + 2 * d, bf,
                                     a->o, a->lse, dout, dqkv, dtau_sum, work, a->stream));

@@ -1,45 +1,52 @@
-// Sparse Regional Attention on the tensor cores: bf16 mma.sync m16n8k16 with fp32 accumulation,
-// operands fetched with ldmatrix - the kernel of the bf16 configuration.
+// Sparse Regional Attention on the tensor cores: bf16 mma.sync m16n8k16 with fp32 accumulation, operands fetched with
+// ldmatrix from 128B-swizzled shared-memory tiles that TMA fills - the kernels of the bf16 configuration.
 //
-// Same operator and data layout as sra_attention.cu (reference: cosine_msa.py:114-176,
-// sst_basic_block.py:22-54, sst_utils.py:107-181): flat tokens, CSR windows, 64-row positional
-// LUT, nothing padded in HBM; here q/k/v arrive as bf16 (the in-projection GEMM writes them so).
-// The fp32 SIMT kernel is the parity path.  Its r1 profile: 107 M warp instructions per launch for
-// 16 M query-key-head triples, issue bound; every CTA pays the row_info -> q/k/v -> LUT dependent
-// load chain before any math.  This kernel removes both:
-//   * persistent, one CTA per SM, each owning a 64-channel slice (2 heads of 32 or 4 heads of 16) and
-//     walking bins of 64 CSR rows (the windows that START in the bin, <= 127 rows).  The slice of the
-//     positional LUT lives in shared memory (bf16) for the whole kernel;
-//   * warp specialised and decoupled: "stager" warps copy the rows of a bin with cp.async (three stage buffers) and
-//     normalise q and k in place, "math" warps run the MMAs; the two roles meet only through mbarriers (bin staged /
-//     bin consumed) - no CTA barrier inside the bin loop, a math warp that runs out of work in bin j moves on to bin
-//     j+1 on its own.  try_wait carries a suspend hint: a polling wait was measured to burn a third of the issue slots;
+// Same operator as sra_attention.cu (reference: cosine_msa.py:114-176, sst_basic_block.py:22-54, sst_utils.py:107-181):
+// flat tokens, CSR windows, 64-row positional LUT, nothing padded in HBM.  The fp32 SIMT kernels are the parity path.
+//
+// r2 layout ("window-major"): the in-projection GEMM's epilogue (tc_gemm.cu, mode 4) adds the positional LUT row,
+// L2-normalises q and k per head in fp32, folds log2(e)/tau into q and writes q^, k^, v as bf16 ROWS IN CSR (WINDOW)
+// ORDER, one plane per (tensor, 64-channel slice):  qkvw[(part * d/64 + slice)][row][64].  The rows of a bin are then
+// one contiguous rectangle per plane, so a bin is fetched with a handful of cp.async.bulk.tensor (TMA) boxes of 16 rows x
+// 128 bytes issued by ONE thread - the r1 kernel gathered 128-byte row pieces with 1536 cp.async instructions per bin and
+// re-did the normalisation in every launch (forward, and again in backward); a copy-only build of it ran at 1.9 TB/s.
+//   * persistent, one CTA per SM, each owning a 64-channel slice (2 heads of 32 or 4 heads of 16) and walking bins of 64
+//     CSR rows (the windows that START in the bin, <= 127 rows);
+//   * warp 0 is the producer: per bin one mbarrier.expect_tx, bulk copies of the row records / work units (/ per-row
+//     scalars in the backward) and the TMA boxes of the tiles; the other 15 warps run the MMAs.  The two roles meet only
+//     through mbarriers (bin landed / bin consumed) - no CTA barrier inside the bin loop;
+//   * SWIZZLE_128B tiles (row r, 16-byte chunk c at r * 128 + ((c ^ (r & 7)) << 4)): every ldmatrix phase touches the 32
+//     banks once, and the tile needs no padding;
 //   * the work units of every bin are built ONCE per window table (gdmae_sra_bin_units: a table serves two layers,
 //     forward and backward) and arrive with the bin's row records; (unit, head) entries are handed out through a
 //     shared-memory counter that arrives zeroed with them;
-//   * one pass over q and k only: + LUT, L2-normalise per head, fold log2(e)/tau into q, back to
-//     bf16 in place.  v is used as it arrives;
-//   * work units are PACKED: a unit is either a run of whole small windows totalling <= 16 rows, or a
-//     16-row chunk of a large window; per-row key bounds (from row_info) give the block-diagonal
-//     mask.  A 3-token window therefore costs 3/16 of an MMA tile instead of a whole one;
+//   * work units are PACKED: a unit is either a run of whole small windows totalling <= 16 rows, or a 16-row chunk of a
+//     large window; per-row key bounds (from row_info) give the block-diagonal mask.  A 3-token window therefore costs
+//     3/16 of an MMA tile instead of a whole one;
 //   * one warp per (unit, head) - per (unit, head pair) for 16-channel heads, the two heads interleaved as independent
-//     instruction streams: S = Q K^T accumulates in registers (ldmatrix operands), the softmax
-//     runs on the C fragments with quad shuffles, P goes back into the second MMA as the A operand
-//     directly from registers, V comes in through ldmatrix.trans.  Row pitch 144 B makes every
-//     ldmatrix phase conflict free.  The unit body is compiled for 16 / 32 / 48 / 64 keys.
-// bf16 operands (8-bit mantissa): tests hold this kernel to 1e-2 against the fp32 kernel on the same
-// (bf16-rounded) inputs.
+//     instruction streams: S = Q K^T accumulates in registers, the softmax runs on the C fragments with quad shuffles,
+//     P goes back into the second MMA as the A operand directly from registers, V comes in through ldmatrix.trans.
+//     The unit body is compiled for 16 / 32 / 48 / 64 keys.
+// The entry points that take the flat (N, 3d) bf16 q|k|v of r1 (gdmae_sra_attention_fwd_tc / _bwd_tc) run a small
+// re-layout kernel first (sra_prep_kernel) and exist for callers outside the fused encoder layer and for the tests.
+// bf16 operands (8-bit mantissa): tests hold these kernels to 1e-2 against the fp32 kernels / the oracle.
 #include "common.cuh"
+#include <cuda.h>
 #include <cuda_bf16.h>
 
 #define MM_BIN 64
 #define MM_ROWS 144            // 127 rows + 16 rows of MMA overrun + 1
-#define MM_INFO 128            // row_info records cached per bin
+#define MM_INFO 128            // row_info records per bin
 #define MM_SLICE 64
-#define MM_PITCH 72            // bf16 elements per smem row (144 B)
-#define MM_THREADS 512
-#ifndef MM_STAGER_WARPS
-#define MM_STAGER_WARPS 6      // forward: warps that copy and stage bins; the other 16 - MM_STAGER_WARPS run the MMAs
+#define MM_BOX 16              // rows per TMA box (2 KB)
+#define MM_GROUPS (MM_ROWS / MM_BOX)           // 16-row groups of a staged bin
+#define MF_GROUP (3 * MM_BOX * MM_SLICE)      // forward: bf16 elements of one group = the q | k | v boxes of 16 rows (6 KB)
+#define MB_GROUP (4 * MM_BOX * MM_SLICE)      // backward: q | k | v | dO (8 KB)
+#ifndef MM_THREADS
+#define MM_THREADS 512         // backward CTA size
+#endif
+#ifndef MF_THREADS
+#define MF_THREADS 512         // forward CTA size (the register cap follows: 65536 / MF_THREADS)
 #endif
 // forward: heads one math warp runs interleaved per work entry.  Measured (tools/sweep_sra_tc.py, r1): two heads win for the
 // 16-channel heads of d = 128 (28.7 vs 30.7 us), one head for the 32-channel heads of d = 256 (78 vs 89 us: the two-head body
@@ -49,52 +56,37 @@
 #else
 #define MM_HEADS_PER_ENTRY(HD) ((HD) == 16 ? 2 : 1)
 #endif
-#ifndef MM_STAGE_ILP
-#define MM_STAGE_ILP 4         // forward: rows a stager thread keeps in flight
-#endif
-#ifndef MF_THREADS
-#define MF_THREADS 512         // forward CTA size (the register cap follows: 65536 / MF_THREADS)
-#endif
-#define MM_GROUP (32 * MM_STAGER_WARPS)   // stager threads (forward)
-#define MM_MATH_WARPS (MF_THREADS / 32 - MM_STAGER_WARPS)
+#define MM_MATH_WARPS (MF_THREADS / 32 - 1)
+#ifndef MM_STAGES
 #define MM_STAGES 3
-#define MM_NINFO 5
+#endif
 #define MM_UNITS 48
-#define MM_UNIT_STRIDE 64      // ints per bin in the unit table: [0, 48) units, [48] count, [49] work counter (0), pad
-#define MM_UNIT_CHUNKS 13      // 16-byte chunks copied per bin (52 ints)
-#define MM_ARR (MM_ROWS * MM_PITCH)
-#define MM_STAGE_ELEMS (3 * MM_ARR)
-#define MM_SMEM_BYTES (64 * 2 * MM_SLICE * 2 + MM_STAGES * MM_STAGE_ELEMS * 2 + MM_NINFO * MM_INFO * 16 + MM_NINFO * MM_UNIT_STRIDE * 4)
+#define MM_UNIT_STRIDE 64      // ints of the unit list: [0, 48) units, [48] count, [49] work counter (0), [50] first row, [51] rows, pad
+#define MM_BLOCK_INTS (MM_UNIT_STRIDE + 4 * MM_INFO)   // per-bin block of the table: unit list + the 128 row records from the bin's first row (2304 B)
+#define MM_RR_SLOTS 256        // (first row, rows) of a CTA's first bins, preloaded into shared memory
+#define MM_STAGE_BYTES (MM_GROUPS * MF_GROUP * 2 + MM_BLOCK_INTS * 4)
+#define MM_SMEM_BYTES (MM_STAGES * MM_STAGE_BYTES + MM_RR_SLOTS * 8 + 2 * MM_STAGES * 8 + 1024)
 
 typedef __nv_bfloat16 bf16;
 
 struct MmArgs {
-  const bf16* qkv;     // (N, 3d) bf16
-  const float* lut;    // (64, 2d)
-  const int4* row_info;
-  const int* bin_units; // (ceil(N/64), 64) work units per bin (gdmae_sra_bin_units)
-  const float* tau;
-  const float* bv;     // (d) value bias added to the output, nullable
-  float tau_min;
+  const int* bin_units; // per-bin blocks (gdmae_sra_bin_units)
+  const float* bv;      // (d) value bias added to the output, nullable
   int N, d;
   int out_bf16;
+  int lse_by_row;       // lse goes to column h of the (N, 24) per-row record of the backward (CSR-row order) instead of (N, 8) by token
 };
 
-__device__ __forceinline__ void mm_cp16(void* smem_dst, const void* gmem_src) {
-  unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void mm_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N_>
-__device__ __forceinline__ void mm_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
-__device__ __forceinline__ void mm_bar_stagers() { asm volatile("bar.sync 1, %0;" ::"n"(MM_GROUP) : "memory"); }
-
 // ---- mbarriers (shared::cta): producer/consumer hand-over of stage buffers without CTA-wide barriers
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 // bounded waits that ran out (a logic error or a lost signal) are FATAL: the counter is bumped (gdmae_sra_wait_timeouts
 // tells the host why) and the kernel traps, so the launch ends in a sticky CUDA error that the next stream
@@ -110,7 +102,7 @@ __device__ __noinline__ void sra_wait_timed_out() {
 // hardware until the phase completes (a polling loop without it was measured to burn a third of the SM's issue slots and
 // starve the producer warps).  Bounded (about a second) so that a logic error ends in a trapped launch, not in a hung GPU.
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+  const unsigned addr = smem_u32(bar);
   for (int spin = 0; spin < 50000; ++spin) {
     unsigned ok;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
@@ -119,6 +111,27 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
   }
   sra_wait_timed_out();
 }
+
+// ---- the producer's copies (async proxy): a box = 16 rows of every tensor (q, k, v[, dO]) of one channel slice of the
+// (64 channels, N rows, d/64 slices, 3 or 4 tensors) window-major array - one TMA operation per 16-row group (a TMA
+// operation costs ~80 cycles of the engine whatever its size: r2 measurement, tools/sweep_sra_tc.py) - and plain byte ranges
+__device__ __forceinline__ void tma_box(void* dst, const CUtensorMap* map, unsigned long long* bar, int row, int slice) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(smem_u32(dst)), "l"((unsigned long long)map), "r"(smem_u32(bar)), "r"(0), "r"(row), "r"(slice), "r"(0) : "memory");
+}
+__device__ __forceinline__ void bulk_copy(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// element offset of (row, channel) of the first tensor inside a staged bin: groups of 16 rows, GE elements apart (the boxes of
+// the other tensors follow at + 1024 elements each), SWIZZLE_128B inside a box (16-byte chunk c of row r at chunk c ^ (r & 7))
+template <int GE>
+__device__ __forceinline__ int sw_off(int row, int col) {
+  return (row >> 4) * GE + ((row & 15) << 6) + ((((col >> 3) ^ row) & 7) << 3) + (col & 7);
+}
+#define SWF(row, col) sw_off<MF_GROUP>(row, col)
+#define SWB(row, col) sw_off<MB_GROUP>(row, col)
 
 __device__ __forceinline__ void ldsm_x4(unsigned (&r)[4], const bf16* p) {
   unsigned sa = (unsigned)__cvta_generic_to_shared(p);
@@ -144,42 +157,6 @@ __device__ __forceinline__ unsigned pack_bf16(float lo, float hi) {
   return *reinterpret_cast<unsigned*>(&v);
 }
 
-// rows [row0, row1) = the windows that start inside the bin; inf = records of rows bin .. bin+127
-__device__ __forceinline__ void mm_bin_range(const int4* inf, int bin, int N, int& row0, int& R) {
-  int4 f = inf[0];
-  row0 = (f.y == bin) ? bin : f.z;
-  int row1 = N;
-  if (bin + MM_BIN < N) {
-    int4 l = inf[MM_BIN];
-    row1 = (l.y == bin + MM_BIN) ? bin + MM_BIN : l.z;
-  }
-  R = row1 - row0;
-  if (R < 0) R = 0;
-}
-
-// the stager group (MM_GROUP threads, index gt) issues all copies
-__device__ __forceinline__ void mm_issue_info(int4* inf, int* units, const int4* row_info, const int* bin_units, int bin, int N, int gt) {
-  if (gt < MM_INFO) {
-    if (bin + gt < N) mm_cp16(inf + gt, row_info + bin + gt);
-  } else if (gt < MM_INFO + MM_UNIT_CHUNKS) {
-    mm_cp16(units + 4 * (gt - MM_INFO), bin_units + (long long)(bin / MM_BIN) * MM_UNIT_STRIDE + 4 * (gt - MM_INFO));
-  }
-}
-
-__device__ __forceinline__ void mm_issue_rows(bf16* stage, const int4* inf, const bf16* qkv, int d, int col, int bin, int N, int gt) {
-  int row0, R;
-  mm_bin_range(inf, bin, N, row0, R);
-  const int shift = row0 - bin;
-  for (int idx = gt; idx < R * 8; idx += MM_GROUP) {      // one 16-byte chunk of q, k and v each
-    const int r = idx >> 3, c8 = idx & 7;
-    const bf16* src = qkv + (long long)inf[r + shift].x * 3 * d + col + 8 * c8;
-    bf16* dst = stage + r * MM_PITCH + 8 * c8;
-    mm_cp16(dst, src);
-    mm_cp16(dst + MM_ARR, src + d);
-    mm_cp16(dst + 2 * MM_ARR, src + 2 * d);
-  }
-}
-
 // bits [pos, pos+32) of the 128-bit mask (m1:m0)
 __device__ __forceinline__ unsigned mm_bits(unsigned long long m0, unsigned long long m1, int pos) {
   unsigned long long v;
@@ -189,100 +166,12 @@ __device__ __forceinline__ unsigned mm_bits(unsigned long long m0, unsigned long
   return (unsigned)v;
 }
 
-// Staging of U 8-channel groups (U rows, same channels) of q or k, in place: + LUT (packed bf16 add), L2 norm of the
-// head in fp32 (the 8-channel groups of a head sit in adjacent lanes: 2 lanes for 16-channel heads, 4 for 32), scale,
-// back to bf16.  All loads come first and all stores last so that the U dependency chains overlap.  rn[u] = 1/|x|.
-template <int HD, int U>
-__device__ __forceinline__ void mm_stage_tasks(bf16* const (&p)[U], const bf16* const (&lut_row)[U], float extra_scale,
-                                               const bool (&valid)[U], float (&rn)[U]) {
-  uint4 raw[U], lr[U];
-#pragma unroll
-  for (int u = 0; u < U; ++u) {
-    raw[u] = *reinterpret_cast<const uint4*>(p[u]);
-    lr[u] = *reinterpret_cast<const uint4*>(lut_row[u]);
-  }
-  float x[U][8], ss[U];
-#pragma unroll
-  for (int u = 0; u < U; ++u) {
-    const unsigned w[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
-    const unsigned l[4] = {lr[u].x, lr[u].y, lr[u].z, lr[u].w};
-    float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      __nv_bfloat162 sum = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]), *reinterpret_cast<const __nv_bfloat162*>(&l[i]));
-      const unsigned v = *reinterpret_cast<unsigned*>(&sum);
-      x[u][2 * i] = __uint_as_float(v << 16);
-      x[u][2 * i + 1] = __uint_as_float(v & 0xffff0000u);
-      s0 = fmaf(x[u][2 * i], x[u][2 * i], s0);
-      s1 = fmaf(x[u][2 * i + 1], x[u][2 * i + 1], s1);
-    }
-    ss[u] = s0 + s1;
-  }
-#pragma unroll
-  for (int u = 0; u < U; ++u) ss[u] += __shfl_xor_sync(0xffffffffu, ss[u], 1);
-  if (HD == 32) {
-#pragma unroll
-    for (int u = 0; u < U; ++u) ss[u] += __shfl_xor_sync(0xffffffffu, ss[u], 2);
-  }
-#pragma unroll
-  for (int u = 0; u < U; ++u) {
-    float r;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaxf(ss[u], 1e-24f)));
-    rn[u] = r;
-  }
-#pragma unroll
-  for (int u = 0; u < U; ++u) {
-    const float f = rn[u] * extra_scale;
-    if (valid[u]) {
-      uint4 o;
-      o.x = pack_bf16(x[u][0] * f, x[u][1] * f);
-      o.y = pack_bf16(x[u][2] * f, x[u][3] * f);
-      o.z = pack_bf16(x[u][4] * f, x[u][5] * f);
-      o.w = pack_bf16(x[u][6] * f, x[u][7] * f);
-      *reinterpret_cast<uint4*>(p[u]) = o;
-    }
-  }
-}
-
-// The staging pass of one bin: NT threads (index t) own the 8-channel group t & 7 of array (t >> 3) & 1 (q or k) and walk
-// the rows U * NT / 16 at a time.  srq / srk (nullable): 1/|q|, 1/|k| per (row, head) for the backward.
-template <int HD, int U, int NT>
-__device__ __forceinline__ void mm_stage_bin(bf16* sq, const bf16* slut, const int4* inf, int R, float qscale, int t, float* srq,
-                                             float* srk) {
-  constexpr int RP = NT / 16;                                 // rows per sub-pass
-  const int c8 = t & 7, part = (t >> 3) & 1, rsub = t >> 4;
-  const float sc = part == 0 ? qscale : 1.f;
-  bf16* base = sq + part * MM_ARR + 8 * c8;
-  const bf16* lutc = slut + part * MM_SLICE + 8 * c8;
-  float* srn = part == 0 ? srq : srk;
-  for (int rb = 0; rb < R; rb += U * RP) {                    // uniform trip count: the tasks shuffle inside the warp
-    bf16* p[U];
-    const bf16* l[U];
-    bool valid[U];
-    float rn[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int r = rb + rsub + u * RP;
-      valid[u] = r < R;
-      const int c = valid[u] ? r : 0;
-      p[u] = base + c * MM_PITCH;
-      l[u] = lutc + inf[c].w * 2 * MM_SLICE;
-    }
-    mm_stage_tasks<HD, U>(p, l, sc, valid, rn);
-    if (srn != nullptr && (c8 & (HD / 8 - 1)) == 0) {
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (valid[u]) srn[(rb + rsub + u * RP) * 4 + c8 / (HD / 8)] = rn[u];
-    }
-  }
-}
-
 // One unit and NH adjacent heads on one warp: S = Q K^T, masked softmax, O = P V, for NT2 8-key tiles (NT2 even).  The NH
 // heads are independent instruction streams over the same rows and masks; every step is written as a loop over the heads
 // so that their dependency chains (ldmatrix -> mma -> shuffle -> exp2 -> mma) overlap in the one warp.
 template <int HD, int NT2, int NH>
 __device__ __forceinline__ void mm_unit(const MmArgs& a, const bf16* sq, const bf16* sk, const bf16* sv, int q0, int qn, int k0,
-                                        int ch, int4 recA, int4 recB, int kbase, int lane, long long out_col, int lse_col,
+                                        int ch, int4 recA, int4 recB, int kbase, int rowbase, int lane, long long out_col, int lse_col,
                                         void* __restrict__ out, float* __restrict__ lse) {
   constexpr int KS = HD / 16, ND = HD / 8;
   const int g = lane >> 2, t = lane & 3;
@@ -292,7 +181,7 @@ __device__ __forceinline__ void mm_unit(const MmArgs& a, const bf16* sq, const b
   for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
     for (int hh = 0; hh < NH; ++hh)
-      ldsm_x4(qa[hh][ks], sq + (q0 + (lane & 7) + 8 * ((lane >> 3) & 1)) * MM_PITCH + ch + hh * HD + 16 * ks + 8 * (lane >> 4));
+      ldsm_x4(qa[hh][ks], sq + SWF(q0 + (lane & 7) + 8 * ((lane >> 3) & 1), ch + hh * HD + 16 * ks + 8 * (lane >> 4)));
   float c[NH][NT2][4];
 #pragma unroll
   for (int hh = 0; hh < NH; ++hh)
@@ -306,7 +195,7 @@ __device__ __forceinline__ void mm_unit(const MmArgs& a, const bf16* sq, const b
         unsigned kb[NH][4];
 #pragma unroll
         for (int hh = 0; hh < NH; ++hh)
-          ldsm_x4(kb[hh], sk + (k0 + 8 * (2 * np + u) + (lane & 7)) * MM_PITCH + ch + hh * HD + 8 * (lane >> 3));
+          ldsm_x4(kb[hh], sk + SWF(k0 + 8 * (2 * np + u) + (lane & 7), ch + hh * HD + 8 * (lane >> 3)));
 #pragma unroll
         for (int hh = 0; hh < NH; ++hh) mma_bf16(c[hh][2 * np + u], qa[hh][0], kb[hh][0], kb[hh][1]);
 #pragma unroll
@@ -316,7 +205,7 @@ __device__ __forceinline__ void mm_unit(const MmArgs& a, const bf16* sq, const b
       unsigned kb[NH][4];
 #pragma unroll
       for (int hh = 0; hh < NH; ++hh)
-        ldsm_x4(kb[hh], sk + (k0 + 16 * np + 8 * (lane >> 4) + (lane & 7)) * MM_PITCH + ch + hh * HD + 8 * ((lane >> 3) & 1));
+        ldsm_x4(kb[hh], sk + SWF(k0 + 16 * np + 8 * (lane >> 4) + (lane & 7), ch + hh * HD + 8 * ((lane >> 3) & 1)));
 #pragma unroll
       for (int hh = 0; hh < NH; ++hh) {
         mma_bf16(c[hh][2 * np], qa[hh][0], kb[hh][0], kb[hh][1]);
@@ -389,7 +278,7 @@ __device__ __forceinline__ void mm_unit(const MmArgs& a, const bf16* sq, const b
       unsigned vb[NH][4];
 #pragma unroll
       for (int hh = 0; hh < NH; ++hh)
-        ldsm_x4_t(vb[hh], sv + (k0 + 16 * kt + (lane & 7) + 8 * ((lane >> 3) & 1)) * MM_PITCH + ch + hh * HD + 16 * np + 8 * (lane >> 4));
+        ldsm_x4_t(vb[hh], sv + SWF(k0 + 16 * kt + (lane & 7) + 8 * ((lane >> 3) & 1), ch + hh * HD + 16 * np + 8 * (lane >> 4)));
 #pragma unroll
       for (int hh = 0; hh < NH; ++hh) {
         mma_bf16(o[hh][2 * np], pa[hh], vb[hh][0], vb[hh][1]);
@@ -416,15 +305,16 @@ __device__ __forceinline__ void mm_unit(const MmArgs& a, const bf16* sq, const b
           else *reinterpret_cast<float2*>((float*)out + e0 + 8 * nd) = make_float2(x0, x1);
         }
         // natural-log lse of the scores S = cos / tau (the backward kernels expect it)
+        // (lse_by_row: indexed by CSR row - the layout the window-major backward reads with one bulk copy per bin)
         if (t == 0)
-          lse[(long long)tok * 8 + lse_col + hh] = ((half ? mx1[hh] : mx0[hh]) + __log2f(half ? l1[hh] : l0[hh])) * 0.6931471805599453f;
+          lse[(a.lse_by_row ? (long long)(rowbase + g + 8 * half) * 24 : (long long)tok * 8) + lse_col + hh] =
+              ((half ? mx1[hh] : mx0[hh]) + __log2f(half ? l1[hh] : l0[hh])) * 0.6931471805599453f;
       }
     }
   }
 }
-
 #ifdef MM_PROFILE
-// development build only (tools/sweep_sra_tc.py -DMM_PROFILE): cycle counters of one stager warp and one math warp per CTA
+// development build only (tools/sweep_sra_tc.py -DMM_PROFILE): cycle counters of the producer and one math warp per CTA
 __device__ unsigned long long g_mm_prof[16];
 #define MM_PROF_T(var) const long long var = clock64()
 #define MM_PROF_ADD(slot, cycles) do { if (lane == 0) atomicAdd(&g_mm_prof[slot], (unsigned long long)(cycles)); } while (0)
@@ -438,15 +328,17 @@ extern "C" int gdmae_sra_prof_read(unsigned long long* out16, int reset) {
 #define MM_PROF_ADD(slot, cycles)
 #endif
 
+// tmQ: (64 channels, N rows, d/64 slices, 3 tensors) bf16 view of the window-major q^ | k^ | v, box 64 x 16 x 1 x 3, SWIZZLE_128B
 template <int HD>
-__global__ void __launch_bounds__(MF_THREADS, 1) sra_fwd_mma_kernel(MmArgs a, void* __restrict__ out, float* __restrict__ lse) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  bf16* slut = (bf16*)smem_raw;                               // [64][128]: q part | k part of this slice
-  bf16* sdata = slut + 64 * 2 * MM_SLICE;                     // MM_STAGES x {q, k, v} x [144][72]
-  int4* sinfo_all = (int4*)(sdata + MM_STAGES * MM_STAGE_ELEMS);
-  int* sunit_all = (int*)(sinfo_all + MM_NINFO * MM_INFO);    // MM_NINFO x { units: q0 | qn << 7 | k0 << 12 | kn << 19 ; [MM_UNITS] = count, [+1] = work counter }
-  __shared__ unsigned long long s_full[MM_STAGES], s_empty[MM_STAGES];   // bin staged / bin consumed
-  static_assert(MM_GROUP >= MM_INFO + MM_UNIT_CHUNKS && MM_MATH_WARPS >= 1, "stager group too small for the record copies");
+__global__ void __launch_bounds__(MF_THREADS, 1) sra_fwd_mma_kernel(const __grid_constant__ CUtensorMap tmQ, MmArgs a, void* __restrict__ out,
+                                                                    float* __restrict__ lse) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);   // swizzled boxes: 1024-byte aligned
+  bf16* sdata = (bf16*)smem_raw;                              // MM_STAGES x 9 groups x {q, k, v} x [16][64]
+  int* sblock_all = (int*)(sdata + MM_STAGES * MM_GROUPS * MF_GROUP);   // MM_STAGES x { unit list (64 ints) | 128 row records }
+  int2* s_rr = (int2*)(sblock_all + MM_STAGES * MM_BLOCK_INTS);         // (first row, rows) of this CTA's bins
+  unsigned long long* s_full = (unsigned long long*)(s_rr + MM_RR_SLOTS);   // bin landed
+  unsigned long long* s_empty = s_full + MM_STAGES;                         // bin consumed
   constexpr int HS = MM_SLICE / HD;
   const int d = a.d;
   const int nsl = d / MM_SLICE;
@@ -454,123 +346,68 @@ __global__ void __launch_bounds__(MF_THREADS, 1) sra_fwd_mma_kernel(MmArgs a, vo
   const int col = sl * MM_SLICE;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nbins = (a.N + MM_BIN - 1) / MM_BIN;
-  const bool stager = warp < MM_STAGER_WARPS;
-  const int gt = tid;                                         // index inside the stager group (stagers are warps 0 ..)
   if (cta >= nbins) return;
   const int my_bins = (nbins - cta + ncta - 1) / ncta;        // bins cta, cta + ncta, ...
   MM_PROF_T(k0_);
 
-  // ---- prologue: first records (their latency hides behind the rest), LUT slice -> bf16 (loads batched), zeroed data
-  // buffers (overrun rows must hold finite values), barriers
-  if (stager) {
-#pragma unroll
-    for (int j = 0; j < 3; ++j)
-      if (j < my_bins)
-        mm_issue_info(sinfo_all + j * MM_INFO, sunit_all + j * MM_UNIT_STRIDE, a.row_info, a.bin_units, (cta + j * ncta) * MM_BIN, a.N, gt);
-    mm_commit();
-  }
-  {
-    constexpr int NL = (64 * MM_SLICE + MF_THREADS - 1) / MF_THREADS;   // bf16 pairs per thread
-    float2 v[NL];
-#pragma unroll
-    for (int i = 0; i < NL; ++i) {
-      const int idx = tid + i * MF_THREADS;
-      const int pos = idx >> 6, c2 = idx & 63;
-      const int part = c2 >> 5, cc = (c2 & 31) * 2;
-      v[i] = idx < 64 * MM_SLICE ? __ldg(reinterpret_cast<const float2*>(a.lut + (long long)pos * 2 * d + part * d + col + cc))
-                                 : make_float2(0.f, 0.f);
-    }
-    for (int i = tid; i < MM_STAGES * MM_STAGE_ELEMS / 8; i += MF_THREADS) reinterpret_cast<uint4*>(sdata)[i] = make_uint4(0, 0, 0, 0);
-#pragma unroll
-    for (int i = 0; i < NL; ++i) {
-      const int idx = tid + i * MF_THREADS;
-      const int pos = idx >> 6, c2 = idx & 63;
-      const int part = c2 >> 5, cc = (c2 & 31) * 2;
-      if (idx < 64 * MM_SLICE) *reinterpret_cast<unsigned*>(slut + pos * 2 * MM_SLICE + part * MM_SLICE + cc) = pack_bf16(v[i].x, v[i].y);
-    }
-  }
+  // ---- prologue: (first row, rows) of the CTA's bins, zeroed data buffers (overrun rows must hold finite values), barriers
+  if (tid < MM_RR_SLOTS && tid < my_bins)
+    s_rr[tid] = __ldg(reinterpret_cast<const int2*>(a.bin_units + (long long)(cta + tid * ncta) * MM_BLOCK_INTS + MM_UNITS + 2));
+  for (int i = tid; i < MM_STAGES * MM_GROUPS * MF_GROUP / 8; i += MF_THREADS) reinterpret_cast<uint4*>(sdata)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
 #pragma unroll
     for (int st = 0; st < MM_STAGES; ++st) {
-      mbar_init(&s_full[st], MM_STAGER_WARPS);   // every stager warp arrives once its share of the bin is staged (one
-                                                 // arrival per thread was measured at ~900 cycles per bin on the stagers)
+      mbar_init(&s_full[st], 1);                 // the producer's expect_tx arrival + the bytes of its copies
       mbar_init(&s_empty[st], MM_MATH_WARPS);    // every math warp arrives once it has no more work in the bin
     }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (stager) mm_wait<0>();
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the zero fill is ordered before the first TMA writes
   __syncthreads();     // the only CTA-wide barrier: from here the two roles meet through the mbarriers
   MM_PROF_T(k1_);
 
-  if (stager) {
-    // ================= stagers: stage bin j in place and hand it over, then start the copies of bin j+2 (rows) and
-    // bin j+4 (records + units) into the buffers the math warps release with bin j-1.  Staging never waits for the math
-    // warps; only the copies do.  (cp.async per thread: 1-D TMA bulk copies of the 128-byte row pieces were measured at
-    // ~60 cycles of issue per copy from one warp - 11.6 k cycles per bin - and dropped.)
-    const float qscale = 1.4426950408889634f / fmaxf(__ldg(a.tau), a.tau_min);   // log2(e) / tau: softmax in base 2
-    mm_issue_rows(sdata, sinfo_all, a.qkv, d, col, cta * MM_BIN, a.N, gt);
-    mm_commit();                                                                  // group 0: rows of bin 0
-    if (1 < my_bins)
-      mm_issue_rows(sdata + MM_STAGE_ELEMS, sinfo_all + MM_INFO, a.qkv, d, col, (cta + ncta) * MM_BIN, a.N, gt);
-    if (3 < my_bins)
-      mm_issue_info(sinfo_all + 3 * MM_INFO, sunit_all + 3 * MM_UNIT_STRIDE, a.row_info, a.bin_units, (cta + 3 * ncta) * MM_BIN, a.N, gt);
-    mm_commit();                                                                  // group 1: rows of bin 1, records of bin 3
-    for (int j = 0; j < my_bins; ++j) {
-      const int bin = (cta + j * ncta) * MM_BIN;
-      const int4* sinfo = sinfo_all + (j % MM_NINFO) * MM_INFO;
-      bf16* sq = sdata + (j % MM_STAGES) * MM_STAGE_ELEMS;
-      MM_PROF_T(t0);
-      mm_wait<1>();          // everything but the latest group: rows of bin j, records + units of bin j+2
-      mm_bar_stagers();      // ... from every stager thread
-      MM_PROF_T(t1);
-      int row0, R;
-      mm_bin_range(sinfo, bin, a.N, row0, R);
-      const int shift = row0 - bin;
-#ifndef MM_DEBUG_NO_STAGE
-      mm_stage_bin<HD, MM_STAGE_ILP, MM_GROUP>(sq, slut, sinfo + shift, R, qscale, gt, nullptr, nullptr);
-#endif
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_full[j % MM_STAGES]);     // release: the warp's copies (waited above) and staged rows
-      MM_PROF_T(t2);
-      if (j + 2 < my_bins) {
-        // the buffer of bin j+2 held bin j-1 (and the record slot bin j+4 takes is bin j-1's): math must be done with it
-        if (j + 2 >= MM_STAGES) mbar_wait(&s_empty[(j + 2) % MM_STAGES], (((j + 2) / MM_STAGES) - 1) & 1);
-      }
-      MM_PROF_T(t3);
-      if (j + 2 < my_bins)
-        mm_issue_rows(sdata + ((j + 2) % MM_STAGES) * MM_STAGE_ELEMS, sinfo_all + ((j + 2) % MM_NINFO) * MM_INFO, a.qkv, d, col,
-                      (cta + (j + 2) * ncta) * MM_BIN, a.N, gt);
-      if (j + 4 < my_bins)
-        mm_issue_info(sinfo_all + ((j + 4) % MM_NINFO) * MM_INFO, sunit_all + ((j + 4) % MM_NINFO) * MM_UNIT_STRIDE, a.row_info,
-                      a.bin_units, (cta + (j + 4) * ncta) * MM_BIN, a.N, gt);
-      mm_commit();
+  if (warp == 0) {
+    // ================= producer (one thread): bin j into stage j % MM_STAGES as soon as the math warps have released
+    // bin j - MM_STAGES.  One transaction per bin: the bin's block of the table (unit list incl. the zeroed work counter +
+    // row records) and one box per 16 rows (q^, k^ and v together).
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&tmQ) : "memory");
+      for (int j = 0; j < my_bins; ++j) {
+        const int bi = cta + j * ncta, st = j % MM_STAGES;
+        const int2 rr = j < MM_RR_SLOTS ? s_rr[j]
+                                        : __ldg(reinterpret_cast<const int2*>(a.bin_units + (long long)bi * MM_BLOCK_INTS + MM_UNITS + 2));
+        MM_PROF_T(t0);
+        if (j >= MM_STAGES) mbar_wait(&s_empty[st], ((j / MM_STAGES) - 1) & 1);
+        MM_PROF_T(t1);
+        const int row0 = rr.x, nbox = (rr.y + MM_BOX - 1) / MM_BOX;
+        mbar_expect_tx(&s_full[st], (unsigned)(nbox * MF_GROUP * 2 + MM_BLOCK_INTS * 4));
+        bulk_copy(sblock_all + st * MM_BLOCK_INTS, a.bin_units + (long long)bi * MM_BLOCK_INTS, MM_BLOCK_INTS * 4, &s_full[st]);
+        bf16* tile = sdata + st * MM_GROUPS * MF_GROUP;
+        for (int i = 0; i < nbox; ++i) tma_box(tile + i * MF_GROUP, &tmQ, &s_full[st], row0 + i * MM_BOX, sl);
 #ifdef MM_PROFILE
-      if (warp == 0) {
-        MM_PROF_T(t4);
-        MM_PROF_ADD(0, t3 - t2); MM_PROF_ADD(1, t4 - t3); MM_PROF_ADD(2, t1 - t0); MM_PROF_ADD(4, t2 - t1); MM_PROF_ADD(5, 1);
-      }
+        MM_PROF_T(t2);
+        MM_PROF_ADD(0, t1 - t0); MM_PROF_ADD(1, t2 - t1); MM_PROF_ADD(5, 1);
 #endif
+      }
     }
-    mm_wait<0>();
   } else {
     // ================= math warps: entries of bin j (a unit and one or two heads), handed out through the bin's
     // work counter; a warp that finds the bin exhausted signals and moves on to bin j+1 without waiting for the others
     const int g = lane >> 2;
     for (int j = 0; j < my_bins; ++j) {
-      const int bin = (cta + j * ncta) * MM_BIN;
-      const int4* sinfo = sinfo_all + (j % MM_NINFO) * MM_INFO;
-      const bf16* sq = sdata + (j % MM_STAGES) * MM_STAGE_ELEMS;
-      const bf16* sk = sq + MM_ARR;
-      const bf16* sv = sk + MM_ARR;
-      int* sunit = sunit_all + (j % MM_NINFO) * MM_UNIT_STRIDE;
+      const int st = j % MM_STAGES;
+      int* sunit = sblock_all + st * MM_BLOCK_INTS;
+      const int4* sinfo = (const int4*)(sunit + MM_UNIT_STRIDE);      // records of rows row0 .. row0 + 127
+      const bf16* sq = sdata + st * MM_GROUPS * MF_GROUP;
+      const bf16* sk = sq + MM_BOX * MM_SLICE;
+      const bf16* sv = sk + MM_BOX * MM_SLICE;
       MM_PROF_T(m0);
-      mbar_wait(&s_full[j % MM_STAGES], (j / MM_STAGES) & 1);
+      mbar_wait(&s_full[st], (j / MM_STAGES) & 1);
       MM_PROF_T(m1);
 #ifdef MM_PROFILE
       int n_done = 0;
 #endif
-      int row0, R;
-      mm_bin_range(sinfo, bin, a.N, row0, R);
-      const int shift = row0 - bin;
+      const int row0 = sunit[MM_UNITS + 2], R = sunit[MM_UNITS + 3];
       constexpr int HPE = MM_HEADS_PER_ENTRY(HD);
       constexpr int EPU = HS / HPE;                           // entries per unit
 #ifdef MM_DEBUG_NO_MATH
@@ -590,27 +427,27 @@ __global__ void __launch_bounds__(MF_THREADS, 1) sra_fwd_mma_kernel(MmArgs a, vo
         const int h = (e % EPU) * HPE;
         const int q0 = code & 127, qn = (code >> 7) & 31, k0 = (code >> 12) & 127, kn = (code >> 19) & 127;
         const int ch = h * HD;
-        const int4 recA = sinfo[min(q0 + g, R - 1) + shift], recB = sinfo[min(q0 + g + 8, R - 1) + shift];
-        const int kbase = row0 + k0;
+        const int4 recA = sinfo[min(q0 + g, R - 1)], recB = sinfo[min(q0 + g + 8, R - 1)];
+        const int kbase = row0 + k0, rowbase = row0 + q0;
         const long long oc = col + ch;
         const int lc = sl * HS + h;
-        if (kn <= 16) mm_unit<HD, 2, HPE>(a, sq, sk, sv, q0, qn, k0, ch, recA, recB, kbase, lane, oc, lc, out, lse);
-        else if (kn <= 32) mm_unit<HD, 4, HPE>(a, sq, sk, sv, q0, qn, k0, ch, recA, recB, kbase, lane, oc, lc, out, lse);
+        if (kn <= 16) mm_unit<HD, 2, HPE>(a, sq, sk, sv, q0, qn, k0, ch, recA, recB, kbase, rowbase, lane, oc, lc, out, lse);
+        else if (kn <= 32) mm_unit<HD, 4, HPE>(a, sq, sk, sv, q0, qn, k0, ch, recA, recB, kbase, rowbase, lane, oc, lc, out, lse);
         else {
           // large windows: one head at a time (the two-head body would spill at the register cap)
 #pragma unroll 1
           for (int hh = 0; hh < HPE; ++hh) {
-            if (kn <= 48) mm_unit<HD, 6, 1>(a, sq, sk, sv, q0, qn, k0, ch + hh * HD, recA, recB, kbase, lane, oc + hh * HD, lc + hh, out, lse);
-            else mm_unit<HD, 8, 1>(a, sq, sk, sv, q0, qn, k0, ch + hh * HD, recA, recB, kbase, lane, oc + hh * HD, lc + hh, out, lse);
+            if (kn <= 48) mm_unit<HD, 6, 1>(a, sq, sk, sv, q0, qn, k0, ch + hh * HD, recA, recB, kbase, rowbase, lane, oc + hh * HD, lc + hh, out, lse);
+            else mm_unit<HD, 8, 1>(a, sq, sk, sv, q0, qn, k0, ch + hh * HD, recA, recB, kbase, rowbase, lane, oc + hh * HD, lc + hh, out, lse);
           }
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[j % MM_STAGES]);
+      if (lane == 0) mbar_arrive(&s_empty[st]);
 #ifdef MM_PROFILE
-      if (warp == MM_STAGER_WARPS || warp == MF_THREADS / 32 - 1) {
+      if (warp == 1 || warp == MF_THREADS / 32 - 1) {
         MM_PROF_T(m2);
-        const int o = warp == MM_STAGER_WARPS ? 6 : 10;
+        const int o = warp == 1 ? 6 : 10;
         MM_PROF_ADD(o, m1 - m0); MM_PROF_ADD(o + 1, m2 - m1); MM_PROF_ADD(o + 2, n_done);
         if (o == 6) MM_PROF_ADD(9, nent);
       }
@@ -627,10 +464,11 @@ __global__ void __launch_bounds__(MF_THREADS, 1) sra_fwd_mma_kernel(MmArgs a, vo
   }
 }
 
+
 // =====================================================================================================
-// Backward.  Same bins, packing, operand staging and stager / math decoupling as the forward kernel; four staged arrays
-// (Qs = q_hat * log2(e)/tau, K_hat, V, dO) in two stage buffers, scalars (lse, 1/|q|, 1/|k|, D) per stage:
-//   stage    : + LUT, normalise q and k in place, keep 1/|q|, 1/|k| per (row, head); lse rows by cp.async
+// Backward.  Same bins, packing, tiles and producer / math decoupling as the forward kernel; four staged tiles
+// (Qs = q_hat * log2(e)/tau, K_hat, V, dO - all window-major, one TMA box per 16 rows) in two stages, the per-row records
+// (lse, 1/|q|, 1/|k| as the forward pass left them, CSR-row order: one bulk copy per bin) and D per stage:
 //   entries  : query side of every (unit, head), then key side, from one work queue; a key-side entry waits on a
 //              shared-memory counter for the query-side entries of its window (they produce D), not on a barrier
 //   phase 1  : one warp per (unit, head), query side.  One sweep over the key tiles computes S' = Qs K^T and
@@ -642,64 +480,31 @@ __global__ void __launch_bounds__(MF_THREADS, 1) sra_fwd_mma_kernel(MmArgs a, vo
 //              queries of a key tile are exactly the unit's key range): per 16-query step S'^T = K Qs^T,
 //              dP^T = V dO^T, P^T, dS^T = P^T (dP^T - D), then dV += P^T dO and H += dS^T Qs; nothing is held
 //              across steps.  dk = ln2 (H - K (K.H)) / |k|.
-// dq, dk, dv rows go straight from the fragments to dqkv (bf16); sum dS S is reduced per CTA into dtau_sum.
+// dq, dk, dv rows go straight from the fragments to the flat (N, 3d) dqkv (bf16, token order: the operand of the
+// in-projection's gradient GEMMs); sum dS S is reduced per CTA into dtau_sum.
 #define MB_STAGES 2
-#define MB_NINFO 4
-#define MB_STAGE_ELEMS (4 * MM_ARR)
-#define MB_SCAL (MM_ROWS * 4)      // one fp32 per (row, head of the slice)
-#ifndef MB_STAGER_WARPS
-#define MB_STAGER_WARPS 5      // backward: warps that copy and stage bins (>= 5: 141 threads copy records + units)
-#endif
-#define MB_GROUP (32 * MB_STAGER_WARPS)
-#define MB_MATH_WARPS (MM_THREADS / 32 - MB_STAGER_WARPS)
-// LUT | stages x {q,k,v,dO} | records | per stage: lse, 1/|q|, 1/|k|, D | units | per stage: query-side completion counters
-#define MB_SMEM_BYTES (64 * 2 * MM_SLICE * 2 + MB_STAGES * MB_STAGE_ELEMS * 2 + MB_NINFO * MM_INFO * 16 + MB_STAGES * 4 * MB_SCAL * 4 + MB_NINFO * MM_UNIT_STRIDE * 4 + MB_STAGES * 128 * 4 * 4)
+#define MB_SCAL (MM_ROWS * 24)     // per-row record of 24 fp32: lse | 1/|q| | 1/|k|, each per head
+#define MB_MATH_WARPS (MM_THREADS / 32 - 1)
+// stages x 9 groups x {q,k,v,dO} | per stage: row records [144][24], D [144][4] | table block | query-side completion counters | barriers
+#define MB_STAGE_BYTES (MM_GROUPS * MB_GROUP * 2 + MB_SCAL * 4 + MM_ROWS * 4 * 4 + MM_BLOCK_INTS * 4 + 128 * 4 * 4)
+#define MB_SMEM_BYTES (MB_STAGES * MB_STAGE_BYTES + MM_RR_SLOTS * 8 + 2 * MB_STAGES * 8 + 1024)
 
 struct MbArgs {
-  const bf16* qkv;     // (N, 3d) bf16
-  const float* lut;    // (64, 2d)
-  const int4* row_info;
-  const int* bin_units; // (ceil(N/64), 64) work units per bin (gdmae_sra_bin_units)
+  const int* bin_units; // per-bin blocks (gdmae_sra_bin_units)
   const float* tau;
-  const float* lse;    // (N, 8)
-  const bf16* dout;    // (N, d) bf16
-  bf16* dqkv;          // (N, 3d) bf16
+  const float* lrr;    // (N, 24) by CSR row: lse (forward kernel) | 1/|q| | 1/|k| (in-projection epilogue), 8 heads each
+  bf16* dqkv;          // (N, 3d) bf16, token order
   double* dtau_sum;
   float tau_min;
   int N, d;
 };
-
-template <int NT>
-__device__ __forceinline__ void mb_issue_rows(bf16* stage, float* slse, const int4* inf, const MbArgs& a, int col, int hs, int lse_col,
-                                              int bin, int tid) {
-  int row0, R;
-  mm_bin_range(inf, bin, a.N, row0, R);
-  const int shift = row0 - bin;
-  const int d = a.d;
-  for (int idx = tid; idx < R * 8; idx += NT) {              // one 16-byte chunk of q, k, v and dO each
-    const int r = idx >> 3, c8 = idx & 7;
-    const long long tok = inf[r + shift].x;
-    const bf16* src = a.qkv + tok * 3 * d + col + 8 * c8;
-    bf16* dst = stage + r * MM_PITCH + 8 * c8;
-    mm_cp16(dst, src);
-    mm_cp16(dst + MM_ARR, src + d);
-    mm_cp16(dst + 2 * MM_ARR, src + 2 * d);
-    mm_cp16(dst + 3 * MM_ARR, a.dout + tok * d + col + 8 * c8);
-  }
-  for (int idx = tid; idx < R * hs; idx += NT) {             // lse of the slice's heads, 4 bytes each
-    const int r = idx / hs, h = idx - r * hs;
-    unsigned sa = (unsigned)__cvta_generic_to_shared(slse + r * 4 + h);
-    const float* src = a.lse + (long long)inf[r + shift].x * 8 + lse_col + h;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(src) : "memory");
-  }
-}
 
 __device__ __forceinline__ float2 unpack_bf16(unsigned u) { return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
 
 // query side of one (unit, head): writes dq rows and sD, returns this lane's share of sum dS*S' (valid rows only)
 template <int HD, int NT2>
 __device__ __forceinline__ float mb_unit_q(const MbArgs& a, const bf16* sq, const bf16* sk, const bf16* sv, const bf16* sdo,
-                                           const float* slse, const float* srq, float* sD, int q0, int qn, int k0, int h, int4 recA,
+                                           const float* slse, const float* srq, float* sD, int* sdone_slot, int q0, int qn, int k0, int h, int hg, int4 recA,
                                            int4 recB, int kbase, int lane, int col, float inv_tau, float inv_qs2) {
   constexpr int KS = HD / 16, ND = HD / 8;
   const int g = lane >> 2, t = lane & 3, ch = h * HD;
@@ -708,12 +513,12 @@ __device__ __forceinline__ float mb_unit_q(const MbArgs& a, const bf16* sq, cons
   unsigned qa[KS][4], da[KS][4];
 #pragma unroll
   for (int ks = 0; ks < KS; ++ks) {
-    const int off = (q0 + (lane & 7) + 8 * ((lane >> 3) & 1)) * MM_PITCH + ch + 16 * ks + 8 * (lane >> 4);
+    const int off = SWB(q0 + (lane & 7) + 8 * ((lane >> 3) & 1), ch + 16 * ks + 8 * (lane >> 4));
     ldsm_x4(qa[ks], sq + off);
     ldsm_x4(da[ks], sdo + off);
   }
-  const float lA = slse[min(q0 + g, MM_ROWS - 1) * 4 + h] * 1.4426950408889634f;
-  const float lB = slse[min(q0 + g + 8, MM_ROWS - 1) * 4 + h] * 1.4426950408889634f;
+  const float lA = slse[min(q0 + g, MM_ROWS - 1) * 24 + hg] * 1.4426950408889634f;
+  const float lB = slse[min(q0 + g + 8, MM_ROWS - 1) * 24 + hg] * 1.4426950408889634f;
   unsigned pp[NT2][2];   // P packed bf16: [nt][0] = row g, [nt][1] = row g+8
   float dp[NT2][4];
   float D0 = 0.f, D1 = 0.f, T10 = 0.f, T11 = 0.f, T20 = 0.f, T21 = 0.f;
@@ -729,7 +534,7 @@ __device__ __forceinline__ float mb_unit_q(const MbArgs& a, const bf16* sq, cons
     if (KS == 2) {
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        const int off = (k0 + 8 * (2 * np + u) + (lane & 7)) * MM_PITCH + ch + 8 * (lane >> 3);
+        const int off = SWB(k0 + 8 * (2 * np + u) + (lane & 7), ch + 8 * (lane >> 3));
         ldsm_x4(kb, sk + off);
         ldsm_x4(vb, sv + off);
         mma_bf16(s[u], qa[0], kb[0], kb[1]);
@@ -738,7 +543,7 @@ __device__ __forceinline__ float mb_unit_q(const MbArgs& a, const bf16* sq, cons
         mma_bf16(dp[2 * np + u], da[KS - 1], vb[2], vb[3]);
       }
     } else {
-      const int off = (k0 + 16 * np + 8 * (lane >> 4) + (lane & 7)) * MM_PITCH + ch + 8 * ((lane >> 3) & 1);
+      const int off = SWB(k0 + 16 * np + 8 * (lane >> 4) + (lane & 7), ch + 8 * ((lane >> 3) & 1));
       ldsm_x4(kb, sk + off);
       ldsm_x4(vb, sv + off);
       mma_bf16(s[0], qa[0], kb[0], kb[1]);
@@ -776,6 +581,13 @@ __device__ __forceinline__ float mb_unit_q(const MbArgs& a, const bf16* sq, cons
     if (g < qn) { dtau_part += T10 - D0 * T20; sD[(q0 + g) * 4 + h] = D0; }
     if (g + 8 < qn) { dtau_part += T11 - D1 * T21; sD[(q0 + g + 8) * 4 + h] = D1; }
   }
+  // D of these rows is published here, before the long tail of the entry: the key-side entries of the window wait for it
+  // (the fence would otherwise also wait for this entry's global dq stores: r2 profile, ~4 % of the warp samples)
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence_block();
+    atomicAdd(sdone_slot, 1);
+  }
   // G = dS K_hat
   float acc[ND][4];
 #pragma unroll
@@ -793,7 +605,7 @@ __device__ __forceinline__ float mb_unit_q(const MbArgs& a, const bf16* sq, cons
 #pragma unroll
     for (int np = 0; np < ND / 2; ++np) {
       unsigned kb[4];
-      ldsm_x4_t(kb, sk + (k0 + 16 * kt + (lane & 7) + 8 * ((lane >> 3) & 1)) * MM_PITCH + ch + 16 * np + 8 * (lane >> 4));
+      ldsm_x4_t(kb, sk + SWB(k0 + 16 * kt + (lane & 7) + 8 * ((lane >> 3) & 1), ch + 16 * np + 8 * (lane >> 4)));
       mma_bf16(acc[2 * np], sa, kb[0], kb[1]);
       mma_bf16(acc[2 * np + 1], sa, kb[2], kb[3]);
     }
@@ -806,14 +618,14 @@ __device__ __forceinline__ float mb_unit_q(const MbArgs& a, const bf16* sq, cons
     float dot = 0.f;
 #pragma unroll
     for (int nd = 0; nd < ND; ++nd) {
-      qv[nd] = unpack_bf16(*reinterpret_cast<const unsigned*>(sq + row * MM_PITCH + ch + 8 * nd + 2 * t));
+      qv[nd] = unpack_bf16(*reinterpret_cast<const unsigned*>(sq + SWB(row, ch + 8 * nd + 2 * t)));
       dot = fmaf(qv[nd].x, acc[nd][2 * half], dot);
       dot = fmaf(qv[nd].y, acc[nd][2 * half + 1], dot);
     }
     dot += __shfl_xor_sync(0xffffffffu, dot, 1);
     dot += __shfl_xor_sync(0xffffffffu, dot, 2);
     if (g + 8 * half < qn) {
-      const float f = srq[row * 4 + h] * inv_tau, c2 = dot * inv_qs2;
+      const float f = srq[row * 24 + hg] * inv_tau, c2 = dot * inv_qs2;
       bf16* dst = a.dqkv + (long long)(half ? recB.x : recA.x) * 3 * a.d + col + ch + 2 * t;
 #pragma unroll
       for (int nd = 0; nd < ND; ++nd)
@@ -827,7 +639,7 @@ __device__ __forceinline__ float mb_unit_q(const MbArgs& a, const bf16* sq, cons
 // key side of one (unit, head): rows = the unit's 16-row tile as KEYS, columns = its key range as QUERIES
 template <int HD, int NT2>
 __device__ __forceinline__ void mb_unit_kv(const MbArgs& a, const bf16* sq, const bf16* sk, const bf16* sv, const bf16* sdo,
-                                           const float* slse, const float* srk, const float* sD, int q0, int qn, int k0, int h,
+                                           const float* slse, const float* srk, const float* sD, int q0, int qn, int k0, int h, int hg,
                                            int4 recA, int4 recB, int kbase, int lane, int col) {
   constexpr int KS = HD / 16, ND = HD / 8;
   const int g = lane >> 2, t = lane & 3, ch = h * HD;
@@ -836,7 +648,7 @@ __device__ __forceinline__ void mb_unit_kv(const MbArgs& a, const bf16* sq, cons
   unsigned ka_f[KS][4], va_f[KS][4];
 #pragma unroll
   for (int ks = 0; ks < KS; ++ks) {
-    const int off = (q0 + (lane & 7) + 8 * ((lane >> 3) & 1)) * MM_PITCH + ch + 16 * ks + 8 * (lane >> 4);
+    const int off = SWB(q0 + (lane & 7) + 8 * ((lane >> 3) & 1), ch + 16 * ks + 8 * (lane >> 4));
     ldsm_x4(ka_f[ks], sk + off);
     ldsm_x4(va_f[ks], sv + off);
   }
@@ -858,7 +670,7 @@ __device__ __forceinline__ void mb_unit_kv(const MbArgs& a, const bf16* sq, cons
     if (KS == 2) {
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        const int off = (k0 + 8 * (2 * np + u) + (lane & 7)) * MM_PITCH + ch + 8 * (lane >> 3);
+        const int off = SWB(k0 + 8 * (2 * np + u) + (lane & 7), ch + 8 * (lane >> 3));
         ldsm_x4(qb, sq + off);
         ldsm_x4(ob, sdo + off);
         mma_bf16(s[u], ka_f[0], qb[0], qb[1]);
@@ -867,7 +679,7 @@ __device__ __forceinline__ void mb_unit_kv(const MbArgs& a, const bf16* sq, cons
         mma_bf16(dp[u], va_f[KS - 1], ob[2], ob[3]);
       }
     } else {
-      const int off = (k0 + 16 * np + 8 * (lane >> 4) + (lane & 7)) * MM_PITCH + ch + 8 * ((lane >> 3) & 1);
+      const int off = SWB(k0 + 16 * np + 8 * (lane >> 4) + (lane & 7), ch + 8 * ((lane >> 3) & 1));
       ldsm_x4(qb, sq + off);
       ldsm_x4(ob, sdo + off);
       mma_bf16(s[0], ka_f[0], qb[0], qb[1]);
@@ -881,7 +693,7 @@ __device__ __forceinline__ void mb_unit_kv(const MbArgs& a, const bf16* sq, cons
       const int nt = 2 * np + u;
       // this lane's two query columns of the tile
       const int qc = min(k0 + 8 * nt + 2 * t, MM_ROWS - 2);
-      const float l0 = slse[qc * 4 + h] * 1.4426950408889634f, l1 = slse[(qc + 1) * 4 + h] * 1.4426950408889634f;
+      const float l0 = slse[qc * 24 + hg] * 1.4426950408889634f, l1 = slse[(qc + 1) * 24 + hg] * 1.4426950408889634f;
       const float d0 = sD[qc * 4 + h], d1 = sD[(qc + 1) * 4 + h];
       const float p0 = (unsigned)(ka + 8 * nt) < (unsigned)wA ? fast_exp2(s[u][0] - l0) : 0.f;
       const float p1 = (unsigned)(ka + 8 * nt + 1) < (unsigned)wA ? fast_exp2(s[u][1] - l1) : 0.f;
@@ -895,7 +707,7 @@ __device__ __forceinline__ void mb_unit_kv(const MbArgs& a, const bf16* sq, cons
 #pragma unroll
     for (int nq = 0; nq < ND / 2; ++nq) {
       unsigned ob2[4], qb2[4];
-      const int off = (k0 + 16 * np + (lane & 7) + 8 * ((lane >> 3) & 1)) * MM_PITCH + ch + 16 * nq + 8 * (lane >> 4);
+      const int off = SWB(k0 + 16 * np + (lane & 7) + 8 * ((lane >> 3) & 1), ch + 16 * nq + 8 * (lane >> 4));
       ldsm_x4_t(ob2, sdo + off);
       ldsm_x4_t(qb2, sq + off);
       mma_bf16(dv[2 * nq], pa, ob2[0], ob2[1]);
@@ -911,14 +723,14 @@ __device__ __forceinline__ void mb_unit_kv(const MbArgs& a, const bf16* sq, cons
     float dot = 0.f;
 #pragma unroll
     for (int nd = 0; nd < ND; ++nd) {
-      kv[nd] = unpack_bf16(*reinterpret_cast<const unsigned*>(sk + row * MM_PITCH + ch + 8 * nd + 2 * t));
+      kv[nd] = unpack_bf16(*reinterpret_cast<const unsigned*>(sk + SWB(row, ch + 8 * nd + 2 * t)));
       dot = fmaf(kv[nd].x, hk[nd][2 * half], dot);
       dot = fmaf(kv[nd].y, hk[nd][2 * half + 1], dot);
     }
     dot += __shfl_xor_sync(0xffffffffu, dot, 1);
     dot += __shfl_xor_sync(0xffffffffu, dot, 2);
     if (g + 8 * half < qn) {
-      const float f = srk[row * 4 + h] * 0.6931471805599453f;
+      const float f = srk[row * 24 + hg] * 0.6931471805599453f;
       bf16* dst = a.dqkv + (long long)(half ? recB.x : recA.x) * 3 * a.d + a.d + col + ch + 2 * t;
 #pragma unroll
       for (int nd = 0; nd < ND; ++nd) {
@@ -929,19 +741,20 @@ __device__ __forceinline__ void mb_unit_kv(const MbArgs& a, const bf16* sq, cons
     }
   }
 }
-
+// tmQ: (64 channels, N rows, d/64 slices, 4 tensors) view of the window-major q^ | k^ | v | dO, box 64 x 16 x 1 x 4
 template <int HD>
-__global__ void __launch_bounds__(MM_THREADS, 1) sra_bwd_mma_kernel(MbArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  bf16* slut = (bf16*)smem_raw;
-  bf16* sdata = slut + 64 * 2 * MM_SLICE;                     // MB_STAGES x {q, k, v, dO} x [144][72]
-  int4* sinfo_all = (int4*)(sdata + MB_STAGES * MB_STAGE_ELEMS);
-  float* sscal_all = (float*)(sinfo_all + MB_NINFO * MM_INFO); // MB_STAGES x { lse, 1/|q|, 1/|k|, D } x [144][4]
-  int* sunit_all = (int*)(sscal_all + MB_STAGES * 4 * MB_SCAL);
-  int* sdone_all = sunit_all + MB_NINFO * MM_UNIT_STRIDE;     // MB_STAGES x [128 window start rows][4 heads]: query-side entries finished
+__global__ void __launch_bounds__(MM_THREADS, 1) sra_bwd_mma_kernel(const __grid_constant__ CUtensorMap tmQ, MbArgs a) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  bf16* sdata = (bf16*)smem_raw;                               // MB_STAGES x 9 groups x {q, k, v, dO} x [16][64]
+  float* sscal_all = (float*)(sdata + MB_STAGES * MM_GROUPS * MB_GROUP);   // MB_STAGES x { records [144][24], D [144][4] }
+  constexpr int SCAL_STAGE = MB_SCAL + MM_ROWS * 4;
+  int* sblock_all = (int*)(sscal_all + MB_STAGES * SCAL_STAGE);
+  int* sdone_all = sblock_all + MB_STAGES * MM_BLOCK_INTS;     // MB_STAGES x [128 window start rows][4 heads]: query-side entries finished
+  int2* s_rr = (int2*)(sdone_all + MB_STAGES * 512);
+  unsigned long long* b_full = (unsigned long long*)(s_rr + MM_RR_SLOTS);   // bin landed
+  unsigned long long* b_empty = b_full + MB_STAGES;                         // bin consumed
   __shared__ float s_dtau[MM_THREADS / 32];
-  __shared__ unsigned long long b_full[MB_STAGES], b_empty[MB_STAGES];   // bin staged / bin consumed
-  static_assert(MB_GROUP >= MM_INFO + MM_UNIT_CHUNKS && MB_MATH_WARPS >= 1, "stager group too small for the record copies");
   constexpr int HS = MM_SLICE / HD;
   const int d = a.d;
   const int nsl = d / MM_SLICE;
@@ -952,82 +765,48 @@ __global__ void __launch_bounds__(MM_THREADS, 1) sra_bwd_mma_kernel(MbArgs a) {
   if (cta >= nbins) return;
   const int my_bins = (nbins - cta + ncta - 1) / ncta;
   const int lse_col = sl * HS;
-  const bool stager = warp < MB_STAGER_WARPS;
 
-  // ---- prologue: first records, LUT slice -> bf16 (loads batched), zeroed buffers (overrun rows and scalars must be finite)
-  if (stager) {
-#pragma unroll
-    for (int j = 0; j < 3; ++j)
-      if (j < my_bins)
-        mm_issue_info(sinfo_all + j * MM_INFO, sunit_all + j * MM_UNIT_STRIDE, a.row_info, a.bin_units, (cta + j * ncta) * MM_BIN, a.N, tid);
-    mm_commit();
-  }
-  {
-    constexpr int NL = (64 * MM_SLICE + MM_THREADS - 1) / MM_THREADS;   // bf16 pairs per thread
-    float2 v[NL];
-#pragma unroll
-    for (int i = 0; i < NL; ++i) {
-      const int idx = tid + i * MM_THREADS;
-      const int pos = idx >> 6, c2 = idx & 63;
-      const int part = c2 >> 5, cc = (c2 & 31) * 2;
-      v[i] = idx < 64 * MM_SLICE ? __ldg(reinterpret_cast<const float2*>(a.lut + (long long)pos * 2 * d + part * d + col + cc))
-                                 : make_float2(0.f, 0.f);
-    }
-    for (int i = tid; i < MB_STAGES * MB_STAGE_ELEMS / 8; i += MM_THREADS) reinterpret_cast<uint4*>(sdata)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < MB_STAGES * 4 * MB_SCAL; i += MM_THREADS) sscal_all[i] = 0.f;
-#pragma unroll
-    for (int i = 0; i < NL; ++i) {
-      const int idx = tid + i * MM_THREADS;
-      const int pos = idx >> 6, c2 = idx & 63;
-      const int part = c2 >> 5, cc = (c2 & 31) * 2;
-      if (idx < 64 * MM_SLICE) *reinterpret_cast<unsigned*>(slut + pos * 2 * MM_SLICE + part * MM_SLICE + cc) = pack_bf16(v[i].x, v[i].y);
-    }
-  }
+  // ---- prologue: (first row, rows) of the CTA's bins, zeroed buffers (overrun rows and scalars must be finite), barriers
+  if (tid < MM_RR_SLOTS && tid < my_bins)
+    s_rr[tid] = __ldg(reinterpret_cast<const int2*>(a.bin_units + (long long)(cta + tid * ncta) * MM_BLOCK_INTS + MM_UNITS + 2));
+  for (int i = tid; i < MB_STAGES * MM_GROUPS * MB_GROUP / 8; i += MM_THREADS) reinterpret_cast<uint4*>(sdata)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < MB_STAGES * SCAL_STAGE; i += MM_THREADS) sscal_all[i] = 0.f;
   if (tid == 0) {
 #pragma unroll
     for (int st = 0; st < MB_STAGES; ++st) {
-      mbar_init(&b_full[st], MB_STAGER_WARPS);
+      mbar_init(&b_full[st], 1);
       mbar_init(&b_empty[st], MB_MATH_WARPS);
     }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (stager) mm_wait<0>();
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();     // from here the two roles meet through the mbarriers (and once more for the d tau sum)
   const float tau_c = fmaxf(__ldg(a.tau), a.tau_min);
   const float qscale = 1.4426950408889634f / tau_c, inv_tau = 1.f / tau_c, inv_qs2 = 1.f / (qscale * qscale);
   float dtau_acc = 0.f;
 
-  if (stager) {
-    // ================= stagers: stage bin k in place (+ LUT, normalise, keep 1/|q|, 1/|k| per (row, head)), hand it over, then
-    // copy bin k+1 (rows, lse) and the records + units of bin k+3 into the buffers the math warps release with bin k-1
-    mb_issue_rows<MB_GROUP>(sdata, sscal_all, sinfo_all, a, col, HS, lse_col, cta * MM_BIN, tid);
-    mm_commit();
+  if (warp == 0) {
+    // ================= producer warp: once the math warps have released bin k - 2 the warp zeroes the stage's completion
+    // counters, then one lane issues the bin's transaction: table block, row records and one box per 16 rows
+    if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&tmQ) : "memory");
     for (int k = 0; k < my_bins; ++k) {
-      const int bin = (cta + k * ncta) * MM_BIN;
-      const int st = k % MB_STAGES;
-      const int4* sinfo = sinfo_all + (k % MB_NINFO) * MM_INFO;
-      bf16* sq = sdata + st * MB_STAGE_ELEMS;
-      float* sscal = sscal_all + st * 4 * MB_SCAL;
-      mm_wait<0>();        // rows of bin k, records + units of bin k+2
-      asm volatile("bar.sync 1, %0;" ::"n"(MB_GROUP) : "memory");   // ... from every stager thread
-      int row0, R;
-      mm_bin_range(sinfo, bin, a.N, row0, R);
-      const int shift = row0 - bin;
-      for (int i = tid; i < 128 * 4; i += MB_GROUP) sdone_all[st * 512 + i] = 0;
-      mm_stage_bin<HD, 4, MB_GROUP>(sq, slut, sinfo + shift, R, qscale, tid, sscal + MB_SCAL, sscal + 2 * MB_SCAL);
+      const int bi = cta + k * ncta, st = k % MB_STAGES;
+      if (lane == 0 && k >= MB_STAGES) mbar_wait(&b_empty[st], ((k / MB_STAGES) - 1) & 1);
       __syncwarp();
-      if (lane == 0) mbar_arrive(&b_full[st]);
-      if (k + 1 < my_bins) {
-        const int sn = (k + 1) % MB_STAGES;
-        if (k + 1 >= MB_STAGES) mbar_wait(&b_empty[sn], (((k + 1) / MB_STAGES) - 1) & 1);   // math is done with bin k-1
-        mb_issue_rows<MB_GROUP>(sdata + sn * MB_STAGE_ELEMS, sscal_all + sn * 4 * MB_SCAL, sinfo_all + ((k + 1) % MB_NINFO) * MM_INFO, a, col, HS,
-                                lse_col, (cta + (k + 1) * ncta) * MM_BIN, tid);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) reinterpret_cast<int4*>(sdone_all + st * 512)[lane + 32 * i] = make_int4(0, 0, 0, 0);
+      __syncwarp();
+      if (lane == 0) {
+        const int2 rr = k < MM_RR_SLOTS ? s_rr[k]
+                                        : __ldg(reinterpret_cast<const int2*>(a.bin_units + (long long)bi * MM_BLOCK_INTS + MM_UNITS + 2));
+        const int row0 = rr.x, R = rr.y, nbox = (R + MM_BOX - 1) / MM_BOX;
+        mbar_expect_tx(&b_full[st], (unsigned)(nbox * MB_GROUP * 2 + MM_BLOCK_INTS * 4 + R * 96));
+        bulk_copy(sblock_all + st * MM_BLOCK_INTS, a.bin_units + (long long)bi * MM_BLOCK_INTS, MM_BLOCK_INTS * 4, &b_full[st]);
+        if (R > 0) bulk_copy(sscal_all + st * SCAL_STAGE, a.lrr + (long long)row0 * 24, R * 96, &b_full[st]);
+        bf16* tile = sdata + st * MM_GROUPS * MB_GROUP;
+        for (int i = 0; i < nbox; ++i) tma_box(tile + i * MB_GROUP, &tmQ, &b_full[st], row0 + i * MM_BOX, sl);
       }
-      if (k + 3 < my_bins)
-        mm_issue_info(sinfo_all + ((k + 3) % MB_NINFO) * MM_INFO, sunit_all + ((k + 3) % MB_NINFO) * MM_UNIT_STRIDE, a.row_info, a.bin_units,
-                      (cta + (k + 3) * ncta) * MM_BIN, a.N, tid);
-      mm_commit();
     }
-    mm_wait<0>();
   } else {
     // ================= math warps.  Entries [0, nent): query side; [nent, 2 nent): key side, handed out in this order through the
     // work counter that arrived (zero) with the unit list.  A key-side entry needs D of every query row of its window: it waits
@@ -1036,23 +815,20 @@ __global__ void __launch_bounds__(MM_THREADS, 1) sra_bwd_mma_kernel(MbArgs a) {
     // warp that finds the bin exhausted signals and moves on to bin k+1 without waiting for the others.
     const int g = lane >> 2;
     for (int k = 0; k < my_bins; ++k) {
-      const int bin = (cta + k * ncta) * MM_BIN;
       const int st = k % MB_STAGES;
-      const int4* sinfo = sinfo_all + (k % MB_NINFO) * MM_INFO;
-      const bf16* sq = sdata + st * MB_STAGE_ELEMS;
-      const bf16* sk = sq + MM_ARR;
-      const bf16* sv = sk + MM_ARR;
-      const bf16* sdo = sv + MM_ARR;
-      float* slse = sscal_all + st * 4 * MB_SCAL;
-      float* srq = slse + MB_SCAL;
-      float* srk = srq + MB_SCAL;
-      float* sD = srk + MB_SCAL;
+      int* sunit = sblock_all + st * MM_BLOCK_INTS;
+      const int4* sinfo = (const int4*)(sunit + MM_UNIT_STRIDE);      // records of rows row0 .. row0 + 127
+      const bf16* sq = sdata + st * MM_GROUPS * MB_GROUP;
+      const bf16* sk = sq + MM_BOX * MM_SLICE;
+      const bf16* sv = sk + MM_BOX * MM_SLICE;
+      const bf16* sdo = sv + MM_BOX * MM_SLICE;
+      float* slse = sscal_all + st * SCAL_STAGE;                      // [row][24]: lse | 1/|q| | 1/|k|
+      float* srq = slse + 8;
+      float* srk = slse + 16;
+      float* sD = slse + MB_SCAL;
       int* sdone = sdone_all + st * 512;
-      int* sunit = sunit_all + (k % MB_NINFO) * MM_UNIT_STRIDE;
       mbar_wait(&b_full[st], (k / MB_STAGES) & 1);
-      int row0, R;
-      mm_bin_range(sinfo, bin, a.N, row0, R);
-      const int shift = row0 - bin;
+      const int row0 = sunit[MM_UNITS + 2], R = sunit[MM_UNITS + 3];
       const int nent = sunit[MM_UNITS] * HS;
       for (;;) {
         int e = 0;
@@ -1062,32 +838,33 @@ __global__ void __launch_bounds__(MM_THREADS, 1) sra_bwd_mma_kernel(MbArgs a) {
         const bool key_side = e >= nent;
         if (key_side) e -= nent;
         const int code = sunit[e / HS];
-        const int h = e % HS;
+        const int h = e % HS, hg = lse_col + h;
         const int q0 = code & 127, qn = (code >> 7) & 31, k0 = (code >> 12) & 127, kn = (code >> 19) & 127;
-        const int4 recA = sinfo[min(q0 + g, R - 1) + shift], recB = sinfo[min(q0 + g + 8, R - 1) + shift];
+        const int4 recA = sinfo[min(q0 + g, R - 1)], recB = sinfo[min(q0 + g + 8, R - 1)];
         const int kbase = row0 + k0;
         if (!key_side) {
-          if (kn <= 16) dtau_acc += mb_unit_q<HD, 2>(a, sq, sk, sv, sdo, slse, srq, sD, q0, qn, k0, h, recA, recB, kbase, lane, col, inv_tau, inv_qs2);
-          else if (kn <= 32) dtau_acc += mb_unit_q<HD, 4>(a, sq, sk, sv, sdo, slse, srq, sD, q0, qn, k0, h, recA, recB, kbase, lane, col, inv_tau, inv_qs2);
-          else if (kn <= 48) dtau_acc += mb_unit_q<HD, 6>(a, sq, sk, sv, sdo, slse, srq, sD, q0, qn, k0, h, recA, recB, kbase, lane, col, inv_tau, inv_qs2);
-          else dtau_acc += mb_unit_q<HD, 8>(a, sq, sk, sv, sdo, slse, srq, sD, q0, qn, k0, h, recA, recB, kbase, lane, col, inv_tau, inv_qs2);
-          __threadfence_block();
-          __syncwarp();
-          if (lane == 0) atomicAdd(sdone + k0 * 4 + h, 1);
+          if (kn <= 16) dtau_acc += mb_unit_q<HD, 2>(a, sq, sk, sv, sdo, slse, srq, sD, sdone + k0 * 4 + h, q0, qn, k0, h, hg, recA, recB, kbase, lane, col, inv_tau, inv_qs2);
+          else if (kn <= 32) dtau_acc += mb_unit_q<HD, 4>(a, sq, sk, sv, sdo, slse, srq, sD, sdone + k0 * 4 + h, q0, qn, k0, h, hg, recA, recB, kbase, lane, col, inv_tau, inv_qs2);
+          else if (kn <= 48) dtau_acc += mb_unit_q<HD, 6>(a, sq, sk, sv, sdo, slse, srq, sD, sdone + k0 * 4 + h, q0, qn, k0, h, hg, recA, recB, kbase, lane, col, inv_tau, inv_qs2);
+          else dtau_acc += mb_unit_q<HD, 8>(a, sq, sk, sv, sdo, slse, srq, sD, sdone + k0 * 4 + h, q0, qn, k0, h, hg, recA, recB, kbase, lane, col, inv_tau, inv_qs2);
         } else {
           const int need = kn > 16 ? (kn + 15) >> 4 : 1;
           if (lane == 0) {
-            const volatile int* flag = sdone + k0 * 4 + h;
+            const unsigned flag = smem_u32(sdone + k0 * 4 + h);
             int spin = 0;
-            for (; *flag < need && spin < (1 << 20); ++spin) __nanosleep(32);   // bounded: a logic error must not hang the GPU
+            for (; spin < (1 << 20); ++spin) {                                   // bounded: a logic error must not hang the GPU
+              int v;
+              asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(flag) : "memory");
+              if (v >= need) break;
+              __nanosleep(32);
+            }
             if (spin == (1 << 20)) sra_wait_timed_out();
           }
           __syncwarp();
-          __threadfence_block();
-          if (kn <= 16) mb_unit_kv<HD, 2>(a, sq, sk, sv, sdo, slse, srk, sD, q0, qn, k0, h, recA, recB, kbase, lane, col);
-          else if (kn <= 32) mb_unit_kv<HD, 4>(a, sq, sk, sv, sdo, slse, srk, sD, q0, qn, k0, h, recA, recB, kbase, lane, col);
-          else if (kn <= 48) mb_unit_kv<HD, 6>(a, sq, sk, sv, sdo, slse, srk, sD, q0, qn, k0, h, recA, recB, kbase, lane, col);
-          else mb_unit_kv<HD, 8>(a, sq, sk, sv, sdo, slse, srk, sD, q0, qn, k0, h, recA, recB, kbase, lane, col);
+          if (kn <= 16) mb_unit_kv<HD, 2>(a, sq, sk, sv, sdo, slse, srk, sD, q0, qn, k0, h, hg, recA, recB, kbase, lane, col);
+          else if (kn <= 32) mb_unit_kv<HD, 4>(a, sq, sk, sv, sdo, slse, srk, sD, q0, qn, k0, h, hg, recA, recB, kbase, lane, col);
+          else if (kn <= 48) mb_unit_kv<HD, 6>(a, sq, sk, sv, sdo, slse, srk, sD, q0, qn, k0, h, hg, recA, recB, kbase, lane, col);
+          else mb_unit_kv<HD, 8>(a, sq, sk, sv, sdo, slse, srk, sD, q0, qn, k0, h, hg, recA, recB, kbase, lane, col);
         }
       }
       __syncwarp();
@@ -1105,17 +882,20 @@ __global__ void __launch_bounds__(MM_THREADS, 1) sra_bwd_mma_kernel(MbArgs a) {
   }
 }
 
+
 // =====================================================================================================
-// Work units of every 64-row bin, built once per window table (a table serves 2 encoder layers, forward and
-// backward) instead of by one warp of every CTA for every bin of every launch.  One warp per bin.
-// units[bin][0..47] = q0 | qn << 7 | k0 << 12 | kn << 19 (rows relative to the first window that starts in the bin),
-// [48] = number of units, [49] = 0 (the kernels' work counter lands on it), rest padding.
+// The per-bin table, built once per window table (a table serves 2 encoder layers, forward and backward) instead of by
+// one warp of every CTA for every bin of every launch.  One warp per 64-row bin writes the bin's BLOCK (576 ints):
+// [0..47] work units q0 | qn << 7 | k0 << 12 | kn << 19 (rows relative to the first window that starts in the bin),
+// [48] number of units, [49] 0 (the kernels' work counter lands on it), [50] first CSR row of the bin's windows, [51] their
+// row count, [64..575] the 128 row records (token, window start, window end, cell) from that first row on - everything a
+// CTA needs about a bin arrives with ONE bulk copy.
 __global__ void __launch_bounds__(256) sra_bin_units_kernel(const int4* __restrict__ row_info, int N, int* __restrict__ units) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nbins = (N + MM_BIN - 1) / MM_BIN;
   if (warp >= nbins) return;
   const int bin = warp * MM_BIN;
-  int* out = units + (long long)warp * MM_UNIT_STRIDE;
+  int* out = units + (long long)warp * MM_BLOCK_INTS;
   const int4 f = __ldg(row_info + bin);
   const int row0 = (f.y == bin) ? bin : f.z;
   int row1 = N;
@@ -1130,7 +910,9 @@ __global__ void __launch_bounds__(256) sra_bin_units_kernel(const int4* __restri
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
       const int r = 32 * w + lane;
-      const bool st = r < R && __ldg(row_info + row0 + min(r, R - 1)).y == row0 + r;
+      const int4 rec = __ldg(row_info + min(row0 + r, N - 1));
+      reinterpret_cast<int4*>(out + MM_UNIT_STRIDE)[r] = row0 + r < N ? rec : make_int4(0, 0, 0, 0);
+      const bool st = r < R && rec.y == row0 + r;
       const unsigned long long b = __ballot_sync(0xffffffffu, st);
       if (w < 2) m0 |= b << (32 * w);
       else m1 |= b << (32 * (w - 2));
@@ -1155,18 +937,37 @@ __global__ void __launch_bounds__(256) sra_bin_units_kernel(const int4* __restri
         s += n;
       }
     }
+  } else {
+#pragma unroll
+    for (int w = 0; w < 4; ++w) reinterpret_cast<int4*>(out + MM_UNIT_STRIDE)[32 * w + lane] = make_int4(0, 0, 0, 0);
   }
-  if (lane < MM_UNIT_STRIDE - MM_UNITS) out[MM_UNITS + lane] = lane == 0 ? nu : 0;
+  if (lane < MM_UNIT_STRIDE - MM_UNITS) out[MM_UNITS + lane] = lane == 0 ? nu : (lane == 2 ? row0 : (lane == 3 ? R : 0));
 }
 
-extern "C" size_t gdmae_sra_bin_units_bytes(int64_t N) { return (size_t)((N + MM_BIN - 1) / MM_BIN + 1) * MM_UNIT_STRIDE * 4; }
+// tok_info[token] = CSR row | in-window cell << 26: what the in-projection's epilogue needs per token (destination row of
+// the window-major layout, row of the positional LUT)
+__global__ void __launch_bounds__(256) sra_tok_info_kernel(const int4* __restrict__ row_info, int N, int* __restrict__ tok_info) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < N; r += gridDim.x * blockDim.x) {
+    const int4 f = __ldg(row_info + r);
+    tok_info[f.x] = r | (f.w << 26);
+  }
+}
 
-// bin_units (gdmae_sra_bin_units_bytes(N), 16-byte aligned) <- work units of the CSR rows described by row_info (N,4)
+static inline long long sra_units_ints(long long N) { return ((N + MM_BIN - 1) / MM_BIN + 1) * MM_BLOCK_INTS; }
+
+extern "C" size_t gdmae_sra_bin_units_bytes(int64_t N) { return (size_t)(sra_units_ints(N) + ((N + 3) & ~3ll)) * 4; }
+// offset (in int32 elements) of tok_info (N) inside the bin_units buffer
+extern "C" int64_t gdmae_sra_tok_info_offset(int64_t N) { return sra_units_ints(N); }
+
+// bin_units (gdmae_sra_bin_units_bytes(N), 16-byte aligned) <- per-bin blocks of the CSR rows described by row_info (N,4),
+// followed by tok_info (N)
 extern "C" int gdmae_sra_bin_units(const int32_t* row_info, int64_t N, int32_t* bin_units, void* stream_) {
-  GDMAE_CHECK_ARG(N >= 0 && N < (1ll << 27) && ((uintptr_t)row_info % 16) == 0 && ((uintptr_t)bin_units % 16) == 0);
+  GDMAE_CHECK_ARG(N >= 0 && N < (1ll << 26) && ((uintptr_t)row_info % 16) == 0 && ((uintptr_t)bin_units % 16) == 0);
   if (N == 0) return GDMAE_OK;
   const long long nbins = (N + MM_BIN - 1) / MM_BIN;
   sra_bin_units_kernel<<<(unsigned)((nbins * 32 + 255) / 256), 256, 0, (cudaStream_t)stream_>>>((const int4*)row_info, (int)N, bin_units);
+  GDMAE_LAUNCH_CHECK();
+  sra_tok_info_kernel<<<gdmae_grid(N, 256), 256, 0, (cudaStream_t)stream_>>>((const int4*)row_info, (int)N, bin_units + sra_units_ints(N));
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;
 }
@@ -1178,6 +979,81 @@ extern "C" int gdmae_sra_wait_timeouts(int* out) {
   GDMAE_CHECK_ARG(out != nullptr);
   GDMAE_CHECK_CUDA(cudaMemcpyFromSymbol(&v, g_sra_wait_timeouts, sizeof(v)));
   *out = (int)v;
+  return GDMAE_OK;
+}
+
+// ---- re-layout for callers that hold the flat (N, 3d) bf16 q | k | v (no biases, no positional term) of r1:
+// one warp per CSR row adds the LUT row, normalises q and k per head (fp32), folds log2(e)/tau into q and writes the
+// window-major tensors 0..2 + 1/|q|, 1/|k| into the row's record; optionally moves dO (N, d) into tensor 3 and lse (N, 8,
+// token order) into the record.  In the fused encoder layer the GEMM epilogues do this (tc_gemm.cu modes 4 / 5).
+// qkvdw[tensor][slice][row][64] bf16; lrr[row][24] fp32 = lse | 1/|q| | 1/|k|.
+template <int D>
+__global__ void __launch_bounds__(256) sra_prep_kernel(const bf16* __restrict__ qkv, const float* __restrict__ lut,
+                                                       const int4* __restrict__ row_info, const float* __restrict__ tau, float tau_min,
+                                                       int N, bf16* __restrict__ qkvdw, float* __restrict__ lrr,
+                                                       const bf16* __restrict__ dout, const float* __restrict__ lse_tok) {
+  constexpr int C = D / 32, NSL = D / 64;     // channels per lane: 4 lanes per head for both head sizes
+  const int lane = threadIdx.x & 31;
+  const int c0 = lane * C, sl = c0 >> 6, cw = c0 & 63;
+  const float qscale = qkv ? 1.4426950408889634f / fmaxf(__ldg(tau), tau_min) : 0.f;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < N; row += (gridDim.x * blockDim.x) >> 5) {
+    const int4 rec = __ldg(row_info + row);
+    const long long tok = rec.x;
+    if (qkv) {
+#pragma unroll
+      for (int part = 0; part < 3; ++part) {
+        float x[C];
+        const bf16* src = qkv + tok * 3 * D + part * D + c0;
+#pragma unroll
+        for (int i = 0; i < C; ++i) x[i] = __bfloat162float(src[i]);
+        if (part < 2) {
+          const float* l = lut + (long long)rec.w * 2 * D + part * D + c0;
+          float ss = 0.f;
+#pragma unroll
+          for (int i = 0; i < C; ++i) { x[i] += __ldg(l + i); ss = fmaf(x[i], x[i], ss); }
+          ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+          ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+          const float rn = rsqrtf(fmaxf(ss, 1e-24f));
+          if ((lane & 3) == 0) lrr[(long long)row * 24 + 8 + 8 * part + (lane >> 2)] = rn;
+          const float f = part == 0 ? rn * qscale : rn;
+#pragma unroll
+          for (int i = 0; i < C; ++i) x[i] *= f;
+        }
+        bf16* dst = qkvdw + ((long long)(part * NSL + sl) * N + row) * 64 + cw;
+#pragma unroll
+        for (int i = 0; i < C; i += 2) *reinterpret_cast<unsigned*>(dst + i) = pack_bf16(x[i], x[i + 1]);
+      }
+    }
+    if (dout) {
+      const bf16* src = dout + tok * D + c0;
+      bf16* dst = qkvdw + ((long long)(3 * NSL + sl) * N + row) * 64 + cw;
+#pragma unroll
+      for (int i = 0; i < C; i += 2) *reinterpret_cast<unsigned*>(dst + i) = *reinterpret_cast<const unsigned*>(src + i);
+    }
+    if (lse_tok && lane < 8) lrr[(long long)row * 24 + lane] = __ldg(lse_tok + tok * 8 + lane);
+  }
+}
+
+// (64 channels, N rows, d/64 slices, `tensors`) bf16 array, box 64 x 16 x 1 x tensors, SWIZZLE_128B; rows past N read as zero
+void* gdmae_tensor_map_encoder();   // tc_gemm.cu: cuTensorMapEncodeTiled from the driver, or nullptr
+static int sra_make_map(CUtensorMap* m, const void* ptr, long long N, int nsl, int tensors) {
+  typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  EncodeTiledFn enc = (EncodeTiledFn)gdmae_tensor_map_encoder();
+  if (!enc) { gdmae_set_error("cuTensorMapEncodeTiled is not available from the driver"); return GDMAE_ERR_CUDA; }
+  cuuint64_t dims[4] = {64, (cuuint64_t)N, (cuuint64_t)nsl, (cuuint64_t)tensors};
+  cuuint64_t strides[3] = {128, (cuuint64_t)N * 128, (cuuint64_t)N * 128 * nsl};
+  cuuint32_t box[4] = {64, MM_BOX, 1, (cuuint32_t)tensors};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char b[160];
+    snprintf(b, sizeof(b), "cuTensorMapEncodeTiled (sra) failed (%d): ptr %p N %lld slices %d tensors %d", (int)r, ptr, N, nsl, tensors);
+    gdmae_set_error(b);
+    return GDMAE_ERR_CUDA;
+  }
   return GDMAE_OK;
 }
 
@@ -1193,44 +1069,117 @@ static int mm_attrs() {
   return GDMAE_OK;
 }
 
-// Tensor-core variant of gdmae_sra_attention_fwd for bf16 q/k/v: qkv (N, 3d) bf16, otherwise the same arguments and outputs.
-extern "C" int gdmae_sra_attention_fwd_tc(const void* qkv_bf16, const float* lut, const int32_t* row_info, const int32_t* bin_units,
-                                          int64_t N, int d, int nhead, const float* tau, float tau_min, const float* bv, int io_bf16,
-                                          void* out, float* lse, void* stream_) {
+// Forward on the window-major layout: qkvw[tensor][slice][row][64] bf16 (q^ * log2(e)/tau, k^, v; rows in CSR order, as
+// tc_gemm mode 4 or the re-layout kernel writes them); out (N, d) token order, fp32 or bf16; lse: (N, 8) by token, or
+// (lse_by_row) columns 0..7 of the (N, 24) per-row records the backward reads.
+extern "C" int gdmae_sra_fwd_win(const void* qkvw, const int32_t* bin_units, int64_t N, int d, const float* bv, int out_bf16, void* out,
+                                 float* lse, int lse_by_row, void* stream_) {
   GDMAE_CHECK_ARG(bin_units != nullptr && ((uintptr_t)bin_units % 16) == 0);
-  GDMAE_CHECK_ARG(N >= 0 && N < (1ll << 27) && nhead == 8 && (d == 128 || d == 256));
-  GDMAE_CHECK_ARG(((uintptr_t)row_info % 16) == 0 && ((uintptr_t)qkv_bf16 % 16) == 0 && ((uintptr_t)lut % 8) == 0);
-  GDMAE_CHECK_ARG(bv == nullptr || ((uintptr_t)bv % 8) == 0);
+  GDMAE_CHECK_ARG(N >= 0 && N < (1ll << 26) && (d == 128 || d == 256));
+  GDMAE_CHECK_ARG(((uintptr_t)qkvw % 128) == 0 && (bv == nullptr || ((uintptr_t)bv % 8) == 0));
   if (N == 0) return GDMAE_OK;
   int rc = mm_attrs();
   if (rc) return rc;
-  MmArgs a{(const bf16*)qkv_bf16, lut, (const int4*)row_info, bin_units, tau, bv, tau_min, (int)N, d, io_bf16};
+  CUtensorMap tq;
+  rc = sra_make_map(&tq, qkvw, N, d / MM_SLICE, 3);
+  if (rc) return rc;
+  MmArgs a{bin_units, bv, (int)N, d, out_bf16, lse_by_row};
   cudaStream_t st = (cudaStream_t)stream_;
   // one CTA per SM; 148 is a multiple of the 2 (d = 128) and 4 (d = 256) channel slices
-  if (d == 128) sra_fwd_mma_kernel<16><<<GDMAE_NUM_SMS, MF_THREADS, MM_SMEM_BYTES, st>>>(a, out, lse);
-  else sra_fwd_mma_kernel<32><<<GDMAE_NUM_SMS, MF_THREADS, MM_SMEM_BYTES, st>>>(a, out, lse);
+  if (d == 128) sra_fwd_mma_kernel<16><<<GDMAE_NUM_SMS, MF_THREADS, MM_SMEM_BYTES, st>>>(tq, a, out, lse);
+  else sra_fwd_mma_kernel<32><<<GDMAE_NUM_SMS, MF_THREADS, MM_SMEM_BYTES, st>>>(tq, a, out, lse);
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;
 }
 
-// Tensor-core backward for bf16 tensors: qkv (N,3d), dout (N,d) and dqkv (N,3d) are bf16; lse (N,8) from the forward;
-// dtau_sum (1, double, caller zeroes) accumulates sum dS*S as gdmae_sra_attention_bwd does.  The value bias and the
-// forward output are not needed (sum_j P dP replaces dO.(o - bv)).
-extern "C" int gdmae_sra_attention_bwd_tc(const void* qkv_bf16, const float* lut, const int32_t* row_info, const int32_t* bin_units,
-                                          int64_t N, int d, int nhead, const float* tau, float tau_min, const float* lse,
-                                          const void* dout_bf16, void* dqkv_bf16, double* dtau_sum, void* stream_) {
+// Backward on the window-major layout: qkvdw = the forward's three tensors + dO as the fourth (tc_gemm mode 5 / re-layout);
+// lrr (N, 24) per-row records by CSR row: lse | 1/|q| | 1/|k|; dqkv (N, 3d) bf16 in token order; dtau_sum (1, double,
+// caller zeroes) accumulates sum dS*S.
+extern "C" int gdmae_sra_bwd_win(const void* qkvdw, const float* lrr, const int32_t* bin_units, int64_t N, int d, const float* tau,
+                                 float tau_min, void* dqkv_bf16, double* dtau_sum, void* stream_) {
   GDMAE_CHECK_ARG(bin_units != nullptr && ((uintptr_t)bin_units % 16) == 0);
-  GDMAE_CHECK_ARG(N >= 0 && N < (1ll << 27) && nhead == 8 && (d == 128 || d == 256));
-  GDMAE_CHECK_ARG(((uintptr_t)row_info % 16) == 0 && ((uintptr_t)qkv_bf16 % 16) == 0 && ((uintptr_t)lut % 8) == 0);
-  GDMAE_CHECK_ARG(((uintptr_t)dout_bf16 % 16) == 0 && ((uintptr_t)dqkv_bf16 % 16) == 0 && ((uintptr_t)lse % 4) == 0);
+  GDMAE_CHECK_ARG(N >= 0 && N < (1ll << 26) && (d == 128 || d == 256));
+  GDMAE_CHECK_ARG(((uintptr_t)qkvdw % 128) == 0 && ((uintptr_t)lrr % 32) == 0 && ((uintptr_t)dqkv_bf16 % 16) == 0);
   if (N == 0) return GDMAE_OK;
   int rc = mm_attrs();
   if (rc) return rc;
-  MbArgs a{(const bf16*)qkv_bf16, lut, (const int4*)row_info, bin_units, tau, lse, (const bf16*)dout_bf16, (bf16*)dqkv_bf16, dtau_sum, tau_min,
-           (int)N, d};
+  CUtensorMap tq;
+  rc = sra_make_map(&tq, qkvdw, N, d / MM_SLICE, 4);
+  if (rc) return rc;
+  MbArgs a{bin_units, tau, lrr, (bf16*)dqkv_bf16, dtau_sum, tau_min, (int)N, d};
   cudaStream_t st = (cudaStream_t)stream_;
-  if (d == 128) sra_bwd_mma_kernel<16><<<GDMAE_NUM_SMS, MM_THREADS, MB_SMEM_BYTES, st>>>(a);
-  else sra_bwd_mma_kernel<32><<<GDMAE_NUM_SMS, MM_THREADS, MB_SMEM_BYTES, st>>>(a);
+  if (d == 128) sra_bwd_mma_kernel<16><<<GDMAE_NUM_SMS, MM_THREADS, MB_SMEM_BYTES, st>>>(tq, a);
+  else sra_bwd_mma_kernel<32><<<GDMAE_NUM_SMS, MM_THREADS, MB_SMEM_BYTES, st>>>(tq, a);
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;
+}
+
+// workspace of the flat-layout entry points below: qkvdw (4, N, d) bf16 + lrr (N, 24) fp32
+extern "C" size_t gdmae_sra_tc_workspace_bytes(int64_t N, int d) {
+  const size_t n = (size_t)(N > 0 ? N : 1);
+  return gdmae_align(n * 4 * d * 2) + gdmae_align(n * 24 * 4) + 1024;
+}
+
+struct SraWs {
+  bf16* qkvdw;
+  float* lrr;
+};
+static int sra_carve(void* workspace, size_t ws_bytes, int64_t N, int d, SraWs* w) {
+  Workspace ws(workspace, ws_bytes);
+  w->qkvdw = ws.take<bf16>(N * 4 * d);
+  w->lrr = ws.take<float>(N * 24);
+  if (!w->lrr || ((uintptr_t)w->qkvdw % 128) != 0) { gdmae_set_error("sra tc: workspace too small or not 256-byte aligned (gdmae_sra_tc_workspace_bytes)"); return GDMAE_ERR_WORKSPACE; }
+  return GDMAE_OK;
+}
+
+// flat (N, 3d) bf16 q | k | v (nullable) -> tensors 0..2 of qkvdw + 1/|q|, 1/|k| in lrr; dout (N, d, nullable) -> tensor 3;
+// lse_tok (N, 8, nullable) -> lrr.  The stand-alone form of what the fused layer's GEMM epilogues do.
+extern "C" int gdmae_sra_relayout(const void* qkv_bf16, const float* lut, const int32_t* row_info, const float* tau, float tau_min,
+                                  int64_t N, int d, const void* dout_bf16, const float* lse_tok, void* qkvdw, float* lrr, void* stream_) {
+  GDMAE_CHECK_ARG(N >= 0 && N < (1ll << 26) && (d == 128 || d == 256) && ((uintptr_t)row_info % 16) == 0 && qkvdw && lrr);
+  GDMAE_CHECK_ARG(!qkv_bf16 || (lut && tau));
+  if (N == 0) return GDMAE_OK;
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (d == 128)
+    sra_prep_kernel<128><<<gdmae_grid(N * 32, 256), 256, 0, st>>>((const bf16*)qkv_bf16, lut, (const int4*)row_info, tau, tau_min, (int)N, (bf16*)qkvdw,
+                                                                  lrr, (const bf16*)dout_bf16, lse_tok);
+  else
+    sra_prep_kernel<256><<<gdmae_grid(N * 32, 256), 256, 0, st>>>((const bf16*)qkv_bf16, lut, (const int4*)row_info, tau, tau_min, (int)N, (bf16*)qkvdw,
+                                                                  lrr, (const bf16*)dout_bf16, lse_tok);
+  GDMAE_LAUNCH_CHECK();
+  return GDMAE_OK;
+}
+
+// Tensor-core variant of gdmae_sra_attention_fwd for the flat bf16 q/k/v: qkv (N, 3d) bf16, otherwise the same arguments
+// and outputs (lse by token); re-layout + window-major kernel.  workspace: gdmae_sra_tc_workspace_bytes(N, d).
+extern "C" int gdmae_sra_attention_fwd_tc(const void* qkv_bf16, const float* lut, const int32_t* row_info, const int32_t* bin_units,
+                                          int64_t N, int d, int nhead, const float* tau, float tau_min, const float* bv, int io_bf16,
+                                          void* out, float* lse, void* workspace, size_t ws_bytes, void* stream_) {
+  GDMAE_CHECK_ARG(N >= 0 && N < (1ll << 26) && nhead == 8 && (d == 128 || d == 256));
+  GDMAE_CHECK_ARG(((uintptr_t)qkv_bf16 % 16) == 0 && ((uintptr_t)lut % 8) == 0);
+  if (N == 0) return GDMAE_OK;
+  SraWs w;
+  int rc = sra_carve(workspace, ws_bytes, N, d, &w);
+  if (rc) return rc;
+  rc = gdmae_sra_relayout(qkv_bf16, lut, row_info, tau, tau_min, N, d, nullptr, nullptr, w.qkvdw, w.lrr, stream_);
+  if (rc) return rc;
+  return gdmae_sra_fwd_win(w.qkvdw, bin_units, N, d, bv, io_bf16, out, lse, 0, stream_);
+}
+
+// Tensor-core backward for the flat bf16 tensors: qkv (N,3d), dout (N,d) and dqkv (N,3d) are bf16; lse (N,8) by token from
+// the forward; dtau_sum (1, double, caller zeroes) accumulates sum dS*S as gdmae_sra_attention_bwd does.  The value bias
+// and the forward output are not needed (sum_j P dP replaces dO.(o - bv)).
+extern "C" int gdmae_sra_attention_bwd_tc(const void* qkv_bf16, const float* lut, const int32_t* row_info, const int32_t* bin_units,
+                                          int64_t N, int d, int nhead, const float* tau, float tau_min, const float* lse,
+                                          const void* dout_bf16, void* dqkv_bf16, double* dtau_sum, void* workspace, size_t ws_bytes,
+                                          void* stream_) {
+  GDMAE_CHECK_ARG(N >= 0 && N < (1ll << 26) && nhead == 8 && (d == 128 || d == 256));
+  GDMAE_CHECK_ARG(((uintptr_t)qkv_bf16 % 16) == 0 && ((uintptr_t)lut % 8) == 0 && ((uintptr_t)dout_bf16 % 16) == 0 && ((uintptr_t)lse % 4) == 0);
+  if (N == 0) return GDMAE_OK;
+  SraWs w;
+  int rc = sra_carve(workspace, ws_bytes, N, d, &w);
+  if (rc) return rc;
+  rc = gdmae_sra_relayout(qkv_bf16, lut, row_info, tau, tau_min, N, d, dout_bf16, lse, w.qkvdw, w.lrr, stream_);
+  if (rc) return rc;
+  return gdmae_sra_bwd_win(w.qkvdw, w.lrr, bin_units, N, d, tau, tau_min, dqkv_bf16, dtau_sum, stream_);
 }

@@ -50,6 +50,7 @@ struct TcgParams {
   const float* bias; void* C2; long long ldc2;
   const float* res; const float* gamma; const float* beta_ln; float eps; float* y32; void* y16; float* mean; float* rstd;
   const void* h16; long long ldh; float* colsum;      // GELU-backward epilogue
+  const int* tok_info; const float* lut; const float* tau; float tau_min; float* lrr; int plane0;   // window-major epilogues
 };
 
 __device__ unsigned int g_tcg_wait_timeouts;
@@ -281,7 +282,23 @@ __device__ __forceinline__ float unit_colsum(const uint8_t* buf, int lane) {
   return t;
 }
 
-enum { EPI_PLAIN = 0, EPI_GELU = 1, EPI_LN = 2, EPI_GELU_BWD = 3 };
+// staged bf16 unit -> the window-major array [plane][M rows][64] (sra_attention_tc.cu): the 32 columns starting at `col` of
+// row r go to row wrow(r) of plane plane0 + col / 64 - 64 contiguous bytes per row, 8 rows per warp instruction
+__device__ __forceinline__ void flush_bf16_win(uint8_t* buf, int lane, __nv_bfloat16* base, int plane0, int col, long long M, int wrow, bool valid) {
+  __syncwarp();
+  __nv_bfloat16* dst0 = base + (long long)(plane0 + (col >> 6)) * M * 64 + (col & 63);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = (lane >> 2) + 8 * i, j = lane & 3;
+    const uint4 val = *reinterpret_cast<const uint4*>(buf + bf16_slot(r, j));
+    const int wr = __shfl_sync(0xffffffffu, wrow, r);
+    const bool ok = __shfl_sync(0xffffffffu, (int)valid, r) != 0;
+    if (ok) *reinterpret_cast<uint4*>(dst0 + (long long)wr * 64 + j * 8) = val;
+  }
+  __syncwarp();
+}
+
+enum { EPI_PLAIN = 0, EPI_GELU = 1, EPI_LN = 2, EPI_GELU_BWD = 3, EPI_QKV_WIN = 4, EPI_ROWS_WIN = 5 };
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tcg_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -432,6 +449,68 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tcg_gemm_kernel(const __grid_c
             if (p.atomic) reduce_f32(buf, lane, &tmC, col0 + c * 32, r0);     // split-K partial tile: C += tile in the L2
             else flush_f32(buf, lane, reinterpret_cast<float*>(p.C), p.ldc, r0, col0 + c * 32, p.M);
           }
+        }
+      } else if (EPI == EPI_QKV_WIN) {
+        // in-projection of the attention (N = 3d, BN = d: the tile is 128 tokens of ONE of q, k, v).  q and k: + row of the
+        // positional LUT (pos_table [Wq;Wk]^T + [bq;bk], row = the token's in-window cell), L2 norm per head (the 32
+        // accumulator columns a thread holds are one head of 32 channels or two of 16), q also * log2(e) / tau; 1/|q|, 1/|k|
+        // go to the per-row records of the backward.  Rows leave as bf16 in CSR (window) order, one plane per (tensor, slice).
+        const int part = n_blk;
+        const bool valid = r0 + lane < p.M;
+        const int ti = valid ? __ldg(p.tok_info + r0 + lane) : 0;
+        const int wrow = ti & 0x3ffffff, cell = (ti >> 26) & 63;
+        const float qs = part == 0 ? 1.4426950408889634f / fmaxf(__ldg(p.tau), p.tau_min) : 1.f;
+        const int colp0 = half * HC;                  // first column of this warp inside the tensor
+        float4 pre[8];
+        if (part < 2) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int cl = __shfl_sync(0xffffffffu, cell, (lane >> 3) + 4 * i);
+            pre[i] = __ldg(reinterpret_cast<const float4*>(p.lut + (long long)cl * 2 * BN + part * BN + colp0) + (lane & 7));
+          }
+        }
+        mbar_wait(tfull + acc, acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < HC / 32; ++c) {
+          tmem_ld32(taddr + c * 32, v);
+          if (part < 2) {
+            add_prefetched(buf, lane, pre, v);
+            if (c + 1 < HC / 32) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int cl = __shfl_sync(0xffffffffu, cell, (lane >> 3) + 4 * i);
+                pre[i] = __ldg(reinterpret_cast<const float4*>(p.lut + (long long)cl * 2 * BN + part * BN + colp0 + (c + 1) * 32) + (lane & 7));
+              }
+            }
+            constexpr int HD = BN / 8, NH = 32 / HD;     // heads inside the 32 columns
+#pragma unroll
+            for (int hh = 0; hh < NH; ++hh) {
+              float ss = 0.f;
+#pragma unroll
+              for (int j = 0; j < HD; ++j) ss = fmaf(v[hh * HD + j], v[hh * HD + j], ss);
+              const float rn = rsqrtf(fmaxf(ss, 1e-24f));
+              if (valid) p.lrr[(long long)wrow * 24 + 8 + 8 * part + (colp0 + c * 32) / HD + hh] = rn;
+              const float f = rn * qs;
+#pragma unroll
+              for (int j = 0; j < HD; ++j) v[hh * HD + j] *= f;
+            }
+          }
+          stage_bf16(buf, lane, v);
+          flush_bf16_win(buf, lane, reinterpret_cast<__nv_bfloat16*>(p.C), part * (BN / 64), colp0 + c * 32, p.M, wrow, valid);
+        }
+      } else if (EPI == EPI_ROWS_WIN) {
+        // plain bf16 output whose rows leave in CSR (window) order into planes plane0 + column / 64 of the window-major array
+        // (dO of the attention: the out-projection's input gradient)
+        const bool valid = r0 + lane < p.M;
+        const int wrow = valid ? (__ldg(p.tok_info + r0 + lane) & 0x3ffffff) : 0;
+        mbar_wait(tfull + acc, acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < HC / 32; ++c) {
+          tmem_ld32(taddr + c * 32, v);
+          stage_bf16(buf, lane, v);
+          flush_bf16_win(buf, lane, reinterpret_cast<__nv_bfloat16*>(p.C), p.plane0, col0 + c * 32, p.M, wrow, valid);
         }
       } else if (EPI == EPI_GELU) {
         // C = h (pre-activation, kept for the backward pass), C2 = gelu(h + bias): both bf16
@@ -622,6 +701,9 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
 
 }  // namespace
 
+// cuTensorMapEncodeTiled from the driver (nullptr if unavailable) for the other TMA users of the library (sra_attention_tc.cu)
+void* gdmae_tensor_map_encoder() { return (void*)encode_fn(); }
+
 extern "C" int gdmae_tc_gemm_timeouts(int* out) {
   unsigned int v = 0;
   GDMAE_CHECK_CUDA(cudaMemcpyFromSymbol(&v, g_tcg_wait_timeouts, sizeof(v)));
@@ -637,9 +719,9 @@ extern "C" int gdmae_tc_gemm(int transa, int transb, int64_t M, int64_t N, int64
   GDMAE_CHECK_ARG(beta == 0.f || (beta == 1.f && c_dtype == 0));
   if (M == 0) return GDMAE_OK;
   const int mode = epi ? epi->mode : 0;
-  GDMAE_CHECK_ARG(mode >= 0 && mode <= 3);
+  GDMAE_CHECK_ARG(mode >= 0 && mode <= 5);
   GDMAE_CHECK_ARG(N % 64 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0);
-  GDMAE_CHECK_ARG(mode == EPI_LN || (C && ((uintptr_t)C & 15) == 0 && ldc % 8 == 0));
+  GDMAE_CHECK_ARG(mode == EPI_LN || (C && ((uintptr_t)C & 15) == 0 && (ldc % 8 == 0 || mode >= EPI_QKV_WIN)));
   GDMAE_CHECK_ARG(!transa || M % 64 == 0);           // MN-major A is loaded as 64-wide boxes
   cudaStream_t st = (cudaStream_t)stream_;
   int BN = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 64);
@@ -650,6 +732,13 @@ extern "C" int gdmae_tc_gemm(int transa, int transb, int64_t M, int64_t N, int64
   }
   if (mode == EPI_GELU_BWD)
     GDMAE_CHECK_ARG(epi->bias && epi->h16 && epi->colsum && c_dtype == 1 && N % 128 == 0 && epi->ldh % 8 == 0 && ((uintptr_t)epi->h16 & 15) == 0);
+  if (mode == EPI_QKV_WIN) {
+    // N = 3d with d in {128, 256}: one N tile per tensor
+    GDMAE_CHECK_ARG((N == 384 || N == 768) && c_dtype == 1 && !split_k_atomic && epi->tok_info && epi->lut && epi->tau && epi->lrr);
+    GDMAE_CHECK_ARG(((uintptr_t)epi->lut & 15) == 0 && M < (1ll << 26));
+    BN = (int)(N / 3);
+  }
+  if (mode == EPI_ROWS_WIN) GDMAE_CHECK_ARG(N % 128 == 0 && c_dtype == 1 && !split_k_atomic && epi->tok_info && epi->plane0 >= 0 && M < (1ll << 26));
   if (mode == EPI_GELU) GDMAE_CHECK_ARG(epi->bias && epi->c2 && c_dtype == 1 && N % 128 == 0 && epi->ldc2 % 8 == 0 && ((uintptr_t)epi->c2 & 15) == 0);
   TcgParams p = {};
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
@@ -678,6 +767,9 @@ extern "C" int gdmae_tc_gemm(int transa, int transb, int64_t M, int64_t N, int64
     p.bias = epi->bias; p.C2 = epi->c2; p.ldc2 = epi->ldc2; p.res = epi->res; p.gamma = epi->gamma; p.beta_ln = epi->beta_ln;
     p.eps = epi->eps; p.y32 = epi->y32; p.y16 = epi->y16; p.mean = epi->mean; p.rstd = epi->rstd;
     p.h16 = epi->h16; p.ldh = epi->ldh; p.colsum = epi->colsum;
+    if (mode >= EPI_QKV_WIN) {
+      p.tok_info = epi->tok_info; p.lut = epi->lut; p.tau = epi->tau; p.tau_min = epi->tau_min; p.lrr = epi->lrr; p.plane0 = epi->plane0;
+    }
   }
   CUtensorMap ta, tb, tc;
   int rc;
@@ -699,6 +791,14 @@ extern "C" int gdmae_tc_gemm(int transa, int transb, int64_t M, int64_t N, int64
     if (BN == 256) return launch<256, EPI_PLAIN>(ta, tb, tc, p, st);
     if (BN == 128) return launch<128, EPI_PLAIN>(ta, tb, tc, p, st);
     return launch<64, EPI_PLAIN>(ta, tb, tc, p, st);
+  }
+  if (mode == EPI_QKV_WIN) {
+    if (BN == 256) return launch<256, EPI_QKV_WIN>(ta, tb, tc, p, st);
+    return launch<128, EPI_QKV_WIN>(ta, tb, tc, p, st);
+  }
+  if (mode == EPI_ROWS_WIN) {
+    if (BN == 256) return launch<256, EPI_ROWS_WIN>(ta, tb, tc, p, st);
+    return launch<128, EPI_ROWS_WIN>(ta, tb, tc, p, st);
   }
   if (mode == EPI_GELU_BWD) {
     if (BN == 256) return launch<256, EPI_GELU_BWD>(ta, tb, tc, p, st);

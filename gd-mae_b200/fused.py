@@ -258,11 +258,12 @@ class EncoderLayerFunction(torch.autograd.Function):
         Nd, Nf = _r64(N * d), _r64(N * dff)
         # a, h, f (GEMM outputs that only feed a row kernel) are bf16 in the bf16 configuration: half the 32-bit words
         Na, Nh = (Nd // 2, Nf // 2) if bf else (Nd, Nf)
-        n32 = (0 if tc else 3 * Nd) + 2 * Na + Nh + Nd + _r64(N * 8) + 4 * _r64(N) + 128 * d + (0 if bf else Nd + Nf)
+        Nl = _r64(N * (24 if tc else 8))    # tensor-core SRA: per-row records lse | 1/|q| | 1/|k|
+        n32 = (0 if tc else 3 * Nd) + 2 * Na + Nh + Nd + Nl + 4 * _r64(N) + 128 * d + (0 if bf else Nd + Nf)
         save32 = torch.empty((max(n32, 1),), dtype=F32, device=dev)
         b = save32.data_ptr()
         off = 0
-        for name, n in (("qkv", 0 if tc else 3 * Nd), ("a", Na), ("x1", Nd), ("h", Nh), ("f", Na), ("lse", _r64(N * 8)), ("mean1", _r64(N)),
+        for name, n in (("qkv", 0 if tc else 3 * Nd), ("a", Na), ("x1", Nd), ("h", Nh), ("f", Na), ("lse", Nl), ("mean1", _r64(N)),
                         ("rstd1", _r64(N)), ("mean2", _r64(N)), ("rstd2", _r64(N)), ("lut", 128 * d)):
             setattr(A, name, b + 4 * off)
             off += n
@@ -270,7 +271,8 @@ class EncoderLayerFunction(torch.autograd.Function):
         A.x2 = x2.data_ptr()
         save16 = x2g = None
         if bf:
-            save16 = torch.empty((max(4 * Nd + Nf + (3 * Nd if tc else 0), 1),), dtype=BF16, device=dev)
+            # tensor-core SRA: window-major q^ | k^ | v (forward) | dO (backward) - N * d is a multiple of 64 elements (128 B)
+            save16 = torch.empty((max(4 * Nd + Nf + (4 * Nd if tc else 0), 1),), dtype=BF16, device=dev)
             b16 = save16.data_ptr()
             A.xg, A.o, A.x1g, A.x2g, A.g = b16, b16 + 2 * Nd, b16 + 4 * Nd, b16 + 6 * Nd, b16 + 8 * Nd
             if tc:
@@ -526,7 +528,8 @@ class TcEpilogue(ctypes.Structure):
     """mirror of gdmae_tc_epilogue (include/gdmae_b200.h)"""
     _fields_ = [("mode", ctypes.c_int), ("bias", _VP), ("c2", _VP), ("ldc2", ctypes.c_int64), ("res", _VP), ("gamma", _VP),
                 ("beta_ln", _VP), ("eps", ctypes.c_float), ("y32", _VP), ("y16", _VP), ("mean", _VP), ("rstd", _VP),
-                ("h16", _VP), ("ldh", ctypes.c_int64), ("colsum", _VP)]
+                ("h16", _VP), ("ldh", ctypes.c_int64), ("colsum", _VP), ("tok_info", _VP), ("lut", _VP), ("tau", _VP),
+                ("tau_min", ctypes.c_float), ("lrr", _VP), ("plane0", ctypes.c_int)]
 
 
 def tc_gemm(a, b, out=None, beta=0.0, out_dtype=F32, split_k=False, epilogue=None):

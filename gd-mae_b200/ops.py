@@ -333,8 +333,10 @@ def sra_fwd(qkv, lut, tau, table, tau_min, nhead, bv=None, out_dtype=torch.float
     # algorithmic bytes (SURVEY.md 8d, a18 minus projections): N*d*(3*s_in + s_out) + N*8
     with L.timed(f"sra_fwd_d{d}", N * d * (3 * qkv.element_size() + out.element_size()) + N * 8 * 4):
         if qkv.dtype == torch.bfloat16:
+            ws = L.workspace(L.lib().gdmae_sra_tc_workspace_bytes(L.i64(N), d), qkv.device)
             L.check(L.lib().gdmae_sra_attention_fwd_tc(L.P(qkv), L.P(lut), L.P(table.row_info), L.P(table.bin_units()), L.i64(N), d, nhead, L.P(tau),
-                                                       L.f32(tau_min), L.P(bv), _DT[out_dtype], L.P(out), L.P(lse), L.stream()),
+                                                       L.f32(tau_min), L.P(bv), _DT[out_dtype], L.P(out), L.P(lse), L.P(ws),
+                                                       ctypes.c_size_t(ws.numel()), L.stream()),
                     "gdmae_sra_attention_fwd_tc")
         else:
             L.check(L.lib().gdmae_sra_attention_fwd(L.P(qkv), L.P(lut), L.P(table.row_info), L.i64(N), d, nhead, L.P(tau),
@@ -353,8 +355,10 @@ def sra_bwd(qkv, lut, tau, table, tau_min, nhead, out, lse, dout, bv=None, io_dt
         assert dout.dtype == torch.bfloat16
         dqkv = torch.empty((N, d3), dtype=torch.bfloat16, device=qkv.device)
         with L.timed(f"sra_bwd_d{d}", N * d * (6 + 2 + 6) + N * 8 * 4):
+            ws = L.workspace(L.lib().gdmae_sra_tc_workspace_bytes(L.i64(N), d), qkv.device)
             L.check(L.lib().gdmae_sra_attention_bwd_tc(L.P(qkv), L.P(lut), L.P(table.row_info), L.P(table.bin_units()), L.i64(N), d, nhead, L.P(tau),
-                                                       L.f32(tau_min), L.P(lse), L.P(dout), L.P(dqkv), L.P(dtau_sum), L.stream()),
+                                                       L.f32(tau_min), L.P(lse), L.P(dout), L.P(dqkv), L.P(dtau_sum), L.P(ws),
+                                                       ctypes.c_size_t(ws.numel()), L.stream()),
                     "gdmae_sra_attention_bwd_tc")
         return dqkv, dtau_sum
     assert out.dtype == io_dtype

@@ -145,22 +145,44 @@ int gdmae_sra_attention_fwd(const float* qkv, const float* lut, const int32_t* r
                             const float* tau, float tau_min, const float* bv, int io_bf16, void* out, float* lse,
                             void* stream);
 /* same operator for bf16 q/k/v (qkv_bf16 (N,3d) bf16): QK^T and PV on the tensor cores (bf16 mma, fp32 accumulate,
- * softmax in fp32), persistent cp.async-pipelined kernel; other arguments and outputs as above */
+ * softmax in fp32).  Flat-layout entry point: a re-layout kernel (+ LUT, per-head L2 norm, log2(e)/tau folded into q,
+ * rows moved to CSR order) followed by the window-major kernel below; workspace gdmae_sra_tc_workspace_bytes(N, d);
+ * other arguments and outputs as above */
+size_t gdmae_sra_tc_workspace_bytes(int64_t N, int d);
 int gdmae_sra_attention_fwd_tc(const void* qkv_bf16, const float* lut, const int32_t* row_info, const int32_t* bin_units,
                                int64_t N, int d, int nhead, const float* tau, float tau_min, const float* bv, int io_bf16,
-                               void* out, float* lse, void* stream);
+                               void* out, float* lse, void* workspace, size_t ws_bytes, void* stream);
 /* work units of the tensor-core kernels, built once per window table: bin_units (gdmae_sra_bin_units_bytes(N) bytes,
  * 16-byte aligned) <- for every 64-row bin of the CSR rows the packed (query tile, key range) units of the windows that
- * start in the bin (a run of whole small windows totalling <= 16 rows, or a 16-row chunk of a larger window) */
+ * start in the bin (a run of whole small windows totalling <= 16 rows, or a 16-row chunk of a larger window), the
+ * bin's first row / row count and a copy of its 128 row records (one 2304-byte block per bin = one bulk copy); followed, at int32 offset gdmae_sra_tok_info_offset(N), by tok_info (N): CSR row |
+ * in-window cell << 26 per token (read by the in-projection epilogue, gdmae_tc_gemm mode 4) */
 /* the kernels' internal waits are bounded; *out <- how many ran out since load (device sync; must be 0) */
 int gdmae_sra_wait_timeouts(int* out);
 size_t gdmae_sra_bin_units_bytes(int64_t N);
+int64_t gdmae_sra_tok_info_offset(int64_t N);
 int gdmae_sra_bin_units(const int32_t* row_info, int64_t N, int32_t* bin_units, void* stream);
 /* tensor-core backward for bf16 tensors: qkv (N,3d), dout (N,d), dqkv (N,3d) all bf16; needs neither the forward
- * output nor the value bias */
+ * output nor the value bias; workspace as the forward */
 int gdmae_sra_attention_bwd_tc(const void* qkv_bf16, const float* lut, const int32_t* row_info, const int32_t* bin_units,
                                int64_t N, int d, int nhead, const float* tau, float tau_min, const float* lse,
-                               const void* dout_bf16, void* dqkv_bf16, double* dtau_sum, void* stream);
+                               const void* dout_bf16, void* dqkv_bf16, double* dtau_sum, void* workspace, size_t ws_bytes,
+                               void* stream);
+/* the same kernels on the WINDOW-MAJOR layout the fused encoder layer uses (r2): qkvw[tensor][d/64 slices][N rows][64]
+ * bf16 holding q^ * log2(e)/tau, k^ (positional term added, L2-normalised per head) and v with rows in CSR (window)
+ * order - written by the in-projection GEMM's epilogue (gdmae_tc_gemm mode 4), so that a bin of windows is a rectangle
+ * per tensor and arrives by TMA (one cp.async.bulk.tensor box per 16 rows) instead of per-row gathers.  out (N, d) token
+ * order; lse (N, 8) by token, or (lse_by_row) columns 0..7 of lrr.  Backward: qkvdw = the same array with dO as a fourth
+ * tensor (gdmae_tc_gemm mode 5); lrr (N, 24) fp32 per-row records by CSR row = lse | 1/|q| | 1/|k| (8 heads each);
+ * dqkv (N, 3d) bf16 in token order. */
+/* flat -> window-major: qkv_bf16 (N, 3d, nullable) -> tensors 0..2 of qkvdw and 1/|q|, 1/|k| in lrr; dout_bf16 (N, d,
+ * nullable) -> tensor 3; lse_tok (N, 8, token order, nullable) -> lrr.  What modes 4 / 5 do inside the fused layer. */
+int gdmae_sra_relayout(const void* qkv_bf16, const float* lut, const int32_t* row_info, const float* tau, float tau_min,
+                       int64_t N, int d, const void* dout_bf16, const float* lse_tok, void* qkvdw, float* lrr, void* stream);
+int gdmae_sra_fwd_win(const void* qkvw, const int32_t* bin_units, int64_t N, int d, const float* bv, int out_bf16, void* out,
+                      float* lse, int lse_by_row, void* stream);
+int gdmae_sra_bwd_win(const void* qkvdw, const float* lrr, const int32_t* bin_units, int64_t N, int d, const float* tau,
+                      float tau_min, void* dqkv_bf16, double* dtau_sum, void* stream);
 int gdmae_sra_attention_bwd(const float* qkv, const float* lut, const int32_t* row_info, int64_t N, int d, int nhead,
                             const float* tau, float tau_min, const float* bv, int io_bf16, const void* out,
                             const float* lse, const float* dout, void* dqkv, double* dtau_sum, float* work_D,
@@ -253,10 +275,10 @@ typedef struct gdmae_encoder_layer_args {
   const void *w_in_g, *w_o_g, *w1_g, *w2_g;
   /* activations written by forward and read by backward */
   void* xg;                  /* (N,d) op; used when xg_in == NULL and gemm_mode == 1 */
-  void* qkv;                 /* (N,3d) fp32, or bf16 when sra_tensor_cores */
+  void* qkv;                 /* (N,3d) fp32; when sra_tensor_cores: (4, d/64, N, 64) bf16 window-major q^ | k^ | v | dO (gdmae_sra_fwd_win) */
   float* lut;                /* (64,2d) */
   void* o;                   /* (N,d) op */
-  float* lse;                /* (N,8) */
+  float* lse;                /* (N,8); when sra_tensor_cores: (N,24) per-row records lse | 1/|q| | 1/|k| by CSR row */
   void* a;                   /* (N,d) out-projection output: fp32, bf16 when gemm_mode == 1 */
   float* x1;                 /* (N,d) */
   void* x1g;                 /* (N,d) op (bf16 mode only) */
@@ -298,6 +320,11 @@ int gdmae_gemm(int transa, int transb, int64_t M, int64_t N, int64_t K, const vo
  *                                                                                     - out_proj / linear2 + residual + norm, :78-83
  *   mode 3  acc = gradient w.r.t. gelu(h + bias): C = acc * gelu'(h16 + bias) (bf16) and colsum (N, fp32) += its column sums
  *                                                                                     - backward of linear1's bias + GELU
+ *   mode 4  in-projection of the attention, N = 3d: q / k tiles += lut[cell(token)], L2-normalised per head (q also
+ *           * log2(e)/max(tau, tau_min)), 1/|q|, 1/|k| -> lrr; q^, k^, v rows (bf16) go to C = the window-major array
+ *           [tensor][d/64][M][64] at the token's CSR row (gdmae_sra_fwd_win's operand)       - cosine_msa.py:57-62,114-140
+ *   mode 5  C = window-major array: bf16 rows of the (M, N) result go to planes plane0 + column/64 at the token's CSR row
+ *           (dO of the attention, plane0 = 3 d/64)
  * replaces F.linear of cosine_msa.py:57-62,431 / sst_basic_block.py:77-84 and the spconv / deblock / VFE GEMMs. */
 typedef struct gdmae_tc_epilogue {
   int mode;
@@ -315,6 +342,12 @@ typedef struct gdmae_tc_epilogue {
   const void* h16;           /* mode 3: (M, ldh) bf16 pre-activation saved by mode 1 */
   int64_t ldh;
   float* colsum;             /* mode 3: (N) fp32, accumulated into */
+  const int32_t* tok_info;   /* modes 4, 5: (M) CSR row | cell << 26 per token (gdmae_sra_bin_units) */
+  const float* lut;          /* mode 4: (64, 2d) positional LUT incl. the q / k biases */
+  const float* tau;          /* mode 4: (1) temperature parameter */
+  float tau_min;
+  float* lrr;                /* mode 4: (M, 24) per-row records: 1/|q| -> columns 8..15, 1/|k| -> 16..23 */
+  int plane0;                /* mode 5: first destination plane */
 } gdmae_tc_epilogue;
 int gdmae_tc_gemm(int transa, int transb, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
                   int64_t ldb, void* C, int64_t ldc, int c_dtype, float beta, int split_k_atomic,

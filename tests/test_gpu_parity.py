@@ -542,17 +542,30 @@ def test_sra_bin_units_cover_every_row(G, golden):
         for shifted in (0, 1):
             t = G.ops.window_table(idx.contiguous().cuda(), B, Y, X, shifted)
             N = t.N
-            units = t.bin_units().cpu().view(-1, 64)
-            info = t.row_info.cpu()
-            start, end = info[:, 1].long(), info[:, 2].long()                    # window extent [start, end) of every CSR row
             nbins = (N + 63) // 64
+            raw = t.bin_units().cpu()
+            off = int(G.pkg._lib.lib().gdmae_sra_tok_info_offset(G.pkg._lib.i64(N)))
+            blocks = raw[:off].view(-1, 576)                                     # per bin: 64 ints of units | 128 row records
+            units = blocks[:, :64]
+            info = t.row_info.cpu()
+            # tok_info (N) after the blocks: CSR row | cell << 26 per token
+            tok_info = raw[off:off + N].long()
+            rows_of_tok = torch.empty(N, dtype=torch.long)
+            rows_of_tok[info[:, 0].long()] = torch.arange(N)
+            assert torch.equal(tok_info & 0x3ffffff, rows_of_tok)
+            assert torch.equal((tok_info >> 26) & 63, t.pos_of_token.cpu().long())
+            start, end = info[:, 1].long(), info[:, 2].long()                    # window extent [start, end) of every CSR row
             assert units.shape[0] >= nbins
             seen = torch.zeros(N, dtype=torch.int32)
             for b in range(nbins):
                 bin0 = 64 * b
                 row0 = bin0 if int(start[bin0]) == bin0 else int(end[bin0])      # first window that starts in the bin
+                row1 = N if bin0 + 64 >= N else (bin0 + 64 if int(start[bin0 + 64]) == bin0 + 64 else int(end[bin0 + 64]))
                 nu = int(units[b, 48])
                 assert 0 <= nu <= 48 and int(units[b, 49]) == 0
+                assert int(units[b, 50]) == row0 and int(units[b, 51]) == max(row1 - row0, 0)
+                nrec = min(128, N - row0)                                        # the block carries the records from row0 on
+                assert torch.equal(blocks[b, 64:64 + 4 * nrec].view(-1, 4), info[row0:row0 + nrec])
                 for u in range(nu):
                     code = int(units[b, u])
                     q0, qn, k0, kn = code & 127, (code >> 7) & 31, (code >> 12) & 127, (code >> 19) & 127
