@@ -57,15 +57,21 @@
 #define MM_HEADS_PER_ENTRY(HD) ((HD) == 16 ? 2 : 1)
 #endif
 #define MM_MATH_WARPS (MF_THREADS / 32 - 1)
-#ifndef MM_STAGES
-#define MM_STAGES 3
+// Staging memory is a RING of 16-row groups, not worst-case (144-row) stages: a bin takes ceil(rows / 16) consecutive groups
+// (4.5 on average), so ~7 bins are in flight in the forward kernel instead of 3.  r2 measurement: with 3 stages the period
+// per bin was (release -> issue -> landing -> slowest entry) / 3 = ~3000 cycles whatever the math per bin - a latency-bound
+// pipeline; the 16 MMA-overrun rows behind a bin's last group may belong to a neighbour (masked, only finite values needed).
+#ifndef MF_SLOTS
+#define MF_SLOTS 8             // forward: bins in flight (table block + barriers per slot)
+#endif
+#ifndef MF_RING
+#define MF_RING 33             // forward: groups of the ring (+ 1 never-written pad group behind it)
 #endif
 #define MM_UNITS 48
 #define MM_UNIT_STRIDE 64      // ints of the unit list: [0, 48) units, [48] count, [49] work counter (0), [50] first row, [51] rows, pad
 #define MM_BLOCK_INTS (MM_UNIT_STRIDE + 4 * MM_INFO)   // per-bin block of the table: unit list + the 128 row records from the bin's first row (2304 B)
 #define MM_RR_SLOTS 256        // (first row, rows) of a CTA's first bins, preloaded into shared memory
-#define MM_STAGE_BYTES (MM_GROUPS * MF_GROUP * 2 + MM_BLOCK_INTS * 4)
-#define MM_SMEM_BYTES (MM_STAGES * MM_STAGE_BYTES + MM_RR_SLOTS * 8 + 2 * MM_STAGES * 8 + 1024)
+#define MM_SMEM_BYTES ((MF_RING + 1) * MF_GROUP * 2 + MF_SLOTS * (MM_BLOCK_INTS * 4 + 8 + 16) + MM_RR_SLOTS * 8 + 1024)
 
 typedef __nv_bfloat16 bf16;
 
@@ -101,12 +107,15 @@ __device__ __noinline__ void sra_wait_timed_out() {
 // waits for the completion of the phase with the given parity.  try_wait carries a suspend-time hint: the warp sleeps in
 // hardware until the phase completes (a polling loop without it was measured to burn a third of the SM's issue slots and
 // starve the producer warps).  Bounded (about a second) so that a logic error ends in a trapped launch, not in a hung GPU.
+#ifndef MM_WAIT_HINT
+#define MM_WAIT_HINT 20000u
+#endif
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
   const unsigned addr = smem_u32(bar);
-  for (int spin = 0; spin < 50000; ++spin) {
+  for (int spin = 0; spin < 50000 * (20000u / MM_WAIT_HINT); ++spin) {
     unsigned ok;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(addr), "r"(parity), "r"(20000u) : "memory");
+                 : "=r"(ok) : "r"(addr), "r"(parity), "r"(MM_WAIT_HINT) : "memory");
     if (ok) return;
   }
   sra_wait_timed_out();
@@ -169,7 +178,7 @@ __device__ __forceinline__ unsigned mm_bits(unsigned long long m0, unsigned long
 // One unit and NH adjacent heads on one warp: S = Q K^T, masked softmax, O = P V, for NT2 8-key tiles (NT2 even).  The NH
 // heads are independent instruction streams over the same rows and masks; every step is written as a loop over the heads
 // so that their dependency chains (ldmatrix -> mma -> shuffle -> exp2 -> mma) overlap in the one warp.
-template <int HD, int NT2, int NH>
+template <int HD, int NT2, int NH, int FUSED>
 __device__ __forceinline__ void mm_unit(const MmArgs& a, const bf16* sq, const bf16* sk, const bf16* sv, int q0, int qn, int k0,
                                         int ch, int4 recA, int4 recB, int kbase, int rowbase, int lane, long long out_col, int lse_col,
                                         void* __restrict__ out, float* __restrict__ lse) {
@@ -301,13 +310,13 @@ __device__ __forceinline__ void mm_unit(const MmArgs& a, const bf16* sq, const b
 #pragma unroll
         for (int nd = 0; nd < ND; ++nd) {
           const float x0 = fmaf(o[hh][nd][2 * half], il, bias[nd].x), x1 = fmaf(o[hh][nd][2 * half + 1], il, bias[nd].y);
-          if (a.out_bf16) *reinterpret_cast<unsigned*>((bf16*)out + e0 + 8 * nd) = pack_bf16(x0, x1);
+          if (FUSED || a.out_bf16) *reinterpret_cast<unsigned*>((bf16*)out + e0 + 8 * nd) = pack_bf16(x0, x1);
           else *reinterpret_cast<float2*>((float*)out + e0 + 8 * nd) = make_float2(x0, x1);
         }
         // natural-log lse of the scores S = cos / tau (the backward kernels expect it)
         // (lse_by_row: indexed by CSR row - the layout the window-major backward reads with one bulk copy per bin)
         if (t == 0)
-          lse[(a.lse_by_row ? (long long)(rowbase + g + 8 * half) * 24 : (long long)tok * 8) + lse_col + hh] =
+          lse[((FUSED || a.lse_by_row) ? (long long)(rowbase + g + 8 * half) * 24 : (long long)tok * 8) + lse_col + hh] =
               ((half ? mx1[hh] : mx0[hh]) + __log2f(half ? l1[hh] : l0[hh])) * 0.6931471805599453f;
       }
     }
@@ -329,16 +338,19 @@ extern "C" int gdmae_sra_prof_read(unsigned long long* out16, int reset) {
 #endif
 
 // tmQ: (64 channels, N rows, d/64 slices, 3 tensors) bf16 view of the window-major q^ | k^ | v, box 64 x 16 x 1 x 3, SWIZZLE_128B
-template <int HD>
+// FUSED = 1: bf16 output and lse into the per-row records (the encoder layer's call) as compile-time facts
+template <int HD, int FUSED>
 __global__ void __launch_bounds__(MF_THREADS, 1) sra_fwd_mma_kernel(const __grid_constant__ CUtensorMap tmQ, MmArgs a, void* __restrict__ out,
                                                                     float* __restrict__ lse) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);   // swizzled boxes: 1024-byte aligned
-  bf16* sdata = (bf16*)smem_raw;                              // MM_STAGES x 9 groups x {q, k, v} x [16][64]
-  int* sblock_all = (int*)(sdata + MM_STAGES * MM_GROUPS * MF_GROUP);   // MM_STAGES x { unit list (64 ints) | 128 row records }
-  int2* s_rr = (int2*)(sblock_all + MM_STAGES * MM_BLOCK_INTS);         // (first row, rows) of this CTA's bins
+  bf16* sdata = (bf16*)smem_raw;                              // ring: (MF_RING + 1) groups x {q, k, v} x [16][64]
+  int* sblock_all = (int*)(sdata + (MF_RING + 1) * MF_GROUP); // MF_SLOTS x { unit list (64 ints) | 128 row records }
+  int2* s_rr = (int2*)(sblock_all + MF_SLOTS * MM_BLOCK_INTS);          // (first row, rows) of this CTA's bins
   unsigned long long* s_full = (unsigned long long*)(s_rr + MM_RR_SLOTS);   // bin landed
-  unsigned long long* s_empty = s_full + MM_STAGES;                         // bin consumed
+  unsigned long long* s_empty = s_full + MF_SLOTS;                          // bin consumed
+  int* s_base = (int*)(s_empty + MF_SLOTS);                   // first ring group of the slot's bin
+  int* s_alloc = s_base + MF_SLOTS;                           // groups the slot's bin holds (producer only)
   constexpr int HS = MM_SLICE / HD;
   const int d = a.d;
   const int nsl = d / MM_SLICE;
@@ -353,10 +365,10 @@ __global__ void __launch_bounds__(MF_THREADS, 1) sra_fwd_mma_kernel(const __grid
   // ---- prologue: (first row, rows) of the CTA's bins, zeroed data buffers (overrun rows must hold finite values), barriers
   if (tid < MM_RR_SLOTS && tid < my_bins)
     s_rr[tid] = __ldg(reinterpret_cast<const int2*>(a.bin_units + (long long)(cta + tid * ncta) * MM_BLOCK_INTS + MM_UNITS + 2));
-  for (int i = tid; i < MM_STAGES * MM_GROUPS * MF_GROUP / 8; i += MF_THREADS) reinterpret_cast<uint4*>(sdata)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < (MF_RING + 1) * MF_GROUP / 8; i += MF_THREADS) reinterpret_cast<uint4*>(sdata)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
 #pragma unroll
-    for (int st = 0; st < MM_STAGES; ++st) {
+    for (int st = 0; st < MF_SLOTS; ++st) {
       mbar_init(&s_full[st], 1);                 // the producer's expect_tx arrival + the bytes of its copies
       mbar_init(&s_empty[st], MM_MATH_WARPS);    // every math warp arrives once it has no more work in the bin
     }
@@ -367,22 +379,43 @@ __global__ void __launch_bounds__(MF_THREADS, 1) sra_fwd_mma_kernel(const __grid
   MM_PROF_T(k1_);
 
   if (warp == 0) {
-    // ================= producer (one thread): bin j into stage j % MM_STAGES as soon as the math warps have released
-    // bin j - MM_STAGES.  One transaction per bin: the bin's block of the table (unit list incl. the zeroed work counter +
-    // row records) and one box per 16 rows (q^, k^ and v together).
+    // ================= producer (one thread): bin j takes slot j % MF_SLOTS and ceil(rows / 16) consecutive groups of the
+    // ring (allocated in FIFO order, never split across the end of the ring), as soon as the math warps have released
+    // enough of the oldest bins.  One transaction per bin: the bin's block of the table (unit list incl. the zeroed work
+    // counter + row records) and one box per 16 rows (q^, k^ and v together).
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&tmQ) : "memory");
+      int head = 0, used = 0, tail = 0;          // next free group, groups held by the bins tail .. j-1, oldest unreclaimed bin
       for (int j = 0; j < my_bins; ++j) {
-        const int bi = cta + j * ncta, st = j % MM_STAGES;
+        const int bi = cta + j * ncta, st = j % MF_SLOTS;
         const int2 rr = j < MM_RR_SLOTS ? s_rr[j]
                                         : __ldg(reinterpret_cast<const int2*>(a.bin_units + (long long)bi * MM_BLOCK_INTS + MM_UNITS + 2));
-        MM_PROF_T(t0);
-        if (j >= MM_STAGES) mbar_wait(&s_empty[st], ((j / MM_STAGES) - 1) & 1);
-        MM_PROF_T(t1);
         const int row0 = rr.x, nbox = (rr.y + MM_BOX - 1) / MM_BOX;
+        MM_PROF_T(t0);
+        int need;
+        for (;;) {
+          need = nbox + (head + nbox > MF_RING ? MF_RING - head : 0);   // the tail of the ring is skipped (and held) if the bin does not fit
+          if (j - tail < MF_SLOTS && used + need <= MF_RING) break;
+          mbar_wait(&s_empty[tail % MF_SLOTS], (tail / MF_SLOTS) & 1);
+          used -= s_alloc[tail % MF_SLOTS];
+          ++tail;
+        }
+        MM_PROF_T(t1);
+        const int start = head + nbox > MF_RING ? 0 : head;
+        head = start + nbox;
+        used += need;
+        s_alloc[st] = need;
+        s_base[st] = start;
+#ifdef MM_DEBUG_NO_COPY
+        mbar_expect_tx(&s_full[st], (unsigned)((j < 8 ? nbox * MF_GROUP * 2 : 0) + MM_BLOCK_INTS * 4));
+#else
         mbar_expect_tx(&s_full[st], (unsigned)(nbox * MF_GROUP * 2 + MM_BLOCK_INTS * 4));
+#endif
         bulk_copy(sblock_all + st * MM_BLOCK_INTS, a.bin_units + (long long)bi * MM_BLOCK_INTS, MM_BLOCK_INTS * 4, &s_full[st]);
-        bf16* tile = sdata + st * MM_GROUPS * MF_GROUP;
+        bf16* tile = sdata + start * MF_GROUP;
+#ifdef MM_DEBUG_NO_COPY
+        if (j < 8)      // development build: math on whatever the first bins left in the ring
+#endif
         for (int i = 0; i < nbox; ++i) tma_box(tile + i * MF_GROUP, &tmQ, &s_full[st], row0 + i * MM_BOX, sl);
 #ifdef MM_PROFILE
         MM_PROF_T(t2);
@@ -395,15 +428,15 @@ __global__ void __launch_bounds__(MF_THREADS, 1) sra_fwd_mma_kernel(const __grid
     // work counter; a warp that finds the bin exhausted signals and moves on to bin j+1 without waiting for the others
     const int g = lane >> 2;
     for (int j = 0; j < my_bins; ++j) {
-      const int st = j % MM_STAGES;
+      const int st = j % MF_SLOTS;
       int* sunit = sblock_all + st * MM_BLOCK_INTS;
       const int4* sinfo = (const int4*)(sunit + MM_UNIT_STRIDE);      // records of rows row0 .. row0 + 127
-      const bf16* sq = sdata + st * MM_GROUPS * MF_GROUP;
+      MM_PROF_T(m0);
+      mbar_wait(&s_full[st], (j / MF_SLOTS) & 1);
+      MM_PROF_T(m1);
+      const bf16* sq = sdata + s_base[st] * MF_GROUP;
       const bf16* sk = sq + MM_BOX * MM_SLICE;
       const bf16* sv = sk + MM_BOX * MM_SLICE;
-      MM_PROF_T(m0);
-      mbar_wait(&s_full[st], (j / MM_STAGES) & 1);
-      MM_PROF_T(m1);
 #ifdef MM_PROFILE
       int n_done = 0;
 #endif
@@ -431,14 +464,14 @@ __global__ void __launch_bounds__(MF_THREADS, 1) sra_fwd_mma_kernel(const __grid
         const int kbase = row0 + k0, rowbase = row0 + q0;
         const long long oc = col + ch;
         const int lc = sl * HS + h;
-        if (kn <= 16) mm_unit<HD, 2, HPE>(a, sq, sk, sv, q0, qn, k0, ch, recA, recB, kbase, rowbase, lane, oc, lc, out, lse);
-        else if (kn <= 32) mm_unit<HD, 4, HPE>(a, sq, sk, sv, q0, qn, k0, ch, recA, recB, kbase, rowbase, lane, oc, lc, out, lse);
+        if (kn <= 16) mm_unit<HD, 2, HPE, FUSED>(a, sq, sk, sv, q0, qn, k0, ch, recA, recB, kbase, rowbase, lane, oc, lc, out, lse);
+        else if (kn <= 32) mm_unit<HD, 4, HPE, FUSED>(a, sq, sk, sv, q0, qn, k0, ch, recA, recB, kbase, rowbase, lane, oc, lc, out, lse);
         else {
           // large windows: one head at a time (the two-head body would spill at the register cap)
 #pragma unroll 1
           for (int hh = 0; hh < HPE; ++hh) {
-            if (kn <= 48) mm_unit<HD, 6, 1>(a, sq, sk, sv, q0, qn, k0, ch + hh * HD, recA, recB, kbase, rowbase, lane, oc + hh * HD, lc + hh, out, lse);
-            else mm_unit<HD, 8, 1>(a, sq, sk, sv, q0, qn, k0, ch + hh * HD, recA, recB, kbase, rowbase, lane, oc + hh * HD, lc + hh, out, lse);
+            if (kn <= 48) mm_unit<HD, 6, 1, FUSED>(a, sq, sk, sv, q0, qn, k0, ch + hh * HD, recA, recB, kbase, rowbase, lane, oc + hh * HD, lc + hh, out, lse);
+            else mm_unit<HD, 8, 1, FUSED>(a, sq, sk, sv, q0, qn, k0, ch + hh * HD, recA, recB, kbase, rowbase, lane, oc + hh * HD, lc + hh, out, lse);
           }
         }
       }
@@ -467,8 +500,8 @@ __global__ void __launch_bounds__(MF_THREADS, 1) sra_fwd_mma_kernel(const __grid
 
 // =====================================================================================================
 // Backward.  Same bins, packing, tiles and producer / math decoupling as the forward kernel; four staged tiles
-// (Qs = q_hat * log2(e)/tau, K_hat, V, dO - all window-major, one TMA box per 16 rows) in two stages, the per-row records
-// (lse, 1/|q|, 1/|k| as the forward pass left them, CSR-row order: one bulk copy per bin) and D per stage:
+// (Qs = q_hat * log2(e)/tau, K_hat, V, dO - all window-major, one TMA box per 16 rows) in the ring, the per-row records
+// (lse, 1/|q|, 1/|k| as the forward pass left them, CSR-row order: one bulk copy per bin) and D per slot:
 //   entries  : query side of every (unit, head), then key side, from one work queue; a key-side entry waits on a
 //              shared-memory counter for the query-side entries of its window (they produce D), not on a barrier
 //   phase 1  : one warp per (unit, head), query side.  One sweep over the key tiles computes S' = Qs K^T and
@@ -482,12 +515,17 @@ __global__ void __launch_bounds__(MF_THREADS, 1) sra_fwd_mma_kernel(const __grid
 //              across steps.  dk = ln2 (H - K (K.H)) / |k|.
 // dq, dk, dv rows go straight from the fragments to the flat (N, 3d) dqkv (bf16, token order: the operand of the
 // in-projection's gradient GEMMs); sum dS S is reduced per CTA into dtau_sum.
-#define MB_STAGES 2
+#ifndef MB_SLOTS
+#define MB_SLOTS 3             // backward: bins in flight (sweep r2: 3 slots + 19 groups 137 us, 4 + 16 147 us, 2 + 18 143 us at d = 256)
+#endif
+#ifndef MB_RING
+#define MB_RING 19             // backward: groups of the ring (+ 1 never-written pad group)
+#endif
 #define MB_SCAL (MM_ROWS * 24)     // per-row record of 24 fp32: lse | 1/|q| | 1/|k|, each per head
 #define MB_MATH_WARPS (MM_THREADS / 32 - 1)
-// stages x 9 groups x {q,k,v,dO} | per stage: row records [144][24], D [144][4] | table block | query-side completion counters | barriers
-#define MB_STAGE_BYTES (MM_GROUPS * MB_GROUP * 2 + MB_SCAL * 4 + MM_ROWS * 4 * 4 + MM_BLOCK_INTS * 4 + 128 * 4 * 4)
-#define MB_SMEM_BYTES (MB_STAGES * MB_STAGE_BYTES + MM_RR_SLOTS * 8 + 2 * MB_STAGES * 8 + 1024)
+// ring of {q,k,v,dO} groups | per slot: row records [144][24], D [144][4], table block, query-side completion counters, barriers
+#define MB_SLOT_BYTES (MB_SCAL * 4 + MM_ROWS * 4 * 4 + MM_BLOCK_INTS * 4 + 128 * 4 * 4 + 8 + 16)
+#define MB_SMEM_BYTES ((MB_RING + 1) * MB_GROUP * 2 + MB_SLOTS * MB_SLOT_BYTES + MM_RR_SLOTS * 8 + 1024)
 
 struct MbArgs {
   const int* bin_units; // per-bin blocks (gdmae_sra_bin_units)
@@ -746,14 +784,16 @@ template <int HD>
 __global__ void __launch_bounds__(MM_THREADS, 1) sra_bwd_mma_kernel(const __grid_constant__ CUtensorMap tmQ, MbArgs a) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
-  bf16* sdata = (bf16*)smem_raw;                               // MB_STAGES x 9 groups x {q, k, v, dO} x [16][64]
-  float* sscal_all = (float*)(sdata + MB_STAGES * MM_GROUPS * MB_GROUP);   // MB_STAGES x { records [144][24], D [144][4] }
+  bf16* sdata = (bf16*)smem_raw;                               // ring: (MB_RING + 1) groups x {q, k, v, dO} x [16][64]
+  float* sscal_all = (float*)(sdata + (MB_RING + 1) * MB_GROUP);            // MB_SLOTS x { records [144][24], D [144][4] }
   constexpr int SCAL_STAGE = MB_SCAL + MM_ROWS * 4;
-  int* sblock_all = (int*)(sscal_all + MB_STAGES * SCAL_STAGE);
-  int* sdone_all = sblock_all + MB_STAGES * MM_BLOCK_INTS;     // MB_STAGES x [128 window start rows][4 heads]: query-side entries finished
-  int2* s_rr = (int2*)(sdone_all + MB_STAGES * 512);
+  int* sblock_all = (int*)(sscal_all + MB_SLOTS * SCAL_STAGE);
+  int* sdone_all = sblock_all + MB_SLOTS * MM_BLOCK_INTS;      // MB_SLOTS x [128 window start rows][4 heads]: query-side entries finished
+  int2* s_rr = (int2*)(sdone_all + MB_SLOTS * 512);
   unsigned long long* b_full = (unsigned long long*)(s_rr + MM_RR_SLOTS);   // bin landed
-  unsigned long long* b_empty = b_full + MB_STAGES;                         // bin consumed
+  unsigned long long* b_empty = b_full + MB_SLOTS;                          // bin consumed
+  int* s_base = (int*)(b_empty + MB_SLOTS);                    // first ring group of the slot's bin
+  int* s_alloc = s_base + MB_SLOTS;                            // groups the slot's bin holds (producer only)
   __shared__ float s_dtau[MM_THREADS / 32];
   constexpr int HS = MM_SLICE / HD;
   const int d = a.d;
@@ -769,11 +809,11 @@ __global__ void __launch_bounds__(MM_THREADS, 1) sra_bwd_mma_kernel(const __grid
   // ---- prologue: (first row, rows) of the CTA's bins, zeroed buffers (overrun rows and scalars must be finite), barriers
   if (tid < MM_RR_SLOTS && tid < my_bins)
     s_rr[tid] = __ldg(reinterpret_cast<const int2*>(a.bin_units + (long long)(cta + tid * ncta) * MM_BLOCK_INTS + MM_UNITS + 2));
-  for (int i = tid; i < MB_STAGES * MM_GROUPS * MB_GROUP / 8; i += MM_THREADS) reinterpret_cast<uint4*>(sdata)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < MB_STAGES * SCAL_STAGE; i += MM_THREADS) sscal_all[i] = 0.f;
+  for (int i = tid; i < (MB_RING + 1) * MB_GROUP / 8; i += MM_THREADS) reinterpret_cast<uint4*>(sdata)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < MB_SLOTS * SCAL_STAGE; i += MM_THREADS) sscal_all[i] = 0.f;
   if (tid == 0) {
 #pragma unroll
-    for (int st = 0; st < MB_STAGES; ++st) {
+    for (int st = 0; st < MB_SLOTS; ++st) {
       mbar_init(&b_full[st], 1);
       mbar_init(&b_empty[st], MB_MATH_WARPS);
     }
@@ -786,24 +826,40 @@ __global__ void __launch_bounds__(MM_THREADS, 1) sra_bwd_mma_kernel(const __grid
   float dtau_acc = 0.f;
 
   if (warp == 0) {
-    // ================= producer warp: once the math warps have released bin k - 2 the warp zeroes the stage's completion
-    // counters, then one lane issues the bin's transaction: table block, row records and one box per 16 rows
+    // ================= producer warp: slot and ring groups are claimed as in the forward kernel (lane 0), the warp zeroes the
+    // slot's completion counters, then lane 0 issues the bin's transaction: table block, row records and one box per 16 rows
     if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)&tmQ) : "memory");
+    int head = 0, used = 0, tail = 0;
     for (int k = 0; k < my_bins; ++k) {
-      const int bi = cta + k * ncta, st = k % MB_STAGES;
-      if (lane == 0 && k >= MB_STAGES) mbar_wait(&b_empty[st], ((k / MB_STAGES) - 1) & 1);
+      const int bi = cta + k * ncta, st = k % MB_SLOTS;
+      int row0 = 0, R = 0, nbox = 0, start = 0;
+      if (lane == 0) {
+        const int2 rr = k < MM_RR_SLOTS ? s_rr[k]
+                                        : __ldg(reinterpret_cast<const int2*>(a.bin_units + (long long)bi * MM_BLOCK_INTS + MM_UNITS + 2));
+        row0 = rr.x; R = rr.y; nbox = (R + MM_BOX - 1) / MM_BOX;
+        int need;
+        for (;;) {
+          need = nbox + (head + nbox > MB_RING ? MB_RING - head : 0);
+          if (k - tail < MB_SLOTS && used + need <= MB_RING) break;
+          mbar_wait(&b_empty[tail % MB_SLOTS], (tail / MB_SLOTS) & 1);
+          used -= s_alloc[tail % MB_SLOTS];
+          ++tail;
+        }
+        start = head + nbox > MB_RING ? 0 : head;
+        head = start + nbox;
+        used += need;
+        s_alloc[st] = need;
+        s_base[st] = start;
+      }
       __syncwarp();
 #pragma unroll
       for (int i = 0; i < 4; ++i) reinterpret_cast<int4*>(sdone_all + st * 512)[lane + 32 * i] = make_int4(0, 0, 0, 0);
       __syncwarp();
       if (lane == 0) {
-        const int2 rr = k < MM_RR_SLOTS ? s_rr[k]
-                                        : __ldg(reinterpret_cast<const int2*>(a.bin_units + (long long)bi * MM_BLOCK_INTS + MM_UNITS + 2));
-        const int row0 = rr.x, R = rr.y, nbox = (R + MM_BOX - 1) / MM_BOX;
         mbar_expect_tx(&b_full[st], (unsigned)(nbox * MB_GROUP * 2 + MM_BLOCK_INTS * 4 + R * 96));
         bulk_copy(sblock_all + st * MM_BLOCK_INTS, a.bin_units + (long long)bi * MM_BLOCK_INTS, MM_BLOCK_INTS * 4, &b_full[st]);
         if (R > 0) bulk_copy(sscal_all + st * SCAL_STAGE, a.lrr + (long long)row0 * 24, R * 96, &b_full[st]);
-        bf16* tile = sdata + st * MM_GROUPS * MB_GROUP;
+        bf16* tile = sdata + start * MB_GROUP;
         for (int i = 0; i < nbox; ++i) tma_box(tile + i * MB_GROUP, &tmQ, &b_full[st], row0 + i * MM_BOX, sl);
       }
     }
@@ -815,19 +871,19 @@ __global__ void __launch_bounds__(MM_THREADS, 1) sra_bwd_mma_kernel(const __grid
     // warp that finds the bin exhausted signals and moves on to bin k+1 without waiting for the others.
     const int g = lane >> 2;
     for (int k = 0; k < my_bins; ++k) {
-      const int st = k % MB_STAGES;
+      const int st = k % MB_SLOTS;
       int* sunit = sblock_all + st * MM_BLOCK_INTS;
       const int4* sinfo = (const int4*)(sunit + MM_UNIT_STRIDE);      // records of rows row0 .. row0 + 127
-      const bf16* sq = sdata + st * MM_GROUPS * MB_GROUP;
-      const bf16* sk = sq + MM_BOX * MM_SLICE;
-      const bf16* sv = sk + MM_BOX * MM_SLICE;
-      const bf16* sdo = sv + MM_BOX * MM_SLICE;
       float* slse = sscal_all + st * SCAL_STAGE;                      // [row][24]: lse | 1/|q| | 1/|k|
       float* srq = slse + 8;
       float* srk = slse + 16;
       float* sD = slse + MB_SCAL;
       int* sdone = sdone_all + st * 512;
-      mbar_wait(&b_full[st], (k / MB_STAGES) & 1);
+      mbar_wait(&b_full[st], (k / MB_SLOTS) & 1);
+      const bf16* sq = sdata + s_base[st] * MB_GROUP;
+      const bf16* sk = sq + MM_BOX * MM_SLICE;
+      const bf16* sv = sk + MM_BOX * MM_SLICE;
+      const bf16* sdo = sv + MM_BOX * MM_SLICE;
       const int row0 = sunit[MM_UNITS + 2], R = sunit[MM_UNITS + 3];
       const int nent = sunit[MM_UNITS] * HS;
       for (;;) {
@@ -1060,8 +1116,10 @@ static int sra_make_map(CUtensorMap* m, const void* ptr, long long N, int nsl, i
 static int mm_attrs() {
   static bool done = false;
   if (!done) {
-    GDMAE_CHECK_CUDA(cudaFuncSetAttribute(sra_fwd_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
-    GDMAE_CHECK_CUDA(cudaFuncSetAttribute(sra_fwd_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
+    GDMAE_CHECK_CUDA(cudaFuncSetAttribute(sra_fwd_mma_kernel<16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
+    GDMAE_CHECK_CUDA(cudaFuncSetAttribute(sra_fwd_mma_kernel<32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
+    GDMAE_CHECK_CUDA(cudaFuncSetAttribute(sra_fwd_mma_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
+    GDMAE_CHECK_CUDA(cudaFuncSetAttribute(sra_fwd_mma_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM_BYTES));
     GDMAE_CHECK_CUDA(cudaFuncSetAttribute(sra_bwd_mma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_SMEM_BYTES));
     GDMAE_CHECK_CUDA(cudaFuncSetAttribute(sra_bwd_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_SMEM_BYTES));
     done = true;
@@ -1086,8 +1144,13 @@ extern "C" int gdmae_sra_fwd_win(const void* qkvw, const int32_t* bin_units, int
   MmArgs a{bin_units, bv, (int)N, d, out_bf16, lse_by_row};
   cudaStream_t st = (cudaStream_t)stream_;
   // one CTA per SM; 148 is a multiple of the 2 (d = 128) and 4 (d = 256) channel slices
-  if (d == 128) sra_fwd_mma_kernel<16><<<GDMAE_NUM_SMS, MF_THREADS, MM_SMEM_BYTES, st>>>(tq, a, out, lse);
-  else sra_fwd_mma_kernel<32><<<GDMAE_NUM_SMS, MF_THREADS, MM_SMEM_BYTES, st>>>(tq, a, out, lse);
+  if (out_bf16 && lse_by_row) {
+    if (d == 128) sra_fwd_mma_kernel<16, 1><<<GDMAE_NUM_SMS, MF_THREADS, MM_SMEM_BYTES, st>>>(tq, a, out, lse);
+    else sra_fwd_mma_kernel<32, 1><<<GDMAE_NUM_SMS, MF_THREADS, MM_SMEM_BYTES, st>>>(tq, a, out, lse);
+  } else {
+    if (d == 128) sra_fwd_mma_kernel<16, 0><<<GDMAE_NUM_SMS, MF_THREADS, MM_SMEM_BYTES, st>>>(tq, a, out, lse);
+    else sra_fwd_mma_kernel<32, 0><<<GDMAE_NUM_SMS, MF_THREADS, MM_SMEM_BYTES, st>>>(tq, a, out, lse);
+  }
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;
 }

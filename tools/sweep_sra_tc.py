@@ -65,13 +65,16 @@ def main():
             assert rc == 0, lib.gdmae_last_error()
 
             def fwd():
-                rc = lib.gdmae_sra_fwd_win(L.P(qkvdw), L.P(units), L.i64(N), d, None, 1, L.P(out), L.P(lse), 0, st())
+                rc = lib.gdmae_sra_fwd_win(L.P(qkvdw), L.P(units), L.i64(N), d, None, 1, L.P(out), L.P(lrr if FUSED else lse), FUSED, st())
                 assert rc == 0, lib.gdmae_last_error()
 
             def bwd():
                 rc = lib.gdmae_sra_bwd_win(L.P(qkvdw), L.P(lrr), L.P(units), L.i64(N), d, L.P(tau), L.f32(0.01), L.P(dqkv), L.P(dts), st())
                 assert rc == 0, lib.gdmae_last_error()
 
+            FUSED = 0
+            fwd()                                                  # lse by token, for the check below
+            FUSED = 1                                              # timed as the encoder layer calls it: lse into the row records
             tf = timeit(fwd, flush)
             tb = timeit(bwd, flush)
             ef = float((out.float() - o_ref).abs().max())
