@@ -539,6 +539,36 @@ class DecoderTail(torch.autograd.Function):
         return dy, dgamma, dbeta, None, None, None, None, None, None, None
 
 
+class DecoderConv3x3(torch.autograd.Function):
+    """decoder_conv_out's Conv2d(384, 128, 3, padding=1, bias=False) (spt_backbone_mae.py:45-49) on the NHWC bf16 map.
+    Forward and the input gradient are the library convolution (cuDNN runs them at the dense tensor roofline); the WEIGHT
+    gradient is the own tcgen05 / TMA kernel (gdmae_conv3x3_wgrad: shifted TMA boxes of the map as the operand of every
+    tap, K = pixels split across the SMs, TMA reduce-add) - cuDNN's wgrad moved 6x the operand bytes through DRAM.
+    x (B, Y, X, 384) bf16, weight = the fp32 master (128, 384, 3, 3), w_op = its bf16 copy."""
+
+    @staticmethod
+    def forward(ctx, x_nhwc, weight, w_op):
+        x = x_nhwc.contiguous()
+        w_cl = w_op.contiguous(memory_format=torch.channels_last)
+        y = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), w_cl, padding=1)
+        ctx.save_for_backward(x, w_cl)
+        return y.permute(0, 2, 3, 1)
+
+    @staticmethod
+    def backward(ctx, dy_nhwc):
+        x, w_cl = ctx.saved_tensors
+        dy = dy_nhwc.contiguous()
+        B, Y, X, Ci = x.shape
+        Co = dy.shape[3]
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.ops.aten.convolution_backward(dy.permute(0, 3, 1, 2), x.permute(0, 3, 1, 2), w_cl, None, [1, 1], [1, 1], [1, 1],
+                                                     False, [0, 0], 1, [True, False, False])[0].permute(0, 2, 3, 1)
+        dw = torch.empty((Co, 3, 3, Ci), dtype=F32, device=x.device)
+        L.check(L.lib().gdmae_conv3x3_wgrad(L.P(dy), L.P(x), B, Y, X, Ci, Co, L.P(dw), 0, L.stream()), "gdmae_conv3x3_wgrad")
+        return dx, dw.permute(0, 3, 1, 2), None
+
+
 # ----------------------------------------------------------------------------- chamfer head
 def group_points_centered(ps, pc_range, voxel_size, K):
     """gt_points - voxel_centers of target_assigner (spt_backbone_mae.py:67-72), (M, K, 3)."""

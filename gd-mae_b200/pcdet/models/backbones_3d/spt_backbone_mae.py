@@ -183,8 +183,14 @@ class SPTBackboneMAE(nn.Module):
         fused = _ops.DenseFill.apply(rows[0], rows[1], rows[2], bgs[0], bgs[1], bgs[2], [sp.rank_grid() for sp in srcs],
                                      [sp.indices for sp in srcs], self.fuse_strides, batch_size, Y, X, dt)  # (B,Y,X,384) NHWC
         conv, bn = self.decoder_conv_out[0], self.decoder_conv_out[1]
-        w = _fused.cast_param(conv.weight, dt)
-        y = F.conv2d(fused.permute(0, 3, 1, 2), w.contiguous(memory_format=torch.channels_last), padding=1)  # cuDNN, NHWC
+        own_wgrad = (dt == torch.bfloat16 and self.training and conv.in_channels == 384 and conv.out_channels == 128
+                     and conv.kernel_size == (3, 3) and conv.bias is None)
+        if own_wgrad:
+            # cuDNN forward / input gradient, own tcgen05 weight gradient (ops.DecoderConv3x3)
+            y = _ops.DecoderConv3x3.apply(fused, conv.weight, _fused._gw(conv.weight)).permute(0, 3, 1, 2)
+        else:
+            w = _fused.cast_param(conv.weight, dt)
+            y = F.conv2d(fused.permute(0, 3, 1, 2), w.contiguous(memory_format=torch.channels_last), padding=1)  # cuDNN, NHWC
         fuse_tail = self.training and not self.dense_spatial_features and ps.cell2pillar.numel() == batch_size * Y * X
         if fuse_tail:
             # BN statistics over the whole map, BN + ReLU values only at the pillar cells the head gathers (ops.DecoderTail)

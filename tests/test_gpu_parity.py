@@ -582,6 +582,81 @@ def test_sra_bin_units_cover_every_row(G, golden):
             assert bool((seen == 1).all()), (int((seen == 0).sum()), int((seen > 1).sum()))
 
 
+# ------------------------------------------------------------------------------ window-major epilogues of the own GEMM
+def test_tc_gemm_window_major_epilogues(G, golden):
+    """gdmae_tc_gemm mode 4 (in-projection: + positional LUT row, per-head L2 norm, log2(e)/tau into q, rows to CSR order,
+    1/|q| and 1/|k| into the row records) and mode 5 (rows of a plain bf16 result to CSR order) against the plain GEMM
+    followed by the stand-alone re-layout kernel (gdmae_sra_relayout), for both model widths."""
+    from gd_mae_b200 import fused, _lib as L
+    import ctypes
+    g = torch.Generator().manual_seed(5)
+    sites = torch.nonzero(torch.rand(2, 61, 45, generator=g) < 0.3).int().contiguous().cuda()
+    for d, shifted in ((128, 0), (256, 1)):
+        t = G.ops.window_table(sites, 2, 61, 45, shifted)
+        N = t.N
+        gen = torch.Generator("cuda").manual_seed(d)
+        x = torch.randn(N, d, device="cuda", generator=gen).to(torch.bfloat16)
+        w = (torch.randn(3 * d, d, device="cuda", generator=gen) * d ** -0.5).to(torch.bfloat16)
+        lut = 0.5 * torch.randn(64, 2 * d, device="cuda", generator=gen)
+        tau = torch.full((1,), 0.07, device="cuda")
+        units = t.bin_units()
+        tok_info = units[int(L.lib().gdmae_sra_tok_info_offset(L.i64(N))):]
+        lib = L.lib()
+        # reference: plain bf16 GEMM, then the re-layout kernel
+        qkv = fused.tc_gemm(x, w.t(), out_dtype=torch.bfloat16)
+        dflat = fused.tc_gemm(x, w[:d].t(), out_dtype=torch.bfloat16)                   # any (N, d) bf16 result
+        ref = torch.zeros(4 * N * d, dtype=torch.bfloat16, device="cuda")
+        lrr_ref = torch.zeros(N, 24, device="cuda")
+        L.check(lib.gdmae_sra_relayout(L.P(qkv), L.P(lut), L.P(t.row_info), L.P(tau), L.f32(0.01), L.i64(N), d, L.P(dflat), None,
+                                       L.P(ref), L.P(lrr_ref), L.stream()), "gdmae_sra_relayout")
+        got = torch.zeros(4 * N * d, dtype=torch.bfloat16, device="cuda")
+        lrr = torch.zeros(N, 24, device="cuda")
+        E = fused.TcEpilogue()
+        E.mode, E.tok_info, E.lut, E.tau, E.tau_min, E.lrr = 4, tok_info.data_ptr(), lut.data_ptr(), tau.data_ptr(), 0.01, lrr.data_ptr()
+        L.check(lib.gdmae_tc_gemm(0, 1, L.i64(N), L.i64(3 * d), L.i64(d), L.P(x), L.i64(d), L.P(w), L.i64(d), L.P(got), L.i64(3 * d), 1,
+                                  L.f32(0.0), 0, ctypes.byref(E), L.stream()), "gdmae_tc_gemm mode 4")
+        E5 = fused.TcEpilogue()
+        E5.mode, E5.tok_info, E5.plane0 = 5, tok_info.data_ptr(), 3 * (d // 64)
+        L.check(lib.gdmae_tc_gemm(0, 1, L.i64(N), L.i64(d), L.i64(d), L.P(x), L.i64(d), L.P(w[:d].contiguous()), L.i64(d), L.P(got), L.i64(d), 1,
+                                  L.f32(0.0), 0, ctypes.byref(E5), L.stream()), "gdmae_tc_gemm mode 5")
+        torch.cuda.synchronize()
+        a, b = got.view(4, N * d).float(), ref.view(4, N * d).float()
+        # q^, k^: the fused epilogue normalises the fp32 accumulator, the reference a bf16-rounded copy of it (2 roundings)
+        for part, tol in ((0, 2e-2), (1, 2e-2), (2, 0.0)):
+            err = float((a[part] - b[part]).abs().max() / b[part].abs().max())
+            print(f"window-major epilogue d={d} tensor {part}: rel err {err:.2e}")
+            assert err <= tol, (d, part, err)
+        assert torch.equal(got.view(4, -1)[3], ref.view(4, -1)[3])                        # mode 5 is a pure row permutation
+        assert rel(lrr[:, 8:], lrr_ref[:, 8:]) < 5e-3
+
+
+def test_conv3x3_wgrad_matches_torch(G):
+    """gdmae_conv3x3_wgrad (tcgen05 / TMA weight gradient of the decoder conv, shifted TMA boxes as tap operands) against
+    torch's conv2d_weight in fp32 on the same bf16-rounded tensors; map sizes that are not multiples of the 64-pixel box."""
+    from gd_mae_b200 import _lib as L
+    for B, Y, X in ((2, 37, 70), (1, 9, 130)):
+        gen = torch.Generator("cuda").manual_seed(Y)
+        x = torch.randn(B, Y, X, 384, device="cuda", generator=gen).to(torch.bfloat16)
+        dy = torch.randn(B, Y, X, 128, device="cuda", generator=gen).to(torch.bfloat16)
+        dw = torch.empty(128, 3, 3, 384, device="cuda")
+        L.check(L.lib().gdmae_conv3x3_wgrad(L.P(dy), L.P(x), B, Y, X, 384, 128, L.P(dw), 0, L.stream()), "gdmae_conv3x3_wgrad")
+        ref = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (128, 384, 3, 3), dy.float().permute(0, 3, 1, 2), padding=1)
+        err = rel(dw.permute(0, 3, 1, 2), ref)
+        print(f"conv3x3 wgrad B={B} Y={Y} X={X}: rel err {err:.2e}")
+        assert err < 2e-3, err
+        # accumulate = 1 adds to dW
+        L.check(L.lib().gdmae_conv3x3_wgrad(L.P(dy), L.P(x), B, Y, X, 384, 128, L.P(dw), 1, L.stream()), "gdmae_conv3x3_wgrad")
+        assert rel(dw.permute(0, 3, 1, 2), 2 * ref) < 2e-3
+    to = ctypes_int()
+    L.check(L.lib().gdmae_tc_gemm_timeouts(to), "gdmae_tc_gemm_timeouts")
+    assert to._obj.value == 0
+
+
+def ctypes_int():
+    import ctypes
+    return ctypes.byref(ctypes.c_int(0))
+
+
 # ------------------------------------------------------------------------------ index pipeline one step ahead
 def test_prefetched_index_pipeline_matches_inline(G):
     """GDMAE.prefetch_index (voxelisation, mask, site sets, window tables of the NEXT batch on a side stream, used by
