@@ -28,6 +28,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <mutex>
+#include <stdlib.h>
 #include "../../include/gdmae_b200.h"
 
 namespace {
@@ -653,9 +654,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tcg_gemm_kernel(const __grid_c
 //   The pixel rows are split across 16 groups of CTAs (9 x 16 = 144 CTAs, one wave); the CTAs of a group walk the same
 //   rows at the same time, so the operands come from DRAM once and from the L2 nine times.  Every CTA adds its three
 //   partial tiles to dW with TMA reduce-add.
+//   SHIFT variant: the three kx taps read ONE box of 64 + 2 pixels (72 rows of 128 bytes); the tap's operand is that box
+//   entered kx rows further down (shared-memory descriptor start + kx * 128 bytes - the 128B swizzle is a function of the
+//   absolute shared-memory address, so a start inside a swizzle atom addresses the rows TMA wrote): 34 KB per k-step.
 constexpr int CW_GROUPS = 16;
-constexpr int CW_STAGE_BYTES = 16384 + 3 * 16384;
-constexpr int CW_STAGES = 3;
+template <bool SHIFT> struct CwCfg {
+  static constexpr int B_HALF = SHIFT ? 72 * 128 : 8192;                  // one 64-channel half of a B box
+  static constexpr int STAGE_BYTES = 16384 + (SHIFT ? 2 * B_HALF : 3 * 16384);
+  static constexpr int STAGES = SHIFT ? 5 : 3;
+};
 
 struct ConvWgradParams {
   int B, Y, X;
@@ -669,9 +676,11 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
 
 // tmDy: (128 co, X, Y, B) bf16, box 64 x 64 x 1 x 1;  tmIn: (384 ci, X, Y, B) bf16, box 64 x 64 x 1 x 1;
 // tmW: dW as (3456 = (ky, kx, ci), 128 co) fp32, box 32 x 32 (the reduce-add units of the GEMM epilogue)
+template <bool SHIFT>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy,
                                                                        const __grid_constant__ CUtensorMap tmIn,
                                                                        const __grid_constant__ CUtensorMap tmW, const ConvWgradParams p) {
+  constexpr int CW_STAGE_BYTES = CwCfg<SHIFT>::STAGE_BYTES, CW_STAGES = CwCfg<SHIFT>::STAGES, B_HALF = CwCfg<SHIFT>::B_HALF;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* units = smem + CW_STAGES * CW_STAGE_BYTES;
@@ -718,11 +727,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_wgrad_kernel(const __g
           tma_load_4d(sa, &tmDy, full + stage, 0, xb * 64, y, b);
           tma_load_4d(sa + 8192, &tmDy, full + stage, 64, xb * 64, y, b);
           // B: the input map shifted by (ky - 1, kx - 1); rows / columns outside the map arrive as zeros
+          if (SHIFT) {
+            const uint32_t sb = sa + 16384;          // pixels x0 - 1 .. x0 + 70 (box of 72 rows), both channel halves
+            tma_load_4d(sb, &tmIn, full + stage, cchunk * 128, xb * 64 - 1, y + ky - 1, b);
+            tma_load_4d(sb + B_HALF, &tmIn, full + stage, cchunk * 128 + 64, xb * 64 - 1, y + ky - 1, b);
+          } else {
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            const uint32_t sb = sa + 16384 + kx * 16384;
-            tma_load_4d(sb, &tmIn, full + stage, cchunk * 128, xb * 64 + kx - 1, y + ky - 1, b);
-            tma_load_4d(sb + 8192, &tmIn, full + stage, cchunk * 128 + 64, xb * 64 + kx - 1, y + ky - 1, b);
+            for (int kx = 0; kx < 3; ++kx) {
+              const uint32_t sb = sa + 16384 + kx * 16384;
+              tma_load_4d(sb, &tmIn, full + stage, cchunk * 128, xb * 64 + kx - 1, y + ky - 1, b);
+              tma_load_4d(sb + 8192, &tmIn, full + stage, cchunk * 128 + 64, xb * 64 + kx - 1, y + ky - 1, b);
+            }
           }
           if (++stage == CW_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -741,11 +756,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_wgrad_kernel(const __g
         const uint32_t sa = smem_u32(smem + stage * CW_STAGE_BYTES);
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-          const uint32_t sb = sa + 16384 + kx * 16384;
+          const uint32_t sb = sa + 16384 + (SHIFT ? kx * 128 : kx * 16384);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adesc = make_smem_desc(sa + k * (UMMA_K * 128), BK * 128, 1024);
-            const uint64_t bdesc = make_smem_desc(sb + k * (UMMA_K * 128), BK * 128, 1024);
+            const uint64_t bdesc = make_smem_desc(sb + k * (UMMA_K * 128), B_HALF, 1024);
             umma_bf16(tmem_base + (uint32_t)(kx * 128), adesc, bdesc, idesc, (ks > 0 || k > 0) ? 1u : 0u);
           }
         }
@@ -822,12 +837,12 @@ int make_map(CUtensorMap* m, const void* ptr, int esize, long long inner, long l
 }
 
 // NHWC activation (B, Y, X, C) bf16 as a 4-D tensor (C, X, Y, B): box = 64 channels x 64 pixels of one image row
-int make_map_nhwc(CUtensorMap* m, const void* ptr, int C, int X, int Y, int B) {
+int make_map_nhwc(CUtensorMap* m, const void* ptr, int C, int X, int Y, int B, int box_px = 64) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) { gdmae_set_error("cuTensorMapEncodeTiled is not available from the driver"); return GDMAE_ERR_CUDA; }
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)X, (cuuint64_t)Y, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * X, (cuuint64_t)C * 2 * X * Y};
-  cuuint32_t box[4] = {64, 64, 1, 1};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_px, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -870,24 +885,36 @@ extern "C" int gdmae_conv3x3_wgrad(const void* dy_bf16, const void* in_bf16, int
   GDMAE_CHECK_ARG(((uintptr_t)dy_bf16 & 15) == 0 && ((uintptr_t)in_bf16 & 15) == 0 && ((uintptr_t)dW & 15) == 0);
   cudaStream_t st = (cudaStream_t)stream_;
   if (!accumulate) GDMAE_CHECK_CUDA(cudaMemsetAsync(dW, 0, (size_t)c_out * 9 * c_in * sizeof(float), st));
+  // GDMAE_WGRAD_SHIFT=0 selects the variant that loads one box per tap (development / A-B measurements)
+  static const bool shift = [] { const char* e = getenv("GDMAE_WGRAD_SHIFT"); return !(e && e[0] == '0'); }();
   CUtensorMap tdy, tin, tw;
   int rc = make_map_nhwc(&tdy, dy_bf16, c_out, X, Y, B);
   if (rc) return rc;
-  rc = make_map_nhwc(&tin, in_bf16, c_in, X, Y, B);
+  rc = make_map_nhwc(&tin, in_bf16, c_in, X, Y, B, shift ? 72 : 64);
   if (rc) return rc;
   rc = make_map(&tw, dW, 4, 9 * c_in, c_out, 9 * c_in, 32);
   if (rc) return rc;
-  constexpr int SMEM = CW_STAGES * CW_STAGE_BYTES + UNIT_BYTES_TOTAL + (2 * CW_STAGES + 1) * 8 + 16;
-  static_assert(SMEM <= 227 * 1024, "shared memory budget");
-  static bool configured[64] = {};
+  ConvWgradParams p = {B, Y, X, B * Y};
   int dev = 0;
   GDMAE_CHECK_CUDA(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && !configured[dev]) {
-    GDMAE_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    configured[dev] = true;
+  static bool configured[2][64] = {};
+  if (shift) {
+    constexpr int SMEM = CwCfg<true>::STAGES * CwCfg<true>::STAGE_BYTES + UNIT_BYTES_TOTAL + (2 * CwCfg<true>::STAGES + 1) * 8 + 16;
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
+    if (dev >= 0 && dev < 64 && !configured[1][dev]) {
+      GDMAE_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+      configured[1][dev] = true;
+    }
+    conv3x3_wgrad_kernel<true><<<9 * CW_GROUPS, NUM_THREADS, SMEM, st>>>(tdy, tin, tw, p);
+  } else {
+    constexpr int SMEM = CwCfg<false>::STAGES * CwCfg<false>::STAGE_BYTES + UNIT_BYTES_TOTAL + (2 * CwCfg<false>::STAGES + 1) * 8 + 16;
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
+    if (dev >= 0 && dev < 64 && !configured[0][dev]) {
+      GDMAE_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+      configured[0][dev] = true;
+    }
+    conv3x3_wgrad_kernel<false><<<9 * CW_GROUPS, NUM_THREADS, SMEM, st>>>(tdy, tin, tw, p);
   }
-  ConvWgradParams p = {B, Y, X, B * Y};
-  conv3x3_wgrad_kernel<<<9 * CW_GROUPS, NUM_THREADS, SMEM, st>>>(tdy, tin, tw, p);
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;
 }

@@ -565,7 +565,8 @@ class DecoderConv3x3(torch.autograd.Function):
             dx = torch.ops.aten.convolution_backward(dy.permute(0, 3, 1, 2), x.permute(0, 3, 1, 2), w_cl, None, [1, 1], [1, 1], [1, 1],
                                                      False, [0, 0], 1, [True, False, False])[0].permute(0, 2, 3, 1)
         dw = torch.empty((Co, 3, 3, Ci), dtype=F32, device=x.device)
-        L.check(L.lib().gdmae_conv3x3_wgrad(L.P(dy), L.P(x), B, Y, X, Ci, Co, L.P(dw), 0, L.stream()), "gdmae_conv3x3_wgrad")
+        with L.timed("conv3x3_wgrad", 2 * B * Y * X * 9 * Ci * Co):          # FLOPs, not bytes: the kernel is tensor bound
+            L.check(L.lib().gdmae_conv3x3_wgrad(L.P(dy), L.P(x), B, Y, X, Ci, Co, L.P(dw), 0, L.stream()), "gdmae_conv3x3_wgrad")
         return dx, dw.permute(0, 3, 1, 2), None
 
 

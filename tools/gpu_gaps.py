@@ -67,3 +67,11 @@ for k, (c, t) in sorted(gaps.items(), key=lambda x: -x[1][1])[:25]:
 print("largest single gaps (us, after -> before):")
 for g, a, b in sorted(big, reverse=True)[:25]:
     print(f"  {g:8.1f}  {a}  ->  {b}")
+# in-step (warm cache, steady-state clocks) time per kernel name: what the step really spends, next to the cold ncu list
+busy_by = collections.defaultdict(lambda: [0, 0.0])
+for e in seg:
+    busy_by[e["name"][:90]][0] += 1
+    busy_by[e["name"][:90]][1] += e["dur"]
+print("in-step GPU time by kernel (last step):")
+for k, (c, t) in sorted(busy_by.items(), key=lambda x: -x[1][1])[:40]:
+    print(f"  {t:8.1f} us  {c:4d}x  {100 * t / busy:5.1f} %  {k}")
