@@ -34,6 +34,7 @@ BYTES_DEF = {
     "sra_bwd": "N*d*(3*s + s + 3*s) + N*32 per launch: q,k,v,dO in, dq,dk,dv out, lse in",
     "pillar_scatter_max": "Np*C*s + Np*4 + M*C*4 per launch: point rows + segment index in, pillar maxima out (SURVEY.md 8d a6)",
 }
+SETTLE_STEPS = 12
 SPAN_NAMES = {0: "sra_fwd_d{d}", 1: "sra_bwd_d{d}", 2: "pillar_scatter_max_c{d}"}
 
 
@@ -218,6 +219,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--no-augment", action="store_true", help="e2e leg without the device-side world augmentation")
     ap.add_argument("--impl", default="gdmae_b200")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "tf32", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -258,7 +260,7 @@ def main():
     if world > 1:  # identical initial weights on every rank (DDP broadcasts rank 0's, train.py:146)
         for t in list(model.parameters()) + list(model.buffers()):
             dist.broadcast(t.data, 0)
-    total_steps = 2 * (args.steps + args.warmup) + 8
+    total_steps = 2 * (args.steps + args.warmup) + 8 + SETTLE_STEPS + 12
     trainer = MAETrainer(model, cfg.OPTIMIZATION, total_steps=total_steps, world_size=world)
 
     cfg_o = O.make_cfg("waymo_ssl")
@@ -282,13 +284,25 @@ def main():
     # 30 MB H2D transfer overlaps compute instead of preceding it; all copies lie inside the timed region.
     copy_stream = torch.cuda.Stream(device=dev)
     pending = {}
+    # the input side of the SSL config (tools/cfgs/waymo_models/gd_mae_ssl.yaml:18-31: random_world_flip / rotation / scaling,
+    # then mask_points_and_boxes_outside_range = the voxeliser's keep mask): the collated batch is augmented ON THE DEVICE,
+    # one launch, right behind its H2D copy on the copy stream
+    from gd_mae_b200.pcdet.datasets.augmentor.data_augmentor import DataAugmentor
+    augmentor = DataAugmentor(None, config.to_attr({"DISABLE_AUG_LIST": ["placeholder"], "AUG_CONFIG_LIST": [
+        {"NAME": "random_world_flip", "PROBABILITY": 0.5, "ALONG_AXIS_LIST": ["x", "y"]},
+        {"NAME": "random_world_rotation", "PROBABILITY": 1.0, "WORLD_ROT_ANGLE": [-0.78539816, 0.78539816]},
+        {"NAME": "random_world_scaling", "PROBABILITY": 1.0, "WORLD_SCALE_RANGE": [0.95, 1.05]}]}), ["Vehicle", "Pedestrian", "Cyclist"])
+    np.random.seed(1000 + rank)
 
     def prefetch(i):
         with torch.cuda.stream(copy_stream):
             t = host_batches[i % n_pool].to(dev, non_blocking=True)
+            bd = {"points": t, "batch_size": B_PER_GPU}
+            if not args.no_augment:
+                bd = augmentor.forward(bd)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
-        pending[i] = ({"points": t, "batch_size": B_PER_GPU}, ev)
+        pending[i] = ({"points": bd["points"], "batch_size": B_PER_GPU}, ev)
 
     def step_e2e(i):
         if i not in pending:
@@ -334,6 +348,12 @@ def main():
         device_allocs.append(torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - mallocs0)
         return float(ms) / steps, last, _lib.lib().gdmae_launch_count() - l0
 
+    # ---- settle: a fresh box still pages the image in and loads CUDA modules lazily; r2 traces (tools/step_times.py) showed a
+    # rare 50-80 ms host stall within the first ~30 steps of a process.  A few untimed steps through every batch of the
+    # pool come before the W warm-up steps of each leg (they are not counted anywhere).
+    for i in range(SETTLE_STEPS):
+        step_resident(i)
+    res_bd.clear()
     # ---- leg 1: device-resident timing (`value`)
     ms_step, last_loss, launches = timed(step_resident, args.steps, args.warmup)
     # ---- leg 2: end-to-end timing through the public API with host inputs (`e2e`)
@@ -421,10 +441,12 @@ def main():
         "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames_per_gpu": B_PER_GPU, "global_batch": frames, "points_per_batch": pts_per_batch,
                    "grid": "468x468x1", "parallelism": f"dp{world}", "params": trainer.n_params,
+                   "settle_steps_before_warmup": SETTLE_STEPS,
                    "l2": "per-step working set (>2 GB of activations) exceeds the 126 MB L2; input batch changes every step"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(pts_per_batch * 6 * 4), "d2h_bytes_per_step": 4 + 2 * 4 * (4 + B_PER_GPU + 1),
-                "input_pipeline": "pinned host batch of step i+1 copied on a side stream during step i and its index structures "
+                "input_pipeline": "pinned host batch of step i+1 copied on a side stream during step i, world flip / rotation / "
+                                  "scaling of the SSL config applied to it on the device (one launch), its index structures "
                                   "prefetched (MAETrainer.step(batch, next_batch)); loss.item() every step"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "rooflines": rooflines, "kernels": kernels,
         "instrumented_pass": {"steps": n_prof + 1, "ms_per_step": ms_prof, "note": "separate pass after both timed legs; CUDA events around the kernels listed in `kernels`"},

@@ -11,7 +11,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libgdmae_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-         "-Wno-deprecated-declarations"]
+         "-Wno-deprecated-declarations"] + os.environ.get("GDMAE_EXTRA_NVCC_FLAGS", "").split()   # tuning builds: -DTCG_EPI_WARPS=16 ...
 
 
 def _stale(target, sources):

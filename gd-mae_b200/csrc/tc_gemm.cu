@@ -36,11 +36,15 @@ namespace {
 constexpr int BM = 128;        // UMMA M (one TMEM lane per accumulator row)
 constexpr int BK = 64;         // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_EPI_WARPS = 8;   // two per TMEM lane quarter: each takes half of the tile's columns
+#ifndef TCG_EPI_WARPS
+#define TCG_EPI_WARPS 8
+#endif
+constexpr int NUM_EPI_WARPS = TCG_EPI_WARPS;   // NQ = NUM_EPI_WARPS / 4 per TMEM lane quarter: each takes 1 / NQ of the tile's columns
+constexpr int NQ = NUM_EPI_WARPS / 4;
 constexpr int NUM_THREADS = 128 + 32 * NUM_EPI_WARPS;
-constexpr int RING_BYTES = 192 * 1024;
 constexpr int UNIT_BYTES = 32 * 128;                  // one epilogue output unit: 32 rows x 128 bytes
 constexpr int UNIT_BYTES_TOTAL = NUM_EPI_WARPS * UNIT_BYTES;
+constexpr int RING_BYTES = NUM_EPI_WARPS <= 8 ? 192 * 1024 : 156 * 1024;   // + unit buffers + barriers <= 227 KB
 
 struct TcgParams {
   int M, N, K;
@@ -311,8 +315,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tcg_gemm_kernel(const __grid_c
   extern __shared__ __align__(1024) uint8_t smem[];                  // SWIZZLE_128B stages need 1024-byte alignment
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* units = smem + STAGES * STAGE_BYTES;                      // one 4 KB unit buffer per epilogue warp
-  float* ln_stat = reinterpret_cast<float*>(units + UNIT_BYTES_TOTAL); // LayerNorm partial sums of the two column halves: [2][2][128]
-  uint64_t* full = reinterpret_cast<uint64_t*>(ln_stat + 512);
+  float* ln_stat = reinterpret_cast<float*>(units + UNIT_BYTES_TOTAL); // LayerNorm partial sums of the NQ column parts: [2][NQ][128]
+  uint64_t* full = reinterpret_cast<uint64_t*>(ln_stat + 2 * NQ * 128);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
@@ -412,8 +416,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tcg_gemm_kernel(const __grid_c
     __syncwarp();
   } else if (warp >= 4) {
     const int q = warp & 3;                           // TMEM lane quarter this warp may access
-    const int half = (warp - 4) >> 2;                 // which half of the tile's columns it handles
-    constexpr int HC = BN / 2;                        // columns per epilogue warp
+    // NP column parts per TMEM lane quarter (as many warps as the tile has 32-column chunks for, at most NQ); the
+    // other epilogue warps of a narrow tile only keep the accumulator hand-shake going
+    constexpr int NP = BN / 32 < NQ ? BN / 32 : NQ;
+    const int half = (warp - 4) >> 2;                 // which part of the tile's columns it handles
+    constexpr int HC = BN / NP;                       // columns per epilogue warp
+    const bool idle = half >= NP;
     uint8_t* buf = units + (warp - 4) * UNIT_BYTES;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -423,7 +431,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tcg_gemm_kernel(const __grid_c
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * HC);
       const int col0 = n_blk * BN + half * HC;
       float v[32];
-      if (EPI == EPI_PLAIN && p.beta_one) {
+      if (idle) {
+        mbar_wait(tfull + acc, acc_phase);
+      } else if (EPI == EPI_PLAIN && p.beta_one) {
         // C += acc (fp32): the old values of chunk c + 1 are requested while chunk c is processed
         float4 pre[8];
         prefetch_f32(reinterpret_cast<const float*>(p.C), p.ldc, r0, col0, p.M, lane, pre);
@@ -563,8 +573,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tcg_gemm_kernel(const __grid_c
         // z = acc + bias + residual row; y = LayerNorm(z) * gamma + beta.  N == BN: the tile holds whole rows, shared by
         // the two warps of a lane quarter (column halves), which exchange their partial sums through shared memory.  z
         // goes back into the accumulator columns (tcgen05.st): the two further passes read tensor memory only.
-        float* st_sum = ln_stat;            // [2][128]
-        float* st_sq = ln_stat + 256;       // [2][128]
+        float* st_sum = ln_stat;                 // [NP][128]
+        float* st_sq = ln_stat + NQ * 128;       // [NP][128]
         const int rl = q * 32 + lane;       // row inside the tile
         float sum = 0.f;
         float4 pre[8];                      // residual rows of the next chunk, requested one chunk ahead
@@ -591,8 +601,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tcg_gemm_kernel(const __grid_c
         }
         tmem_st_wait();
         st_sum[half * 128 + rl] = sum;
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");       // the two warps of this lane quarter
-        const float mean = (st_sum[rl] + st_sum[128 + rl]) * (1.f / BN);
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "n"(32 * NP) : "memory");       // the NP warps of this lane quarter
+        float tot = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < NP; ++pp) tot += st_sum[pp * 128 + rl];
+        const float mean = tot * (1.f / BN);
         float sq = 0.f;
 #pragma unroll 1
         for (int c = 0; c < HC / 32; ++c) {
@@ -601,8 +614,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tcg_gemm_kernel(const __grid_c
           for (int j = 0; j < 32; ++j) { const float dlt = v[j] - mean; sq = fmaf(dlt, dlt, sq); }
         }
         st_sq[half * 128 + rl] = sq;
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-        const float rstd = rsqrtf((st_sq[rl] + st_sq[128 + rl]) * (1.f / BN) + p.eps);
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "n"(32 * NP) : "memory");
+        float totq = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < NP; ++pp) totq += st_sq[pp * 128 + rl];
+        const float rstd = rsqrtf(totq * (1.f / BN) + p.eps);
 #pragma unroll 1
         for (int c = 0; c < HC / 32; ++c) {
           tmem_ld32(taddr + c * 32, v);
@@ -676,15 +692,17 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
 
 // tmDy: (128 co, X, Y, B) bf16, box 64 x 64 x 1 x 1;  tmIn: (384 ci, X, Y, B) bf16, box 64 x 64 x 1 x 1;
 // tmW: dW as (3456 = (ky, kx, ci), 128 co) fp32, box 32 x 32 (the reduce-add units of the GEMM epilogue)
+constexpr int CW_THREADS = 128 + 32 * 8;      // eight epilogue warps, whatever the GEMM kernel uses
+constexpr int CW_UNIT_BYTES_TOTAL = 8 * UNIT_BYTES;
 template <bool SHIFT>
-__global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy,
+__global__ void __launch_bounds__(CW_THREADS, 1) conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy,
                                                                        const __grid_constant__ CUtensorMap tmIn,
                                                                        const __grid_constant__ CUtensorMap tmW, const ConvWgradParams p) {
   constexpr int CW_STAGE_BYTES = CwCfg<SHIFT>::STAGE_BYTES, CW_STAGES = CwCfg<SHIFT>::STAGES, B_HALF = CwCfg<SHIFT>::B_HALF;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* units = smem + CW_STAGES * CW_STAGE_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(units + UNIT_BYTES_TOTAL);
+  uint64_t* full = reinterpret_cast<uint64_t*>(units + CW_UNIT_BYTES_TOTAL);
   uint64_t* empty = full + CW_STAGES;
   uint64_t* tfull = empty + CW_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
@@ -859,7 +877,7 @@ template <int BN, int EPI>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const TcgParams& p, cudaStream_t st) {
   constexpr int STAGE_BYTES = BM * BK * 2 + BN * BK * 2;
   constexpr int STAGES = RING_BYTES / STAGE_BYTES;
-  constexpr int SMEM = STAGES * STAGE_BYTES + UNIT_BYTES_TOTAL + 512 * 4 + (2 * STAGES + 4) * 8 + 16;
+  constexpr int SMEM = STAGES * STAGE_BYTES + UNIT_BYTES_TOTAL + 2 * NQ * 128 * 4 + (2 * STAGES + 4) * 8 + 16;
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
   static bool configured[64] = {};
   int dev = 0;
@@ -899,21 +917,21 @@ extern "C" int gdmae_conv3x3_wgrad(const void* dy_bf16, const void* in_bf16, int
   GDMAE_CHECK_CUDA(cudaGetDevice(&dev));
   static bool configured[2][64] = {};
   if (shift) {
-    constexpr int SMEM = CwCfg<true>::STAGES * CwCfg<true>::STAGE_BYTES + UNIT_BYTES_TOTAL + (2 * CwCfg<true>::STAGES + 1) * 8 + 16;
+    constexpr int SMEM = CwCfg<true>::STAGES * CwCfg<true>::STAGE_BYTES + CW_UNIT_BYTES_TOTAL + (2 * CwCfg<true>::STAGES + 1) * 8 + 16;
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
     if (dev >= 0 && dev < 64 && !configured[1][dev]) {
       GDMAE_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
       configured[1][dev] = true;
     }
-    conv3x3_wgrad_kernel<true><<<9 * CW_GROUPS, NUM_THREADS, SMEM, st>>>(tdy, tin, tw, p);
+    conv3x3_wgrad_kernel<true><<<9 * CW_GROUPS, CW_THREADS, SMEM, st>>>(tdy, tin, tw, p);
   } else {
-    constexpr int SMEM = CwCfg<false>::STAGES * CwCfg<false>::STAGE_BYTES + UNIT_BYTES_TOTAL + (2 * CwCfg<false>::STAGES + 1) * 8 + 16;
+    constexpr int SMEM = CwCfg<false>::STAGES * CwCfg<false>::STAGE_BYTES + CW_UNIT_BYTES_TOTAL + (2 * CwCfg<false>::STAGES + 1) * 8 + 16;
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
     if (dev >= 0 && dev < 64 && !configured[0][dev]) {
       GDMAE_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
       configured[0][dev] = true;
     }
-    conv3x3_wgrad_kernel<false><<<9 * CW_GROUPS, NUM_THREADS, SMEM, st>>>(tdy, tin, tw, p);
+    conv3x3_wgrad_kernel<false><<<9 * CW_GROUPS, CW_THREADS, SMEM, st>>>(tdy, tin, tw, p);
   }
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;

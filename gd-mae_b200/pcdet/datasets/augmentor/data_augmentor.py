@@ -81,7 +81,16 @@ class DataAugmentor(object):
                 src.append(np.random.permutation(counts[b]) + off)
                 off += counts[b]
             per_frame.append(fp)
-        params = torch.tensor(np.asarray(rows, dtype=np.float32), device=points.device)
+        # parameters through a small ring of pinned staging rows: a pageable copy would block the host until everything queued
+        # before it on this stream (the 30 MB H2D copy of the batch) has drained
+        ring = getattr(self, '_param_ring', None)
+        if ring is None or ring[0].shape[0] != B:
+            ring = self._param_ring = [torch.empty((B, 6), dtype=torch.float32).pin_memory() for _ in range(8)]
+            self._param_slot = 0
+        stage = ring[self._param_slot % len(ring)]
+        self._param_slot += 1
+        stage.copy_(torch.from_numpy(np.asarray(rows, dtype=np.float32)))
+        params = stage.to(points.device, non_blocking=True)
         src_index = torch.from_numpy(np.concatenate(src).astype(np.int32)).to(points.device) if shuffle and src else None
         data_dict['points'] = _ops.world_augment(points, params, src_index)
         data_dict['transformation_3d_list'] = [c.func.__name__ for c in self.data_augmentor_queue]

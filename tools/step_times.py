@@ -35,11 +35,25 @@ if args.nogc:
 if args.timers:
     _lib.KERNEL_TIMERS = {}
     _lib.lib().gdmae_timing_enable(1)
+import time  # noqa: E402
 evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+host = [0.0] * (args.steps + 1)
+mall = [0] * (args.steps + 1)
 evs[0].record()
+host[0] = time.perf_counter()
+mall[0] = torch.cuda.memory_stats().get("num_device_alloc", 0)
 for i in range(args.steps):
     trainer.step({"points": batches[i % 4], "batch_size": 8})
     evs[i + 1].record()
+    host[i + 1] = time.perf_counter()
+    mall[i + 1] = torch.cuda.memory_stats().get("num_device_alloc", 0)
 torch.cuda.synchronize()
 ts = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
 print(f"timers={args.timers} nogc={args.nogc} mean {sum(ts) / len(ts):.2f} ms  steps: " + " ".join(f"{t:.1f}" for t in ts))
+med = sorted(ts)[len(ts) // 2]
+for i, t_ in enumerate(ts):
+    if t_ > 1.08 * med:
+        # device time of the step, host time to enqueue it (and the two before it: the host runs up to two steps ahead), cudaMallocs
+        print(f"  hiccup step {i}: device {t_:.1f} ms, host enqueue {1e3 * (host[i + 1] - host[i]):.1f} ms (previous "
+              f"{1e3 * (host[i] - host[i - 1]) if i else 0:.1f}, {1e3 * (host[i - 1] - host[i - 2]) if i > 1 else 0:.1f}), "
+              f"cudaMallocs in step {mall[i + 1] - mall[i]} (previous {mall[i] - mall[i - 1] if i else 0})")
