@@ -8,6 +8,7 @@
 // ATen's path for the same work is batch_norm_collect_statistics + transform_input + a separate
 // ReLU forward, and threshold_backward + backward_reduce + backward_elemt backward.
 #include "common.cuh"
+#include <cuda_bf16.h>
 #include "bn_common.cuh"
 
 
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const float4* __
                                                                 const float4* __restrict__ rstd, const float4* __restrict__ gamma,
                                                                 const float4* __restrict__ dbeta, const float4* __restrict__ dgamma,
                                                                 float inv_count, long long n4, int C4, int relu,
-                                                                float4* __restrict__ dy) {
+                                                                float4* __restrict__ dy, uint2* __restrict__ dy16) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     int c = (int)(i % C4);
     float4 v = __ldg(y + i), g = __ldg(dout + i), m = __ldg(mean + c), r = __ldg(rstd + c), ga = __ldg(gamma + c);
@@ -112,7 +113,11 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const float4* __
     d.y = ga.y * r.y * (g.y - db.y * inv_count - (v.y - m.y) * r.y * dg.y * inv_count);
     d.z = ga.z * r.z * (g.z - db.z * inv_count - (v.z - m.z) * r.z * dg.z * inv_count);
     d.w = ga.w * r.w * (g.w - db.w * inv_count - (v.w - m.w) * r.w * dg.w * inv_count);
-    dy[i] = d;
+    if (dy) dy[i] = d;
+    if (dy16) {        // bf16 copy = the operand of the GEMMs that consume the gradient (deblock rows in the bf16 configuration)
+      __nv_bfloat162 lo = __floats2bfloat162_rn(d.x, d.y), hi = __floats2bfloat162_rn(d.z, d.w);
+      dy16[i] = make_uint2(*reinterpret_cast<unsigned*>(&lo), *reinterpret_cast<unsigned*>(&hi));
+    }
   }
 }
 
@@ -159,9 +164,9 @@ extern "C" int gdmae_batchnorm_relu_fwd(const float* y, const float* gamma, cons
 // extra_dbeta / extra_dgamma (C, nullable) are added to the batch sums (rows that exist only implicitly).
 extern "C" int gdmae_batchnorm_relu_bwd(const float* y, const float* beta, const float* dout, const float* gamma, const float* mean,
                                         const float* rstd, int64_t N, int C, double count, int relu, const float* extra_dbeta,
-                                        const float* extra_dgamma, float* dy, float* dgamma, float* dbeta, void* workspace,
-                                        size_t ws_bytes, void* stream_) {
-  GDMAE_CHECK_ARG(N >= 0 && C > 0 && (C % 4) == 0 && (C / 4) <= 256 && count >= (double)N && count >= 1.0);
+                                        const float* extra_dgamma, float* dy, void* dy_bf16, float* dgamma, float* dbeta,
+                                        void* workspace, size_t ws_bytes, void* stream_) {
+  GDMAE_CHECK_ARG(N >= 0 && C > 0 && (C % 4) == 0 && (C / 4) <= 256 && count >= (double)N && count >= 1.0 && (dy || dy_bf16));
   if (ws_bytes < gdmae_batchnorm_workspace_bytes(C)) { gdmae_set_error("batchnorm: workspace too small"); return GDMAE_ERR_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream_;
   float* partial = (float*)workspace;
@@ -180,7 +185,7 @@ extern "C" int gdmae_batchnorm_relu_bwd(const float* y, const float* beta, const
   if (N == 0) return GDMAE_OK;
   bn_relu_bwd_apply_kernel<<<gdmae_grid(N * C4, 256, 16), 256, 0, st>>>(
       (const float4*)y, (const float4*)beta, (const float4*)dout, (const float4*)mean, (const float4*)rstd, (const float4*)gamma,
-      (const float4*)dbeta, (const float4*)dgamma, (float)(1.0 / count), N * C4, C4, relu, (float4*)dy);
+      (const float4*)dbeta, (const float4*)dgamma, (float)(1.0 / count), N * C4, C4, relu, (float4*)dy, (uint2*)dy_bf16);
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;
 }

@@ -504,10 +504,75 @@ class BatchNormReLUFunction(torch.autograd.Function):
         lib = L.lib()
         ws = L.workspace(lib.gdmae_batchnorm_workspace_bytes(C), dev)
         L.check(lib.gdmae_batchnorm_relu_bwd(L.P(y), L.P(beta), L.P(dout.contiguous()), L.P(gamma), L.P(mean), L.P(rstd), L.i64(N), C,
-                                             ctypes.c_double(ctx.count), int(ctx.relu), L.P(e_db), L.P(e_dg), L.P(dy), L.P(dgamma),
+                                             ctypes.c_double(ctx.count), int(ctx.relu), L.P(e_db), L.P(e_dg), L.P(dy), None, L.P(dgamma),
                                              L.P(dbeta), L.P(ws), ctypes.c_size_t(ws.numel()), L.stream()),
                 "gdmae_batchnorm_relu_bwd")
         return dy, dgamma, dbeta, None, None, None, None, None, None
+
+
+class DeblockRowsFunction(torch.autograd.Function):
+    """One decoder deblock on its sparse rows in the bf16 configuration: ConvTranspose2d(k = stride) as ONE GEMM
+    (N, C_in) x (C_in, k*k*C_out) on the own tcgen05 kernel + training-mode BatchNorm2d + ReLU over the N*k*k produced rows
+    (statistics over ``count`` cells, the others are zeros) - spt_backbone_mae.py:31-44, 125-132.  One autograd node so
+    that the BatchNorm backward can hand its gradient to the two backward GEMMs as bf16 (no fp32 round trip, no cast pass):
+    dx = du W^T, dW = x^T du (K = rows, split over the SMs).  Returns (rows (N*k*k, C_out) fp32, bg (C_out))."""
+
+    @staticmethod
+    def forward(ctx, x, weight, k, gamma, beta, running_mean, running_var, momentum, eps, count):
+        x = x.contiguous()
+        N, C_in = x.shape
+        c_out = weight.shape[1]
+        dev = x.device
+        xg = _LAST_OUT[1] if _LAST_OUT[0] is x else x.to(BF16)
+        wg = _gw(weight).permute(0, 2, 3, 1).reshape(C_in, k * k * c_out).contiguous()       # (C_in, [a, b, c_out]) bf16
+        u = tc_gemm(xg, wg, out_dtype=F32).view(N * k * k, c_out)
+        out = torch.empty_like(u)
+        mean = torch.empty((c_out,), dtype=F32, device=dev)
+        rstd = torch.empty((c_out,), dtype=F32, device=dev)
+        lib = L.lib()
+        ws = L.workspace(lib.gdmae_batchnorm_workspace_bytes(c_out), dev)
+        L.check(lib.gdmae_batchnorm_relu_fwd(L.P(u), L.P(gamma), L.P(beta), L.i64(u.shape[0]), c_out, ctypes.c_double(count), L.f32(eps),
+                                             L.f32(momentum), 1, L.P(out), L.P(mean), L.P(rstd), L.P(running_mean),
+                                             L.P(running_var), L.P(ws), ctypes.c_size_t(ws.numel()), L.stream()),
+                "gdmae_batchnorm_relu_fwd")
+        shift = beta - mean * rstd * gamma
+        ctx.save_for_backward(xg, wg, u, beta, gamma, mean, rstd, shift)
+        ctx.count, ctx.k, ctx.wshape = count, k, weight.shape
+        return out, torch.relu(shift)
+
+    @staticmethod
+    def backward(ctx, dout, dbg):
+        xg, wg, u, beta, gamma, mean, rstd, shift = ctx.saved_tensors
+        R, c_out = u.shape
+        N, C_in = xg.shape
+        k = ctx.k
+        dev = u.device
+        e_db = e_dg = None
+        if ctx.count > R and dbg is not None:
+            e_db = (dbg * (shift > 0)).contiguous().float()
+            e_dg = (e_db * (-mean * rstd)).contiguous()
+        du16 = torch.empty((R, c_out), dtype=BF16, device=dev)
+        dgamma = torch.empty((c_out,), dtype=F32, device=dev)
+        dbeta = torch.empty((c_out,), dtype=F32, device=dev)
+        lib = L.lib()
+        ws = L.workspace(lib.gdmae_batchnorm_workspace_bytes(c_out), dev)
+        L.check(lib.gdmae_batchnorm_relu_bwd(L.P(u), L.P(beta), L.P(dout.contiguous()), L.P(gamma), L.P(mean), L.P(rstd), L.i64(R), c_out,
+                                             ctypes.c_double(ctx.count), 1, L.P(e_db), L.P(e_dg), None, L.P(du16), L.P(dgamma),
+                                             L.P(dbeta), L.P(ws), ctypes.c_size_t(ws.numel()), L.stream()),
+                "gdmae_batchnorm_relu_bwd")
+        du16 = du16.view(N, k * k * c_out)
+        dx = tc_gemm(du16, wg.t(), out_dtype=F32) if ctx.needs_input_grad[0] else None
+        dw = tc_gemm(xg.t(), du16, out_dtype=F32, split_k=True)                               # (C_in, k*k*c_out)
+        dw = dw.view(C_in, k, k, c_out).permute(0, 3, 1, 2)
+        return dx, dw, None, dgamma, dbeta, None, None, None, None, None
+
+
+def deblock_rows(deconv, bn, k, x, count):
+    """ConvTranspose2d(k = stride) + BatchNorm2d(train) + ReLU on the sparse rows, bf16 configuration (see DeblockRowsFunction)"""
+    out, bg = DeblockRowsFunction.apply(x, deconv.weight, k, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps,
+                                        float(count))
+    bn.num_batches_tracked += 1
+    return out, bg
 
 
 def batchnorm_relu(bn, y, training, relu=True, count=None):

@@ -92,6 +92,10 @@ class SPTBackboneMAE(nn.Module):
         deconv, bn = self.decoder_deblocks[i][0], self.decoder_deblocks[i][1]
         k = self.fuse_strides[i]
         c_out = deconv.out_channels
+        if (_fused.GEMM_DTYPE == torch.bfloat16 and self.training and deconv.bias is None and deconv.in_channels % 64 == 0
+                and (k * k * c_out) % 64 == 0):
+            # bf16 configuration: GEMM on the own tcgen05 kernel, BatchNorm backward hands bf16 gradients to the backward GEMMs
+            return _fused.deblock_rows(deconv, bn, k, sp.features, n_cells_total)
         w = deconv.weight.permute(0, 2, 3, 1).reshape(deconv.in_channels, k * k * c_out)  # (C_in, [a, b, c_out])
         u = (sp.features @ w).view(-1, c_out)                                                 # (N*k*k, c_out)
         # fused BN(batch statistics over all B*Y*X cells, zeros included)+ReLU on the sparse rows; bg = value of an empty cell

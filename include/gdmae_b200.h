@@ -372,8 +372,8 @@ int gdmae_batchnorm_relu_fwd(const float* y, const float* gamma, const float* be
                              float* running_mean, float* running_var, void* workspace, size_t ws_bytes, void* stream);
 int gdmae_batchnorm_relu_bwd(const float* y, const float* beta, const float* dout, const float* gamma, const float* mean,
                              const float* rstd, int64_t N, int C, double count, int relu, const float* extra_dbeta,
-                             const float* extra_dgamma, float* dy, float* dgamma, float* dbeta, void* workspace,
-                             size_t ws_bytes, void* stream);
+                             const float* extra_dgamma, float* dy /* nullable */, void* dy_bf16 /* nullable: bf16 copy of dy */,
+                             float* dgamma, float* dbeta, void* workspace, size_t ws_bytes, void* stream);
 
 /* ---- a22/a23 decoder dense fill and pillar gather --------------------------------------------
  * replaces SparseConvTensor.dense() + ConvTranspose2d(k=s) + BatchNorm2d + ReLU + torch.cat
