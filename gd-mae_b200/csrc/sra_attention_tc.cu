@@ -185,12 +185,22 @@ __device__ __forceinline__ void mm_unit(const MmArgs& a, const bf16* sq, const b
   constexpr int KS = HD / 16, ND = HD / 8;
   const int g = lane >> 2, t = lane & 3;
   const int loA = recA.y - kbase, wA = recA.z - recA.y, loB = recB.y - kbase, wB = recB.z - recB.y;
+  // Operand addresses: three swizzled base offsets per entry; every further tile is a compile-time offset from them.  Rows:
+  // + 16 rows = + one group; + 8 rows alternates between + 512 elements and + (group - 512) depending on bit 3 of the first
+  // row.  Channels: + 16 / + 32 channels toggles bit 1 / 2 of the 16-byte chunk index, which the bases leave clear
+  // (ch is a multiple of 32 wherever a channel step is taken), so it is an XOR on the offset.  (r2 profile: the generic
+  // form spent ~7 integer instructions on each of the 11-25 ldmatrix addresses of an entry.)
+  const int qoff = SWF(q0 + (lane & 7) + 8 * ((lane >> 3) & 1), ch + 8 * (lane >> 4));
+  const int krow = KS == 2 ? k0 + (lane & 7) : k0 + 8 * (lane >> 4) + (lane & 7);
+  const int koff0 = SWF(krow, ch + (KS == 2 ? 8 * (lane >> 3) : 8 * ((lane >> 3) & 1)));
+  const int koffA = koff0 + ((krow & 8) ? MF_GROUP - 512 : 512);          // KS == 2: the odd 8-key tiles
+  const int voff = SWF(k0 + (lane & 7) + 8 * ((lane >> 3) & 1), ch + 8 * (lane >> 4));
   unsigned qa[NH][KS][4];
 #pragma unroll
   for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
     for (int hh = 0; hh < NH; ++hh)
-      ldsm_x4(qa[hh][ks], sq + SWF(q0 + (lane & 7) + 8 * ((lane >> 3) & 1), ch + hh * HD + 16 * ks + 8 * (lane >> 4)));
+      ldsm_x4(qa[hh][ks], sq + (qoff ^ (hh * HD + 16 * ks)));
   float c[NH][NT2][4];
 #pragma unroll
   for (int hh = 0; hh < NH; ++hh)
@@ -204,7 +214,7 @@ __device__ __forceinline__ void mm_unit(const MmArgs& a, const bf16* sq, const b
         unsigned kb[NH][4];
 #pragma unroll
         for (int hh = 0; hh < NH; ++hh)
-          ldsm_x4(kb[hh], sk + SWF(k0 + 8 * (2 * np + u) + (lane & 7), ch + hh * HD + 8 * (lane >> 3)));
+          ldsm_x4(kb[hh], sk + (((u ? koffA : koff0) + np * MF_GROUP) ^ (hh * HD)));
 #pragma unroll
         for (int hh = 0; hh < NH; ++hh) mma_bf16(c[hh][2 * np + u], qa[hh][0], kb[hh][0], kb[hh][1]);
 #pragma unroll
@@ -214,7 +224,7 @@ __device__ __forceinline__ void mm_unit(const MmArgs& a, const bf16* sq, const b
       unsigned kb[NH][4];
 #pragma unroll
       for (int hh = 0; hh < NH; ++hh)
-        ldsm_x4(kb[hh], sk + SWF(k0 + 16 * np + 8 * (lane >> 4) + (lane & 7), ch + hh * HD + 8 * ((lane >> 3) & 1)));
+        ldsm_x4(kb[hh], sk + ((koff0 + np * MF_GROUP) ^ (hh * HD)));
 #pragma unroll
       for (int hh = 0; hh < NH; ++hh) {
         mma_bf16(c[hh][2 * np], qa[hh][0], kb[hh][0], kb[hh][1]);
@@ -287,7 +297,7 @@ __device__ __forceinline__ void mm_unit(const MmArgs& a, const bf16* sq, const b
       unsigned vb[NH][4];
 #pragma unroll
       for (int hh = 0; hh < NH; ++hh)
-        ldsm_x4_t(vb[hh], sv + SWF(k0 + 16 * kt + (lane & 7) + 8 * ((lane >> 3) & 1), ch + hh * HD + 16 * np + 8 * (lane >> 4)));
+        ldsm_x4_t(vb[hh], sv + ((voff + kt * MF_GROUP) ^ (hh * HD + 16 * np)));
 #pragma unroll
       for (int hh = 0; hh < NH; ++hh) {
         mma_bf16(o[hh][2 * np], pa[hh], vb[hh][0], vb[hh][1]);
@@ -548,10 +558,16 @@ __device__ __forceinline__ float mb_unit_q(const MbArgs& a, const bf16* sq, cons
   const int g = lane >> 2, t = lane & 3, ch = h * HD;
   const int loA = recA.y - kbase, wA = recA.z - recA.y, loB = recB.y - kbase, wB = recB.z - recB.y;
   const int ka = 2 * t - loA, kb_ = 2 * t - loB;
+  // operand addresses as in the forward kernel: swizzled bases, compile-time group / half-group steps, XOR channel steps
+  const int qoff = SWB(q0 + (lane & 7) + 8 * ((lane >> 3) & 1), ch + 8 * (lane >> 4));
+  const int krow = KS == 2 ? k0 + (lane & 7) : k0 + 8 * (lane >> 4) + (lane & 7);
+  const int koff0 = SWB(krow, ch + (KS == 2 ? 8 * (lane >> 3) : 8 * ((lane >> 3) & 1)));
+  const int koffA = koff0 + ((krow & 8) ? MB_GROUP - 512 : 512);
+  const int voff = SWB(k0 + (lane & 7) + 8 * ((lane >> 3) & 1), ch + 8 * (lane >> 4));
   unsigned qa[KS][4], da[KS][4];
 #pragma unroll
   for (int ks = 0; ks < KS; ++ks) {
-    const int off = SWB(q0 + (lane & 7) + 8 * ((lane >> 3) & 1), ch + 16 * ks + 8 * (lane >> 4));
+    const int off = qoff ^ (16 * ks);
     ldsm_x4(qa[ks], sq + off);
     ldsm_x4(da[ks], sdo + off);
   }
@@ -572,7 +588,7 @@ __device__ __forceinline__ float mb_unit_q(const MbArgs& a, const bf16* sq, cons
     if (KS == 2) {
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        const int off = SWB(k0 + 8 * (2 * np + u) + (lane & 7), ch + 8 * (lane >> 3));
+        const int off = (u ? koffA : koff0) + np * MB_GROUP;
         ldsm_x4(kb, sk + off);
         ldsm_x4(vb, sv + off);
         mma_bf16(s[u], qa[0], kb[0], kb[1]);
@@ -581,7 +597,7 @@ __device__ __forceinline__ float mb_unit_q(const MbArgs& a, const bf16* sq, cons
         mma_bf16(dp[2 * np + u], da[KS - 1], vb[2], vb[3]);
       }
     } else {
-      const int off = SWB(k0 + 16 * np + 8 * (lane >> 4) + (lane & 7), ch + 8 * ((lane >> 3) & 1));
+      const int off = koff0 + np * MB_GROUP;
       ldsm_x4(kb, sk + off);
       ldsm_x4(vb, sv + off);
       mma_bf16(s[0], qa[0], kb[0], kb[1]);
@@ -643,7 +659,7 @@ __device__ __forceinline__ float mb_unit_q(const MbArgs& a, const bf16* sq, cons
 #pragma unroll
     for (int np = 0; np < ND / 2; ++np) {
       unsigned kb[4];
-      ldsm_x4_t(kb, sk + SWB(k0 + 16 * kt + (lane & 7) + 8 * ((lane >> 3) & 1), ch + 16 * np + 8 * (lane >> 4)));
+      ldsm_x4_t(kb, sk + ((voff + kt * MB_GROUP) ^ (16 * np)));
       mma_bf16(acc[2 * np], sa, kb[0], kb[1]);
       mma_bf16(acc[2 * np + 1], sa, kb[2], kb[3]);
     }
@@ -652,11 +668,12 @@ __device__ __forceinline__ float mb_unit_q(const MbArgs& a, const bf16* sq, cons
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const int row = q0 + g + 8 * half;
+    const int noff = SWB(row, ch + 2 * t);
     float2 qv[ND];
     float dot = 0.f;
 #pragma unroll
     for (int nd = 0; nd < ND; ++nd) {
-      qv[nd] = unpack_bf16(*reinterpret_cast<const unsigned*>(sq + SWB(row, ch + 8 * nd + 2 * t)));
+      qv[nd] = unpack_bf16(*reinterpret_cast<const unsigned*>(sq + (noff ^ (8 * nd))));
       dot = fmaf(qv[nd].x, acc[nd][2 * half], dot);
       dot = fmaf(qv[nd].y, acc[nd][2 * half + 1], dot);
     }
@@ -683,10 +700,15 @@ __device__ __forceinline__ void mb_unit_kv(const MbArgs& a, const bf16* sq, cons
   const int g = lane >> 2, t = lane & 3, ch = h * HD;
   const int loA = recA.y - kbase, wA = recA.z - recA.y, loB = recB.y - kbase, wB = recB.z - recB.y;
   const int ka = 2 * t - loA, kb_ = 2 * t - loB;
+  const int aoff = SWB(q0 + (lane & 7) + 8 * ((lane >> 3) & 1), ch + 8 * (lane >> 4));
+  const int krow = KS == 2 ? k0 + (lane & 7) : k0 + 8 * (lane >> 4) + (lane & 7);
+  const int koff0 = SWB(krow, ch + (KS == 2 ? 8 * (lane >> 3) : 8 * ((lane >> 3) & 1)));
+  const int koffA = koff0 + ((krow & 8) ? MB_GROUP - 512 : 512);
+  const int voff = SWB(k0 + (lane & 7) + 8 * ((lane >> 3) & 1), ch + 8 * (lane >> 4));
   unsigned ka_f[KS][4], va_f[KS][4];
 #pragma unroll
   for (int ks = 0; ks < KS; ++ks) {
-    const int off = SWB(q0 + (lane & 7) + 8 * ((lane >> 3) & 1), ch + 16 * ks + 8 * (lane >> 4));
+    const int off = aoff ^ (16 * ks);
     ldsm_x4(ka_f[ks], sk + off);
     ldsm_x4(va_f[ks], sv + off);
   }
@@ -708,7 +730,7 @@ __device__ __forceinline__ void mb_unit_kv(const MbArgs& a, const bf16* sq, cons
     if (KS == 2) {
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        const int off = SWB(k0 + 8 * (2 * np + u) + (lane & 7), ch + 8 * (lane >> 3));
+        const int off = (u ? koffA : koff0) + np * MB_GROUP;
         ldsm_x4(qb, sq + off);
         ldsm_x4(ob, sdo + off);
         mma_bf16(s[u], ka_f[0], qb[0], qb[1]);
@@ -717,7 +739,7 @@ __device__ __forceinline__ void mb_unit_kv(const MbArgs& a, const bf16* sq, cons
         mma_bf16(dp[u], va_f[KS - 1], ob[2], ob[3]);
       }
     } else {
-      const int off = SWB(k0 + 16 * np + 8 * (lane >> 4) + (lane & 7), ch + 8 * ((lane >> 3) & 1));
+      const int off = koff0 + np * MB_GROUP;
       ldsm_x4(qb, sq + off);
       ldsm_x4(ob, sdo + off);
       mma_bf16(s[0], ka_f[0], qb[0], qb[1]);
@@ -745,7 +767,7 @@ __device__ __forceinline__ void mb_unit_kv(const MbArgs& a, const bf16* sq, cons
 #pragma unroll
     for (int nq = 0; nq < ND / 2; ++nq) {
       unsigned ob2[4], qb2[4];
-      const int off = SWB(k0 + 16 * np + (lane & 7) + 8 * ((lane >> 3) & 1), ch + 16 * nq + 8 * (lane >> 4));
+      const int off = (voff + np * MB_GROUP) ^ (16 * nq);
       ldsm_x4_t(ob2, sdo + off);
       ldsm_x4_t(qb2, sq + off);
       mma_bf16(dv[2 * nq], pa, ob2[0], ob2[1]);
@@ -757,11 +779,12 @@ __device__ __forceinline__ void mb_unit_kv(const MbArgs& a, const bf16* sq, cons
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const int row = q0 + g + 8 * half;
+    const int noff = SWB(row, ch + 2 * t);
     float2 kv[ND];
     float dot = 0.f;
 #pragma unroll
     for (int nd = 0; nd < ND; ++nd) {
-      kv[nd] = unpack_bf16(*reinterpret_cast<const unsigned*>(sk + SWB(row, ch + 8 * nd + 2 * t)));
+      kv[nd] = unpack_bf16(*reinterpret_cast<const unsigned*>(sk + (noff ^ (8 * nd))));
       dot = fmaf(kv[nd].x, hk[nd][2 * half], dot);
       dot = fmaf(kv[nd].y, hk[nd][2 * half + 1], dot);
     }
