@@ -6,17 +6,19 @@
 //
 // r2 layout ("window-major"): the in-projection GEMM's epilogue (tc_gemm.cu, mode 4) adds the positional LUT row,
 // L2-normalises q and k per head in fp32, folds log2(e)/tau into q and writes q^, k^, v as bf16 ROWS IN CSR (WINDOW)
-// ORDER, one plane per (tensor, 64-channel slice):  qkvw[(part * d/64 + slice)][row][64].  The rows of a bin are then
-// one contiguous rectangle per plane, so a bin is fetched with a handful of cp.async.bulk.tensor (TMA) boxes of 16 rows x
-// 128 bytes issued by ONE thread - the r1 kernel gathered 128-byte row pieces with 1536 cp.async instructions per bin and
-// re-did the normalisation in every launch (forward, and again in backward); a copy-only build of it ran at 1.9 TB/s.
+// ORDER: qkvw[tensor][d/64 slices][row][64] (dO joins as a fourth tensor for the backward, mode 5).  The rows of a bin are
+// then one contiguous rectangle per (tensor, slice), so a bin is fetched by TMA: ONE cp.async.bulk.tensor (4-D box: 64
+// channels x 16 rows x 1 slice x all tensors) per 16 rows, issued by one thread - the r1 kernel gathered 128-byte row
+// pieces with 1536 cp.async instructions per bin and re-did the normalisation in every launch (forward, and again in
+// backward); a copy-only build of it ran at 1.9 TB/s.
 //   * persistent, one CTA per SM, each owning a 64-channel slice (2 heads of 32 or 4 heads of 16) and walking bins of 64
 //     CSR rows (the windows that START in the bin, <= 127 rows);
-//   * warp 0 is the producer: per bin one mbarrier.expect_tx, bulk copies of the row records / work units (/ per-row
-//     scalars in the backward) and the TMA boxes of the tiles; the other 15 warps run the MMAs.  The two roles meet only
-//     through mbarriers (bin landed / bin consumed) - no CTA barrier inside the bin loop;
-//   * SWIZZLE_128B tiles (row r, 16-byte chunk c at r * 128 + ((c ^ (r & 7)) << 4)): every ldmatrix phase touches the 32
-//     banks once, and the tile needs no padding;
+//   * warp 0 is the producer: per bin one mbarrier.expect_tx, ONE bulk copy of the bin's table block (work units + row
+//     records; + the per-row scalars in the backward) and ceil(rows / 16) boxes; the other 15 warps run the MMAs.  The two
+//     roles meet only through mbarriers (bin landed / bin consumed) - no CTA barrier inside the bin loop;
+//   * staging memory is a RING of 16-row groups ({q, k, v[, dO]} boxes of 16 rows each, SWIZZLE_128B: 16-byte chunk c of
+//     row r at chunk c ^ (r & 7), so every ldmatrix phase touches the 32 banks once and nothing is padded); a bin takes
+//     ceil(rows / 16) consecutive groups, ~7 bins are in flight in the forward kernel;
 //   * the work units of every bin are built ONCE per window table (gdmae_sra_bin_units: a table serves two layers,
 //     forward and backward) and arrive with the bin's row records; (unit, head) entries are handed out through a
 //     shared-memory counter that arrives zeroed with them;

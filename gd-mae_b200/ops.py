@@ -570,6 +570,34 @@ class DecoderConv3x3(torch.autograd.Function):
         return dx, dw.permute(0, 3, 1, 2), None
 
 
+class TallLinear(torch.autograd.Function):
+    """y = x W^T + b for a tall x (M rows = all pillars, 10^5..10^6) and a small W (decoder_pred, spt_backbone_mae.py:57,84).
+    Forward and input gradient are plain library GEMMs; the weight gradient dW = dy^T x has K = M: the library picks a kernel
+    without split-K for it (r2 timeline: 193 us on 4 SMs' worth of tiles), so it is taken as a batched product over S row
+    blocks (one tile per block on every SM) followed by a sum over the blocks."""
+    S = 128
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        return torch.addmm(bias, x, weight.t())
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        M = x.shape[0]
+        dx = dy @ weight if ctx.needs_input_grad[0] else None
+        S = TallLinear.S
+        mb = M // S
+        if mb >= 8:
+            head = torch.bmm(dy[:mb * S].view(S, mb, -1).transpose(1, 2), x[:mb * S].view(S, mb, -1)).sum(0)
+            dw = head if mb * S == M else head.addmm_(dy[mb * S:].t(), x[mb * S:])
+        else:
+            dw = dy.t() @ x
+        return dx, dw, dy.sum(0)
+
+
 # ----------------------------------------------------------------------------- chamfer head
 def group_points_centered(ps, pc_range, voxel_size, K):
     """gt_points - voxel_centers of target_assigner (spt_backbone_mae.py:67-72), (M, K, 3)."""

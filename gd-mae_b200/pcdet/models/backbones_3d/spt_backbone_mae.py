@@ -81,7 +81,11 @@ class SPTBackboneMAE(nn.Module):
         norm_gt_points = batch_dict.get('mae_gt_points', None)      # prefetched by index_pass, else built here
         if norm_gt_points is None:
             norm_gt_points = _ops.group_points_centered(ps, self.point_cloud_range, self.voxel_size, K)
-        pred_points = self.decoder_pred(voxel_features).view(voxel_features.shape[0], -1, 3)
+        if voxel_features.is_cuda and self.training:
+            pred_points = _ops.TallLinear.apply(voxel_features.contiguous(), self.decoder_pred.weight, self.decoder_pred.bias)
+        else:
+            pred_points = self.decoder_pred(voxel_features)
+        pred_points = pred_points.view(voxel_features.shape[0], -1, 3)
         return {'pred_points': pred_points, 'gt_points': norm_gt_points, 'mask': batch_dict['voxel_mae_mask']}
 
     # ------------------------------------------------------------------ decoder (:123-132)

@@ -159,6 +159,24 @@ class MAETrainer:
                 fused.BF16_SHADOW[p.data_ptr()] = self.flat_bf16[off:off + p.numel()].view(p.shape)
         self.flat_bf16.copy_(self.flat_params)
 
+    def release_bf16_mirror(self):
+        """Drops this trainer's entries of fused.BF16_SHADOW (keyed by raw data pointers): a later model whose parameters land
+        on recycled addresses must not pick up a dead trainer's mirror.  Called by __del__; call it explicitly
+        before building another trainer in the same process."""
+        from . import fused
+        if self.flat_bf16 is not None:
+            for p in self._params:
+                sh = fused.BF16_SHADOW.get(p.data_ptr())
+                if sh is not None and sh.untyped_storage().data_ptr() == self.flat_bf16.untyped_storage().data_ptr():
+                    del fused.BF16_SHADOW[p.data_ptr()]
+            self.flat_bf16 = None
+
+    def __del__(self):
+        try:
+            self.release_bf16_mirror()
+        except Exception:
+            pass
+
     def _comm(self):
         if self._comm_stream is None:
             self._comm_stream = torch.cuda.Stream(device=self.flat_grads.device, priority=-1)
