@@ -652,6 +652,59 @@ def test_conv3x3_wgrad_matches_torch(G):
     assert to._obj.value == 0
 
 
+def test_deblock_rows_and_tall_linear_match_torch(G):
+    """fused.DeblockRowsFunction (ConvTranspose2d as a GEMM on the sparse rows + BatchNorm + ReLU in one node, bf16 operands on
+    the own tcgen05 GEMM, bf16 gradient hand-over) against the same computation written with torch in fp32, forward and all
+    gradients; ops.TallLinear (decoder_pred with the block-wise weight gradient) against F.linear."""
+    from gd_mae_b200 import fused
+    torch.manual_seed(3)
+    old = fused.GEMM_DTYPE
+    fused.GEMM_DTYPE = torch.bfloat16
+    try:
+        for C_in, c_out, k, N in ((128, 128, 1, 3001), (256, 128, 2, 2500), (256, 128, 4, 1777)):
+            deconv = torch.nn.ConvTranspose2d(C_in, c_out, k, stride=k, bias=False).cuda()
+            bn = torch.nn.BatchNorm2d(c_out, eps=1e-3, momentum=0.01).cuda()
+            with torch.no_grad():
+                bn.weight.uniform_(0.5, 1.5)
+                bn.bias.uniform_(-0.3, 0.3)
+            x = torch.randn(N, C_in, device="cuda", requires_grad=True)
+            count = float(N * k * k * 3)
+            out, bg = fused.deblock_rows(deconv, bn, k, x, count)
+            gout, gbg = torch.randn_like(out), torch.randn_like(bg)
+            (out * gout).sum().add((bg * gbg).sum()).backward()
+            got = [out, bg, x.grad.clone(), deconv.weight.grad.clone(), bn.weight.grad.clone(), bn.bias.grad.clone()]
+            # torch fp32 reference of the same function
+            x2 = x.detach().clone().requires_grad_()
+            w2 = deconv.weight.detach().clone().requires_grad_()
+            g2, b2 = bn.weight.detach().clone().requires_grad_(), bn.bias.detach().clone().requires_grad_()
+            u = (x2 @ w2.permute(0, 2, 3, 1).reshape(C_in, k * k * c_out)).view(-1, c_out)
+            mean = u.sum(0) / count
+            var = (u * u).sum(0) / count - mean * mean
+            rstd = torch.rsqrt(var + bn.eps)
+            ref_out = torch.relu((u - mean) * rstd * g2 + b2)
+            ref_bg = torch.relu(b2 - mean * rstd * g2)
+            (ref_out * gout).sum().add((ref_bg * gbg).sum()).backward()
+            ref = [ref_out, ref_bg, x2.grad, w2.grad, g2.grad, b2.grad]
+            for name, a, b in zip(("out", "bg", "dx", "dW", "dgamma", "dbeta"), got, ref):
+                e = rel(a, b)
+                print(f"deblock k={k} {name}: rel err {e:.2e}")
+                assert e < 2e-2, (k, name, e)          # bf16 GEMM operands (8-bit mantissa) against fp32
+    finally:
+        fused.GEMM_DTYPE = old
+    x = torch.randn(50003, 128, device="cuda", requires_grad=True)
+    lin = torch.nn.Linear(128, 48).cuda()
+    y = G.ops.TallLinear.apply(x, lin.weight, lin.bias)
+    g = torch.randn_like(y)
+    y.backward(g)
+    got = [y, x.grad.clone(), lin.weight.grad.clone(), lin.bias.grad.clone()]
+    x2 = x.detach().clone().requires_grad_()
+    lin.zero_grad()
+    y2 = torch.nn.functional.linear(x2, lin.weight, lin.bias)
+    y2.backward(g)
+    for name, a, b in zip(("y", "dx", "dW", "db"), got, [y2, x2.grad, lin.weight.grad, lin.bias.grad]):
+        assert rel(a, b) < 1e-5, (name, rel(a, b))
+
+
 def ctypes_int():
     import ctypes
     return ctypes.byref(ctypes.c_int(0))
