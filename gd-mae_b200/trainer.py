@@ -126,6 +126,7 @@ class MAETrainer:
         self.max_steps_in_flight = 2
         self._inflight = []
         self._comm_stream = None
+        self._loss_ring = None       # loss_to_host(): two pinned slots + their copy-complete events
         self._early_work = None
         self._late_works = []
         # multi-GPU schedule knobs (measured on 2 B200s, r2)
@@ -312,6 +313,57 @@ class MAETrainer:
             "gdmae_adam_onecycle_step")
         self.it += 1
         return lr, mom
+
+    def reserve_memory(self, main_gb=24.0, side_gb=2.0, extra_streams=()):
+        """Maps device memory for the caching allocator's pools up front: one block of ``main_gb`` on the current stream and
+        one of ``side_gb`` on every side stream of the step (the index-prefetch stream, ``extra_streams`` such as the caller's
+        H2D copy stream) is allocated and released again, which leaves the address range mapped and cached.  Batches differ in
+        size from step to step, so the pools keep growing by a few blocks long after warm-up; growing a pool inside a step
+        costs one cuMemCreate + cuMemMap per 20 MB (r2 measurement: 30-120 ms of host stall per growth of the step's
+        GB-sized buffers, 1-6 of them inside a 20-step timed leg on a fresh box).  A B200 has 180 GB; the step peaks far below
+        the default reservation."""
+        if not self.flat_grads.is_cuda:
+            return
+        dev = self.flat_grads.device
+        if hasattr(self.model, 'prefetch_index') and getattr(self.model, '_side_stream', None) is None:
+            self.model._side_stream = torch.cuda.Stream(device=dev, priority=-1)
+        plan = [(torch.cuda.current_stream(dev), main_gb)]
+        plan += [(st, side_gb) for st in [getattr(self.model, '_side_stream', None), *extra_streams] if st is not None]
+        free_b, _ = torch.cuda.mem_get_info(dev)
+        for st, gb in plan:
+            nbytes = int(min(gb * 2 ** 30, 0.5 * free_b))
+            with torch.cuda.stream(st):
+                block = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                del block
+        torch.cuda.synchronize(dev)
+
+    def loss_to_host(self, loss):
+        """The per-iteration `loss.item()` of train_one_epoch (tools/train_utils/train_utils.py:68-79: on rank 0 only, the value
+        feeds the progress bar and tensorboard) without draining the launch queue: the loss of THIS iteration is copied to a pinned host slot behind the
+        step on the current stream, and the call returns the loss of the PREVIOUS iteration (None on the first call), waiting
+        only for that older copy.  One device-to-host read per iteration; the host stays one step ahead of the device.
+        `drain_loss()` returns the newest value (blocking)."""
+        if self._loss_ring is None:
+            self._loss_ring = {"buf": torch.empty(2, dtype=torch.float32).pin_memory(), "ev": [None, None], "k": 0}
+        r = self._loss_ring
+        k = r["k"]
+        r["buf"][k:k + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        r["ev"][k] = ev
+        r["k"] = k ^ 1
+        prev = r["ev"][k ^ 1]
+        if prev is None:
+            return None
+        prev.synchronize()
+        return float(r["buf"][k ^ 1])
+
+    def drain_loss(self):
+        r = self._loss_ring
+        if r is None or r["ev"][r["k"] ^ 1] is None:
+            return None
+        r["ev"][r["k"] ^ 1].synchronize()
+        return float(r["buf"][r["k"] ^ 1])
 
     def step(self, batch_dict, next_batch=None, next_ready_event=None):
         """One iteration (train_utils.py:34-53): zero_grad, forward, backward, all-reduce, clip, update.

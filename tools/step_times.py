@@ -57,3 +57,18 @@ for i, t_ in enumerate(ts):
         print(f"  hiccup step {i}: device {t_:.1f} ms, host enqueue {1e3 * (host[i + 1] - host[i]):.1f} ms (previous "
               f"{1e3 * (host[i] - host[i - 1]) if i else 0:.1f}, {1e3 * (host[i - 1] - host[i - 2]) if i > 1 else 0:.1f}), "
               f"cudaMallocs in step {mall[i + 1] - mall[i]} (previous {mall[i] - mall[i - 1] if i else 0})")
+# host time to ENQUEUE one step (queue empty at entry, so nothing inside step() waits for the device) and the device time of
+# the same step started from an empty queue: enqueue > device means the step is launch bound whenever the host cannot run ahead
+hq, dq = [], []
+for i in range(6):
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    a.record()
+    trainer.step({"points": batches[i % 4], "batch_size": 8})
+    b.record()
+    hq.append(1e3 * (time.perf_counter() - t0))
+    torch.cuda.synchronize()
+    dq.append(a.elapsed_time(b))
+print("host enqueue per step from an empty queue (ms): " + " ".join(f"{t:.1f}" for t in hq))
+print("device span of the same steps (ms):            " + " ".join(f"{t:.1f}" for t in dq))
