@@ -416,3 +416,163 @@ extern "C" int gdmae_decoder_tail_bwd(const void* y, int dtype, int B, int Y, in
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;
 }
+
+// =====================================================================================================
+// Typed BatchNorm + ReLU over (N, C) rows: y / out / dout / dy each fp32 or bf16 (dtype 0 / 1), 8-channel packets
+// (one 16-byte access per thread in bf16, two in fp32), per-thread channel constants in registers (every thread keeps its
+// channel packet for the whole launch: the trip length is a multiple of C8).  Used by the decoder deblocks of the bf16
+// configuration (spt_backbone_mae.py:31-44): their output rows only feed the bf16 dense map and their upstream gradient IS
+// bf16 (rows gathered from d(map)), so keeping both as bf16 loses nothing and halves four passes.
+template <typename TY, typename TO>
+__global__ void __launch_bounds__(256) bn8_relu_apply_kernel(const TY* __restrict__ y, const float* __restrict__ mean,
+                                                             const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, long long n8, int C8, int relu,
+                                                             TO* __restrict__ out) {
+  const int c = threadIdx.x % C8;      // blockDim.x = 256 is a multiple of C8
+  float m[8], r[8], g[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { m[i] = __ldg(mean + 8 * c + i); r[i] = __ldg(rstd + 8 * c + i); g[i] = __ldg(gamma + 8 * c + i); b[i] = __ldg(beta + 8 * c + i); }
+  const long long step = (long long)gridDim.x * blockDim.x;
+#pragma unroll 2
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += step) {
+    float v[8];
+    Row8<TY>::load(y, i, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      v[k] = (v[k] - m[k]) * r[k] * g[k] + b[k];
+      if (relu) v[k] = fmaxf(v[k], 0.f);
+    }
+    Row8<TO>::store(out, i, v);
+  }
+}
+
+template <typename TY, typename TD>
+__global__ void __launch_bounds__(256) bn8_relu_bwd_stats_kernel(const TY* __restrict__ y, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, const TD* __restrict__ dout,
+                                                                 const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                 long long N, int C8, int relu, float* __restrict__ partial) {
+  const int c = threadIdx.x % C8, rsub = threadIdx.x / C8, rper = blockDim.x / C8;
+  float m[8], r[8], ga[8], be[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { m[i] = __ldg(mean + 8 * c + i); r[i] = __ldg(rstd + 8 * c + i); ga[i] = __ldg(gamma + 8 * c + i); be[i] = __ldg(beta + 8 * c + i); }
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, q[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+  for (long long row = (long long)blockIdx.x * rper + rsub; row < N; row += (long long)gridDim.x * rper) {
+    float v[8], d[8];
+    Row8<TY>::load(y, row * C8 + c, v);
+    Row8<TD>::load(dout, row * C8 + c, d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float xh = (v[k] - m[k]) * r[k];
+      if (relu && !((v[k] - m[k]) * r[k] * ga[k] + be[k] > 0.f)) d[k] = 0.f;
+      s[k] += d[k];
+      q[k] = fmaf(d[k], xh, q[k]);
+    }
+  }
+  tail_block_reduce(s, q, C8, partial);        // [dbeta(C) | dgamma(C)] per CTA
+}
+
+template <typename TY, typename TD, typename TG>
+__global__ void __launch_bounds__(256) bn8_relu_bwd_apply_kernel(const TY* __restrict__ y, const float* __restrict__ beta,
+                                                                 const TD* __restrict__ dout, const float* __restrict__ mean,
+                                                                 const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ dbeta, const float* __restrict__ dgamma,
+                                                                 float inv_count, long long n8, int C8, int relu, TG* __restrict__ dy) {
+  const int c = threadIdx.x % C8;
+  float m[8], r[8], ga[8], be[8], db[8], dg[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    m[i] = __ldg(mean + 8 * c + i); r[i] = __ldg(rstd + 8 * c + i); ga[i] = __ldg(gamma + 8 * c + i); be[i] = __ldg(beta + 8 * c + i);
+    db[i] = __ldg(dbeta + 8 * c + i) * inv_count; dg[i] = __ldg(dgamma + 8 * c + i);
+  }
+  const long long step = (long long)gridDim.x * blockDim.x;
+#pragma unroll 2
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += step) {
+    float v[8], d[8];
+    Row8<TY>::load(y, i, v);
+    Row8<TD>::load(dout, i, d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float xh = (v[k] - m[k]) * r[k];
+      if (relu && !((v[k] - m[k]) * r[k] * ga[k] + be[k] > 0.f)) d[k] = 0.f;
+      d[k] = ga[k] * r[k] * (d[k] - db[k] - xh * dg[k] * inv_count);
+    }
+    Row8<TG>::store(dy, i, d);
+  }
+}
+
+#define BN8_DISPATCH2(A, B, CALL)                                                  \
+  do {                                                                             \
+    if ((A) == 0 && (B) == 0) { using T0 = float; using T1 = float; CALL; }        \
+    else if ((A) == 0) { using T0 = float; using T1 = __nv_bfloat16; CALL; }       \
+    else if ((B) == 0) { using T0 = __nv_bfloat16; using T1 = float; CALL; }       \
+    else { using T0 = __nv_bfloat16; using T1 = __nv_bfloat16; CALL; }             \
+  } while (0)
+
+// as gdmae_batchnorm_relu_fwd, y and out typed (0 = fp32, 1 = bf16); C % 8 == 0 and 256 % (C / 8) == 0
+extern "C" int gdmae_batchnorm_relu_fwd_t(const void* y, int y_dtype, const float* gamma, const float* beta, int64_t N, int C, double count,
+                                          float eps, float momentum, int relu, void* out, int out_dtype, float* mean, float* rstd,
+                                          float* running_mean, float* running_var, void* workspace, size_t ws_bytes, void* stream_) {
+  GDMAE_CHECK_ARG(N >= 0 && C > 0 && (C % 8) == 0 && 256 % (C / 8) == 0 && count >= (double)N && count >= 1.0);
+  GDMAE_CHECK_ARG((y_dtype == 0 || y_dtype == 1) && (out_dtype == 0 || out_dtype == 1));
+  if (ws_bytes < gdmae_batchnorm_workspace_bytes(C)) { gdmae_set_error("batchnorm: workspace too small"); return GDMAE_ERR_WORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream_;
+  float* partial = (float*)workspace;
+  const int C8 = C / 8, rper = 256 / C8;
+  int grid = (int)min((long long)BN_PART_BLOCKS, (long long)((N + rper - 1) / rper));
+  if (N == 0) {
+    GDMAE_CHECK_CUDA(cudaMemsetAsync(partial, 0, (size_t)2 * C * 4, st));
+    grid = 1;
+  } else {
+    if (y_dtype == 0) tail_dense_stats_kernel<float><<<grid, 256, 0, st>>>((const float*)y, N, C8, partial);
+    else tail_dense_stats_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)y, N, C8, partial);
+    GDMAE_LAUNCH_CHECK();
+  }
+  bn_finalize_kernel<<<gdmae_div_up(C * 32, 256), 256, 0, st>>>(partial, grid, C, count, eps, momentum, mean, rstd, running_mean, running_var);
+  GDMAE_LAUNCH_CHECK();
+  if (N == 0) return GDMAE_OK;
+  const long long n8 = N * C8;
+  const int g2 = gdmae_grid(n8, 256, 16);
+  BN8_DISPATCH2(y_dtype, out_dtype,
+                (bn8_relu_apply_kernel<T0, T1><<<g2, 256, 0, st>>>((const T0*)y, mean, rstd, gamma, beta, n8, C8, relu, (T1*)out)));
+  GDMAE_LAUNCH_CHECK();
+  return GDMAE_OK;
+}
+
+// as gdmae_batchnorm_relu_bwd, y / dout / dy typed (0 = fp32, 1 = bf16)
+extern "C" int gdmae_batchnorm_relu_bwd_t(const void* y, int y_dtype, const float* beta, const void* dout, int dout_dtype, const float* gamma,
+                                          const float* mean, const float* rstd, int64_t N, int C, double count, int relu,
+                                          const float* extra_dbeta, const float* extra_dgamma, void* dy, int dy_dtype, float* dgamma,
+                                          float* dbeta, void* workspace, size_t ws_bytes, void* stream_) {
+  GDMAE_CHECK_ARG(N >= 0 && C > 0 && (C % 8) == 0 && 256 % (C / 8) == 0 && count >= (double)N && count >= 1.0 && dy);
+  GDMAE_CHECK_ARG((y_dtype == 0 || y_dtype == 1) && (dout_dtype == 0 || dout_dtype == 1) && (dy_dtype == 0 || dy_dtype == 1));
+  if (ws_bytes < gdmae_batchnorm_workspace_bytes(C)) { gdmae_set_error("batchnorm: workspace too small"); return GDMAE_ERR_WORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream_;
+  float* partial = (float*)workspace;
+  const int C8 = C / 8, rper = 256 / C8;
+  int grid = (int)min((long long)BN_PART_BLOCKS, (long long)((N + rper - 1) / rper));
+  if (N == 0) {
+    GDMAE_CHECK_CUDA(cudaMemsetAsync(partial, 0, (size_t)2 * C * 4, st));
+    grid = 1;
+  } else {
+    BN8_DISPATCH2(y_dtype, dout_dtype,
+                  (bn8_relu_bwd_stats_kernel<T0, T1><<<grid, 256, 0, st>>>((const T0*)y, gamma, beta, (const T1*)dout, mean, rstd, N, C8, relu, partial)));
+    GDMAE_LAUNCH_CHECK();
+  }
+  bn_bwd_finalize_kernel<<<gdmae_div_up(C, 32), 256, 0, st>>>(partial, grid, C, extra_dbeta, extra_dgamma, dbeta, dgamma);
+  GDMAE_LAUNCH_CHECK();
+  if (N == 0) return GDMAE_OK;
+  const long long n8 = N * C8;
+  const int g2 = gdmae_grid(n8, 256, 16);
+  const float inv = (float)(1.0 / count);
+  if (dy_dtype == 0)
+    BN8_DISPATCH2(y_dtype, dout_dtype,
+                  (bn8_relu_bwd_apply_kernel<T0, T1, float><<<g2, 256, 0, st>>>((const T0*)y, beta, (const T1*)dout, mean, rstd, gamma, dbeta, dgamma,
+                                                                                inv, n8, C8, relu, (float*)dy)));
+  else
+    BN8_DISPATCH2(y_dtype, dout_dtype,
+                  (bn8_relu_bwd_apply_kernel<T0, T1, __nv_bfloat16><<<g2, 256, 0, st>>>((const T0*)y, beta, (const T1*)dout, mean, rstd, gamma, dbeta,
+                                                                                        dgamma, inv, n8, C8, relu, (__nv_bfloat16*)dy)));
+  GDMAE_LAUNCH_CHECK();
+  return GDMAE_OK;
+}

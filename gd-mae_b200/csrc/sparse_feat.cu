@@ -105,7 +105,7 @@ extern "C" int gdmae_gather_rows_transposed(const void* dcol, int in_dtype, cons
 // (Y/k_s, X/k_s) lattice and rows a_s (N_s * k_s^2, Cs): row (rank*k_s^2 + (y%k_s)*k_s + x%k_s).
 // Cells whose scale-s site is empty receive bg_s (Cs).
 struct DenseFillArgs {
-  const float* rows[3];
+  const void* rows[3];       // fp32 or bf16 (rows_dtype of the entry points)
   const float* bg[3];
   const int* grid[3];
   int k[3];
@@ -113,138 +113,172 @@ struct DenseFillArgs {
   int B, Y, X, Cs;
 };
 
-// 8-channel packets: fp32 = two 16-byte stores, bf16 = one 16-byte store
-template <typename T> struct Pack8;
-template <> struct Pack8<float> {
-  static __device__ __forceinline__ void store(float* p, long long i8, float4 a, float4 b) {
-    __stcs(reinterpret_cast<float4*>(p) + 2 * i8, a);
-    __stcs(reinterpret_cast<float4*>(p) + 2 * i8 + 1, b);
+// 8 channels as they lie in memory: fp32 = two float4, bf16 = one uint4.  Same-type moves copy the bits.
+template <typename T> struct P8;
+template <> struct P8<float> {
+  float4 a, b;
+  static __device__ __forceinline__ P8 load_stream(const float* p, long long i8) {
+    P8 r; r.a = __ldcs(reinterpret_cast<const float4*>(p) + 2 * i8); r.b = __ldcs(reinterpret_cast<const float4*>(p) + 2 * i8 + 1); return r;
   }
-  static __device__ __forceinline__ void load(const float* p, long long i8, float4& a, float4& b) {
-    a = __ldcs(reinterpret_cast<const float4*>(p) + 2 * i8);
-    b = __ldcs(reinterpret_cast<const float4*>(p) + 2 * i8 + 1);
+  static __device__ __forceinline__ P8 load_keep(const float* p, long long i8) {
+    P8 r; r.a = __ldg(reinterpret_cast<const float4*>(p) + 2 * i8); r.b = __ldg(reinterpret_cast<const float4*>(p) + 2 * i8 + 1); return r;
   }
-};
-template <> struct Pack8<__nv_bfloat16> {
-  static __device__ __forceinline__ void store(__nv_bfloat16* p, long long i8, float4 a, float4 b) {
-    __nv_bfloat162 x0 = __floats2bfloat162_rn(a.x, a.y), x1 = __floats2bfloat162_rn(a.z, a.w);
-    __nv_bfloat162 x2 = __floats2bfloat162_rn(b.x, b.y), x3 = __floats2bfloat162_rn(b.z, b.w);
-    float4 u;
-    u.x = __uint_as_float(*reinterpret_cast<unsigned*>(&x0)); u.y = __uint_as_float(*reinterpret_cast<unsigned*>(&x1));
-    u.z = __uint_as_float(*reinterpret_cast<unsigned*>(&x2)); u.w = __uint_as_float(*reinterpret_cast<unsigned*>(&x3));
-    __stcs(reinterpret_cast<float4*>(p) + i8, u);
+  __device__ __forceinline__ void store_stream(float* p, long long i8) const {
+    __stcs(reinterpret_cast<float4*>(p) + 2 * i8, a); __stcs(reinterpret_cast<float4*>(p) + 2 * i8 + 1, b);
   }
-  static __device__ __forceinline__ void load(const __nv_bfloat16* p, long long i8, float4& a, float4& b) {
-    float4 u = __ldcs(reinterpret_cast<const float4*>(p) + i8);
-    unsigned w0 = __float_as_uint(u.x), w1 = __float_as_uint(u.y), w2 = __float_as_uint(u.z), w3 = __float_as_uint(u.w);
-    float2 f0 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w0)), f1 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w1));
-    float2 f2 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w2)), f3 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w3));
-    a = make_float4(f0.x, f0.y, f1.x, f1.y);
-    b = make_float4(f2.x, f2.y, f3.x, f3.y);
+  __device__ __forceinline__ void add_to(float4& s0, float4& s1) const {
+    s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w; s1.x += b.x; s1.y += b.y; s1.z += b.z; s1.w += b.w;
   }
 };
+template <> struct P8<__nv_bfloat16> {
+  uint4 u;
+  static __device__ __forceinline__ P8 load_stream(const __nv_bfloat16* p, long long i8) {
+    P8 r; r.u = __ldcs(reinterpret_cast<const uint4*>(p) + i8); return r;
+  }
+  static __device__ __forceinline__ P8 load_keep(const __nv_bfloat16* p, long long i8) {
+    P8 r; r.u = __ldg(reinterpret_cast<const uint4*>(p) + i8); return r;
+  }
+  __device__ __forceinline__ void store_stream(__nv_bfloat16* p, long long i8) const { __stcs(reinterpret_cast<uint4*>(p) + i8, u); }
+  __device__ __forceinline__ void add_to(float4& s0, float4& s1) const {
+    s0.x += __uint_as_float(u.x << 16); s0.y += __uint_as_float(u.x & 0xffff0000u);
+    s0.z += __uint_as_float(u.y << 16); s0.w += __uint_as_float(u.y & 0xffff0000u);
+    s1.x += __uint_as_float(u.z << 16); s1.y += __uint_as_float(u.z & 0xffff0000u);
+    s1.z += __uint_as_float(u.w << 16); s1.w += __uint_as_float(u.w & 0xffff0000u);
+  }
+};
+__device__ __forceinline__ unsigned pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<unsigned*>(&v);
+}
+template <typename TO, typename TI> __device__ __forceinline__ P8<TO> p8_convert(const P8<TI>& v);
+template <> __device__ __forceinline__ P8<float> p8_convert<float, float>(const P8<float>& v) { return v; }
+template <> __device__ __forceinline__ P8<__nv_bfloat16> p8_convert<__nv_bfloat16, __nv_bfloat16>(const P8<__nv_bfloat16>& v) { return v; }
+template <> __device__ __forceinline__ P8<__nv_bfloat16> p8_convert<__nv_bfloat16, float>(const P8<float>& v) {
+  P8<__nv_bfloat16> r;
+  r.u = make_uint4(pack_bf16x2(v.a.x, v.a.y), pack_bf16x2(v.a.z, v.a.w), pack_bf16x2(v.b.x, v.b.y), pack_bf16x2(v.b.z, v.b.w));
+  return r;
+}
+template <> __device__ __forceinline__ P8<float> p8_convert<float, __nv_bfloat16>(const P8<__nv_bfloat16>& v) {
+  P8<float> r;
+  r.a = make_float4(__uint_as_float(v.u.x << 16), __uint_as_float(v.u.x & 0xffff0000u), __uint_as_float(v.u.y << 16), __uint_as_float(v.u.y & 0xffff0000u));
+  r.b = make_float4(__uint_as_float(v.u.z << 16), __uint_as_float(v.u.z & 0xffff0000u), __uint_as_float(v.u.w << 16), __uint_as_float(v.u.w & 0xffff0000u));
+  return r;
+}
 
-// one thread = 8 channels of one (cell, scale): a streaming 16-byte store per thread in bf16.
-// grid = (Y, B): a CTA walks one map row, 8 cells x 3 scales x C8 lanes per trip (the 8 cells' 6 KB are
-// contiguous in the output), four trips in flight.  Coordinates come from the block index; the only
-// per-trip index math is x += 8 and a shift (strides are powers of two).
-template <typename T>
-__global__ void __launch_bounds__(384) dense_fill_kernel(DenseFillArgs a, T* __restrict__ out) {
-  const int C8 = a.Cs >> 3;                 // 16 for Cs = 128
-  const int per_cell = 3 * C8;
-  const int xl = threadIdx.x / per_cell, rem = threadIdx.x - xl * per_cell;
-  const int s = rem / C8, c = rem - s * C8;
-  const int y = blockIdx.x, b = blockIdx.y;
-  const int sh = a.k[s] == 1 ? 0 : (a.k[s] == 2 ? 1 : 2);
-  const int k = 1 << sh;
-  const int gy = y >> sh;
-  const bool row_ok = gy < a.H[s];
-  const int Ws = a.W[s];
-  const int* grow = a.grid[s] + ((long long)b * a.H[s] + gy) * Ws;
-  const float4* rows = reinterpret_cast<const float4*>(a.rows[s]);
-  const float4* bg = reinterpret_cast<const float4*>(a.bg[s]) + 2 * c;
-  const int suby = (y - (gy << sh)) * k;
-  const long long t0 = ((long long)b * a.Y + y) * a.X * per_cell + rem;
-#pragma unroll 4
-  for (int x = xl; x < a.X; x += 8) {
+// Thread map of both fill kernels (Cs = 128: 16 packets per (cell, scale), 48 per cell): 12 warps = 4 cell pairs x 3 scales,
+// a warp = 2 adjacent cells x 16 packets of ONE scale, so the scale - hence every shift and the rank-grid row - is
+// warp-uniform and a k > 1 site is looked up once for both cells.  grid = map rows; a CTA walks a row 8 cells per trip,
+// four trips in flight; the row's 8 x 768 B are contiguous.  (r2: the earlier map - 48 consecutive threads per cell - mixed
+// scales inside a warp and spent ~80 instructions per 16-byte packet on index arithmetic: 360 us forward for a 1.35 GB
+// bf16 map whichever type the rows had.)
+#define FILL_C8 16
+#define FILL_PER_CELL 48
+struct FillLane {
+  int c, sub, s, xp, sh, k, Ws, suby;
+  bool row_ok;
+  const int* grow;
+  __device__ __forceinline__ void init(const DenseFillArgs& a, int b, int y) {
+    c = threadIdx.x & 15; sub = (threadIdx.x >> 4) & 1;
+    const int warp = threadIdx.x >> 5;
+    s = warp % 3; xp = warp / 3;
+    k = a.k[s];
+    sh = k == 1 ? 0 : (k == 2 ? 1 : 2);
+    const int gy = y >> sh;
+    row_ok = gy < a.H[s];
+    Ws = a.W[s];
+    grow = a.grid[s] + ((long long)b * a.H[s] + gy) * Ws;
+    suby = (y & (k - 1)) << sh;
+  }
+  // rank of the site covering cell x at this scale, or -1
+  __device__ __forceinline__ int rank_of(int x, int X) const {
     const int gx = x >> sh;
-    int rank = (row_ok && gx < Ws) ? __ldg(grow + gx) : -1;
-    const float4* src = rank >= 0 ? rows + ((long long)rank * k * k + suby + (x - (gx << sh))) * (2 * C8) + 2 * c : bg;
-    Pack8<T>::store(out, t0 + (long long)x * per_cell, __ldg(src), __ldg(src + 1));
+    return (row_ok && x < X && gx < Ws) ? __ldg(grow + gx) : -1;
+  }
+  // packet index of (rank, cell x) inside the scale's rows
+  __device__ __forceinline__ int row_packet(int rank, int x) const { return (((rank << (2 * sh)) + suby + (x & (k - 1))) << 4) + c; }
+};
+
+template <typename T, typename TR>
+__global__ void __launch_bounds__(384) dense_fill_kernel(const __grid_constant__ DenseFillArgs a, T* __restrict__ out) {
+  const int y = blockIdx.x, b = blockIdx.y;
+  FillLane L;
+  L.init(a, b, y);
+  const TR* rows = reinterpret_cast<const TR*>(a.rows[L.s]);
+  P8<float> bgf = P8<float>::load_keep(a.bg[L.s], L.c);
+  const P8<T> bg = p8_convert<T, float>(bgf);
+  T* orow = out + (((long long)b * a.Y + y) * a.X * FILL_PER_CELL + L.s * FILL_C8 + L.c) * 8;     // packet (x = 0, s, c)
+  for (int x0 = 2 * L.xp + L.sub; x0 < a.X; x0 += 32) {
+    int rank[4];
+    P8<T> v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) rank[u] = L.rank_of(x0 + 8 * u, a.X);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      v[u] = bg;
+      if (rank[u] >= 0) v[u] = p8_convert<T, TR>(P8<TR>::load_keep(rows, L.row_packet(rank[u], x0 + 8 * u)));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (x0 + 8 * u < a.X) v[u].store_stream(orow, (x0 + 8 * u) * FILL_PER_CELL);
   }
 }
 
-// backward: drows_s[row] = dout[cell, s*Cs : (s+1)*Cs] at covered cells (gather),
-//           dbg_s[c]     = sum over uncovered cells of dout[cell, s*Cs + c].
-template <typename T>
-__global__ void dense_fill_bwd_rows_kernel(DenseFillArgs a, int s, const int* __restrict__ indices, long long Ns,
-                                           const T* __restrict__ dout, float4* __restrict__ drows) {
-  int C4 = a.Cs >> 2;
-  int k = a.k[s], kk = k * k;
-  long long total = Ns * kk * C4;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(t % C4);
-    long long row = t / C4;
-    long long n = row / kk;
-    int sub = (int)(row % kk);
-    int b = indices[3 * n], y = indices[3 * n + 1] * k + sub / k, x = indices[3 * n + 2] * k + sub % k;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (y < a.Y && x < a.X) v = Pack4<T>::load(dout, ((((long long)b * a.Y + y) * a.X + x) * 3 + s) * C4 + c);
-    drows[t] = v;
-  }
-}
-
-// column sums of dout over the cells NOT covered at scale s.  grid = (Y*B / rows_per_cta, 3); block 256 =
-// 16 cell-lanes x 16 channel-lanes (8 channels = one 16-byte streaming load in bf16); a CTA walks whole map rows,
-// so the only per-cell index math is a shift.  Per-block partials are combined with float atomics into dbg
-// (3*Cs, caller zeroes).
-template <typename T>
-__global__ void __launch_bounds__(256) dense_fill_bwd_bg_kernel(DenseFillArgs a, const T* __restrict__ dout,
-                                                               float* __restrict__ dbg) {
-  const int C8 = a.Cs >> 3;  // == 16 for Cs = 128
-  const int s = blockIdx.y;
-  const int lane = threadIdx.x % C8, sub = threadIdx.x / C8, nsub = blockDim.x / C8;
-  const int sh = a.k[s] == 1 ? 0 : (a.k[s] == 2 ? 1 : 2);
-  const int n_rows = a.B * a.Y;
+// backward, ONE pass over dout (B, Y, X, 3*Cs) with the forward's walk: a covered (cell, scale) packet goes to its sparse
+// row drows_s[rank*k*k + sub] (TR: bf16 rows are the map's own bits), an uncovered one is added to the thread's running sum
+// for dbg_s.  dout is read exactly once, sequentially (r2 before this kernel: a gather kernel per scale plus a pass over
+// the uncovered cells - 556 us for 1.35 GB).  grid-stride over the map rows; per-CTA sums meet in dbg by float atomics.
+template <typename T, typename TR>
+__global__ void __launch_bounds__(384, 3) dense_fill_bwd_kernel(const __grid_constant__ DenseFillArgs a, const T* __restrict__ dout, void* d0,
+                                                             void* d1, void* d2, float* __restrict__ dbg) {
   float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+  const int n_rows = a.B * a.Y;
+  FillLane L;
   for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
     const int b = row / a.Y, y = row - b * a.Y;
-    const int gy = y >> sh;
-    const bool row_ok = gy < a.H[s];
-    const int* grow = a.grid[s] + ((long long)b * a.H[s] + gy) * a.W[s];
-    const long long base = (long long)row * a.X;
-    for (int x = sub; x < a.X; x += nsub) {
-      int gx = x >> sh;
-      int rank = (row_ok && gx < a.W[s]) ? __ldg(grow + gx) : -1;
-      if (rank < 0) {
-        float4 v0, v1;
-        Pack8<T>::load(dout, ((base + x) * 3 + s) * C8 + lane, v0, v1);
-        acc0.x += v0.x; acc0.y += v0.y; acc0.z += v0.z; acc0.w += v0.w;
-        acc1.x += v1.x; acc1.y += v1.y; acc1.z += v1.z; acc1.w += v1.w;
+    L.init(a, b, y);
+    TR* drows = reinterpret_cast<TR*>(L.s == 0 ? d0 : (L.s == 1 ? d1 : d2));
+    const T* irow = dout + ((long long)row * a.X * FILL_PER_CELL + L.s * FILL_C8 + L.c) * 8;
+    for (int x0 = 2 * L.xp + L.sub; x0 < a.X; x0 += 32) {
+      int rank[4];
+      P8<T> v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        rank[u] = L.rank_of(x0 + 8 * u, a.X);
+        if (x0 + 8 * u < a.X) v[u] = P8<T>::load_stream(irow, (x0 + 8 * u) * FILL_PER_CELL);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (rank[u] >= 0) p8_convert<TR, T>(v[u]).store_stream(drows, L.row_packet(rank[u], x0 + 8 * u));
+        else if (x0 + 8 * u < a.X) v[u].add_to(acc0, acc1);
       }
     }
   }
-  __shared__ float4 red[2][256];
+  // the 8 lanes (4 cell pairs x 2 cells) that share (scale, packet) meet in shared memory
+  __shared__ float4 red[2][384];
   red[0][threadIdx.x] = acc0;
   red[1][threadIdx.x] = acc1;
   __syncthreads();
-  if (sub == 0) {
-    for (int j = 1; j < nsub; ++j) {
-      float4 v0 = red[0][j * C8 + lane], v1 = red[1][j * C8 + lane];
-      acc0.x += v0.x; acc0.y += v0.y; acc0.z += v0.z; acc0.w += v0.w;
-      acc1.x += v1.x; acc1.y += v1.y; acc1.z += v1.z; acc1.w += v1.w;
-    }
-    float* dst = dbg + s * a.Cs + 8 * lane;
+  if (L.xp == 0 && L.sub == 0) {
+    for (int j = 0; j < 4; ++j)
+      for (int h = 0; h < 2; ++h) {
+        if (j == 0 && h == 0) continue;
+        const int t = (j * 3 + L.s) * 32 + h * 16 + L.c;
+        const float4 v0 = red[0][t], v1 = red[1][t];
+        acc0.x += v0.x; acc0.y += v0.y; acc0.z += v0.z; acc0.w += v0.w;
+        acc1.x += v1.x; acc1.y += v1.y; acc1.z += v1.z; acc1.w += v1.w;
+      }
+    float* dst = dbg + L.s * a.Cs + 8 * L.c;
     atomicAdd(dst, acc0.x); atomicAdd(dst + 1, acc0.y); atomicAdd(dst + 2, acc0.z); atomicAdd(dst + 3, acc0.w);
     atomicAdd(dst + 4, acc1.x); atomicAdd(dst + 5, acc1.y); atomicAdd(dst + 6, acc1.z); atomicAdd(dst + 7, acc1.w);
   }
 }
 
-static int fill_args(DenseFillArgs& a, const float* const* rows, const float* const* bg, const int32_t* const* grids,
+static int fill_args(DenseFillArgs& a, const void* const* rows, const float* const* bg, const int32_t* const* grids,
                      const int* strides, int B, int Y, int X, int Cs) {
   GDMAE_CHECK_ARG(B >= 1 && Y >= 1 && X >= 1 && Cs > 0 && (Cs % 8) == 0 && 256 % (Cs / 8) == 0);
+  GDMAE_CHECK_ARG(Cs == 128 && B < 65536);  // block = 8 cells x 3 scales x 16 lanes
   for (int s = 0; s < 3; ++s) {
-    GDMAE_CHECK_ARG(strides[s] >= 1);
+    GDMAE_CHECK_ARG(strides[s] == 1 || strides[s] == 2 || strides[s] == 4);
     a.rows[s] = rows ? rows[s] : nullptr;
     a.bg[s] = bg ? bg[s] : nullptr;
     a.grid[s] = grids[s];
@@ -258,52 +292,47 @@ static int fill_args(DenseFillArgs& a, const float* const* rows, const float* co
   return GDMAE_OK;
 }
 
-template <typename T>
-static int dense_fill_impl(const float* const* rows, const float* const* bg, const int32_t* const* rank_grids, const int* strides,
-                           int B, int Y, int X, int Cs, T* out, void* stream_) {
+#define FILL_DISPATCH2(A, B, CALL)                                                 \
+  do {                                                                             \
+    if ((A) == 0 && (B) == 0) { using T0 = float; using T1 = float; CALL; }        \
+    else if ((A) == 0) { using T0 = float; using T1 = __nv_bfloat16; CALL; }       \
+    else if ((B) == 0) { using T0 = __nv_bfloat16; using T1 = float; CALL; }       \
+    else { using T0 = __nv_bfloat16; using T1 = __nv_bfloat16; CALL; }             \
+  } while (0)
+
+// rows_dtype / out_dtype / dtype / drows_dtype: 0 = fp32, 1 = bf16 (the dense BEV map feeds the decoder conv)
+extern "C" int gdmae_dense_fill(const void* const* rows, int rows_dtype, const float* const* bg, const int32_t* const* rank_grids,
+                                const int* strides, int B, int Y, int X, int Cs, void* out, int out_dtype, void* stream_) {
+  GDMAE_CHECK_ARG((rows_dtype == 0 || rows_dtype == 1) && (out_dtype == 0 || out_dtype == 1));
   DenseFillArgs a;
   int rc = fill_args(a, rows, bg, rank_grids, strides, B, Y, X, Cs);
   if (rc) return rc;
-  GDMAE_CHECK_ARG(Cs == 128 && B < 65536);  // block = 8 cells x 3 scales x 16 lanes
-  for (int s = 0; s < 3; ++s) GDMAE_CHECK_ARG(strides[s] == 1 || strides[s] == 2 || strides[s] == 4);
   dim3 grid(Y, B);
-  dense_fill_kernel<T><<<grid, 384, 0, (cudaStream_t)stream_>>>(a, out);
+  FILL_DISPATCH2(out_dtype, rows_dtype, (dense_fill_kernel<T0, T1><<<grid, 384, 0, (cudaStream_t)stream_>>>(a, (T0*)out)));
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;
 }
 
-template <typename T>
-static int dense_fill_bwd_impl(const T* dout, const int32_t* const* rank_grids, const int32_t* const* indices, const int64_t* n_sites,
-                               const int* strides, int B, int Y, int X, int Cs, float* const* drows, float* dbg, void* stream_) {
+// drows[s] (n_sites[s] * k_s^2, Cs) in drows_dtype, dbg (3*Cs) fp32.  Sub-cells of boundary sites that fall outside the map
+// (odd lattice sizes) are never visited by the pass over the map: those scales are zero-filled first.
+extern "C" int gdmae_dense_fill_bwd(const void* dout, int dtype, const int32_t* const* rank_grids, const int64_t* n_sites,
+                                    const int* strides, int B, int Y, int X, int Cs, void* const* drows, int drows_dtype,
+                                    float* dbg /* (3*Cs) */, void* stream_) {
+  GDMAE_CHECK_ARG((dtype == 0 || dtype == 1) && (drows_dtype == 0 || drows_dtype == 1));
   cudaStream_t st = (cudaStream_t)stream_;
   DenseFillArgs a;
   int rc = fill_args(a, nullptr, nullptr, rank_grids, strides, B, Y, X, Cs);
   if (rc) return rc;
   GDMAE_CHECK_CUDA(cudaMemsetAsync(dbg, 0, (size_t)3 * Cs * 4, st));
-  for (int s = 0; s < 3; ++s) {
-    long long total = n_sites[s] * strides[s] * strides[s] * (Cs / 4);
-    if (total == 0) continue;
-    dense_fill_bwd_rows_kernel<T><<<gdmae_grid(total, 256, 32), 256, 0, st>>>(a, s, indices[s], n_sites[s], dout, (float4*)drows[s]);
-    GDMAE_LAUNCH_CHECK();
-  }
-  dim3 grid(GDMAE_NUM_SMS * 8, 3);
-  dense_fill_bwd_bg_kernel<T><<<grid, 256, 0, st>>>(a, dout, dbg);
+  for (int s = 0; s < 3; ++s)
+    if ((a.H[s] * a.k[s] > Y || a.W[s] * a.k[s] > X) && n_sites[s] > 0)
+      GDMAE_CHECK_CUDA(cudaMemsetAsync(drows[s], 0, (size_t)n_sites[s] * a.k[s] * a.k[s] * Cs * (drows_dtype ? 2 : 4), st));
+  const int n_rows = B * Y;
+  const int grid = n_rows < GDMAE_NUM_SMS * 5 ? n_rows : GDMAE_NUM_SMS * 5;      // 5 CTAs of 384 threads per SM
+  FILL_DISPATCH2(dtype, drows_dtype,
+                 (dense_fill_bwd_kernel<T0, T1><<<grid, 384, 0, st>>>(a, (const T0*)dout, drows[0], drows[1], drows[2], dbg)));
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;
-}
-
-// out_dtype / dtype: 0 = fp32, 1 = bf16 (the dense BEV map feeds the cuDNN decoder conv)
-extern "C" int gdmae_dense_fill(const float* const* rows, const float* const* bg, const int32_t* const* rank_grids,
-                                const int* strides, int B, int Y, int X, int Cs, void* out, int out_dtype, void* stream_) {
-  if (out_dtype == 0) return dense_fill_impl<float>(rows, bg, rank_grids, strides, B, Y, X, Cs, (float*)out, stream_);
-  return dense_fill_impl<__nv_bfloat16>(rows, bg, rank_grids, strides, B, Y, X, Cs, (__nv_bfloat16*)out, stream_);
-}
-
-extern "C" int gdmae_dense_fill_bwd(const void* dout, int dtype, const int32_t* const* rank_grids, const int32_t* const* indices,
-                                    const int64_t* n_sites, const int* strides, int B, int Y, int X, int Cs,
-                                    float* const* drows, float* dbg /* (3*Cs) */, void* stream_) {
-  if (dtype == 0) return dense_fill_bwd_impl<float>((const float*)dout, rank_grids, indices, n_sites, strides, B, Y, X, Cs, drows, dbg, stream_);
-  return dense_fill_bwd_impl<__nv_bfloat16>((const __nv_bfloat16*)dout, rank_grids, indices, n_sites, strides, B, Y, X, Cs, drows, dbg, stream_);
 }
 
 // out[m, :] = src[b, y, x, :] for NHWC src (B,Y,X,C) at the M pillar cells (coalesced row gather);

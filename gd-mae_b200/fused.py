@@ -17,6 +17,7 @@ Replaces (reference file:line, relative to /root/reference):
   post_act_block (conv + BN1d + ReLU)   pcdet/utils/spconv_utils.py:37-56
 """
 import ctypes
+import os
 
 import torch
 
@@ -510,6 +511,12 @@ class BatchNormReLUFunction(torch.autograd.Function):
         return dy, dgamma, dbeta, None, None, None, None, None, None
 
 
+_DTC = {torch.float32: 0, torch.bfloat16: 1}      # dtype codes of the C ABI
+# pre-BatchNorm deconvolution output u of the deblocks: fp32 (statistics from the fp32 accumulators' values) or, with
+# GDMAE_DEBLOCK_U16=1, bf16 straight from the GEMM epilogue (halves five more passes; rounds u before the statistics)
+DEBLOCK_U_DTYPE = torch.bfloat16 if os.environ.get("GDMAE_DEBLOCK_U16", "0") == "1" else torch.float32
+
+
 class DeblockRowsFunction(torch.autograd.Function):
     """One decoder deblock on its sparse rows in the bf16 configuration: ConvTranspose2d(k = stride) as ONE GEMM
     (N, C_in) x (C_in, k*k*C_out) on the own tcgen05 kernel + training-mode BatchNorm2d + ReLU over the N*k*k produced rows
@@ -525,16 +532,18 @@ class DeblockRowsFunction(torch.autograd.Function):
         dev = x.device
         xg = _LAST_OUT[1] if _LAST_OUT[0] is x else x.to(BF16)
         wg = _gw(weight).permute(0, 2, 3, 1).reshape(C_in, k * k * c_out).contiguous()       # (C_in, [a, b, c_out]) bf16
-        u = tc_gemm(xg, wg, out_dtype=F32).view(N * k * k, c_out)
-        out = torch.empty_like(u)
+        u = tc_gemm(xg, wg, out_dtype=DEBLOCK_U_DTYPE).view(N * k * k, c_out)
+        # the rows only feed the bf16 dense map (ops.DenseFill): they leave the BatchNorm pass as bf16 - the one rounding
+        # the map's store would have applied anyway
+        out = torch.empty(u.shape, dtype=BF16, device=dev)
         mean = torch.empty((c_out,), dtype=F32, device=dev)
         rstd = torch.empty((c_out,), dtype=F32, device=dev)
         lib = L.lib()
         ws = L.workspace(lib.gdmae_batchnorm_workspace_bytes(c_out), dev)
-        L.check(lib.gdmae_batchnorm_relu_fwd(L.P(u), L.P(gamma), L.P(beta), L.i64(u.shape[0]), c_out, ctypes.c_double(count), L.f32(eps),
-                                             L.f32(momentum), 1, L.P(out), L.P(mean), L.P(rstd), L.P(running_mean),
-                                             L.P(running_var), L.P(ws), ctypes.c_size_t(ws.numel()), L.stream()),
-                "gdmae_batchnorm_relu_fwd")
+        L.check(lib.gdmae_batchnorm_relu_fwd_t(L.P(u), _DTC[u.dtype], L.P(gamma), L.P(beta), L.i64(u.shape[0]), c_out, ctypes.c_double(count),
+                                               L.f32(eps), L.f32(momentum), 1, L.P(out), 1, L.P(mean), L.P(rstd), L.P(running_mean),
+                                               L.P(running_var), L.P(ws), ctypes.c_size_t(ws.numel()), L.stream()),
+                "gdmae_batchnorm_relu_fwd_t")
         shift = beta - mean * rstd * gamma
         ctx.save_for_backward(xg, wg, u, beta, gamma, mean, rstd, shift)
         ctx.count, ctx.k, ctx.wshape = count, k, weight.shape
@@ -551,15 +560,16 @@ class DeblockRowsFunction(torch.autograd.Function):
         if ctx.count > R and dbg is not None:
             e_db = (dbg * (shift > 0)).contiguous().float()
             e_dg = (e_db * (-mean * rstd)).contiguous()
+        dout = dout.contiguous()          # bf16 rows gathered from d(map) by ops.DenseFill (fp32 from any other consumer)
         du16 = torch.empty((R, c_out), dtype=BF16, device=dev)
         dgamma = torch.empty((c_out,), dtype=F32, device=dev)
         dbeta = torch.empty((c_out,), dtype=F32, device=dev)
         lib = L.lib()
         ws = L.workspace(lib.gdmae_batchnorm_workspace_bytes(c_out), dev)
-        L.check(lib.gdmae_batchnorm_relu_bwd(L.P(u), L.P(beta), L.P(dout.contiguous()), L.P(gamma), L.P(mean), L.P(rstd), L.i64(R), c_out,
-                                             ctypes.c_double(ctx.count), 1, L.P(e_db), L.P(e_dg), None, L.P(du16), L.P(dgamma),
-                                             L.P(dbeta), L.P(ws), ctypes.c_size_t(ws.numel()), L.stream()),
-                "gdmae_batchnorm_relu_bwd")
+        L.check(lib.gdmae_batchnorm_relu_bwd_t(L.P(u), _DTC[u.dtype], L.P(beta), L.P(dout), _DTC[dout.dtype], L.P(gamma), L.P(mean), L.P(rstd),
+                                               L.i64(R), c_out, ctypes.c_double(ctx.count), 1, L.P(e_db), L.P(e_dg), L.P(du16), 1,
+                                               L.P(dgamma), L.P(dbeta), L.P(ws), ctypes.c_size_t(ws.numel()), L.stream()),
+                "gdmae_batchnorm_relu_bwd_t")
         du16 = du16.view(N, k * k * c_out)
         dx = tc_gemm(du16, wg.t(), out_dtype=F32) if ctx.needs_input_grad[0] else None
         dw = tc_gemm(xg.t(), du16, out_dtype=F32, split_k=True)                               # (C_in, k*k*c_out)

@@ -448,15 +448,19 @@ class DenseFill(torch.autograd.Function):
     @staticmethod
     @_fwd
     def forward(ctx, r0, r1, r2, bg0, bg1, bg2, grids, indices, strides, B, Y, X, out_dtype=torch.float32):
-        rows = [r.contiguous().float() for r in (r0, r1, r2)]
+        # bf16 rows (the deblocks of the bf16 configuration emit them) are read as they are; anything else as fp32
+        row_dtype = torch.bfloat16 if all(r.dtype == torch.bfloat16 for r in (r0, r1, r2)) else F32
+        rows = [r.contiguous().to(row_dtype) for r in (r0, r1, r2)]
         bgs = [b.contiguous().float() for b in (bg0, bg1, bg2)]
         Cs = bgs[0].shape[0]
         out = torch.empty((B, Y, X, 3 * Cs), dtype=out_dtype, device=_dev(rows[0]))
         with L.timed("dense_fill", out.numel() * out.element_size()):
-            L.check(L.lib().gdmae_dense_fill(L.parr(rows), L.parr(bgs), L.parr(grids), L.iarr(strides), B, Y, X, Cs, L.P(out),
-                                             _DT[out_dtype], L.stream()), "gdmae_dense_fill")
-        ctx.grids, ctx.indices, ctx.strides, ctx.dims = grids, indices, strides, (B, Y, X, Cs)
+            L.check(L.lib().gdmae_dense_fill(L.parr(rows), _DT[row_dtype], L.parr(bgs), L.parr(grids), L.iarr(strides), B, Y, X, Cs,
+                                             L.P(out), _DT[out_dtype], L.stream()), "gdmae_dense_fill")
+        ctx.grids, ctx.strides, ctx.dims = grids, strides, (B, Y, X, Cs)
         ctx.row_shapes = [r.shape for r in rows]
+        ctx.in_dtypes = [r.dtype for r in (r0, r1, r2)]
+        ctx.row_dtype = row_dtype
         return out
 
     @staticmethod
@@ -464,13 +468,15 @@ class DenseFill(torch.autograd.Function):
     def backward(ctx, dout):
         B, Y, X, Cs = ctx.dims
         dout = dout.contiguous()
-        drows = [torch.empty(s, dtype=F32, device=dout.device) for s in ctx.row_shapes]
+        drows = [torch.empty(s, dtype=ctx.row_dtype, device=dout.device) for s in ctx.row_shapes]
         dbg = torch.empty((3 * Cs,), dtype=F32, device=dout.device)
-        n_sites = (ctypes.c_int64 * 3)(*[int(i.shape[0]) for i in ctx.indices])
+        k2 = [int(k) * int(k) for k in ctx.strides]
+        n_sites = (ctypes.c_int64 * 3)(*[int(s[0]) // k2[i] for i, s in enumerate(ctx.row_shapes)])
         with L.timed("dense_fill_bwd", dout.numel() * dout.element_size()):
-            L.check(L.lib().gdmae_dense_fill_bwd(L.P(dout), _DT[dout.dtype], L.parr(ctx.grids), L.parr(ctx.indices), n_sites,
-                                                 L.iarr(ctx.strides), B, Y, X, Cs, L.parr(drows), L.P(dbg), L.stream()),
+            L.check(L.lib().gdmae_dense_fill_bwd(L.P(dout), _DT[dout.dtype], L.parr(ctx.grids), n_sites, L.iarr(ctx.strides), B, Y, X, Cs,
+                                                 L.parr(drows), _DT[ctx.row_dtype], L.P(dbg), L.stream()),
                     "gdmae_dense_fill_bwd")
+        drows = [d if d.dtype == t else d.to(t) for d, t in zip(drows, ctx.in_dtypes)]
         return (drows[0], drows[1], drows[2], dbg[:Cs], dbg[Cs:2 * Cs], dbg[2 * Cs:], None, None, None, None, None, None, None)
 
 

@@ -374,18 +374,28 @@ int gdmae_batchnorm_relu_bwd(const float* y, const float* beta, const float* dou
                              const float* rstd, int64_t N, int C, double count, int relu, const float* extra_dbeta,
                              const float* extra_dgamma, float* dy /* nullable */, void* dy_bf16 /* nullable: bf16 copy of dy */,
                              float* dgamma, float* dbeta, void* workspace, size_t ws_bytes, void* stream);
+/* the same pair with typed tensors (dtype 0 = fp32, 1 = bf16; C % 8 == 0): the decoder deblocks of the bf16 configuration
+ * (spt_backbone_mae.py:31-44) keep their output rows and the rows of the map's gradient as bf16 - the map itself is bf16 */
+int gdmae_batchnorm_relu_fwd_t(const void* y, int y_dtype, const float* gamma, const float* beta, int64_t N, int C, double count,
+                               float eps, float momentum, int relu, void* out, int out_dtype, float* mean, float* rstd,
+                               float* running_mean, float* running_var, void* workspace, size_t ws_bytes, void* stream);
+int gdmae_batchnorm_relu_bwd_t(const void* y, int y_dtype, const float* beta, const void* dout, int dout_dtype, const float* gamma,
+                               const float* mean, const float* rstd, int64_t N, int C, double count, int relu,
+                               const float* extra_dbeta, const float* extra_dgamma, void* dy, int dy_dtype, float* dgamma,
+                               float* dbeta, void* workspace, size_t ws_bytes, void* stream);
 
 /* ---- a22/a23 decoder dense fill and pillar gather --------------------------------------------
  * replaces SparseConvTensor.dense() + ConvTranspose2d(k=s) + BatchNorm2d + ReLU + torch.cat
  * (spt_backbone_mae.py:125-132) once the per-site GEMM/BN is done on the sparse rows, and the
- * gather at all pillars (spt_backbone_mae.py:141-143).  rows/bg/rank_grids/indices/drows are HOST
+ * gather at all pillars (spt_backbone_mae.py:141-143).  rows/bg/rank_grids/drows are HOST
  * arrays of 3 device pointers; out (B, Y, X, 3*Cs) NHWC. */
-int gdmae_dense_fill(const float* const* rows, const float* const* bg, const int32_t* const* rank_grids,
-                     const int* strides, int B, int Y, int X, int Cs, void* out, int out_dtype /* 0 fp32, 1 bf16 */,
-                     void* stream);
-int gdmae_dense_fill_bwd(const void* dout, int dtype, const int32_t* const* rank_grids, const int32_t* const* indices,
-                         const int64_t* n_sites, const int* strides, int B, int Y, int X, int Cs,
-                         float* const* drows, float* dbg, void* stream);
+int gdmae_dense_fill(const void* const* rows, int rows_dtype /* 0 fp32, 1 bf16 */, const float* const* bg,
+                     const int32_t* const* rank_grids, const int* strides, int B, int Y, int X, int Cs, void* out,
+                     int out_dtype /* 0 fp32, 1 bf16 */, void* stream);
+/* one pass over dout: covered (cell, scale) packets go to drows[s] (n_sites[s] * k_s^2, Cs), the others are summed into dbg */
+int gdmae_dense_fill_bwd(const void* dout, int dtype, const int32_t* const* rank_grids, const int64_t* n_sites,
+                         const int* strides, int B, int Y, int X, int Cs, void* const* drows, int drows_dtype,
+                         float* dbg /* (3*Cs) */, void* stream);
 int gdmae_gather_nhwc(const void* src, int dtype, const int64_t* voxel_coords, int64_t M, int Y, int X, int C, float* out,
                       void* stream);
 int gdmae_scatter_nhwc(const float* dout, const int64_t* voxel_coords, int64_t M, int Y, int X, int C, void* dsrc,

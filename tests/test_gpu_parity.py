@@ -670,12 +670,15 @@ def test_deblock_rows_and_tall_linear_match_torch(G):
             x = torch.randn(N, C_in, device="cuda", requires_grad=True)
             count = float(N * k * k * 3)
             out, bg = fused.deblock_rows(deconv, bn, k, x, count)
+            assert out.dtype == torch.bfloat16          # the rows feed the bf16 map (ops.DenseFill) and nothing else
             gout, gbg = torch.randn_like(out), torch.randn_like(bg)
-            (out * gout).sum().add((bg * gbg).sum()).backward()
+            torch.autograd.backward([out, bg], [gout, gbg])
             got = [out, bg, x.grad.clone(), deconv.weight.grad.clone(), bn.weight.grad.clone(), bn.bias.grad.clone()]
-            # torch fp32 reference of the same function
-            x2 = x.detach().clone().requires_grad_()
-            w2 = deconv.weight.detach().clone().requires_grad_()
+            # torch fp32 reference of the same function on the bf16-rounded GEMM operands (fp32 accumulation, as the tensor
+            # cores do): with unrounded operands u differs by ~4e-3 and a handful of ReLU masks flip, which a max-norm
+            # comparison of dx sees as whole rows of W
+            x2 = x.detach().bfloat16().float().requires_grad_()
+            w2 = deconv.weight.detach().bfloat16().float().requires_grad_()
             g2, b2 = bn.weight.detach().clone().requires_grad_(), bn.bias.detach().clone().requires_grad_()
             u = (x2 @ w2.permute(0, 2, 3, 1).reshape(C_in, k * k * c_out)).view(-1, c_out)
             mean = u.sum(0) / count
@@ -683,7 +686,7 @@ def test_deblock_rows_and_tall_linear_match_torch(G):
             rstd = torch.rsqrt(var + bn.eps)
             ref_out = torch.relu((u - mean) * rstd * g2 + b2)
             ref_bg = torch.relu(b2 - mean * rstd * g2)
-            (ref_out * gout).sum().add((ref_bg * gbg).sum()).backward()
+            torch.autograd.backward([ref_out, ref_bg], [gout.float(), gbg])
             ref = [ref_out, ref_bg, x2.grad, w2.grad, g2.grad, b2.grad]
             for name, a, b in zip(("out", "bg", "dx", "dW", "dgamma", "dbeta"), got, ref):
                 e = rel(a, b)
@@ -703,6 +706,50 @@ def test_deblock_rows_and_tall_linear_match_torch(G):
     y2.backward(g)
     for name, a, b in zip(("y", "dx", "dW", "db"), got, [y2, x2.grad, lin.weight.grad, lin.bias.grad]):
         assert rel(a, b) < 1e-5, (name, rel(a, b))
+
+
+def test_dense_fill_typed_rows_and_one_pass_backward(G):
+    """ops.DenseFill (SparseConvTensor.dense() + cat of the three deblock outputs, spt_backbone_mae.py:125-132) with fp32 and
+    bf16 sparse rows, fp32 and bf16 map, on an odd-sized grid (boundary sites whose k x k block leaves the map) against the
+    same map assembled with torch indexing; the one-pass backward (rows gathered + background sums) against autograd."""
+    torch.manual_seed(11)
+    B, Y, X, Cs = 2, 21, 19, 128
+    strides = [1, 2, 4]
+    lat = lambda n, k: n if k == 1 else lat((n - 1) // 2 + 1, k // 2)  # noqa: E731
+    bb, yy, xx = torch.meshgrid(torch.arange(B), torch.arange(Y), torch.arange(X), indexing="ij")
+    bb, yy, xx = bb.cuda(), yy.cuda(), xx.cuda()
+    for row_dtype, out_dtype in ((torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16), (torch.float32, torch.bfloat16),
+                                 (torch.bfloat16, torch.float32)):
+        grids, rows, bgs = [], [], []
+        for k in strides:
+            H, W = lat(Y, k), lat(X, k)
+            occ = torch.rand(B, H, W, device="cuda") < 0.4
+            grid = torch.full((B, H, W), -1, dtype=torch.int32, device="cuda")
+            grid[occ] = torch.arange(int(occ.sum()), dtype=torch.int32, device="cuda")
+            grids.append(grid.contiguous())
+            rows.append(torch.randn(int(occ.sum()) * k * k, Cs, device="cuda").to(row_dtype).requires_grad_())
+            bgs.append(torch.randn(Cs, device="cuda").requires_grad_())
+        out = G.ops.DenseFill.apply(rows[0], rows[1], rows[2], bgs[0], bgs[1], bgs[2], grids, None, strides, B, Y, X, out_dtype)
+        assert out.dtype == out_dtype and out.shape == (B, Y, X, 3 * Cs)
+        gout = torch.randn(B, Y, X, 3 * Cs, device="cuda").to(out_dtype)
+        out.backward(gout)
+        # torch restatement on fp32 leaves
+        rows2 = [r.detach().float().requires_grad_() for r in rows]
+        bgs2 = [b.detach().clone().requires_grad_() for b in bgs]
+        parts = []
+        for k, grid, r2, b2 in zip(strides, grids, rows2, bgs2):
+            rank = grid[bb, yy // k, xx // k].long()
+            row = rank * k * k + (yy % k) * k + (xx % k)
+            part = torch.where((rank >= 0)[..., None], r2[row.clamp(min=0)], b2.expand(B, Y, X, Cs))
+            parts.append(part)
+        ref = torch.cat(parts, dim=-1)
+        assert torch.equal(out.float(), ref.to(out_dtype).float()), (row_dtype, out_dtype)
+        ref.backward(gout.float())
+        for s in range(3):
+            want = rows2[s].grad.to(row_dtype)
+            assert rows[s].grad.dtype == row_dtype and torch.equal(rows[s].grad, want), (row_dtype, out_dtype, s)   # pure data movement
+            e = rel(bgs[s].grad, bgs2[s].grad)
+            assert e < 1e-5, (s, e)        # float sums in a different order
 
 
 def ctypes_int():
@@ -731,12 +778,16 @@ def test_prefetched_index_pipeline_matches_inline(G):
         m, *_ = build(G, "tiny", 0.85, 9)
         tr = MAETrainer(m, cfg.OPTIMIZATION, total_steps=20)
         bds = [dict(points=p.clone(), batch_size=2, voxel_mae_noise=nz) for p, nz in batches]
-        losses = []
+        losses, lagged = [], []
         for i, bd in enumerate(bds):
             nxt = bds[i + 1] if (prefetch and i + 1 < len(bds)) else None
-            losses.append(float(tr.step(bd, next_batch=nxt)))
+            loss = tr.step(bd, next_batch=nxt)
+            lagged.append(tr.loss_to_host(loss))            # pinned-slot read: the loss of the step before
+            losses.append(float(loss))
             if prefetch and i > 0:
                 assert '_index_event' not in bd and bd.get('mae_index') is not None   # the prefetched structures were consumed
+        assert lagged[0] is None and lagged[1:] == losses[:-1] and tr.drain_loss() == losses[-1], (lagged, losses)
+        tr.reserve_memory(main_gb=0.25, side_gb=0.05)       # maps pool memory, leaves every live tensor alone
         return losses, {k: v.detach().clone() for k, v in m.state_dict().items()}
 
     l0, s0 = run(False)
