@@ -559,6 +559,69 @@ __global__ void __launch_bounds__(256) vfe2_apply_max_kernel(const T* __restrict
 // and lane instead of ~28 for convert + normalise + ReLU + max + arg-max per element (r2 ncu: the pass was issue-bound at 53 %
 // issue-active, 3.4 TB/s) - and applies BatchNorm + ReLU once per pillar.  No arg-max is stored: the backward pass recognises
 // the arg-max row as the first row whose activation equals the stored maximum (same arithmetic, bit-equal).
+// Two pillars in flight per warp: while pillar m is reduced, the first nine rows of pillar m + stride are already on their
+// way and the segment bounds of m + 2 stride are being fetched - the one-pillar-at-a-time form below exposes a full DRAM
+// round trip per 1.4 KB segment (r2 ncu: 41 % of the DRAM rate with 40 % of the warp slots active).
+__global__ void __launch_bounds__(256, 4) vfe2_apply_max_piped_kernel(const vbf16* __restrict__ y, const int* __restrict__ seg_off, int M,
+                                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                      float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const float4 mu = __ldg(reinterpret_cast<const float4*>(mean) + lane), rs = __ldg(reinterpret_cast<const float4*>(rstd) + lane);
+  const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + lane), be = __ldg(reinterpret_cast<const float4*>(beta) + lane);
+  const float4 a = make_float4(rs.x * ga.x, rs.y * ga.y, rs.z * ga.z, rs.w * ga.w);
+  const uint2* rows = reinterpret_cast<const uint2*>(y) + lane;
+  const int stride = (gridDim.x * blockDim.x) >> 5;
+  int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (m >= M) return;
+  int s = __ldg(seg_off + m), e = __ldg(seg_off + m + 1);
+  int sn = 0, en = 0;
+  if (m + stride < M) { sn = __ldg(seg_off + m + stride); en = __ldg(seg_off + m + stride + 1); }
+  uint2 v[9];
+#pragma unroll
+  for (int u = 0; u < 9; ++u) v[u] = __ldg(rows + (long long)(s + u < e ? s + u : s) * (V_C2 / 4));
+  while (true) {
+    const int mn = m + stride, mnn = mn + stride;
+    uint2 w[9];
+    if (mn < M) {
+#pragma unroll
+      for (int u = 0; u < 9; ++u) w[u] = __ldg(rows + (long long)(sn + u < en ? sn + u : sn) * (V_C2 / 4));
+    }
+    int snn = 0, enn = 0;
+    if (mnn < M) { snn = __ldg(seg_off + mnn); enn = __ldg(seg_off + mnn + 1); }
+    __nv_bfloat162 mx0 = *reinterpret_cast<__nv_bfloat162*>(&v[0].x), mx1 = *reinterpret_cast<__nv_bfloat162*>(&v[0].y);
+    __nv_bfloat162 mi0 = mx0, mi1 = mx1;
+#pragma unroll
+    for (int u = 1; u < 9; ++u) {
+      const __nv_bfloat162 p0 = *reinterpret_cast<__nv_bfloat162*>(&v[u].x), p1 = *reinterpret_cast<__nv_bfloat162*>(&v[u].y);
+      mx0 = __hmax2(mx0, p0); mx1 = __hmax2(mx1, p1);
+      mi0 = __hmin2(mi0, p0); mi1 = __hmin2(mi1, p1);
+    }
+    for (int k = s + 9; k < e; k += 8) {          // pillars above nine points: the rest eight rows at a time
+      uint2 t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t[u] = __ldg(rows + (long long)(k + u < e ? k + u : s) * (V_C2 / 4));
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const __nv_bfloat162 p0 = *reinterpret_cast<__nv_bfloat162*>(&t[u].x), p1 = *reinterpret_cast<__nv_bfloat162*>(&t[u].y);
+        mx0 = __hmax2(mx0, p0); mx1 = __hmax2(mx1, p1);
+        mi0 = __hmin2(mi0, p0); mi1 = __hmin2(mi1, p1);
+      }
+    }
+    const float2 hx0 = __bfloat1622float2(mx0), hx1 = __bfloat1622float2(mx1), lo0 = __bfloat1622float2(mi0), lo1 = __bfloat1622float2(mi1);
+    float4 best;
+    best.x = fmaxf(fmaf((a.x >= 0.f ? hx0.x : lo0.x) - mu.x, a.x, be.x), 0.f);
+    best.y = fmaxf(fmaf((a.y >= 0.f ? hx0.y : lo0.y) - mu.y, a.y, be.y), 0.f);
+    best.z = fmaxf(fmaf((a.z >= 0.f ? hx1.x : lo1.x) - mu.z, a.z, be.z), 0.f);
+    best.w = fmaxf(fmaf((a.w >= 0.f ? hx1.y : lo1.y) - mu.w, a.w, be.w), 0.f);
+    __stcs(reinterpret_cast<float4*>(out) + (long long)m * (V_C2 / 4) + lane, best);
+    if (mn >= M) break;
+    m = mn; s = sn; e = en; sn = snn; en = enn;
+#pragma unroll
+    for (int u = 0; u < 9; ++u) v[u] = w[u];
+  }
+}
+
 __global__ void __launch_bounds__(256) vfe2_apply_max_packed_kernel(const vbf16* __restrict__ y, const int* __restrict__ seg_off, int M,
                                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -858,7 +921,13 @@ extern "C" int gdmae_vfe_mlp_fwd(const gdmae_vfe_mlp_args* a) {
       const int gs = gdmae_grid(((long long)a->M + V_STREAM_PILLARS - 1) / V_STREAM_PILLARS * 32, 256, 8);
       vfe2_apply_max_stream_kernel<<<gs, 256, 0, st>>>((const vbf16*)a->y2, a->seg_offsets, (int)a->M, a->mean2, a->rstd2, a->g2, a->b2, a->out);
     } else {
-      vfe2_apply_max_packed_kernel<<<g3, 256, 0, st>>>((const vbf16*)a->y2, a->seg_offsets, (int)a->M, a->mean2, a->rstd2, a->g2, a->b2, a->out);
+      // GDMAE_VFE_PIPE=0 selects the one-pillar-at-a-time form (A/B)
+      static const bool piped = [] { const char* e = getenv("GDMAE_VFE_PIPE"); return !(e && e[0] == '0'); }();
+      if (piped) {
+        const int gp = gdmae_grid((long long)a->M * 32 / 4, 256, 4);      // >= 4 pillars per warp, 4 CTAs per SM
+        vfe2_apply_max_piped_kernel<<<gp, 256, 0, st>>>((const vbf16*)a->y2, a->seg_offsets, (int)a->M, a->mean2, a->rstd2, a->g2, a->b2, a->out);
+      } else
+        vfe2_apply_max_packed_kernel<<<g3, 256, 0, st>>>((const vbf16*)a->y2, a->seg_offsets, (int)a->M, a->mean2, a->rstd2, a->g2, a->b2, a->out);
     }
   }
   else if (sorted) VFE_APPLY_MAX(float, true);
