@@ -38,9 +38,13 @@ BYTES_DEF = {
     "sra_fwd": "N*d*(3*s_qkv + s_o) + N*32 per launch: q,k,v in, o and lse out (s = 2 bytes in the bf16 configuration; SURVEY.md 8d a18)",
     "sra_bwd": "N*d*(3*s + s + 3*s) + N*32 per launch: q,k,v,dO in, dq,dk,dv out, lse in",
     "pillar_scatter_max": "Np*C*s + Np*4 + M*C*4 per launch: point rows + segment index in, pillar maxima out (SURVEY.md 8d a6)",
+    "tc_gemm": "M*K*2 + K*N*2 + M*N*s_out per launch (+ old C for C+=, + M*N*10 for the LayerNorm epilogue's residual in / fp32+bf16 rows "
+               "out, + M*N*2 for the GELU modes' pre-activation); activation-bound shapes (K, N <= 768): arithmetic intensity <= 170 "
+               "FLOP/B, below the 210 FLOP/B balance of the measured peaks, so the bound is HBM",
 }
 SETTLE_STEPS = 12
-SPAN_NAMES = {0: "sra_fwd_d{d}", 1: "sra_bwd_d{d}", 2: "pillar_scatter_max_c{d}"}
+SPAN_NAMES = {0: "sra_fwd_d{d}", 1: "sra_bwd_d{d}", 2: "pillar_scatter_max_c{d}", 3: "tc_gemm_{d}"}
+TC_GEMM_MODES = {0: "plain", 1: "gelu", 2: "ln", 3: "gelu_bwd", 4: "qkv_win", 5: "rows_win"}
 
 
 def peaks():
@@ -395,6 +399,9 @@ def main():
     c_spans = {}
     for i in range(n_span):
         name = SPAN_NAMES.get(int(meta[4 * i]), "kind%d_{d}" % int(meta[4 * i])).format(d=int(meta[4 * i + 1]))
+        if int(meta[4 * i]) == 3:      # own tcgen05 GEMM: one entry per kernel instantiation (tile width BN, epilogue mode)
+            dd = int(meta[4 * i + 1])
+            name = "tc_gemm_bn%d_%s" % (dd // 10, TC_GEMM_MODES.get(dd % 10, str(dd % 10)))
         c_spans.setdefault(name, []).append((float(span_ms[i]), int(meta[4 * i + 3])))
 
     frames = B_PER_GPU * world
@@ -406,6 +413,8 @@ def main():
 
     def add_kernel(name, ms, nbytes):
         gbs = [nb / (t * 1e-3) / 1e9 for nb, t in zip(nbytes, ms) if t > 0]
+        if name.startswith("tc_gemm"):      # launches of very different sizes share a kernel: bytes of all / time of all
+            gbs = [float(np.sum(nbytes)) / (float(np.sum(ms)) * 1e-3) / 1e9]
         kernels[name] = {"launches_per_step": len(ms) / (n_prof + 1), "avg_us": 1e3 * float(np.mean(ms)),
                          "achieved_gbs": float(np.mean(gbs)), "frac": float(np.mean(gbs)) / pk["hbm_gbs"],
                          "share_of_step": float(np.sum(ms)) / (ms_prof * (n_prof + 1)),
@@ -442,7 +451,7 @@ def main():
                 "frac": k["frac"], "traffic": traffic_tab.get(name, {}).get("dram_bytes_per_launch"),
                 "traffic_unit": "DRAM bytes per launch (ncu --set full, cold cache)",
                 "algorithmic_bytes": k["algorithmic_bytes"], "peak_source": pk_src, "avg_us": k["avg_us"],
-                "share_of_step": k["share_of_step"], "bytes_def": BYTES_DEF.get(name.split("_d")[0].split("_c")[0], "SURVEY.md 8d")}
+                "share_of_step": k["share_of_step"], "bytes_def": BYTES_DEF.get("tc_gemm" if name.startswith("tc_gemm") else name.split("_d")[0].split("_c")[0], "SURVEY.md 8d")}
 
     # `roofline` = the hand-written kernel with the largest share of the step; the two kernels north_star names
     # (SRA attention, pillar scatter-max) are reported next to it whichever is dominant.
@@ -452,7 +461,7 @@ def main():
         dom = max(kernels, key=lambda n: kernels[n]["share_of_step"])
         roofline = roofline_of(dom)
         for n in kernels:
-            if n.startswith(("sra_", "pillar_scatter_max", "conv3x3_wgrad")):
+            if n.startswith(("sra_", "pillar_scatter_max", "conv3x3_wgrad", "tc_gemm")):
                 rooflines[n] = roofline_of(n)
 
     out = {

@@ -129,7 +129,8 @@ extern "C" int gdmae_encoder_layer_fwd(const gdmae_encoder_layer_args* a) {
   const int ob = bf ? 1 : 0;
   if (bf) {
     // three GEMMs, no row kernels: residual + bias + LayerNorm and bias + GELU run in the GEMM epilogues on the
-    // accumulator rows in tensor memory; a / h / f (bf16) are still written because the backward pass reads them
+    // accumulator rows in tensor memory; a / f (bf16) are still written because the backward pass reads them, and h holds
+    // gelu'(W1 x1 + b1) (bf16) - the only thing the backward pass needs of the pre-activation
     gdmae_tc_epilogue e1 = {};
     e1.mode = 2; e1.bias = a->b_o; e1.res = a->x; e1.gamma = a->g1; e1.beta_ln = a->be1; e1.eps = a->eps;
     e1.y32 = a->x1; e1.y16 = a->x1g; e1.mean = a->mean1; e1.rstd = a->rstd1;
@@ -194,7 +195,7 @@ extern "C" int gdmae_encoder_layer_bwd(const gdmae_encoder_layer_args* a) {
   const void* dz2_op = bf ? (const void*)dz2g : (const void*)dz2;
   EL_CALL(el_gemm(a, 1, 0, d, dff, N, dz2_op, d, a->g, dff, a->d_w2, dff, 0, wbeta));
   if (bf) {
-    // dgl = dz2 W2 never leaves the GEMM: its epilogue multiplies by gelu'(h + b1), writes dh (bf16) and adds the column
+    // dgl = dz2 W2 never leaves the GEMM: its epilogue multiplies by the saved gelu'(h + b1), writes dh (bf16) and adds the column
     // sums (the gradient of b1) to d_b1
     if (!acc) GDMAE_CHECK_CUDA(cudaMemsetAsync(a->d_b1, 0, (size_t)dff * sizeof(float), st));
     gdmae_tc_epilogue eg = {};

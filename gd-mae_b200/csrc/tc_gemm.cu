@@ -233,25 +233,18 @@ __device__ __forceinline__ void reduce_f32(uint8_t* buf, int lane, const CUtenso
   __syncwarp();
 }
 
-// GELU(v) = v * Phi(v), Phi from one exp and one reciprocal (Abramowitz & Stegun 7.1.26, |erf error| <= 1.5e-7; the same
-// approximation as elementwise.cu's bf16 configuration - inputs and outputs are bf16 here)
-__device__ __forceinline__ float gelu_fast(float v) {
-  const float z = fabsf(v) * 0.70710678118654752440f;
-  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
-  const float e = __expf(-0.5f * v * v);
-  const float poly = fmaf(fmaf(fmaf(fmaf(1.061405429f, t, -1.453152027f), t, 1.421413741f), t, -0.284496736f), t, 0.254829592f) * t;
-  const float erf_abs = fmaf(-poly, e, 1.f);
-  return v * 0.5f * (1.f + copysignf(erf_abs, v));
-}
-
-// d GELU(v) / dv = Phi(v) + v phi(v), same approximation
-__device__ __forceinline__ float gelu_grad_fast(float v) {
+// GELU through Phi from one exp and one reciprocal (Abramowitz & Stegun 7.1.26, |erf error| <= 1.5e-7; the same
+// approximation as elementwise.cu's bf16 configuration - inputs and outputs are bf16 here).
+// GELU(v) and d GELU(v) / dv = Phi(v) + v phi(v) from ONE evaluation of the same approximation: exp(-v^2/2) is both the
+// tail factor of the erf formula and sqrt(2 pi) phi(v)
+__device__ __forceinline__ void gelu_both_fast(float v, float& gl, float& dgl) {
   const float z = fabsf(v) * 0.70710678118654752440f;
   const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
   const float e = __expf(-0.5f * v * v);
   const float poly = fmaf(fmaf(fmaf(fmaf(1.061405429f, t, -1.453152027f), t, 1.421413741f), t, -0.284496736f), t, 0.254829592f) * t;
   const float cdf = 0.5f * (1.f + copysignf(fmaf(-poly, e, 1.f), v));
-  return fmaf(v, 0.39894228040143267794f * e, cdf);
+  gl = v * cdf;
+  dgl = fmaf(v, 0.39894228040143267794f * e, cdf);
 }
 // 32 rows x 32 bf16 columns of a global matrix, coalesced (8 rows x 64 bytes per warp instruction), requested early
 __device__ __forceinline__ void prefetch_bf16(const __nv_bfloat16* base, long long ld, int r0, int col, int M, int lane, uint4 (&pre)[4]) {
@@ -524,27 +517,33 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tcg_gemm_kernel(const __grid_c
           flush_bf16_win(buf, lane, reinterpret_cast<__nv_bfloat16*>(p.C), p.plane0, col0 + c * 32, p.M, wrow, valid);
         }
       } else if (EPI == EPI_GELU) {
-        // C = h (pre-activation, kept for the backward pass), C2 = gelu(h + bias): both bf16
+        // C2 = gelu(h + bias), C = gelu'(h + bias), both bf16, h = the accumulator.  The derivative - not h - is what the
+        // backward pass keeps: it falls out of the forward's evaluation for one more FMA (from the fp32 accumulator, not
+        // from a bf16-rounded h), and the backward epilogue (mode 3) becomes one multiply per element instead of a second
+        // exp + reciprocal + polynomial (r2: 31 instructions per element on 8 epilogue warps, 61 us per launch, 0.29 of the
+        // HBM roofline).
+        float w[32];
         mbar_wait(tfull + acc, acc_phase);
         tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < HC / 32; ++c) {
           tmem_ld32(taddr + c * 32, v);
-          stage_bf16(buf, lane, v);
-          flush_bf16(buf, lane, reinterpret_cast<__nv_bfloat16*>(p.C), p.ldc, r0, col0 + c * 32, p.M);
           const float4* bp = reinterpret_cast<const float4*>(p.bias + col0 + c * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 b = __ldg(bp + j);
-            v[4 * j] = gelu_fast(v[4 * j] + b.x); v[4 * j + 1] = gelu_fast(v[4 * j + 1] + b.y);
-            v[4 * j + 2] = gelu_fast(v[4 * j + 2] + b.z); v[4 * j + 3] = gelu_fast(v[4 * j + 3] + b.w);
+            gelu_both_fast(v[4 * j] + b.x, v[4 * j], w[4 * j]); gelu_both_fast(v[4 * j + 1] + b.y, v[4 * j + 1], w[4 * j + 1]);
+            gelu_both_fast(v[4 * j + 2] + b.z, v[4 * j + 2], w[4 * j + 2]); gelu_both_fast(v[4 * j + 3] + b.w, v[4 * j + 3], w[4 * j + 3]);
           }
+          stage_bf16(buf, lane, w);
+          flush_bf16(buf, lane, reinterpret_cast<__nv_bfloat16*>(p.C), p.ldc, r0, col0 + c * 32, p.M);
           stage_bf16(buf, lane, v);
           flush_bf16(buf, lane, reinterpret_cast<__nv_bfloat16*>(p.C2), p.ldc2, r0, col0 + c * 32, p.M);
         }
       } else if (EPI == EPI_GELU_BWD) {
-        // acc = dg (gradient w.r.t. gelu(h + bias)); C = dh = dg * gelu'(h + bias) (bf16) and its column sums (the
-        // gradient of the bias) are added to p.colsum.  h (bf16) of chunk c + 1 is requested while chunk c is processed.
+        // acc = dg (gradient w.r.t. gelu(h + bias)); C = dh = dg * gelu'(h + bias) (bf16) with the derivative as mode 1 saved
+        // it (h16), and the column sums of dh (the gradient of the bias) are added to p.colsum.  The saved rows of chunk
+        // c + 1 are requested while chunk c is processed.
         uint4 pre[4];
         float hv[32];
         prefetch_bf16(reinterpret_cast<const __nv_bfloat16*>(p.h16), p.ldh, r0, col0, p.M, lane, pre);
@@ -555,13 +554,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tcg_gemm_kernel(const __grid_c
           tmem_ld32(taddr + c * 32, v);
           take_prefetched_bf16(buf, lane, pre, hv);
           if (c + 1 < HC / 32) prefetch_bf16(reinterpret_cast<const __nv_bfloat16*>(p.h16), p.ldh, r0, col0 + (c + 1) * 32, p.M, lane, pre);
-          const float4* bp = reinterpret_cast<const float4*>(p.bias + col0 + c * 32);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b = __ldg(bp + j);
-            v[4 * j] *= gelu_grad_fast(hv[4 * j] + b.x); v[4 * j + 1] *= gelu_grad_fast(hv[4 * j + 1] + b.y);
-            v[4 * j + 2] *= gelu_grad_fast(hv[4 * j + 2] + b.z); v[4 * j + 3] *= gelu_grad_fast(hv[4 * j + 3] + b.w);
-          }
+          for (int j = 0; j < 32; ++j) v[j] *= hv[j];
           stage_f32(buf, lane, v);               // rows past M hold zeros (their A rows were zero-filled by TMA)
           __syncwarp();
           atomicAdd(p.colsum + col0 + c * 32 + lane, unit_colsum(buf, lane));
@@ -967,7 +961,7 @@ extern "C" int gdmae_tc_gemm(int transa, int transb, int64_t M, int64_t N, int64
     BN = (int)N;
   }
   if (mode == EPI_GELU_BWD)
-    GDMAE_CHECK_ARG(epi->bias && epi->h16 && epi->colsum && c_dtype == 1 && N % 128 == 0 && epi->ldh % 8 == 0 && ((uintptr_t)epi->h16 & 15) == 0);
+    GDMAE_CHECK_ARG(epi->h16 && epi->colsum && c_dtype == 1 && N % 128 == 0 && epi->ldh % 8 == 0 && ((uintptr_t)epi->h16 & 15) == 0);
   if (mode == EPI_QKV_WIN) {
     // N = 3d with d in {128, 256}: one N tile per tensor
     GDMAE_CHECK_ARG((N == 384 || N == 768) && c_dtype == 1 && !split_k_atomic && epi->tok_info && epi->lut && epi->tau && epi->lrr);
@@ -1023,27 +1017,40 @@ extern "C" int gdmae_tc_gemm(int transa, int transb, int64_t M, int64_t N, int64
     tc = tb;
   }
   if (mode == EPI_LN && C) GDMAE_CHECK_ARG(c_dtype == 1 && ((uintptr_t)C & 15) == 0 && ldc % 8 == 0);
-  if (mode == EPI_PLAIN) {
-    if (BN == 256) return launch<256, EPI_PLAIN>(ta, tb, tc, p, st);
-    if (BN == 128) return launch<128, EPI_PLAIN>(ta, tb, tc, p, st);
-    return launch<64, EPI_PLAIN>(ta, tb, tc, p, st);
-  }
-  if (mode == EPI_QKV_WIN) {
-    if (BN == 256) return launch<256, EPI_QKV_WIN>(ta, tb, tc, p, st);
-    return launch<128, EPI_QKV_WIN>(ta, tb, tc, p, st);
-  }
-  if (mode == EPI_ROWS_WIN) {
-    if (BN == 256) return launch<256, EPI_ROWS_WIN>(ta, tb, tc, p, st);
-    return launch<128, EPI_ROWS_WIN>(ta, tb, tc, p, st);
-  }
-  if (mode == EPI_GELU_BWD) {
-    if (BN == 256) return launch<256, EPI_GELU_BWD>(ta, tb, tc, p, st);
-    return launch<128, EPI_GELU_BWD>(ta, tb, tc, p, st);
-  }
-  if (mode == EPI_GELU) {
-    if (BN == 256) return launch<256, EPI_GELU>(ta, tb, tc, p, st);
-    return launch<128, EPI_GELU>(ta, tb, tc, p, st);
-  }
-  if (BN == 256) return launch<256, EPI_LN>(ta, tb, tc, p, st);
-  return launch<128, EPI_LN>(ta, tb, tc, p, st);
+  // bench-only span (bench.py `kernels`: tc_gemm_bn<BN>_mode<m>).  Algorithmic bytes: both operands once + the result once,
+  // + what the fused epilogue must move besides (old C of `C +=`; fp32 residual in, fp32 + bf16 row out of the LayerNorm
+  // mode; the bf16 pre-activation out / in of the two GELU modes)
+  GdmaeSpan span(st);
+  const long long s_out = c_dtype ? 2 : 4;
+  long long bytes = M * K * 2 + K * N * 2 + (split_k_atomic ? 0 : M * N * s_out) + (p.beta_one ? M * N * s_out : 0);
+  if (mode == EPI_LN) bytes += M * N * (4 + 4 + 2);
+  if (mode == EPI_GELU || mode == EPI_GELU_BWD) bytes += M * N * 2;
+  auto dispatch = [&]() -> int {
+    if (mode == EPI_PLAIN) {
+      if (BN == 256) return launch<256, EPI_PLAIN>(ta, tb, tc, p, st);
+      if (BN == 128) return launch<128, EPI_PLAIN>(ta, tb, tc, p, st);
+      return launch<64, EPI_PLAIN>(ta, tb, tc, p, st);
+    }
+    if (mode == EPI_QKV_WIN) {
+      if (BN == 256) return launch<256, EPI_QKV_WIN>(ta, tb, tc, p, st);
+      return launch<128, EPI_QKV_WIN>(ta, tb, tc, p, st);
+    }
+    if (mode == EPI_ROWS_WIN) {
+      if (BN == 256) return launch<256, EPI_ROWS_WIN>(ta, tb, tc, p, st);
+      return launch<128, EPI_ROWS_WIN>(ta, tb, tc, p, st);
+    }
+    if (mode == EPI_GELU_BWD) {
+      if (BN == 256) return launch<256, EPI_GELU_BWD>(ta, tb, tc, p, st);
+      return launch<128, EPI_GELU_BWD>(ta, tb, tc, p, st);
+    }
+    if (mode == EPI_GELU) {
+      if (BN == 256) return launch<256, EPI_GELU>(ta, tb, tc, p, st);
+      return launch<128, EPI_GELU>(ta, tb, tc, p, st);
+    }
+    if (BN == 256) return launch<256, EPI_LN>(ta, tb, tc, p, st);
+    return launch<128, EPI_LN>(ta, tb, tc, p, st);
+  };
+  rc = dispatch();
+  span.end(3, BN * 10 + mode, M, bytes);
+  return rc;
 }

@@ -283,7 +283,7 @@ typedef struct gdmae_encoder_layer_args {
   float* x1;                 /* (N,d) */
   void* x1g;                 /* (N,d) op (bf16 mode only) */
   float *mean1, *rstd1;      /* (N) */
-  void* h;                   /* (N,dff) FFN pre-activation: fp32, bf16 when gemm_mode == 1 */
+  void* h;                   /* (N,dff) FFN pre-activation (fp32); when gemm_mode == 1: bf16 gelu'(pre-activation + b1) */
   void* g;                   /* (N,dff) op */
   void* f;                   /* (N,d) FFN output: fp32, bf16 when gemm_mode == 1 */
   float *mean2, *rstd2;      /* (N) */
@@ -315,10 +315,10 @@ int gdmae_gemm(int transa, int transb, int64_t M, int64_t N, int64_t K, const vo
  * c_dtype 0 fp32 (beta 0 or 1) / 1 bf16.  split_k_atomic: the K range is split across the SMs and partial tiles are
  * added to C with fp32 reductions (weight gradients, K = tokens; beta 0 zero-fills C first, needs ldc == N).
  * epilogue (nullable = mode 0):
- *   mode 1  C = acc (bf16, kept for backward), c2 = gelu(acc + bias) (bf16)          - linear1 + GELU, sst_basic_block.py:81
+ *   mode 1  c2 = gelu(acc + bias), C = gelu'(acc + bias) (both bf16; C is what mode 3 reads) - linear1 + GELU, sst_basic_block.py:81
  *   mode 2  z = acc + bias + res; y32/y16 = LayerNorm(z) * gamma + beta_ln, mean, rstd; N in {128, 256}; C (nullable, bf16) = acc
  *                                                                                     - out_proj / linear2 + residual + norm, :78-83
- *   mode 3  acc = gradient w.r.t. gelu(h + bias): C = acc * gelu'(h16 + bias) (bf16) and colsum (N, fp32) += its column sums
+ *   mode 3  acc = gradient w.r.t. gelu(h + bias): C = acc * h16 (bf16; h16 = the derivative saved by mode 1) and colsum (N, fp32) += its column sums
  *                                                                                     - backward of linear1's bias + GELU
  *   mode 4  in-projection of the attention, N = 3d: q / k tiles += lut[cell(token)], L2-normalised per head (q also
  *           * log2(e)/max(tau, tau_min)), 1/|q|, 1/|k| -> lrr; q^, k^, v rows (bf16) go to C = the window-major array
@@ -339,7 +339,7 @@ typedef struct gdmae_tc_epilogue {
   void* y16;                 /* mode 2: (M, N) bf16, nullable */
   float* mean;               /* mode 2: (M) */
   float* rstd;               /* mode 2: (M) */
-  const void* h16;           /* mode 3: (M, ldh) bf16 pre-activation saved by mode 1 */
+  const void* h16;           /* mode 3: (M, ldh) bf16 gelu'(pre-activation + bias) saved by mode 1 (its C) */
   int64_t ldh;
   float* colsum;             /* mode 3: (N) fp32, accumulated into */
   const int32_t* tok_info;   /* modes 4, 5: (M) CSR row | cell << 26 per token (gdmae_sra_bin_units) */

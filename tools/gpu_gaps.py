@@ -73,5 +73,5 @@ for e in seg:
     busy_by[e["name"][:90]][0] += 1
     busy_by[e["name"][:90]][1] += e["dur"]
 print("in-step GPU time by kernel (last step):")
-for k, (c, t) in sorted(busy_by.items(), key=lambda x: -x[1][1])[:40]:
+for k, (c, t) in sorted(busy_by.items(), key=lambda x: -x[1][1])[:int(os.environ.get("GAPS_TOP", "200"))]:
     print(f"  {t:8.1f} us  {c:4d}x  {100 * t / busy:5.1f} %  {k}")
