@@ -54,10 +54,12 @@ extern "C" int gdmae_group_points_centered(const float* points, int n_cols, cons
 #define CH_MAXG 4  // ground-truth points per lane: P2 <= 128
 
 // P2 <= 128 ground-truth points, 16 predicted points per item.
+template <int MAXG>     // ground-truth points per lane: P2 <= 32 * MAXG (2 for the 64 points of the GD-MAE configs)
 __global__ void __launch_bounds__(256) chamfer_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
                                                       const float* __restrict__ w, long long N, int P2,
                                                       float* __restrict__ per_item, float* __restrict__ dpred) {
-  __shared__ float4 sg[8][32 * CH_MAXG];  // per warp: (gx, gy, gz, nearest pred index as float bits) per gt point
+  __shared__ float4 sg[8][32 * MAXG];  // per warp: (gx, gy, gz, nearest pred index as float bits) per gt point
+  __shared__ float4 sp[8][CH_P1];         // per warp: the pillar's predicted points (one broadcast read per point in pass 1)
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   float4* mine = sg[wib];
   const int G = (P2 + 31) >> 5;  // gt points per lane (lane owns j = lane + 32 k)
@@ -74,11 +76,14 @@ __global__ void __launch_bounds__(256) chamfer_kernel(const float* __restrict__ 
       const float* pr = pred + n * CH_P1 * 3 + 3 * lane;
       px = __ldg(pr); py = __ldg(pr + 1); pz = __ldg(pr + 2);
     }
-    float gx[CH_MAXG], gy[CH_MAXG], gz[CH_MAXG], gbest[CH_MAXG];
-    int gidx[CH_MAXG];
+    __syncwarp();
+    if (lane < CH_P1) sp[wib][lane] = make_float4(px, py, pz, 0.f);
+    __syncwarp();
+    float gx[MAXG], gy[MAXG], gz[MAXG], gbest[MAXG];
+    int gidx[MAXG];
     const float* g = gt + n * (long long)P2 * 3;
 #pragma unroll
-    for (int k = 0; k < CH_MAXG; ++k) {
+    for (int k = 0; k < MAXG; ++k) {
       int j = lane + 32 * k;
       bool ok = k < G && j < P2;
       gx[k] = ok ? __ldg(g + 3 * j) : 0.f;
@@ -91,10 +96,11 @@ __global__ void __launch_bounds__(256) chamfer_kernel(const float* __restrict__ 
     unsigned my_key = 0xffffffffu;  // lane i < 16 ends up with the packed arg-min of prediction i
 #pragma unroll
     for (int i = 0; i < CH_P1; ++i) {
-      float qx = __shfl_sync(0xffffffffu, px, i), qy = __shfl_sync(0xffffffffu, py, i), qz = __shfl_sync(0xffffffffu, pz, i);
+      const float4 qp = sp[wib][i];
+      const float qx = qp.x, qy = qp.y, qz = qp.z;
       unsigned dbits = 0xffffffffu, jmin = 0xffffffffu;  // this lane's nearest gt point to prediction i
 #pragma unroll
-      for (int k = 0; k < CH_MAXG; ++k) {
+      for (int k = 0; k < MAXG; ++k) {
         int j = lane + 32 * k;
         if (k < G && j < P2) {
           float dx = qx - gx[k], dy = qy - gy[k], dz = qz - gz[k];
@@ -113,7 +119,7 @@ __global__ void __launch_bounds__(256) chamfer_kernel(const float* __restrict__ 
     float sum_y = 0.f;
     __syncwarp();
 #pragma unroll
-    for (int k = 0; k < CH_MAXG; ++k) {
+    for (int k = 0; k < MAXG; ++k) {
       int j = lane + 32 * k;
       if (k < G && j < P2) {
         sum_y += gbest[k];
@@ -123,21 +129,32 @@ __global__ void __launch_bounds__(256) chamfer_kernel(const float* __restrict__ 
     sum_y = warp_sum(sum_y);
     __syncwarp();
     float sum_x = 0.f;
-    if (lane < CH_P1) {
-      // pred -> gt term: exact distance to the arg-min found above (the packed key dropped 7 mantissa bits)
-      float4 gm = mine[my_key & 127u];
-      float dx = px - gm.x, dy = py - gm.y, dz = pz - gm.z;
-      sum_x = dx * dx + dy * dy + dz * dz;
-      float sx = 2.f * wn / (float)CH_P1, sy = 2.f * wn / (float)P2;
+    {
+      // gt -> pred gradient: prediction (lane & 15) collects the gt points assigned to it; the two half-warps scan one half of
+      // the gt points each (fixed order inside a half, halves added at the end -> deterministic)
+      static_assert(CH_P1 == 16, "half-warp split assumes 16 predicted points");
+      const int pi = lane & 15, hf = lane >> 4;
+      const float4 pp = sp[wib][pi];
+      const int jh = (P2 + 1) >> 1, j0 = hf * jh, j1 = hf ? P2 : jh;
       float ax = 0.f, ay = 0.f, az = 0.f;
-      for (int j = 0; j < P2; ++j) {  // fixed order -> deterministic
-        float4 e = mine[j];
-        if (__float_as_int(e.w) == lane) { ax += px - e.x; ay += py - e.y; az += pz - e.z; }
+      for (int j = j0; j < j1; ++j) {
+        const float4 e = mine[j];
+        if (__float_as_int(e.w) == pi) { ax += pp.x - e.x; ay += pp.y - e.y; az += pp.z - e.z; }
       }
-      float* d = dpred + n * CH_P1 * 3 + 3 * lane;
-      d[0] = sx * dx + sy * ax;
-      d[1] = sx * dy + sy * ay;
-      d[2] = sx * dz + sy * az;
+      ax += __shfl_xor_sync(0xffffffffu, ax, 16);
+      ay += __shfl_xor_sync(0xffffffffu, ay, 16);
+      az += __shfl_xor_sync(0xffffffffu, az, 16);
+      if (lane < CH_P1) {
+        // pred -> gt term: exact distance to the arg-min found above (the packed key dropped 7 mantissa bits)
+        const float4 gm = mine[my_key & 127u];
+        const float dx = px - gm.x, dy = py - gm.y, dz = pz - gm.z;
+        sum_x = dx * dx + dy * dy + dz * dz;
+        const float sx = 2.f * wn / (float)CH_P1, sy = 2.f * wn / (float)P2;
+        float* d = dpred + n * CH_P1 * 3 + 3 * lane;
+        d[0] = sx * dx + sy * ax;
+        d[1] = sx * dy + sy * ay;
+        d[2] = sx * dz + sy * az;
+      }
     }
     sum_x = warp_sum(sum_x);
     if (lane == 0) per_item[n] = wn * (sum_x / (float)CH_P1 + sum_y / (float)P2);
@@ -151,7 +168,8 @@ extern "C" int gdmae_chamfer_fwd(const float* pred, const float* gt, const float
                                  float* per_item, float* dpred, void* stream_) {
   GDMAE_CHECK_ARG(N >= 0 && P1 == CH_P1 && P2 >= 1 && P2 <= 32 * CH_MAXG);
   if (N == 0) return GDMAE_OK;
-  chamfer_kernel<<<gdmae_grid(N * 32, 256, 8), 256, 0, (cudaStream_t)stream_>>>(pred, gt, weights, N, P2, per_item, dpred);
+  if (P2 <= 64) chamfer_kernel<2><<<gdmae_grid(N * 32, 256, 8), 256, 0, (cudaStream_t)stream_>>>(pred, gt, weights, N, P2, per_item, dpred);
+  else chamfer_kernel<CH_MAXG><<<gdmae_grid(N * 32, 256, 8), 256, 0, (cudaStream_t)stream_>>>(pred, gt, weights, N, P2, per_item, dpred);
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;
 }

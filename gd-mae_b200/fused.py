@@ -512,9 +512,11 @@ class BatchNormReLUFunction(torch.autograd.Function):
 
 
 _DTC = {torch.float32: 0, torch.bfloat16: 1}      # dtype codes of the C ABI
-# pre-BatchNorm deconvolution output u of the deblocks: fp32 (statistics from the fp32 accumulators' values) or, with
-# GDMAE_DEBLOCK_U16=1, bf16 straight from the GEMM epilogue (halves five more passes; rounds u before the statistics)
-DEBLOCK_U_DTYPE = torch.bfloat16 if os.environ.get("GDMAE_DEBLOCK_U16", "0") == "1" else torch.float32
+# pre-BatchNorm deconvolution output u of the deblocks: bf16 straight from the GEMM epilogue, like every other GEMM output of
+# the bf16 configuration that only feeds a row kernel (a, h, f, VFE y2): the BatchNorm statistics are taken in fp32 from those
+# values.  Five passes over the 135 M-element tensor move half the bytes (r2: -0.14 ms per step).  GDMAE_DEBLOCK_U16=0 keeps
+# u in fp32.
+DEBLOCK_U_DTYPE = torch.float32 if os.environ.get("GDMAE_DEBLOCK_U16", "1") == "0" else torch.bfloat16
 
 
 class DeblockRowsFunction(torch.autograd.Function):
