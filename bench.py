@@ -487,6 +487,14 @@ def main():
         "cuda_mallocs_in_timed_legs": {"value": device_allocs[0], "e2e": device_allocs[1]},
         "peak_allocated_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30, "reserved_gb": torch.cuda.memory_reserved(dev) / 2 ** 30, "host_cores": len(os.sched_getaffinity(0)),
     }
+    if world > 1:
+        # every rank applied the same all-reduced gradients to the same start: the parameter buckets must be bit-identical
+        chk = torch.stack([trainer.flat_params.double().sum(), trainer.flat_params.double().abs().sum()])
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        out["ddp_params_in_sync"] = bool((lo == hi).all())
+        assert out["ddp_params_in_sync"], "parameter buckets diverged across ranks"
     from gd_mae_b200 import ops as _ops
     n_to = _ops.sra_wait_timeouts()
     assert n_to == 0, f"{n_to} bounded waits inside the SRA kernels timed out: results are invalid"

@@ -756,6 +756,77 @@ def test_dense_fill_typed_rows_and_one_pass_backward(G):
             assert e < 1e-5, (s, e)        # float sums in a different order
 
 
+def test_typed_batchnorm_relu_matches_fp32_kernels(G):
+    """gdmae_batchnorm_relu_fwd_t / _bwd_t (typed tensors, used by the decoder deblocks of the bf16 configuration) against the
+    fp32 entry points: identical arithmetic when every tensor is fp32, and only the roundings of the bf16 tensors otherwise
+    (bf16 out / dout / dy; y stays fp32 here so that the ReLU masks are the same on both sides)."""
+    import ctypes
+    from gd_mae_b200 import _lib as L
+    lib = L.lib()
+    torch.manual_seed(5)
+    N, C = 3001, 128
+    u = torch.randn(N, C, device="cuda")
+    gamma, beta = torch.rand(C, device="cuda") + 0.5, torch.rand(C, device="cuda") - 0.5
+    count = float(3 * N)
+    ws = torch.empty(lib.gdmae_batchnorm_workspace_bytes(C), dtype=torch.uint8, device="cuda")
+    wsz = ctypes.c_size_t(ws.numel())
+    code = {torch.float32: 0, torch.bfloat16: 1}
+    o0, m0, r0 = torch.empty_like(u), torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    L.check(lib.gdmae_batchnorm_relu_fwd(L.P(u), L.P(gamma), L.P(beta), L.i64(N), C, ctypes.c_double(count), L.f32(1e-3), L.f32(0.01), 1,
+                                         L.P(o0), L.P(m0), L.P(r0), None, None, L.P(ws), wsz, L.stream()), "fwd")
+    for od in (torch.float32, torch.bfloat16):
+        o1 = torch.empty((N, C), dtype=od, device="cuda")
+        m1, r1 = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+        L.check(lib.gdmae_batchnorm_relu_fwd_t(L.P(u), 0, L.P(gamma), L.P(beta), L.i64(N), C, ctypes.c_double(count), L.f32(1e-3), L.f32(0.01),
+                                               1, L.P(o1), code[od], L.P(m1), L.P(r1), None, None, L.P(ws), wsz, L.stream()), "fwd_t")
+        assert rel(m1, m0) < 1e-6 and rel(r1, r0) < 1e-6
+        assert torch.equal(o1, o0.to(od)) or rel(o1.float(), o0) < (1e-6 if od == torch.float32 else 4e-3), od
+    dout = torch.randn(N, C, device="cuda").bfloat16()          # a bf16-representable upstream gradient for every variant
+    y0, g0, b0 = torch.empty_like(u), torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    L.check(lib.gdmae_batchnorm_relu_bwd(L.P(u), L.P(beta), L.P(dout.float().contiguous()), L.P(gamma), L.P(m0), L.P(r0), L.i64(N), C,
+                                         ctypes.c_double(count), 1, None, None, L.P(y0), None, L.P(g0), L.P(b0), L.P(ws), wsz, L.stream()), "bwd")
+    for dd in (torch.float32, torch.bfloat16):
+        for gd in (torch.float32, torch.bfloat16):
+            d = dout.to(dd).contiguous()
+            y1 = torch.empty((N, C), dtype=gd, device="cuda")
+            g1, b1 = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+            L.check(lib.gdmae_batchnorm_relu_bwd_t(L.P(u), 0, L.P(beta), L.P(d), code[dd], L.P(gamma), L.P(m0), L.P(r0), L.i64(N), C,
+                                                   ctypes.c_double(count), 1, None, None, L.P(y1), code[gd], L.P(g1), L.P(b1), L.P(ws), wsz,
+                                                   L.stream()), "bwd_t")
+            assert rel(g1, g0) < 1e-5 and rel(b1, b0) < 1e-5, (dd, gd)
+            assert rel(y1.float(), y0) < (1e-6 if gd == torch.float32 else 4e-3), (dd, gd, rel(y1.float(), y0))
+
+
+@pytest.mark.parametrize("C", [128, 256, 96])
+def test_sparse_conv_gathers_match_indexing(G, C):
+    """gdmae_gather_rows / gdmae_gather_rows_transposed (im2col over a 9-tap neighbour map and its transposed gather): the
+    bf16 fast paths (C = 128, 256) and the generic kernels (C = 96, fp32 output) against plain indexing."""
+    torch.manual_seed(C)
+    N, Ns, K = 4099, 3500, 9
+    x = torch.randn(Ns, C, device="cuda")
+    fmap = torch.randint(-1, Ns, (N, K), device="cuda", dtype=torch.int32)
+    fmap[torch.rand(N, K, device="cuda") < 0.5] = -1
+    safe = fmap.long().clamp(min=0)
+    ref = torch.where((fmap >= 0)[..., None], x[safe], torch.zeros((), device="cuda")).reshape(N, K * C)
+    for od in (torch.bfloat16, torch.float32):
+        col = G.ops.gather_rows(x, fmap, od)
+        assert col.dtype == od and torch.equal(col, ref.to(od)), (C, od)
+    # transposed: dsrc[i] = sum_k dcol[tmap[i, k], k]   (mirror = 0)
+    tmap = torch.randint(-1, N, (Ns, K), device="cuda", dtype=torch.int32)
+    tmap[torch.rand(Ns, K, device="cuda") < 0.5] = -1
+    dcol = torch.randn(N, K * C, device="cuda").bfloat16()
+    d3 = dcol.float().view(N, K, C)
+    for mirror in (False, True):
+        want = torch.zeros(Ns, C, device="cuda")
+        for k in range(K):
+            idx = tmap[:, K - 1 - k if mirror else k].long()
+            want += torch.where((idx >= 0)[:, None], d3[idx.clamp(min=0), k], torch.zeros((), device="cuda"))
+        got = G.ops.gather_rows_transposed(dcol, tmap, Ns, mirror)
+        assert rel(got, want) < 1e-6, (C, mirror, rel(got, want))
+        got32 = G.ops.gather_rows_transposed(dcol.float(), tmap, Ns, mirror)
+        assert rel(got32, want) < 1e-6, (C, mirror)
+
+
 def ctypes_int():
     import ctypes
     return ctypes.byref(ctypes.c_int(0))
