@@ -8,8 +8,11 @@
 // ATen's path for the same work is batch_norm_collect_statistics + transform_input + a separate
 // ReLU forward, and threshold_backward + backward_reduce + backward_elemt backward.
 #include "common.cuh"
+#include <stdlib.h>
+#include <stdint.h>
 #include <cuda_bf16.h>
 #include "bn_common.cuh"
+#include "bulk_pipe.cuh"
 
 
 // thread owns float4 column group (threadIdx.x % C4) and rows (threadIdx.x / C4) + k * rows_per_cta
@@ -501,6 +504,110 @@ __global__ void __launch_bounds__(256) bn8_relu_bwd_apply_kernel(const TY* __res
   }
 }
 
+// ---- the bf16 / bf16 / bf16, C = 128 case of the two backward passes with their rows staged by bulk copies -----------------
+// (the decoder deblocks of the bf16 configuration: 135 M elements per tensor and step).  A tile = 32 consecutive rows of y
+// and of dout (8 KB each, contiguous), brought by one elected thread into a ring of BNB_STAGES stages (csrc/bulk_pipe.cuh);
+// the apply pass composes its bf16 output tile in shared memory and sends it back with one bulk store.  Only whole tiles;
+// the host runs the generic kernels above on the last N % 32 rows.  r2: the register-staged kernels ran at 3.0 (statistics)
+// and 3.7 TB/s (apply).
+#define BNB_ROWS 32
+#define BNB_STAGES 4
+#define BNB_C 128
+#define BNB_TILE_BYTES (BNB_ROWS * BNB_C * 2)
+#define BNB_SMEM_STATS (BNB_STAGES * 2 * BNB_TILE_BYTES)
+#define BNB_SMEM_APPLY (BNB_STAGES * 2 * BNB_TILE_BYTES + 2 * BNB_TILE_BYTES)
+
+__device__ __forceinline__ void bnb_unpack(const uint4 u, float (&v)[8]) {
+  const unsigned w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+
+template <bool APPLY>
+__global__ void __launch_bounds__(256, 3) bn8_relu_bwd_bulk_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ gamma,
+                                                                   const float* __restrict__ beta, const __nv_bfloat16* __restrict__ dout,
+                                                                   const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                   const float* __restrict__ dbeta, const float* __restrict__ dgamma,
+                                                                   float inv_count, long long ntile, int relu, float* __restrict__ partial,
+                                                                   __nv_bfloat16* __restrict__ dy) {
+  extern __shared__ __align__(128) unsigned char bnb_smem[];
+  __shared__ unsigned long long full[BNB_STAGES];
+  constexpr int C8 = BNB_C / 8;
+  const int tid = threadIdx.x, c = tid % C8, rsub = tid / C8;       // 16 rows per pass, 2 passes per tile
+  const long long my_tiles = ntile > blockIdx.x ? (ntile - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  if (tid == 0) {
+    for (int st = 0; st < BNB_STAGES; ++st) bp::mbar_init(&full[st], 1);
+    bp::fence_barrier_init();
+  }
+  __syncthreads();
+  auto issue = [&](long long it) {
+    const int st = (int)(it % BNB_STAGES);
+    const long long row0 = (blockIdx.x + it * gridDim.x) * BNB_ROWS;
+    unsigned char* base = bnb_smem + st * 2 * BNB_TILE_BYTES;
+    bp::mbar_expect_tx(&full[st], 2 * BNB_TILE_BYTES);
+    bp::g2s(base, y + row0 * BNB_C, BNB_TILE_BYTES, &full[st]);
+    bp::g2s(base + BNB_TILE_BYTES, dout + row0 * BNB_C, BNB_TILE_BYTES, &full[st]);
+  };
+  if (tid == 0)
+    for (long long it = 0; it < BNB_STAGES && it < my_tiles; ++it) issue(it);
+  float m[8], r[8], ga[8], be[8], db[8], dg[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    m[i] = __ldg(mean + 8 * c + i); r[i] = __ldg(rstd + 8 * c + i); ga[i] = __ldg(gamma + 8 * c + i); be[i] = __ldg(beta + 8 * c + i);
+    db[i] = APPLY ? __ldg(dbeta + 8 * c + i) * inv_count : 0.f;
+    dg[i] = APPLY ? __ldg(dgamma + 8 * c + i) : 0.f;
+  }
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, q[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  unsigned char* obuf = bnb_smem + BNB_STAGES * 2 * BNB_TILE_BYTES;       // APPLY: two output tiles
+  for (long long it = 0; it < my_tiles; ++it) {
+    const int st = (int)(it % BNB_STAGES);
+    bp::mbar_wait(&full[st], (unsigned)((it / BNB_STAGES) & 1));
+    const uint4* ys = reinterpret_cast<const uint4*>(bnb_smem + st * 2 * BNB_TILE_BYTES);
+    const uint4* ds = ys + BNB_TILE_BYTES / 16;
+    uint4* os = reinterpret_cast<uint4*>(obuf + (it & 1) * BNB_TILE_BYTES);
+#pragma unroll
+    for (int ps = 0; ps < BNB_ROWS / 16; ++ps) {
+      const int row = ps * 16 + rsub;
+      float v[8], d[8];
+      bnb_unpack(ys[row * C8 + c], v);
+      bnb_unpack(ds[row * C8 + c], d);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float xh = (v[k] - m[k]) * r[k];
+        if (relu && !((v[k] - m[k]) * r[k] * ga[k] + be[k] > 0.f)) d[k] = 0.f;
+        if (APPLY) d[k] = ga[k] * r[k] * (d[k] - db[k] - xh * dg[k] * inv_count);
+        else { s[k] += d[k]; q[k] = fmaf(d[k], xh, q[k]); }
+      }
+      if (APPLY) {
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(d[0], d[1]), p1 = __floats2bfloat162_rn(d[2], d[3]);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(d[4], d[5]), p3 = __floats2bfloat162_rn(d[6], d[7]);
+        os[row * C8 + c] = make_uint4(*reinterpret_cast<unsigned*>(&p0), *reinterpret_cast<unsigned*>(&p1),
+                                      *reinterpret_cast<unsigned*>(&p2), *reinterpret_cast<unsigned*>(&p3));
+      }
+    }
+    if (APPLY) bp::fence_async_smem();         // the output tile (generic proxy) is read by the bulk store
+    __syncthreads();                           // stage consumed / output tile complete
+    if (tid == 0) {
+      if (APPLY) {
+        const long long row0 = (blockIdx.x + it * gridDim.x) * BNB_ROWS;
+        bp::s2g(dy + row0 * BNB_C, os, BNB_TILE_BYTES);
+        bp::s2g_commit();
+      }
+      if (it + BNB_STAGES < my_tiles) {
+        bp::fence_async_smem();
+        issue(it + BNB_STAGES);
+      }
+      if (APPLY) bp::s2g_wait_read<1>();       // the store of tile it - 1 has read its buffer: tile it + 1 may overwrite it
+    }
+    if (APPLY) __syncthreads();
+  }
+  if (APPLY) {
+    if (tid == 0) bp::s2g_wait_all<0>();
+  } else {
+    tail_block_reduce(s, q, C8, partial);      // [dbeta(C) | dgamma(C)] per CTA
+  }
+}
+
 #define BN8_DISPATCH2(A, B, CALL)                                                  \
   do {                                                                             \
     if ((A) == 0 && (B) == 0) { using T0 = float; using T1 = float; CALL; }        \
@@ -551,12 +658,32 @@ extern "C" int gdmae_batchnorm_relu_bwd_t(const void* y, int y_dtype, const floa
   float* partial = (float*)workspace;
   const int C8 = C / 8, rper = 256 / C8;
   int grid = (int)min((long long)BN_PART_BLOCKS, (long long)((N + rper - 1) / rper));
+  static const bool bulk_on = [] { const char* e = getenv("GDMAE_BN_BULK"); return !(e && e[0] == '0'); }();      // =0: generic kernels (A/B)
+  const long long nt = N / BNB_ROWS, tail = N - nt * BNB_ROWS;
+  const bool bulk = bulk_on && C == BNB_C && y_dtype == 1 && dout_dtype == 1 && dy_dtype == 1 && nt > 0 &&
+                    (((uintptr_t)y | (uintptr_t)dout | (uintptr_t)dy) & 15) == 0;
   if (N == 0) {
     GDMAE_CHECK_CUDA(cudaMemsetAsync(partial, 0, (size_t)2 * C * 4, st));
     grid = 1;
   } else {
-    BN8_DISPATCH2(y_dtype, dout_dtype,
-                  (bn8_relu_bwd_stats_kernel<T0, T1><<<grid, 256, 0, st>>>((const T0*)y, gamma, beta, (const T1*)dout, mean, rstd, N, C8, relu, partial)));
+    if (bulk) {
+      // whole 32-row tiles through the bulk-copy ring, the last N % 32 rows by one CTA of the generic kernel (one more partial row)
+      static int attr_s = cudaFuncSetAttribute(bn8_relu_bwd_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BNB_SMEM_STATS);
+      (void)attr_s;
+      const int gb = (int)min((long long)GDMAE_NUM_SMS * 2, nt);      // 64 KB ring + 16 KB reduction buffer: two CTAs per SM
+      bn8_relu_bwd_bulk_kernel<false><<<gb, 256, BNB_SMEM_STATS, st>>>((const __nv_bfloat16*)y, gamma, beta, (const __nv_bfloat16*)dout, mean, rstd,
+                                                                       nullptr, nullptr, 0.f, nt, relu, partial, nullptr);
+      GDMAE_LAUNCH_CHECK();
+      grid = gb;
+      if (tail > 0) {
+        bn8_relu_bwd_stats_kernel<__nv_bfloat16, __nv_bfloat16><<<1, 256, 0, st>>>((const __nv_bfloat16*)y + nt * BNB_ROWS * C, gamma, beta,
+            (const __nv_bfloat16*)dout + nt * BNB_ROWS * C, mean, rstd, tail, C8, relu, partial + (long long)gb * 2 * C);
+        grid = gb + 1;
+      }
+    } else {
+      BN8_DISPATCH2(y_dtype, dout_dtype,
+                    (bn8_relu_bwd_stats_kernel<T0, T1><<<grid, 256, 0, st>>>((const T0*)y, gamma, beta, (const T1*)dout, mean, rstd, N, C8, relu, partial)));
+    }
     GDMAE_LAUNCH_CHECK();
   }
   bn_bwd_finalize_kernel<<<gdmae_div_up(C, 32), 256, 0, st>>>(partial, grid, C, extra_dbeta, extra_dgamma, dbeta, dgamma);
@@ -565,7 +692,18 @@ extern "C" int gdmae_batchnorm_relu_bwd_t(const void* y, int y_dtype, const floa
   const long long n8 = N * C8;
   const int g2 = gdmae_grid(n8, 256, 16);
   const float inv = (float)(1.0 / count);
-  if (dy_dtype == 0)
+  if (bulk) {
+    static int attr_a = cudaFuncSetAttribute(bn8_relu_bwd_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BNB_SMEM_APPLY);
+    (void)attr_a;
+    const int gb = (int)min((long long)GDMAE_NUM_SMS * 2, nt);
+    bn8_relu_bwd_bulk_kernel<true><<<gb, 256, BNB_SMEM_APPLY, st>>>((const __nv_bfloat16*)y, gamma, beta, (const __nv_bfloat16*)dout, mean, rstd,
+                                                                    dbeta, dgamma, inv, nt, relu, nullptr, (__nv_bfloat16*)dy);
+    GDMAE_LAUNCH_CHECK();
+    if (tail > 0)
+      bn8_relu_bwd_apply_kernel<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16><<<gdmae_grid(tail * C8, 256, 16), 256, 0, st>>>(
+          (const __nv_bfloat16*)y + nt * BNB_ROWS * C, beta, (const __nv_bfloat16*)dout + nt * BNB_ROWS * C, mean, rstd, gamma, dbeta, dgamma, inv,
+          tail * C8, C8, relu, (__nv_bfloat16*)dy + nt * BNB_ROWS * C);
+  } else if (dy_dtype == 0)
     BN8_DISPATCH2(y_dtype, dout_dtype,
                   (bn8_relu_bwd_apply_kernel<T0, T1, float><<<g2, 256, 0, st>>>((const T0*)y, beta, (const T1*)dout, mean, rstd, gamma, dbeta, dgamma,
                                                                                 inv, n8, C8, relu, (float*)dy)));
