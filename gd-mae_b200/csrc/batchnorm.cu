@@ -346,6 +346,97 @@ __global__ void __launch_bounds__(256) tail_dense_bwd_apply_kernel(const T* __re
   }
 }
 
+// The bf16, C = 128 case of tail_dense_bwd_apply_kernel with the dense map staged by bulk copies: a tile = 32 consecutive
+// cells of y (8 KB) + their cell -> pillar indices (128 B) arrives in a ring of TDB_STAGES stages, the 8 KB tile of dy is
+// composed in shared memory and leaves as one bulk store; the rows of out / dout of the ~13 % cells that carry a pillar are
+// plain loads.  r2: the register-staged kernel moved its 900 MB at 3.2 TB/s (283 us).
+#define TDB_ROWS 32
+#define TDB_STAGES 4
+#define TDB_C 128
+#define TDB_TILE_BYTES (TDB_ROWS * TDB_C * 2)
+#define TDB_STAGE_BYTES (TDB_TILE_BYTES + 128)
+#define TDB_SMEM (TDB_STAGES * TDB_STAGE_BYTES + 2 * TDB_TILE_BYTES)
+__global__ void __launch_bounds__(256, 3) tail_dense_bwd_apply_bulk_kernel(const __nv_bfloat16* __restrict__ y, const int* __restrict__ cell2pillar,
+                                                                           long long ntile, const float* __restrict__ out,
+                                                                           const float* __restrict__ dout, const float* __restrict__ mean,
+                                                                           const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                                           const float* __restrict__ dbeta, const float* __restrict__ dgamma,
+                                                                           float inv_n, __nv_bfloat16* __restrict__ dy) {
+  extern __shared__ __align__(128) unsigned char tdb_smem[];
+  __shared__ unsigned long long full[TDB_STAGES];
+  constexpr int C8 = TDB_C / 8;
+  const int tid = threadIdx.x, c = tid % C8, rsub = tid / C8;
+  const long long my_tiles = ntile > blockIdx.x ? (ntile - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  if (tid == 0) {
+    for (int st = 0; st < TDB_STAGES; ++st) bp::mbar_init(&full[st], 1);
+    bp::fence_barrier_init();
+  }
+  __syncthreads();
+  auto issue = [&](long long it) {
+    const int st = (int)(it % TDB_STAGES);
+    const long long cell0 = (blockIdx.x + it * gridDim.x) * TDB_ROWS;
+    unsigned char* base = tdb_smem + st * TDB_STAGE_BYTES;
+    bp::mbar_expect_tx(&full[st], TDB_TILE_BYTES + TDB_ROWS * 4);
+    bp::g2s(base, y + cell0 * TDB_C, TDB_TILE_BYTES, &full[st]);
+    bp::g2s(base + TDB_TILE_BYTES, cell2pillar + cell0, TDB_ROWS * 4, &full[st]);
+  };
+  if (tid == 0)
+    for (long long it = 0; it < TDB_STAGES && it < my_tiles; ++it) issue(it);
+  float mu[8], a0[8], a1[8], c2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int ch = 8 * c + i;
+    const float rs = __ldg(rstd + ch);
+    mu[i] = __ldg(mean + ch);
+    a0[i] = __ldg(gamma + ch) * rs;                    // dy = a0 * g - a1 - (y - mean) * c2,  c2 = rstd * a0 * dgamma / n
+    a1[i] = a0[i] * __ldg(dbeta + ch) * inv_n;
+    c2[i] = rs * (a0[i] * __ldg(dgamma + ch) * inv_n);
+  }
+  unsigned char* obuf = tdb_smem + TDB_STAGES * TDB_STAGE_BYTES;
+  for (long long it = 0; it < my_tiles; ++it) {
+    const int st = (int)(it % TDB_STAGES);
+    bp::mbar_wait(&full[st], (unsigned)((it / TDB_STAGES) & 1));
+    const uint4* ys = reinterpret_cast<const uint4*>(tdb_smem + st * TDB_STAGE_BYTES);
+    const int* ms = reinterpret_cast<const int*>(tdb_smem + st * TDB_STAGE_BYTES + TDB_TILE_BYTES);
+    uint4* os = reinterpret_cast<uint4*>(obuf + (it & 1) * TDB_TILE_BYTES);
+#pragma unroll
+    for (int ps = 0; ps < TDB_ROWS / 16; ++ps) {
+      const int row = ps * 16 + rsub;
+      const uint4 u = ys[row * C8 + c];
+      const int m = ms[row];
+      const unsigned w[4] = {u.x, u.y, u.z, u.w};
+      float r[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        r[2 * i] = -a1[2 * i] - (__uint_as_float(w[i] << 16) - mu[2 * i]) * c2[2 * i];
+        r[2 * i + 1] = -a1[2 * i + 1] - (__uint_as_float(w[i] & 0xffff0000u) - mu[2 * i + 1]) * c2[2 * i + 1];
+      }
+      if (m >= 0) {
+        float o[8], g[8];
+        Row8<float>::load(out, (long long)m * C8 + c, o);
+        Row8<float>::load(dout, (long long)m * C8 + c, g);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = fmaf(a0[i], o[i] > 0.f ? g[i] : 0.f, r[i]);
+      }
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(r[0], r[1]), p1 = __floats2bfloat162_rn(r[2], r[3]);
+      __nv_bfloat162 p2 = __floats2bfloat162_rn(r[4], r[5]), p3 = __floats2bfloat162_rn(r[6], r[7]);
+      os[row * C8 + c] = make_uint4(*reinterpret_cast<unsigned*>(&p0), *reinterpret_cast<unsigned*>(&p1), *reinterpret_cast<unsigned*>(&p2),
+                                    *reinterpret_cast<unsigned*>(&p3));
+    }
+    bp::fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      const long long cell0 = (blockIdx.x + it * gridDim.x) * TDB_ROWS;
+      bp::s2g(dy + cell0 * TDB_C, os, TDB_TILE_BYTES);
+      bp::s2g_commit();
+      if (it + TDB_STAGES < my_tiles) issue(it + TDB_STAGES);
+      bp::s2g_wait_read<1>();
+    }
+    __syncthreads();
+  }
+  if (tid == 0) bp::s2g_wait_all<0>();
+}
+
 static int tail_check(int B, int Y, int X, int C, int dtype, size_t ws_bytes) {
   GDMAE_CHECK_ARG(B >= 1 && Y >= 1 && X >= 1 && C > 0 && (C % 8) == 0 && 256 % (C / 8) == 0 && (dtype == 0 || dtype == 1));
   if (ws_bytes < gdmae_batchnorm_workspace_bytes(C)) { gdmae_set_error("decoder tail: workspace too small"); return GDMAE_ERR_WORKSPACE; }
@@ -413,9 +504,25 @@ extern "C" int gdmae_decoder_tail_bwd(const void* y, int dtype, int B, int Y, in
   if (dtype == 0)
     tail_dense_bwd_apply_kernel<float><<<g2, 256, 0, st>>>((const float*)y, cell2pillar, n_cells, C8, out, dout, mean, rstd, gamma, dbeta,
                                                            dgamma, inv_n, (float*)dy);
-  else
-    tail_dense_bwd_apply_kernel<__nv_bfloat16><<<g2, 256, 0, st>>>((const __nv_bfloat16*)y, cell2pillar, n_cells, C8, out, dout, mean, rstd,
-                                                                   gamma, dbeta, dgamma, inv_n, (__nv_bfloat16*)dy);
+  else {
+    static const bool bulk_on = [] { const char* e = getenv("GDMAE_BN_BULK"); return !(e && e[0] == '0'); }();      // =0: generic kernel (A/B)
+    const long long nt = n_cells / TDB_ROWS, tail = n_cells - nt * TDB_ROWS;
+    if (bulk_on && C == TDB_C && nt > 0 && (((uintptr_t)y | (uintptr_t)dy | (uintptr_t)cell2pillar) & 15) == 0) {
+      static int attr_t = cudaFuncSetAttribute(tail_dense_bwd_apply_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TDB_SMEM);
+      (void)attr_t;
+      const int gb = (int)min((long long)GDMAE_NUM_SMS * 3, nt);
+      tail_dense_bwd_apply_bulk_kernel<<<gb, 256, TDB_SMEM, st>>>((const __nv_bfloat16*)y, cell2pillar, nt, out, dout, mean, rstd, gamma, dbeta,
+                                                                  dgamma, inv_n, (__nv_bfloat16*)dy);
+      GDMAE_LAUNCH_CHECK();
+      if (tail > 0)
+        tail_dense_bwd_apply_kernel<__nv_bfloat16><<<1, 256, 0, st>>>((const __nv_bfloat16*)y + nt * TDB_ROWS * C, cell2pillar + nt * TDB_ROWS, tail,
+                                                                      C8, out, dout, mean, rstd, gamma, dbeta, dgamma, inv_n,
+                                                                      (__nv_bfloat16*)dy + nt * TDB_ROWS * C);
+    } else {
+      tail_dense_bwd_apply_kernel<__nv_bfloat16><<<g2, 256, 0, st>>>((const __nv_bfloat16*)y, cell2pillar, n_cells, C8, out, dout, mean, rstd,
+                                                                     gamma, dbeta, dgamma, inv_n, (__nv_bfloat16*)dy);
+    }
+  }
   GDMAE_LAUNCH_CHECK();
   return GDMAE_OK;
 }
