@@ -579,6 +579,70 @@ class DeblockRowsFunction(torch.autograd.Function):
         return dx, dw, None, dgamma, dbeta, None, None, None, None, None
 
 
+class SparseConvBNReLUFunction(torch.autograd.Function):
+    """post_act_block of the bf16 configuration as ONE autograd node (pcdet/utils/spconv_utils.py:37-56: SubMConv2d /
+    SparseConv2d + BatchNorm1d + ReLU): gather -> GEMM (own tcgen05 kernel, pre-BatchNorm output y as bf16) -> BatchNorm
+    statistics + apply; backward: the BatchNorm backward hands its gradient to the two backward GEMMs as bf16 (no fp32
+    dy, no cast pass), dx by the transposed gather.  y (bf16) is the only activation kept besides the im2col operand."""
+
+    @staticmethod
+    @_ops._fwd
+    def forward(ctx, x, weight, fwd_map, bwd_map, mirror, gamma, beta, running_mean, running_var, momentum, eps):
+        x = x.contiguous()
+        w = _gw(weight).view(weight.shape[0], -1)            # (C_out, 9*C_in) bf16
+        col = _ops.gather_rows(x, fwd_map, BF16)
+        y = gemm(col, w.t(), out_dtype=BF16)                 # (N, C_out)
+        N, C = y.shape
+        dev = y.device
+        out = torch.empty((N, C), dtype=F32, device=dev)     # feeds the fp32 residual stream of the encoder layers
+        mean = torch.empty((C,), dtype=F32, device=dev)
+        rstd = torch.empty((C,), dtype=F32, device=dev)
+        lib = L.lib()
+        ws = L.workspace(lib.gdmae_batchnorm_workspace_bytes(C), dev)
+        L.check(lib.gdmae_batchnorm_relu_fwd_t(L.P(y), 1, L.P(gamma), L.P(beta), L.i64(N), C, ctypes.c_double(float(N)), L.f32(eps),
+                                               L.f32(momentum), 1, L.P(out), 0, L.P(mean), L.P(rstd), L.P(running_mean),
+                                               L.P(running_var), L.P(ws), ctypes.c_size_t(ws.numel()), L.stream()),
+                "gdmae_batchnorm_relu_fwd_t")
+        ctx.save_for_backward(col, w, bwd_map, y, beta, gamma, mean, rstd)
+        ctx.mirror, ctx.n_src, ctx.wshape = mirror, x.shape[0], weight.shape
+        return out
+
+    @staticmethod
+    @_ops._bwd
+    def backward(ctx, dout):
+        col, w, bwd_map, y, beta, gamma, mean, rstd = ctx.saved_tensors
+        N, C = y.shape
+        dev = y.device
+        dout = dout.contiguous()
+        dy16 = torch.empty((N, C), dtype=BF16, device=dev)
+        dgamma = torch.empty((C,), dtype=F32, device=dev)
+        dbeta = torch.empty((C,), dtype=F32, device=dev)
+        lib = L.lib()
+        ws = L.workspace(lib.gdmae_batchnorm_workspace_bytes(C), dev)
+        L.check(lib.gdmae_batchnorm_relu_bwd_t(L.P(y), 1, L.P(beta), L.P(dout), _DTC[dout.dtype], L.P(gamma), L.P(mean), L.P(rstd), L.i64(N), C,
+                                               ctypes.c_double(float(N)), 1, None, None, L.P(dy16), 1, L.P(dgamma), L.P(dbeta), L.P(ws),
+                                               ctypes.c_size_t(ws.numel()), L.stream()),
+                "gdmae_batchnorm_relu_bwd_t")
+        dw = gemm(dy16.t(), col, wgrad=True).view(ctx.wshape)
+        dcol = gemm(dy16, w, out_dtype=BF16)
+        dx = _ops.gather_rows_transposed(dcol, bwd_map, ctx.n_src, ctx.mirror)
+        return dx, dw, None, None, None, dgamma, dbeta, None, None, None, None
+
+
+def sparse_conv_bn_relu_ok(conv, bn, x, training):
+    """the fused node applies: bf16 configuration, training-mode statistics, channel counts the typed BatchNorm kernels take"""
+    c = conv.out_channels
+    return (GEMM_DTYPE == BF16 and TC_GEMM and training and bn.training and bn.track_running_stats and x.is_cuda and c % 64 == 0
+            and 256 % (c // 8) == 0 and os.environ.get("GDMAE_FUSE_SPCONV_BN", "1") != "0")
+
+
+def sparse_conv_bn_relu(conv, bn, feats, fwd_map, bwd_map, mirror):
+    out = SparseConvBNReLUFunction.apply(feats, conv.weight, fwd_map, bwd_map, mirror, bn.weight, bn.bias, bn.running_mean,
+                                         bn.running_var, bn.momentum, bn.eps)
+    bn.num_batches_tracked += 1
+    return out
+
+
 def deblock_rows(deconv, bn, k, x, count):
     """ConvTranspose2d(k = stride) + BatchNorm2d(train) + ReLU on the sparse rows, bf16 configuration (see DeblockRowsFunction)"""
     out, bg = DeblockRowsFunction.apply(x, deconv.weight, k, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps,

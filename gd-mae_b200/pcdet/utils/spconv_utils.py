@@ -149,6 +149,16 @@ class SparseConvolution(SparseModule):
         y = _fused.SparseConvFunction.apply(x.features, self.weight, d.nbr_down, d.nbr_up, False)
         return SparseConvTensor(y, d.indices, d.spatial_shape, x.batch_size, d.struct)
 
+    def forward_bn_relu(self, x, bn):
+        """this convolution followed by BatchNorm1d (training statistics) + ReLU as one autograd node (bf16 configuration)"""
+        from ... import fused as _fused
+        if self.subm:
+            nbr = x.subm_map()
+            return x.replace_feature(_fused.sparse_conv_bn_relu(self, bn, x.features, nbr, nbr, True))
+        d = x.down()
+        y = _fused.sparse_conv_bn_relu(self, bn, x.features, d.nbr_down, d.nbr_up, False)
+        return SparseConvTensor(y, d.indices, d.spatial_shape, x.batch_size, d.struct)
+
 
 class SubMConv2d(SparseConvolution):
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, bias=False, indice_key=None):
@@ -167,7 +177,13 @@ class SparseSequential(nn.Sequential):
         i = 0
         while i < len(mods):
             m = mods[i]
-            if isinstance(m, SparseModule):
+            if (isinstance(m, SparseConvolution) and i + 2 < len(mods) and isinstance(mods[i + 1], nn.BatchNorm1d)
+                    and isinstance(mods[i + 2], nn.ReLU)
+                    and _fused.sparse_conv_bn_relu_ok(m, mods[i + 1], x.features, self.training and mods[i + 1].training)):
+                # conv + BatchNorm1d + ReLU (post_act_block) as one node: bf16 gradient hand-over inside (fused.py)
+                x = m.forward_bn_relu(x, mods[i + 1])
+                i += 2
+            elif isinstance(m, SparseModule):
                 x = m(x)
             elif (isinstance(m, nn.BatchNorm1d) and i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU) and x.features.is_cuda
                   and m.track_running_stats):
