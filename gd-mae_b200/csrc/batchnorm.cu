@@ -617,30 +617,43 @@ __global__ void __launch_bounds__(256) bn8_relu_bwd_apply_kernel(const TY* __res
 // the apply pass composes its bf16 output tile in shared memory and sends it back with one bulk store.  Only whole tiles;
 // the host runs the generic kernels above on the last N % 32 rows.  r2: the register-staged kernels ran at 3.0 (statistics)
 // and 3.7 TB/s (apply).
-#define BNB_ROWS 32
 #define BNB_STAGES 4
-#define BNB_C 128
-#define BNB_TILE_BYTES (BNB_ROWS * BNB_C * 2)
-#define BNB_SMEM_STATS (BNB_STAGES * 2 * BNB_TILE_BYTES)
-#define BNB_SMEM_APPLY (BNB_STAGES * 2 * BNB_TILE_BYTES + 2 * BNB_TILE_BYTES)
+#define BNB_TILE_BYTES 8192                  // one tile of y: 32 rows of 128 channels or 16 rows of 256, bf16
+template <typename TD, int C> struct BnbCfg {
+  static constexpr int ROWS = BNB_TILE_BYTES / (C * 2);
+  static constexpr int D_BYTES = ROWS * C * (int)sizeof(TD);
+  static constexpr int STAGE = BNB_TILE_BYTES + D_BYTES;
+  static constexpr int SMEM_STATS = BNB_STAGES * STAGE;
+  static constexpr int SMEM_APPLY = BNB_STAGES * STAGE + 2 * BNB_TILE_BYTES;
+};
 
 __device__ __forceinline__ void bnb_unpack(const uint4 u, float (&v)[8]) {
   const unsigned w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
 }
+template <typename TD> __device__ __forceinline__ void bnb_load_d(const unsigned char* tile, int i8, float (&d)[8]);
+template <> __device__ __forceinline__ void bnb_load_d<__nv_bfloat16>(const unsigned char* tile, int i8, float (&d)[8]) {
+  bnb_unpack(reinterpret_cast<const uint4*>(tile)[i8], d);
+}
+template <> __device__ __forceinline__ void bnb_load_d<float>(const unsigned char* tile, int i8, float (&d)[8]) {
+  const float4 a = reinterpret_cast<const float4*>(tile)[2 * i8], b = reinterpret_cast<const float4*>(tile)[2 * i8 + 1];
+  d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+}
 
-template <bool APPLY>
-__global__ void __launch_bounds__(256, 3) bn8_relu_bwd_bulk_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ gamma,
-                                                                   const float* __restrict__ beta, const __nv_bfloat16* __restrict__ dout,
+// y bf16, dout TD (bf16: deblock rows gathered from d(map); fp32: sparse-conv outputs feeding the fp32 residual stream), dy bf16
+template <bool APPLY, typename TD, int C>
+__global__ void __launch_bounds__(256, 2) bn8_relu_bwd_bulk_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ gamma,
+                                                                   const float* __restrict__ beta, const TD* __restrict__ dout,
                                                                    const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                    const float* __restrict__ dbeta, const float* __restrict__ dgamma,
                                                                    float inv_count, long long ntile, int relu, float* __restrict__ partial,
                                                                    __nv_bfloat16* __restrict__ dy) {
+  using Cfg = BnbCfg<TD, C>;
   extern __shared__ __align__(128) unsigned char bnb_smem[];
   __shared__ unsigned long long full[BNB_STAGES];
-  constexpr int C8 = BNB_C / 8;
-  const int tid = threadIdx.x, c = tid % C8, rsub = tid / C8;       // 16 rows per pass, 2 passes per tile
+  constexpr int C8 = C / 8, RPP = 256 / C8;                          // rows per pass
+  const int tid = threadIdx.x, c = tid % C8, rsub = tid / C8;
   const long long my_tiles = ntile > blockIdx.x ? (ntile - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   if (tid == 0) {
     for (int st = 0; st < BNB_STAGES; ++st) bp::mbar_init(&full[st], 1);
@@ -649,11 +662,11 @@ __global__ void __launch_bounds__(256, 3) bn8_relu_bwd_bulk_kernel(const __nv_bf
   __syncthreads();
   auto issue = [&](long long it) {
     const int st = (int)(it % BNB_STAGES);
-    const long long row0 = (blockIdx.x + it * gridDim.x) * BNB_ROWS;
-    unsigned char* base = bnb_smem + st * 2 * BNB_TILE_BYTES;
-    bp::mbar_expect_tx(&full[st], 2 * BNB_TILE_BYTES);
-    bp::g2s(base, y + row0 * BNB_C, BNB_TILE_BYTES, &full[st]);
-    bp::g2s(base + BNB_TILE_BYTES, dout + row0 * BNB_C, BNB_TILE_BYTES, &full[st]);
+    const long long row0 = (blockIdx.x + it * gridDim.x) * Cfg::ROWS;
+    unsigned char* base = bnb_smem + st * Cfg::STAGE;
+    bp::mbar_expect_tx(&full[st], BNB_TILE_BYTES + Cfg::D_BYTES);
+    bp::g2s(base, y + row0 * C, BNB_TILE_BYTES, &full[st]);
+    bp::g2s(base + BNB_TILE_BYTES, dout + row0 * C, Cfg::D_BYTES, &full[st]);
   };
   if (tid == 0)
     for (long long it = 0; it < BNB_STAGES && it < my_tiles; ++it) issue(it);
@@ -665,19 +678,19 @@ __global__ void __launch_bounds__(256, 3) bn8_relu_bwd_bulk_kernel(const __nv_bf
     dg[i] = APPLY ? __ldg(dgamma + 8 * c + i) : 0.f;
   }
   float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, q[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  unsigned char* obuf = bnb_smem + BNB_STAGES * 2 * BNB_TILE_BYTES;       // APPLY: two output tiles
+  unsigned char* obuf = bnb_smem + BNB_STAGES * Cfg::STAGE;           // APPLY: two output tiles
   for (long long it = 0; it < my_tiles; ++it) {
     const int st = (int)(it % BNB_STAGES);
     bp::mbar_wait(&full[st], (unsigned)((it / BNB_STAGES) & 1));
-    const uint4* ys = reinterpret_cast<const uint4*>(bnb_smem + st * 2 * BNB_TILE_BYTES);
-    const uint4* ds = ys + BNB_TILE_BYTES / 16;
+    const unsigned char* base = bnb_smem + st * Cfg::STAGE;
+    const uint4* ys = reinterpret_cast<const uint4*>(base);
     uint4* os = reinterpret_cast<uint4*>(obuf + (it & 1) * BNB_TILE_BYTES);
 #pragma unroll
-    for (int ps = 0; ps < BNB_ROWS / 16; ++ps) {
-      const int row = ps * 16 + rsub;
+    for (int ps = 0; ps < Cfg::ROWS / RPP; ++ps) {
+      const int row = ps * RPP + rsub;
       float v[8], d[8];
       bnb_unpack(ys[row * C8 + c], v);
-      bnb_unpack(ds[row * C8 + c], d);
+      bnb_load_d<TD>(base + BNB_TILE_BYTES, row * C8 + c, d);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const float xh = (v[k] - m[k]) * r[k];
@@ -696,8 +709,8 @@ __global__ void __launch_bounds__(256, 3) bn8_relu_bwd_bulk_kernel(const __nv_bf
     __syncthreads();                           // stage consumed / output tile complete
     if (tid == 0) {
       if (APPLY) {
-        const long long row0 = (blockIdx.x + it * gridDim.x) * BNB_ROWS;
-        bp::s2g(dy + row0 * BNB_C, os, BNB_TILE_BYTES);
+        const long long row0 = (blockIdx.x + it * gridDim.x) * Cfg::ROWS;
+        bp::s2g(dy + row0 * C, os, BNB_TILE_BYTES);
         bp::s2g_commit();
       }
       if (it + BNB_STAGES < my_tiles) {
@@ -713,6 +726,34 @@ __global__ void __launch_bounds__(256, 3) bn8_relu_bwd_bulk_kernel(const __nv_bf
   } else {
     tail_block_reduce(s, q, C8, partial);      // [dbeta(C) | dgamma(C)] per CTA
   }
+}
+
+// launches the bulk form over the whole tiles and returns the rows it covered (0: not applicable, the caller runs the generic form)
+template <bool APPLY, typename TD, int C>
+static long long bnb_launch(const void* y, const float* gamma, const float* beta, const void* dout, const float* mean, const float* rstd,
+                            const float* dbeta, const float* dgamma, float inv, long long N, int relu, float* partial, void* dy, int* nblocks,
+                            cudaStream_t st) {
+  using Cfg = BnbCfg<TD, C>;
+  const long long nt = N / Cfg::ROWS;
+  if (nt == 0) return 0;
+  constexpr int SMEM = APPLY ? Cfg::SMEM_APPLY : Cfg::SMEM_STATS;
+  static int attr = cudaFuncSetAttribute(bn8_relu_bwd_bulk_kernel<APPLY, TD, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+  (void)attr;
+  const int gb = (int)min((long long)GDMAE_NUM_SMS * 2, nt);
+  bn8_relu_bwd_bulk_kernel<APPLY, TD, C><<<gb, 256, SMEM, st>>>((const __nv_bfloat16*)y, gamma, beta, (const TD*)dout, mean, rstd, dbeta, dgamma, inv,
+                                                                nt, relu, partial, (__nv_bfloat16*)dy);
+  if (nblocks) *nblocks = gb;
+  return nt * Cfg::ROWS;
+}
+template <bool APPLY>
+static long long bnb_dispatch(int dout_dtype, int C, const void* y, const float* gamma, const float* beta, const void* dout, const float* mean,
+                              const float* rstd, const float* dbeta, const float* dgamma, float inv, long long N, int relu, float* partial,
+                              void* dy, int* nblocks, cudaStream_t st) {
+  if (C == 128 && dout_dtype == 1) return bnb_launch<APPLY, __nv_bfloat16, 128>(y, gamma, beta, dout, mean, rstd, dbeta, dgamma, inv, N, relu, partial, dy, nblocks, st);
+  if (C == 128 && dout_dtype == 0) return bnb_launch<APPLY, float, 128>(y, gamma, beta, dout, mean, rstd, dbeta, dgamma, inv, N, relu, partial, dy, nblocks, st);
+  if (C == 256 && dout_dtype == 1) return bnb_launch<APPLY, __nv_bfloat16, 256>(y, gamma, beta, dout, mean, rstd, dbeta, dgamma, inv, N, relu, partial, dy, nblocks, st);
+  if (C == 256 && dout_dtype == 0) return bnb_launch<APPLY, float, 256>(y, gamma, beta, dout, mean, rstd, dbeta, dgamma, inv, N, relu, partial, dy, nblocks, st);
+  return 0;
 }
 
 #define BN8_DISPATCH2(A, B, CALL)                                                  \
@@ -766,25 +807,22 @@ extern "C" int gdmae_batchnorm_relu_bwd_t(const void* y, int y_dtype, const floa
   const int C8 = C / 8, rper = 256 / C8;
   int grid = (int)min((long long)BN_PART_BLOCKS, (long long)((N + rper - 1) / rper));
   static const bool bulk_on = [] { const char* e = getenv("GDMAE_BN_BULK"); return !(e && e[0] == '0'); }();      // =0: generic kernels (A/B)
-  const long long nt = N / BNB_ROWS, tail = N - nt * BNB_ROWS;
-  const bool bulk = bulk_on && C == BNB_C && y_dtype == 1 && dout_dtype == 1 && dy_dtype == 1 && nt > 0 &&
-                    (((uintptr_t)y | (uintptr_t)dout | (uintptr_t)dy) & 15) == 0;
+  const bool bulk = bulk_on && y_dtype == 1 && dy_dtype == 1 && (((uintptr_t)y | (uintptr_t)dout | (uintptr_t)dy) & 15) == 0;
+  long long done = 0;                    // rows the bulk form covered (whole tiles); the generic kernels take the rest
   if (N == 0) {
     GDMAE_CHECK_CUDA(cudaMemsetAsync(partial, 0, (size_t)2 * C * 4, st));
     grid = 1;
   } else {
-    if (bulk) {
-      // whole 32-row tiles through the bulk-copy ring, the last N % 32 rows by one CTA of the generic kernel (one more partial row)
-      static int attr_s = cudaFuncSetAttribute(bn8_relu_bwd_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BNB_SMEM_STATS);
-      (void)attr_s;
-      const int gb = (int)min((long long)GDMAE_NUM_SMS * 2, nt);      // 64 KB ring + 16 KB reduction buffer: two CTAs per SM
-      bn8_relu_bwd_bulk_kernel<false><<<gb, 256, BNB_SMEM_STATS, st>>>((const __nv_bfloat16*)y, gamma, beta, (const __nv_bfloat16*)dout, mean, rstd,
-                                                                       nullptr, nullptr, 0.f, nt, relu, partial, nullptr);
-      GDMAE_LAUNCH_CHECK();
+    int gb = 0;
+    if (bulk) done = bnb_dispatch<false>(dout_dtype, C, y, gamma, beta, dout, mean, rstd, nullptr, nullptr, 0.f, N, relu, partial, nullptr, &gb, st);
+    GDMAE_LAUNCH_CHECK();
+    if (done > 0) {
       grid = gb;
-      if (tail > 0) {
-        bn8_relu_bwd_stats_kernel<__nv_bfloat16, __nv_bfloat16><<<1, 256, 0, st>>>((const __nv_bfloat16*)y + nt * BNB_ROWS * C, gamma, beta,
-            (const __nv_bfloat16*)dout + nt * BNB_ROWS * C, mean, rstd, tail, C8, relu, partial + (long long)gb * 2 * C);
+      if (N > done) {                    // one CTA of the generic kernel on the last rows, one more partial row
+        const size_t yo = (size_t)done * C * 2, dd = (size_t)done * C * (dout_dtype ? 2 : 4);
+        BN8_DISPATCH2(1, dout_dtype,
+                      (bn8_relu_bwd_stats_kernel<T0, T1><<<1, 256, 0, st>>>((const T0*)((const char*)y + yo), gamma, beta, (const T1*)((const char*)dout + dd),
+                                                                            mean, rstd, N - done, C8, relu, partial + (long long)gb * 2 * C)));
         grid = gb + 1;
       }
     } else {
@@ -799,17 +837,17 @@ extern "C" int gdmae_batchnorm_relu_bwd_t(const void* y, int y_dtype, const floa
   const long long n8 = N * C8;
   const int g2 = gdmae_grid(n8, 256, 16);
   const float inv = (float)(1.0 / count);
-  if (bulk) {
-    static int attr_a = cudaFuncSetAttribute(bn8_relu_bwd_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BNB_SMEM_APPLY);
-    (void)attr_a;
-    const int gb = (int)min((long long)GDMAE_NUM_SMS * 2, nt);
-    bn8_relu_bwd_bulk_kernel<true><<<gb, 256, BNB_SMEM_APPLY, st>>>((const __nv_bfloat16*)y, gamma, beta, (const __nv_bfloat16*)dout, mean, rstd,
-                                                                    dbeta, dgamma, inv, nt, relu, nullptr, (__nv_bfloat16*)dy);
+  if (done > 0) {
+    bnb_dispatch<true>(dout_dtype, C, y, gamma, beta, dout, mean, rstd, dbeta, dgamma, inv, N, relu, nullptr, dy, nullptr, st);
     GDMAE_LAUNCH_CHECK();
-    if (tail > 0)
-      bn8_relu_bwd_apply_kernel<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16><<<gdmae_grid(tail * C8, 256, 16), 256, 0, st>>>(
-          (const __nv_bfloat16*)y + nt * BNB_ROWS * C, beta, (const __nv_bfloat16*)dout + nt * BNB_ROWS * C, mean, rstd, gamma, dbeta, dgamma, inv,
-          tail * C8, C8, relu, (__nv_bfloat16*)dy + nt * BNB_ROWS * C);
+    if (N > done) {
+      const size_t yo = (size_t)done * C * 2, dd = (size_t)done * C * (dout_dtype ? 2 : 4);
+      const long long t8 = (N - done) * C8;
+      BN8_DISPATCH2(1, dout_dtype,
+                    (bn8_relu_bwd_apply_kernel<T0, T1, __nv_bfloat16><<<gdmae_grid(t8, 256, 16), 256, 0, st>>>(
+                        (const T0*)((const char*)y + yo), beta, (const T1*)((const char*)dout + dd), mean, rstd, gamma, dbeta, dgamma, inv, t8, C8, relu,
+                        (__nv_bfloat16*)((char*)dy + yo))));
+    }
   } else if (dy_dtype == 0)
     BN8_DISPATCH2(y_dtype, dout_dtype,
                   (bn8_relu_bwd_apply_kernel<T0, T1, float><<<g2, 256, 0, st>>>((const T0*)y, beta, (const T1*)dout, mean, rstd, gamma, dbeta, dgamma,
