@@ -728,6 +728,86 @@ __global__ void __launch_bounds__(256, 2) bn8_relu_bwd_bulk_kernel(const __nv_bf
   }
 }
 
+// forward apply on the same ring: y bf16 in, out TO (fp32: sparse-conv outputs, bf16: deblock rows) composed in shared memory
+template <typename TO, int C>
+__global__ void __launch_bounds__(256, 3) bn8_relu_apply_bulk_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
+                                                                     const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                                     const float* __restrict__ beta, long long ntile, int relu,
+                                                                     TO* __restrict__ out) {
+  constexpr int ROWS = BNB_TILE_BYTES / (C * 2), O_BYTES = ROWS * C * (int)sizeof(TO);
+  extern __shared__ __align__(128) unsigned char bnb_smem[];        // BNB_STAGES y tiles | two output tiles
+  __shared__ unsigned long long full[BNB_STAGES];
+  constexpr int C8 = C / 8, RPP = 256 / C8;
+  const int tid = threadIdx.x, c = tid % C8, rsub = tid / C8;
+  const long long my_tiles = ntile > blockIdx.x ? (ntile - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  if (tid == 0) {
+    for (int st = 0; st < BNB_STAGES; ++st) bp::mbar_init(&full[st], 1);
+    bp::fence_barrier_init();
+  }
+  __syncthreads();
+  auto issue = [&](long long it) {
+    const int st = (int)(it % BNB_STAGES);
+    const long long row0 = (blockIdx.x + it * gridDim.x) * ROWS;
+    bp::mbar_expect_tx(&full[st], BNB_TILE_BYTES);
+    bp::g2s(bnb_smem + st * BNB_TILE_BYTES, y + row0 * C, BNB_TILE_BYTES, &full[st]);
+  };
+  if (tid == 0)
+    for (long long it = 0; it < BNB_STAGES && it < my_tiles; ++it) issue(it);
+  float m[8], r[8], g[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { m[i] = __ldg(mean + 8 * c + i); r[i] = __ldg(rstd + 8 * c + i); g[i] = __ldg(gamma + 8 * c + i); b[i] = __ldg(beta + 8 * c + i); }
+  unsigned char* obuf = bnb_smem + BNB_STAGES * BNB_TILE_BYTES;
+  for (long long it = 0; it < my_tiles; ++it) {
+    const int st = (int)(it % BNB_STAGES);
+    bp::mbar_wait(&full[st], (unsigned)((it / BNB_STAGES) & 1));
+    const uint4* ys = reinterpret_cast<const uint4*>(bnb_smem + st * BNB_TILE_BYTES);
+    unsigned char* os = obuf + (it & 1) * O_BYTES;
+#pragma unroll
+    for (int ps = 0; ps < ROWS / RPP; ++ps) {
+      const int row = ps * RPP + rsub;
+      float v[8];
+      bnb_unpack(ys[row * C8 + c], v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        v[k] = (v[k] - m[k]) * r[k] * g[k] + b[k];
+        if (relu) v[k] = fmaxf(v[k], 0.f);
+      }
+      if (sizeof(TO) == 2) {
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
+        reinterpret_cast<uint4*>(os)[row * C8 + c] = make_uint4(*reinterpret_cast<unsigned*>(&p0), *reinterpret_cast<unsigned*>(&p1),
+                                                                *reinterpret_cast<unsigned*>(&p2), *reinterpret_cast<unsigned*>(&p3));
+      } else {
+        reinterpret_cast<float4*>(os)[2 * (row * C8 + c)] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4*>(os)[2 * (row * C8 + c) + 1] = make_float4(v[4], v[5], v[6], v[7]);
+      }
+    }
+    bp::fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      const long long row0 = (blockIdx.x + it * gridDim.x) * ROWS;
+      bp::s2g(out + row0 * C, os, O_BYTES);
+      bp::s2g_commit();
+      if (it + BNB_STAGES < my_tiles) issue(it + BNB_STAGES);
+      bp::s2g_wait_read<1>();
+    }
+    __syncthreads();
+  }
+  if (tid == 0) bp::s2g_wait_all<0>();
+}
+template <typename TO, int C>
+static long long bnb_apply_launch(const void* y, const float* mean, const float* rstd, const float* gamma, const float* beta, long long N, int relu,
+                                  void* out, cudaStream_t st) {
+  constexpr int ROWS = BNB_TILE_BYTES / (C * 2), SMEM = BNB_STAGES * BNB_TILE_BYTES + 2 * ROWS * C * (int)sizeof(TO);
+  const long long nt = N / ROWS;
+  if (nt == 0) return 0;
+  static int attr = cudaFuncSetAttribute(bn8_relu_apply_bulk_kernel<TO, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+  (void)attr;
+  const int gb = (int)min((long long)GDMAE_NUM_SMS * 3, nt);
+  bn8_relu_apply_bulk_kernel<TO, C><<<gb, 256, SMEM, st>>>((const __nv_bfloat16*)y, mean, rstd, gamma, beta, nt, relu, (TO*)out);
+  return nt * ROWS;
+}
+
 // launches the bulk form over the whole tiles and returns the rows it covered (0: not applicable, the caller runs the generic form)
 template <bool APPLY, typename TD, int C>
 static long long bnb_launch(const void* y, const float* gamma, const float* beta, const void* dout, const float* mean, const float* rstd,
@@ -786,11 +866,24 @@ extern "C" int gdmae_batchnorm_relu_fwd_t(const void* y, int y_dtype, const floa
   bn_finalize_kernel<<<gdmae_div_up(C * 32, 256), 256, 0, st>>>(partial, grid, C, count, eps, momentum, mean, rstd, running_mean, running_var);
   GDMAE_LAUNCH_CHECK();
   if (N == 0) return GDMAE_OK;
-  const long long n8 = N * C8;
-  const int g2 = gdmae_grid(n8, 256, 16);
-  BN8_DISPATCH2(y_dtype, out_dtype,
-                (bn8_relu_apply_kernel<T0, T1><<<g2, 256, 0, st>>>((const T0*)y, mean, rstd, gamma, beta, n8, C8, relu, (T1*)out)));
-  GDMAE_LAUNCH_CHECK();
+  static const bool bulk_on = [] { const char* e = getenv("GDMAE_BN_BULK"); return !(e && e[0] == '0'); }();      // =0: generic kernel (A/B)
+  long long done = 0;
+  if (bulk_on && y_dtype == 1 && (((uintptr_t)y | (uintptr_t)out) & 15) == 0) {
+    if (C == 128 && out_dtype == 1) done = bnb_apply_launch<__nv_bfloat16, 128>(y, mean, rstd, gamma, beta, N, relu, out, st);
+    else if (C == 128) done = bnb_apply_launch<float, 128>(y, mean, rstd, gamma, beta, N, relu, out, st);
+    else if (C == 256 && out_dtype == 1) done = bnb_apply_launch<__nv_bfloat16, 256>(y, mean, rstd, gamma, beta, N, relu, out, st);
+    else if (C == 256) done = bnb_apply_launch<float, 256>(y, mean, rstd, gamma, beta, N, relu, out, st);
+    GDMAE_LAUNCH_CHECK();
+  }
+  if (N > done) {
+    const long long n8 = (N - done) * C8;
+    const int g2 = gdmae_grid(n8, 256, 16);
+    const size_t yo = (size_t)done * C * (y_dtype ? 2 : 4), oo = (size_t)done * C * (out_dtype ? 2 : 4);
+    BN8_DISPATCH2(y_dtype, out_dtype,
+                  (bn8_relu_apply_kernel<T0, T1><<<g2, 256, 0, st>>>((const T0*)((const char*)y + yo), mean, rstd, gamma, beta, n8, C8, relu,
+                                                                     (T1*)((char*)out + oo))));
+    GDMAE_LAUNCH_CHECK();
+  }
   return GDMAE_OK;
 }
 
