@@ -339,6 +339,32 @@ def test_mask_from_noise_inside_model_and_trainer_steps(G):
             assert torch.equal(sd[k].cpu(), P0[k]), k
 
 
+def test_deferred_gradient_handover_fills_the_bucket(G, monkeypatch):
+    """MAETrainer's deferred hand-over (AccumulateGrad keeps the produced tensors, one multi-tensor copy moves them into the
+    flat bucket) must leave the same gradient bucket as `.grad = bucket view` + one `grad += g` per parameter."""
+    from gd_mae_b200.trainer import MAETrainer
+    r = np.random.RandomState(4)
+    n = 2200
+    pts = np.concatenate([r.randint(0, 2, (n, 1)), r.normal(0, 3, (n, 2)), r.uniform(-2, 4, (n, 1)), r.uniform(0, 1, (n, 2))], 1)
+    pts = torch.from_numpy(pts[np.argsort(pts[:, 0], kind="stable")].astype(np.float32)).cuda()
+    buckets = []
+    for defer in ("1", "0"):
+        monkeypatch.setenv("GDMAE_DEFER_GRADS", defer)
+        model, cfg, ocfg, P, Bf = build(G, "tiny", 0.85, 5)
+        _, _, _, ovc, _ = O.voxelize(pts.cpu(), ocfg)
+        noise = torch.rand(ovc.shape[0], generator=torch.Generator().manual_seed(1)).cuda()
+        tr = MAETrainer(model, cfg.OPTIMIZATION, total_steps=20)
+        assert (len(tr._deferred) > 0) == (defer == "1")
+        tr.step(dict(points=pts.clone(), batch_size=2, voxel_mae_noise=noise))
+        for p_, view in tr._deferred:
+            assert p_.grad is not None and p_.grad.data_ptr() == view.data_ptr()      # .grad is the bucket view again
+        buckets.append((tr.flat_grads.clone(), [(o, k) for o, k in tr.slices.values()]))
+    (g1, sl), (g0, _) = buckets
+    assert rel(g1, g0) < 1e-4, rel(g1, g0)                       # float atomics order only
+    for off, k in sl:                                            # every tensor of the bucket received its gradient in both runs
+        assert bool((g1[off:off + k] != 0).any()) == bool((g0[off:off + k] != 0).any())
+
+
 def test_fused_adam_onecycle_kernel_matches_oracle(G):
     """The clip + decoupled-wd + Adam kernel in isolation: identical synthetic gradients on both sides."""
     from gd_mae_b200.trainer import MAETrainer
