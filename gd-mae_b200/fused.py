@@ -155,6 +155,11 @@ def gather_add_rows(x, table, idx_u8):
 
 # bf16 copy of the previous layer's output (written by its LayerNorm kernel) handed to the next layer
 _LAST_OUT = (None, None)
+# Parameter gradients of the two C executors (EncoderLayer, VFE) go straight into `.grad` - as a side effect, with None returned
+# to autograd - only while this flag is set: MAETrainer sets it around its backward (its `.grad` tensors are views of the flat
+# bucket).  Anything else (torch.autograd.grad, hooks, a DDP wrapper, parameters that merely happen to have a .grad) gets the
+# gradients returned the normal way.
+INPLACE_PARAM_GRADS = False
 
 # bf16 shadows of parameters, keyed by the parameter's data pointer: the trainer keeps one bf16 mirror of its
 # flat parameter bucket (refreshed once per step) so no per-layer weight casts are launched.
@@ -299,8 +304,12 @@ class EncoderLayerFunction(torch.autograd.Function):
         N, d, dff = A.N, A.d, A.dff
         dx = torch.empty((N, d), dtype=F32, device=dev)
         A.dy, A.dx = dx2.data_ptr(), dx.data_ptr()
-        # parameter gradients: straight into .grad when the caller pre-allocated them (the trainer's flat bucket)
-        inplace = all(p.grad is not None and p.grad.dtype == F32 and p.grad.is_contiguous() for p in params)
+        if getattr(ctx, "_consumed", False):
+            raise RuntimeError("EncoderLayerFunction.backward called twice: the activation buffers were released after the first call "
+                               "(retain_graph is not supported by the fused node)")
+        ctx._consumed = True
+        # parameter gradients: straight into .grad when the trainer asked for it (its flat bucket)
+        inplace = INPLACE_PARAM_GRADS and all(p.grad is not None and p.grad.dtype == F32 and p.grad.is_contiguous() for p in params)
         if inplace:
             grads = [p.grad for p in params]
             A.accumulate = 1
@@ -393,7 +402,10 @@ class VfeMlpFunction(torch.autograd.Function):
         opdt = BF16 if A.gemm_mode == 1 else F32
         dy2 = torch.empty((A.Np, 128), dtype=opdt, device=dev)
         dh1 = torch.empty((A.Np, 64), dtype=opdt, device=dev)
-        inplace = all(p.grad is not None and p.grad.dtype == F32 and p.grad.is_contiguous() for p in params)
+        if getattr(ctx, "_consumed", False):
+            raise RuntimeError("VfeMlpFunction.backward called twice: the activation buffers were released after the first call")
+        ctx._consumed = True
+        inplace = INPLACE_PARAM_GRADS and all(p.grad is not None and p.grad.dtype == F32 and p.grad.is_contiguous() for p in params)
         grads = [p.grad for p in params] if inplace else [torch.empty_like(p) for p in params]
         A.accumulate = int(inplace)
         A.dout, A.dy2, A.dh1 = dout.data_ptr(), dy2.data_ptr(), dh1.data_ptr()

@@ -415,7 +415,12 @@ class MAETrainer:
                 hook = pf.register_hook(self._reduce_early)
         for p_, _ in self._deferred:
             p_.grad = None
-        loss.backward()
+        from . import fused as _fused
+        prev_inplace, _fused.INPLACE_PARAM_GRADS = _fused.INPLACE_PARAM_GRADS, True      # the executors write into the bucket
+        try:
+            loss.backward()
+        finally:
+            _fused.INPLACE_PARAM_GRADS = prev_inplace
         if hook is not None:
             hook.remove()
         self._flush_deferred()

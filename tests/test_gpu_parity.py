@@ -487,7 +487,11 @@ def test_bf16_configuration_close_to_reference(G, golden):
         bd = dict(points=torch.from_numpy(K["points_in"]).cuda(), batch_size=int(K["batch_size"]),
                   voxel_mae_mask=torch.from_numpy(K["voxel_mae_mask"]).cuda())
         ret, _, _ = model(bd)
-        ret["loss"].backward()
+        fused.INPLACE_PARAM_GRADS = True            # what MAETrainer.step sets around its backward
+        try:
+            ret["loss"].backward()
+        finally:
+            fused.INPLACE_PARAM_GRADS = False
         grads = {k: p.grad for k, p in model.named_parameters()}
         for k, gn in zip([str(s) for s in K["grad_keys"]], K["grad_norms"]):
             mine = float(grads[k].norm())
